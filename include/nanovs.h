@@ -1,0 +1,162 @@
+/* nanovs.h -- C ABI of libnanovs.so: sm_100a kernels for the KP2DTiny perception hot path.
+ *
+ * The reference (ETH-PBL/Nano-VS-SLAM) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it exposes for this path is the nn.Module surface of KP2DTinyV2/V3
+ * (src/kp2dtiny/models/kp2dtiny.py:284,650) plus two third-party call sites
+ * (faiss.IndexFlatL2, src/evaluation/global_descriptor.py:55-60; cv2.BFMatcher,
+ * src/visual_odometry/feature_matcher.py:248).  Each entry point below names the reference
+ * statement(s) it replaces.  The Python package nano_vs_slam_b200 binds these with ctypes and
+ * re-creates that module surface on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 NCHW-contiguous data unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises
+ *     and nothing allocates: outputs and workspaces are supplied by the caller;
+ *   - return value: NVS_OK (0) or a negative NVS_ERR_* code; nvs_last_error() gives the text;
+ *   - functions are re-entrant across streams (no hidden global state except the error text).
+ */
+#ifndef NANOVS_H_
+#define NANOVS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVS_ABI_VERSION 1
+
+#define NVS_OK 0
+#define NVS_ERR_ARG (-1)         /* bad shape / null pointer / unsupported size */
+#define NVS_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define NVS_ERR_UNSUPPORTED (-3) /* configuration outside what the kernels implement */
+#define NVS_ERR_NO_DEVICE (-4)   /* no sm_100 device visible */
+
+/* activation codes for the conv epilogue */
+#define NVS_ACT_NONE 0
+#define NVS_ACT_LRELU 1        /* LeakyReLU(0.01)            modules/base.py:33 */
+#define NVS_ACT_RELU 2         /* ReLU                       modules/base.py:35 */
+#define NVS_ACT_SIGMOID 3      /* score                      kp2dtiny.py:574 */
+#define NVS_ACT_TANH 4         /* centre shift               kp2dtiny.py:575 */
+#define NVS_ACT_SIGMOID_TANH 5 /* V3 fused head: ch0 sigmoid, rest tanh   kp2dtiny.py:927-935 */
+#define NVS_ACT_GELU 6         /* exact erf GELU             modules/segformer.py:184 */
+
+/* where the conv epilogue writes */
+#define NVS_OUT_PLAIN 0     /* dst[b, dst_c_off + co, y, x] */
+#define NVS_OUT_POOL 1      /* only MaxPool2d(2,2) of the result -> dst2   encoders.py:111 */
+#define NVS_OUT_BOTH 2      /* full result -> dst and pooled -> dst2       encoders.py:121-123 */
+#define NVS_OUT_SHUFFLE 3   /* PixelShuffle(2): dst[b, dst_c_off + co/4, 2y + (co%4)/2, 2x + co%2]  heads.py:98 */
+
+/* how the conv reads its input */
+#define NVS_IN_PLAIN 0
+#define NVS_IN_S2D 1        /* 2x2 stride-2 conv expressed as 1x1 over space-to-depth(2): segformer.py:93-95 */
+
+const char* nvs_last_error(void);
+int nvs_abi_version(void);
+/* 0 when an sm_100 device is current and the kernels can launch, else NVS_ERR_NO_DEVICE. */
+int nvs_device_ok(void);
+
+/* ---- conv3x3 / conv1x1 + folded BN + activation (+ pool / pixel-shuffle / concat-read) -----------
+ * Replaces AnnotatedConvBnReLUModel.forward (modules/base.py:39-46), the biased plain convs
+ * (heads.py:33,96,102; segmentation.py:154,339-342), MaxPool2d (encoders.py:111,123;
+ * segmentation.py:132,448), PixelShuffle + torch.cat (heads.py:98-99; segmentation.py:139-149) and
+ * the 1x1 / 2x2-s2 projections of the attention block (segformer.py:105-106,136,193-198).
+ * The input is the channel-concatenation of slice [c0_off, c0_off+c0) of src0 and (optionally)
+ * slice [c1_off, c1_off+c1) of src1, both (B, c*_total, H, W).
+ * weight: packed [cin_pad][ksize*ksize][cout_pad] with BN scale folded in; bias: [cout_pad].
+ * cin_pad = round_up(c0+c1, chunk), cout_pad = round_up(cout, nvs_conv_cout_tile(cout)). */
+typedef struct NvsConvArgs {
+  const float* src0;
+  const float* src1; /* may be NULL */
+  const float* weight;
+  const float* bias;
+  float* dst;  /* may be NULL for NVS_OUT_POOL */
+  float* dst2; /* pooled output for NVS_OUT_POOL / NVS_OUT_BOTH */
+  int32_t c0_total, c0_off, c0;
+  int32_t c1_total, c1_off, c1;
+  int32_t dst_c_total, dst_c_off;
+  int32_t dst2_c_total, dst2_c_off;
+  int32_t B, H, W; /* OUTPUT plane of the conv (before pool/shuffle); for NVS_IN_S2D the input is (2H+r, 2W+r) */
+  int32_t in_H, in_W; /* input plane size (== H, W unless NVS_IN_S2D) */
+  int32_t cout;
+  int32_t ksize;   /* 3 (pad 1) or 1 */
+  int32_t act;     /* NVS_ACT_* */
+  int32_t out_mode;/* NVS_OUT_* */
+  int32_t in_mode; /* NVS_IN_* */
+} NvsConvArgs;
+
+int nvs_conv_cout_tile(int32_t cout);   /* output-channel tile the kernel uses for `cout` */
+int nvs_conv_cin_chunk(int32_t cin);    /* input-channel chunk (4 or 8) the kernel uses for `cin` */
+int nvs_conv(const NvsConvArgs* args, void* stream);
+
+/* depthwise 3x3 + bias (DsConv2d first half, modules/segformer.py:46-54). w: (C,3,3), bias: (C). */
+int nvs_dwconv3x3(const float* src, const float* w, const float* bias, float* dst,
+                  int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+
+/* channel LayerNorm (x-mean)/(std+eps)*g+b, biased variance (modules/segformer.py:70-73). */
+int nvs_channel_layernorm(const float* src, const float* g, const float* b, float* dst,
+                          int32_t B, int32_t C, int32_t HW, float eps, void* stream);
+
+/* softmax over channels, Softmax2d (kp2dtiny.py:942-943). */
+int nvs_softmax_channels(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, void* stream);
+
+/* efficient self-attention core (modules/segformer.py:113-133): q (B,C,Nq), kv (B,2C,Nk) with
+ * k = kv[:, :C], v = kv[:, C:], heads split the channel axis; out (B,C,Nq) =
+ * softmax(q k^T * (C/heads)^-1/2) v per head, streaming softmax (sim is never materialised). */
+int nvs_attention(const float* q, const float* kv, float* out, int32_t B, int32_t C, int32_t heads,
+                  int32_t Nq, int32_t Nk, void* stream);
+
+/* NetVLAD (modules/aggregators/netvlad.py:79-106 and the loop form :158-193):
+ * x (B,C,S) -> vlad (B, K*C).  w_assign (K,C) = conv.weight, centroids (K,C).
+ * workspace: nvs_netvlad_workspace_bytes(B,C,K,S) bytes. */
+size_t nvs_netvlad_workspace_bytes(int32_t B, int32_t C, int32_t K, int32_t S);
+int nvs_netvlad(const float* x, const float* w_assign, const float* centroids, float* vlad,
+                void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t K, int32_t S,
+                void* stream);
+/* L2 normalisation over channels (VPRHead only_encoder path, decoders/vpr.py:85-86). */
+int nvs_l2norm_channels(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, void* stream);
+
+/* keypoint decode = KP2DTinyV*.post_processing with training False (kp2dtiny.py:593-647, 959-1015):
+ * border mask, cell coordinates, bilinear descriptor sampling (align_corners=True, zero pad) + L2 norm.
+ * score (B,1,Hc,Wc), shift (B,2,Hc,Wc) raw tanh, feat (B,D,Hf,Wf)  ->
+ * out_score (B,1,Hc,Wc), out_coord (B,2,Hc,Wc) pixels, out_feat (B,D,Hc,Wc) unit norm. */
+int nvs_decode(const float* score, const float* shift, const float* feat, float* out_score,
+               float* out_coord, float* out_feat, int32_t B, int32_t Hc, int32_t Wc, int32_t D,
+               int32_t Hf, int32_t Wf, int32_t H, int32_t W, int32_t cell, float cross_ratio,
+               void* stream);
+
+/* seg argmax over classes -> int64 (kp2dtiny.py:639, 1007).  If coord != NULL the class map is first
+ * nearest-sampled at the keypoint coordinates (sample_segmentation, kp2dtiny.py:634-637) and the
+ * output is (B,1,Hc,Wc); otherwise (B,1,Hs,Ws). */
+int nvs_seg_argmax(const float* seg, const float* coord, int64_t* out, int32_t B, int32_t C,
+                   int32_t Hs, int32_t Ws, int32_t Hc, int32_t Wc, int32_t H, int32_t W, void* stream);
+
+/* keypoint selection = frontend.py:94-126 per frame: score > thresh (strict), optional class filter,
+ * top-k by score (ties -> lowest cell index); outputs compacted in ascending cell order.
+ * seg_cells: (B, n_cells) int64 per-cell labels or NULL; filter_classes: device int32[n_filter] or NULL.
+ * out_pts (B,k,2) xy, out_desc (B,k,D), out_score (B,k), out_cell (B,k) int32, out_label (B,k) int64
+ * (only if seg_cells), out_count (B) int32.  n_cells <= 65536*4. */
+int nvs_select_keypoints(const float* score, const float* coord, const float* feat,
+                         const int64_t* seg_cells, const int32_t* filter_classes, int32_t n_filter,
+                         float thresh, int32_t top_k, float* out_pts, float* out_desc,
+                         float* out_score, int32_t* out_cell, int64_t* out_label, int32_t* out_count,
+                         int32_t B, int32_t n_cells, int32_t D, void* stream);
+
+/* descriptor matching = BfFeatureMatcher.match (feature_matcher.py:89-98) + goodMatchesOneToOne
+ * (:179-209), or mutual nearest neighbour (cv2 crossCheck=True, evaluation/descriptor.py:221).
+ * des1 (n1,D) query, des2 (n2,D) train, row-major.
+ * mode 0: ratio test + one-to-one (literal reference semantics; needs n2 >= 2);
+ * mode 1: mutual NN;  mode 2: raw 2-NN -> out_idx1 = idx (n1,2) int32, out_dist = dist (n1,2) L2 (not
+ * squared), out_idx2 / out_count untouched.
+ * outputs for modes 0/1 (capacity n1): out_idx1, out_idx2 int32, out_dist float, out_count int32[1].
+ * D in {32, 64, 128}.  workspace: nvs_match_workspace_bytes(n1, n2). */
+size_t nvs_match_workspace_bytes(int32_t n1, int32_t n2);
+int nvs_match(const float* des1, const float* des2, int32_t n1, int32_t n2, int32_t D, double ratio,
+              int32_t mode, int32_t* out_idx1, int32_t* out_idx2, float* out_dist, int32_t* out_count,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOVS_H_ */

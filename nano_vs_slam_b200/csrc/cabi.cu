@@ -1,0 +1,36 @@
+// Error plumbing + device probe for the C ABI.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int nvs_set_cuda_error(cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d: %s", (int)e, cudaGetErrorString(e));
+  return NVS_ERR_CUDA;
+}
+
+extern "C" const char* nvs_last_error(void) { return g_err; }
+extern "C" int nvs_abi_version(void) { return NVS_ABI_VERSION; }
+
+extern "C" int nvs_device_ok(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    nvs_set_cuda_error(e);
+    return NVS_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    nvs_set_cuda_error(e);
+    return NVS_ERR_NO_DEVICE;
+  }
+  if (prop.major != 10) {
+    snprintf(g_err, sizeof(g_err), "device %d is sm_%d%d; libnanovs is built for sm_100a only", dev,
+             prop.major, prop.minor);
+    return NVS_ERR_NO_DEVICE;
+  }
+  return NVS_OK;
+}

@@ -1,0 +1,376 @@
+// Direct fp32 convolution (3x3 pad 1, or 1x1) with folded BatchNorm, activation and fused
+// pool / pixel-shuffle / concat-read epilogues.  sm_100a, FFMA pipe.
+//
+// Why FFMA and not tcgen05: parity is 1e-4 relative on fp32 features and >= 99.9 % segmentation argmax
+// agreement through ~20 chained layers; single-pass TF32/BF16 tensor-core products miss that
+// (SURVEY.md §7 "Precision vs tensor cores"), so the layers run exact fp32 multiply-adds.  The kernel is
+// therefore math-pipe bound (K = 9*Cin is contracted per output), and everything below is organised to
+// keep the FFMA pipe issuing: 64 accumulators per thread, 30 shared-memory loads per 576 FFMAs,
+// conflict-free LDS.64 activation reads, warp-broadcast LDS.128 weight reads, cp.async double buffering.
+//
+// Tiling
+//   thread : 4 rows x 2 cols of output pixels x 8 output channels (64 accumulators)
+//   warp   : lanes 2x16 -> 8 rows x 32 cols   (WIDE)   or lanes 4x8 -> 16 rows x 16 cols (NARROW)
+//   CTA    : WM pixel-warps stacked in y  x  WN channel-warps (8 channels each): CT = 8*WN channels
+//   K loop : input channels in chunks of CK (4 or 8), double buffered in shared memory:
+//            s_in[2][CK][TH+2][PITCH] (halo tile, zero filled = conv padding) and s_w[2][CK][taps][CT]
+#include "common.cuh"
+
+namespace nvs {
+
+struct ConvP {
+  const float* src0;
+  const float* src1;
+  const float* w;
+  const float* bias;
+  float* dst;
+  float* dst2;
+  int c0_total, c0_off, c0;
+  int c1_total, c1_off, c1;
+  int dst_c_total, dst_c_off;
+  int dst2_c_total, dst2_c_off;
+  int H, W, inH, inW;
+  int cin_pad, cout, cout_pad;
+  int act, out_mode, in_mode;
+  int tiles_x;
+};
+
+__device__ __noinline__ float slow_act(float v, int act, int channel) { return apply_act(v, act, channel); }
+
+template <int KS, int CK, int WN, int WM, bool NARROW>
+struct ConvCfg {
+  static constexpr int TAPS = KS * KS;
+  static constexpr int HALO = (KS == 3) ? 1 : 0;
+  static constexpr int LX = NARROW ? 8 : 16;
+  static constexpr int LY = 32 / LX;
+  static constexpr int TW = LX * 2;
+  static constexpr int TH = LY * 4 * WM;
+  static constexpr int IW = TW + 2 * HALO;
+  static constexpr int IH = TH + 2 * HALO;
+  // NARROW: a half-warp spans two lane-rows (4 tile rows apart); PITCH % 8 == 4 puts them on
+  // disjoint bank pairs.  WIDE: a half-warp is one lane-row, any even pitch is conflict free.
+  static constexpr int PITCH = NARROW ? 20 : (KS == 3 ? 36 : 32);
+  static constexpr int CT = WN * 8;
+  static constexpr int NT = 32 * WN * WM;
+  static constexpr int IN_ELEMS = CK * IH * PITCH;
+  static constexpr int W_ELEMS = CK * TAPS * CT;
+  static constexpr size_t SMEM = sizeof(float) * 2 * (IN_ELEMS + W_ELEMS);
+};
+
+template <int KS, int CK, int WN, int WM, bool NARROW>
+__global__ void __launch_bounds__(32 * WN * WM, 2) conv_kernel(const ConvP p) {
+  using C = ConvCfg<KS, CK, WN, WM, NARROW>;
+  constexpr int TAPS = C::TAPS, HALO = C::HALO, PITCH = C::PITCH, CT = C::CT, NT = C::NT;
+  constexpr int WR = 4 + 2 * HALO;  // window rows per thread
+  constexpr int WC = 2 + 2 * HALO;  // window cols per thread
+
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;                    // [2][CK][IH][PITCH]
+  float* s_w = smem + 2 * C::IN_ELEMS;   // [2][CK][TAPS][CT]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wn = warp % WN, wm = warp / WN;
+  const int lx = lane % C::LX, ly = lane / C::LX;
+  const int py = wm * (C::LY * 4) + ly * 4;  // thread's first output row inside the tile
+  const int px = lx * 2;
+
+  const int tile = blockIdx.x;
+  const int x0 = (tile % p.tiles_x) * C::TW;
+  const int y0 = (tile / p.tiles_x) * C::TH;
+  const int ct0 = blockIdx.y * CT;  // first output channel of this CTA
+  const int b = blockIdx.z;
+
+  const int cin = p.c0 + p.c1;
+  const int nchunks = p.cin_pad / CK;
+  const size_t in_plane = (size_t)p.inH * p.inW;
+
+  auto load_chunk = [&](int chunk, int buf) {
+    float* di = s_in + buf * C::IN_ELEMS;
+    // ---- activations: CK x IH x IW elements, 4-byte cp.async with zero fill outside the image ----
+    for (int idx = tid; idx < CK * C::IH * C::IW; idx += NT) {
+      const int c = idx / (C::IH * C::IW);
+      const int rem = idx - c * (C::IH * C::IW);
+      const int yy = rem / C::IW, xx = rem - yy * C::IW;
+      const int cg = chunk * CK + c;
+      const float* src = p.src0;
+      bool ok = cg < cin;
+      size_t off = 0;
+      if (p.in_mode == NVS_IN_S2D) {
+        // virtual channel cg = ci*4 + i*2 + j reads in[ci][2y+i][2x+j]
+        const int ci = cg >> 2, i = (cg >> 1) & 1, j = cg & 1;
+        const int gy = 2 * (y0 + yy) + i, gx = 2 * (x0 + xx) + j;
+        ok = ok && (y0 + yy) < p.H && (x0 + xx) < p.W;
+        off = ((size_t)b * p.c0_total + p.c0_off + ci) * in_plane + (size_t)gy * p.inW + gx;
+      } else {
+        const int gy = y0 - HALO + yy, gx = x0 - HALO + xx;
+        ok = ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+        if (cg < p.c0) {
+          off = ((size_t)b * p.c0_total + p.c0_off + cg) * in_plane + (size_t)gy * p.W + gx;
+        } else {
+          src = p.src1;
+          off = ((size_t)b * p.c1_total + p.c1_off + (cg - p.c0)) * in_plane + (size_t)gy * p.W + gx;
+        }
+      }
+      cp_async4(di + (c * C::IH + yy) * PITCH + xx, ok ? (src + off) : p.src0, ok);
+    }
+    // ---- weights: CK x TAPS rows of CT floats, 16-byte cp.async ----
+    float* dw = s_w + buf * C::W_ELEMS;
+    const float* gw = p.w + ((size_t)chunk * CK * TAPS) * p.cout_pad + ct0;
+    for (int idx = tid; idx < CK * TAPS * (CT / 4); idx += NT) {
+      const int row = idx / (CT / 4), q = idx - row * (CT / 4);
+      cp_async16(dw + row * CT + q * 4, gw + (size_t)row * p.cout_pad + q * 4);
+    }
+  };
+
+  float acc[4][2][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[r][c][o] = 0.f;
+
+  load_chunk(0, 0);
+  cp_async_commit();
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      load_chunk(ch + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    const float* si = s_in + buf * C::IN_ELEMS + py * PITCH + px;
+    const float* sw = s_w + buf * C::W_ELEMS + wn * 8;
+#pragma unroll 1
+    for (int c = 0; c < CK; ++c) {
+      float a[WR][WC];
+#pragma unroll
+      for (int r = 0; r < WR; ++r) {
+#pragma unroll
+        for (int q = 0; q < WC / 2; ++q) {
+          const float2 v = *reinterpret_cast<const float2*>(si + (c * C::IH + r) * PITCH + 2 * q);
+          a[r][2 * q] = v.x;
+          a[r][2 * q + 1] = v.y;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) {
+        const int ky = t / KS, kx = t % KS;
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + (c * TAPS + t) * CT);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + (c * TAPS + t) * CT + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const float v = a[r + ky][cc + kx];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[r][cc][o] = fmaf(v, wv[o], acc[r][cc][o]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------ epilogue ------------------------------------
+  const int co0 = ct0 + wn * 8;  // this thread's first output channel
+  if (co0 >= p.cout) return;
+  const int gy0 = y0 + py, gx0 = x0 + px;
+  if (gy0 >= p.H || gx0 >= p.W) return;
+
+  float bias[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) bias[o] = p.bias[co0 + o];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const float v = acc[r][c][o] + bias[o];
+        // LeakyReLU / ReLU / identity inline; transcendental activations (tiny head layers) out of line
+        acc[r][c][o] = p.act == NVS_ACT_LRELU  ? (v > 0.f ? v : 0.01f * v)
+                       : p.act == NVS_ACT_NONE ? v
+                       : p.act == NVS_ACT_RELU ? fmaxf(v, 0.f)
+                                               : slow_act(v, p.act, co0 + o);
+      }
+
+  const bool x1ok = gx0 + 1 < p.W;
+
+  if (p.out_mode == NVS_OUT_PLAIN || p.out_mode == NVS_OUT_BOTH) {
+    const bool vec = x1ok && ((p.W & 1) == 0);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (co0 + o >= p.cout) break;
+      float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + co0 + o) * p.H + gy0) * p.W + gx0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (gy0 + r >= p.H) break;
+        if (vec) {
+          *reinterpret_cast<float2*>(d + (size_t)r * p.W) = make_float2(acc[r][0][o], acc[r][1][o]);
+        } else {
+          d[(size_t)r * p.W] = acc[r][0][o];
+          if (x1ok) d[(size_t)r * p.W + 1] = acc[r][1][o];
+        }
+      }
+    }
+  }
+  if (p.out_mode == NVS_OUT_POOL || p.out_mode == NVS_OUT_BOTH) {
+    // MaxPool2d(2,2), floor: thread-local because the thread owns aligned 2x2 blocks.
+    const int Hp = p.H >> 1, Wp = p.W >> 1;
+    const int qx = gx0 >> 1;
+    if (qx < Wp) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        if (co0 + o >= p.cout) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int qy = (gy0 >> 1) + h;
+          if (qy >= Hp) break;
+          const float m = fmaxf(fmaxf(acc[2 * h][0][o], acc[2 * h][1][o]),
+                                fmaxf(acc[2 * h + 1][0][o], acc[2 * h + 1][1][o]));
+          p.dst2[(((size_t)b * p.dst2_c_total + p.dst2_c_off + co0 + o) * Hp + qy) * Wp + qx] = m;
+        }
+      }
+    }
+  }
+  if (p.out_mode == NVS_OUT_SHUFFLE) {
+    // PixelShuffle(2): channel co -> (co/4, i=(co%4)/2, j=co%2); thread's 8 channels = 2 shuffled channels.
+    const int H2 = p.H * 2, W2 = p.W * 2;
+    const bool vec = x1ok && ((p.W & 1) == 0);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (co0 + 4 * s >= p.cout) break;
+      const int cs = (co0 >> 2) + s;
+      float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cs) * H2) * W2;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (gy0 + r >= p.H) break;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float* row = d + (size_t)(2 * (gy0 + r) + i) * W2 + 2 * gx0;
+          const float v0 = acc[r][0][4 * s + 2 * i], v1 = acc[r][0][4 * s + 2 * i + 1];
+          const float v2 = acc[r][1][4 * s + 2 * i], v3 = acc[r][1][4 * s + 2 * i + 1];
+          if (vec) {
+            *reinterpret_cast<float4*>(row) = make_float4(v0, v1, v2, v3);
+          } else {
+            row[0] = v0;
+            row[1] = v1;
+            if (x1ok) {
+              row[2] = v2;
+              row[3] = v3;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KS, int CK, int WN, int WM, bool NARROW>
+static int launch_conv(const ConvP& p0, int B, cudaStream_t st) {
+  using C = ConvCfg<KS, CK, WN, WM, NARROW>;
+  ConvP p = p0;
+  p.tiles_x = (p.W + C::TW - 1) / C::TW;
+  const int tiles_y = (p.H + C::TH - 1) / C::TH;
+  dim3 grid(p.tiles_x * tiles_y, p.cout_pad / C::CT, B);
+  auto kern = conv_kernel<KS, CK, WN, WM, NARROW>;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return nvs_set_cuda_error(e);
+    attr_done = true;
+  }
+  kern<<<grid, C::NT, C::SMEM, st>>>(p);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+// padding waste of a tile width against the plane width
+static inline bool prefer_narrow(int H, int W) {
+  auto waste = [](int n, int t) { return (double)(((n + t - 1) / t) * t) / n; };
+  const double wide = waste(W, 32) * waste(H, 8);
+  const double narrow = waste(W, 16) * waste(H, 16);
+  return narrow < wide - 1e-9;
+}
+
+template <int KS, int CK>
+static int dispatch_ct(const ConvP& p, int B, int ct, cudaStream_t st) {
+  const bool narrow = prefer_narrow(p.H, p.W);
+#define NVS_CASE(WN_, WM_)                                                   \
+  return narrow ? launch_conv<KS, CK, WN_, WM_, true>(p, B, st)              \
+                : launch_conv<KS, CK, WN_, WM_, false>(p, B, st)
+  switch (ct) {
+    case 8: NVS_CASE(1, 8);
+    case 16: NVS_CASE(2, 4);
+    case 24: NVS_CASE(3, 2);
+    case 32: NVS_CASE(4, 2);
+    case 48: NVS_CASE(6, 1);
+    case 64: NVS_CASE(8, 1);
+  }
+#undef NVS_CASE
+  return NVS_ERR_UNSUPPORTED;
+}
+
+}  // namespace nvs
+
+extern "C" int nvs_conv_cout_tile(int32_t cout) {
+  if (cout <= 0) return NVS_ERR_ARG;
+  if (cout <= 8) return 8;
+  if (cout <= 16) return 16;
+  if (cout <= 24) return 24;
+  if (cout <= 32) return 32;
+  if (cout <= 48) return 48;
+  if (cout <= 64) return 64;
+  if (cout % 64 == 0) return 64;
+  if (cout % 48 == 0) return 48;
+  return 64;
+}
+
+extern "C" int nvs_conv_cin_chunk(int32_t cin) { return cin <= 4 ? 4 : 8; }
+
+extern "C" int nvs_conv(const NvsConvArgs* a, void* stream) {
+  using namespace nvs;
+  if (!a || !a->src0 || !a->weight || !a->bias) return NVS_ERR_ARG;
+  if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->cout <= 0 || a->c0 <= 0) return NVS_ERR_ARG;
+  if (a->B > 65535) return NVS_ERR_ARG;
+  if (a->ksize != 1 && a->ksize != 3) return NVS_ERR_UNSUPPORTED;
+  if (a->c1 > 0 && !a->src1) return NVS_ERR_ARG;
+  if (a->out_mode != NVS_OUT_POOL && !a->dst) return NVS_ERR_ARG;
+  if ((a->out_mode == NVS_OUT_POOL || a->out_mode == NVS_OUT_BOTH) && !a->dst2) return NVS_ERR_ARG;
+  if (a->in_mode == NVS_IN_S2D && (a->ksize != 1 || a->c1 != 0)) return NVS_ERR_UNSUPPORTED;
+  const int cin = (a->in_mode == NVS_IN_S2D) ? 4 * a->c0 : a->c0 + a->c1;
+  const int ck = nvs_conv_cin_chunk(cin);
+  if (a->c1 > 0 && (a->c0 % ck) != 0) return NVS_ERR_UNSUPPORTED;  // chunk must not straddle sources
+  const int ct = nvs_conv_cout_tile(a->cout);
+  if (a->out_mode == NVS_OUT_SHUFFLE && (a->cout % 4) != 0) return NVS_ERR_ARG;
+
+  ConvP p;
+  p.src0 = a->src0; p.src1 = a->src1; p.w = a->weight; p.bias = a->bias;
+  p.dst = a->dst; p.dst2 = a->dst2;
+  p.c0_total = a->c0_total; p.c0_off = a->c0_off;
+  p.c0 = (a->in_mode == NVS_IN_S2D) ? 4 * a->c0 : a->c0;  // virtual channel count under S2D
+  p.c1_total = a->c1_total; p.c1_off = a->c1_off; p.c1 = a->c1;
+  p.dst_c_total = a->dst_c_total; p.dst_c_off = a->dst_c_off;
+  p.dst2_c_total = a->dst2_c_total; p.dst2_c_off = a->dst2_c_off;
+  p.H = a->H; p.W = a->W;
+  p.inH = (a->in_mode == NVS_IN_S2D) ? a->in_H : a->H;
+  p.inW = (a->in_mode == NVS_IN_S2D) ? a->in_W : a->W;
+  if (a->in_mode == NVS_IN_S2D && (a->in_H < 2 * a->H || a->in_W < 2 * a->W)) return NVS_ERR_ARG;
+  p.cin_pad = (cin + ck - 1) / ck * ck;
+  p.cout = a->cout;
+  p.cout_pad = (a->cout + ct - 1) / ct * ct;
+  p.act = a->act; p.out_mode = a->out_mode; p.in_mode = a->in_mode;
+  p.tiles_x = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->ksize == 3) {
+    return ck == 4 ? dispatch_ct<3, 4>(p, a->B, ct, st) : dispatch_ct<3, 8>(p, a->B, ct, st);
+  }
+  return ck == 4 ? dispatch_ct<1, 4>(p, a->B, ct, st) : dispatch_ct<1, 8>(p, a->B, ct, st);
+}

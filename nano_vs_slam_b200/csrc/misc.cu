@@ -1,0 +1,267 @@
+// Small HBM/latency-bound kernels around the conv chain: depthwise 3x3, channel LayerNorm,
+// channel softmax, channel L2 norm, seg argmax and the keypoint decode (post_processing).
+#include "common.cuh"
+
+namespace nvs {
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3 + bias (modules/segformer.py:46-54).  One thread per output pixel, coalesced in x.
+// ---------------------------------------------------------------------------------------------
+__global__ void dwconv3x3_kernel(const float* __restrict__ src, const float* __restrict__ w,
+                                 const float* __restrict__ bias, float* __restrict__ dst, int C, int H,
+                                 int W, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const size_t bc = i / ((size_t)W * H);
+    const int c = (int)(bc % C);
+    const float* s = src + bc * (size_t)H * W;
+    const float* k = w + c * 9;
+    float acc = bias ? bias[c] : 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        acc = fmaf(__ldg(s + (size_t)yy * W + xx), k[(dy + 1) * 3 + dx + 1], acc);
+      }
+    }
+    dst[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-pixel statistics over channels.  One thread per pixel; every channel read is coalesced across
+// the warp (NCHW planes).  MODE 0: LayerNorm (x-mean)/(std+eps)*g+b  (segformer.py:70-73)
+//                          MODE 1: softmax over channels (Softmax2d)
+//                          MODE 2: x / max(||x||_2, 1e-12)  (F.normalize, vpr.py:85-86)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void channel_stat_kernel(const float* __restrict__ src, const float* __restrict__ g,
+                                    const float* __restrict__ bb, float* __restrict__ dst, int C, int HW,
+                                    size_t npix, float eps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW;
+    const int s = (int)(i - b * HW);
+    const float* p = src + b * (size_t)C * HW + s;
+    float* d = dst + b * (size_t)C * HW + s;
+    if (MODE == 0) {
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) sum += p[(size_t)c * HW];
+      const float mean = sum / C;
+      float var = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float t = p[(size_t)c * HW] - mean;
+        var = fmaf(t, t, var);
+      }
+      const float inv = 1.f / (sqrtf(var / C) + eps);
+      for (int c = 0; c < C; ++c) d[(size_t)c * HW] = (p[(size_t)c * HW] - mean) * inv * g[c] + bb[c];
+    } else if (MODE == 1) {
+      float m = -INFINITY;
+      for (int c = 0; c < C; ++c) m = fmaxf(m, p[(size_t)c * HW]);
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) sum += expf(p[(size_t)c * HW] - m);
+      const float inv = 1.f / sum;
+      for (int c = 0; c < C; ++c) d[(size_t)c * HW] = expf(p[(size_t)c * HW] - m) * inv;
+    } else {
+      float ss = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float t = p[(size_t)c * HW];
+        ss = fmaf(t, t, ss);
+      }
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      for (int c = 0; c < C; ++c) d[(size_t)c * HW] = p[(size_t)c * HW] * inv;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// argmax over classes -> int64 (first maximal index, like torch.argmax on distinct values).
+// Optional nearest sampling at keypoint coordinates (grid_sample mode='nearest', align_corners=True).
+// ---------------------------------------------------------------------------------------------
+__global__ void seg_argmax_kernel(const float* __restrict__ seg, const float* __restrict__ coord,
+                                  int64_t* __restrict__ out, int C, int Hs, int Ws, int Hc, int Wc, int H,
+                                  int W, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t b;
+    int sy, sx;
+    bool inb = true;
+    if (coord) {
+      const int ncell = Hc * Wc;
+      b = i / ncell;
+      const int cell = (int)(i - b * ncell);
+      const float cx = coord[(b * 2 + 0) * ncell + cell];
+      const float cy = coord[(b * 2 + 1) * ncell + cell];
+      const float gx = cx / ((float)(W - 1) / 2.f) - 1.f;
+      const float gy = cy / ((float)(H - 1) / 2.f) - 1.f;
+      const float fx = (gx + 1.f) * ((float)(Ws - 1) / 2.f);
+      const float fy = (gy + 1.f) * ((float)(Hs - 1) / 2.f);
+      sx = (int)nearbyintf(fx);
+      sy = (int)nearbyintf(fy);
+      inb = sx >= 0 && sx < Ws && sy >= 0 && sy < Hs;
+    } else {
+      const int hw = Hs * Ws;
+      b = i / hw;
+      const int s = (int)(i - b * hw);
+      sy = s / Ws;
+      sx = s - sy * Ws;
+    }
+    int best = 0;
+    if (inb) {
+      const float* p = seg + b * (size_t)C * Hs * Ws + (size_t)sy * Ws + sx;
+      float bv = p[0];
+      for (int c = 1; c < C; ++c) {
+        const float v = p[(size_t)c * Hs * Ws];
+        if (v > bv) {
+          bv = v;
+          best = c;
+        }
+      }
+    }
+    out[i] = best;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// keypoint decode (kp2dtiny.py:593-647): one thread per cell.
+//   score  <- score * border_mask                                    (:520-528)
+//   coord  <- clamp(cell_xy*cell + step + shift*cross_ratio*step)    (:597-614)
+//   feat   <- grid_sample(feat, coord_norm, bilinear, align_corners=True, zeros) / ||.||_2   (:627-631)
+// Arithmetic follows ATen's grid_sampler (unnormalise ((g+1)/2)*(size-1); weights from floor corners)
+// ---------------------------------------------------------------------------------------------
+template <int DMAX>
+__global__ void decode_kernel(const float* __restrict__ score, const float* __restrict__ shift,
+                              const float* __restrict__ feat, float* __restrict__ out_score,
+                              float* __restrict__ out_coord, float* __restrict__ out_feat, int Hc, int Wc,
+                              int D, int Hf, int Wf, int H, int W, float cell, float step, float cross,
+                              size_t total) {
+  const int ncell = Hc * Wc;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / ncell;
+    const int cidx = (int)(i - b * ncell);
+    const int cy = cidx / Wc, cx = cidx - cy * Wc;
+    const bool border = (cy == 0) | (cy == Hc - 1) | (cx == 0) | (cx == Wc - 1);
+    out_score[i] = border ? 0.f : score[i];
+    const float sx = shift[(b * 2 + 0) * ncell + cidx];
+    const float sy = shift[(b * 2 + 1) * ncell + cidx];
+    // base + shift * (cross_ratio * step): separate multiply and add, as torch evaluates it
+    float px = __fadd_rn(__fadd_rn(__fmul_rn((float)cx, cell), step), __fmul_rn(sx, cross * step));
+    float py = __fadd_rn(__fadd_rn(__fmul_rn((float)cy, cell), step), __fmul_rn(sy, cross * step));
+    px = fminf(fmaxf(px, 0.f), (float)(W - 1));
+    py = fminf(fmaxf(py, 0.f), (float)(H - 1));
+    out_coord[(b * 2 + 0) * ncell + cidx] = px;
+    out_coord[(b * 2 + 1) * ncell + cidx] = py;
+    if (!feat) continue;
+    // normalize_coord (:642-647) then ATen grid_sampler (align_corners): (g + 1) * ((size - 1) / 2)
+    const float gx = __fsub_rn(__fdiv_rn(px, (float)(W - 1) / 2.f), 1.f);
+    const float gy = __fsub_rn(__fdiv_rn(py, (float)(H - 1) / 2.f), 1.f);
+    const float ix = __fmul_rn(__fadd_rn(gx, 1.f), (float)(Wf - 1) / 2.f);
+    const float iy = __fmul_rn(__fadd_rn(gy, 1.f), (float)(Hf - 1) / 2.f);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const float ww = ix - fx0, we = 1.f - ww, wn_ = iy - fy0, ws = 1.f - wn_;
+    const float wnw = ws * we, wne = ws * ww, wsw = wn_ * we, wse = wn_ * ww;
+    const bool vx0 = x0 >= 0 && x0 < Wf, vx1 = x1 >= 0 && x1 < Wf;
+    const bool vy0 = y0 >= 0 && y0 < Hf, vy1 = y1 >= 0 && y1 < Hf;
+    const float* f = feat + b * (size_t)D * Hf * Wf;
+    float v[DMAX];
+    float ss = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < DMAX; ++c) {
+      if (c < D) {
+        const float* fc = f + (size_t)c * Hf * Wf;
+        const float tnw = (vy0 && vx0) ? __ldg(fc + (size_t)y0 * Wf + x0) : 0.f;
+        const float tne = (vy0 && vx1) ? __ldg(fc + (size_t)y0 * Wf + x1) : 0.f;
+        const float tsw = (vy1 && vx0) ? __ldg(fc + (size_t)y1 * Wf + x0) : 0.f;
+        const float tse = (vy1 && vx1) ? __ldg(fc + (size_t)y1 * Wf + x1) : 0.f;
+        const float a = tnw * wnw + tne * wne + tsw * wsw + tse * wse;
+        v[c] = a;
+        ss = fmaf(a, a, ss);
+      }
+    }
+    const float nrm = sqrtf(ss);  // no epsilon in the reference (:629-630)
+#pragma unroll 4
+    for (int c = 0; c < DMAX; ++c)
+      if (c < D) out_feat[(b * D + c) * (size_t)ncell + cidx] = v[c] / nrm;
+  }
+}
+
+static inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 32;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace nvs
+
+using namespace nvs;
+
+extern "C" int nvs_dwconv3x3(const float* src, const float* w, const float* bias, float* dst, int32_t B,
+                             int32_t C, int32_t H, int32_t W, void* stream) {
+  if (!src || !w || !dst || B <= 0 || C <= 0 || H <= 0 || W <= 0) return NVS_ERR_ARG;
+  const size_t total = (size_t)B * C * H * W;
+  dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, w, bias, dst, C, H, W, total);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+extern "C" int nvs_channel_layernorm(const float* src, const float* g, const float* b, float* dst, int32_t B,
+                                     int32_t C, int32_t HW, float eps, void* stream) {
+  if (!src || !g || !b || !dst || B <= 0 || C <= 0 || HW <= 0) return NVS_ERR_ARG;
+  const size_t npix = (size_t)B * HW;
+  channel_stat_kernel<0><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(src, g, b, dst, C, HW, npix, eps);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+extern "C" int nvs_softmax_channels(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, void* stream) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return NVS_ERR_ARG;
+  const size_t npix = (size_t)B * HW;
+  channel_stat_kernel<1><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(src, nullptr, nullptr, dst, C, HW, npix, 0.f);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+extern "C" int nvs_l2norm_channels(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, void* stream) {
+  if (!src || !dst || B <= 0 || C <= 0 || HW <= 0) return NVS_ERR_ARG;
+  const size_t npix = (size_t)B * HW;
+  channel_stat_kernel<2><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(src, nullptr, nullptr, dst, C, HW, npix, 0.f);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+extern "C" int nvs_seg_argmax(const float* seg, const float* coord, int64_t* out, int32_t B, int32_t C,
+                              int32_t Hs, int32_t Ws, int32_t Hc, int32_t Wc, int32_t H, int32_t W,
+                              void* stream) {
+  if (!seg || !out || B <= 0 || C <= 0 || Hs <= 0 || Ws <= 0) return NVS_ERR_ARG;
+  if (coord && (Hc <= 0 || Wc <= 0 || H <= 1 || W <= 1)) return NVS_ERR_ARG;
+  const size_t total = coord ? (size_t)B * Hc * Wc : (size_t)B * Hs * Ws;
+  seg_argmax_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(seg, coord, out, C, Hs, Ws, Hc, Wc, H, W, total);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+extern "C" int nvs_decode(const float* score, const float* shift, const float* feat, float* out_score,
+                          float* out_coord, float* out_feat, int32_t B, int32_t Hc, int32_t Wc, int32_t D,
+                          int32_t Hf, int32_t Wf, int32_t H, int32_t W, int32_t cell, float cross_ratio,
+                          void* stream) {
+  if (!score || !shift || !out_score || !out_coord || B <= 0 || Hc <= 0 || Wc <= 0) return NVS_ERR_ARG;
+  if (feat && (!out_feat || D <= 0 || Hf <= 0 || Wf <= 0 || H <= 1 || W <= 1)) return NVS_ERR_ARG;
+  if (feat && D > 128) return NVS_ERR_UNSUPPORTED;
+  const size_t total = (size_t)B * Hc * Wc;
+  const float step = (cell - 1) / 2.0f;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!feat || D <= 32)
+    decode_kernel<32><<<grid_for(total, 128), 128, 0, st>>>(score, shift, feat, out_score, out_coord, out_feat, Hc, Wc, D, Hf, Wf, H, W, (float)cell, step, cross_ratio, total);
+  else
+    decode_kernel<128><<<grid_for(total, 128), 128, 0, st>>>(score, shift, feat, out_score, out_coord, out_feat, Hc, Wc, D, Hf, Wf, H, W, (float)cell, step, cross_ratio, total);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}

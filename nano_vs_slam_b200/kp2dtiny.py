@@ -1,0 +1,723 @@
+"""KP2DTinyV2 / KP2DTinyV3 with the reference's constructor, config letters, state_dict names and
+forward / post_processing output dict, executed by the sm_100a kernels in libnanovs.so.
+
+Mirrors src/kp2dtiny/models/kp2dtiny.py of ETH-PBL/Nano-VS-SLAM:
+  KP2DTINY_CONFIGS :198, KP2DTINYV3_CONFIGS :210, tiny_factory :221, get_config :245,
+  KP2DTinyV2 :284 (forward :552, post_processing :593), KP2DTinyV3 :650 (forward :906,
+  post_processing :959).
+
+The nn.Module tree below only *holds parameters* under the reference's names (so reference ``.ckpt``
+state_dicts load with strict=True); it never calls ATen convolutions.  ``forward`` folds BatchNorm into
+packed weights once, builds a per-(B,H,W) launch plan (pre-filled C-ABI argument structs + cached
+intermediate buffers) and replays it.  Inference only: the module raises in training mode and on CPU
+tensors -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import copy
+import inspect
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._cabi import NanovsError
+
+# ----------------------------------------------------------------------------------------------
+# config letters (kp2dtiny.py:46-218)
+# ----------------------------------------------------------------------------------------------
+_S = [16, 32, 32, 64, 64, 128]
+_N = [16, 24, 24, 48, 48, 96]
+_D = [64, 128, 128, 256, 256, 512]
+
+KP2DTINY_CONFIGS = {
+    "S": dict(nfeatures=32, channel_dims=_S, downsample=2, use_attention=False, leaky_relu=True, encoder_dim=64),
+    "S_A": dict(nfeatures=32, channel_dims=_S, downsample=2, use_attention=True, leaky_relu=True, encoder_dim=64),
+    "N": dict(nfeatures=32, channel_dims=_N, downsample=2, use_attention=False, leaky_relu=True, num_clusters=32,
+              encoder_dim=48),
+    "N_A": dict(nfeatures=32, channel_dims=_N, downsample=2, use_attention=True, leaky_relu=True, num_clusters=32,
+                encoder_dim=48),
+    "D": dict(nfeatures=128, channel_dims=_D, downsample=2, use_attention=True, leaky_relu=True, encoder_dim=128,
+              global_descriptor_method="convap"),
+    "F": dict(nfeatures=64, channel_dims=[16, 32, 64, 128, 128, 256], downsample=3, use_attention=False,
+              leaky_relu=True),
+    "GEM_N": dict(nfeatures=32, channel_dims=_N, downsample=2, use_attention=False, leaky_relu=True,
+                  num_clusters=32, encoder_dim=48, global_descriptor_method="gem"),
+    "GEM_S_A": dict(nfeatures=32, channel_dims=_S, downsample=2, use_attention=True, leaky_relu=True,
+                    encoder_dim=64, global_descriptor_method="gem"),
+    "CONVAP_S_A": dict(nfeatures=32, channel_dims=_S, downsample=2, use_attention=True, leaky_relu=True,
+                       encoder_dim=64, global_descriptor_method="convap"),
+}
+
+KP2DTINYV3_CONFIGS = {
+    "S": dict(nfeatures=32, channel_dims=_S, bn_momentum=0.1, downsample=2, use_attention=False, leaky_relu=True,
+              encoder_dim=64),
+    "S_A": dict(nfeatures=32, channel_dims=_S, bn_momentum=0.1, downsample=2, use_attention=True, leaky_relu=True,
+                encoder_dim=64),
+    "N": dict(nfeatures=32, channel_dims=_N, bn_momentum=0.1, downsample=2, use_attention=False, encoder_dim=48),
+    "N_A": dict(nfeatures=32, channel_dims=_N, bn_momentum=0.1, downsample=2, use_attention=True, encoder_dim=48),
+    "D": dict(nfeatures=128, channel_dims=_D, downsample=2, use_attention=False, leaky_relu=True, encoder_dim=128,
+              global_descriptor_method="convap"),
+    "D_A": dict(nfeatures=128, channel_dims=_D, downsample=2, use_attention=True, leaky_relu=True,
+                encoder_dim=128, global_descriptor_method="convap"),
+    "CONVAP_S_A": dict(nfeatures=32, channel_dims=_S, bn_momentum=0.1, downsample=2, use_attention=True,
+                       leaky_relu=True, encoder_dim=64, global_descriptor_method="convap"),
+}
+
+
+def get_config(config, to_mcu=False, to_export=False, v3=False):
+    """kp2dtiny.py:245-281.  Returns a *copy* (the reference mutates the shared dict, :271-278)."""
+    table = KP2DTINYV3_CONFIGS if v3 else KP2DTINY_CONFIGS
+    if config not in table:
+        raise ValueError("Config {} not supported, choose from ".format(config), list(table.keys()))
+    conf = copy.deepcopy(table[config])
+    if to_mcu:
+        conf["upscale_method"] = "convtranspose"
+        conf["leaky_relu"] = False
+    if to_export:
+        conf["remove_netvlad"] = True
+    return conf
+
+
+def tiny_factory(config, n_classes, to_mcu=False, to_export=False, v3=False):
+    """kp2dtiny.py:221-242."""
+    conf = get_config(config, to_mcu=to_mcu, to_export=to_export, v3=v3)
+    return (KP2DTinyV3 if v3 else KP2DTinyV2)(**conf, nClasses=n_classes)
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter holders (same attribute names as the reference modules => same state_dict keys)
+# ----------------------------------------------------------------------------------------------
+class _ConvBnAct(nn.Module):
+    """modules/base.py:14-46 (conv.weight, bn.{weight,bias,running_mean,running_var,num_batches_tracked})."""
+
+    def __init__(self, c0, c1, bn_momentum=0.1):
+        super().__init__()
+        self.conv = nn.Conv2d(c0, c1, 3, 1, 1, bias=False)
+        self.bn = nn.BatchNorm2d(c1, momentum=bn_momentum)
+
+
+class _BackBone(nn.Module):  # modules/encoders.py:5-103
+    def __init__(self, c0, c1, c2, c3, c4, bn_momentum):
+        super().__init__()
+        self.conv1a = _ConvBnAct(c0, c1, bn_momentum)
+        self.conv1b = _ConvBnAct(c1, c2, bn_momentum)
+        self.conv2a = _ConvBnAct(c2, c2, bn_momentum)
+        self.conv2b = _ConvBnAct(c2, c3, bn_momentum)
+        self.conv3a = _ConvBnAct(c3, c3, bn_momentum)
+        self.conv3b = _ConvBnAct(c3, c4, bn_momentum)
+        self.conv4a = _ConvBnAct(c4, c4, bn_momentum)
+        self.conv4b = _ConvBnAct(c4, c4, bn_momentum)
+
+
+class _TaskHead(nn.Module):  # modules/decoders/heads.py:7-35
+    def __init__(self, c_in, c_hidden, c_out, bn_momentum):
+        super().__init__()
+        self.convDa = _ConvBnAct(c_in, c_hidden, bn_momentum)
+        self.convDb = nn.Conv2d(c_hidden, c_out, 3, 1, 1)
+
+
+class _UpscaleHead(nn.Module):  # modules/decoders/heads.py:38-104
+    def __init__(self, c0, c1, c2, c3, c4, c5, bn_momentum):
+        super().__init__()
+        self.convA = _ConvBnAct(c0, c1, bn_momentum)
+        self.convB = nn.Conv2d(c1, c2, 3, 1, 1)
+        self.confAa = _ConvBnAct(c3, c4, bn_momentum)
+        self.confBb = nn.Conv2d(c4, c5, 3, 1, 1)
+
+
+class _ChanLN(nn.Module):  # modules/segformer.py:63-73
+    def __init__(self, dim):
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(1, dim, 1, 1))
+        self.b = nn.Parameter(torch.zeros(1, dim, 1, 1))
+
+
+class _PreNorm(nn.Module):  # modules/segformer.py:76-83
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.fn = fn
+        self.norm = _ChanLN(dim)
+
+
+class _ESA(nn.Module):  # modules/segformer.py:86-98
+    def __init__(self, dim, heads=4, reduction_ratio=2):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Conv2d(dim, dim, 1, bias=False)
+        self.to_kv = nn.Conv2d(dim, dim * 2, reduction_ratio, stride=reduction_ratio, bias=False)
+        self.to_out = nn.Conv2d(dim, dim, 1, bias=False)
+
+
+class _DsConv(nn.Module):  # modules/segformer.py:43-60
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.Sequential(nn.Conv2d(dim, dim, 3, padding=1, groups=dim), nn.Conv2d(dim, dim, 1))
+
+
+class _MixFFN(nn.Module):  # modules/segformer.py:182-200
+    def __init__(self, dim, expansion_factor=2):
+        super().__init__()
+        hidden = dim * expansion_factor
+        self.net = nn.Sequential(nn.Conv2d(dim, hidden, 1), _DsConv(hidden), nn.GELU(), nn.Conv2d(hidden, dim, 1))
+
+
+class _AttModule(nn.Module):  # modules/segformer.py:209-220
+    def __init__(self, c):
+        super().__init__()
+        self.att = _PreNorm(c, _ESA(c))
+        self.mff = _PreNorm(c, _MixFFN(c))
+
+
+class _SegHead(nn.Module):
+    """The four segmentation heads (modules/decoders/segmentation.py:8,169,350,478) as one holder."""
+
+    def __init__(self, c_in, c_hidden, c_exp, c_out, d1, bn_momentum, attention, n_feat=None):
+        super().__init__()
+        fused = n_feat is not None  # V3: seg + feat from one trunk
+        self.dim_split = c_hidden // 2
+        if fused:
+            assert c_hidden % 2 == 0, "c_hidden must be divisible by 2"
+        cb = lambda a, b: _ConvBnAct(a, b, bn_momentum)  # noqa: E731
+        if attention:
+            layers = [cb(c_in, c_hidden), _AttModule(c_hidden), _AttModule(c_hidden)]
+        else:
+            layers = [cb(c_in, c_hidden), cb(c_hidden, c_hidden), cb(c_hidden, c_hidden), cb(c_hidden, c_hidden)]
+        layers += [cb(c_hidden, d1), cb(c_hidden + d1 // 4, c_hidden), cb(c_hidden, d1), cb(c_exp, c_hidden),
+                   nn.Conv2d(self.dim_split if fused else c_hidden, c_out, 3, 1, 1)]
+        self.convs = nn.ModuleList(layers)
+        if fused:
+            self.featB = nn.Conv2d(self.dim_split, n_feat, 3, 1, 1)
+
+    def freeze(self, except_last_layer=False):  # segmentation.py:159-166
+        for p in self.parameters():
+            p.requires_grad = False
+        if except_last_layer:
+            for p in self.convs[len(self.convs) - 1].parameters():
+                p.requires_grad = True
+
+
+class _NetVLAD(nn.Module):  # modules/aggregators/netvlad.py:19-48
+    def __init__(self, num_clusters, dim):
+        super().__init__()
+        self.num_clusters, self.dim = num_clusters, dim
+        self.conv = nn.Conv2d(dim, num_clusters, kernel_size=(1, 1), bias=False)
+        self.centroids = nn.Parameter(torch.rand(num_clusters, dim))
+
+    def get_desc_size(self):
+        return self.dim * self.num_clusters
+
+    def init_params(self, clsts, traindescs):  # netvlad.py:50-63 (vladv2=False branch)
+        import numpy as np
+
+        assign = clsts / np.linalg.norm(clsts, axis=1, keepdims=True)
+        dots = np.dot(assign, traindescs.T)
+        dots.sort(0)
+        dots = dots[::-1, :]
+        alpha = (-np.log(0.01) / np.mean(dots[0, :] - dots[1, :])).item()
+        dev = self.centroids.device
+        self.centroids = nn.Parameter(torch.from_numpy(clsts).to(dev))
+        self.conv.weight = nn.Parameter(torch.from_numpy(alpha * assign).unsqueeze(2).unsqueeze(3).to(dev))
+
+
+class _VPRHead(nn.Module):  # modules/decoders/vpr.py:8-76
+    def __init__(self, c_in, encoder_dim, num_clusters, bn_momentum, remove_netvlad, method):
+        super().__init__()
+        self.convlad1 = _ConvBnAct(c_in, encoder_dim, bn_momentum)
+        self.convlad2 = _ConvBnAct(encoder_dim, encoder_dim, bn_momentum)
+        self.convlad3 = _ConvBnAct(encoder_dim, encoder_dim, bn_momentum)
+        self.remove_netvlad = remove_netvlad
+        if method != "netvlad":
+            raise NotImplementedError(
+                f"global_descriptor_method={method!r}: only 'netvlad' is on the B200 hot path (GeM/ConvAP: SURVEY §8(f))")
+        if not remove_netvlad:
+            self.netvlad = _NetVLAD(num_clusters, encoder_dim)
+            self.global_desc_dim = self.netvlad.get_desc_size()
+        else:
+            self.global_desc_dim = 0
+
+
+# ----------------------------------------------------------------------------------------------
+# launch plan
+# ----------------------------------------------------------------------------------------------
+class _Plan:
+    """Everything shape dependent: cached intermediates + pre-filled NvsConvArgs, replayed per forward."""
+
+    def __init__(self, model: "_KP2DTinyBase", B: int, H: int, W: int, device: torch.device):
+        self.steps: List = []
+        self.out_slots: Dict[str, List] = {}
+        self.B, self.H, self.W, self.device = B, H, W, device
+        self.bufs: Dict[str, torch.Tensor] = {}
+        model._build_plan(self)
+
+    def buf(self, name: str, c: int, h: int, w: int) -> torch.Tensor:
+        t = torch.empty(self.B, c, h, w, device=self.device, dtype=torch.float32)
+        self.bufs[name] = t
+        return t
+
+    def conv(self, packed, src0, cout, *, out_name=None, **kw):
+        """Register a conv; if ``out_name`` is given its dst pointer is patched per call (fresh output)."""
+        wp, bp = packed
+        args = ops.make_conv_args(src0, wp, bp, cout, **kw)
+        self.steps.append(("conv", args))
+        if out_name is not None:
+            self.out_slots.setdefault(out_name, []).append(args)
+
+    def call(self, fn, *a):
+        self.steps.append(("call", fn, a))
+
+
+class _KP2DTinyBase(nn.Module):
+    version = 0
+
+    # --- shared constructor tail ---------------------------------------------------------------
+    def _finish_init(self):
+        self.cell = pow(2, self.downsample)  # kp2dtiny.py:455
+        self.cross_ratio = 2.0  # :339
+        self.global_desc_dim = self.vlad_head.global_desc_dim
+        self.training = True  # the reference leaves construction in "training" (:456); callers set False
+        self._packed = None
+        self._packed_key = None
+        self._plans: Dict = {}
+        if self.downsample != 2:
+            raise NotImplementedError("downsample != 2 (config letters D/F cell 8) is listed under SURVEY §8(f)")
+        if self.upscale_method != "pixelshuffle":
+            raise NotImplementedError("upscale_method='convtranspose' (to_mcu) is MCU-export only (SURVEY §2 #2)")
+        if self.depth:
+            raise NotImplementedError("depth heads are outside the hot path (SURVEY §8(f))")
+        self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
+
+    # --- reference API ------------------------------------------------------------------------
+    def gather_info(self):  # kp2dtiny.py:463-485
+        params = inspect.signature(self.__init__).parameters
+        init_args = {n: getattr(self, n) for n in params.keys() if hasattr(self, n)}
+        total = sum(p.numel() for p in self.parameters())
+        train = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return {"init_args": init_args, "total_params": total, "trainable_params": train,
+                "netvlad_dim": self.global_desc_dim, "upscale_method": self.upscale_method,
+                "leaky_relu": self.leaky_relu, "use_attention": self.use_attention}
+
+    def get_global_desc_dim(self):
+        return self.global_desc_dim
+
+    def get_netvlad_dim(self):
+        return self.global_desc_dim
+
+    def get_num_clusters(self):
+        return self.vlad_head.netvlad.num_clusters
+
+    def init_netvlad(self, clsts, traindescs):
+        self.vlad_head.netvlad.init_params(clsts, traindescs)
+        self._invalidate()
+
+    def freeze_backbone(self):
+        for p in self.backbone.parameters():
+            p.requires_grad = False
+
+    def freeze_segmentation(self, except_last_layer=False):
+        self.seg_head.freeze(except_last_layer)
+
+    def fuse(self):
+        """Reference: torch.quantization.fuse_modules for PTQ (kp2dtiny.py:507-513).  BatchNorm is always
+        folded at pack time here, so this is a no-op kept for API compatibility."""
+        return None
+
+    # --- cache handling -----------------------------------------------------------------------
+    def _invalidate(self):
+        self._packed = None
+        self._plans = {}
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return r
+
+    def repack(self):
+        """Call after editing parameters in place (load_state_dict / .to() are tracked automatically)."""
+        self._invalidate()
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def _ensure_packed(self, device):
+        key = self._param_key()
+        if self._packed is None or self._packed_key != key:
+            first = next(self.parameters())
+            if first.device != device:
+                raise NanovsError(f"model parameters are on {first.device} but the input is on {device}; "
+                                  "call model.to(device) first")
+            with torch.no_grad():
+                self._packed = self._pack()
+            self._packed_key = key
+            self._plans = {}
+        return self._packed
+
+    def _pk_block(self, m: _ConvBnAct):
+        bn = {"weight": m.bn.weight, "bias": m.bn.bias, "running_mean": m.bn.running_mean,
+              "running_var": m.bn.running_var}
+        return ops.pack_conv(m.conv.weight, bn=bn, eps=m.bn.eps)
+
+    @staticmethod
+    def _pk_conv(m: nn.Conv2d, s2d=False):
+        return ops.pack_conv(m.weight, bias=m.bias, s2d=s2d)
+
+    def _pack_att(self, m: _AttModule):
+        f, g = m.att.fn, m.mff.fn.net
+        return {
+            "ln1": (m.att.norm.g.detach().reshape(-1).contiguous(), m.att.norm.b.detach().reshape(-1).contiguous()),
+            "q": self._pk_conv(f.to_q), "kv": self._pk_conv(f.to_kv, s2d=True), "out": self._pk_conv(f.to_out),
+            "ln2": (m.mff.norm.g.detach().reshape(-1).contiguous(), m.mff.norm.b.detach().reshape(-1).contiguous()),
+            "m0": self._pk_conv(g[0]),
+            "dw": (g[1].net[0].weight.detach().reshape(-1, 9).contiguous(), g[1].net[0].bias.detach().contiguous()),
+            "pw": self._pk_conv(g[1].net[1]), "m3": self._pk_conv(g[3]), "heads": f.heads,
+        }
+
+    def _pack(self) -> dict:
+        P = {}
+        bb = self.backbone
+        for n in ("conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"):
+            P["bb." + n] = self._pk_block(getattr(bb, n))
+        sh = self.seg_head
+        for i, m in enumerate(sh.convs):
+            if isinstance(m, _ConvBnAct):
+                P[f"seg.{i}"] = self._pk_block(m)
+            elif isinstance(m, _AttModule):
+                P[f"seg.{i}"] = self._pack_att(m)
+            else:
+                P[f"seg.{i}"] = self._pk_conv(m)
+        vh = self.vlad_head
+        for n in ("convlad1", "convlad2", "convlad3"):
+            P["vlad." + n] = self._pk_block(getattr(vh, n))
+        if not vh.remove_netvlad:
+            nv = vh.netvlad
+            P["vlad.assign"] = nv.conv.weight.detach().reshape(nv.num_clusters, nv.dim).contiguous().float()
+            P["vlad.cent"] = nv.centroids.detach().contiguous().float()
+        self._pack_heads(P)
+        return P
+
+    # --- forward --------------------------------------------------------------------------------
+    def _check_input(self, x):
+        if self.training is not False:
+            raise NanovsError("nano_vs_slam_b200 is inference only: call model.eval() and set model.training = False "
+                              "as the reference callers do (eval_multitask.py:195-196, frontend.py:56-58)")
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected a (B,3,H,W) tensor")
+        if not x.is_cuda:
+            raise NanovsError("input must be a CUDA tensor: the sm_100a kernels are the only implementation")
+        B, _, H, W = x.shape
+        if (H // 2) % 4 != 0 or (W // 2) % 4 != 0:
+            # the reference fails in torch.cat when pool/pixel-shuffle sizes disagree
+            raise RuntimeError(f"input {H}x{W}: floor(H/2) and floor(W/2) must be multiples of 4 "
+                               "(pixel-shuffle/skip concat sizes would differ, as in the reference)")
+        return x.contiguous().float()
+
+    @torch.no_grad()
+    def forward(self, x):
+        """Returns {'score','coord','feat','vlad','seg'} like kp2dtiny.py:552-591 / :906-957."""
+        x = self._check_input(x)
+        B, _, H, W = x.shape
+        self._ensure_packed(x.device)
+        key = (B, H, W, x.device)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:
+                self._plans.clear()
+            plan = self._plans[key] = _Plan(self, B, H, W, x.device)
+        return self._run(plan, x)
+
+    def _run(self, plan: _Plan, x: torch.Tensor):
+        dev = x.device
+        outs = {}
+        for name, shape in plan.out_shapes.items():
+            outs[name] = torch.empty(shape, device=dev, dtype=torch.float32)
+            for a in plan.out_slots.get(name, []):
+                a.dst = outs[name].data_ptr()
+        plan.in_args.src0 = x.data_ptr()
+        run_conv = ops.run_conv
+        for st in plan.steps:
+            if st[0] == "conv":
+                run_conv(st[1])
+            else:
+                st[1](outs, *st[2])
+        result = {"score": outs["score"], "coord": outs["coord"], "feat": outs["feat"]}
+        if "vlad" in outs:
+            result["vlad"] = outs["vlad"]
+        else:
+            result["vlad"] = plan.bufs["v3"].clone()  # remove_netvlad: raw encoder map (vpr.py:83-89)
+        result["seg"] = outs["seg"]
+        # keep x alive until the kernels that read it have been enqueued (they have: stream ordered)
+        return result
+
+    # --- plan construction ------------------------------------------------------------------------
+    def _build_plan(self, pl: _Plan):
+        P = self._packed
+        B, H, W = pl.B, pl.H, pl.W
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        act = ops.ACT_LRELU if self.leaky_relu else ops.ACT_RELU
+        H2, W2 = H // 2, W // 2
+        H4, W4 = H2 // 2, W2 // 2
+        H8, W8 = H4 // 2, W4 // 2
+        nf, ncls = self.nfeatures, self.nClasses
+        pl.out_shapes = {"score": (B, 1, H4, W4), "coord": (B, 2, H4, W4), "feat": (B, nf, H2, W2),
+                         "seg": (B, ncls, H2, W2)}
+
+        # ---- backbone (modules/encoders.py:105-129) ----
+        xin = torch.empty(B, 3, H, W, device=pl.device)  # shape carrier; pointer patched per call
+        t1a = pl.buf("t1a", c1, H, W)
+        pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a)
+        pl.in_args = pl.steps[-1][1]
+        p1 = pl.buf("p1", c2, H2, W2)
+        pl.conv(P["bb.conv1b"], t1a, c2, act=act, out_mode=ops.OUT_POOL, dst2=p1)
+        t2a = pl.buf("t2a", c2, H2, W2)
+        pl.conv(P["bb.conv2a"], p1, c2, act=act, dst=t2a)
+        t2b = pl.buf("t2b", c3, H2, W2)
+        pl.conv(P["bb.conv2b"], t2a, c3, act=act, dst=t2b)
+        t3a = pl.buf("t3a", c3, H2, W2)
+        pl.conv(P["bb.conv3a"], t2b, c3, act=act, dst=t3a)
+        skip = pl.buf("skip", c4, H2, W2)
+        p3 = pl.buf("p3", c4, H4, W4)
+        pl.conv(P["bb.conv3b"], t3a, c4, act=act, out_mode=ops.OUT_BOTH, dst=skip, dst2=p3)
+        t4a = pl.buf("t4a", c4, H4, W4)
+        pl.conv(P["bb.conv4a"], p3, c4, act=act, dst=t4a)
+        xb = pl.buf("xb", c4, H4, W4)
+        pl.conv(P["bb.conv4b"], t4a, c4, act=act, dst=xb)
+
+        # ---- keypoint / descriptor heads (version specific) ----
+        self._plan_heads(pl, xb, skip, act)
+
+        # ---- segmentation trunk (modules/decoders/segmentation.py) ----
+        s0 = pl.buf("s0", c5, H4, W4)
+        pl.conv(P["seg.0"], xb, c5, act=act, dst=s0)
+        sp3 = pl.buf("sp3", c5, H8, W8)
+        if self.use_attention:
+            sp = pl.buf("sp", c5, H8, W8)
+            self._plan_att(pl, P["seg.1"], s0, c5, H4, W4, "a1", pooled_out=sp)
+            self._plan_att(pl, P["seg.2"], sp, c5, H8, W8, "a2", plain_out=sp3)
+            nxt = 3
+        else:
+            sp = pl.buf("sp", c5, H8, W8)
+            pl.conv(P["seg.1"], s0, c5, act=act, out_mode=ops.OUT_POOL, dst2=sp)
+            s2 = pl.buf("s2", c5, H8, W8)
+            pl.conv(P["seg.2"], sp, c5, act=act, dst=s2)
+            pl.conv(P["seg.3"], s2, c5, act=act, dst=sp3)
+            nxt = 4
+        ps1 = pl.buf("ps1", d1 // 4, H4, W4)
+        pl.conv(P[f"seg.{nxt}"], sp3, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps1)
+        s5 = pl.buf("s5", c5, H4, W4)
+        pl.conv(P[f"seg.{nxt + 1}"], ps1, c5, act=act, src1=xb, dst=s5)
+        ps2 = pl.buf("ps2", d1 // 4, H2, W2)
+        pl.conv(P[f"seg.{nxt + 2}"], s5, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps2)
+        s7 = pl.buf("s7", c5, H2, W2)
+        pl.conv(P[f"seg.{nxt + 3}"], ps2, c5, act=act, src1=skip, dst=s7)
+        self._plan_seg_out(pl, s7, P[f"seg.{nxt + 4}"])
+
+        # ---- VPR head (modules/decoders/vpr.py:78-89) ----
+        enc = self.encoder_dim
+        v1 = pl.buf("v1", enc, H4, W4)
+        pl.conv(P["vlad.convlad1"], xb, enc, act=act, dst=v1)
+        v2 = pl.buf("v2", enc, H4, W4)
+        pl.conv(P["vlad.convlad2"], v1, enc, act=act, dst=v2)
+        v3 = pl.buf("v3", enc, H4, W4)
+        pl.conv(P["vlad.convlad3"], v2, enc, act=act, dst=v3)
+        if not self.vlad_head.remove_netvlad:
+            K = self.vlad_head.netvlad.num_clusters
+            pl.out_shapes["vlad"] = (B, K * enc)
+            ws = torch.empty(ops.netvlad_workspace_bytes(B, enc, K, H4 * W4), dtype=torch.uint8, device=pl.device)
+            pl.bufs["vlad_ws"] = ws
+            pl.call(lambda outs, v3=v3, ws=ws: ops.netvlad(v3, P["vlad.assign"], P["vlad.cent"], out=outs["vlad"],
+                                                           workspace=ws))
+
+    def _plan_att(self, pl: _Plan, A: dict, x: torch.Tensor, C: int, h: int, w: int, tag: str,
+                  pooled_out: Optional[torch.Tensor] = None, plain_out: Optional[torch.Tensor] = None):
+        """SegFormerAttentionModule (modules/segformer.py:209-220): LN -> q / kv -> attention -> to_out ->
+        LN -> 1x1 -> dw3x3 -> 1x1 -> GELU -> 1x1.  No residual adds."""
+        ln1 = pl.buf(tag + ".ln1", C, h, w)
+        pl.call(lambda outs: ops.channel_layernorm(x, A["ln1"][0], A["ln1"][1], 1e-5, out=ln1))
+        q = pl.buf(tag + ".q", C, h, w)
+        pl.conv(A["q"], ln1, C, ksize=1, dst=q)
+        kv = pl.buf(tag + ".kv", 2 * C, h // 2, w // 2)
+        pl.conv(A["kv"], ln1, 2 * C, ksize=1, in_mode=ops.IN_S2D, dst=kv)
+        at = pl.buf(tag + ".att", C, h, w)
+        pl.call(lambda outs: ops.attention(q, kv, A["heads"], out=at))
+        ao = pl.buf(tag + ".ao", C, h, w)
+        pl.conv(A["out"], at, C, ksize=1, dst=ao)
+        ln2 = pl.buf(tag + ".ln2", C, h, w)
+        pl.call(lambda outs: ops.channel_layernorm(ao, A["ln2"][0], A["ln2"][1], 1e-5, out=ln2))
+        m0 = pl.buf(tag + ".m0", 2 * C, h, w)
+        pl.conv(A["m0"], ln2, 2 * C, ksize=1, dst=m0)
+        m1 = pl.buf(tag + ".m1", 2 * C, h, w)
+        pl.call(lambda outs: ops.dwconv3x3(m0, A["dw"][0], A["dw"][1], out=m1))
+        m2 = pl.buf(tag + ".m2", 2 * C, h, w)
+        pl.conv(A["pw"], m1, 2 * C, ksize=1, act=ops.ACT_GELU, dst=m2)
+        if pooled_out is not None:
+            pl.conv(A["m3"], m2, C, ksize=1, out_mode=ops.OUT_POOL, dst2=pooled_out)
+        else:
+            pl.conv(A["m3"], m2, C, ksize=1, dst=plain_out)
+
+    # --- post_processing (kp2dtiny.py:593-647 / :959-1015) ------------------------------------------
+    @torch.no_grad()
+    def post_processing(self, out, H, W):
+        score, shift, feat = out["score"], out["coord"], out["feat"]
+        if not score.is_cuda:
+            raise NanovsError("post_processing needs CUDA tensors (no CPU fallback)")
+        sample = self.training is False
+        o_s, o_c, o_f = ops.decode(score, shift, feat if sample else None, H, W, self.cell, self.cross_ratio)
+        if sample:
+            seg = out["seg"]
+            # V2: argmax(softmax(logits)) == argmax(logits); V3: forward already returned probabilities
+            out["seg"] = ops.seg_argmax(seg, o_c if self.sample_segmentation else None, H, W)
+            out["feat"] = o_f
+        else:
+            out["feat"] = feat
+        out["coord"] = o_c
+        out["score"] = o_s
+        return out
+
+    def only_encoder(self, x):
+        """L2-normalised VPR encoder map (kp2dtiny.py:515-518, vpr.py:85-86)."""
+        x = self._check_input(x)
+        self.forward(x)
+        plan = self._plans[(x.shape[0], x.shape[2], x.shape[3], x.device)]
+        return ops.l2norm_channels(plan.bufs["v3"])
+
+
+class KP2DTinyV2(_KP2DTinyBase):
+    """Dedicated-decoder model (kp2dtiny.py:284-647)."""
+
+    version = 2
+
+    def __init__(self, nfeatures=256, device="cpu", channel_dims=[32, 64, 128, 256, 256, 512], bn_momentum=0.1,
+                 nClasses=8, num_clusters=64, downsample=3, use_attention=False, mem_efficient=False,
+                 upscale_method="pixelshuffle", remove_netvlad=False, leaky_relu=True, depth=False,
+                 encoder_dim=None, global_descriptor_method="netvlad", **kwargs):
+        super().__init__()
+        self.device = device
+        self.with_drop = True
+        self.nfeatures, self.downsample, self.nClasses = nfeatures, downsample, nClasses
+        self.sample_segmentation = False
+        self.use_attention, self.leaky_relu = use_attention, leaky_relu
+        self.remove_netvlad, self.upscale_method, self.depth = remove_netvlad, upscale_method, depth
+        self.num_clusters, self.global_descriptor_method = num_clusters, global_descriptor_method
+        self.mem_efficient = mem_efficient  # same math, same keys (netvlad.py:110-197): one kernel serves both
+        self.bn_momentum = bn_momentum
+        self.channel_dims = list(channel_dims)
+        c1, c2, c3, c4, c5, d1 = channel_dims
+        self.encoder_dim = encoder_dim if encoder_dim is not None else c4
+        self.backbone = _BackBone(3, c1, c2, c3, c4, bn_momentum)
+        self.score_head = _TaskHead(c4, c4, 1, bn_momentum)
+        self.loc_head = _TaskHead(c4, c4, 2, bn_momentum)
+        self.desc_head = _UpscaleHead(c4, c4, c3 * 4, c3 + c4, c4, nfeatures, bn_momentum)
+        self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention)
+        self.vlad_head = _VPRHead(c4, self.encoder_dim, num_clusters, bn_momentum, remove_netvlad,
+                                  global_descriptor_method)
+        self._finish_init()
+
+    def _pack_heads(self, P):
+        P["score.a"] = self._pk_block(self.score_head.convDa)
+        P["score.b"] = self._pk_conv(self.score_head.convDb)
+        P["loc.a"] = self._pk_block(self.loc_head.convDa)
+        P["loc.b"] = self._pk_conv(self.loc_head.convDb)
+        d = self.desc_head
+        P["desc.A"] = self._pk_block(d.convA)
+        P["desc.B"] = self._pk_conv(d.convB)
+        P["desc.Aa"] = self._pk_block(d.confAa)
+        P["desc.Bb"] = self._pk_conv(d.confBb)
+
+    def _plan_heads(self, pl, xb, skip, act):
+        P = self._packed
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        B, _, H4, W4 = xb.shape
+        H2, W2 = skip.shape[2:]
+        sh = pl.buf("sh", c4, H4, W4)
+        pl.conv(P["score.a"], xb, c4, act=act, dst=sh)
+        pl.conv(P["score.b"], sh, 1, act=ops.ACT_SIGMOID, dst=torch.empty(B, 1, H4, W4, device=pl.device),
+                out_name="score")
+        lh = pl.buf("lh", c4, H4, W4)
+        pl.conv(P["loc.a"], xb, c4, act=act, dst=lh)
+        pl.conv(P["loc.b"], lh, 2, act=ops.ACT_TANH, dst=torch.empty(B, 2, H4, W4, device=pl.device),
+                out_name="coord")
+        # UpscaleHead (heads.py:91-104): convB's epilogue writes the pixel-shuffled map; confAa reads
+        # [shuffled | skip] as two sources, so torch.cat is never materialised.
+        da = pl.buf("da", c4, H4, W4)
+        pl.conv(P["desc.A"], xb, c4, act=act, dst=da)
+        dps = pl.buf("dps", c3, H2, W2)
+        pl.conv(P["desc.B"], da, 4 * c3, out_mode=ops.OUT_SHUFFLE, dst=dps)
+        dA = pl.buf("dA", c4, H2, W2)
+        pl.conv(P["desc.Aa"], dps, c4, act=act, src1=skip, dst=dA)
+        pl.conv(P["desc.Bb"], dA, self.nfeatures, dst=torch.empty(B, self.nfeatures, H2, W2, device=pl.device),
+                out_name="feat")
+
+    def _plan_seg_out(self, pl, s7, packed_last):
+        B, _, H2, W2 = s7.shape
+        pl.conv(packed_last, s7, self.nClasses, dst=torch.empty(B, self.nClasses, H2, W2, device=pl.device),
+                out_name="seg")
+
+
+class KP2DTinyV3(_KP2DTinyBase):
+    """Decoder-fusion model (kp2dtiny.py:650-1015): one score+loc head, descriptors from the seg trunk."""
+
+    version = 3
+
+    def __init__(self, use_color=True, do_cross=True, with_drop=True, nfeatures=256, device="cpu",
+                 channel_dims=[32, 64, 128, 256, 256, 512], bn_momentum=0.1, nClasses=8, num_clusters=64,
+                 downsample=3, use_attention=False, encoder_dim=None, mem_efficient=False,
+                 upscale_method="pixelshuffle", remove_netvlad=False, leaky_relu=True, remove_softmax=False,
+                 depth=False, global_descriptor_method="netvlad", **kwargs):
+        super().__init__()
+        if not use_color:
+            raise NotImplementedError("use_color=False (1-channel input) is not on the hot path")
+        self.device = device
+        self.with_drop = with_drop
+        self.nfeatures, self.downsample, self.nClasses = nfeatures, downsample, nClasses
+        self.sample_segmentation = False
+        self.use_color, self.do_cross, self.fuse_score_loc = use_color, do_cross, True
+        self.remove_softmax, self.depth = remove_softmax, depth
+        self.use_attention, self.leaky_relu = use_attention, leaky_relu
+        self.remove_netvlad, self.upscale_method = remove_netvlad, upscale_method
+        self.num_clusters, self.global_descriptor_method = num_clusters, global_descriptor_method
+        self.mem_efficient = mem_efficient
+        self.bn_momentum = bn_momentum
+        self.channel_dims = list(channel_dims)
+        c1, c2, c3, c4, c5, d1 = channel_dims
+        self.encoder_dim = encoder_dim if encoder_dim is not None else c4
+        self.backbone = _BackBone(3, c1, c2, c3, c4, 0.1)
+        self.score_loc_head = _TaskHead(c4, c4, 3, bn_momentum)
+        self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention, n_feat=nfeatures)
+        self.vlad_head = _VPRHead(c4, self.encoder_dim, num_clusters, bn_momentum, remove_netvlad,
+                                  global_descriptor_method)
+        self._finish_init()
+
+    def _pack_heads(self, P):
+        h = self.score_loc_head
+        P["sl.a"] = self._pk_block(h.convDa)
+        # convDb (c4 -> 3) is launched as two tiny convs so that score (ch 0, sigmoid) and shift (ch 1:3, tanh)
+        # land directly in their own output tensors (kp2dtiny.py:927-935) without a slicing copy.
+        P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
+        P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
+        P["featB"] = self._pk_conv(self.seg_head.featB)
+
+    def _plan_heads(self, pl, xb, skip, act):
+        P = self._packed
+        c4 = self.channel_dims[3]
+        B, _, H4, W4 = xb.shape
+        sl = pl.buf("sl", c4, H4, W4)
+        pl.conv(P["sl.a"], xb, c4, act=act, dst=sl)
+        pl.conv(P["sl.score"], sl, 1, act=ops.ACT_SIGMOID, dst=torch.empty(B, 1, H4, W4, device=pl.device),
+                out_name="score")
+        pl.conv(P["sl.shift"], sl, 2, act=ops.ACT_TANH, dst=torch.empty(B, 2, H4, W4, device=pl.device),
+                out_name="coord")
+
+    def _plan_seg_out(self, pl, s7, packed_last):
+        # segmentation.py:337-347 / :609-619: feat from the first half of the trunk, seg from the last half
+        B, c5, H2, W2 = s7.shape
+        ds = self.seg_head.dim_split
+        pl.conv(self._packed["featB"], s7, self.nfeatures, c0_off=0, c0=ds,
+                dst=torch.empty(B, self.nfeatures, H2, W2, device=pl.device), out_name="feat")
+        if self.remove_softmax:
+            pl.conv(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds,
+                    dst=torch.empty(B, self.nClasses, H2, W2, device=pl.device), out_name="seg")
+        else:
+            logits = pl.buf("seg_logits", self.nClasses, H2, W2)
+            pl.conv(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds, dst=logits)
+            pl.call(lambda outs: ops.softmax_channels(logits, out=outs["seg"]))  # Softmax2d (:942-943)

@@ -1,0 +1,321 @@
+"""Tensor-level wrappers over the C ABI (device pointers + current stream in, nothing else).
+
+PyTorch is plumbing here: it owns device memory and the stream; every function hands raw pointers to
+libnanovs.so.  CUDA tensors only -- there is deliberately no CPU implementation behind these calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMOID_TANH, ACT_TANH,  # noqa: F401
+                    IN_PLAIN, IN_S2D, OUT_BOTH, OUT_PLAIN, OUT_POOL, OUT_SHUFFLE, NvsConvArgs, check, lib)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _cabi.NanovsError("nanovs ops need CUDA tensors (no CPU fallback by design)")
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (done once per model, see kp2dtiny._Packed)
+# ----------------------------------------------------------------------------------------------
+def conv_cout_tile(cout: int) -> int:
+    return lib().nvs_conv_cout_tile(cout)
+
+
+def conv_cin_chunk(cin: int) -> int:
+    return lib().nvs_conv_cin_chunk(cin)
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
+              s2d: bool = False, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """OIHW conv weight (+ optional BatchNorm running stats) -> kernel layout.
+
+    Returns (w_packed [cin_pad][k*k][cout_pad], b_packed [cout_pad]) on the weight's device, fp32.
+    BN(eval) y = (conv - mean) * gamma / sqrt(var + eps) + beta is folded as
+    w' = w * s, b' = beta - mean * s with s = gamma / sqrt(var + eps)   (modules/base.py:42-43).
+    ``s2d``: a 2x2 stride-2 kernel becomes a 1x1 kernel over 4*cin space-to-depth channels
+    (virtual channel ci*4 + ky*2 + kx), modules/segformer.py:93-95.
+    """
+    w = weight.detach().to(torch.float64)
+    cout, cin, kh, kw = w.shape
+    if bn is not None:
+        s = bn["weight"].detach().double() / torch.sqrt(bn["running_var"].detach().double() + eps)
+        w = w * s.view(-1, 1, 1, 1)
+        b = bn["bias"].detach().double() - bn["running_mean"].detach().double() * s
+    elif bias is not None:
+        b = bias.detach().double()
+    else:
+        b = torch.zeros(cout, dtype=torch.float64, device=w.device)
+    if s2d:
+        assert kh == 2 and kw == 2
+        w = w.permute(1, 2, 3, 0).reshape(cin * 4, 1, cout)
+        cin, taps = cin * 4, 1
+    else:
+        assert kh == kw and kh in (1, 3)
+        taps = kh * kw
+        w = w.permute(1, 2, 3, 0).reshape(cin, taps, cout)
+    ck, ct = conv_cin_chunk(cin), conv_cout_tile(cout)
+    cin_pad, cout_pad = _round_up(cin, ck), _round_up(cout, ct)
+    wp = torch.zeros(cin_pad, taps, cout_pad, dtype=torch.float32, device=w.device)
+    wp[:cin, :, :cout] = w.to(torch.float32)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bp[:cout] = b.to(torch.float32)
+    return wp.contiguous(), bp.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# conv
+# ----------------------------------------------------------------------------------------------
+def make_conv_args(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout: int, *, ksize: int = 3,
+                   act: int = ACT_NONE, out_mode: int = OUT_PLAIN, in_mode: int = IN_PLAIN,
+                   src1: Optional[torch.Tensor] = None, dst: Optional[torch.Tensor] = None,
+                   dst2: Optional[torch.Tensor] = None, c0_off: int = 0, c0: Optional[int] = None,
+                   c1_off: int = 0, c1: Optional[int] = None, dst_c_off: int = 0, dst2_c_off: int = 0
+                   ) -> NvsConvArgs:
+    """Fill an NvsConvArgs for (B, C, H, W) tensors; shapes are validated here, once, at plan time."""
+    B, c0_total, inH, inW = src0.shape
+    c0 = c0_total - c0_off if c0 is None else c0
+    if in_mode == IN_S2D:
+        H, W = inH // 2, inW // 2
+    else:
+        H, W = inH, inW
+    a = NvsConvArgs()
+    a.src0, a.weight, a.bias = src0.data_ptr(), wp.data_ptr(), bp.data_ptr()
+    a.c0_total, a.c0_off, a.c0 = c0_total, c0_off, c0
+    if src1 is not None:
+        assert src1.shape[0] == B and tuple(src1.shape[2:]) == (inH, inW), (src0.shape, src1.shape)
+        a.src1 = src1.data_ptr()
+        a.c1_total, a.c1_off = src1.shape[1], c1_off
+        a.c1 = src1.shape[1] - c1_off if c1 is None else c1
+    else:
+        a.src1, a.c1_total, a.c1_off, a.c1 = None, 0, 0, 0
+    cin = (4 * c0) if in_mode == IN_S2D else (c0 + a.c1)
+    assert wp.shape[0] == _round_up(cin, conv_cin_chunk(cin)), (wp.shape, cin)
+    assert wp.shape[1] == ksize * ksize and wp.shape[2] == _round_up(cout, conv_cout_tile(cout))
+    if out_mode in (OUT_PLAIN, OUT_BOTH):
+        assert dst is not None and tuple(dst.shape[2:]) == (H, W) and dst.shape[0] == B
+        assert dst.shape[1] >= dst_c_off + cout
+    if out_mode == OUT_SHUFFLE:
+        assert dst is not None and tuple(dst.shape[2:]) == (2 * H, 2 * W) and dst.shape[1] >= dst_c_off + cout // 4
+    if out_mode in (OUT_POOL, OUT_BOTH):
+        assert dst2 is not None and tuple(dst2.shape[2:]) == (H // 2, W // 2)
+        assert dst2.shape[1] >= dst2_c_off + cout
+    a.dst = _ptr(dst)
+    a.dst2 = _ptr(dst2)
+    a.dst_c_total = dst.shape[1] if dst is not None else 0
+    a.dst_c_off = dst_c_off
+    a.dst2_c_total = dst2.shape[1] if dst2 is not None else 0
+    a.dst2_c_off = dst2_c_off
+    a.B, a.H, a.W, a.in_H, a.in_W = B, H, W, inH, inW
+    a.cout, a.ksize, a.act, a.out_mode, a.in_mode = cout, ksize, act, out_mode, in_mode
+    return a
+
+
+def run_conv(args: NvsConvArgs) -> None:
+    check(lib().nvs_conv(C.byref(args), _stream()), "nvs_conv")
+
+
+def conv(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout: int, **kw):
+    """Allocate outputs and run one conv (unit tests / ad-hoc use; the model uses cached plans)."""
+    src0 = _req(src0)
+    if kw.get("src1") is not None:
+        kw["src1"] = _req(kw["src1"])
+    B, _, inH, inW = src0.shape
+    in_mode, out_mode = kw.get("in_mode", IN_PLAIN), kw.get("out_mode", OUT_PLAIN)
+    H, W = (inH // 2, inW // 2) if in_mode == IN_S2D else (inH, inW)
+    dst = dst2 = None
+    if out_mode in (OUT_PLAIN, OUT_BOTH):
+        dst = torch.empty(B, cout, H, W, device=src0.device, dtype=torch.float32)
+    if out_mode == OUT_SHUFFLE:
+        dst = torch.empty(B, cout // 4, 2 * H, 2 * W, device=src0.device, dtype=torch.float32)
+    if out_mode in (OUT_POOL, OUT_BOTH):
+        dst2 = torch.empty(B, cout, H // 2, W // 2, device=src0.device, dtype=torch.float32)
+    run_conv(make_conv_args(src0, wp, bp, cout, dst=dst, dst2=dst2, **kw))
+    if out_mode == OUT_BOTH:
+        return dst, dst2
+    return dst2 if out_mode == OUT_POOL else dst
+
+
+# ----------------------------------------------------------------------------------------------
+# small ops
+# ----------------------------------------------------------------------------------------------
+def dwconv3x3(x, w, b, out=None):
+    x = _req(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nvs_dwconv3x3(x.data_ptr(), w.data_ptr(), _ptr(b), out.data_ptr(), B, Cc, H, W, _stream()),
+          "nvs_dwconv3x3")
+    return out
+
+
+def channel_layernorm(x, g, b, eps: float = 1e-5, out=None):
+    x = _req(x)
+    B, Cc = x.shape[:2]
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nvs_channel_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), B, Cc,
+                                      x[0, 0].numel(), eps, _stream()), "nvs_channel_layernorm")
+    return out
+
+
+def softmax_channels(x, out=None):
+    x = _req(x)
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nvs_softmax_channels(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x[0, 0].numel(),
+                                     _stream()), "nvs_softmax_channels")
+    return out
+
+
+def l2norm_channels(x, out=None):
+    x = _req(x)
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nvs_l2norm_channels(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x[0, 0].numel(),
+                                    _stream()), "nvs_l2norm_channels")
+    return out
+
+
+def attention(q, kv, heads: int, out=None):
+    """q (B,C,h,w), kv (B,2C,hk,wk) -> (B,C,h,w)  (modules/segformer.py:113-133)."""
+    q, kv = _req(q), _req(kv)
+    B, Cc = q.shape[:2]
+    out = torch.empty_like(q) if out is None else out
+    check(lib().nvs_attention(q.data_ptr(), kv.data_ptr(), out.data_ptr(), B, Cc, heads, q[0, 0].numel(),
+                              kv[0, 0].numel(), _stream()), "nvs_attention")
+    return out
+
+
+def netvlad_workspace_bytes(B: int, Cc: int, K: int, S: int) -> int:
+    return int(lib().nvs_netvlad_workspace_bytes(B, Cc, K, S))
+
+
+def netvlad(x, w_assign, centroids, out=None, workspace=None):
+    """x (B,C,h,w) -> (B, K*C)  (modules/aggregators/netvlad.py:79-106)."""
+    x = _req(x)
+    B, Cc = x.shape[:2]
+    S = x[0, 0].numel()
+    K = centroids.shape[0]
+    nbytes = netvlad_workspace_bytes(B, Cc, K, S)
+    if workspace is None:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty(B, K * Cc, device=x.device, dtype=torch.float32) if out is None else out
+    check(lib().nvs_netvlad(x.data_ptr(), w_assign.data_ptr(), centroids.data_ptr(), out.data_ptr(),
+                            workspace.data_ptr(), workspace.numel(), B, Cc, K, S, _stream()), "nvs_netvlad")
+    return out
+
+
+def decode(score, shift, feat, H: int, W: int, cell: int, cross_ratio: float = 2.0):
+    """post_processing core (kp2dtiny.py:593-631): returns (score_masked, coord_px, feat_sampled_unit)."""
+    score, shift = _req(score), _req(shift)
+    B, _, Hc, Wc = score.shape
+    o_s = torch.empty_like(score)
+    o_c = torch.empty_like(shift)
+    if feat is not None:
+        feat = _req(feat)
+        D, Hf, Wf = feat.shape[1:]
+        o_f = torch.empty(B, D, Hc, Wc, device=score.device, dtype=torch.float32)
+    else:
+        D = Hf = Wf = 0
+        o_f = None
+    check(lib().nvs_decode(score.data_ptr(), shift.data_ptr(), _ptr(feat), o_s.data_ptr(), o_c.data_ptr(),
+                           _ptr(o_f), B, Hc, Wc, D, Hf, Wf, H, W, cell, float(cross_ratio), _stream()),
+          "nvs_decode")
+    return o_s, o_c, o_f
+
+
+def seg_argmax(seg, coord=None, H: int = 0, W: int = 0):
+    """argmax over classes -> int64 (B,1,h,w); with ``coord`` nearest-sampled at keypoints first."""
+    seg = _req(seg)
+    B, Cc, Hs, Ws = seg.shape
+    if coord is not None:
+        coord = _req(coord)
+        Hc, Wc = coord.shape[2:]
+        out = torch.empty(B, 1, Hc, Wc, device=seg.device, dtype=torch.int64)
+    else:
+        Hc = Wc = 0
+        out = torch.empty(B, 1, Hs, Ws, device=seg.device, dtype=torch.int64)
+    check(lib().nvs_seg_argmax(seg.data_ptr(), _ptr(coord), out.data_ptr(), B, Cc, Hs, Ws, Hc, Wc, H, W,
+                               _stream()), "nvs_seg_argmax")
+    return out
+
+
+def select_keypoints(score, coord, feat, thresh: float, top_k: int, seg_cells=None,
+                     classes_to_filter: Optional[Sequence[int]] = None):
+    """Device version of frontend.py:94-126 for a whole batch.
+
+    score (B,1,Hc,Wc), coord (B,2,Hc,Wc), feat (B,D,Hc,Wc) [, seg_cells (B,1,Hc,Wc) int64]
+    -> dict(pts (B,k,2), desc (B,k,D), score (B,k), cell (B,k) int32, label (B,k) int64|None, count (B,) int32)
+    Rows >= count[b] are unspecified.
+    """
+    score, coord = _req(score), _req(coord)
+    B = score.shape[0]
+    n_cells = score[0].numel()
+    k = n_cells if top_k <= 0 else min(top_k, n_cells)
+    dev = score.device
+    D = 0
+    if feat is not None:
+        feat = _req(feat)
+        D = feat.shape[1]
+    pts = torch.empty(B, k, 2, device=dev, dtype=torch.float32)
+    desc = torch.empty(B, k, D, device=dev, dtype=torch.float32) if feat is not None else None
+    sc = torch.empty(B, k, device=dev, dtype=torch.float32)
+    cell = torch.empty(B, k, device=dev, dtype=torch.int32)
+    count = torch.empty(B, device=dev, dtype=torch.int32)
+    label = filt = None
+    if seg_cells is not None:
+        seg_cells = _req(seg_cells, torch.int64)
+        assert seg_cells[0].numel() == n_cells, "seg labels must be per cell (sample_segmentation=True)"
+        label = torch.empty(B, k, device=dev, dtype=torch.int64)
+        if classes_to_filter:
+            filt = torch.tensor(list(classes_to_filter), device=dev, dtype=torch.int32)
+    check(lib().nvs_select_keypoints(score.data_ptr(), coord.data_ptr(), _ptr(feat), _ptr(seg_cells), _ptr(filt),
+                                     0 if filt is None else filt.numel(), float(thresh), k, pts.data_ptr(),
+                                     _ptr(desc), sc.data_ptr(), cell.data_ptr(), _ptr(label), count.data_ptr(),
+                                     B, n_cells, D, _stream()), "nvs_select_keypoints")
+    return {"pts": pts, "desc": desc, "score": sc, "cell": cell, "label": label, "count": count}
+
+
+def match(des1, des2, ratio: float = 0.7, mode: int = 0):
+    """mode 0: 2-NN + ratio + one-to-one (feature_matcher.py:89-98,179-209); 1: mutual NN; 2: raw 2-NN.
+
+    Returns device tensors: modes 0/1 -> (idx1, idx2, dist, count[1]); mode 2 -> (idx (n1,2), dist (n1,2)).
+    """
+    des1, des2 = _req(des1), _req(des2)
+    n1, D = des1.shape
+    n2 = des2.shape[0]
+    dev = des1.device
+    ws = torch.empty(int(lib().nvs_match_workspace_bytes(n1, n2)), dtype=torch.uint8, device=dev)
+    if mode == 2:
+        idx = torch.empty(n1, 2, device=dev, dtype=torch.int32)
+        dist = torch.empty(n1, 2, device=dev, dtype=torch.float32)
+        dummy = torch.empty(1, device=dev, dtype=torch.int32)
+        check(lib().nvs_match(des1.data_ptr(), des2.data_ptr(), n1, n2, D, float(ratio), 2, idx.data_ptr(),
+                              dummy.data_ptr(), dist.data_ptr(), dummy.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _stream()), "nvs_match")
+        return idx, dist
+    i1 = torch.empty(n1, device=dev, dtype=torch.int32)
+    i2 = torch.empty(n1, device=dev, dtype=torch.int32)
+    dd = torch.empty(n1, device=dev, dtype=torch.float32)
+    cnt = torch.zeros(1, device=dev, dtype=torch.int32)
+    check(lib().nvs_match(des1.data_ptr(), des2.data_ptr(), n1, n2, D, float(ratio), mode, i1.data_ptr(),
+                          i2.data_ptr(), dd.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "nvs_match")
+    return i1, i2, dd, cnt

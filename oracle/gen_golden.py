@@ -1,0 +1,103 @@
+"""Generate tests/golden/*.npz by running the REAL reference package (build container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+Imports ``src.kp2dtiny`` from /root/reference (read-only, never copied), loads name-hashed
+spread-init weights (nano_vs_slam_b200.synthetic.spread_init) into the reference modules, runs
+``model(x)`` + ``model.post_processing`` exactly as the reference callers do
+(eval_multitask.py:195-198, frontend.py:56-60,84-85) and stores inputs' seeds and outputs.
+Also stores cv2.BFMatcher 2-NN results for the matcher oracle.
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("NVS_REFERENCE", "/root/reference")
+sys.path.insert(0, REPO)
+
+from nano_vs_slam_b200.synthetic import spread_init, synthetic_frames  # noqa: E402
+
+# (name, letter, v3, n_classes, B, H, W, weight seed, input seed)
+CASES = [
+    ("v2_S", "S", False, 28, 2, 40, 56, 1234, 0),
+    ("v2_S_A", "S_A", False, 19, 1, 40, 56, 1235, 1),
+    ("v2_N", "N", False, 28, 1, 40, 56, 1236, 2),
+    ("v2_N_A", "N_A", False, 19, 1, 32, 48, 1237, 3),
+    ("v3_S", "S", True, 19, 1, 40, 56, 1238, 4),
+    ("v3_S_A", "S_A", True, 28, 1, 32, 48, 1239, 5),
+    ("v3_N", "N", True, 28, 2, 40, 56, 1240, 6),
+    ("v3_N_A", "N_A", True, 19, 1, 40, 56, 1241, 7),
+]
+
+
+def load_reference():
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "src"))
+    sys.dont_write_bytecode = True
+    from src.kp2dtiny.models.kp2dtiny import tiny_factory  # type: ignore
+
+    return tiny_factory
+
+
+def run_reference(tiny_factory, letter, v3, n_classes, B, H, W, wseed, xseed):
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = tiny_factory(letter, n_classes, v3=v3)
+    sd = spread_init(m.state_dict(), wseed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    m.training = False
+    x = synthetic_frames(B, H, W, xseed)
+    with torch.no_grad():
+        out = m(x)
+        fwd = {k: v.clone() for k, v in out.items()}
+        post = m.post_processing(dict(out), H, W)
+    return fwd, post
+
+
+def main():
+    tiny_factory = load_reference()
+    gold = os.path.join(REPO, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    for name, letter, v3, ncls, B, H, W, wseed, xseed in CASES:
+        fwd, post = run_reference(tiny_factory, letter, v3, ncls, B, H, W, wseed, xseed)
+        arrs = {"meta": np.array([int(v3), ncls, B, H, W, wseed, xseed], dtype=np.int64)}
+        arrs["letter"] = np.array(letter)
+        for k, v in fwd.items():
+            arrs["fwd_" + k] = v.numpy()
+        for k, v in post.items():
+            arrs["post_" + k] = v.numpy()
+        np.savez_compressed(os.path.join(gold, f"model_{name}.npz"), **arrs)
+        print(name, {k: tuple(v.shape) for k, v in fwd.items()},
+              "kp>0.7:", int((post["score"] > 0.7).sum()))
+
+    # matcher: cv2.BFMatcher(NORM_L2).knnMatch(k=2) on unit descriptors with planted matches
+    import cv2
+
+    rng = np.random.default_rng(7)
+    n1, n2, d = 300, 280, 32
+    des2 = rng.standard_normal((n2, d)).astype(np.float32)
+    des2 /= np.linalg.norm(des2, axis=1, keepdims=True)
+    src = rng.integers(0, n2, size=n1)
+    des1 = des2[src] + 0.25 * rng.standard_normal((n1, d)).astype(np.float32) * rng.random((n1, 1)).astype(np.float32)
+    des1 /= np.linalg.norm(des1, axis=1, keepdims=True)
+    des1 = des1.astype(np.float32)
+    knn = cv2.BFMatcher(cv2.NORM_L2).knnMatch(des1, des2, k=2)
+    idx = np.array([[m.trainIdx, n.trainIdx] for m, n in knn], dtype=np.int64)
+    dist = np.array([[m.distance, n.distance] for m, n in knn], dtype=np.float32)
+    cc = cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).match(des1, des2)
+    cross = np.array([[m.queryIdx, m.trainIdx] for m in cc], dtype=np.int64)
+    np.savez_compressed(os.path.join(gold, "matcher_cv2.npz"), des1=des1, des2=des2, idx=idx, dist=dist,
+                        cross=cross, cv2_version=np.array(cv2.__version__))
+    print("matcher", idx.shape, cross.shape)
+
+
+if __name__ == "__main__":
+    main()

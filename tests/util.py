@@ -1,0 +1,33 @@
+"""Shared helpers for the parity tests (tolerances from BASELINE.json:north_star)."""
+import glob
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-4  # fp32 features / descriptors / VLAD: 1e-4 relative (north_star)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a-b||_inf / ||b||_inf."""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def golden_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz")))
+
+
+def load_golden(path):
+    z = np.load(path, allow_pickle=False)
+    v3, ncls, B, H, W, wseed, xseed = [int(v) for v in z["meta"]]
+    letter = str(z["letter"])
+    fwd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("fwd_")}
+    post = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("post_")}
+    return dict(letter=letter, v3=bool(v3), n_classes=ncls, B=B, H=H, W=W, wseed=wseed, xseed=xseed,
+                fwd=fwd, post=post)
+
+
+def argmax_agreement(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.cpu() == b.cpu()).float().mean())
