@@ -1,0 +1,104 @@
+"""Whole-model parity through the reference-shaped module surface (KP2DTinyV2/V3.forward + post_processing)."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import REL_TOL, golden_cases, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(letter, n_classes, v3, wseed):
+    from nano_vs_slam_b200 import tiny_factory
+    from nano_vs_slam_b200.synthetic import spread_init
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = tiny_factory(letter, n_classes, v3=v3)
+    sd = spread_init(m.state_dict(), wseed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    m.training = False
+    return m.to("cuda"), sd
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[6:-4])
+def test_model_matches_reference_golden(path):
+    """Fixtures were produced by the REAL reference package (oracle/gen_golden.py)."""
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    c = load_golden(path)
+    m, _ = _model(c["letter"], c["n_classes"], c["v3"], c["wseed"])
+    x = synthetic_frames(c["B"], c["H"], c["W"], c["xseed"]).cuda()
+    out = m(x)
+    for k in ("score", "coord", "feat", "vlad", "seg"):
+        assert out[k].shape == c["fwd"][k].shape, k
+        assert rel_err(out[k], c["fwd"][k]) < REL_TOL, (k, rel_err(out[k], c["fwd"][k]))
+    post = m.post_processing(dict(out), c["H"], c["W"])
+    assert torch.equal(post["score"].cpu() > 0, c["post"]["score"] > 0)
+    assert rel_err(post["score"], c["post"]["score"]) < REL_TOL
+    assert float((post["coord"].cpu() - c["post"]["coord"]).abs().max()) < 1e-3
+    assert rel_err(post["feat"], c["post"]["feat"]) < REL_TOL
+    assert post["seg"].dtype == torch.int64
+    assert (post["seg"].cpu() == c["post"]["seg"]).float().mean() >= 0.999
+    assert torch.equal(post["vlad"], out["vlad"])
+
+
+@pytest.mark.parametrize("letter,v3,ncls,B,H,W", [
+    ("S", False, 28, 2, 240, 320),      # config 1 shape
+    ("N", True, 28, 3, 240, 320),       # config 2 model
+    ("S", False, 19, 1, 376, 1241),     # config 3 KITTI shape (odd W, odd W/8)
+    ("S_A", False, 19, 1, 128, 256),    # config 4 model at a size the CPU oracle finishes quickly
+    ("N_A", True, 28, 1, 240, 320),
+])
+def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W):
+    from oracle import kp2dtiny_ref as R
+    from oracle import glue_ref
+    from nano_vs_slam_b200 import ops
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    m, sd = _model(letter, ncls, v3, 4321)
+    x = synthetic_frames(B, H, W, 17)
+    out = m(x.cuda())
+    a = R.arch_for(letter, v3, ncls)
+    ref = R.forward(x, sd, a)
+    for k in ("score", "coord", "feat", "vlad", "seg"):
+        assert rel_err(out[k], ref[k]) < REL_TOL, (k, rel_err(out[k], ref[k]))
+    post = m.post_processing(dict(out), H, W)
+    rpost = R.post_processing(dict(ref), H, W, a)
+    assert float((post["coord"].cpu() - rpost["coord"]).abs().max()) < 1e-3
+    assert rel_err(post["feat"], rpost["feat"]) < REL_TOL
+    assert (post["seg"].cpu() == rpost["seg"]).float().mean() >= 0.999
+    # keypoint sets (threshold + top-k), per frame, Jaccard >= 99.9 %
+    thr = float(rpost["score"].flatten().kthvalue(int(0.8 * rpost["score"].numel())).values)  # ~20 % pass
+    sel = ops.select_keypoints(post["score"], post["coord"], post["feat"], thr, 300)
+    for b in range(B):
+        one = {k: rpost[k][b:b + 1] for k in ("score", "coord", "feat", "seg")}
+        pts, desc, _, cells = glue_ref.frontend_decode(one, 32, thr, 300)
+        n = int(sel["count"][b])
+        got = set(sel["cell"][b, :n].cpu().tolist())
+        jac = len(got & set(cells.tolist())) / max(1, len(got | set(cells.tolist())))
+        assert jac >= 0.99, jac  # single near-threshold flips allowed at k=300 (1/300 > 0.1 %)
+
+
+def test_state_dict_roundtrip_and_errors():
+    from nano_vs_slam_b200 import tiny_factory
+    from nano_vs_slam_b200._cabi import NanovsError
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = tiny_factory("S", 28, v3=False)
+    assert len(m.state_dict()) == 150  # V2-S has 150 entries
+    with pytest.raises(NanovsError):
+        m(torch.zeros(1, 3, 64, 64))  # training flag still True
+    m.eval(); m.training = False
+    with pytest.raises(NanovsError):
+        m(torch.zeros(1, 3, 64, 64))  # CPU tensor: no fallback
+    m = m.cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 60, 64, device="cuda"))  # floor(H/2) % 4 != 0
+    out = m(torch.zeros(1, 3, 64, 64, device="cuda"))
+    assert set(out) == {"score", "coord", "feat", "vlad", "seg"}
+    assert out["vlad"].shape == (1, 4096) and m.get_global_desc_dim() == 4096
