@@ -16,7 +16,7 @@ ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SIGMOID_TANH, ACT_GELU
 OUT_PLAIN, OUT_POOL, OUT_BOTH, OUT_SHUFFLE = range(4)
 IN_PLAIN, IN_S2D = range(2)
 
-_vp, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_size_t
+_vp, _i32, _f32, _f64, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_size_t, C.c_int64
 
 
 class NvsConvArgs(C.Structure):
@@ -53,6 +53,11 @@ SIGNATURES = {
                                     _i32, _i32, _i32, _vp]),
     "nvs_match_workspace_bytes": (_sz, [_i32, _i32]),
     "nvs_match": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nvs_flat_padded_dim": (_i32, [_i32]),
+    "nvs_flat_prepare": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "nvs_flat_search_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "nvs_flat_search": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "nvs_topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,86 @@
+"""KP2DtinyFrontend -- device-side version of src/visual_odometry/frontend.py:11-129.
+
+The reference moves score / coord / feat / seg to the host every frame and does the threshold,
+optional semantic filter and argpartition top-k in numpy (frontend.py:94-126).  Here the whole decode
+(post_processing + selection) stays on the GPU; ``run`` keeps the reference's single-image signature and
+numpy return types, ``run_batch`` is the batched form used for throughput (frames are independent, the
+reference glue is simply applied per frame).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .kp2dtiny import tiny_factory
+
+
+class KP2DtinyFrontend(object):
+    def __init__(self, new_size=None, weights_path=None, nn_thresh=0.7, device="cuda", semantic_filter=False,
+                 classes_to_filter=(21,), debug=False, method="kp2dtiny", config="S", top_k=4000, v3=False,
+                 nClasses=28, state_dict=None):
+        if method != "kp2dtiny":
+            raise NotImplementedError("only the kp2dtiny extractor is on the B200 hot path")
+        self.name = method
+        self.device = device
+        self.nn_thresh = nn_thresh
+        self.border_remove = 4
+        self.classes_to_filter = list(classes_to_filter)
+        self.apply_semantic_filer = semantic_filter  # (sic) attribute name of the reference, frontend.py:34
+        self.weights_path = weights_path
+        self.plot = False  # cv2.imshow debugging of the reference (:95-105) is not part of the hot path
+        self.top_k = top_k
+        self.new_size = new_size
+        self.net = tiny_factory(config, nClasses, to_export=False, to_mcu=False, v3=v3)
+        self.net.sample_segmentation = semantic_filter  # frontend.py:47
+        if weights_path is not None:
+            state_dict = torch.load(weights_path, map_location=torch.device("cpu"))["state_dict"]  # :51-53
+        if state_dict is not None:
+            self.net.load_state_dict(state_dict)
+        self.net.eval()
+        self.net.training = False
+        self.net = self.net.to(self.device)
+        self.net.device = self.device
+
+    def get_info(self):
+        return {"nn_thresh": self.nn_thresh, "border_remove": self.border_remove, "weights_path": self.weights_path,
+                "device": self.device, "apply_semantic_filer": self.apply_semantic_filer,
+                "classes_to_filter": self.classes_to_filter, "plot": self.plot, "top_k": self.top_k,
+                "new_size": self.new_size, "name": self.name, "model": self.net.gather_info()}
+
+    @torch.no_grad()
+    def run_batch(self, imgs: torch.Tensor, normalized: bool = False):
+        """imgs (B,3,H,W) in [0,1] (or already in [-1,1] if ``normalized``) on any device.
+
+        Returns (sel, post): ``sel`` = dict(pts, desc, score, cell, label, count) device tensors from
+        ops.select_keypoints, ``post`` = the post_processing dict (vlad, seg argmax, dense maps).
+        """
+        x = imgs.to(self.device, non_blocking=True)
+        if not normalized:
+            x = x.sub(0.5).mul(2.0)  # frontend.py:79
+        _, _, H, W = x.shape
+        out = self.net.forward(x)
+        post = self.net.post_processing(out, H, W)
+        seg_cells = post["seg"] if self.apply_semantic_filer else None
+        sel = ops.select_keypoints(post["score"], post["coord"], post["feat"], self.nn_thresh, self.top_k,
+                                   seg_cells=seg_cells,
+                                   classes_to_filter=self.classes_to_filter if self.apply_semantic_filer else None)
+        return sel, post
+
+    def run(self, img: torch.Tensor):
+        """Reference signature (frontend.py:78-129): img (3,H,W) in [0,1] -> (pts (n,2), desc (n,D), seg)."""
+        sel, post = self.run_batch(img.unsqueeze(0))
+        n = int(sel["count"][0])
+        pts = sel["pts"][0, :n].cpu().numpy()
+        feat = sel["desc"][0, :n].cpu().numpy()
+        if self.apply_semantic_filer:
+            seg = sel["label"][0, :n].cpu().numpy()
+        else:
+            # the reference indexes the H/2 x W/2 label map by cell index when more than top_k points pass
+            # (frontend.py:116,126: "harmless quirk"); mirrored for drop-in equality
+            seg = post["seg"].view(-1).cpu().numpy()
+            if int((post["score"] > self.nn_thresh).sum()) > self.top_k > 0:
+                seg = seg[sel["cell"][0, :n].cpu().numpy()]
+        return pts.copy(), feat.copy(), seg.copy()

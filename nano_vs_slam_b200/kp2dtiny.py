@@ -249,6 +249,8 @@ class _Plan:
         self.out_slots: Dict[str, List] = {}
         self.B, self.H, self.W, self.device = B, H, W, device
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.meta: Dict[int, dict] = {}   # step index -> {flops, bytes} of conv launches (for bench.py)
+        self.profile: Optional[dict] = None  # {"idx": step index, "events": [(start, end), ...]}
         model._build_plan(self)
 
     def buf(self, name: str, c: int, h: int, w: int) -> torch.Tensor:
@@ -260,6 +262,16 @@ class _Plan:
         """Register a conv; if ``out_name`` is given its dst pointer is patched per call (fresh output)."""
         wp, bp = packed
         args = ops.make_conv_args(src0, wp, bp, cout, **kw)
+        cin = (4 * args.c0) if args.in_mode == ops.IN_S2D else (args.c0 + args.c1)
+        n_out = cout * args.H * args.W
+        if args.out_mode == ops.OUT_POOL:
+            n_out //= 4
+        elif args.out_mode == ops.OUT_BOTH:
+            n_out += n_out // 4
+        self.meta[len(self.steps)] = {
+            "flops": 2.0 * args.ksize * args.ksize * cin * cout * args.H * args.W * self.B,
+            "bytes": 4.0 * self.B * ((args.c0 + args.c1) * args.in_H * args.in_W + n_out),
+            "shape": f"{cin}->{cout} k{args.ksize} @{args.H}x{args.W}"}
         self.steps.append(("conv", args))
         if out_name is not None:
             self.out_slots.setdefault(out_name, []).append(args)
@@ -435,8 +447,15 @@ class _KP2DTinyBase(nn.Module):
                 a.dst = outs[name].data_ptr()
         plan.in_args.src0 = x.data_ptr()
         run_conv = ops.run_conv
-        for st in plan.steps:
-            if st[0] == "conv":
+        prof = plan.profile
+        for i, st in enumerate(plan.steps):
+            if prof is not None and i == prof["idx"]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run_conv(st[1])
+                e1.record()
+                prof["events"].append((e0, e1))
+            elif st[0] == "conv":
                 run_conv(st[1])
             else:
                 st[1](outs, *st[2])

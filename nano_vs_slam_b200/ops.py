@@ -15,6 +15,10 @@ from ._cabi import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SI
                     IN_PLAIN, IN_S2D, OUT_BOTH, OUT_PLAIN, OUT_POOL, OUT_SHUFFLE, NvsConvArgs, check, lib)
 
 
+# number of libnanovs kernels launched by this process (bench.py reports it as "gpu_launches")
+LAUNCHES = [0]
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -133,6 +137,7 @@ def make_conv_args(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout:
 
 def run_conv(args: NvsConvArgs) -> None:
     check(lib().nvs_conv(C.byref(args), _stream()), "nvs_conv")
+    LAUNCHES[0] += 1
 
 
 def conv(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout: int, **kw):
@@ -165,6 +170,7 @@ def dwconv3x3(x, w, b, out=None):
     out = torch.empty_like(x) if out is None else out
     check(lib().nvs_dwconv3x3(x.data_ptr(), w.data_ptr(), _ptr(b), out.data_ptr(), B, Cc, H, W, _stream()),
           "nvs_dwconv3x3")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -174,6 +180,7 @@ def channel_layernorm(x, g, b, eps: float = 1e-5, out=None):
     out = torch.empty_like(x) if out is None else out
     check(lib().nvs_channel_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), B, Cc,
                                       x[0, 0].numel(), eps, _stream()), "nvs_channel_layernorm")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -182,6 +189,7 @@ def softmax_channels(x, out=None):
     out = torch.empty_like(x) if out is None else out
     check(lib().nvs_softmax_channels(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x[0, 0].numel(),
                                      _stream()), "nvs_softmax_channels")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -190,6 +198,7 @@ def l2norm_channels(x, out=None):
     out = torch.empty_like(x) if out is None else out
     check(lib().nvs_l2norm_channels(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x[0, 0].numel(),
                                     _stream()), "nvs_l2norm_channels")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -200,6 +209,7 @@ def attention(q, kv, heads: int, out=None):
     out = torch.empty_like(q) if out is None else out
     check(lib().nvs_attention(q.data_ptr(), kv.data_ptr(), out.data_ptr(), B, Cc, heads, q[0, 0].numel(),
                               kv[0, 0].numel(), _stream()), "nvs_attention")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -219,6 +229,7 @@ def netvlad(x, w_assign, centroids, out=None, workspace=None):
     out = torch.empty(B, K * Cc, device=x.device, dtype=torch.float32) if out is None else out
     check(lib().nvs_netvlad(x.data_ptr(), w_assign.data_ptr(), centroids.data_ptr(), out.data_ptr(),
                             workspace.data_ptr(), workspace.numel(), B, Cc, K, S, _stream()), "nvs_netvlad")
+    LAUNCHES[0] += 2
     return out
 
 
@@ -238,6 +249,7 @@ def decode(score, shift, feat, H: int, W: int, cell: int, cross_ratio: float = 2
     check(lib().nvs_decode(score.data_ptr(), shift.data_ptr(), _ptr(feat), o_s.data_ptr(), o_c.data_ptr(),
                            _ptr(o_f), B, Hc, Wc, D, Hf, Wf, H, W, cell, float(cross_ratio), _stream()),
           "nvs_decode")
+    LAUNCHES[0] += 1
     return o_s, o_c, o_f
 
 
@@ -254,6 +266,7 @@ def seg_argmax(seg, coord=None, H: int = 0, W: int = 0):
         out = torch.empty(B, 1, Hs, Ws, device=seg.device, dtype=torch.int64)
     check(lib().nvs_seg_argmax(seg.data_ptr(), _ptr(coord), out.data_ptr(), B, Cc, Hs, Ws, Hc, Wc, H, W,
                                _stream()), "nvs_seg_argmax")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -290,6 +303,7 @@ def select_keypoints(score, coord, feat, thresh: float, top_k: int, seg_cells=No
                                      0 if filt is None else filt.numel(), float(thresh), k, pts.data_ptr(),
                                      _ptr(desc), sc.data_ptr(), cell.data_ptr(), _ptr(label), count.data_ptr(),
                                      B, n_cells, D, _stream()), "nvs_select_keypoints")
+    LAUNCHES[0] += 1
     return {"pts": pts, "desc": desc, "score": sc, "cell": cell, "label": label, "count": count}
 
 
@@ -310,6 +324,7 @@ def match(des1, des2, ratio: float = 0.7, mode: int = 0):
         check(lib().nvs_match(des1.data_ptr(), des2.data_ptr(), n1, n2, D, float(ratio), 2, idx.data_ptr(),
                               dummy.data_ptr(), dist.data_ptr(), dummy.data_ptr(), ws.data_ptr(), ws.numel(),
                               _stream()), "nvs_match")
+        LAUNCHES[0] += 2
         return idx, dist
     i1 = torch.empty(n1, device=dev, dtype=torch.int32)
     i2 = torch.empty(n1, device=dev, dtype=torch.int32)
@@ -318,4 +333,5 @@ def match(des1, des2, ratio: float = 0.7, mode: int = 0):
     check(lib().nvs_match(des1.data_ptr(), des2.data_ptr(), n1, n2, D, float(ratio), mode, i1.data_ptr(),
                           i2.data_ptr(), dd.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "nvs_match")
+    LAUNCHES[0] += 3 if mode == 0 else 5
     return i1, i2, dd, cnt

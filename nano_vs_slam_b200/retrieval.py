@@ -1,0 +1,142 @@
+"""IndexFlatL2 -- exact L2 retrieval with faiss's call shape (src/evaluation/global_descriptor.py:55-60):
+
+    index = IndexFlatL2(d); index.add(db); D, I = index.search(q, k)
+
+``add`` keeps the fp32 rows resident in HBM and builds the bf16 GEMM operand + squared norms once;
+``search`` runs the tcgen05/TMEM GEMM with fused per-row top-k and the fp32 re-rank (csrc/retrieval.cu).
+numpy in -> numpy out (like faiss); CUDA tensors in -> CUDA tensors out.
+
+ShardedIndexFlatL2 row-shards the database over the ranks of a torch.distributed process group: every rank
+searches its shard with global ids, one all_gather moves the (Q,k) partial results (NCCL over NVLink on GPUs),
+and every rank merges world_size*k candidates per query.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from ._cabi import check, lib
+
+KMAX = 31
+
+
+def _as_dev(x, device) -> Tuple[torch.Tensor, bool]:
+    was_np = isinstance(x, np.ndarray)
+    if was_np:
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    return x.to(device=device, dtype=torch.float32).contiguous(), was_np
+
+
+class IndexFlatL2(object):
+    def __init__(self, d: int, device="cuda"):
+        self.d = int(d)
+        self.device = torch.device(device)
+        self.ntotal = 0
+        self._x = None       # fp32 rows (re-rank operand, exact distances)
+        self._xb = None      # bf16 rows padded to a multiple of 64 columns (GEMM operand)
+        self._xn = None      # |x|^2
+        self._ws = None
+
+    def add(self, x) -> None:
+        x, _ = _as_dev(x, self.device)
+        assert x.dim() == 2 and x.shape[1] == self.d, (x.shape, self.d)
+        self._x = x if self._x is None else torch.cat([self._x, x], 0)
+        n = self._x.shape[0]
+        dpad = int(lib().nvs_flat_padded_dim(self.d))
+        self._xb = torch.empty(n, dpad, dtype=torch.bfloat16, device=self.device)
+        self._xn = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(lib().nvs_flat_prepare(self._x.data_ptr(), n, self.d, self._xb.data_ptr(), self._xn.data_ptr(),
+                                     ops._stream()), "nvs_flat_prepare")
+        ops.LAUNCHES[0] += 1
+        self.ntotal = n
+
+    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0):
+        assert self.ntotal > 0, "empty index"
+        if k > KMAX:
+            raise NotImplementedError(f"k <= {KMAX} (per-row top-k list lives in shared memory)")
+        nq = q.shape[0]
+        D = torch.empty(nq, k, dtype=torch.float32, device=self.device)
+        I = torch.empty(nq, k, dtype=torch.int64, device=self.device)
+        nbytes = int(lib().nvs_flat_search_workspace_bytes(self.ntotal, nq, self.d, k))
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        check(lib().nvs_flat_search(self._x.data_ptr(), self._xb.data_ptr(), self._xn.data_ptr(), self.ntotal,
+                                    q.data_ptr(), nq, self.d, k, id_offset, D.data_ptr(), I.data_ptr(),
+                                    self._ws.data_ptr(), self._ws.numel(), ops._stream()), "nvs_flat_search")
+        ops.LAUNCHES[0] += 4
+        return D, I
+
+    def search(self, q, k: int):
+        qd, was_np = _as_dev(q, self.device)
+        assert qd.dim() == 2 and qd.shape[1] == self.d
+        D, I = self.search_device(qd, k)
+        if was_np:
+            return D.cpu().numpy(), I.cpu().numpy()
+        return D, I
+
+
+def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor):
+    """(parts, Q, k) sorted partial results -> (Q, k) global top-k (csrc/retrieval.cu merge_parts_kernel)."""
+    parts, nq, k = D_parts.shape
+    D_parts, I_parts = D_parts.contiguous(), I_parts.contiguous()
+    D = torch.empty(nq, k, dtype=torch.float32, device=D_parts.device)
+    I = torch.empty(nq, k, dtype=torch.int64, device=D_parts.device)
+    check(lib().nvs_topk_merge(D_parts.data_ptr(), I_parts.data_ptr(), parts, nq, k, D.data_ptr(), I.data_ptr(),
+                               ops._stream()), "nvs_topk_merge")
+    ops.LAUNCHES[0] += 1
+    return D, I
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range [lo, hi) of ``rank``: the first n_total % world ranks get one extra row."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedIndexFlatL2(object):
+    """Row-sharded exact index: shard-local search + ONE all_gather + merge.
+
+    ``local_search(shard, q, k, id_offset) -> (D, I)`` and ``merge(D_parts, I_parts) -> (D, I)`` default to the
+    CUDA kernels; the CPU gloo tests inject the oracle's functions to exercise the host-side sharding logic.
+    """
+
+    def __init__(self, d: int, n_total: int, group=None, device="cuda",
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.d, self.n_total = d, n_total
+        self.lo, self.hi = shard_bounds(n_total, self.world, self.rank)
+        self.device = torch.device(device)
+        self._index = IndexFlatL2(d, device) if local_search is None else None
+        self._local_search = local_search
+        self._merge = merge if merge is not None else merge_topk_device
+        self._shard = None
+
+    def add_local(self, x_shard) -> None:
+        """Rows [lo, hi) of the global database (each rank adds only its own shard)."""
+        assert x_shard.shape[0] == self.hi - self.lo, (x_shard.shape, self.lo, self.hi)
+        if self._index is not None:
+            self._index.add(x_shard)
+        else:
+            self._shard = x_shard
+
+    def search(self, q: torch.Tensor, k: int):
+        if self._index is not None:
+            D, I = self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo)
+        else:
+            D, I = self._local_search(self._shard, q, k, self.lo)
+        if self.world == 1:
+            return D, I
+        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        self.dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        return self._merge(Dg, Ig)

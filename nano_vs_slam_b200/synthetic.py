@@ -98,3 +98,14 @@ def planted_retrieval_set(n_db: int, n_q: int, dim: int, k: int, seed: int = 0,
         rows = rows / rows.norm(dim=-1, keepdim=True)
         db[planted[q0:q0 + qchunk].reshape(-1)] = rows.reshape(-1, dim)
     return db, q, planted
+
+
+def algorithmic_bytes_per_frame(model, H: int, W: int, with_decode: bool = True) -> float:
+    """fp32 input + forward-dict outputs (+ decode outputs) of one frame -- the compulsory HBM traffic
+    used as the roofline numerator; weights (<= 3.7 MB) amortise to 0 over a batch."""
+    h2, w2 = H // 2, W // 2
+    h4, w4 = h2 // 2, w2 // 2
+    n = 3 * H * W + 3 * h4 * w4 + model.nfeatures * h2 * w2 + model.nClasses * h2 * w2 + model.get_global_desc_dim()
+    if with_decode:
+        n += (3 + model.nfeatures) * h4 * w4 + 2 * h2 * w2  # score, coord, sampled feat (f32) + seg argmax (i64)
+    return 4.0 * n
