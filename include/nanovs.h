@@ -162,6 +162,8 @@ int nvs_match(const float* des1, const float* des2, int32_t n1, int32_t n2, int3
  * search: d2 = |q|^2 + |x|^2 - 2 q.x; bf16 tcgen05/TMEM GEMM with a fused per-row running top-k selects
  *         candidates, which are re-ranked with the fp32 formula; out_D (nq,k) ascending, out_I (nq,k) int64
  *         = row index + id_offset (id_offset = first global row of this shard).  k <= 31.
+ *         ev_gemm_start / ev_gemm_stop: optional cudaEvent_t (may be NULL) recorded on `stream` around the
+ *         GEMM+top-k kernel so callers can time it (bench.py roofline).
  * merge:  nvs_topk_merge combines `parts` (<= 16) sorted (nq,k) lists laid out [parts][nq][k] (the NCCL
  *         allgather buffer of a sharded index) into the global top-k. */
 int32_t nvs_flat_padded_dim(int32_t d);
@@ -169,7 +171,8 @@ int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_bf16, float* 
 size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int32_t d, int32_t k);
 int nvs_flat_search(const float* db, const void* db_bf16, const float* db_norms, int64_t n_db, const float* q,
                     int32_t nq, int32_t d, int32_t k, int64_t id_offset, float* out_D, int64_t* out_I,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    void* workspace, size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop,
+                    void* stream);
 int nvs_topk_merge(const float* D_parts, const int64_t* I_parts, int32_t parts, int32_t nq, int32_t k,
                    float* out_D, int64_t* out_I, void* stream);
 

@@ -562,7 +562,8 @@ extern "C" size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int3
 
 extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float* db_norms, int64_t n_db,
                                const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset, float* out_D,
-                               int64_t* out_I, void* workspace, size_t workspace_bytes, void* stream) {
+                               int64_t* out_I, void* workspace, size_t workspace_bytes, void* ev_gemm_start,
+                               void* ev_gemm_stop, void* stream) {
   if (!db || !db_bf16 || !db_norms || !q || !out_D || !out_I || !workspace) return NVS_ERR_ARG;
   if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0) return NVS_ERR_ARG;
   if (k > KMAX) return NVS_ERR_UNSUPPORTED;   // per-row list lives in shared memory
@@ -607,8 +608,10 @@ extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float
   }
   const int n_units = L.n_mblk * L.n_strips;
   const int grid = n_units < sm_count ? n_units : sm_count;
+  if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
   flat_l2_topk_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mq, mx, p);
   NVS_CHECK_LAUNCH();
+  if (ev_gemm_stop) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_stop), st);
 
   const int n_cand = L.n_strips * k;
   static bool sel_attr = false;

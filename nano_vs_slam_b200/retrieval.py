@@ -53,7 +53,8 @@ class IndexFlatL2(object):
         ops.LAUNCHES[0] += 1
         self.ntotal = n
 
-    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0):
+    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0, gemm_events=None):
+        """``gemm_events``: optional (start, stop) torch.cuda.Event pair recorded around the GEMM kernel."""
         assert self.ntotal > 0, "empty index"
         if k > KMAX:
             raise NotImplementedError(f"k <= {KMAX} (per-row top-k list lives in shared memory)")
@@ -63,9 +64,15 @@ class IndexFlatL2(object):
         nbytes = int(lib().nvs_flat_search_workspace_bytes(self.ntotal, nq, self.d, k))
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        e0 = e1 = None
+        if gemm_events is not None:
+            for ev in gemm_events:
+                ev.record()  # forces creation of the underlying cudaEvent_t; re-recorded inside the library
+            e0, e1 = gemm_events[0].cuda_event, gemm_events[1].cuda_event
         check(lib().nvs_flat_search(self._x.data_ptr(), self._xb.data_ptr(), self._xn.data_ptr(), self.ntotal,
                                     q.data_ptr(), nq, self.d, k, id_offset, D.data_ptr(), I.data_ptr(),
-                                    self._ws.data_ptr(), self._ws.numel(), ops._stream()), "nvs_flat_search")
+                                    self._ws.data_ptr(), self._ws.numel(), e0, e1, ops._stream()),
+              "nvs_flat_search")
         ops.LAUNCHES[0] += 4
         return D, I
 
@@ -128,15 +135,18 @@ class ShardedIndexFlatL2(object):
         else:
             self._shard = x_shard
 
-    def search(self, q: torch.Tensor, k: int):
+    def search(self, q: torch.Tensor, k: int, gemm_events=None):
         if self._index is not None:
-            D, I = self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo)
+            D, I = self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo,
+                                             gemm_events=gemm_events)
         else:
             D, I = self._local_search(self._shard, q, k, self.lo)
         if self.world == 1:
             return D, I
-        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        nq = D.shape[0]
+        # rank-major concatenation along dim 0 == the [parts][nq][k] layout nvs_topk_merge expects
+        Dg = torch.empty(self.world * nq, k, dtype=D.dtype, device=D.device)
+        Ig = torch.empty(self.world * nq, k, dtype=I.dtype, device=I.device)
         self.dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
         self.dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
-        return self._merge(Dg, Ig)
+        return self._merge(Dg.view(self.world, nq, k), Ig.view(self.world, nq, k))

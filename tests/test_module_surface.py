@@ -1,0 +1,82 @@
+"""Drop-in surface: config letters, constructor kwargs, attributes and state_dict names/shapes equal the
+reference's (checked against the live reference package when it is present, else against the golden files)."""
+import contextlib
+import io
+import os
+import sys
+
+import pytest
+import torch
+
+from util import golden_cases, load_golden
+
+REF = "/root/reference"
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_config_tables_and_factory():
+    from nano_vs_slam_b200 import KP2DTINY_CONFIGS, KP2DTINYV3_CONFIGS, get_config, tiny_factory
+
+    assert set(KP2DTINY_CONFIGS) == {"S", "S_A", "N", "N_A", "D", "F", "GEM_N", "GEM_S_A", "CONVAP_S_A"}
+    assert set(KP2DTINYV3_CONFIGS) == {"S", "S_A", "N", "N_A", "D", "D_A", "CONVAP_S_A"}
+    with pytest.raises(ValueError):
+        get_config("nope")
+    c = get_config("S", to_export=True)
+    assert c["remove_netvlad"] is True and "remove_netvlad" not in KP2DTINY_CONFIGS["S"]  # no shared-dict mutation
+    m = _quiet(tiny_factory, "N", 28, v3=True)
+    assert m.get_global_desc_dim() == 3072 and m.cell == 4 and m.nfeatures == 32 and m.training is True
+    m2 = _quiet(tiny_factory, "N", 28, v3=False)
+    assert m2.get_global_desc_dim() == 1536  # V2-N: num_clusters 32 x 48
+    assert sum(p.numel() for p in m.parameters()) == 404639  # V3-N
+    assert sum(p.numel() for p in _quiet(tiny_factory, "S", 28).parameters()) == 928079  # V2-S
+    info = m.gather_info()
+    assert info["netvlad_dim"] == 3072 and info["total_params"] == 404639
+    for bad in ("GEM_N", "CONVAP_S_A", "F"):
+        with pytest.raises(NotImplementedError):
+            _quiet(tiny_factory, bad, 28)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="live reference not present")
+@pytest.mark.parametrize("letter,v3", [(l, v) for v in (False, True) for l in ("S", "S_A", "N", "N_A")])
+def test_state_dict_keys_equal_reference(letter, v3):
+    sys.path[:0] = [REF, os.path.join(REF, "src")]
+    sys.dont_write_bytecode = True
+    from src.kp2dtiny.models.kp2dtiny import tiny_factory as ref_factory  # type: ignore
+    from nano_vs_slam_b200 import tiny_factory
+
+    ref = _quiet(ref_factory, letter, 19, v3=v3).state_dict()
+    ours = _quiet(tiny_factory, letter, 19, v3=v3)
+    sd = ours.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    ours.load_state_dict(ref, strict=True)  # a reference checkpoint loads unchanged
+
+
+def test_load_state_dict_invalidates_packed_weights():
+    from nano_vs_slam_b200 import tiny_factory
+    from nano_vs_slam_b200.synthetic import spread_init
+
+    m = _quiet(tiny_factory, "S", 28)
+    m._packed = {"stale": True}
+    m.load_state_dict(spread_init(m.state_dict(), 1))
+    assert m._packed is None
+    m._packed = {"stale": True}
+    m.float()
+    assert m._packed is None
+
+
+def test_reference_import_path_shim():
+    import importlib
+    import subprocess
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from src.kp2dtiny.models.kp2dtiny import KP2DTinyV2, KP2DTinyV3, get_config, tiny_factory; "
+            "import nano_vs_slam_b200 as n; assert KP2DTinyV2 is n.KP2DTinyV2; print('ok')")
+    env = dict(os.environ, PYTHONPATH=os.path.join(repo, "nano_vs_slam_b200", "compat") + os.pathsep + repo)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
