@@ -84,11 +84,47 @@ typedef struct NvsConvArgs {
   int32_t act;     /* NVS_ACT_* */
   int32_t out_mode;/* NVS_OUT_* */
   int32_t in_mode; /* NVS_IN_* */
+  int32_t dst_nhwc;  /* 1: dst is (B,H,W,dst_c_total) channels-last (input layout of nvs_conv_tc_*), else NCHW */
+  int32_t dst2_nhwc; /* same for the pooled output */
 } NvsConvArgs;
 
 int nvs_conv_cout_tile(int32_t cout);   /* output-channel tile the kernel uses for `cout` */
 int nvs_conv_cin_chunk(int32_t cin);    /* input-channel chunk (4 or 8) the kernel uses for `cin` */
 int nvs_conv(const NvsConvArgs* args, void* stream);
+
+/* ---- tensor-core 3x3 conv (tcgen05, "3xTF32": fp32-grade accuracy, see csrc/conv_tc.cu) ---------------
+ * Same reference statements as nvs_conv, for layers whose input channel counts are multiples of 32 and
+ * cout <= 128.  Activations are channels-last: src (B,H,W,c_total) fp32; weights packed as
+ * w_hi / w_lo [9][cout_pad][c0+c1] (tap-major, K contiguous; w_hi has the low 13 mantissa bits cleared,
+ * w_lo = w - w_hi; BN folded), bias [cout_pad], cout_pad = nvs_conv_tc_cout_pad(cout).
+ * dst_mode 0: no full-resolution output, 1: plain, 2: PixelShuffle(2) into NHWC (B,2H,2W,cout/4 at dst_c_off);
+ * dst_layout 0: NHWC, 1: NCHW (plain only); dst_pool (optional): MaxPool2d(2,2) of the result, NHWC.
+ * The plan (TMA descriptors + parameters) lives in caller memory of nvs_conv_tc_plan_bytes() bytes. */
+typedef struct NvsConvTcArgs {
+  const float* src0;
+  const float* src1; /* may be NULL */
+  const float* w_hi;
+  const float* w_lo;
+  const float* bias;
+  float* dst;      /* may be NULL at plan time when it is supplied per call (dst_override) */
+  float* dst_pool; /* may be NULL */
+  int32_t c0_total, c0_off, c0;
+  int32_t c1_total, c1_off, c1;
+  int32_t dst_c_total, dst_c_off, dst_layout, dst_mode;
+  int32_t pool_c_total, pool_c_off;
+  int32_t B, H, W, cout, act;
+} NvsConvTcArgs;
+int32_t nvs_conv_tc_cout_pad(int32_t cout);
+int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout);
+size_t nvs_conv_tc_plan_bytes(void);
+int nvs_conv_tc_plan_init(void* plan, const NvsConvTcArgs* args);
+int nvs_conv_tc_run(const void* plan, float* dst_override, void* stream);
+
+/* 3x3 conv with 1..4 output channels from a channels-last input (score / location heads,
+ * heads.py:33): src (B,H,W,cin) NHWC, weight [9][cout][cin], bias [cout], dst (B,cout,H,W) NCHW;
+ * act: NVS_ACT_NONE / SIGMOID / TANH. */
+int nvs_conv_small(const float* src, const float* weight, const float* bias, float* dst, int32_t B, int32_t H,
+                   int32_t W, int32_t cin, int32_t cout, int32_t act, void* stream);
 
 /* depthwise 3x3 + bias (DsConv2d first half, modules/segformer.py:46-54). w: (C,3,3), bias: (C). */
 int nvs_dwconv3x3(const float* src, const float* w, const float* bias, float* dst,

@@ -29,6 +29,18 @@ class NvsConvArgs(C.Structure):
         ("B", _i32), ("H", _i32), ("W", _i32),
         ("in_H", _i32), ("in_W", _i32),
         ("cout", _i32), ("ksize", _i32), ("act", _i32), ("out_mode", _i32), ("in_mode", _i32),
+        ("dst_nhwc", _i32), ("dst2_nhwc", _i32),
+    ]
+
+
+class NvsConvTcArgs(C.Structure):
+    _fields_ = [
+        ("src0", _vp), ("src1", _vp), ("w_hi", _vp), ("w_lo", _vp), ("bias", _vp), ("dst", _vp), ("dst_pool", _vp),
+        ("c0_total", _i32), ("c0_off", _i32), ("c0", _i32),
+        ("c1_total", _i32), ("c1_off", _i32), ("c1", _i32),
+        ("dst_c_total", _i32), ("dst_c_off", _i32), ("dst_layout", _i32), ("dst_mode", _i32),
+        ("pool_c_total", _i32), ("pool_c_off", _i32),
+        ("B", _i32), ("H", _i32), ("W", _i32), ("cout", _i32), ("act", _i32),
     ]
 
 
@@ -40,6 +52,12 @@ SIGNATURES = {
     "nvs_conv_cout_tile": (_i32, [_i32]),
     "nvs_conv_cin_chunk": (_i32, [_i32]),
     "nvs_conv": (_i32, [C.POINTER(NvsConvArgs), _vp]),
+    "nvs_conv_tc_cout_pad": (_i32, [_i32]),
+    "nvs_conv_tc_supported": (_i32, [_i32, _i32, _i32]),
+    "nvs_conv_tc_plan_bytes": (_sz, []),
+    "nvs_conv_tc_plan_init": (_i32, [_vp, C.POINTER(NvsConvTcArgs)]),
+    "nvs_conv_tc_run": (_i32, [_vp, _vp, _vp]),
+    "nvs_conv_small": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nvs_dwconv3x3": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "nvs_channel_layernorm": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "nvs_softmax_channels": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),

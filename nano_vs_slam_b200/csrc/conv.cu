@@ -32,6 +32,7 @@ struct ConvP {
   int H, W, inH, inW;
   int cin_pad, cout, cout_pad;
   int act, out_mode, in_mode;
+  int dst_nhwc, dst2_nhwc;  // store layout of dst / dst2: 0 = NCHW planes, 1 = NHWC (feeds the tensor-core convs)
   int tiles_x;
 };
 
@@ -203,7 +204,27 @@ __global__ void __launch_bounds__(32 * WN * WM, 2) conv_kernel(const ConvP p) {
 
   const bool x1ok = gx0 + 1 < p.W;
 
-  if (p.out_mode == NVS_OUT_PLAIN || p.out_mode == NVS_OUT_BOTH) {
+  if ((p.out_mode == NVS_OUT_PLAIN || p.out_mode == NVS_OUT_BOTH) && p.dst_nhwc) {
+    // NHWC: the thread's 8 channels of one pixel are contiguous (2 x 16-byte stores)
+    const bool full8 = co0 + 8 <= p.cout && ((p.dst_c_total | p.dst_c_off) & 3) == 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (gy0 + r >= p.H) break;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c == 1 && !x1ok) break;
+        float* d = p.dst + (((size_t)b * p.H + gy0 + r) * p.W + gx0 + c) * p.dst_c_total + p.dst_c_off + co0;
+        if (full8) {
+          reinterpret_cast<float4*>(d)[0] = make_float4(acc[r][c][0], acc[r][c][1], acc[r][c][2], acc[r][c][3]);
+          reinterpret_cast<float4*>(d)[1] = make_float4(acc[r][c][4], acc[r][c][5], acc[r][c][6], acc[r][c][7]);
+        } else {
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (co0 + o < p.cout) d[o] = acc[r][c][o];
+        }
+      }
+    }
+  } else if (p.out_mode == NVS_OUT_PLAIN || p.out_mode == NVS_OUT_BOTH) {
     const bool vec = x1ok && ((p.W & 1) == 0);
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -225,7 +246,27 @@ __global__ void __launch_bounds__(32 * WN * WM, 2) conv_kernel(const ConvP p) {
     // MaxPool2d(2,2), floor: thread-local because the thread owns aligned 2x2 blocks.
     const int Hp = p.H >> 1, Wp = p.W >> 1;
     const int qx = gx0 >> 1;
-    if (qx < Wp) {
+    if (qx < Wp && p.dst2_nhwc) {
+      const bool full8 = co0 + 8 <= p.cout && ((p.dst2_c_total | p.dst2_c_off) & 3) == 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int qy = (gy0 >> 1) + h;
+        if (qy >= Hp) break;
+        float m[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          m[o] = fmaxf(fmaxf(acc[2 * h][0][o], acc[2 * h][1][o]), fmaxf(acc[2 * h + 1][0][o], acc[2 * h + 1][1][o]));
+        float* d = p.dst2 + (((size_t)b * Hp + qy) * Wp + qx) * p.dst2_c_total + p.dst2_c_off + co0;
+        if (full8) {
+          reinterpret_cast<float4*>(d)[0] = make_float4(m[0], m[1], m[2], m[3]);
+          reinterpret_cast<float4*>(d)[1] = make_float4(m[4], m[5], m[6], m[7]);
+        } else {
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (co0 + o < p.cout) d[o] = m[o];
+        }
+      }
+    } else if (qx < Wp) {
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
         if (co0 + o >= p.cout) break;
@@ -367,6 +408,8 @@ extern "C" int nvs_conv(const NvsConvArgs* a, void* stream) {
   p.cout = a->cout;
   p.cout_pad = (a->cout + ct - 1) / ct * ct;
   p.act = a->act; p.out_mode = a->out_mode; p.in_mode = a->in_mode;
+  p.dst_nhwc = a->dst_nhwc; p.dst2_nhwc = a->dst2_nhwc;
+  if (a->out_mode == NVS_OUT_SHUFFLE && a->dst_nhwc) return NVS_ERR_UNSUPPORTED;
   p.tiles_x = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->ksize == 3) {

@@ -193,6 +193,50 @@ __global__ void decode_kernel(const float* __restrict__ score, const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3x3 conv with 1..4 output channels from a channels-last map (score / location heads, heads.py:33).
+// 0.03 % of the model's FLOPs: one thread per output pixel, 16-byte loads of the pixel's channel vector
+// for each tap (neighbouring threads re-hit L1), weights broadcast from shared memory.  Output NCHW.
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_small_kernel(const float* __restrict__ src,
+                                                         const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ dst,
+                                                         int H, int W, int cin, int act, size_t total) {
+  extern __shared__ __align__(16) float ws[];  // [9][COUT][cin]
+  for (int i = threadIdx.x; i < 9 * COUT * cin; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const size_t b = i / ((size_t)W * H);
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const float4* s = reinterpret_cast<const float4*>(src + ((b * H + yy) * (size_t)W + xx) * cin);
+      const float4* wt = reinterpret_cast<const float4*>(ws + tap * COUT * cin);
+      for (int c4 = 0; c4 < cin / 4; ++c4) {
+        const float4 v = __ldg(s + c4);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float4 k = wt[o * (cin / 4) + c4];
+          acc[o] = fmaf(v.x, k.x, acc[o]);
+          acc[o] = fmaf(v.y, k.y, acc[o]);
+          acc[o] = fmaf(v.z, k.z, acc[o]);
+          acc[o] = fmaf(v.w, k.w, acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o)
+      dst[((b * COUT + o) * H + y) * (size_t)W + x] = apply_act(acc[o] + bias[o], act, o);
+  }
+}
+
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 32;
@@ -262,6 +306,25 @@ extern "C" int nvs_decode(const float* score, const float* shift, const float* f
     decode_kernel<32><<<grid_for(total, 128), 128, 0, st>>>(score, shift, feat, out_score, out_coord, out_feat, Hc, Wc, D, Hf, Wf, H, W, (float)cell, step, cross_ratio, total);
   else
     decode_kernel<128><<<grid_for(total, 128), 128, 0, st>>>(score, shift, feat, out_score, out_coord, out_feat, Hc, Wc, D, Hf, Wf, H, W, (float)cell, step, cross_ratio, total);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+extern "C" int nvs_conv_small(const float* src, const float* weight, const float* bias, float* dst, int32_t B,
+                              int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t act, void* stream) {
+  if (!src || !weight || !bias || !dst || B <= 0 || H <= 0 || W <= 0) return NVS_ERR_ARG;
+  if (cin <= 0 || (cin % 4) != 0 || cout < 1 || cout > 4) return NVS_ERR_UNSUPPORTED;
+  const size_t total = (size_t)B * H * W;
+  const size_t smem = sizeof(float) * 9 * cout * cin;
+  if (smem > 48 * 1024) return NVS_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(total, 128);
+  switch (cout) {
+    case 1: conv_small_kernel<1><<<grid, 128, smem, st>>>(src, weight, bias, dst, H, W, cin, act, total); break;
+    case 2: conv_small_kernel<2><<<grid, 128, smem, st>>>(src, weight, bias, dst, H, W, cin, act, total); break;
+    case 3: conv_small_kernel<3><<<grid, 128, smem, st>>>(src, weight, bias, dst, H, W, cin, act, total); break;
+    case 4: conv_small_kernel<4><<<grid, 128, smem, st>>>(src, weight, bias, dst, H, W, cin, act, total); break;
+  }
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }

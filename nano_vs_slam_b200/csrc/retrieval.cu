@@ -279,17 +279,36 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float d = fmaf(-2.f, v[j], xs[c * 32 + j]);
-            if (d < thr) {
-              my_d[pmax] = d;
-              my_i[pmax] = n0 + c * 32 + j;
-              thr = my_d[0];
-              pmax = 0;
-              for (int q = 1; q < p.k; ++q) {
-                const float w = my_d[q];
-                if (w > thr) {
-                  thr = w;
-                  pmax = q;
+            // Warp-cooperative insertion: a per-lane "replace max + rescan k entries" serialises up to 32
+            // divergent scans per column; instead the whole warp services one inserting row at a time
+            // (lane q holds list entry q of that row; 5-step shuffle arg-max finds the new threshold).
+            unsigned pend = __ballot_sync(0xffffffffu, d < thr);
+            while (pend) {
+              const int src = __ffs(pend) - 1;
+              pend &= pend - 1;
+              const float dv = __shfl_sync(0xffffffffu, d, src);
+              const int pm = __shfl_sync(0xffffffffu, pmax, src);
+              float* rd = list_d + (ew * 32 + src) * p.kp;
+              int32_t* ri = list_i + (ew * 32 + src) * p.kp;
+              if (lane == 0) {
+                rd[pm] = dv;
+                ri[pm] = n0 + c * 32 + j;
+              }
+              __syncwarp();
+              float e = lane < p.k ? rd[lane] : -INFINITY;
+              int pos = lane;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const float oe = __shfl_xor_sync(0xffffffffu, e, o);
+                const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+                if (oe > e || (oe == e && op < pos)) {
+                  e = oe;
+                  pos = op;
                 }
+              }
+              if (lane == src) {
+                thr = e;
+                pmax = pos;
               }
             }
           }

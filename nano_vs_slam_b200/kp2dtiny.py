@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import copy
 import inspect
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -276,6 +277,22 @@ class _Plan:
         if out_name is not None:
             self.out_slots.setdefault(out_name, []).append(args)
 
+    def buf_nhwc(self, name: str, c: int, h: int, w: int) -> torch.Tensor:
+        t = torch.empty(self.B, h, w, c, device=self.device, dtype=torch.float32)
+        self.bufs[name] = t
+        return t
+
+    def tc(self, packed, src0, cout, *, out_name=None, **kw):
+        """Register a tensor-core conv (channels-last operands).  ``out_name``: write that forward output."""
+        op = ops.TcConv(src0, packed, cout, **kw)
+        n_in = src0.shape[1] * src0.shape[2] * ((kw.get("c0") or src0.shape[3]) + (kw.get("c1") or (
+            kw["src1"].shape[3] if kw.get("src1") is not None else 0)))
+        n_out = cout * src0.shape[1] * src0.shape[2] * (1 if kw.get("dst_mode", 1) else 0)
+        if kw.get("dst_pool") is not None:
+            n_out += cout * (src0.shape[1] // 2) * (src0.shape[2] // 2)
+        self.meta[len(self.steps)] = {"flops": op.flops, "bytes": 4.0 * self.B * (n_in + n_out), "shape": op.shape}
+        self.steps.append(("tc", op, out_name))
+
     def call(self, fn, *a):
         self.steps.append(("call", fn, a))
 
@@ -299,6 +316,13 @@ class _KP2DTinyBase(nn.Module):
         if self.depth:
             raise NotImplementedError("depth heads are outside the hot path (SURVEY §8(f))")
         self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
+        # conv backend: "tc" = tcgen05 3xTF32 implicit GEMM on channels-last maps (needs 32-channel multiples:
+        # the S letters), "ffma" = exact fp32 direct conv (any channel count: the N letters).
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        tc_ok = all(c % 32 == 0 for c in (c2, c3, c4, c5, d1 // 4, self.encoder_dim)) and max(c4, c5, d1) <= 128
+        self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
+        if self.conv_backend == "tc" and not tc_ok:
+            raise NotImplementedError("tensor-core conv backend needs channel counts that are multiples of 32")
 
     # --- reference API ------------------------------------------------------------------------
     def gather_info(self):  # kp2dtiny.py:463-485
@@ -365,13 +389,17 @@ class _KP2DTinyBase(nn.Module):
             self._plans = {}
         return self._packed
 
-    def _pk_block(self, m: _ConvBnAct):
+    def _pk_block(self, m: _ConvBnAct, tc: bool = False):
         bn = {"weight": m.bn.weight, "bias": m.bn.bias, "running_mean": m.bn.running_mean,
               "running_var": m.bn.running_var}
+        if tc:
+            return ops.pack_conv_tc(m.conv.weight, bn=bn, eps=m.bn.eps)
         return ops.pack_conv(m.conv.weight, bn=bn, eps=m.bn.eps)
 
     @staticmethod
-    def _pk_conv(m: nn.Conv2d, s2d=False):
+    def _pk_conv(m: nn.Conv2d, s2d=False, tc: bool = False):
+        if tc:
+            return ops.pack_conv_tc(m.weight, bias=m.bias)
         return ops.pack_conv(m.weight, bias=m.bias, s2d=s2d)
 
     def _pack_att(self, m: _AttModule):
@@ -387,20 +415,22 @@ class _KP2DTinyBase(nn.Module):
 
     def _pack(self) -> dict:
         P = {}
+        tc = self.conv_backend == "tc"
         bb = self.backbone
         for n in ("conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"):
-            P["bb." + n] = self._pk_block(getattr(bb, n))
+            # the 3- and 16-channel stem layers stay on the FFMA kernel (K too thin for a 128-byte TMA row)
+            P["bb." + n] = self._pk_block(getattr(bb, n), tc=tc and n not in ("conv1a", "conv1b"))
         sh = self.seg_head
         for i, m in enumerate(sh.convs):
             if isinstance(m, _ConvBnAct):
-                P[f"seg.{i}"] = self._pk_block(m)
+                P[f"seg.{i}"] = self._pk_block(m, tc=tc)
             elif isinstance(m, _AttModule):
                 P[f"seg.{i}"] = self._pack_att(m)
             else:
-                P[f"seg.{i}"] = self._pk_conv(m)
+                P[f"seg.{i}"] = self._pk_conv(m, tc=tc)
         vh = self.vlad_head
         for n in ("convlad1", "convlad2", "convlad3"):
-            P["vlad." + n] = self._pk_block(getattr(vh, n))
+            P["vlad." + n] = self._pk_block(getattr(vh, n), tc=tc)
         if not vh.remove_netvlad:
             nv = vh.netvlad
             P["vlad.assign"] = nv.conv.weight.detach().reshape(nv.num_clusters, nv.dim).contiguous().float()
@@ -452,11 +482,16 @@ class _KP2DTinyBase(nn.Module):
             if prof is not None and i == prof["idx"]:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                run_conv(st[1])
+                if st[0] == "conv":
+                    run_conv(st[1])
+                else:
+                    st[1].run(outs[st[2]] if st[2] is not None else None)
                 e1.record()
                 prof["events"].append((e0, e1))
             elif st[0] == "conv":
                 run_conv(st[1])
+            elif st[0] == "tc":
+                st[1].run(outs[st[2]] if st[2] is not None else None)
             else:
                 st[1](outs, *st[2])
         result = {"score": outs["score"], "coord": outs["coord"], "feat": outs["feat"]}
@@ -470,6 +505,11 @@ class _KP2DTinyBase(nn.Module):
 
     # --- plan construction ------------------------------------------------------------------------
     def _build_plan(self, pl: _Plan):
+        if self.conv_backend == "tc":
+            return self._build_plan_tc(pl)
+        return self._build_plan_ffma(pl)
+
+    def _build_plan_ffma(self, pl: _Plan):
         P = self._packed
         B, H, W = pl.B, pl.H, pl.W
         c1, c2, c3, c4, c5, d1 = self.channel_dims
@@ -547,8 +587,91 @@ class _KP2DTinyBase(nn.Module):
             pl.call(lambda outs, v3=v3, ws=ws: ops.netvlad(v3, P["vlad.assign"], P["vlad.cent"], out=outs["vlad"],
                                                            workspace=ws))
 
+    def _build_plan_tc(self, pl: _Plan):
+        """Same graph as _build_plan_ffma with channels-last intermediates and tcgen05 convs (csrc/conv_tc.cu).
+        Only the 3->16 and 16->32 stem layers, the attention internals and the 1..3-channel head outputs use
+        other kernels."""
+        P = self._packed
+        B, H, W = pl.B, pl.H, pl.W
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        act = ops.ACT_LRELU if self.leaky_relu else ops.ACT_RELU
+        H2, W2 = H // 2, W // 2
+        H4, W4 = H2 // 2, W2 // 2
+        H8, W8 = H4 // 2, W4 // 2
+        nf, ncls = self.nfeatures, self.nClasses
+        pl.out_shapes = {"score": (B, 1, H4, W4), "coord": (B, 2, H4, W4), "feat": (B, nf, H2, W2),
+                         "seg": (B, ncls, H2, W2)}
+        # ---- stem on the FFMA kernel: NCHW in, channels-last pooled map out ----
+        xin = torch.empty(B, 3, H, W, device=pl.device)
+        t1a = pl.buf("t1a", c1, H, W)
+        pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a)
+        pl.in_args = pl.steps[-1][1]
+        p1 = pl.buf_nhwc("p1", c2, H2, W2)
+        pl.conv(P["bb.conv1b"], t1a, c2, act=act, out_mode=ops.OUT_POOL, dst2=p1, dst2_nhwc=True)
+        # ---- backbone on tensor cores ----
+        t2a = pl.buf_nhwc("t2a", c2, H2, W2)
+        pl.tc(P["bb.conv2a"], p1, c2, act=act, dst=t2a)
+        t2b = pl.buf_nhwc("t2b", c3, H2, W2)
+        pl.tc(P["bb.conv2b"], t2a, c3, act=act, dst=t2b)
+        t3a = pl.buf_nhwc("t3a", c3, H2, W2)
+        pl.tc(P["bb.conv3a"], t2b, c3, act=act, dst=t3a)
+        skip = pl.buf_nhwc("skip", c4, H2, W2)
+        p3 = pl.buf_nhwc("p3", c4, H4, W4)
+        pl.tc(P["bb.conv3b"], t3a, c4, act=act, dst=skip, dst_pool=p3)
+        t4a = pl.buf_nhwc("t4a", c4, H4, W4)
+        pl.tc(P["bb.conv4a"], p3, c4, act=act, dst=t4a)
+        xb = pl.buf_nhwc("xb", c4, H4, W4)
+        pl.tc(P["bb.conv4b"], t4a, c4, act=act, dst=xb)
+
+        self._plan_heads_tc(pl, xb, skip, act)
+
+        # ---- segmentation trunk ----
+        sp3 = pl.buf_nhwc("sp3", c5, H8, W8)
+        if self.use_attention:
+            s0 = pl.buf("s0", c5, H4, W4)  # NCHW: the attention block's LN / projections read planes
+            pl.tc(P["seg.0"], xb, c5, act=act, dst=s0, dst_layout=1)
+            sp = pl.buf("sp", c5, H8, W8)
+            self._plan_att(pl, P["seg.1"], s0, c5, H4, W4, "a1", pooled_out=sp)
+            self._plan_att(pl, P["seg.2"], sp, c5, H8, W8, "a2", plain_out=sp3, plain_nhwc=True)
+            nxt = 3
+        else:
+            s0 = pl.buf_nhwc("s0", c5, H4, W4)
+            pl.tc(P["seg.0"], xb, c5, act=act, dst=s0)
+            sp = pl.buf_nhwc("sp", c5, H8, W8)
+            pl.tc(P["seg.1"], s0, c5, act=act, dst=None, dst_mode=0, dst_pool=sp)
+            s2 = pl.buf_nhwc("s2", c5, H8, W8)
+            pl.tc(P["seg.2"], sp, c5, act=act, dst=s2)
+            pl.tc(P["seg.3"], s2, c5, act=act, dst=sp3)
+            nxt = 4
+        ps1 = pl.buf_nhwc("ps1", d1 // 4, H4, W4)
+        pl.tc(P[f"seg.{nxt}"], sp3, d1, act=act, dst=ps1, dst_mode=2)
+        s5 = pl.buf_nhwc("s5", c5, H4, W4)
+        pl.tc(P[f"seg.{nxt + 1}"], ps1, c5, act=act, src1=xb, dst=s5)
+        ps2 = pl.buf_nhwc("ps2", d1 // 4, H2, W2)
+        pl.tc(P[f"seg.{nxt + 2}"], s5, d1, act=act, dst=ps2, dst_mode=2)
+        s7 = pl.buf_nhwc("s7", c5, H2, W2)
+        pl.tc(P[f"seg.{nxt + 3}"], ps2, c5, act=act, src1=skip, dst=s7)
+        self._plan_seg_out_tc(pl, s7, P[f"seg.{nxt + 4}"])
+
+        # ---- VPR head ----
+        enc = self.encoder_dim
+        v1 = pl.buf_nhwc("v1", enc, H4, W4)
+        pl.tc(P["vlad.convlad1"], xb, enc, act=act, dst=v1)
+        v2 = pl.buf_nhwc("v2", enc, H4, W4)
+        pl.tc(P["vlad.convlad2"], v1, enc, act=act, dst=v2)
+        v3 = pl.buf("v3", enc, H4, W4)  # NCHW for the NetVLAD kernel
+        pl.tc(P["vlad.convlad3"], v2, enc, act=act, dst=v3, dst_layout=1)
+        if not self.vlad_head.remove_netvlad:
+            K = self.vlad_head.netvlad.num_clusters
+            pl.out_shapes["vlad"] = (B, K * enc)
+            ws = torch.empty(ops.netvlad_workspace_bytes(B, enc, K, H4 * W4), dtype=torch.uint8, device=pl.device)
+            pl.bufs["vlad_ws"] = ws
+            pl.call(lambda outs, v3=v3, ws=ws: ops.netvlad(v3, P["vlad.assign"], P["vlad.cent"], out=outs["vlad"],
+                                                           workspace=ws))
+
     def _plan_att(self, pl: _Plan, A: dict, x: torch.Tensor, C: int, h: int, w: int, tag: str,
-                  pooled_out: Optional[torch.Tensor] = None, plain_out: Optional[torch.Tensor] = None):
+                  pooled_out: Optional[torch.Tensor] = None, plain_out: Optional[torch.Tensor] = None,
+                  plain_nhwc: bool = False):
         """SegFormerAttentionModule (modules/segformer.py:209-220): LN -> q / kv -> attention -> to_out ->
         LN -> 1x1 -> dw3x3 -> 1x1 -> GELU -> 1x1.  No residual adds."""
         ln1 = pl.buf(tag + ".ln1", C, h, w)
@@ -572,7 +695,7 @@ class _KP2DTinyBase(nn.Module):
         if pooled_out is not None:
             pl.conv(A["m3"], m2, C, ksize=1, out_mode=ops.OUT_POOL, dst2=pooled_out)
         else:
-            pl.conv(A["m3"], m2, C, ksize=1, dst=plain_out)
+            pl.conv(A["m3"], m2, C, ksize=1, dst=plain_out, dst_nhwc=plain_nhwc)
 
     # --- post_processing (kp2dtiny.py:593-647 / :959-1015) ------------------------------------------
     @torch.no_grad()
@@ -633,15 +756,20 @@ class KP2DTinyV2(_KP2DTinyBase):
         self._finish_init()
 
     def _pack_heads(self, P):
-        P["score.a"] = self._pk_block(self.score_head.convDa)
-        P["score.b"] = self._pk_conv(self.score_head.convDb)
-        P["loc.a"] = self._pk_block(self.loc_head.convDa)
-        P["loc.b"] = self._pk_conv(self.loc_head.convDb)
+        tc = self.conv_backend == "tc"
+        P["score.a"] = self._pk_block(self.score_head.convDa, tc=tc)
+        P["loc.a"] = self._pk_block(self.loc_head.convDa, tc=tc)
+        if tc:
+            P["score.b"] = ops.pack_conv_small(self.score_head.convDb.weight, self.score_head.convDb.bias)
+            P["loc.b"] = ops.pack_conv_small(self.loc_head.convDb.weight, self.loc_head.convDb.bias)
+        else:
+            P["score.b"] = self._pk_conv(self.score_head.convDb)
+            P["loc.b"] = self._pk_conv(self.loc_head.convDb)
         d = self.desc_head
-        P["desc.A"] = self._pk_block(d.convA)
-        P["desc.B"] = self._pk_conv(d.convB)
-        P["desc.Aa"] = self._pk_block(d.confAa)
-        P["desc.Bb"] = self._pk_conv(d.confBb)
+        P["desc.A"] = self._pk_block(d.convA, tc=tc)
+        P["desc.B"] = self._pk_conv(d.convB, tc=tc)
+        P["desc.Aa"] = self._pk_block(d.confAa, tc=tc)
+        P["desc.Bb"] = self._pk_conv(d.confBb, tc=tc)
 
     def _plan_heads(self, pl, xb, skip, act):
         P = self._packed
@@ -671,6 +799,28 @@ class KP2DTinyV2(_KP2DTinyBase):
         B, _, H2, W2 = s7.shape
         pl.conv(packed_last, s7, self.nClasses, dst=torch.empty(B, self.nClasses, H2, W2, device=pl.device),
                 out_name="seg")
+
+    def _plan_heads_tc(self, pl, xb, skip, act):
+        P = self._packed
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        B, H4, W4, _ = xb.shape
+        H2, W2 = skip.shape[1:3]
+        sh = pl.buf_nhwc("sh", c4, H4, W4)
+        pl.tc(P["score.a"], xb, c4, act=act, dst=sh)
+        pl.call(lambda outs: ops.conv_small(sh, P["score.b"], act=ops.ACT_SIGMOID, out=outs["score"]))
+        lh = pl.buf_nhwc("lh", c4, H4, W4)
+        pl.tc(P["loc.a"], xb, c4, act=act, dst=lh)
+        pl.call(lambda outs: ops.conv_small(lh, P["loc.b"], act=ops.ACT_TANH, out=outs["coord"]))
+        da = pl.buf_nhwc("da", c4, H4, W4)
+        pl.tc(P["desc.A"], xb, c4, act=act, dst=da)
+        dps = pl.buf_nhwc("dps", c3, H2, W2)
+        pl.tc(P["desc.B"], da, 4 * c3, dst=dps, dst_mode=2)
+        dA = pl.buf_nhwc("dA", c4, H2, W2)
+        pl.tc(P["desc.Aa"], dps, c4, act=act, src1=skip, dst=dA)
+        pl.tc(P["desc.Bb"], dA, self.nfeatures, dst=None, dst_layout=1, dst_c_total=self.nfeatures, out_name="feat")
+
+    def _plan_seg_out_tc(self, pl, s7, packed_last):
+        pl.tc(packed_last, s7, self.nClasses, dst=None, dst_layout=1, dst_c_total=self.nClasses, out_name="seg")
 
 
 class KP2DTinyV3(_KP2DTinyBase):
@@ -709,12 +859,17 @@ class KP2DTinyV3(_KP2DTinyBase):
 
     def _pack_heads(self, P):
         h = self.score_loc_head
-        P["sl.a"] = self._pk_block(h.convDa)
+        tc = self.conv_backend == "tc"
+        P["sl.a"] = self._pk_block(h.convDa, tc=tc)
         # convDb (c4 -> 3) is launched as two tiny convs so that score (ch 0, sigmoid) and shift (ch 1:3, tanh)
         # land directly in their own output tensors (kp2dtiny.py:927-935) without a slicing copy.
-        P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
-        P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
-        P["featB"] = self._pk_conv(self.seg_head.featB)
+        if tc:
+            P["sl.score"] = ops.pack_conv_small(h.convDb.weight[0:1], h.convDb.bias[0:1])
+            P["sl.shift"] = ops.pack_conv_small(h.convDb.weight[1:3], h.convDb.bias[1:3])
+        else:
+            P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
+            P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
+        P["featB"] = self._pk_conv(self.seg_head.featB, tc=tc)
 
     def _plan_heads(self, pl, xb, skip, act):
         P = self._packed
@@ -740,3 +895,25 @@ class KP2DTinyV3(_KP2DTinyBase):
             logits = pl.buf("seg_logits", self.nClasses, H2, W2)
             pl.conv(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds, dst=logits)
             pl.call(lambda outs: ops.softmax_channels(logits, out=outs["seg"]))  # Softmax2d (:942-943)
+
+    def _plan_heads_tc(self, pl, xb, skip, act):
+        P = self._packed
+        c4 = self.channel_dims[3]
+        B, H4, W4, _ = xb.shape
+        sl = pl.buf_nhwc("sl", c4, H4, W4)
+        pl.tc(P["sl.a"], xb, c4, act=act, dst=sl)
+        pl.call(lambda outs: ops.conv_small(sl, P["sl.score"], act=ops.ACT_SIGMOID, out=outs["score"]))
+        pl.call(lambda outs: ops.conv_small(sl, P["sl.shift"], act=ops.ACT_TANH, out=outs["coord"]))
+
+    def _plan_seg_out_tc(self, pl, s7, packed_last):
+        B, H2, W2, c5 = s7.shape
+        ds = self.seg_head.dim_split
+        pl.tc(self._packed["featB"], s7, self.nfeatures, c0_off=0, c0=ds, dst=None, dst_layout=1,
+              dst_c_total=self.nfeatures, out_name="feat")
+        if self.remove_softmax:
+            pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds, dst=None, dst_layout=1,
+                  dst_c_total=self.nClasses, out_name="seg")
+        else:
+            logits = pl.buf("seg_logits", self.nClasses, H2, W2)
+            pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds, dst=logits, dst_layout=1)
+            pl.call(lambda outs: ops.softmax_channels(logits, out=outs["seg"]))

@@ -94,8 +94,8 @@ def make_conv_args(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout:
                    act: int = ACT_NONE, out_mode: int = OUT_PLAIN, in_mode: int = IN_PLAIN,
                    src1: Optional[torch.Tensor] = None, dst: Optional[torch.Tensor] = None,
                    dst2: Optional[torch.Tensor] = None, c0_off: int = 0, c0: Optional[int] = None,
-                   c1_off: int = 0, c1: Optional[int] = None, dst_c_off: int = 0, dst2_c_off: int = 0
-                   ) -> NvsConvArgs:
+                   c1_off: int = 0, c1: Optional[int] = None, dst_c_off: int = 0, dst2_c_off: int = 0,
+                   dst_nhwc: bool = False, dst2_nhwc: bool = False) -> NvsConvArgs:
     """Fill an NvsConvArgs for (B, C, H, W) tensors; shapes are validated here, once, at plan time."""
     B, c0_total, inH, inW = src0.shape
     c0 = c0_total - c0_off if c0 is None else c0
@@ -116,20 +116,25 @@ def make_conv_args(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout:
     cin = (4 * c0) if in_mode == IN_S2D else (c0 + a.c1)
     assert wp.shape[0] == _round_up(cin, conv_cin_chunk(cin)), (wp.shape, cin)
     assert wp.shape[1] == ksize * ksize and wp.shape[2] == _round_up(cout, conv_cout_tile(cout))
-    if out_mode in (OUT_PLAIN, OUT_BOTH):
+    if out_mode in (OUT_PLAIN, OUT_BOTH) and dst_nhwc:
+        assert dst is not None and tuple(dst.shape[:3]) == (B, H, W) and dst.shape[3] >= dst_c_off + cout
+    elif out_mode in (OUT_PLAIN, OUT_BOTH):
         assert dst is not None and tuple(dst.shape[2:]) == (H, W) and dst.shape[0] == B
         assert dst.shape[1] >= dst_c_off + cout
     if out_mode == OUT_SHUFFLE:
         assert dst is not None and tuple(dst.shape[2:]) == (2 * H, 2 * W) and dst.shape[1] >= dst_c_off + cout // 4
-    if out_mode in (OUT_POOL, OUT_BOTH):
+    if out_mode in (OUT_POOL, OUT_BOTH) and dst2_nhwc:
+        assert dst2 is not None and tuple(dst2.shape[1:3]) == (H // 2, W // 2) and dst2.shape[3] >= dst2_c_off + cout
+    elif out_mode in (OUT_POOL, OUT_BOTH):
         assert dst2 is not None and tuple(dst2.shape[2:]) == (H // 2, W // 2)
         assert dst2.shape[1] >= dst2_c_off + cout
     a.dst = _ptr(dst)
     a.dst2 = _ptr(dst2)
-    a.dst_c_total = dst.shape[1] if dst is not None else 0
+    a.dst_c_total = (dst.shape[3] if dst_nhwc else dst.shape[1]) if dst is not None else 0
     a.dst_c_off = dst_c_off
-    a.dst2_c_total = dst2.shape[1] if dst2 is not None else 0
+    a.dst2_c_total = (dst2.shape[3] if dst2_nhwc else dst2.shape[1]) if dst2 is not None else 0
     a.dst2_c_off = dst2_c_off
+    a.dst_nhwc, a.dst2_nhwc = int(dst_nhwc), int(dst2_nhwc)
     a.B, a.H, a.W, a.in_H, a.in_W = B, H, W, inH, inW
     a.cout, a.ksize, a.act, a.out_mode, a.in_mode = cout, ksize, act, out_mode, in_mode
     return a
@@ -149,11 +154,15 @@ def conv(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout: int, **kw
     in_mode, out_mode = kw.get("in_mode", IN_PLAIN), kw.get("out_mode", OUT_PLAIN)
     H, W = (inH // 2, inW // 2) if in_mode == IN_S2D else (inH, inW)
     dst = dst2 = None
-    if out_mode in (OUT_PLAIN, OUT_BOTH):
+    if out_mode in (OUT_PLAIN, OUT_BOTH) and kw.get("dst_nhwc"):
+        dst = torch.empty(B, H, W, cout, device=src0.device, dtype=torch.float32)
+    elif out_mode in (OUT_PLAIN, OUT_BOTH):
         dst = torch.empty(B, cout, H, W, device=src0.device, dtype=torch.float32)
     if out_mode == OUT_SHUFFLE:
         dst = torch.empty(B, cout // 4, 2 * H, 2 * W, device=src0.device, dtype=torch.float32)
-    if out_mode in (OUT_POOL, OUT_BOTH):
+    if out_mode in (OUT_POOL, OUT_BOTH) and kw.get("dst2_nhwc"):
+        dst2 = torch.empty(B, H // 2, W // 2, cout, device=src0.device, dtype=torch.float32)
+    elif out_mode in (OUT_POOL, OUT_BOTH):
         dst2 = torch.empty(B, cout, H // 2, W // 2, device=src0.device, dtype=torch.float32)
     run_conv(make_conv_args(src0, wp, bp, cout, dst=dst, dst2=dst2, **kw))
     if out_mode == OUT_BOTH:
@@ -335,3 +344,117 @@ def match(des1, des2, ratio: float = 0.7, mode: int = 0):
           "nvs_match")
     LAUNCHES[0] += 3 if mode == 0 else 5
     return i1, i2, dd, cnt
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core conv (csrc/conv_tc.cu): channels-last activations, 3xTF32 weights
+# ----------------------------------------------------------------------------------------------
+def conv_tc_supported(c0: int, c1: int, cout: int) -> bool:
+    return bool(lib().nvs_conv_tc_supported(c0, c1, cout))
+
+
+def _fold(weight, bias, bn, eps):
+    w = weight.detach().to(torch.float64)
+    cout = w.shape[0]
+    if bn is not None:
+        s = bn["weight"].detach().double() / torch.sqrt(bn["running_var"].detach().double() + eps)
+        w = w * s.view(-1, 1, 1, 1)
+        b = bn["bias"].detach().double() - bn["running_mean"].detach().double() * s
+    elif bias is not None:
+        b = bias.detach().double()
+    else:
+        b = torch.zeros(cout, dtype=torch.float64, device=w.device)
+    return w.to(torch.float32), b.to(torch.float32)
+
+
+def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
+                 eps: float = 1e-5):
+    """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc.
+
+    w_hi keeps the 10 tf32 mantissa bits (low 13 bits cleared), w_lo = w - w_hi exactly (fp32)."""
+    w, b = _fold(weight, bias, bn, eps)
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    cpad = int(lib().nvs_conv_tc_cout_pad(cout))
+    assert cpad > 0, cout
+    wt = torch.zeros(9, cpad, cin, dtype=torch.float32, device=w.device)
+    wt[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    hi = (wt.view(torch.int32) & -8192).view(torch.float32).contiguous()
+    lo = (wt - hi).contiguous()
+    bp = torch.zeros(cpad, dtype=torch.float32, device=w.device)
+    bp[:cout] = b
+    return hi, lo, bp
+
+
+def pack_conv_small(weight: torch.Tensor, bias: torch.Tensor):
+    """OIHW (cout<=4) -> ([9][cout][cin], bias[cout]) for nvs_conv_small."""
+    w = weight.detach().float()
+    cout, cin = w.shape[:2]
+    return w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous(), bias.detach().float().contiguous()
+
+
+class TcConv(object):
+    """One planned nvs_conv_tc launch: owns the plan memory (TMA descriptors) and keeps operands alive.
+
+    All activation tensors are channels-last *shaped* torch tensors: (B, H, W, C)."""
+
+    def __init__(self, src0: torch.Tensor, packed, cout: int, *, act: int = ACT_NONE,
+                 src1: Optional[torch.Tensor] = None, c0_off: int = 0, c0: Optional[int] = None, c1_off: int = 0,
+                 c1: Optional[int] = None, dst: Optional[torch.Tensor] = None, dst_layout: int = 0,
+                 dst_mode: int = 1, dst_c_off: int = 0, dst_c_total: Optional[int] = None,
+                 dst_pool: Optional[torch.Tensor] = None, pool_c_off: int = 0):
+        hi, lo, bp = packed
+        B, H, W, c0_total = src0.shape
+        a = _cabi.NvsConvTcArgs()
+        a.src0, a.w_hi, a.w_lo, a.bias = src0.data_ptr(), hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
+        a.c0_total, a.c0_off = c0_total, c0_off
+        a.c0 = c0_total - c0_off if c0 is None else c0
+        if src1 is not None:
+            assert tuple(src1.shape[:3]) == (B, H, W)
+            a.src1, a.c1_total, a.c1_off = src1.data_ptr(), src1.shape[3], c1_off
+            a.c1 = src1.shape[3] - c1_off if c1 is None else c1
+        else:
+            a.src1, a.c1_total, a.c1_off, a.c1 = None, 0, 0, 0
+        assert hi.shape[2] == a.c0 + a.c1, (hi.shape, a.c0, a.c1)
+        a.dst = _ptr(dst)
+        a.dst_pool = _ptr(dst_pool)
+        if dst_c_total is None:
+            if dst is None:
+                dst_c_total = cout // 4 if dst_mode == 2 else cout
+            else:
+                dst_c_total = dst.shape[1] if dst_layout == 1 else dst.shape[3]
+        a.dst_c_total, a.dst_c_off, a.dst_layout, a.dst_mode = dst_c_total, dst_c_off, dst_layout, dst_mode
+        a.pool_c_total = dst_pool.shape[3] if dst_pool is not None else 0
+        a.pool_c_off = pool_c_off
+        a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
+        if dst is not None:
+            if dst_mode == 1 and dst_layout == 0:
+                assert tuple(dst.shape[:3]) == (B, H, W)
+            elif dst_mode == 1:
+                assert dst.shape[0] == B and tuple(dst.shape[2:]) == (H, W)
+            elif dst_mode == 2:
+                assert tuple(dst.shape[:3]) == (B, 2 * H, 2 * W)
+        if dst_pool is not None:
+            assert tuple(dst_pool.shape[:3]) == (B, H // 2, W // 2)
+        self._keep = (src0, src1, hi, lo, bp, dst, dst_pool)
+        self._mem = C.create_string_buffer(int(lib().nvs_conv_tc_plan_bytes()))
+        check(lib().nvs_conv_tc_plan_init(self._mem, C.byref(a)), "nvs_conv_tc_plan_init")
+        self.flops = 2.0 * 9 * (a.c0 + a.c1) * cout * H * W * B
+        self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05"
+
+    def run(self, dst_override: Optional[torch.Tensor] = None) -> None:
+        check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _stream()), "nvs_conv_tc_run")
+        LAUNCHES[0] += 1
+
+
+def conv_small(src_nhwc: torch.Tensor, packed, act: int = ACT_NONE, out: Optional[torch.Tensor] = None):
+    """(B,H,W,cin) channels-last -> (B,cout,H,W), cout <= 4 (score / location heads)."""
+    w, b = packed
+    B, H, W, cin = src_nhwc.shape
+    cout = w.shape[1]
+    if out is None:
+        out = torch.empty(B, cout, H, W, device=src_nhwc.device, dtype=torch.float32)
+    check(lib().nvs_conv_small(src_nhwc.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, cin, cout,
+                               act, _stream()), "nvs_conv_small")
+    LAUNCHES[0] += 1
+    return out

@@ -65,3 +65,12 @@ def run(dev, world: int, rank: int, n_db: int = None, n_q: int = None, dim: int 
         "roofline": {"bound": "tensor", "achieved": flops_rank / (gemm / 1e3) / 1e12, "unit": "TFLOP/s",
                      "kind": "bf16 tcgen05.mma cta_group::1 128x256x16"},
     }
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+
+    n_db = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
+    n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+    print(json.dumps(run(torch.device("cuda", 0), 1, 0, n_db=n_db, n_q=n_q, steps=2, warmup=1)))

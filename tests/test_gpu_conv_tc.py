@@ -1,0 +1,112 @@
+"""Tensor-core conv (tcgen05 3xTF32, channels-last) and the small-cout head conv vs torch fp32 on CPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,H,W,act", [
+    (64, 64, 60, 80, 1), (32, 32, 24, 40, 1), (64, 128, 15, 20, 0), (96, 64, 33, 50, 1), (32, 64, 17, 31, 2),
+    (64, 28, 20, 28, 0), (64, 32, 9, 19, 0), (128, 64, 8, 16, 1),
+])
+def test_conv_tc_plain_nhwc_and_nchw(cin, cout, H, W, act):
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(cin + cout + H)
+    B = 3
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x, w, b, padding=1)
+    ref = F.leaky_relu(ref, 0.01) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    xs = _nhwc(x).cuda()
+    cpad = packed[2].numel()
+    if cout % 4 == 0:
+        out = torch.zeros(B, H, W, cout, device="cuda")
+        ops.TcConv(xs, packed, cout, act=act, dst=out, dst_layout=0).run()
+        torch.cuda.synchronize()
+        assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5, rel_err(out.permute(0, 3, 1, 2), ref)
+    out2 = torch.zeros(B, cout, H, W, device="cuda")
+    op = ops.TcConv(xs, packed, cout, act=act, dst=None, dst_layout=1, dst_c_total=cout)
+    op.run(dst_override=out2)
+    torch.cuda.synchronize()
+    assert rel_err(out2, ref) < 2e-5, rel_err(out2, ref)
+
+
+def test_conv_tc_pool_shuffle_concat_slice():
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 22, 38
+    x = torch.randn(B, 32, H, W, generator=g)
+    w = torch.randn(64, 32, 3, 3, generator=g) * 0.08
+    b = torch.randn(64, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    full = torch.zeros(B, H, W, 64, device="cuda")
+    pooled = torch.zeros(B, H // 2, W // 2, 64, device="cuda")
+    ops.TcConv(_nhwc(x).cuda(), packed, 64, act=1, dst=full, dst_pool=pooled).run()
+    assert rel_err(full.permute(0, 3, 1, 2), ref) < 2e-5
+    assert rel_err(pooled.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
+    only = torch.zeros_like(pooled)
+    ops.TcConv(_nhwc(x).cuda(), packed, 64, act=1, dst=None, dst_mode=0, dst_pool=only).run()
+    assert torch.equal(only, pooled)
+    # pixel shuffle (odd and even sizes)
+    for (hh, ww) in ((11, 19), (16, 32)):
+        xs = torch.randn(B, 64, hh, ww, generator=g)
+        w2 = torch.randn(128, 64, 3, 3, generator=g) * 0.05
+        b2 = torch.randn(128, generator=g) * 0.1
+        out = torch.zeros(B, 2 * hh, 2 * ww, 32, device="cuda")
+        ops.TcConv(_nhwc(xs).cuda(), ops.pack_conv_tc(w2.cuda(), bias=b2.cuda()), 128, dst=out, dst_mode=2).run()
+        assert rel_err(out.permute(0, 3, 1, 2), F.pixel_shuffle(F.conv2d(xs, w2, b2, padding=1), 2)) < 2e-5
+    # two sources (concat) + channel slice + BN fold
+    a = torch.randn(B, 32, H, W, generator=g)
+    s = torch.randn(B, 64, H, W, generator=g)
+    conv = torch.nn.Conv2d(96, 64, 3, 1, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(64).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1); bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 1.5)
+        ref = F.leaky_relu(bn(conv(torch.cat([a, s], 1))), 0.01)
+    bnd = {k: getattr(bn, k).cuda() for k in ("weight", "bias", "running_mean", "running_var")}
+    out = torch.zeros(B, H, W, 64, device="cuda")
+    ops.TcConv(_nhwc(a).cuda(), ops.pack_conv_tc(conv.weight.detach().cuda(), bn=bnd), 64, act=1, src1=_nhwc(s).cuda(),
+               dst=out).run()
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5
+    w3 = torch.randn(32, 32, 3, 3, generator=g) * 0.08
+    b3 = torch.randn(32, generator=g) * 0.1
+    out = torch.zeros(B, 32, H, W, device="cuda")
+    ops.TcConv(_nhwc(s).cuda(), ops.pack_conv_tc(w3.cuda(), bias=b3.cuda()), 32, c0_off=32, c0=32, dst=out,
+               dst_layout=1).run()
+    assert rel_err(out, F.conv2d(s[:, 32:], w3, b3, padding=1)) < 2e-5
+
+
+def test_conv_small_and_ffma_nhwc_store():
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(8)
+    B, H, W = 2, 17, 23
+    x = torch.randn(B, 64, H, W, generator=g)
+    for cout, act in ((1, 3), (2, 4), (3, 0)):
+        w = torch.randn(cout, 64, 3, 3, generator=g) * 0.06
+        b = torch.randn(cout, generator=g) * 0.1
+        ref = F.conv2d(x, w, b, padding=1)
+        ref = ref.sigmoid() if act == 3 else (ref.tanh() if act == 4 else ref)
+        out = ops.conv_small(_nhwc(x).cuda(), ops.pack_conv_small(w.cuda(), b.cuda()), act=act)
+        assert rel_err(out, ref) < 2e-5
+    # FFMA conv writing channels-last (plain and pooled) for the tensor-core consumers
+    w = torch.randn(32, 16, 3, 3, generator=g) * 0.1
+    b = torch.randn(32, generator=g) * 0.1
+    x16 = torch.randn(B, 16, 24, 36, generator=g)
+    ref = F.leaky_relu(F.conv2d(x16, w, b, padding=1), 0.01)
+    wp, bp = ops.pack_conv(w.cuda(), bias=b.cuda())
+    full, pooled = ops.conv(x16.cuda(), wp, bp, 32, act=1, out_mode=ops.OUT_BOTH, dst_nhwc=True, dst2_nhwc=True)
+    assert rel_err(full.permute(0, 3, 1, 2), ref) < 2e-5
+    assert rel_err(pooled.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
