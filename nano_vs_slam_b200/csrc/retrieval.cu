@@ -123,6 +123,7 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >
 
 struct Params {
   const float* xnorm;   // [N]   |x|^2 (fp32, from the fp32 rows)
+  float* gbound;        // [Qpad] running upper bound of each query's k-th smallest (|x|^2 - 2 q.x), init +inf
   float* cand_d;        // [Qpad][n_strips][k]  approximate |x|^2 - 2 q.x
   int32_t* cand_i;      // [Qpad][n_strips][k]  row index inside this shard (-1 = empty)
   int Q, N, kblocks;    // kblocks = Dpad / 64
@@ -258,6 +259,9 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       float thr = INFINITY;
       int pmax = 0;
+      const int qrow = mblk * BM + row;
+      // upper bound on this query's final k-th distance, published by units that finished earlier
+      const float gbound = qrow < p.Q ? __ldcg(p.gbound + qrow) : INFINITY;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = t * BN;
         // stage |x|^2 of this tile (+inf past the end of the shard so padded columns never enter a list)
@@ -279,36 +283,19 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float d = fmaf(-2.f, v[j], xs[c * 32 + j]);
-            // Warp-cooperative insertion: a per-lane "replace max + rescan k entries" serialises up to 32
-            // divergent scans per column; instead the whole warp services one inserting row at a time
-            // (lane q holds list entry q of that row; 5-step shuffle arg-max finds the new threshold).
-            unsigned pend = __ballot_sync(0xffffffffu, d < thr);
-            while (pend) {
-              const int src = __ffs(pend) - 1;
-              pend &= pend - 1;
-              const float dv = __shfl_sync(0xffffffffu, d, src);
-              const int pm = __shfl_sync(0xffffffffu, pmax, src);
-              float* rd = list_d + (ew * 32 + src) * p.kp;
-              int32_t* ri = list_i + (ew * 32 + src) * p.kp;
-              if (lane == 0) {
-                rd[pm] = dv;
-                ri[pm] = n0 + c * 32 + j;
-              }
-              __syncwarp();
-              float e = lane < p.k ? rd[lane] : -INFINITY;
-              int pos = lane;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                const float oe = __shfl_xor_sync(0xffffffffu, e, o);
-                const int op = __shfl_xor_sync(0xffffffffu, pos, o);
-                if (oe > e || (oe == e && op < pos)) {
-                  e = oe;
-                  pos = op;
+            // two filters: the row's own k-th best so far (strict) and the bound published by strips that
+            // already finished for this query (<=, ties must survive); insertions are rare after warm-up
+            if (d < thr && d <= gbound) {
+              my_d[pmax] = d;
+              my_i[pmax] = n0 + c * 32 + j;
+              thr = my_d[0];
+              pmax = 0;
+              for (int q = 1; q < p.k; ++q) {
+                const float w = my_d[q];
+                if (w > thr) {
+                  thr = w;
+                  pmax = q;
                 }
-              }
-              if (lane == src) {
-                thr = e;
-                pmax = pos;
               }
             }
           }
@@ -321,9 +308,12 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           acc_phase ^= 1;
         }
       }
-      // flush this (query block, strip) candidate list
-      const int qrow = mblk * BM + row;
+      // flush this (query block, strip) candidate list; a full list tightens the published bound
       if (qrow < p.Q) {
+        if (thr < INFINITY) {
+          if (thr >= 0.f) atomicMin(reinterpret_cast<int*>(p.gbound + qrow), __float_as_int(thr));
+          else atomicMax(reinterpret_cast<unsigned int*>(p.gbound + qrow), __float_as_uint(thr));
+        }
         const size_t o = ((size_t)qrow * p.n_strips + strip) * p.k;
         for (int j = 0; j < p.k; ++j) {
           p.cand_d[o + j] = my_d[j];
@@ -359,6 +349,11 @@ __global__ void to_bf16_norm_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
   ss = warp_sum(ss);
   if (lane == 0) norms[row] = ss;
+}
+
+__global__ void fill_inf_kernel(float* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = INFINITY;
 }
 
 // Per query: keep the kk smallest of n_cand (approximate distance, index) pairs, ascending (d, i).
@@ -530,7 +525,7 @@ static inline int dpad_of(int d) { return (d + BK - 1) / BK * BK; }
 
 struct Layout {
   int dpad, n_mblk, n_tiles, tiles_per_strip, n_strips, kk, qpad;
-  size_t off_qb, off_qn, off_cd, off_ci, off_sd, off_si, total;
+  size_t off_qb, off_qn, off_gb, off_cd, off_ci, off_sd, off_si, total;
 };
 
 static Layout make_layout(long long n_db, int nq, int d, int k) {
@@ -549,6 +544,7 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   size_t o = 0;
   L.off_qb = o; o += al256((size_t)L.qpad * L.dpad * 2);
   L.off_qn = o; o += al256((size_t)L.qpad * 4);
+  L.off_gb = o; o += al256((size_t)L.qpad * 4);
   L.off_cd = o; o += al256((size_t)L.qpad * L.n_strips * k * 4);
   L.off_ci = o; o += al256((size_t)L.qpad * L.n_strips * k * 4);
   L.off_sd = o; o += al256((size_t)nq * L.kk * 4);
@@ -594,6 +590,7 @@ extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + L.off_qb);
   float* qn = reinterpret_cast<float*>(ws + L.off_qn);
+  float* gb = reinterpret_cast<float*>(ws + L.off_gb);
   float* cd = reinterpret_cast<float*>(ws + L.off_cd);
   int32_t* ci = reinterpret_cast<int32_t*>(ws + L.off_ci);
   float* sd = reinterpret_cast<float*>(ws + L.off_sd);
@@ -604,13 +601,15 @@ extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float
   if (e != cudaSuccess) return nvs_set_cuda_error(e);
   to_bf16_norm_kernel<<<(nq + 7) / 8, 256, 0, st>>>(q, qb, qn, nq, d, L.dpad);
   NVS_CHECK_LAUNCH();
+  fill_inf_kernel<<<(L.qpad + 255) / 256, 256, 0, st>>>(gb, L.qpad);
+  NVS_CHECK_LAUNCH();
 
   CUtensorMap mq, mx;
   if (make_map(&mq, qb, (uint64_t)L.qpad, (uint64_t)L.dpad, BM) != NVS_OK) return NVS_ERR_CUDA;
   if (make_map(&mx, db_bf16, (uint64_t)n_db, (uint64_t)L.dpad, BN) != NVS_OK) return NVS_ERR_CUDA;
 
   Params p;
-  p.xnorm = db_norms; p.cand_d = cd; p.cand_i = ci;
+  p.xnorm = db_norms; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
   p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
   p.k = k; p.kp = k | 1;
   p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;

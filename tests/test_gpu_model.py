@@ -12,12 +12,14 @@ from util import REL_TOL, golden_cases, load_golden, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _model(letter, n_classes, v3, wseed):
+def _model(letter, n_classes, v3, wseed, backend=None):
     from nano_vs_slam_b200 import tiny_factory
     from nano_vs_slam_b200.synthetic import spread_init
 
     with contextlib.redirect_stdout(io.StringIO()):
         m = tiny_factory(letter, n_classes, v3=v3)
+    if backend is not None:
+        m.conv_backend = backend  # "tc" (tcgen05 3xTF32, default for S letters) or "ffma" (exact fp32)
     sd = spread_init(m.state_dict(), wseed)
     m.load_state_dict(sd, strict=True)
     m.eval()
@@ -82,6 +84,25 @@ def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W):
         got = set(sel["cell"][b, :n].cpu().tolist())
         jac = len(got & set(cells.tolist())) / max(1, len(got | set(cells.tolist())))
         assert jac >= 0.99, jac  # single near-threshold flips allowed at k=300 (1/300 > 0.1 %)
+
+
+@pytest.mark.parametrize("letter,v3", [("S", False), ("S_A", True)])
+def test_both_conv_backends_agree_with_golden(letter, v3):
+    """The S letters run on tensor cores by default; the exact-fp32 FFMA backend must stay green too."""
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    path = [p for p in golden_cases() if p.endswith(f"model_{'v3' if v3 else 'v2'}_{letter}.npz")][0]
+    c = load_golden(path)
+    x = synthetic_frames(c["B"], c["H"], c["W"], c["xseed"]).cuda()
+    outs = {}
+    for backend in ("tc", "ffma"):
+        m, _ = _model(c["letter"], c["n_classes"], c["v3"], c["wseed"], backend=backend)
+        assert m.conv_backend == backend
+        outs[backend] = m(x)
+        for k in ("score", "coord", "feat", "vlad", "seg"):
+            assert rel_err(outs[backend][k], c["fwd"][k]) < REL_TOL, (backend, k, rel_err(outs[backend][k], c["fwd"][k]))
+    for k in ("feat", "seg", "vlad"):
+        assert rel_err(outs["tc"][k], outs["ffma"][k]) < REL_TOL
 
 
 def test_state_dict_roundtrip_and_errors():
