@@ -9,15 +9,19 @@
 //               canonical K-major SWIZZLE_128B layout; out-of-image coordinates are zero filled by TMA,
 //               which *is* the convolution's zero padding.  No im2col buffer, no halo bookkeeping.
 //   B operand:  packed weights [tap][Cout][Cin] (hi and lo parts), 3-D TMA box (32, Cout, 1).
-//   split:      4 converter warps turn the landed fp32 tile into hi (low 13 mantissa bits cleared, in place)
-//               and lo = a - hi (second buffer) so only ONE copy of the activations ever crosses L2/HBM.
-//   MMA:        one thread issues 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Cout, K=8) per stage
+//   split:      4 converter warps read the landed fp32 tile (one 128-byte swizzled row per thread), form
+//               hi (low 13 mantissa bits cleared) and lo = a - hi and write both straight into TENSOR MEMORY
+//               with tcgen05.st (lane = pixel, column = channel): only ONE copy of the activations crosses
+//               L2/HBM, and the A operand never goes back through shared memory (the first version of this
+//               kernel was shared-memory-bandwidth bound: TMA writes + split round trip + 3 UMMA operand reads).
+//   MMA:        one thread issues 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Cout, K=8) per stage with
+//               A from TMEM and B (weights) from shared memory
 //   epilogue:   4 warps read TMEM (thread = pixel, columns = channels), add bias, activation, then store
 //               NHWC / NCHW, 2x2 max-pool via warp shuffles (a warp owns 2 image rows x 16 cols) or
 //               pixel-shuffled NHWC.
 //
-// Warp roles (320 threads): 0-3 epilogue (TMEM lane quadrants), 4-7 converters, 8 TMA producer,
-// 9 TMEM allocator + MMA issuer.  Persistent CTAs, static round-robin over (frame, tile_y, tile_x).
+// Warp roles: 0-3 epilogue (TMEM lane quadrants), then CONV_GROUPS x 4 converter warps (groups take pipeline
+// stages round-robin), one TMA producer warp, one TMEM-allocator + MMA-issuer warp.  Persistent CTAs, static round-robin over (frame, tile_y, tile_x).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -29,19 +33,36 @@ constexpr int TM = 128;            // pixels per tile
 constexpr int TX = 16, TY = 8;     // tile shape
 constexpr int KC = 32;             // channels per stage (128 bytes of fp32)
 constexpr int A_BYTES = TM * KC * 4;   // 16 KiB
-constexpr int THREADS = 320;
+constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each) taking pipeline stages round-robin
+constexpr int WARP_TMA = 4 + 4 * CONV_GROUPS;
+constexpr int WARP_MMA = WARP_TMA + 1;
+constexpr int THREADS = 32 * (WARP_MMA + 1);
 
 template <int COUT>
 struct Cfg {
   static constexpr int W_BYTES = COUT * KC * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int STAGES = (COUT <= 64) ? 4 : 3;
-  static constexpr int TMEM_COLS = (2 * COUT < 32) ? 32 : 2 * COUT;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * W_BYTES;  // fp32 activation tile + W_hi + W_lo
+  // tcgen05.mma costs max(N/2, ~50) cycles per instruction (profiles/microbench/mma_rate.cu), so for
+  // Cout <= 64 the two products that share A_hi are issued as ONE instruction with N = 2*Cout against the
+  // concatenated [W_hi ; W_lo] tile (they are contiguous in shared memory): columns [0,Cout) collect
+  // a_hi w_hi + a_lo w_hi, columns [Cout,2Cout) collect a_hi w_lo, and the epilogue adds the two halves.
+  static constexpr bool CONCAT = COUT <= 64;
+  static constexpr int ACC_STAGE_COLS = CONCAT ? 2 * COUT : COUT;
+  static constexpr int ACC_COLS = 2 * ACC_STAGE_COLS;   // double-buffered accumulator
+  static constexpr int A_COLS = 2 * KC;                 // per stage: 32 columns hi + 32 columns lo
+  // pipeline depth: bounded by TMEM (ACC_COLS + STAGES*A_COLS <= 512) and by ~200 KB of shared memory
+  static constexpr int STAGES = (COUT <= 32) ? 6 : 4;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(ACC_COLS + STAGES * A_COLS <= 512, "TMEM budget");
+  static_assert(STAGES * STAGE_BYTES <= 200 * 1024, "smem budget");
   static constexpr int SM_BIAS = STAGES * STAGE_BYTES;
   static constexpr int SM_BAR = SM_BIAS + COUT * 4;
   static constexpr int SMEM_BYTES = SM_BAR + 256 + 1024;
-  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                                    ((uint32_t)(TM >> 4) << 24);
+  static constexpr uint32_t idesc_n(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  }
+  static constexpr uint32_t IDESC = idesc_n(COUT);
+  static constexpr uint32_t IDESC2 = idesc_n(2 * COUT);
 };
 
 struct Params {
@@ -111,6 +132,27 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row m, one tf32 element per 32-bit column), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -160,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < COUT; i += THREADS) bias_s[i] = p.bias[i];
-  if (warp == 8 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
@@ -175,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -189,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int chunks = p.c0_chunks + p.c1_chunks;
   const int ksteps = 9 * chunks;  // pipeline stages per tile
 
-  if (warp == 8) {
+  if (warp == WARP_TMA) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0;
@@ -208,8 +250,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             else
               tma_load_4d(s_base, &map_a1, full_bar(stage), p.c1_off + (ch - p.c0_chunks) * KC, x0 + kx - 1,
                           y0 + ky - 1, b);
-            tma_load_3d(s_base + 2 * A_BYTES, &map_whi, full_bar(stage), ch * KC, 0, tap);
-            tma_load_3d(s_base + 2 * A_BYTES + C::W_BYTES, &map_wlo, full_bar(stage), ch * KC, 0, tap);
+            tma_load_3d(s_base + A_BYTES, &map_whi, full_bar(stage), ch * KC, 0, tap);
+            tma_load_3d(s_base + A_BYTES + C::W_BYTES, &map_wlo, full_bar(stage), ch * KC, 0, tap);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -218,29 +260,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // =========================== hi / lo split ===========================
-    const int ct = threadIdx.x - 128;  // 0..127
-    int stage = 0;
+  } else if (warp >= 4 && warp < WARP_TMA) {
+    // =========================== hi / lo split -> TMEM ===========================
+    const int cw = warp & 3;            // TMEM lane quadrant this warp may write (warp % 4)
+    const int grp = (warp - 4) >> 2;    // converter group: handles k-steps with (global index % CONV_GROUPS == grp)
+    const int r = cw * 32 + lane;       // tile row (pixel) == TMEM lane
+    int stage = 0, turn = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(full_bar(stage), phase);
-        float4* hi = reinterpret_cast<float4*>(sm + stage * C::STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(sm + stage * C::STAGE_BYTES + A_BYTES);
-#pragma unroll
-        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {  // element-wise, so the swizzled layout is preserved
-          const int idx = ct + i * 128;
-          float4 v = hi[idx];
-          float4 h;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          hi[idx] = h;
-          lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        if (turn != grp) {
+          if (++turn == CONV_GROUPS) turn = 0;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to UMMA
+        if (++turn == CONV_GROUPS) turn = 0;
+        mbar_wait(full_bar(stage), phase);
+        // row r of the TMA box: 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7)) (SWIZZLE_128B); the
+        // XOR makes the 8 lanes of a quarter-warp hit 8 different bank groups -> conflict-free LDS.128
+        const uint8_t* rowp = sm + stage * C::STAGE_BYTES + r * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+          const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+            hi[4 * c + e] = h;
+            lo[4 * c + e] = __float_as_uint(f[e] - __uint_as_float(h));
+          }
+        }
+        const uint32_t ta = tmem_base + (uint32_t)(C::ACC_COLS + stage * C::A_COLS) + ((uint32_t)(cw * 32) << 16);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + KC, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         mbar_arrive(conv_bar(stage));
         if (++stage == STAGES) {
           stage = 0;
@@ -248,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       int stage = 0, acc = 0;
@@ -256,19 +314,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(conv_bar(stage), phase);
           tc_fence_after();
           const uint32_t s_base = base + stage * C::STAGE_BYTES;
-          const uint64_t a_hi = make_sdesc(s_base), a_lo = make_sdesc(s_base + A_BYTES);
-          const uint64_t w_hi = make_sdesc(s_base + 2 * A_BYTES), w_lo = make_sdesc(s_base + 2 * A_BYTES + C::W_BYTES);
+          const uint32_t a_hi = tmem_base + (uint32_t)(C::ACC_COLS + stage * C::A_COLS), a_lo = a_hi + KC;
+          const uint64_t w_hi = make_sdesc(s_base + A_BYTES), w_lo = make_sdesc(s_base + A_BYTES + C::W_BYTES);
 #pragma unroll
-          for (int k = 0; k < KC / 8; ++k) {  // 8 tf32 = 32 bytes along K: +2 in the (addr >> 4) field
+          for (int k = 0; k < KC / 8; ++k) {
+            // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
             const uint64_t o = (uint64_t)(2 * k);
-            tc_mma_tf32(d_tmem, a_hi + o, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
-            tc_mma_tf32(d_tmem, a_lo + o, w_hi + o, C::IDESC, 1u);
-            tc_mma_tf32(d_tmem, a_hi + o, w_lo + o, C::IDESC, 1u);
+            if (C::CONCAT) {
+              tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC2, (ks | k) != 0 ? 1u : 0u);  // x [W_hi;W_lo]
+              tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
+            } else {
+              tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
+              tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
+              tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_lo + o, C::IDESC, 1u);
+            }
           }
           tc_commit(empty_bar(stage));
           if (++stage == STAGES) {
@@ -294,12 +358,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool valid = gx < p.W && gy < p.H;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * COUT) + ((uint32_t)(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < COUT / 32; ++cc) {
         float v[32];
         __syncwarp();
         tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+        if (C::CONCAT) {
+          float v2[32];
+          tmem_ld32(taddr + (uint32_t)(COUT + cc * 32), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float a = v[j] + bias_s[cc * 32 + j];
@@ -363,7 +433,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)C::TMEM_COLS)

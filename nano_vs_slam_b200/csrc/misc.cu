@@ -10,12 +10,11 @@ namespace nvs {
 __global__ void dwconv3x3_kernel(const float* __restrict__ src, const float* __restrict__ w,
                                  const float* __restrict__ bias, float* __restrict__ dst, int C, int H,
                                  int W, size_t total) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {  // 32-bit index math: 64-bit div/mod is emulated
     const int x = (int)(i % W);
     const int y = (int)((i / W) % H);
-    const size_t bc = i / ((size_t)W * H);
-    const int c = (int)(bc % C);
+    const unsigned bc = i / (unsigned)(W * H);
+    const int c = (int)(bc % (unsigned)C);
     const float* s = src + bc * (size_t)H * W;
     const float* k = w + c * 9;
     float acc = bias ? bias[c] : 0.f;
@@ -44,8 +43,7 @@ template <int MODE>
 __global__ void channel_stat_kernel(const float* __restrict__ src, const float* __restrict__ g,
                                     const float* __restrict__ bb, float* __restrict__ dst, int C, int HW,
                                     size_t npix, float eps) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix;
-       i += (size_t)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)npix; i += gridDim.x * blockDim.x) {
     const size_t b = i / HW;
     const int s = (int)(i - b * HW);
     const float* p = src + b * (size_t)C * HW + s;
@@ -87,8 +85,7 @@ __global__ void channel_stat_kernel(const float* __restrict__ src, const float* 
 __global__ void seg_argmax_kernel(const float* __restrict__ seg, const float* __restrict__ coord,
                                   int64_t* __restrict__ out, int C, int Hs, int Ws, int Hc, int Wc, int H,
                                   int W, size_t total) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {  // 32-bit index math: 64-bit div/mod is emulated
     size_t b;
     int sy, sx;
     bool inb = true;
@@ -142,8 +139,7 @@ __global__ void decode_kernel(const float* __restrict__ score, const float* __re
                               int D, int Hf, int Wf, int H, int W, float cell, float step, float cross,
                               size_t total) {
   const int ncell = Hc * Wc;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {  // 32-bit index math: 64-bit div/mod is emulated
     const size_t b = i / ncell;
     const int cidx = (int)(i - b * ncell);
     const int cy = cidx / Wc, cx = cidx - cy * Wc;
@@ -203,39 +199,77 @@ __global__ void __launch_bounds__(128) conv_small_kernel(const float* __restrict
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ dst,
                                                          int H, int W, int cin, int act, size_t total) {
+  // A warp handles 8 consecutive pixels (linear index over b,y,x).  16 lanes share one pixel: lane q = l%16
+  // owns the 16-byte channel chunks q, q+16, ... of that pixel, so every load instruction of the warp reads
+  // whole 128-byte lines (the first version gave each lane its own pixel = 32 lines per load and ran 10x
+  // slower than its byte count).  Partial dot products are reduced over the 16 lanes by shuffles.
   extern __shared__ __align__(16) float ws[];  // [9][COUT][cin]
   for (int i = threadIdx.x; i < 9 * COUT * cin; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const size_t b = i / ((size_t)W * H);
-    float acc[COUT];
+  const int lane = threadIdx.x & 31, q = lane & 15, half = lane >> 4;
+  const int chunks = cin >> 2;  // float4 chunks per pixel
+  const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned utotal = (unsigned)total, uW = (unsigned)W, uH = (unsigned)H;
+  for (unsigned p0 = warp_id * 8; p0 < utotal; p0 += n_warps * 8) {
+    float acc[4][COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const float4* s = reinterpret_cast<const float4*>(src + ((b * H + yy) * (size_t)W + xx) * cin);
-      const float4* wt = reinterpret_cast<const float4*>(ws + tap * COUT * cin);
-      for (int c4 = 0; c4 < cin / 4; ++c4) {
-        const float4 v = __ldg(s + c4);
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-          const float4 k = wt[o * (cin / 4) + c4];
-          acc[o] = fmaf(v.x, k.x, acc[o]);
-          acc[o] = fmaf(v.y, k.y, acc[o]);
-          acc[o] = fmaf(v.z, k.z, acc[o]);
-          acc[o] = fmaf(v.w, k.w, acc[o]);
+      for (int o = 0; o < COUT; ++o) acc[i][o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned pix = p0 + 2 * i + half;
+      if (pix >= utotal) continue;
+      const int x = (int)(pix % uW);
+      const int y = (int)((pix / uW) % uH);
+      const size_t b = pix / (uW * uH);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float4* s = reinterpret_cast<const float4*>(src + ((b * H + yy) * (size_t)W + xx) * cin);
+        const float4* wt = reinterpret_cast<const float4*>(ws + tap * COUT * cin);
+        for (int c4 = q; c4 < chunks; c4 += 16) {
+          const float4 v = __ldg(s + c4);
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) {
+            const float4 k = wt[o * chunks + c4];
+            acc[i][o] = fmaf(v.x, k.x, acc[i][o]);
+            acc[i][o] = fmaf(v.y, k.y, acc[i][o]);
+            acc[i][o] = fmaf(v.z, k.z, acc[i][o]);
+            acc[i][o] = fmaf(v.w, k.w, acc[i][o]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < COUT; ++o)
-      dst[((b * COUT + o) * H + y) * (size_t)W + x] = apply_act(acc[o] + bias[o], act, o);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        float v = acc[i][o];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        acc[i][o] = v;
+      }
+    if (q == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned pix = p0 + 2 * i + half;
+        if (pix >= utotal) continue;
+        const int x = (int)(pix % uW);
+        const int y = (int)((pix / uW) % uH);
+        const size_t b = pix / (uW * uH);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o)
+          dst[((b * COUT + o) * H + y) * (size_t)W + x] = apply_act(acc[i][o] + bias[o], act, o);
+      }
+    }
   }
 }
+
+#define NVS_REQUIRE_32BIT(total) do { if ((total) >= 0x7fffffffULL) return NVS_ERR_UNSUPPORTED; } while (0)
 
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
@@ -251,6 +285,7 @@ extern "C" int nvs_dwconv3x3(const float* src, const float* w, const float* bias
                              int32_t C, int32_t H, int32_t W, void* stream) {
   if (!src || !w || !dst || B <= 0 || C <= 0 || H <= 0 || W <= 0) return NVS_ERR_ARG;
   const size_t total = (size_t)B * C * H * W;
+  NVS_REQUIRE_32BIT(total);
   dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, w, bias, dst, C, H, W, total);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
@@ -287,6 +322,7 @@ extern "C" int nvs_seg_argmax(const float* seg, const float* coord, int64_t* out
   if (!seg || !out || B <= 0 || C <= 0 || Hs <= 0 || Ws <= 0) return NVS_ERR_ARG;
   if (coord && (Hc <= 0 || Wc <= 0 || H <= 1 || W <= 1)) return NVS_ERR_ARG;
   const size_t total = coord ? (size_t)B * Hc * Wc : (size_t)B * Hs * Ws;
+  NVS_REQUIRE_32BIT(total);
   seg_argmax_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(seg, coord, out, C, Hs, Ws, Hc, Wc, H, W, total);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
@@ -318,7 +354,7 @@ extern "C" int nvs_conv_small(const float* src, const float* weight, const float
   const size_t smem = sizeof(float) * 9 * cout * cin;
   if (smem > 48 * 1024) return NVS_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(total, 128);
+  const int grid = grid_for((total + 7) / 8 * 32, 128);  // one warp per 8 pixels
   switch (cout) {
     case 1: conv_small_kernel<1><<<grid, 128, smem, st>>>(src, weight, bias, dst, H, W, cin, act, total); break;
     case 2: conv_small_kernel<2><<<grid, 128, smem, st>>>(src, weight, bias, dst, H, W, cin, act, total); break;
