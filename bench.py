@@ -107,8 +107,9 @@ def build_model(device):
     return m.to(device), sd
 
 
-def cpu_reference_fps(sd, sample_frames: int, iters: int, threads: int):
-    """The oracle (CPU restatement; same ATen CPU kernels the reference runs) on a bounded sample."""
+def cpu_reference_fps(sd, sample_frames: int, iters: int, threads: int, min_seconds: float = 0.0):
+    """The oracle (CPU restatement; same ATen CPU kernels the reference runs) on a bounded sample.
+    Runs ``iters`` steps, and keeps going until ``min_seconds`` of CPU work have been timed."""
     from oracle import glue_ref, kp2dtiny_ref as R
     from nano_vs_slam_b200.synthetic import synthetic_frames
 
@@ -125,10 +126,12 @@ def cpu_reference_fps(sd, sample_frames: int, iters: int, threads: int):
 
     step()
     t0 = time.perf_counter()
-    for _ in range(iters):
+    done = 0
+    while done < iters or (time.perf_counter() - t0) < min_seconds:
         step()
+        done += 1
     dt = time.perf_counter() - t0
-    return sample_frames * iters / dt, dt
+    return sample_frames * done / dt, dt
 
 
 def run_reference(args):
@@ -142,7 +145,7 @@ def run_reference(args):
         m = tiny_factory(LETTER, NCLS, v3=V3)
     sd = spread_init(m.state_dict(), WSEED)
     threads = os.cpu_count() or 1
-    sample = 4  # frames per step: bounded sample of the batch-256 workload
+    sample = 8  # frames per step: bounded sample of the batch-256 workload
     for _ in range(max(1, args.warmup)):
         cpu_reference_fps(sd, sample, 1, threads)
     fps, dt = cpu_reference_fps(sd, sample, args.steps, threads)
@@ -163,7 +166,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
@@ -203,14 +206,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.5 s to start: sample from warm-up on
     for i in range(warm):
         step(xs[i % 2])
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 1.0:  # keep the GPU under load while the sampler spins up (untimed)
+        step(xs[0])
+        torch.cuda.synchronize()
     plan = next(iter(model._plans.values()))
     heavy = max(plan.meta, key=lambda i: plan.meta[i]["flops"])
     plan.profile = {"idx": heavy, "events": []}
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     l0 = ops.LAUNCHES[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,39 +240,32 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end through the public API with HOST buffers ("e2e") ----
-    from nano_vs_slam_b200.frontend import KP2DtinyFrontend  # noqa: F401  (same calls, see step())
+    # KP2DtinyFrontend.stream: pinned host frames in -> pinned host keypoints/descriptors/VLAD/labels out, every
+    # step; H2D / kernels / D2H of consecutive batches overlap on three CUDA streams (copies are inside the
+    # timed region, the host consumes every batch's results).
+    from nano_vs_slam_b200.frontend import KP2DtinyFrontend
+    fe = KP2DtinyFrontend(config=LETTER, v3=V3, nClasses=NCLS, nn_thresh=THRESH, top_k=TOPK, device=dev,
+                          state_dict=sd)
     host_x = [synthetic_frames(B, H, W, XSEED + 100 * rank + i).pin_memory() for i in range(2)]
-    n_cells = (H // 4) * (W // 4)
-    k = min(TOPK, n_cells)
-    host_out = {
-        "pts": torch.empty(B, k, 2).pin_memory(), "desc": torch.empty(B, k, 32).pin_memory(),
-        "score": torch.empty(B, k).pin_memory(), "count": torch.empty(B, dtype=torch.int32).pin_memory(),
-        "vlad": torch.empty(B, model.get_global_desc_dim()).pin_memory(),
-        "seg": torch.empty(B, 1, H // 2, W // 2, dtype=torch.int64).pin_memory(),
-    }
     h2d = host_x[0].numel() * 4
-    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
 
-    def e2e_step(i):
-        x = host_x[i % 2].to(dev, non_blocking=True)
-        sel, post = step(x)
-        for name in ("pts", "desc", "score", "count"):
-            host_out[name].copy_(sel[name], non_blocking=True)
-        host_out["vlad"].copy_(post["vlad"], non_blocking=True)
-        host_out["seg"].copy_(post["seg"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the results of every step
+    def run_stream(n):
+        d2h_bytes, got = 0, 0
+        for res in fe.stream((host_x[i % 2] for i in range(n)), normalized=True):
+            got += int(res["count"][0] >= 0)  # the host reads the results of every batch
+            d2h_bytes = sum(t.numel() * t.element_size() for t in res.values())
+        assert got == n
+        return d2h_bytes
 
-    for i in range(2):
-        e2e_step(i)
+    run_stream(3)
     barrier()
-    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     f0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    d2h = run_stream(args.steps)
     f1.record()
     barrier()
-    e2e_ms = f0.elapsed_time(f1)
+    e2e_ms = f0.elapsed_time(f1)  # device clock around the whole host-driven stream (results all on the host)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,18 +279,33 @@ def main():
     hbm_peak, bf16_peak, which = _peaks()
     fps_gpu = value / world
     ach_gbs = heavy_meta["bytes"] / (kern_ms / 1e3) / 1e9
-    roofline = {
-        "kernel": f"conv_kernel<3x3> {heavy_meta['shape']} (B={B})", "bound": "hbm",
-        "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
-        "peak_source": which, "kernel_ms": kern_ms,
-        "note": "fp32 FFMA direct conv: math-pipe bound (K=9*Cin per output), HBM fraction at algorithmic bytes "
-                "is necessarily small; see flop_* keys",
-        "flop_pipe": "fp32_ffma", "flop_achieved_tflops": heavy_meta["flops"] / (kern_ms / 1e3) / 1e12,
-        "flop_peak_tflops": FP32_FFMA_PEAK_TFLOPS,
-        "flop_frac": heavy_meta["flops"] / (kern_ms / 1e3) / 1e12 / FP32_FFMA_PEAK_TFLOPS,
-        "step_hbm_frac_at_algorithmic_bytes": fps_gpu * bytes_frame / (hbm_peak * 1e9),
-        "step_flop_frac_fp32_ffma": fps_gpu * flops_frame / (FP32_FFMA_PEAK_TFLOPS * 1e12),
-    }
+    ach_tf = heavy_meta["flops"] / (kern_ms / 1e3) / 1e12
+    if "tcgen05" in heavy_meta["shape"]:
+        # 3xTF32: every algorithmic FLOP costs three tf32 tensor-core FLOPs; tf32 runs at half the bf16 rate, so
+        # the ceiling for ALGORITHMIC FLOP/s is (measured bf16 dense peak) / 2 / 3.
+        peak_tf = bf16_peak / 2.0 / 3.0
+        roofline = {
+            "kernel": f"conv_tc_kernel {heavy_meta['shape']} (B={B})", "bound": "tensor",
+            "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+            "peak_source": which + " bf16 sustained / 2 (tf32) / 3 (3xTF32 split)", "kernel_ms": kern_ms,
+            "mma_tflops_executed": 3.0 * ach_tf, "tf32_peak_tflops": bf16_peak / 2.0,
+            "hbm_gbs_at_algorithmic_bytes": ach_gbs, "hbm_frac_at_algorithmic_bytes": ach_gbs / hbm_peak,
+            "note": "implicit-GEMM conv on tcgen05 (kind::tf32, A via TMEM, 3xTF32 for fp32-grade accuracy); "
+                    "achieved = algorithmic conv FLOPs / kernel time",
+        }
+    else:
+        roofline = {
+            "kernel": f"conv_kernel<3x3> {heavy_meta['shape']} (B={B})", "bound": "hbm",
+            "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+            "peak_source": which, "kernel_ms": kern_ms,
+            "note": "fp32 FFMA direct conv: math-pipe bound (K=9*Cin per output), HBM fraction at algorithmic bytes "
+                    "is necessarily small; see flop_* keys",
+            "flop_pipe": "fp32_ffma", "flop_achieved_tflops": ach_tf, "flop_peak_tflops": FP32_FFMA_PEAK_TFLOPS,
+            "flop_frac": ach_tf / FP32_FFMA_PEAK_TFLOPS,
+        }
+    roofline["step_hbm_frac_at_algorithmic_bytes"] = fps_gpu * bytes_frame / (hbm_peak * 1e9)
+    roofline["step_algorithmic_tflops"] = fps_gpu * flops_frame / 1e12
+    roofline["step_frac_of_fp32_ffma_peak"] = fps_gpu * flops_frame / (FP32_FFMA_PEAK_TFLOPS * 1e12)
 
     extra = {}
     if not args.no_retrieval:
@@ -303,9 +319,10 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            fps_cpu, dt = cpu_reference_fps(sd, 4, 6, threads)
+            fps_cpu, dt = cpu_reference_fps(sd, 8, 4, threads, min_seconds=12.0)
             cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
-                   "sample": f"4 frames x 6 steps of the same workload ({dt:.1f} s), torch CPU restatement in oracle/"}
+                   "sample": f"{round(fps_cpu * dt)} frames of the same workload in batches of 8 ({dt:.1f} s of CPU "
+                             "work), torch CPU (oneDNN) restatement in oracle/"}
         line = {
             "metric": "KP2DTiny-S frames/s @240x320", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -313,6 +330,7 @@ def main():
             "config": {"workload": f"KP2DTiny-S (V2 dedicated decoders, {NCLS} classes) forward + post_processing + "
                                    f"keypoint select (thr {THRESH}, top-{TOPK}), batch {B} x {H}x{W} per GPU",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"frame-dp{world}",
+                       "conv_backend": model.conv_backend,
                        "l2": "two alternating resident input batches of 236 MB each (> 126 MB L2); activations "
                              "per step ~10 GB"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

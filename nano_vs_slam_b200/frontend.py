@@ -8,7 +8,8 @@ reference glue is simply applied per frame).
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from collections import deque
+from typing import Dict, Iterable, Iterator, Optional, Sequence
 
 import numpy as np
 import torch
@@ -68,6 +69,71 @@ class KP2DtinyFrontend(object):
                                    seg_cells=seg_cells,
                                    classes_to_filter=self.classes_to_filter if self.apply_semantic_filer else None)
         return sel, post
+
+    @torch.no_grad()
+    def stream(self, host_batches: Iterable[torch.Tensor], normalized: bool = True,
+               with_seg: bool = True) -> Iterator[Dict[str, torch.Tensor]]:
+        """Host-to-host streaming: pinned (B,3,H,W) batches in, dicts of pinned host tensors out.
+
+        The reference front-end does `.to(device)` -> forward -> `.cpu()` serially per frame
+        (frontend.py:81-116).  Here the same three phases are software-pipelined over three CUDA streams
+        (H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i; B200 has independent copy
+        engines per direction), so the host always gets every batch's results, one batch behind the GPU.
+        Yields, per batch: pts (B,k,2), desc (B,k,D), score (B,k), count (B,), vlad (B,G) [, seg (B,1,H/2,W/2)]."""
+        dev = torch.device(self.device)
+        comp = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        host_sets: list = []
+
+        def upload(hb):
+            with torch.cuda.stream(h2d):
+                x = hb.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(h2d)
+            return x, ev
+
+        it = iter(host_batches)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        pending: deque = deque()
+        step = 0
+        while nxt is not None:
+            x, ev = nxt
+            try:
+                nxt = upload(next(it))  # prefetch the next batch while this one computes
+            except StopIteration:
+                nxt = None
+            comp.wait_event(ev)
+            sel, post = self.run_batch(x, normalized=normalized)
+            x.record_stream(comp)
+            done = torch.cuda.Event()
+            done.record(comp)
+            dev_out = {"pts": sel["pts"], "desc": sel["desc"], "score": sel["score"], "count": sel["count"],
+                       "vlad": post["vlad"]}
+            if with_seg:
+                dev_out["seg"] = post["seg"]
+            if len(host_sets) < 2:  # two pinned result sets, alternated
+                host_sets.append({k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_out.items()})
+            host = host_sets[step % 2]
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                for k, v in dev_out.items():
+                    host[k].copy_(v, non_blocking=True)
+                    v.record_stream(d2h)
+                fin = torch.cuda.Event()
+                fin.record(d2h)
+            pending.append((host, fin))
+            step += 1
+            if len(pending) > 1:
+                h, e = pending.popleft()
+                e.synchronize()
+                yield h
+        while pending:
+            h, e = pending.popleft()
+            e.synchronize()
+            yield h
 
     def run(self, img: torch.Tensor):
         """Reference signature (frontend.py:78-129): img (3,H,W) in [0,1] -> (pts (n,2), desc (n,D), seg)."""
