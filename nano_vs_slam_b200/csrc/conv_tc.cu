@@ -4,24 +4,31 @@
 // order as fp32 FFMA accumulation error over K = 9*Cin terms).
 //
 //   GEMM view:  M = 128 output pixels (8 rows x 16 cols of one frame),  N = Cout,  K = 9 taps x Cin
-//   A operand:  NHWC activations.  For tap (ky,kx) and a 32-channel chunk, ONE 4-D TMA box
-//               (32 ch, 16 x, 8 y, 1 frame) at (x0+kx-1, y0+ky-1) lands as 128 rows x 128 bytes in the
-//               canonical K-major SWIZZLE_128B layout; out-of-image coordinates are zero filled by TMA,
-//               which *is* the convolution's zero padding.  No im2col buffer, no halo bookkeeping.
-//   B operand:  packed weights [tap][Cout][Cin] (hi and lo parts), 3-D TMA box (32, Cout, 1).
-//   split:      4 converter warps read the landed fp32 tile (one 128-byte swizzled row per thread), form
-//               hi (low 13 mantissa bits cleared) and lo = a - hi and write both straight into TENSOR MEMORY
-//               with tcgen05.st (lane = pixel, column = channel): only ONE copy of the activations crosses
-//               L2/HBM, and the A operand never goes back through shared memory (the first version of this
-//               kernel was shared-memory-bandwidth bound: TMA writes + split round trip + 3 UMMA operand reads).
-//   MMA:        one thread issues 12 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Cout, K=8) per stage with
-//               A from TMEM and B (weights) from shared memory
+//   activations: NHWC.  Per tile and KC-channel chunk ONE 4-D TMA box (KC ch, 18 x, 10 y, 1 frame) -- the tile
+//               plus its 1-pixel halo -- lands in shared memory; out-of-image coordinates are zero filled by
+//               TMA, which *is* the convolution's zero padding.  The nine taps are nine shifted windows of that
+//               one box: every activation byte crosses L2 once per layer, not nine times.
+//   split:      converter warps (thread = output pixel) read the window row of the current tap from the halo
+//               box (un-swizzling the 16-byte chunks), form hi (low 13 mantissa bits cleared) and lo = a - hi
+//               and write both straight into TENSOR MEMORY with tcgen05.st (lane = pixel, column = channel):
+//               the A operand never returns to shared memory (an earlier version that staged hi/lo in smem
+//               was shared-memory-bandwidth bound).
+//   weights:    packed [tap][Cout][Cin] (hi and lo parts), 3-D TMA box (KC, Cout, 1) per tap into a 6-8 deep
+//               ring, canonical K-major swizzled layout for the UMMA descriptor.
+//   MMA:        one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, K=8) with A from TMEM and B from
+//               shared memory.  An instruction costs max(N/2, ~50) cycles (profiles/microbench/mma_rate.cu), so
+//               for Cout <= 64 the two products sharing a_hi are ONE instruction with N = 2*Cout against the
+//               contiguous [W_hi ; W_lo] tile; columns [0,Cout) collect a_hi w_hi + a_lo w_hi, columns
+//               [Cout,2Cout) collect a_hi w_lo and the epilogue adds the halves.
 //   epilogue:   4 warps read TMEM (thread = pixel, columns = channels), add bias, activation, then store
 //               NHWC / NCHW, 2x2 max-pool via warp shuffles (a warp owns 2 image rows x 16 cols) or
 //               pixel-shuffled NHWC.
 //
-// Warp roles: 0-3 epilogue (TMEM lane quadrants), then CONV_GROUPS x 4 converter warps (groups take pipeline
-// stages round-robin), one TMA producer warp, one TMEM-allocator + MMA-issuer warp.  Persistent CTAs, static round-robin over (frame, tile_y, tile_x).
+// Warp roles: 0-3 epilogue (TMEM lane quadrants), CONV_GROUPS x 4 converter warps (groups take pipeline steps
+// round-robin), halo producer warp, weight producer warp, TMEM-allocator + MMA-issuer warp.
+// Persistent CTAs, static round-robin over (frame, tile_y, tile_x).  Four mbarrier rings: halo boxes
+// (producer <-> converters), weight tiles (producer <-> MMA), TMEM A slots (converters <-> MMA), accumulators
+// (MMA <-> epilogue).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,33 +38,38 @@ namespace tc {
 
 constexpr int TM = 128;            // pixels per tile
 constexpr int TX = 16, TY = 8;     // tile shape
-constexpr int KC = 32;             // channels per stage (128 bytes of fp32)
-constexpr int A_BYTES = TM * KC * 4;   // 16 KiB
-constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each) taking pipeline stages round-robin
-constexpr int WARP_TMA = 4 + 4 * CONV_GROUPS;
-constexpr int WARP_MMA = WARP_TMA + 1;
+constexpr int HX = TX + 2, HY = TY + 2;   // halo box
+constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each)
+constexpr int WARP_HALO = 4 + 4 * CONV_GROUPS;
+constexpr int WARP_W = WARP_HALO + 1;
+constexpr int WARP_MMA = WARP_W + 1;
 constexpr int THREADS = 32 * (WARP_MMA + 1);
 
-template <int COUT>
+template <int COUT, int KC>
 struct Cfg {
-  static constexpr int W_BYTES = COUT * KC * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + 2 * W_BYTES;  // fp32 activation tile + W_hi + W_lo
-  // tcgen05.mma costs max(N/2, ~50) cycles per instruction (profiles/microbench/mma_rate.cu), so for
-  // Cout <= 64 the two products that share A_hi are issued as ONE instruction with N = 2*Cout against the
-  // concatenated [W_hi ; W_lo] tile (they are contiguous in shared memory): columns [0,Cout) collect
-  // a_hi w_hi + a_lo w_hi, columns [Cout,2Cout) collect a_hi w_lo, and the epilogue adds the two halves.
+  static constexpr int ROW_BYTES = KC * 4;                                 // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr int HALO_BYTES = ((HX * HY * ROW_BYTES + 1023) / 1024) * 1024;
+  static constexpr int W_BYTES = COUT * ROW_BYTES;                         // one of W_hi / W_lo
+  static constexpr int W_STAGE = 2 * W_BYTES;
   static constexpr bool CONCAT = COUT <= 64;
   static constexpr int ACC_STAGE_COLS = CONCAT ? 2 * COUT : COUT;
-  static constexpr int ACC_COLS = 2 * ACC_STAGE_COLS;   // double-buffered accumulator
-  static constexpr int A_COLS = 2 * KC;                 // per stage: 32 columns hi + 32 columns lo
-  // pipeline depth: bounded by TMEM (ACC_COLS + STAGES*A_COLS <= 512) and by ~200 KB of shared memory
-  static constexpr int STAGES = (COUT <= 32) ? 6 : 4;
-  static constexpr int TMEM_COLS = 512;
-  static_assert(ACC_COLS + STAGES * A_COLS <= 512, "TMEM budget");
-  static_assert(STAGES * STAGE_BYTES <= 200 * 1024, "smem budget");
-  static constexpr int SM_BIAS = STAGES * STAGE_BYTES;
+  static constexpr int ACC_COLS = 2 * ACC_STAGE_COLS;                      // double-buffered accumulator
+  static constexpr int A_COLS = 2 * KC;                                    // TMEM slot: KC columns hi + KC columns lo
+  // One ring of NS "slots": slot s = weight stage s in shared memory + A slot s in tensor memory, guarded by ONE
+  // full barrier (4 converter warps + the weight TMA) and ONE empty barrier (tcgen05.commit).  The MMA-issuing
+  // thread is the critical resource (it stalls while the tensor pipe is busy and the pipe drains while it polls
+  // barriers), so it must do exactly one wait and one commit per pipeline step.
+  static constexpr int NS = (512 - ACC_COLS) / A_COLS > 8 ? 8 : (512 - ACC_COLS) / A_COLS;
+  static constexpr int NH = 3;                                             // halo boxes in flight
+  static constexpr int KSTEPS = KC / 8;                                    // MMAs (K = 8 tf32) per operand pair
+  static constexpr int SM_W = NH * HALO_BYTES;
+  static constexpr int SM_BIAS = SM_W + NS * W_STAGE;
   static constexpr int SM_BAR = SM_BIAS + COUT * 4;
-  static constexpr int SMEM_BYTES = SM_BAR + 256 + 1024;
+  static constexpr int N_BARS = 2 * NH + 2 * NS + 4;
+  static constexpr int SMEM_BYTES = SM_BAR + 8 * N_BARS + 16 + 1024;
+  static_assert(NS >= 2, "TMEM budget");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+  static_assert(W_BYTES % 1024 == 0 || (KC == 16 && W_BYTES % 512 == 0), "[W_hi;W_lo] must keep the swizzle phase");
   static constexpr uint32_t idesc_n(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   }
@@ -74,6 +86,7 @@ struct Params {
   int pool_c_total, pool_c_off;
   int B, H, W, cout, act;
   int tiles_x, tiles_y, n_tiles;
+  long long* dbg;  // optional timeline dump of CTA 0 (NVS_TC_DEBUG builds only)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (see retrieval.cu)
@@ -153,6 +166,19 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+template <int KC>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r) {
+  if (KC == 32) tmem_st32(taddr, r);
+  else tmem_st16(taddr, r);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -180,46 +206,63 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   return d;
 }
 
-template <int COUT>
+// K-major swizzled shared-memory matrix descriptor.  KC = 32: 128-byte rows, SWIZZLE_128B (layout 2), 8-row
+// groups 1024 B apart.  KC = 16: 64-byte rows, SWIZZLE_64B (layout 4), 8-row groups 512 B apart.
+template <int KC>
+__device__ __forceinline__ uint64_t make_wdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((KC == 32 ? 1024u : 512u) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(KC == 32 ? 2 : 4) << 61;
+  return d;
+}
+
+template <int COUT, int KC>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const Params p) {
-  using C = Cfg<COUT>;
-  constexpr int STAGES = C::STAGES;
+  using C = Cfg<COUT, KC>;
+  constexpr int NH = C::NH, NS = C::NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(sm + C::SM_BIAS);
   const uint32_t bar0 = base + C::SM_BAR;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto conv_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * STAGES + 2 + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::SM_BAR + 8 * (3 * STAGES + 4));
+  auto hfull = [&](int i) { return bar0 + 8u * i; };
+  auto hempty = [&](int i) { return bar0 + 8u * (NH + i); };
+  auto sfull = [&](int i) { return bar0 + 8u * (2 * NH + i); };
+  auto sempty = [&](int i) { return bar0 + 8u * (2 * NH + NS + i); };
+  auto afull = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + i); };
+  auto aempty = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + 2 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::SM_BAR + 8 * C::N_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < COUT; i += THREADS) bias_s[i] = p.bias[i];
-  if (warp == WARP_TMA && lane == 0) {
+  if (warp == WARP_HALO && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 128);
-      mbar_init(empty_bar(s), 1);
+    for (int i = 0; i < NH; ++i) {
+      mbar_init(hfull(i), 1);
+      mbar_init(hempty(i), 9 * 4);  // one elected lane per converter warp per tap releases the box
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(sfull(i), 4 + 1);   // 4 converter warps (A slot written) + the weight producer's expect_tx arrive
+      mbar_init(sempty(i), 1);      // tcgen05.commit of the step that used the slot
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(afull(i), 1);
+      mbar_init(aempty(i), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -229,134 +272,198 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int chunks = p.c0_chunks + p.c1_chunks;
-  const int ksteps = 9 * chunks;  // pipeline stages per tile
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
-  if (warp == WARP_TMA) {
-    // =========================== TMA producer ===========================
+  if (warp == WARP_HALO) {
+    // =========================== halo producer: one box per (tile, chunk) ===========================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int hb = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * TX, y0 = ty * TY;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - ky * 3;
-          for (int ch = 0; ch < chunks; ++ch) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t s_base = base + stage * C::STAGE_BYTES;
-            mbar_expect_tx(full_bar(stage), A_BYTES + 2 * C::W_BYTES);
-            if (ch < p.c0_chunks)
-              tma_load_4d(s_base, &map_a0, full_bar(stage), p.c0_off + ch * KC, x0 + kx - 1, y0 + ky - 1, b);
-            else
-              tma_load_4d(s_base, &map_a1, full_bar(stage), p.c1_off + (ch - p.c0_chunks) * KC, x0 + kx - 1,
-                          y0 + ky - 1, b);
-            tma_load_3d(s_base + A_BYTES, &map_whi, full_bar(stage), ch * KC, 0, tap);
-            tma_load_3d(s_base + A_BYTES + C::W_BYTES, &map_wlo, full_bar(stage), ch * KC, 0, tap);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(hempty(hb), ph ^ 1);
+          mbar_expect_tx(hfull(hb), HX * HY * C::ROW_BYTES);
+          if (ch < p.c0_chunks)
+            tma_load_4d(base + hb * C::HALO_BYTES, &map_a0, hfull(hb), p.c0_off + ch * KC, tx * TX - 1, ty * TY - 1, b);
+          else
+            tma_load_4d(base + hb * C::HALO_BYTES, &map_a1, hfull(hb), p.c1_off + (ch - p.c0_chunks) * KC,
+                        tx * TX - 1, ty * TY - 1, b);
+          if (++hb == NH) {
+            hb = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_W) {
+    // =========================== weight producer: one [W_hi;W_lo] tile per (chunk, tap) ===========================
+    if (lane == 0) {
+      int sl = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(sempty(sl), ph ^ 1);
+            const uint32_t dst = base + C::SM_W + sl * C::W_STAGE;
+            mbar_expect_tx(sfull(sl), C::W_STAGE);
+            tma_load_3d(dst, &map_whi, sfull(sl), ch * KC, 0, tap);
+            tma_load_3d(dst + C::W_BYTES, &map_wlo, sfull(sl), ch * KC, 0, tap);
+            if (++sl == NS) {
+              sl = 0;
+              ph ^= 1;
             }
           }
         }
       }
     }
-  } else if (warp >= 4 && warp < WARP_TMA) {
-    // =========================== hi / lo split -> TMEM ===========================
+  } else if (warp >= 4 && warp < WARP_HALO) {
+    // =========================== converters: halo window -> hi / lo -> TMEM ===========================
     const int cw = warp & 3;            // TMEM lane quadrant this warp may write (warp % 4)
-    const int grp = (warp - 4) >> 2;    // converter group: handles k-steps with (global index % CONV_GROUPS == grp)
-    const int r = cw * 32 + lane;       // tile row (pixel) == TMEM lane
-    int stage = 0, turn = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      for (int ks = 0; ks < ksteps; ++ks) {
-        if (turn != grp) {
+    const int grp = (warp - 4) >> 2;    // converter group: handles pipeline steps with (index % CONV_GROUPS == grp)
+    const int r = cw * 32 + lane;       // output pixel inside the tile == TMEM lane
+    const int ly = r >> 4, lx = r & 15;
+    int hb = 0, sl = 0, turn = 0;
+    uint32_t hph = 0, sph = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      for (int ch = 0; ch < chunks; ++ch) {
+        for (int tap = 0; tap < 9; ++tap) {
+          const bool mine = turn == grp;
           if (++turn == CONV_GROUPS) turn = 0;
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-          continue;
-        }
-        if (++turn == CONV_GROUPS) turn = 0;
-        mbar_wait(full_bar(stage), phase);
-        // row r of the TMA box: 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7)) (SWIZZLE_128B); the
-        // XOR makes the 8 lanes of a quarter-warp hit 8 different bank groups -> conflict-free LDS.128
-        const uint8_t* rowp = sm + stage * C::STAGE_BYTES + r * 128;
-        uint32_t hi[32], lo[32];
+          if (mine) {
+            mbar_wait(hfull(hb), hph);
+            mbar_wait(sempty(sl), sph ^ 1);
+            tc_fence_after();
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int rh = (ly + ky) * HX + lx + kx;  // row of the halo box
+            const uint8_t* rowp = sm + hb * C::HALO_BYTES + rh * C::ROW_BYTES;
+            // 16-byte chunk c of row rh sits at chunk (c ^ key): SWIZZLE_128B key = rh & 7, SWIZZLE_64B key = (rh >> 1) & 3.
+            // Consecutive pixels of a quarter-warp read consecutive rows -> distinct keys -> conflict-free LDS.128.
+            const int key = KC == 32 ? (rh & 7) : ((rh >> 1) & 3);
+            uint32_t hi[KC], lo[KC];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-          const float f[4] = {v.x, v.y, v.z, v.w};
+            for (int c = 0; c < KC / 4; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ key) << 4));
+              const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
-            hi[4 * c + e] = h;
-            lo[4 * c + e] = __float_as_uint(f[e] - __uint_as_float(h));
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+                hi[4 * c + e] = h;
+                lo[4 * c + e] = __float_as_uint(f[e] - __uint_as_float(h));
+              }
+            }
+            const uint32_t ta = tmem_base + (uint32_t)(C::ACC_COLS + sl * C::A_COLS) + ((uint32_t)(cw * 32) << 16);
+            tmem_st<KC>(ta, hi);
+            tmem_st<KC>(ta + KC, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(sfull(sl));   // this warp's 32 TMEM lanes of the slot are written
+              mbar_arrive(hempty(hb));  // ... and its reads of the halo box for this tap are done
+            }
+          }
+          if (++sl == NS) {
+            sl = 0;
+            sph ^= 1;
           }
         }
-        const uint32_t ta = tmem_base + (uint32_t)(C::ACC_COLS + stage * C::A_COLS) + ((uint32_t)(cw * 32) << 16);
-        tmem_st32(ta, hi);
-        tmem_st32(ta + KC, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(conv_bar(stage));
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        if (++hb == NH) {
+          hb = 0;
+          hph ^= 1;
         }
       }
     }
   } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
+    // Flat loop over all pipeline steps of this CTA.  The wait for step g+1 is placed between the MMAs of step g:
+    // by then the tensor pipe's queue is full, so the ~80-cycle barrier poll costs nothing (measured with the
+    // NVS_TC_DEBUG timeline: the pipe used to drain for ~300 cycles per step while this thread polled).
+    if (lane == 0 && my_tiles > 0) {
+      const int steps = 9 * chunks;
+      const int total = my_tiles * steps;
+      const uint64_t wdesc0 = make_wdesc<KC>(base + C::SM_W);
+      const uint32_t a0 = tmem_base + (uint32_t)C::ACC_COLS;
+      int sl = 0, acc = 0, ks = 0;
+      uint32_t sph = 0, aph = 0;
+      mbar_wait(aempty(0), 1);
+      mbar_wait(sfull(0), 0);
+      tc_fence_after();
+      for (int g = 0; g < total; ++g) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(conv_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t s_base = base + stage * C::STAGE_BYTES;
-          const uint32_t a_hi = tmem_base + (uint32_t)(C::ACC_COLS + stage * C::A_COLS), a_lo = a_hi + KC;
-          const uint64_t w_hi = make_sdesc(s_base + A_BYTES), w_lo = make_sdesc(s_base + A_BYTES + C::W_BYTES);
+        const uint32_t a_hi = a0 + (uint32_t)(sl * C::A_COLS), a_lo = a_hi + KC;
+        const uint64_t w_hi = wdesc0 + (uint64_t)((sl * C::W_STAGE) >> 4), w_lo = w_hi + (uint64_t)(C::W_BYTES >> 4);
+        // next step's slot / accumulator
+        int nsl = sl + 1;
+        uint32_t nsph = sph;
+        if (nsl == NS) {
+          nsl = 0;
+          nsph ^= 1;
+        }
+        const bool last_of_tile = ks == steps - 1;
+#ifdef NVS_TC_DEBUG
+        const long long c0 = clock64();
+        long long c1 = c0, c2 = c0;
+#endif
 #pragma unroll
-          for (int k = 0; k < KC / 8; ++k) {
-            // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
-            const uint64_t o = (uint64_t)(2 * k);
-            if (C::CONCAT) {
-              tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC2, (ks | k) != 0 ? 1u : 0u);  // x [W_hi;W_lo]
-              tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
-            } else {
-              tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
-              tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
-              tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_lo + o, C::IDESC, 1u);
+        for (int k = 0; k < C::KSTEPS; ++k) {
+          // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
+          const uint64_t o = (uint64_t)(2 * k);
+          if (C::CONCAT) {
+            tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC2, (ks | k) != 0 ? 1u : 0u);  // x [W_hi;W_lo]
+            tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
+          } else {
+            tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
+            tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
+            tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_lo + o, C::IDESC, 1u);
+          }
+          if (k == C::KSTEPS - 2 && g + 1 < total) {
+            // poll the next step's barriers while the queue is full
+#ifdef NVS_TC_DEBUG
+            c1 = clock64();
+#endif
+            if (last_of_tile) {
+              const int nacc = acc ^ 1;
+              mbar_wait(aempty(nacc), (nacc == 0 ? aph ^ 1 : aph) ^ 1);
             }
-          }
-          tc_commit(empty_bar(stage));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+            mbar_wait(sfull(nsl), nsph);
+            tc_fence_after();
+#ifdef NVS_TC_DEBUG
+            c2 = clock64();
+#endif
           }
         }
-        tc_commit(tfull_bar(acc));
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        tc_commit(sempty(sl));  // weight stage + TMEM A slot are free once these MMAs retire
+#ifdef NVS_TC_DEBUG
+        if (p.dbg && blockIdx.x == 0 && g < 512) {
+          long long* d = p.dbg + g * 4;
+          d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64();
         }
+#endif
+        if (last_of_tile) {
+          tc_commit(afull(acc));
+          ks = 0;
+          if (++acc == 2) {
+            acc = 0;
+            aph ^= 1;
+          }
+        } else {
+          ++ks;
+        }
+        sl = nsl;
+        sph = nsph;
       }
     }
   } else if (warp < 4) {
     // =========================== epilogue ===========================
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t aph = 0;
     const int ly = 2 * warp + (lane >> 4), lx = lane & 15;  // pixel inside the tile (TMEM lane = ly*16 + lx)
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
       const int gx = tx * TX + lx, gy = ty * TY + ly;
       const bool valid = gx < p.W && gy < p.H;
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(afull(acc), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -423,10 +530,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(aempty(acc));
       if (++acc == 2) {
         acc = 0;
-        acc_phase ^= 1;
+        aph ^= 1;
       }
     }
   }
@@ -435,9 +542,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   if (warp == WARP_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -460,54 +565,66 @@ static EncodeTiledFn get_encode() {
 struct alignas(64) Plan {
   CUtensorMap a0, a1, whi, wlo;
   Params p;
-  int cout_tpl;
+  int cout_tpl, kc;
   int magic;
 };
-constexpr int PLAN_MAGIC = 0x7C0DE5;
+constexpr int PLAN_MAGIC = 0x7C0DE6;
 
-static int encode_act(CUtensorMap* m, const float* ptr, int B, int H, int W, int Ct) {
+// NHWC activations (B,H,W,Ct): box = (kc channels, 18 x, 10 y, 1 frame) = output tile + 1-pixel halo
+static int encode_act(CUtensorMap* m, const float* ptr, int B, int H, int W, int Ct, int kc) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
   cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)Ct * 4, (cuuint64_t)W * Ct * 4, (cuuint64_t)H * W * Ct * 4};
-  cuuint32_t box[4] = {KC, TX, TY, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kc, HX, HY, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
-static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad) {
+// packed weights [9][cout_pad][cin]: box = (kc, cout_pad, 1)
+static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int kc) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
   cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, 9};
   cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cout_pad * cin * 4};
-  cuuint32_t box[3] = {KC, (cuuint32_t)cout_pad, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)cout_pad, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
 
-template <int COUT>
+template <int COUT, int KC>
 static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
-  using C = Cfg<COUT>;
+  using C = Cfg<COUT, KC>;
   static bool done = false;
   static int sms = 0;
   if (!done) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return nvs_set_cuda_error(e);
     done = true;
   }
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  conv_tc_kernel<COUT><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, p);
+  conv_tc_kernel<COUT, KC><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, p);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
+}
+
+#ifdef NVS_TC_DEBUG
+static long long* g_dbg = nullptr;
+#endif
+
+static inline int pick_kc(int c0, int c1) {
+  if (c0 % 32 == 0 && c1 % 32 == 0) return 32;
+  if (c0 % 16 == 0 && c1 % 16 == 0) return 16;
+  return 0;
 }
 
 }  // namespace tc
@@ -521,8 +638,12 @@ extern "C" int32_t nvs_conv_tc_cout_pad(int32_t cout) {
 }
 
 extern "C" int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout) {
-  if (c0 <= 0 || c0 % tc::KC != 0 || c1 < 0 || c1 % tc::KC != 0) return 0;
-  return nvs_conv_tc_cout_pad(cout) != 0 ? 1 : 0;
+  if (c0 <= 0 || c1 < 0) return 0;
+  const int kc = tc::pick_kc(c0, c1);
+  const int cpad = nvs_conv_tc_cout_pad(cout);
+  if (kc == 0 || cpad == 0) return 0;
+  if (kc == 16 && cpad != 32) return 0;  // the 16-channel variant is instantiated for the stem layer only
+  return 1;
 }
 
 extern "C" size_t nvs_conv_tc_plan_bytes(void) { return sizeof(tc::Plan) + 64; }
@@ -539,23 +660,26 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   tc::Plan* pl = reinterpret_cast<tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   const int cpad = nvs_conv_tc_cout_pad(a->cout);
   const int cin = a->c0 + a->c1;
-  int rc = tc::encode_act(&pl->a0, a->src0, a->B, a->H, a->W, a->c0_total);
+  const int kc = tc::pick_kc(a->c0, a->c1);
+  int rc = tc::encode_act(&pl->a0, a->src0, a->B, a->H, a->W, a->c0_total, kc);
   if (rc != NVS_OK) return rc;
-  rc = tc::encode_act(&pl->a1, a->c1 > 0 ? a->src1 : a->src0, a->B, a->H, a->W, a->c1 > 0 ? a->c1_total : a->c0_total);
+  rc = tc::encode_act(&pl->a1, a->c1 > 0 ? a->src1 : a->src0, a->B, a->H, a->W, a->c1 > 0 ? a->c1_total : a->c0_total, kc);
   if (rc != NVS_OK) return rc;
-  rc = tc::encode_w(&pl->whi, a->w_hi, cin, cpad);
+  rc = tc::encode_w(&pl->whi, a->w_hi, cin, cpad, kc);
   if (rc != NVS_OK) return rc;
-  rc = tc::encode_w(&pl->wlo, a->w_lo, cin, cpad);
+  rc = tc::encode_w(&pl->wlo, a->w_lo, cin, cpad, kc);
   if (rc != NVS_OK) return rc;
   tc::Params& p = pl->p;
   p.bias = a->bias; p.dst = a->dst; p.dst_pool = a->dst_pool;
-  p.c0_off = a->c0_off; p.c0_chunks = a->c0 / tc::KC; p.c1_off = a->c1_off; p.c1_chunks = a->c1 / tc::KC;
+  p.c0_off = a->c0_off; p.c0_chunks = a->c0 / kc; p.c1_off = a->c1_off; p.c1_chunks = a->c1 / kc;
   p.dst_c_total = a->dst_c_total; p.dst_c_off = a->dst_c_off; p.dst_layout = a->dst_layout; p.dst_mode = a->dst_mode;
   p.pool_c_total = a->pool_c_total; p.pool_c_off = a->pool_c_off;
   p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.act = a->act;
   p.tiles_x = (a->W + tc::TX - 1) / tc::TX; p.tiles_y = (a->H + tc::TY - 1) / tc::TY;
   p.n_tiles = p.tiles_x * p.tiles_y * a->B;
+  p.dbg = nullptr;
   pl->cout_tpl = cpad;
+  pl->kc = kc;
   pl->magic = tc::PLAN_MAGIC;
   return NVS_OK;
 }
@@ -566,12 +690,20 @@ extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, void* 
   if (pl->magic != tc::PLAN_MAGIC) return NVS_ERR_ARG;
   tc::Params p = pl->p;
   if (dst_override) p.dst = dst_override;
+#ifdef NVS_TC_DEBUG
+  p.dbg = tc::g_dbg;
+#endif
   if (p.dst_mode != 0 && !p.dst) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl->kc == 16) return pl->cout_tpl == 32 ? tc::launch<32, 16>(*pl, p, st) : NVS_ERR_UNSUPPORTED;
   switch (pl->cout_tpl) {
-    case 32: return tc::launch<32>(*pl, p, st);
-    case 64: return tc::launch<64>(*pl, p, st);
-    case 128: return tc::launch<128>(*pl, p, st);
+    case 32: return tc::launch<32, 32>(*pl, p, st);
+    case 64: return tc::launch<64, 32>(*pl, p, st);
+    case 128: return tc::launch<128, 32>(*pl, p, st);
   }
   return NVS_ERR_UNSUPPORTED;
 }
+
+#ifdef NVS_TC_DEBUG
+extern "C" void nvs_conv_tc_set_debug(long long* dev_buf) { nvs::tc::g_dbg = dev_buf; }
+#endif

@@ -319,7 +319,8 @@ class _KP2DTinyBase(nn.Module):
         # conv backend: "tc" = tcgen05 3xTF32 implicit GEMM on channels-last maps (needs 32-channel multiples:
         # the S letters), "ffma" = exact fp32 direct conv (any channel count: the N letters).
         c1, c2, c3, c4, c5, d1 = self.channel_dims
-        tc_ok = all(c % 32 == 0 for c in (c2, c3, c4, c5, d1 // 4, self.encoder_dim)) and max(c4, c5, d1) <= 128
+        tc_ok = (all(c % 32 == 0 for c in (c2, c3, c4, c5, d1 // 4, self.encoder_dim)) and max(c4, c5, d1) <= 128
+                 and c1 % 16 == 0 and c2 <= 32)
         self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
         if self.conv_backend == "tc" and not tc_ok:
             raise NotImplementedError("tensor-core conv backend needs channel counts that are multiples of 32")
@@ -418,8 +419,9 @@ class _KP2DTinyBase(nn.Module):
         tc = self.conv_backend == "tc"
         bb = self.backbone
         for n in ("conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"):
-            # the 3- and 16-channel stem layers stay on the FFMA kernel (K too thin for a 128-byte TMA row)
-            P["bb." + n] = self._pk_block(getattr(bb, n), tc=tc and n not in ("conv1a", "conv1b"))
+            # the 3-channel stem layer stays on the FFMA kernel (K = 27 is too thin for a TMA row); conv1b
+            # (16 channels) uses the 64-byte-row variant of the tensor-core kernel
+            P["bb." + n] = self._pk_block(getattr(bb, n), tc=tc and n != "conv1a")
         sh = self.seg_head
         for i, m in enumerate(sh.convs):
             if isinstance(m, _ConvBnAct):
@@ -603,12 +605,12 @@ class _KP2DTinyBase(nn.Module):
                          "seg": (B, ncls, H2, W2)}
         # ---- stem on the FFMA kernel: NCHW in, channels-last pooled map out ----
         xin = torch.empty(B, 3, H, W, device=pl.device)
-        t1a = pl.buf("t1a", c1, H, W)
-        pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a)
+        t1a = pl.buf_nhwc("t1a", c1, H, W)
+        pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a, dst_nhwc=True)
         pl.in_args = pl.steps[-1][1]
-        p1 = pl.buf_nhwc("p1", c2, H2, W2)
-        pl.conv(P["bb.conv1b"], t1a, c2, act=act, out_mode=ops.OUT_POOL, dst2=p1, dst2_nhwc=True)
         # ---- backbone on tensor cores ----
+        p1 = pl.buf_nhwc("p1", c2, H2, W2)
+        pl.tc(P["bb.conv1b"], t1a, c2, act=act, dst=None, dst_mode=0, dst_pool=p1)
         t2a = pl.buf_nhwc("t2a", c2, H2, W2)
         pl.tc(P["bb.conv2a"], p1, c2, act=act, dst=t2a)
         t2b = pl.buf_nhwc("t2b", c3, H2, W2)

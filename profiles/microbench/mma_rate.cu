@@ -22,15 +22,16 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint32_t ta, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(ta), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <int KIND, int N, int NMMA>
+template <int KIND, int N, int NMMA, int COMMIT_EVERY>
 __global__ void __launch_bounds__(128, 1) k(long long* out) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t slot;
   const uint32_t base = (smem_u32(sm) + 1023u) & ~1023u;
   for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) ((uint32_t*)sm)[i] = 0;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -48,7 +49,11 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
     const uint64_t a = make_sdesc(base), b = make_sdesc(base + 32768);
     long long t0 = clock64();
 #pragma unroll 4
-    for (int i = 0; i < NMMA; ++i) mma<KIND>(tm, a + 2 * (i & 3), tm + 256 + 8 * (i & 3), b + 2 * (i & 3), idesc, i ? 1u : 0u);
+    for (int i = 0; i < NMMA; ++i) {
+      mma<KIND>(tm, a + 2 * (i & 3), tm + 256 + 8 * (i & 3), b + 2 * (i & 3), idesc, i ? 1u : 0u);
+      if (COMMIT_EVERY > 0 && (i % COMMIT_EVERY) == COMMIT_EVERY - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+    }
     long long t1 = clock64();
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     uint32_t ok = 0;
@@ -62,16 +67,17 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
-template <int KIND, int N>
+template <int KIND, int N, int CE = 0>
 void run(const char* name, long long* d) {
   constexpr int NMMA = 2048;
-  auto kern = k<KIND, N, NMMA>;
+  auto kern = k<KIND, N, NMMA, CE>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   for (int grid : {1, 148}) {
     kern<<<grid, 128, 100 * 1024>>>(d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    if (CE) printf("[commit every %d] ", CE);
     printf("%-28s N=%3d grid=%3d  issue %.1f cyc/mma   complete %.1f cyc/mma  (%s)\n", name, N, grid, h[0] / (double)NMMA,
            h[1] / (double)NMMA, cudaGetErrorString(e));
   }
@@ -91,5 +97,11 @@ int main() {
   run<2, 128>("tf32 TS(A in TMEM) M128 K8", d);
   run<2, 64>("tf32 TS(A in TMEM) M128 K8", d);
   run<2, 32>("tf32 TS(A in TMEM) M128 K8", d);
+  run<2, 128, 8>("tf32 TS", d);
+  run<2, 128, 4>("tf32 TS", d);
+  run<2, 128, 2>("tf32 TS", d);
+  run<2, 64, 8>("tf32 TS", d);
+  run<2, 64, 2>("tf32 TS", d);
+  run<0, 256, 4>("bf16 SS", d);
   return 0;
 }

@@ -15,6 +15,8 @@ def _nhwc(t):
 @pytest.mark.parametrize("cin,cout,H,W,act", [
     (64, 64, 60, 80, 1), (32, 32, 24, 40, 1), (64, 128, 15, 20, 0), (96, 64, 33, 50, 1), (32, 64, 17, 31, 2),
     (64, 28, 20, 28, 0), (64, 32, 9, 19, 0), (128, 64, 8, 16, 1),
+    (16, 32, 40, 56, 1),   # 64-byte-row (SWIZZLE_64B) variant used by the stem layer conv1b
+    (64, 64, 7, 5, 1),     # tile larger than the image
 ])
 def test_conv_tc_plain_nhwc_and_nchw(cin, cout, H, W, act):
     from nano_vs_slam_b200 import ops
