@@ -113,6 +113,7 @@ typedef struct NvsConvTcArgs {
   int32_t dst_c_total, dst_c_off, dst_layout, dst_mode;
   int32_t pool_c_total, pool_c_off;
   int32_t B, H, W, cout, act;
+  int32_t flags; /* bit 0: single MMA issuer = fixed fp32 accumulation order (bit-reproducible, ~15 % slower) */
 } NvsConvTcArgs;
 int32_t nvs_conv_tc_cout_pad(int32_t cout);
 int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout);

@@ -40,7 +40,7 @@ class NvsConvTcArgs(C.Structure):
         ("c1_total", _i32), ("c1_off", _i32), ("c1", _i32),
         ("dst_c_total", _i32), ("dst_c_off", _i32), ("dst_layout", _i32), ("dst_mode", _i32),
         ("pool_c_total", _i32), ("pool_c_off", _i32),
-        ("B", _i32), ("H", _i32), ("W", _i32), ("cout", _i32), ("act", _i32),
+        ("B", _i32), ("H", _i32), ("W", _i32), ("cout", _i32), ("act", _i32), ("flags", _i32),
     ]
 
 

@@ -42,8 +42,8 @@ constexpr int HX = TX + 2, HY = TY + 2;   // halo box
 constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each)
 constexpr int WARP_HALO = 4 + 4 * CONV_GROUPS;
 constexpr int WARP_W = WARP_HALO + 1;
-constexpr int WARP_MMA = WARP_W + 1;
-constexpr int THREADS = 32 * (WARP_MMA + 1);
+constexpr int WARP_MMA = WARP_W + 1;      // first of TWO MMA-issuing warps (they take pipeline steps alternately)
+constexpr int THREADS = 32 * (WARP_MMA + 2);
 
 template <int COUT, int KC>
 struct Cfg {
@@ -65,7 +65,7 @@ struct Cfg {
   static constexpr int SM_W = NH * HALO_BYTES;
   static constexpr int SM_BIAS = SM_W + NS * W_STAGE;
   static constexpr int SM_BAR = SM_BIAS + COUT * 4;
-  static constexpr int N_BARS = 2 * NH + 2 * NS + 4;
+  static constexpr int N_BARS = 2 * NH + 2 * NS + 6;
   static constexpr int SMEM_BYTES = SM_BAR + 8 * N_BARS + 16 + 1024;
   static_assert(NS >= 2, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
@@ -86,6 +86,7 @@ struct Params {
   int pool_c_total, pool_c_off;
   int B, H, W, cout, act;
   int tiles_x, tiles_y, n_tiles;
+  int issuers;     // 2 (default) or 1: a single MMA issuer gives a fixed fp32 accumulation order (bit-reproducible)
   long long* dbg;  // optional timeline dump of CTA 0 (NVS_TC_DEBUG builds only)
 };
 
@@ -237,6 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto sempty = [&](int i) { return bar0 + 8u * (2 * NH + NS + i); };
   auto afull = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + i); };
   auto aempty = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + 2 + i); };
+  auto astart = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + 4 + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::SM_BAR + 8 * C::N_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,8 +257,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(sempty(i), 1);      // tcgen05.commit of the step that used the slot
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(afull(i), 1);
+      mbar_init(afull(i), p.issuers);   // every MMA issuer commits its share of the tile
       mbar_init(aempty(i), 4);
+      mbar_init(astart(i), 1);  // the issuer of a tile's first step has queued the overwriting (accumulate=0) MMA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -374,84 +377,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp == WARP_MMA) {
-    // =========================== MMA issuer ===========================
-    // Flat loop over all pipeline steps of this CTA.  The wait for step g+1 is placed between the MMAs of step g:
-    // by then the tensor pipe's queue is full, so the ~80-cycle barrier poll costs nothing (measured with the
-    // NVS_TC_DEBUG timeline: the pipe used to drain for ~300 cycles per step while this thread polled).
-    if (lane == 0 && my_tiles > 0) {
+  } else if (warp >= WARP_MMA) {
+    // =========================== MMA issuers (two threads) ===========================
+    // A tcgen05.mma instruction blocks its issuing thread while the tensor pipe's short queue is full, and the
+    // pipe drains whenever that thread polls an mbarrier or commits (NVS_TC_DEBUG timeline: ~450 of every ~900
+    // cycles per step were not spent issuing).  Two issuers take the pipeline steps alternately (even / odd
+    // global step index): while one polls and commits, the other's MMAs keep the pipe busy.  Accumulation
+    // order inside a tile is irrelevant except for the very first (overwriting) MMA, which is ordered by the
+    // astart barrier; each issuer commits the slots it consumed, and both commit the tile's accumulator
+    // (afull count 2).
+    const int me = warp - WARP_MMA;  // 0 or 1
+    if (lane == 0 && my_tiles > 0 && me < p.issuers) {
+      const int nis = p.issuers;
       const int steps = 9 * chunks;
       const int total = my_tiles * steps;
       const uint64_t wdesc0 = make_wdesc<KC>(base + C::SM_W);
       const uint32_t a0 = tmem_base + (uint32_t)C::ACC_COLS;
-      int sl = 0, acc = 0, ks = 0;
-      uint32_t sph = 0, aph = 0;
-      mbar_wait(aempty(0), 1);
-      mbar_wait(sfull(0), 0);
-      tc_fence_after();
-      for (int g = 0; g < total; ++g) {
+      int tile = 0, ks = me;  // my current step: tile index (CTA-local) and step inside the tile
+      while (ks >= steps) {
+        ks -= steps;
+        ++tile;
+      }
+      int last_tile_synced = -1;
+      for (int g = me; g < total; g += nis) {
+        const int acc = tile & 1;
+        const uint32_t aph = (uint32_t)(tile >> 1) & 1u;
+        const int sl = g % NS;
+        const uint32_t sph = (uint32_t)(g / NS) & 1u;
+        if (last_tile_synced != tile) {  // my first step in this tile
+          mbar_wait(aempty(acc), aph ^ 1);
+          if (ks != 0) mbar_wait(astart(acc), aph);  // the other issuer queued the tile's first MMA
+          last_tile_synced = tile;
+        }
+        mbar_wait(sfull(sl), sph);
+        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS);
         const uint32_t a_hi = a0 + (uint32_t)(sl * C::A_COLS), a_lo = a_hi + KC;
         const uint64_t w_hi = wdesc0 + (uint64_t)((sl * C::W_STAGE) >> 4), w_lo = w_hi + (uint64_t)(C::W_BYTES >> 4);
-        // next step's slot / accumulator
-        int nsl = sl + 1;
-        uint32_t nsph = sph;
-        if (nsl == NS) {
-          nsl = 0;
-          nsph ^= 1;
-        }
-        const bool last_of_tile = ks == steps - 1;
-#ifdef NVS_TC_DEBUG
-        const long long c0 = clock64();
-        long long c1 = c0, c2 = c0;
-#endif
 #pragma unroll
         for (int k = 0; k < C::KSTEPS; ++k) {
           // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
           const uint64_t o = (uint64_t)(2 * k);
           if (C::CONCAT) {
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC2, (ks | k) != 0 ? 1u : 0u);  // x [W_hi;W_lo]
+            if (k == 0 && ks == 0) mbar_arrive(astart(acc));
             tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
           } else {
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
+            if (k == 0 && ks == 0) mbar_arrive(astart(acc));
             tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_lo + o, C::IDESC, 1u);
           }
-          if (k == C::KSTEPS - 2 && g + 1 < total) {
-            // poll the next step's barriers while the queue is full
-#ifdef NVS_TC_DEBUG
-            c1 = clock64();
-#endif
-            if (last_of_tile) {
-              const int nacc = acc ^ 1;
-              mbar_wait(aempty(nacc), (nacc == 0 ? aph ^ 1 : aph) ^ 1);
-            }
-            mbar_wait(sfull(nsl), nsph);
-            tc_fence_after();
-#ifdef NVS_TC_DEBUG
-            c2 = clock64();
-#endif
-          }
         }
         tc_commit(sempty(sl));  // weight stage + TMEM A slot are free once these MMAs retire
-#ifdef NVS_TC_DEBUG
-        if (p.dbg && blockIdx.x == 0 && g < 512) {
-          long long* d = p.dbg + g * 4;
-          d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64();
+        if (ks >= steps - nis) tc_commit(afull(acc));  // my last step of this tile
+        ks += nis;
+        while (ks >= steps) {
+          ks -= steps;
+          ++tile;
         }
-#endif
-        if (last_of_tile) {
-          tc_commit(afull(acc));
-          ks = 0;
-          if (++acc == 2) {
-            acc = 0;
-            aph ^= 1;
-          }
-        } else {
-          ++ks;
-        }
-        sl = nsl;
-        sph = nsph;
       }
     }
   } else if (warp < 4) {
@@ -677,6 +661,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.act = a->act;
   p.tiles_x = (a->W + tc::TX - 1) / tc::TX; p.tiles_y = (a->H + tc::TY - 1) / tc::TY;
   p.n_tiles = p.tiles_x * p.tiles_y * a->B;
+  p.issuers = (a->flags & 1) ? 1 : 2;
   p.dbg = nullptr;
   pl->cout_tpl = cpad;
   pl->kc = kc;

@@ -402,8 +402,15 @@ class TcConv(object):
                  src1: Optional[torch.Tensor] = None, c0_off: int = 0, c0: Optional[int] = None, c1_off: int = 0,
                  c1: Optional[int] = None, dst: Optional[torch.Tensor] = None, dst_layout: int = 0,
                  dst_mode: int = 1, dst_c_off: int = 0, dst_c_total: Optional[int] = None,
-                 dst_pool: Optional[torch.Tensor] = None, pool_c_off: int = 0):
+                 dst_pool: Optional[torch.Tensor] = None, pool_c_off: int = 0,
+                 deterministic: Optional[bool] = None):
+        """``deterministic``: one MMA-issuing thread instead of two -> fixed fp32 accumulation order, results
+        bit-reproducible run to run (default: env NVS_DETERMINISTIC=1, else the faster two-issuer schedule whose
+        last-ulp rounding depends on timing)."""
+        import os
         hi, lo, bp = packed
+        if deterministic is None:
+            deterministic = os.environ.get("NVS_DETERMINISTIC", "0") == "1"
         B, H, W, c0_total = src0.shape
         a = _cabi.NvsConvTcArgs()
         a.src0, a.w_hi, a.w_lo, a.bias = src0.data_ptr(), hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
@@ -427,6 +434,7 @@ class TcConv(object):
         a.pool_c_total = dst_pool.shape[3] if dst_pool is not None else 0
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
+        a.flags = 1 if deterministic else 0
         if dst is not None:
             if dst_mode == 1 and dst_layout == 0:
                 assert tuple(dst.shape[:3]) == (B, H, W)
