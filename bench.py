@@ -30,6 +30,9 @@ import torch
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; stdout must carry the JSON line only
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NVS_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 H, W = 240, 320
 LETTER, V3, NCLS = "S", False, 28

@@ -97,7 +97,9 @@ int nvs_conv(const NvsConvArgs* args, void* stream);
  * cout <= 128.  Activations are channels-last: src (B,H,W,c_total) fp32; weights packed as
  * w_hi / w_lo [9][cout_pad][c0+c1] (tap-major, K contiguous; w_hi has the low 13 mantissa bits cleared,
  * w_lo = w - w_hi; BN folded), bias [cout_pad], cout_pad = nvs_conv_tc_cout_pad(cout).
- * dst_mode 0: no full-resolution output, 1: plain, 2: PixelShuffle(2) into NHWC (B,2H,2W,cout/4 at dst_c_off);
+ * dst_mode 0: no full-resolution output, 1: plain, 2: PixelShuffle(2) into NHWC (B,2H,2W,cout/4 at dst_c_off),
+ * 3: keypoint-head split (cout = 3): sigmoid(ch 0) -> dst (B,1,H,W), tanh(ch 1,2) -> dst_pool (B,2,H,W), both NCHW
+ *    (kp2dtiny.py:574-575, 927-935);
  * dst_layout 0: NHWC, 1: NCHW (plain only); dst_pool (optional): MaxPool2d(2,2) of the result, NHWC.
  * The plan (TMA descriptors + parameters) lives in caller memory of nvs_conv_tc_plan_bytes() bytes. */
 typedef struct NvsConvTcArgs {
@@ -119,7 +121,8 @@ int32_t nvs_conv_tc_cout_pad(int32_t cout);
 int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout);
 size_t nvs_conv_tc_plan_bytes(void);
 int nvs_conv_tc_plan_init(void* plan, const NvsConvTcArgs* args);
-int nvs_conv_tc_run(const void* plan, float* dst_override, void* stream);
+/* dst_override / dst2_override (may be NULL) replace dst / dst_pool of the plan for this launch. */
+int nvs_conv_tc_run(const void* plan, float* dst_override, float* dst2_override, void* stream);
 
 /* 3x3 conv with 1..4 output channels from a channels-last input (score / location heads,
  * heads.py:33): src (B,H,W,cin) NHWC, weight [9][cout][cin], bias [cout], dst (B,cout,H,W) NCHW;

@@ -469,6 +469,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           v[j] = a;
         }
         const int cbase = cc * 32;
+        if (p.dst_mode == 3) {
+          // keypoint heads (kp2dtiny.py:574-575, 927-935): channel 0 -> sigmoid -> score (B,1,H,W);
+          // channels 1,2 -> tanh -> centre shift (B,2,H,W), two NCHW outputs (dst / dst_pool pointer)
+          if (valid && cc == 0) {
+            const size_t plane = (size_t)p.H * p.W, pix = (size_t)gy * p.W + gx;
+            p.dst[(size_t)b * plane + pix] = 1.f / (1.f + expf(-v[0]));
+            p.dst_pool[((size_t)b * 2 + 0) * plane + pix] = tanhf(v[1]);
+            p.dst_pool[((size_t)b * 2 + 1) * plane + pix] = tanhf(v[2]);
+          }
+          continue;
+        }
         if (p.dst_mode == 1 && valid) {
           if (p.dst_layout == 0) {  // NHWC
             float4* d = reinterpret_cast<float4*>(
@@ -641,6 +652,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   if (a->dst_mode != 0 && ((a->dst_c_total % 4) || (a->dst_c_off % 4)) && a->dst_layout == 0) return NVS_ERR_ARG;
   if (a->dst_mode == 2 && (a->cout % 32) != 0) return NVS_ERR_UNSUPPORTED;
   if (a->act != NVS_ACT_NONE && a->act != NVS_ACT_LRELU && a->act != NVS_ACT_RELU) return NVS_ERR_UNSUPPORTED;
+  if (a->dst_mode == 3 && (a->cout != 3 || a->act != NVS_ACT_NONE)) return NVS_ERR_ARG;
   tc::Plan* pl = reinterpret_cast<tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   const int cpad = nvs_conv_tc_cout_pad(a->cout);
   const int cin = a->c0 + a->c1;
@@ -669,12 +681,14 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   return NVS_OK;
 }
 
-extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, void* stream) {
+extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float* dst2_override, void* stream) {
   if (!plan_mem) return NVS_ERR_ARG;
   const tc::Plan* pl = reinterpret_cast<const tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   if (pl->magic != tc::PLAN_MAGIC) return NVS_ERR_ARG;
   tc::Params p = pl->p;
   if (dst_override) p.dst = dst_override;
+  if (dst2_override) p.dst_pool = dst2_override;
+  if (p.dst_mode == 3 && (!p.dst || !p.dst_pool)) return NVS_ERR_ARG;
 #ifdef NVS_TC_DEBUG
   p.dbg = tc::g_dbg;
 #endif

@@ -282,8 +282,9 @@ class _Plan:
         self.bufs[name] = t
         return t
 
-    def tc(self, packed, src0, cout, *, out_name=None, **kw):
-        """Register a tensor-core conv (channels-last operands).  ``out_name``: write that forward output."""
+    def tc(self, packed, src0, cout, *, out_name=None, out2_name=None, **kw):
+        """Register a tensor-core conv (channels-last operands).  ``out_name`` / ``out2_name``: forward outputs
+        that receive dst / the second output of this launch."""
         op = ops.TcConv(src0, packed, cout, **kw)
         n_in = src0.shape[1] * src0.shape[2] * ((kw.get("c0") or src0.shape[3]) + (kw.get("c1") or (
             kw["src1"].shape[3] if kw.get("src1") is not None else 0)))
@@ -291,7 +292,7 @@ class _Plan:
         if kw.get("dst_pool") is not None:
             n_out += cout * (src0.shape[1] // 2) * (src0.shape[2] // 2)
         self.meta[len(self.steps)] = {"flops": op.flops, "bytes": 4.0 * self.B * (n_in + n_out), "shape": op.shape}
-        self.steps.append(("tc", op, out_name))
+        self.steps.append(("tc", op, out_name, out2_name))
 
     def call(self, fn, *a):
         self.steps.append(("call", fn, a))
@@ -487,13 +488,13 @@ class _KP2DTinyBase(nn.Module):
                 if st[0] == "conv":
                     run_conv(st[1])
                 else:
-                    st[1].run(outs[st[2]] if st[2] is not None else None)
+                    st[1].run(outs[st[2]] if st[2] is not None else None, outs[st[3]] if st[3] is not None else None)
                 e1.record()
                 prof["events"].append((e0, e1))
             elif st[0] == "conv":
                 run_conv(st[1])
             elif st[0] == "tc":
-                st[1].run(outs[st[2]] if st[2] is not None else None)
+                st[1].run(outs[st[2]] if st[2] is not None else None, outs[st[3]] if st[3] is not None else None)
             else:
                 st[1](outs, *st[2])
         result = {"score": outs["score"], "coord": outs["coord"], "feat": outs["feat"]}
@@ -762,8 +763,8 @@ class KP2DTinyV2(_KP2DTinyBase):
         P["score.a"] = self._pk_block(self.score_head.convDa, tc=tc)
         P["loc.a"] = self._pk_block(self.loc_head.convDa, tc=tc)
         if tc:
-            P["score.b"] = ops.pack_conv_small(self.score_head.convDb.weight, self.score_head.convDb.bias)
-            P["loc.b"] = ops.pack_conv_small(self.loc_head.convDb.weight, self.loc_head.convDb.bias)
+            P["kp.b"] = ops.pack_head_pair_tc(self.score_head.convDb.weight, self.score_head.convDb.bias,
+                                              self.loc_head.convDb.weight, self.loc_head.convDb.bias)
         else:
             P["score.b"] = self._pk_conv(self.score_head.convDb)
             P["loc.b"] = self._pk_conv(self.loc_head.convDb)
@@ -809,10 +810,11 @@ class KP2DTinyV2(_KP2DTinyBase):
         H2, W2 = skip.shape[1:3]
         sh = pl.buf_nhwc("sh", c4, H4, W4)
         pl.tc(P["score.a"], xb, c4, act=act, dst=sh)
-        pl.call(lambda outs: ops.conv_small(sh, P["score.b"], act=ops.ACT_SIGMOID, out=outs["score"]))
         lh = pl.buf_nhwc("lh", c4, H4, W4)
         pl.tc(P["loc.a"], xb, c4, act=act, dst=lh)
-        pl.call(lambda outs: ops.conv_small(lh, P["loc.b"], act=ops.ACT_TANH, out=outs["coord"]))
+        # both 1- and 2-channel output convs as one tensor-core launch (block-diagonal weight over [sh | lh]),
+        # sigmoid / tanh and the split into the two NCHW outputs happen in its epilogue
+        pl.tc(P["kp.b"], sh, 3, src1=lh, dst=None, dst_mode=3, dst_layout=1, out_name="score", out2_name="coord")
         da = pl.buf_nhwc("da", c4, H4, W4)
         pl.tc(P["desc.A"], xb, c4, act=act, dst=da)
         dps = pl.buf_nhwc("dps", c3, H2, W2)
@@ -866,8 +868,7 @@ class KP2DTinyV3(_KP2DTinyBase):
         # convDb (c4 -> 3) is launched as two tiny convs so that score (ch 0, sigmoid) and shift (ch 1:3, tanh)
         # land directly in their own output tensors (kp2dtiny.py:927-935) without a slicing copy.
         if tc:
-            P["sl.score"] = ops.pack_conv_small(h.convDb.weight[0:1], h.convDb.bias[0:1])
-            P["sl.shift"] = ops.pack_conv_small(h.convDb.weight[1:3], h.convDb.bias[1:3])
+            P["kp.b"] = ops.pack_head_pair_tc(h.convDb.weight, h.convDb.bias)
         else:
             P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
             P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
@@ -904,8 +905,7 @@ class KP2DTinyV3(_KP2DTinyBase):
         B, H4, W4, _ = xb.shape
         sl = pl.buf_nhwc("sl", c4, H4, W4)
         pl.tc(P["sl.a"], xb, c4, act=act, dst=sl)
-        pl.call(lambda outs: ops.conv_small(sl, P["sl.score"], act=ops.ACT_SIGMOID, out=outs["score"]))
-        pl.call(lambda outs: ops.conv_small(sl, P["sl.shift"], act=ops.ACT_TANH, out=outs["coord"]))
+        pl.tc(P["kp.b"], sl, 3, dst=None, dst_mode=3, dst_layout=1, out_name="score", out2_name="coord")
 
     def _plan_seg_out_tc(self, pl, s7, packed_last):
         B, H2, W2, c5 = s7.shape

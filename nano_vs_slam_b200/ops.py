@@ -386,6 +386,22 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
     return hi, lo, bp
 
 
+def pack_head_pair_tc(w_score: torch.Tensor, b_score: torch.Tensor, w_shift: Optional[torch.Tensor] = None,
+                      b_shift: Optional[torch.Tensor] = None):
+    """Keypoint-head output conv(s) as ONE tensor-core conv with 3 output channels.
+
+    V2: score_head.convDb (1, C, 3, 3) reads the score trunk and loc_head.convDb (2, C, 3, 3) reads the location
+    trunk (heads.py:33): the two trunks are the two sources of the conv, the weight is block diagonal (3, 2C, 3, 3).
+    V3: score_loc_head.convDb (3, C, 3, 3) is used as is (pass it as ``w_score``)."""
+    if w_shift is None:
+        return pack_conv_tc(w_score, bias=b_score)
+    c = w_score.shape[1]
+    w = torch.zeros(3, 2 * c, 3, 3, dtype=torch.float32, device=w_score.device)
+    w[0:1, :c] = w_score.detach().float()
+    w[1:3, c:] = w_shift.detach().float()
+    return pack_conv_tc(w, bias=torch.cat([b_score.detach().float(), b_shift.detach().float()]))
+
+
 def pack_conv_small(weight: torch.Tensor, bias: torch.Tensor):
     """OIHW (cout<=4) -> ([9][cout][cin], bias[cout]) for nvs_conv_small."""
     w = weight.detach().float()
@@ -431,7 +447,7 @@ class TcConv(object):
             else:
                 dst_c_total = dst.shape[1] if dst_layout == 1 else dst.shape[3]
         a.dst_c_total, a.dst_c_off, a.dst_layout, a.dst_mode = dst_c_total, dst_c_off, dst_layout, dst_mode
-        a.pool_c_total = dst_pool.shape[3] if dst_pool is not None else 0
+        a.pool_c_total = dst_pool.shape[3] if (dst_pool is not None and dst_mode != 3) else 0
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
         a.flags = 1 if deterministic else 0
@@ -442,7 +458,9 @@ class TcConv(object):
                 assert dst.shape[0] == B and tuple(dst.shape[2:]) == (H, W)
             elif dst_mode == 2:
                 assert tuple(dst.shape[:3]) == (B, 2 * H, 2 * W)
-        if dst_pool is not None:
+        if dst_mode == 3:
+            assert cout == 3 and act == ACT_NONE
+        if dst_pool is not None and dst_mode != 3:
             assert tuple(dst_pool.shape[:3]) == (B, H // 2, W // 2)
         self._keep = (src0, src1, hi, lo, bp, dst, dst_pool)
         self._mem = C.create_string_buffer(int(lib().nvs_conv_tc_plan_bytes()))
@@ -450,8 +468,9 @@ class TcConv(object):
         self.flops = 2.0 * 9 * (a.c0 + a.c1) * cout * H * W * B
         self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05"
 
-    def run(self, dst_override: Optional[torch.Tensor] = None) -> None:
-        check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _stream()), "nvs_conv_tc_run")
+    def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
+        check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _ptr(dst2_override), _stream()),
+              "nvs_conv_tc_run")
         LAUNCHES[0] += 1
 
 
