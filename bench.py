@@ -153,10 +153,10 @@ def run_reference(args):
         cpu_reference_fps(sd, sample, 1, threads)
     fps, dt = cpu_reference_fps(sd, sample, args.steps, threads)
     line = {
-        "impl": "reference", "metric": "KP2DTiny-S frames/s @240x320", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": f"KP2DTiny-{LETTER} frames/s @{H}x{W}", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"KP2DTiny-S (V2) forward+post_processing+select, {H}x{W}, CPU sample of {sample} frames/step",
+        "config": {"workload": f"KP2DTiny-{LETTER} ({'V3' if V3 else 'V2'}) forward+post_processing+select, {H}x{W}, CPU sample of {sample} frames/step",
                    "thresh": THRESH, "top_k": TOPK},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} frames x {args.steps} steps, torch CPU (oneDNN) restatement in oracle/"},
@@ -167,15 +167,22 @@ def run_reference(args):
 
 
 def main():
+    global LETTER, V3, NCLS, H, W
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--letter", default=LETTER, help="config letter (S, S_A, N, N_A); headline metric is S")
+    ap.add_argument("--v3", action="store_true", help="KP2DTinyV3 (decoder fusion) instead of V2")
+    ap.add_argument("--classes", type=int, default=NCLS)
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
     args = ap.parse_args()
+    LETTER, V3, NCLS, H, W = args.letter, args.v3, args.classes, args.height, args.width
     if args.impl == "reference":
         return run_reference(args)
 
@@ -327,10 +334,10 @@ def main():
                    "sample": f"{round(fps_cpu * dt)} frames of the same workload in batches of 8 ({dt:.1f} s of CPU "
                              "work), torch CPU (oneDNN) restatement in oracle/"}
         line = {
-            "metric": "KP2DTiny-S frames/s @240x320", "value": value, "unit": "frames/s", "n_gpus": world,
+            "metric": f"KP2DTiny-{LETTER} frames/s @{H}x{W}", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"KP2DTiny-S (V2 dedicated decoders, {NCLS} classes) forward + post_processing + "
+            "config": {"workload": f"KP2DTiny-{LETTER} ({'V3 decoder fusion' if V3 else 'V2 dedicated decoders'}, {NCLS} classes) forward + post_processing + "
                                    f"keypoint select (thr {THRESH}, top-{TOPK}), batch {B} x {H}x{W} per GPU",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"frame-dp{world}",
                        "conv_backend": model.conv_backend,

@@ -239,6 +239,11 @@ class _VPRHead(nn.Module):  # modules/decoders/vpr.py:8-76
             self.global_desc_dim = 0
 
 
+def _p32(c: int) -> int:
+    """Channel count of the zero-padded channels-last buffer that carries ``c`` real channels."""
+    return (c + 31) // 32 * 32
+
+
 # ----------------------------------------------------------------------------------------------
 # launch plan
 # ----------------------------------------------------------------------------------------------
@@ -320,11 +325,12 @@ class _KP2DTinyBase(nn.Module):
         # conv backend: "tc" = tcgen05 3xTF32 implicit GEMM on channels-last maps (needs 32-channel multiples:
         # the S letters), "ffma" = exact fp32 direct conv (any channel count: the N letters).
         c1, c2, c3, c4, c5, d1 = self.channel_dims
-        tc_ok = (all(c % 32 == 0 for c in (c2, c3, c4, c5, d1 // 4, self.encoder_dim)) and max(c4, c5, d1) <= 128
-                 and c1 % 16 == 0 and c2 <= 32)
+        # (channel counts that are not multiples of 32 -- the N letters: 24/48/72/96 -- run on zero-padded
+        # 32-channel rows: padded weights are zero, so padded activations stay exactly zero)
+        tc_ok = c1 % 16 == 0 and _p32(c2) <= 32 and max(_p32(c4), _p32(c5), _p32(d1)) <= 128 and d1 % 4 == 0
         self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
         if self.conv_backend == "tc" and not tc_ok:
-            raise NotImplementedError("tensor-core conv backend needs channel counts that are multiples of 32")
+            raise NotImplementedError("tensor-core conv backend: unsupported channel configuration")
 
     # --- reference API ------------------------------------------------------------------------
     def gather_info(self):  # kp2dtiny.py:463-485
@@ -391,18 +397,26 @@ class _KP2DTinyBase(nn.Module):
             self._plans = {}
         return self._packed
 
-    def _pk_block(self, m: _ConvBnAct, tc: bool = False):
+    def _pk_block(self, m: _ConvBnAct, tc: bool = False, seg=None):
         bn = {"weight": m.bn.weight, "bias": m.bn.bias, "running_mean": m.bn.running_mean,
               "running_var": m.bn.running_var}
         if tc:
-            return ops.pack_conv_tc(m.conv.weight, bn=bn, eps=m.bn.eps)
+            return ops.pack_conv_tc(m.conv.weight, bn=bn, eps=m.bn.eps, cin_segments=self._segs(m.conv, seg))
         return ops.pack_conv(m.conv.weight, bn=bn, eps=m.bn.eps)
 
-    @staticmethod
-    def _pk_conv(m: nn.Conv2d, s2d=False, tc: bool = False):
+    def _pk_conv(self, m: nn.Conv2d, s2d=False, tc: bool = False, seg=None):
         if tc:
-            return ops.pack_conv_tc(m.weight, bias=m.bias)
+            return ops.pack_conv_tc(m.weight, bias=m.bias, cin_segments=self._segs(m, seg))
         return ops.pack_conv(m.weight, bias=m.bias, s2d=s2d)
+
+    @staticmethod
+    def _segs(conv: nn.Conv2d, seg):
+        """Input-channel segments [(real, padded)] of a tensor-core conv; default: one segment padded to 32s."""
+        cin = conv.weight.shape[1]
+        if seg is None:
+            return [(cin, cin if cin == 16 else _p32(cin))]
+        assert sum(seg) == cin, (seg, cin)
+        return [(c, _p32(c)) for c in seg]
 
     def _pack_att(self, m: _AttModule):
         f, g = m.att.fn, m.mff.fn.net
@@ -424,9 +438,13 @@ class _KP2DTinyBase(nn.Module):
             # (16 channels) uses the 64-byte-row variant of the tensor-core kernel
             P["bb." + n] = self._pk_block(getattr(bb, n), tc=tc and n != "conv1a")
         sh = self.seg_head
+        c1_, c2_, c3_, c4_, c5_, d1_ = self.channel_dims
+        n_convs = len(sh.convs)
         for i, m in enumerate(sh.convs):
+            # the two concat convs read [pixel-shuffled d1/4 | x (c4)] and [pixel-shuffled d1/4 | skip (c4)]
+            seg = [d1_ // 4, c4_] if i in (n_convs - 4, n_convs - 2) else None
             if isinstance(m, _ConvBnAct):
-                P[f"seg.{i}"] = self._pk_block(m, tc=tc)
+                P[f"seg.{i}"] = self._pk_block(m, tc=tc, seg=seg)
             elif isinstance(m, _AttModule):
                 P[f"seg.{i}"] = self._pack_att(m)
             else:
@@ -592,11 +610,13 @@ class _KP2DTinyBase(nn.Module):
 
     def _build_plan_tc(self, pl: _Plan):
         """Same graph as _build_plan_ffma with channels-last intermediates and tcgen05 convs (csrc/conv_tc.cu).
-        Only the 3->16 and 16->32 stem layers, the attention internals and the 1..3-channel head outputs use
-        other kernels."""
+        Only the 3->16 stem layer and the attention internals use other kernels.  Intermediate buffers carry
+        channel counts padded to multiples of 32 (no-op for the S letters); padded channels are exact zeros."""
         P = self._packed
         B, H, W = pl.B, pl.H, pl.W
         c1, c2, c3, c4, c5, d1 = self.channel_dims
+        c2p, c3p, c4p, c5p, qp = _p32(c2), _p32(c3), _p32(c4), _p32(c5), _p32(d1 // 4)
+        d1p = _p32(d1)
         act = ops.ACT_LRELU if self.leaky_relu else ops.ACT_RELU
         H2, W2 = H // 2, W // 2
         H4, W4 = H2 // 2, W2 // 2
@@ -604,65 +624,67 @@ class _KP2DTinyBase(nn.Module):
         nf, ncls = self.nfeatures, self.nClasses
         pl.out_shapes = {"score": (B, 1, H4, W4), "coord": (B, 2, H4, W4), "feat": (B, nf, H2, W2),
                          "seg": (B, ncls, H2, W2)}
-        # ---- stem on the FFMA kernel: NCHW in, channels-last pooled map out ----
+        # ---- stem layer on the FFMA kernel: NCHW in, channels-last out ----
         xin = torch.empty(B, 3, H, W, device=pl.device)
         t1a = pl.buf_nhwc("t1a", c1, H, W)
         pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a, dst_nhwc=True)
         pl.in_args = pl.steps[-1][1]
         # ---- backbone on tensor cores ----
-        p1 = pl.buf_nhwc("p1", c2, H2, W2)
-        pl.tc(P["bb.conv1b"], t1a, c2, act=act, dst=None, dst_mode=0, dst_pool=p1)
-        t2a = pl.buf_nhwc("t2a", c2, H2, W2)
-        pl.tc(P["bb.conv2a"], p1, c2, act=act, dst=t2a)
-        t2b = pl.buf_nhwc("t2b", c3, H2, W2)
-        pl.tc(P["bb.conv2b"], t2a, c3, act=act, dst=t2b)
-        t3a = pl.buf_nhwc("t3a", c3, H2, W2)
-        pl.tc(P["bb.conv3a"], t2b, c3, act=act, dst=t3a)
-        skip = pl.buf_nhwc("skip", c4, H2, W2)
-        p3 = pl.buf_nhwc("p3", c4, H4, W4)
-        pl.tc(P["bb.conv3b"], t3a, c4, act=act, dst=skip, dst_pool=p3)
-        t4a = pl.buf_nhwc("t4a", c4, H4, W4)
-        pl.tc(P["bb.conv4a"], p3, c4, act=act, dst=t4a)
-        xb = pl.buf_nhwc("xb", c4, H4, W4)
-        pl.tc(P["bb.conv4b"], t4a, c4, act=act, dst=xb)
+        p1 = pl.buf_nhwc("p1", c2p, H2, W2)
+        pl.tc(P["bb.conv1b"], t1a, c2p, act=act, dst=None, dst_mode=0, dst_pool=p1)
+        t2a = pl.buf_nhwc("t2a", c2p, H2, W2)
+        pl.tc(P["bb.conv2a"], p1, c2p, act=act, dst=t2a)
+        t2b = pl.buf_nhwc("t2b", c3p, H2, W2)
+        pl.tc(P["bb.conv2b"], t2a, c3p, act=act, dst=t2b)
+        t3a = pl.buf_nhwc("t3a", c3p, H2, W2)
+        pl.tc(P["bb.conv3a"], t2b, c3p, act=act, dst=t3a)
+        skip = pl.buf_nhwc("skip", c4p, H2, W2)
+        p3 = pl.buf_nhwc("p3", c4p, H4, W4)
+        pl.tc(P["bb.conv3b"], t3a, c4p, act=act, dst=skip, dst_pool=p3)
+        t4a = pl.buf_nhwc("t4a", c4p, H4, W4)
+        pl.tc(P["bb.conv4a"], p3, c4p, act=act, dst=t4a)
+        xb = pl.buf_nhwc("xb", c4p, H4, W4)
+        pl.tc(P["bb.conv4b"], t4a, c4p, act=act, dst=xb)
 
         self._plan_heads_tc(pl, xb, skip, act)
 
         # ---- segmentation trunk ----
-        sp3 = pl.buf_nhwc("sp3", c5, H8, W8)
+        sp3 = pl.buf_nhwc("sp3", c5p, H8, W8)
         if self.use_attention:
-            s0 = pl.buf("s0", c5, H4, W4)  # NCHW: the attention block's LN / projections read planes
+            s0 = pl.buf("s0", c5, H4, W4)  # NCHW, real channels: the attention block's LN / projections read planes
             pl.tc(P["seg.0"], xb, c5, act=act, dst=s0, dst_layout=1)
             sp = pl.buf("sp", c5, H8, W8)
             self._plan_att(pl, P["seg.1"], s0, c5, H4, W4, "a1", pooled_out=sp)
+            sp3.zero_()  # the FFMA 1x1 writes the real channels only; padding must read as zero
             self._plan_att(pl, P["seg.2"], sp, c5, H8, W8, "a2", plain_out=sp3, plain_nhwc=True)
             nxt = 3
         else:
-            s0 = pl.buf_nhwc("s0", c5, H4, W4)
-            pl.tc(P["seg.0"], xb, c5, act=act, dst=s0)
-            sp = pl.buf_nhwc("sp", c5, H8, W8)
-            pl.tc(P["seg.1"], s0, c5, act=act, dst=None, dst_mode=0, dst_pool=sp)
-            s2 = pl.buf_nhwc("s2", c5, H8, W8)
-            pl.tc(P["seg.2"], sp, c5, act=act, dst=s2)
-            pl.tc(P["seg.3"], s2, c5, act=act, dst=sp3)
+            s0 = pl.buf_nhwc("s0", c5p, H4, W4)
+            pl.tc(P["seg.0"], xb, c5p, act=act, dst=s0)
+            sp = pl.buf_nhwc("sp", c5p, H8, W8)
+            pl.tc(P["seg.1"], s0, c5p, act=act, dst=None, dst_mode=0, dst_pool=sp)
+            s2 = pl.buf_nhwc("s2", c5p, H8, W8)
+            pl.tc(P["seg.2"], sp, c5p, act=act, dst=s2)
+            pl.tc(P["seg.3"], s2, c5p, act=act, dst=sp3)
             nxt = 4
-        ps1 = pl.buf_nhwc("ps1", d1 // 4, H4, W4)
-        pl.tc(P[f"seg.{nxt}"], sp3, d1, act=act, dst=ps1, dst_mode=2)
-        s5 = pl.buf_nhwc("s5", c5, H4, W4)
-        pl.tc(P[f"seg.{nxt + 1}"], ps1, c5, act=act, src1=xb, dst=s5)
-        ps2 = pl.buf_nhwc("ps2", d1 // 4, H2, W2)
-        pl.tc(P[f"seg.{nxt + 2}"], s5, d1, act=act, dst=ps2, dst_mode=2)
-        s7 = pl.buf_nhwc("s7", c5, H2, W2)
-        pl.tc(P[f"seg.{nxt + 3}"], ps2, c5, act=act, src1=skip, dst=s7)
+        ps1 = pl.buf_nhwc("ps1", qp, H4, W4)
+        pl.tc(P[f"seg.{nxt}"], sp3, d1p, act=act, dst=ps1, dst_mode=2)
+        s5 = pl.buf_nhwc("s5", c5p, H4, W4)
+        pl.tc(P[f"seg.{nxt + 1}"], ps1, c5p, act=act, src1=xb, dst=s5)
+        ps2 = pl.buf_nhwc("ps2", qp, H2, W2)
+        pl.tc(P[f"seg.{nxt + 2}"], s5, d1p, act=act, dst=ps2, dst_mode=2)
+        s7 = pl.buf_nhwc("s7", c5p, H2, W2)
+        pl.tc(P[f"seg.{nxt + 3}"], ps2, c5p, act=act, src1=skip, dst=s7)
         self._plan_seg_out_tc(pl, s7, P[f"seg.{nxt + 4}"])
 
         # ---- VPR head ----
         enc = self.encoder_dim
-        v1 = pl.buf_nhwc("v1", enc, H4, W4)
-        pl.tc(P["vlad.convlad1"], xb, enc, act=act, dst=v1)
-        v2 = pl.buf_nhwc("v2", enc, H4, W4)
-        pl.tc(P["vlad.convlad2"], v1, enc, act=act, dst=v2)
-        v3 = pl.buf("v3", enc, H4, W4)  # NCHW for the NetVLAD kernel
+        encp = _p32(enc)
+        v1 = pl.buf_nhwc("v1", encp, H4, W4)
+        pl.tc(P["vlad.convlad1"], xb, encp, act=act, dst=v1)
+        v2 = pl.buf_nhwc("v2", encp, H4, W4)
+        pl.tc(P["vlad.convlad2"], v1, encp, act=act, dst=v2)
+        v3 = pl.buf("v3", enc, H4, W4)  # NCHW, real channels, for the NetVLAD kernel
         pl.tc(P["vlad.convlad3"], v2, enc, act=act, dst=v3, dst_layout=1)
         if not self.vlad_head.remove_netvlad:
             K = self.vlad_head.netvlad.num_clusters
@@ -764,14 +786,15 @@ class KP2DTinyV2(_KP2DTinyBase):
         P["loc.a"] = self._pk_block(self.loc_head.convDa, tc=tc)
         if tc:
             P["kp.b"] = ops.pack_head_pair_tc(self.score_head.convDb.weight, self.score_head.convDb.bias,
-                                              self.loc_head.convDb.weight, self.loc_head.convDb.bias)
+                                              self.loc_head.convDb.weight, self.loc_head.convDb.bias,
+                                              cpad=_p32(self.channel_dims[3]))
         else:
             P["score.b"] = self._pk_conv(self.score_head.convDb)
             P["loc.b"] = self._pk_conv(self.loc_head.convDb)
         d = self.desc_head
         P["desc.A"] = self._pk_block(d.convA, tc=tc)
         P["desc.B"] = self._pk_conv(d.convB, tc=tc)
-        P["desc.Aa"] = self._pk_block(d.confAa, tc=tc)
+        P["desc.Aa"] = self._pk_block(d.confAa, tc=tc, seg=[self.channel_dims[2], self.channel_dims[3]])
         P["desc.Bb"] = self._pk_conv(d.confBb, tc=tc)
 
     def _plan_heads(self, pl, xb, skip, act):
@@ -806,21 +829,22 @@ class KP2DTinyV2(_KP2DTinyBase):
     def _plan_heads_tc(self, pl, xb, skip, act):
         P = self._packed
         c1, c2, c3, c4, c5, d1 = self.channel_dims
+        c3p, c4p = _p32(c3), _p32(c4)
         B, H4, W4, _ = xb.shape
         H2, W2 = skip.shape[1:3]
-        sh = pl.buf_nhwc("sh", c4, H4, W4)
-        pl.tc(P["score.a"], xb, c4, act=act, dst=sh)
-        lh = pl.buf_nhwc("lh", c4, H4, W4)
-        pl.tc(P["loc.a"], xb, c4, act=act, dst=lh)
+        sh = pl.buf_nhwc("sh", c4p, H4, W4)
+        pl.tc(P["score.a"], xb, c4p, act=act, dst=sh)
+        lh = pl.buf_nhwc("lh", c4p, H4, W4)
+        pl.tc(P["loc.a"], xb, c4p, act=act, dst=lh)
         # both 1- and 2-channel output convs as one tensor-core launch (block-diagonal weight over [sh | lh]),
         # sigmoid / tanh and the split into the two NCHW outputs happen in its epilogue
         pl.tc(P["kp.b"], sh, 3, src1=lh, dst=None, dst_mode=3, dst_layout=1, out_name="score", out2_name="coord")
-        da = pl.buf_nhwc("da", c4, H4, W4)
-        pl.tc(P["desc.A"], xb, c4, act=act, dst=da)
-        dps = pl.buf_nhwc("dps", c3, H2, W2)
-        pl.tc(P["desc.B"], da, 4 * c3, dst=dps, dst_mode=2)
-        dA = pl.buf_nhwc("dA", c4, H2, W2)
-        pl.tc(P["desc.Aa"], dps, c4, act=act, src1=skip, dst=dA)
+        da = pl.buf_nhwc("da", c4p, H4, W4)
+        pl.tc(P["desc.A"], xb, c4p, act=act, dst=da)
+        dps = pl.buf_nhwc("dps", c3p, H2, W2)
+        pl.tc(P["desc.B"], da, 4 * c3p, dst=dps, dst_mode=2)
+        dA = pl.buf_nhwc("dA", c4p, H2, W2)
+        pl.tc(P["desc.Aa"], dps, c4p, act=act, src1=skip, dst=dA)
         pl.tc(P["desc.Bb"], dA, self.nfeatures, dst=None, dst_layout=1, dst_c_total=self.nfeatures, out_name="feat")
 
     def _plan_seg_out_tc(self, pl, s7, packed_last):
@@ -868,7 +892,7 @@ class KP2DTinyV3(_KP2DTinyBase):
         # convDb (c4 -> 3) is launched as two tiny convs so that score (ch 0, sigmoid) and shift (ch 1:3, tanh)
         # land directly in their own output tensors (kp2dtiny.py:927-935) without a slicing copy.
         if tc:
-            P["kp.b"] = ops.pack_head_pair_tc(h.convDb.weight, h.convDb.bias)
+            P["kp.b"] = ops.pack_head_pair_tc(h.convDb.weight, h.convDb.bias, cpad=_p32(self.channel_dims[3]))
         else:
             P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
             P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
@@ -901,21 +925,23 @@ class KP2DTinyV3(_KP2DTinyBase):
 
     def _plan_heads_tc(self, pl, xb, skip, act):
         P = self._packed
-        c4 = self.channel_dims[3]
+        c4p = _p32(self.channel_dims[3])
         B, H4, W4, _ = xb.shape
-        sl = pl.buf_nhwc("sl", c4, H4, W4)
-        pl.tc(P["sl.a"], xb, c4, act=act, dst=sl)
+        sl = pl.buf_nhwc("sl", c4p, H4, W4)
+        pl.tc(P["sl.a"], xb, c4p, act=act, dst=sl)
         pl.tc(P["kp.b"], sl, 3, dst=None, dst_mode=3, dst_layout=1, out_name="score", out2_name="coord")
 
     def _plan_seg_out_tc(self, pl, s7, packed_last):
-        B, H2, W2, c5 = s7.shape
-        ds = self.seg_head.dim_split
-        pl.tc(self._packed["featB"], s7, self.nfeatures, c0_off=0, c0=ds, dst=None, dst_layout=1,
+        B, H2, W2, _ = s7.shape
+        c5 = self.channel_dims[4]
+        ds = self.seg_head.dim_split   # real channels per half; each conv reads a 32-channel (padded) window
+        dsp = _p32(ds)
+        pl.tc(self._packed["featB"], s7, self.nfeatures, c0_off=0, c0=dsp, dst=None, dst_layout=1,
               dst_c_total=self.nfeatures, out_name="feat")
         if self.remove_softmax:
-            pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds, dst=None, dst_layout=1,
+            pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=dsp, dst=None, dst_layout=1,
                   dst_c_total=self.nClasses, out_name="seg")
         else:
             logits = pl.buf("seg_logits", self.nClasses, H2, W2)
-            pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds, dst=logits, dst_layout=1)
+            pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=dsp, dst=logits, dst_layout=1)
             pl.call(lambda outs: ops.softmax_channels(logits, out=outs["seg"]))

@@ -368,11 +368,24 @@ def _fold(weight, bias, bn, eps):
 
 
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
-                 eps: float = 1e-5):
+                 eps: float = 1e-5, cin_segments=None):
     """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc.
 
-    w_hi keeps the 10 tf32 mantissa bits (low 13 bits cleared), w_lo = w - w_hi exactly (fp32)."""
+    w_hi keeps the 10 tf32 mantissa bits (low 13 bits cleared), w_lo = w - w_hi exactly (fp32).
+    ``cin_segments``: [(real, padded), ...] -- the input channels arrive as consecutive segments of ``real``
+    channels, each stored in a channels-last buffer padded with zeros to ``padded`` channels (the N letters have
+    24/48/72/96 channels; the tensor-core kernel works on 32-channel rows).  Zero weight columns are inserted."""
     w, b = _fold(weight, bias, bn, eps)
+    if cin_segments is not None:
+        assert sum(r for r, _ in cin_segments) == w.shape[1], (cin_segments, w.shape)
+        parts, at = [], 0
+        for real, padded in cin_segments:
+            seg = w[:, at:at + real]
+            if padded > real:
+                seg = torch.cat([seg, torch.zeros(w.shape[0], padded - real, 3, 3, dtype=w.dtype, device=w.device)], 1)
+            parts.append(seg)
+            at += real
+        w = torch.cat(parts, 1)
     cout, cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     cpad = int(lib().nvs_conv_tc_cout_pad(cout))
@@ -387,19 +400,21 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
 
 
 def pack_head_pair_tc(w_score: torch.Tensor, b_score: torch.Tensor, w_shift: Optional[torch.Tensor] = None,
-                      b_shift: Optional[torch.Tensor] = None):
+                      b_shift: Optional[torch.Tensor] = None, cpad: Optional[int] = None):
     """Keypoint-head output conv(s) as ONE tensor-core conv with 3 output channels.
 
     V2: score_head.convDb (1, C, 3, 3) reads the score trunk and loc_head.convDb (2, C, 3, 3) reads the location
     trunk (heads.py:33): the two trunks are the two sources of the conv, the weight is block diagonal (3, 2C, 3, 3).
     V3: score_loc_head.convDb (3, C, 3, 3) is used as is (pass it as ``w_score``)."""
-    if w_shift is None:
-        return pack_conv_tc(w_score, bias=b_score)
     c = w_score.shape[1]
+    cpad = c if cpad is None else cpad
+    if w_shift is None:
+        return pack_conv_tc(w_score, bias=b_score, cin_segments=[(c, cpad)])
     w = torch.zeros(3, 2 * c, 3, 3, dtype=torch.float32, device=w_score.device)
     w[0:1, :c] = w_score.detach().float()
     w[1:3, c:] = w_shift.detach().float()
-    return pack_conv_tc(w, bias=torch.cat([b_score.detach().float(), b_shift.detach().float()]))
+    return pack_conv_tc(w, bias=torch.cat([b_score.detach().float(), b_shift.detach().float()]),
+                        cin_segments=[(c, cpad), (c, cpad)])
 
 
 def pack_conv_small(weight: torch.Tensor, bias: torch.Tensor):

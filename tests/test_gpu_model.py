@@ -86,7 +86,7 @@ def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W):
         assert jac >= 0.99, jac  # single near-threshold flips allowed at k=300 (1/300 > 0.1 %)
 
 
-@pytest.mark.parametrize("letter,v3", [("S", False), ("S_A", True)])
+@pytest.mark.parametrize("letter,v3", [("S", False), ("S_A", True), ("N", True), ("N_A", False)])
 def test_both_conv_backends_agree_with_golden(letter, v3):
     """The S letters run on tensor cores by default; the exact-fp32 FFMA backend must stay green too."""
     from nano_vs_slam_b200.synthetic import synthetic_frames
