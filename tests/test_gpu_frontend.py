@@ -1,0 +1,78 @@
+"""Reference-shaped wrappers: KP2DtinyFrontend (frontend.py:11-129), BfFeatureMatcher (feature_matcher.py:234)."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _frontend(thr, top_k, **kw):
+    from nano_vs_slam_b200 import tiny_factory
+    from nano_vs_slam_b200.frontend import KP2DtinyFrontend
+    from nano_vs_slam_b200.synthetic import spread_init
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        sd = spread_init(tiny_factory("S", 28).state_dict(), 4321)
+        fe = KP2DtinyFrontend(config="S", nClasses=28, nn_thresh=thr, top_k=top_k, device="cuda", state_dict=sd, **kw)
+    return fe, sd
+
+
+def test_frontend_run_matches_oracle_decode():
+    from oracle import glue_ref, kp2dtiny_ref as R
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    H, W, thr, k = 120, 160, 0.45, 150
+    fe, sd = _frontend(thr, k)
+    img01 = (synthetic_frames(1, H, W, 3)[0] + 1) / 2          # the front-end takes [0,1] frames (frontend.py:79)
+    pts, desc, seg = fe.run(img01)
+    a = R.arch_for("S", False, 28)
+    x = img01.unsqueeze(0).sub(0.5).mul(2.0)
+    post = R.post_processing(R.forward(x, sd, a), H, W, a)
+    rp, rd, _, cells = glue_ref.frontend_decode(post, 32, thr, k)
+    assert pts.shape == rp.shape and desc.shape == rd.shape and pts.shape[0] > 20
+    # compare as sets of points (argpartition order is unspecified); allow one near-threshold flip
+    got = {(round(float(x_), 2), round(float(y_), 2)) for x_, y_ in pts}
+    ref = {(round(float(x_), 2), round(float(y_), 2)) for x_, y_ in rp}
+    assert len(got ^ ref) <= 2
+
+
+def test_frontend_stream_equals_run_batch_and_semantic_filter():
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    H, W = 64, 96
+    fe, _ = _frontend(0.4, 50)
+    batches = [synthetic_frames(3, H, W, s).pin_memory() for s in range(4)]
+    ref = []
+    for hb in batches:
+        sel, post = fe.run_batch(hb.cuda(), normalized=True)
+        ref.append({k: sel[k].cpu().clone() for k in ("pts", "desc", "count")} | {"vlad": post["vlad"].cpu().clone()})
+    got = [{k: v.clone() for k, v in r.items()} for r in fe.stream(iter(batches), normalized=True)]
+    assert len(got) == len(batches)
+    for g, r in zip(got, ref):
+        assert torch.equal(g["count"], r["count"])
+        for b in range(3):
+            n = int(r["count"][b])
+            assert torch.allclose(g["pts"][b, :n], r["pts"][b, :n]) and torch.allclose(g["desc"][b, :n], r["desc"][b, :n], atol=1e-5)
+        assert torch.allclose(g["vlad"], r["vlad"], atol=1e-6)
+    # semantic filter path (sample_segmentation=True, labels per cell)
+    fe2, _ = _frontend(0.4, 50, semantic_filter=True, classes_to_filter=[0, 1, 2, 3, 4, 5])
+    pts, desc, seg = fe2.run((batches[0][0] + 1) / 2)
+    assert len(seg) == len(pts) and not np.isin(seg, [0, 1, 2, 3, 4, 5]).any()
+
+
+def test_bf_feature_matcher_wrapper():
+    from nano_vs_slam_b200.matcher import BfFeatureMatcher
+    from oracle import glue_ref
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "matcher_cv2.npz"))
+    m = BfFeatureMatcher()
+    i1, i2, sc = m.match(z["des1"], z["des2"])                   # numpy in, python lists out (reference signature)
+    r1, r2, rs = glue_ref.good_matches_one_to_one(z["idx"], z["dist"], 0.7)
+    assert i1 == r1 and i2 == r2 and np.allclose(sc, rs, rtol=2e-5)
+    mm = BfFeatureMatcher(cross_check=True)
+    j1, j2, _ = mm.match(z["des1"], z["des2"])
+    assert sorted(zip(j1, j2)) == sorted(map(tuple, z["cross"].tolist()))
