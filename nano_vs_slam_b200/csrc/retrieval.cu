@@ -5,7 +5,10 @@
 // The Q x N x D contraction is the one genuinely tensor-core shaped piece of the hot path
 // (10k x 1M x 4096 = 8.2e13 FLOP): it runs as a warp-specialised tcgen05 GEMM
 //   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages bf16 tiles of queries (A, 128 x 64) and
-//     database rows (B, 256 x 64) into a 4-deep shared-memory ring,
+//     database rows (B, 256 x 64) into a 4-deep shared-memory ring.  The kernel is bound by the L2->SM
+//     fabric (~42 B/cycle/SM chip-wide), so CTAs run as clusters of two that work on the same database
+//     tiles for two different query blocks: each CTA fetches HALF of every B tile and TMA-multicasts it
+//     into both CTAs' shared memory (48 -> 32 KB of L2 reads per CTA per stage),
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) into a
 //     double-buffered 128 x 256 fp32 accumulator in TMEM (2 x 256 columns),
 //   * four epilogue warps read the accumulator with tcgen05.ld, form |x|^2 - 2 q.x and keep a running
@@ -75,6 +78,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                               int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -129,9 +154,10 @@ struct Params {
   int Q, N, kblocks;    // kblocks = Dpad / 64
   int k, kp;            // list length and its (odd) pitch
   int n_mblk, n_strips, tiles_per_strip, n_tiles;
+  int n_mpair;          // ceil(n_mblk / 2): a cluster of two CTAs owns query blocks (2*pair, 2*pair + 1)
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                     const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -148,6 +174,8 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // 0 / 1 inside the CTA pair
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
@@ -156,7 +184,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), 2);  // the peer multicasts into this stage too: both CTAs' MMAs must have retired
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -172,27 +200,30 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_units = p.n_mblk * p.n_strips;
+  const int n_units = p.n_mpair * p.n_strips;  // (strip, query-block pair) units, round-robin over clusters
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int strip = u / p.n_mblk, mblk = u - strip * p.n_mblk;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        const int strip = u / p.n_mpair, mblk = 2 * (u - strip * p.n_mpair) + (int)crank;
         const int t_begin = strip * p.tiles_per_strip;
         const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
         for (int t = t_begin; t < t_end; ++t) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t a_dst = base + SM_TILES + stage * STAGE_BYTES;
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BK, mblk * BM);
-            tma_load_2d(a_dst + A_BYTES, &tmap_x, full_bar(stage), kb * BK, t * BN);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);  // own A + own half of B + the peer's half of B
+            tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BK, mblk * BM);  // (rows past Q: zero filled)
+            // my half (128 rows) of the 256-row database tile, delivered to BOTH CTAs of the pair
+            tma_load_2d_mc(a_dst + A_BYTES + crank * (B_BYTES / 2), &tmap_x, full_bar(stage), kb * BK,
+                           t * BN + (int)crank * (BN / 2), (uint16_t)0x3);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -206,8 +237,8 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int strip = u / p.n_mblk;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        const int strip = u / p.n_mpair;
         const int t_begin = strip * p.tiles_per_strip;
         const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
         for (int t = t_begin; t < t_end; ++t) {
@@ -226,7 +257,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
                           (kb | k) != 0 ? 1u : 0u);
             }
-            tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+            tc_commit_mc(empty_bar(stage), (uint16_t)0x3);  // frees this stage in BOTH CTAs when these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -249,8 +280,8 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     int32_t* my_i = list_i + row * p.kp;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int strip = u / p.n_mblk, mblk = u - strip * p.n_mblk;
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+      const int strip = u / p.n_mpair, mblk = 2 * (u - strip * p.n_mpair) + (int)crank;
       const int t_begin = strip * p.tiles_per_strip;
       const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
       for (int j = 0; j < p.k; ++j) {
@@ -325,6 +356,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
@@ -606,13 +638,14 @@ extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float
 
   CUtensorMap mq, mx;
   if (make_map(&mq, qb, (uint64_t)L.qpad, (uint64_t)L.dpad, BM) != NVS_OK) return NVS_ERR_CUDA;
-  if (make_map(&mx, db_bf16, (uint64_t)n_db, (uint64_t)L.dpad, BN) != NVS_OK) return NVS_ERR_CUDA;
+  if (make_map(&mx, db_bf16, (uint64_t)n_db, (uint64_t)L.dpad, BN / 2) != NVS_OK) return NVS_ERR_CUDA;  // half tiles
 
   Params p;
   p.xnorm = db_norms; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
   p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
   p.k = k; p.kp = k | 1;
   p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;
+  p.n_mpair = (L.n_mblk + 1) / 2;
 
   static int sm_count = 0;
   static bool attr_done = false;
@@ -624,8 +657,8 @@ extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float
     if (e != cudaSuccess) return nvs_set_cuda_error(e);
     attr_done = true;
   }
-  const int n_units = L.n_mblk * L.n_strips;
-  const int grid = n_units < sm_count ? n_units : sm_count;
+  const int n_units = ((L.n_mblk + 1) / 2) * L.n_strips;           // work units of CTA pairs
+  int grid = 2 * (n_units < sm_count / 2 ? n_units : sm_count / 2);  // clusters of two CTAs
   if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
   flat_l2_topk_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mq, mx, p);
   NVS_CHECK_LAUNCH();
