@@ -1,15 +1,22 @@
 // Streaming-softmax attention core of EfficientSelfAttention (modules/segformer.py:113-133).
 // The reference materialises sim = q k^T ((B*heads) x Nq x Nk fp32: 92 MB per 240x320 frame, 4.3 GB per
-// 512x1024 frame); here one thread owns one query, K/V of the (frame, head) stream through shared
-// memory in blocks of KB keys and the softmax is kept online (running max / sum), fp32 throughout.
-// head_dim is 16 (S) or 12 (N): far too small for tensor-core tiles to pay, the kernel is FFMA/MUFU bound.
+// 512x1024 frame); here K/V of a (frame, head) stream through shared memory in blocks of KB keys and the
+// softmax is kept online (running max / sum), fp32 throughout.
+//
+// head_dim is 16 (S) or 12 (N): the P.V product would be an N = 16 GEMM, far too narrow for tcgen05 tiles
+// (an MMA costs >= 50 cycles whatever N is), so this stays on the CUDA cores and is organised around their
+// limits instead: every thread owns TWO queries (K/V rows are warp-broadcast LDS.128, so two queries halve the
+// shared-memory instructions per FMA) and all multiply-adds are packed FFMA2 (fma.rn.f32x2, two fp32 FMAs per
+// issue slot on sm_100) so the FMA pipe, not the issue port, is the bound; exp2 with pre-scaled logits.
 #include "common.cuh"
 
 namespace nvs {
 
-constexpr int ATT_THREADS = 128;  // queries per CTA
-constexpr int ATT_KB = 256;       // keys staged per block
-constexpr int ATT_G = 8;          // keys per online-softmax group
+constexpr int ATT_THREADS = 128;              // threads per CTA
+constexpr int ATT_QPT = 2;                    // queries per thread
+constexpr int ATT_QPB = ATT_THREADS * ATT_QPT;  // queries per CTA
+constexpr int ATT_KB = 256;                   // keys staged per block
+constexpr int ATT_G = 8;                      // keys per online-softmax group
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __restrict__ q,
@@ -17,23 +24,32 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
                                                                 float* __restrict__ out, int C, int Nq,
                                                                 int Nk, float scale_log2e) {
   constexpr int DP = 20;  // row pitch: 16-byte aligned rows, 4-way (not 16-way) conflicts on the fill
+  constexpr int H = D / 2;
   static_assert(D <= 16 && D % 4 == 0, "head_dim 12 or 16");
   __shared__ __align__(16) float ks[ATT_KB][DP];
   __shared__ __align__(16) float vs[ATT_KB][DP];
   const int head = blockIdx.y, b = blockIdx.z;
-  const int n = blockIdx.x * ATT_THREADS + threadIdx.x;
-  const bool active = n < Nq;
   const float* qb = q + ((size_t)b * C + head * D) * Nq;
   const float* kb = kv + ((size_t)b * 2 * C + head * D) * Nk;
   const float* vb = kv + ((size_t)b * 2 * C + C + head * D) * Nk;
 
-  float qr[D], o[D];
+  int n[ATT_QPT];
+  bool active[ATT_QPT];
+  float2 qr[ATT_QPT][H], o[ATT_QPT][H];
+  float m[ATT_QPT], l[ATT_QPT];
 #pragma unroll
-  for (int c = 0; c < D; ++c) {
-    qr[c] = active ? qb[(size_t)c * Nq + n] * scale_log2e : 0.f;
-    o[c] = 0.f;
+  for (int t = 0; t < ATT_QPT; ++t) {
+    n[t] = blockIdx.x * ATT_QPB + t * ATT_THREADS + threadIdx.x;  // coalesced along queries
+    active[t] = n[t] < Nq;
+#pragma unroll
+    for (int c = 0; c < H; ++c) {
+      qr[t][c].x = active[t] ? qb[(size_t)(2 * c) * Nq + n[t]] * scale_log2e : 0.f;
+      qr[t][c].y = active[t] ? qb[(size_t)(2 * c + 1) * Nq + n[t]] * scale_log2e : 0.f;
+      o[t][c] = make_float2(0.f, 0.f);
+    }
+    m[t] = -INFINITY;
+    l[t] = 0.f;
   }
-  float m = -INFINITY, l = 0.f;
 
   for (int j0 = 0; j0 < Nk; j0 += ATT_KB) {
     const int nk = min(ATT_KB, Nk - j0);
@@ -46,48 +62,70 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
     }
     __syncthreads();
     for (int g0 = 0; g0 < nk; g0 += ATT_G) {
-      float s[ATT_G];
-      float gm = -INFINITY;
+      float s[ATT_QPT][ATT_G];
+      float gm[ATT_QPT];
+#pragma unroll
+      for (int t = 0; t < ATT_QPT; ++t) gm[t] = -INFINITY;
 #pragma unroll
       for (int g = 0; g < ATT_G; ++g) {
-        float a = 0.f;
+        float2 kk[H];
 #pragma unroll
         for (int c4 = 0; c4 < D; c4 += 4) {
-          const float4 kk = *reinterpret_cast<const float4*>(&ks[g0 + g][c4]);
-          a = fmaf(qr[c4], kk.x, a);
-          a = fmaf(qr[c4 + 1], kk.y, a);
-          a = fmaf(qr[c4 + 2], kk.z, a);
-          a = fmaf(qr[c4 + 3], kk.w, a);
+          const float4 k4 = *reinterpret_cast<const float4*>(&ks[g0 + g][c4]);
+          kk[c4 / 2] = make_float2(k4.x, k4.y);
+          kk[c4 / 2 + 1] = make_float2(k4.z, k4.w);
         }
-        s[g] = (g0 + g < nk) ? a : -INFINITY;
-        gm = fmaxf(gm, s[g]);
-      }
-      const float mn = fmaxf(m, gm);
-      const float corr = exp2f(m - mn);  // m = -inf on the first group -> 0
-      l *= corr;
+        const bool kvalid = g0 + g < nk;
 #pragma unroll
-      for (int c = 0; c < D; ++c) o[c] *= corr;
-      m = mn;
+        for (int t = 0; t < ATT_QPT; ++t) {
+          float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < H; ++c) a = __ffma2_rn(qr[t][c], kk[c], a);
+          s[t][g] = kvalid ? a.x + a.y : -INFINITY;
+          gm[t] = fmaxf(gm[t], s[t][g]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < ATT_QPT; ++t) {
+        const float mn = fmaxf(m[t], gm[t]);
+        const float corr = exp2f(m[t] - mn);  // m = -inf on the first group -> 0
+        l[t] *= corr;
+        const float2 c2 = make_float2(corr, corr);
+#pragma unroll
+        for (int c = 0; c < H; ++c) o[t][c] = __fmul2_rn(o[t][c], c2);
+        m[t] = mn;
+      }
 #pragma unroll
       for (int g = 0; g < ATT_G; ++g) {
-        const float pw = exp2f(s[g] - mn);
-        l += pw;
+        float2 vv[H];
 #pragma unroll
         for (int c4 = 0; c4 < D; c4 += 4) {
-          const float4 vv = *reinterpret_cast<const float4*>(&vs[g0 + g][c4]);
-          o[c4] = fmaf(pw, vv.x, o[c4]);
-          o[c4 + 1] = fmaf(pw, vv.y, o[c4 + 1]);
-          o[c4 + 2] = fmaf(pw, vv.z, o[c4 + 2]);
-          o[c4 + 3] = fmaf(pw, vv.w, o[c4 + 3]);
+          const float4 v4 = *reinterpret_cast<const float4*>(&vs[g0 + g][c4]);
+          vv[c4 / 2] = make_float2(v4.x, v4.y);
+          vv[c4 / 2 + 1] = make_float2(v4.z, v4.w);
+        }
+#pragma unroll
+        for (int t = 0; t < ATT_QPT; ++t) {
+          const float pw = exp2f(s[t][g] - m[t]);
+          l[t] += pw;
+          const float2 p2 = make_float2(pw, pw);
+#pragma unroll
+          for (int c = 0; c < H; ++c) o[t][c] = __ffma2_rn(p2, vv[c], o[t][c]);
         }
       }
     }
   }
-  if (active) {
-    const float inv = 1.f / l;
-    float* ob = out + ((size_t)b * C + head * D) * Nq;
 #pragma unroll
-    for (int c = 0; c < D; ++c) ob[(size_t)c * Nq + n] = o[c] * inv;
+  for (int t = 0; t < ATT_QPT; ++t) {
+    if (active[t]) {
+      const float inv = 1.f / l[t];
+      float* ob = out + ((size_t)b * C + head * D) * Nq;
+#pragma unroll
+      for (int c = 0; c < H; ++c) {
+        ob[(size_t)(2 * c) * Nq + n[t]] = o[t][c].x * inv;
+        ob[(size_t)(2 * c + 1) * Nq + n[t]] = o[t][c].y * inv;
+      }
+    }
   }
 }
 
@@ -100,7 +138,7 @@ extern "C" int nvs_attention(const float* q, const float* kv, float* out, int32_
   if (C % heads != 0 || B > 65535) return NVS_ERR_ARG;
   const int d = C / heads;
   const float scale_log2e = (float)(1.0 / sqrt((double)d) * 1.4426950408889634);
-  dim3 grid((Nq + ATT_THREADS - 1) / ATT_THREADS, heads, B);
+  dim3 grid((Nq + ATT_QPB - 1) / ATT_QPB, heads, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d) {
     case 16: attention_kernel<16><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
