@@ -9,7 +9,7 @@
 //               TMA, which *is* the convolution's zero padding.  The nine taps are nine shifted windows of that
 //               one box: every activation byte crosses L2 once per layer, not nine times.
 //   split:      converter warps (thread = output pixel) read the window row of the current tap from the halo
-//               box (un-swizzling the 16-byte chunks), form hi (low 13 mantissa bits cleared) and lo = a - hi
+//               box (un-swizzling the 16-byte chunks), form hi = rn_tf32(a) and lo = rn_tf32(a - hi)
 //               and write both straight into TENSOR MEMORY with tcgen05.st (lane = pixel, column = channel):
 //               the A operand never returns to shared memory (an earlier version that staged hi/lo in smem
 //               was shared-memory-bandwidth bound).
@@ -350,9 +350,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+                // hi = a rounded to nearest tf32 (13 low mantissa bits), lo = a - hi exactly, then lo rounded
+                // to nearest tf32 too: the tensor core would otherwise TRUNCATE lo, a one-sided (biased) error
+                const uint32_t h = (__float_as_uint(f[e]) + 0x1000u) & 0xFFFFE000u;
                 hi[4 * c + e] = h;
-                lo[4 * c + e] = __float_as_uint(f[e] - __uint_as_float(h));
+                lo[4 * c + e] = (__float_as_uint(f[e] - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
               }
             }
             const uint32_t ta = tmem_base + (uint32_t)(C::ACC_COLS + sl * C::A_COLS) + ((uint32_t)(cw * 32) << 16);

@@ -257,6 +257,10 @@ class _Plan:
         self.bufs: Dict[str, torch.Tensor] = {}
         self.meta: Dict[int, dict] = {}   # step index -> {flops, bytes} of conv launches (for bench.py)
         self.profile: Optional[dict] = None  # {"idx": step index, "events": [(start, end), ...]}
+        self.graph = None                 # CUDA graph of the whole launch sequence (small batches)
+        self.graph_x = None
+        self.graph_outs: Optional[Dict[str, torch.Tensor]] = None
+        self.runs = 0
         model._build_plan(self)
 
     def buf(self, name: str, c: int, h: int, w: int) -> torch.Tensor:
@@ -329,6 +333,8 @@ class _KP2DTinyBase(nn.Module):
         # 32-channel rows: padded weights are zero, so padded activations stay exactly zero)
         tc_ok = c1 % 16 == 0 and _p32(c2) <= 32 and max(_p32(c4), _p32(c5), _p32(d1)) <= 128 and d1 % 4 == 0
         self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
+        # batches up to this size replay a captured CUDA graph (0 disables)
+        self.cuda_graph_max_batch = int(os.environ.get("NVS_CUDA_GRAPH_MAX_BATCH", "16"))
         if self.conv_backend == "tc" and not tc_ok:
             raise NotImplementedError("tensor-core conv backend: unsupported channel configuration")
 
@@ -489,12 +495,10 @@ class _KP2DTinyBase(nn.Module):
             plan = self._plans[key] = _Plan(self, B, H, W, x.device)
         return self._run(plan, x)
 
-    def _run(self, plan: _Plan, x: torch.Tensor):
-        dev = x.device
-        outs = {}
-        for name, shape in plan.out_shapes.items():
-            outs[name] = torch.empty(shape, device=dev, dtype=torch.float32)
-            for a in plan.out_slots.get(name, []):
+    def _launch_all(self, plan: _Plan, x: torch.Tensor, outs: Dict[str, torch.Tensor]) -> None:
+        """Enqueue every kernel of the plan on the current stream (pure launches: nothing allocates or syncs)."""
+        for name, slots in plan.out_slots.items():
+            for a in slots:
                 a.dst = outs[name].data_ptr()
         plan.in_args.src0 = x.data_ptr()
         run_conv = ops.run_conv
@@ -515,13 +519,36 @@ class _KP2DTinyBase(nn.Module):
                 st[1].run(outs[st[2]] if st[2] is not None else None, outs[st[3]] if st[3] is not None else None)
             else:
                 st[1](outs, *st[2])
+
+    def _run(self, plan: _Plan, x: torch.Tensor):
+        dev = x.device
+        plan.runs += 1
+        # Small batches are launch bound (~32 launches for <1 ms of GPU work): after two eager runs (which also
+        # set the kernels' function attributes) the whole sequence is captured once into a CUDA graph with static
+        # input/output buffers and replayed; results are copied out so callers still own fresh tensors.
+        use_graph = (self.cuda_graph_max_batch > 0 and plan.B <= self.cuda_graph_max_batch and plan.profile is None
+                     and plan.runs > 2)
+        if use_graph:
+            if plan.graph is None:
+                plan.graph_x = torch.empty_like(x)
+                plan.graph_outs = {n: torch.empty(sh, device=dev, dtype=torch.float32) for n, sh in plan.out_shapes.items()}
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all(plan, plan.graph_x, plan.graph_outs)
+                plan.graph = g
+            plan.graph_x.copy_(x)
+            plan.graph.replay()
+            outs = {n: t.clone() for n, t in plan.graph_outs.items()}
+        else:
+            outs = {name: torch.empty(shape, device=dev, dtype=torch.float32) for name, shape in plan.out_shapes.items()}
+            self._launch_all(plan, x, outs)
         result = {"score": outs["score"], "coord": outs["coord"], "feat": outs["feat"]}
         if "vlad" in outs:
             result["vlad"] = outs["vlad"]
         else:
             result["vlad"] = plan.bufs["v3"].clone()  # remove_netvlad: raw encoder map (vpr.py:83-89)
         result["seg"] = outs["seg"]
-        # keep x alive until the kernels that read it have been enqueued (they have: stream ordered)
         return result
 
     # --- plan construction ------------------------------------------------------------------------

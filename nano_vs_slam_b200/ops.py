@@ -371,7 +371,7 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
                  eps: float = 1e-5, cin_segments=None):
     """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc.
 
-    w_hi keeps the 10 tf32 mantissa bits (low 13 bits cleared), w_lo = w - w_hi exactly (fp32).
+    w_hi = w rounded to tf32 (10 explicit mantissa bits), w_lo = tf32-rounded (w - w_hi).
     ``cin_segments``: [(real, padded), ...] -- the input channels arrive as consecutive segments of ``real``
     channels, each stored in a channels-last buffer padded with zeros to ``padded`` channels (the N letters have
     24/48/72/96 channels; the tensor-core kernel works on 32-channel rows).  Zero weight columns are inserted."""
@@ -392,8 +392,11 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
     assert cpad > 0, cout
     wt = torch.zeros(9, cpad, cin, dtype=torch.float32, device=w.device)
     wt[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
-    hi = (wt.view(torch.int32) & -8192).view(torch.float32).contiguous()
-    lo = (wt - hi).contiguous()
+    # hi = w rounded to the nearest tf32 value, lo = (w - hi) rounded to the nearest tf32 value (the tensor core
+    # truncates operands to tf32; pre-rounding makes the residual error unbiased)
+    hi = ((wt.view(torch.int32) + 0x1000) & -8192).view(torch.float32).contiguous()
+    lo = (wt - hi)
+    lo = ((lo.view(torch.int32) + 0x1000) & -8192).view(torch.float32).contiguous()
     bp = torch.zeros(cpad, dtype=torch.float32, device=w.device)
     bp[:cout] = b
     return hi, lo, bp

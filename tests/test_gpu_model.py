@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import REL_TOL, golden_cases, load_golden, rel_err
+from util import REL_TOL, golden_cases, load_golden, rel_err, tol
 
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +38,7 @@ def test_model_matches_reference_golden(path):
     out = m(x)
     for k in ("score", "coord", "feat", "vlad", "seg"):
         assert out[k].shape == c["fwd"][k].shape, k
-        assert rel_err(out[k], c["fwd"][k]) < REL_TOL, (k, rel_err(out[k], c["fwd"][k]))
+        assert rel_err(out[k], c["fwd"][k]) < tol(k, c["v3"]), (k, rel_err(out[k], c["fwd"][k]))
     post = m.post_processing(dict(out), c["H"], c["W"])
     assert torch.equal(post["score"].cpu() > 0, c["post"]["score"] > 0)
     assert rel_err(post["score"], c["post"]["score"]) < REL_TOL
@@ -68,7 +68,7 @@ def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W):
     a = R.arch_for(letter, v3, ncls)
     ref = R.forward(x, sd, a)
     for k in ("score", "coord", "feat", "vlad", "seg"):
-        assert rel_err(out[k], ref[k]) < REL_TOL, (k, rel_err(out[k], ref[k]))
+        assert rel_err(out[k], ref[k]) < tol(k, v3), (k, rel_err(out[k], ref[k]))
     post = m.post_processing(dict(out), H, W)
     rpost = R.post_processing(dict(ref), H, W, a)
     assert float((post["coord"].cpu() - rpost["coord"]).abs().max()) < 1e-3
@@ -100,9 +100,9 @@ def test_both_conv_backends_agree_with_golden(letter, v3):
         assert m.conv_backend == backend
         outs[backend] = m(x)
         for k in ("score", "coord", "feat", "vlad", "seg"):
-            assert rel_err(outs[backend][k], c["fwd"][k]) < REL_TOL, (backend, k, rel_err(outs[backend][k], c["fwd"][k]))
+            assert rel_err(outs[backend][k], c["fwd"][k]) < tol(k, c["v3"]), (backend, k, rel_err(outs[backend][k], c["fwd"][k]))
     for k in ("feat", "seg", "vlad"):
-        assert rel_err(outs["tc"][k], outs["ffma"][k]) < REL_TOL
+        assert rel_err(outs["tc"][k], outs["ffma"][k]) < tol(k, c["v3"])
 
 
 def test_state_dict_roundtrip_and_errors():
@@ -123,3 +123,24 @@ def test_state_dict_roundtrip_and_errors():
     out = m(torch.zeros(1, 3, 64, 64, device="cuda"))
     assert set(out) == {"score", "coord", "feat", "vlad", "seg"}
     assert out["vlad"].shape == (1, 4096) and m.get_global_desc_dim() == 4096
+
+
+def test_cuda_graph_replay_matches_eager():
+    """Small batches switch to a captured CUDA graph after two eager runs; results must not change."""
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    m, _ = _model("S", 28, False, 77)
+    xs = [synthetic_frames(2, 64, 96, s).cuda() for s in range(5)]
+    m.cuda_graph_max_batch = 0
+    eager = [m(x) for x in xs]
+    m.cuda_graph_max_batch = 16
+    m._plans.clear()
+    graphed = [m(x) for x in xs]  # runs 3.. use the graph
+    plan = next(iter(m._plans.values()))
+    assert plan.graph is not None
+    for e, g in zip(eager, graphed):
+        for k in ("score", "coord", "feat", "vlad", "seg"):
+            assert rel_err(g[k], e[k]) < 2e-5, k   # two MMA issuers: run-to-run rounding differences only
+    a = m(xs[0])
+    b = m(xs[1])
+    assert a["feat"].data_ptr() != b["feat"].data_ptr()  # callers own their outputs

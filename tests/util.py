@@ -9,6 +9,14 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 REL_TOL = 1e-4  # fp32 features / descriptors / VLAD: 1e-4 relative (north_star)
 
 
+def tol(key: str, v3: bool) -> float:
+    """Tolerance per forward output.  north_star gates features / descriptors / VLAD at 1e-4 relative and the
+    segmentation on its ARGMAX (>= 99.9 % identical).  V3 returns Softmax2d probabilities under 'seg'
+    (kp2dtiny.py:942-943): p(1-p) * d(logit) with |logit| ~ 20 amplifies the logit error, so that one tensor is
+    held to 2e-4 (measured worst case over 20 runs on the tensor-core backend: 9.2e-5)."""
+    return 2e-4 if (key == "seg" and v3) else REL_TOL
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """||a-b||_inf / ||b||_inf."""
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
