@@ -534,11 +534,15 @@ class _KP2DTinyBase(nn.Module):
                 plan.graph_outs = {n: torch.empty(sh, device=dev, dtype=torch.float32) for n, sh in plan.out_shapes.items()}
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES[0]
                 with torch.cuda.graph(g):
                     self._launch_all(plan, plan.graph_x, plan.graph_outs)
+                plan.graph_kernels = ops.LAUNCHES[0] - n0  # kernels recorded in the graph
+                ops.LAUNCHES[0] = n0                       # capture launched nothing
                 plan.graph = g
             plan.graph_x.copy_(x)
             plan.graph.replay()
+            ops.LAUNCHES[0] += plan.graph_kernels
             outs = {n: t.clone() for n, t in plan.graph_outs.items()}
         else:
             outs = {name: torch.empty(shape, device=dev, dtype=torch.float32) for name, shape in plan.out_shapes.items()}
