@@ -1,4 +1,4 @@
-"""Per-step timeline of the MMA-issuing thread of CTA 0 of conv_tc_kernel (debug build, -DNVS_TC_DEBUG)."""
+"""Per-step timeline of CTA 0 of conv_tc_kernel (debug build, -DNVS_TC_DEBUG): MMA issuers + one converter warp."""
 import ctypes as C, sys, torch, numpy as np
 sys.path.insert(0, "/root/repo")
 from nano_vs_slam_b200 import _cabi
@@ -17,9 +17,13 @@ op = ops.TcConv(x, ops.pack_conv_tc(w, bias=b), cout, act=1, dst=out)
 for _ in range(3):
     dbg.zero_(); op.run()
 torch.cuda.synchronize()
-m = dbg.cpu().numpy()[:2048].reshape(512, 4)
-print("step: issue6(first MMAs) | poll next barriers | issue2+commit | period")
+d = dbg.cpu().numpy()
+m = d[:2048].reshape(512, 4); c = d[2048:4096].reshape(512, 4)
+print("issuers (even steps: issuer 0, odd: issuer 1): step, wait sfull, issue 8 MMAs, commit, gap to own next step")
 for i in range(36, 76):
-    print(f"{i:4d}  first {m[i,1]-m[i,0]:6d}  poll {m[i,2]-m[i,1]:6d}  rest {m[i,3]-m[i,2]:5d}   period {m[i,0]-m[i-1,0]:6d}")
-per = np.diff(m[18:324, 0])
-print("mean step period", per.mean(), "median", np.median(per), "total", m[323, 3] - m[0, 0])
+    print(f"{i:4d} i{i%2}  wait {m[i,1]-m[i,0]:6d}  issue {m[i,2]-m[i,1]:6d}  commit {m[i,3]-m[i,2]:5d}   start-to-start(global) {m[i,0]-m[i-1,0]:6d}  own period {m[i,0]-m[i-2,0]:6d}")
+per = np.diff(m[18:324, 0]); print("mean global step period", per.mean(), "median", np.median(per), "total", m[323, 3] - m[0, 0])
+print("converter warp 4 (group 0): step, wait hfull, wait sempty, work")
+idx = [i for i in range(512) if c[i, 0] != 0][18:40]
+for i in idx:
+    print(f"{i:4d}  hfull {c[i,1]-c[i,0]:6d}  sempty {c[i,2]-c[i,1]:6d}  work {c[i,3]-c[i,2]:6d}")
