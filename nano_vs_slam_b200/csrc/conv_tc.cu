@@ -30,6 +30,7 @@
 // (producer <-> converters), weight tiles (producer <-> MMA), TMEM A slots (converters <-> MMA), accumulators
 // (MMA <-> epilogue).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -39,11 +40,14 @@ namespace tc {
 constexpr int TM = 128;            // pixels per tile
 constexpr int TX = 16, TY = 8;     // tile shape
 constexpr int HX = TX + 2, HY = TY + 2;   // halo box
-constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each)
+constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each); group g takes the steps with index % CONV_GROUPS == g
 constexpr int WARP_HALO = 4 + 4 * CONV_GROUPS;
 constexpr int WARP_W = WARP_HALO + 1;
-constexpr int WARP_MMA = WARP_W + 1;      // first of TWO MMA-issuing warps (they take pipeline steps alternately)
-constexpr int THREADS = 32 * (WARP_MMA + 2);
+constexpr int MAX_ISSUERS = 4;
+constexpr int ACC_STAGES = 2;      // accumulator stages in TMEM: the epilogue of a tile overlaps the next tile's MMAs
+                                   // (1 stage frees columns for 6 slots instead of 4: measured no faster)
+constexpr int WARP_MMA = WARP_W + 1;      // first of MAX_ISSUERS MMA-issuing warps (they take pipeline steps round-robin)
+constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
 
 template <int COUT, int KC>
 struct Cfg {
@@ -53,13 +57,18 @@ struct Cfg {
   static constexpr int W_STAGE = 2 * W_BYTES;
   static constexpr bool CONCAT = COUT <= 64;
   static constexpr int ACC_STAGE_COLS = CONCAT ? 2 * COUT : COUT;
-  static constexpr int ACC_COLS = 2 * ACC_STAGE_COLS;                      // double-buffered accumulator
+  static constexpr int ACC_COLS = ACC_STAGES * ACC_STAGE_COLS;
   static constexpr int A_COLS = 2 * KC;                                    // TMEM slot: KC columns hi + KC columns lo
   // One ring of NS "slots": slot s = weight stage s in shared memory + A slot s in tensor memory, guarded by ONE
   // full barrier (4 converter warps + the weight TMA) and ONE empty barrier (tcgen05.commit).  The MMA-issuing
   // thread is the critical resource (it stalls while the tensor pipe is busy and the pipe drains while it polls
   // barriers), so it must do exactly one wait and one commit per pipeline step.
-  static constexpr int NS = (512 - ACC_COLS) / A_COLS > 8 ? 8 : (512 - ACC_COLS) / A_COLS;
+  // NS is a multiple of MAX_ISSUERS: slot s is then always consumed by issuer s % issuers, which keeps every
+  // parity wait at most one phase behind (with 3 issuers on 4 slots an issuer lapped a slow converter warp).
+  static constexpr int NS_TMEM = (512 - ACC_COLS) / A_COLS;
+  static constexpr int NS_SMEM = (227 * 1024 - 4096 - 3 * HALO_BYTES) / W_STAGE;
+  static constexpr int NS_FIT = NS_TMEM < NS_SMEM ? NS_TMEM : NS_SMEM;
+  static constexpr int NS = NS_FIT >= 8 ? 8 : (NS_FIT >= 6 ? 6 : 4);
   static constexpr int NH = 3;                                             // halo boxes in flight
   static constexpr int KSTEPS = KC / 8;                                    // MMAs (K = 8 tf32) per operand pair
   static constexpr int SM_W = NH * HALO_BYTES;
@@ -67,7 +76,7 @@ struct Cfg {
   static constexpr int SM_BAR = SM_BIAS + COUT * 4;
   static constexpr int N_BARS = 2 * NH + 2 * NS + 6;
   static constexpr int SMEM_BYTES = SM_BAR + 8 * N_BARS + 16 + 1024;
-  static_assert(NS >= 2, "TMEM budget");
+  static_assert(NS <= NS_FIT && NS % CONV_GROUPS == 0, "TMEM budget / converter ring");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
   static_assert(W_BYTES % 1024 == 0 || (KC == 16 && W_BYTES % 512 == 0), "[W_hi;W_lo] must keep the swizzle phase");
   static constexpr uint32_t idesc_n(int n) {
@@ -88,7 +97,13 @@ struct Params {
   int tiles_x, tiles_y, n_tiles;
   int issuers;     // 2 (default) or 1: a single MMA issuer gives a fixed fp32 accumulation order (bit-reproducible)
   long long* dbg;  // optional timeline dump of CTA 0 (NVS_TC_DEBUG builds only)
+  int knock;       // NVS_TC_DEBUG builds: stage knock-out bits for bottleneck experiments (results are then garbage)
 };
+#ifdef NVS_TC_DEBUG
+#define NVS_KNOCK(bit) ((p.knock & (bit)) != 0)
+#else
+#define NVS_KNOCK(bit) false
+#endif
 
 // ------------------------------------------------------------------ PTX wrappers (see retrieval.cu)
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -111,6 +126,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef NVS_TC_DEBUG
+__device__ long long* g_timeout_log = nullptr;  // [0] = count, then 4 words per record
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int line) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 40000000LL) {  // ~20 ms: record who is stuck where and carry on (results are garbage)
+      if (g_timeout_log) {
+        const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(g_timeout_log), 1ull);
+        if (i < 200) {
+          long long* r = g_timeout_log + 1 + 4 * i;
+          r[0] = t0; r[1] = ((long long)blockIdx.x << 32) | threadIdx.x; r[2] = ((long long)bar << 8) | parity; r[3] = line;
+        }
+      }
+      return;
+    }
+  }
+}
+#define mbar_wait(b, ph) mbar_wait_((b), (ph), __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -118,6 +153,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 8000000000LL) __trap();  // never hang the box on a protocol bug
   }
 }
+#endif
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(
@@ -175,10 +211,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-template <int KC>
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+template <int N>
 __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r) {
-  if (KC == 32) tmem_st32(taddr, r);
-  else tmem_st16(taddr, r);
+  static_assert(N == 8 || N == 16 || N == 32, "columns per store");
+  if (N == 32) tmem_st32(taddr, r);
+  else if (N == 16) tmem_st16(taddr, r);
+  else tmem_st8(taddr, r);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -286,12 +330,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(hempty(hb), ph ^ 1);
+          if (NVS_KNOCK(64)) {
+            mbar_arrive(hfull(hb));
+          } else {
           mbar_expect_tx(hfull(hb), HX * HY * C::ROW_BYTES);
           if (ch < p.c0_chunks)
             tma_load_4d(base + hb * C::HALO_BYTES, &map_a0, hfull(hb), p.c0_off + ch * KC, tx * TX - 1, ty * TY - 1, b);
           else
             tma_load_4d(base + hb * C::HALO_BYTES, &map_a1, hfull(hb), p.c1_off + (ch - p.c0_chunks) * KC,
                         tx * TX - 1, ty * TY - 1, b);
+          }
           if (++hb == NH) {
             hb = 0;
             ph ^= 1;
@@ -309,9 +357,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(sempty(sl), ph ^ 1);
             const uint32_t dst = base + C::SM_W + sl * C::W_STAGE;
+            if (NVS_KNOCK(32)) {
+              mbar_arrive(sfull(sl));
+            } else {
             mbar_expect_tx(sfull(sl), C::W_STAGE);
             tma_load_3d(dst, &map_whi, sfull(sl), ch * KC, 0, tap);
             tma_load_3d(dst + C::W_BYTES, &map_wlo, sfull(sl), ch * KC, 0, tap);
+            }
             if (++sl == NS) {
               sl = 0;
               ph ^= 1;
@@ -328,15 +380,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int ly = r >> 4, lx = r & 15;
     int hb = 0, sl = 0, turn = 0;
     uint32_t hph = 0, sph = 0;
+    // Splitting the channels of every step over both groups instead (half the latency per step, same work) was
+    // measured slower: the two barrier waits, the tcgen05.wait::st and the fences are per warp and step.
     for (int t = 0; t < my_tiles; ++t) {
       for (int ch = 0; ch < chunks; ++ch) {
         for (int tap = 0; tap < 9; ++tap) {
           const bool mine = turn == grp;
           if (++turn == CONV_GROUPS) turn = 0;
           if (mine) {
-            mbar_wait(hfull(hb), hph);
-            mbar_wait(sempty(sl), sph ^ 1);
-            tc_fence_after();
+#ifdef NVS_TC_DEBUG
+            const long long k0 = clock64();
+#endif
+            if (tap < CONV_GROUPS) mbar_wait(hfull(hb), hph);  // first tap of this chunk for my group
+#ifdef NVS_TC_DEBUG
+            const long long k1 = clock64();
+#endif
             const int ky = tap / 3, kx = tap - ky * 3;
             const int rh = (ly + ky) * HX + lx + kx;  // row of the halo box
             const uint8_t* rowp = sm + hb * C::HALO_BYTES + rh * C::ROW_BYTES;
@@ -344,29 +402,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             // Consecutive pixels of a quarter-warp read consecutive rows -> distinct keys -> conflict-free LDS.128.
             const int key = KC == 32 ? (rh & 7) : ((rh >> 1) & 3);
             uint32_t hi[KC], lo[KC];
+            if (!NVS_KNOCK(2)) {
 #pragma unroll
-            for (int c = 0; c < KC / 4; ++c) {
-              const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ key) << 4));
-              const float f[4] = {v.x, v.y, v.z, v.w};
+              for (int c = 0; c < KC / 4; ++c) {
+                const float4 v = NVS_KNOCK(16) ? make_float4(1.f * tap, 2.f, 3.f * lane, 4.f)
+                                               : *reinterpret_cast<const float4*>(rowp + ((c ^ key) << 4));
+                const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // hi = a rounded to nearest tf32 (13 low mantissa bits), lo = a - hi exactly, then lo rounded
-                // to nearest tf32 too: the tensor core would otherwise TRUNCATE lo, a one-sided (biased) error
-                const uint32_t h = (__float_as_uint(f[e]) + 0x1000u) & 0xFFFFE000u;
-                hi[4 * c + e] = h;
-                lo[4 * c + e] = (__float_as_uint(f[e] - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
+                for (int e = 0; e < 4; ++e) {
+                  // hi = a rounded to nearest tf32 (13 low mantissa bits), lo = a - hi exactly, then lo rounded
+                  // to nearest tf32 too: the tensor core would otherwise TRUNCATE lo, a one-sided (biased) error
+                  const uint32_t h = (__float_as_uint(f[e]) + 0x1000u) & 0xFFFFE000u;
+                  hi[4 * c + e] = h;
+                  lo[4 * c + e] = __float_as_uint(f[e] - __uint_as_float(h)) + 0x1000u;  // low 13 bits: dropped by the MMA
+                }
               }
             }
-            const uint32_t ta = tmem_base + (uint32_t)(C::ACC_COLS + sl * C::A_COLS) + ((uint32_t)(cw * 32) << 16);
-            tmem_st<KC>(ta, hi);
-            tmem_st<KC>(ta + KC, lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            // the loads and the split do not need the slot: only now wait for the MMAs that last read it
+            mbar_wait(sempty(sl), sph ^ 1);
+            tc_fence_after();
+#ifdef NVS_TC_DEBUG
+            const long long k2 = clock64();
+#endif
+            if (!NVS_KNOCK(2)) {
+              const uint32_t ta = tmem_base + (uint32_t)(C::ACC_COLS + sl * C::A_COLS) + ((uint32_t)(cw * 32) << 16);
+              if (!NVS_KNOCK(8)) {
+                tmem_st<KC>(ta, hi);
+                tmem_st<KC>(ta + KC, lo);
+              } else {
+                uint32_t acc_x = 0;
+#pragma unroll
+                for (int c = 0; c < KC; ++c) acc_x ^= hi[c] + lo[c];
+                if (acc_x == 0x12345678u) p.dbg[4095] = 1;
+              }
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(sfull(sl));   // this warp's 32 TMEM lanes of the slot are written
               mbar_arrive(hempty(hb));  // ... and its reads of the halo box for this tap are done
             }
+#ifdef NVS_TC_DEBUG
+            {
+              const int gs = (t * chunks + ch) * 9 + tap;
+              if (p.dbg && blockIdx.x == 0 && warp == 4 + 4 * grp && lane == 0 && gs < 480) {
+                long long* d = p.dbg + 2048 + gs * 4;
+                d[0] = k0; d[1] = k1; d[2] = k2; d[3] = clock64();
+              }
+            }
+#endif
           }
           if (++sl == NS) {
             sl = 0;
@@ -380,15 +465,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else if (warp >= WARP_MMA) {
-    // =========================== MMA issuers (two threads) ===========================
-    // A tcgen05.mma instruction blocks its issuing thread while the tensor pipe's short queue is full, and the
-    // pipe drains whenever that thread polls an mbarrier or commits (NVS_TC_DEBUG timeline: ~450 of every ~900
-    // cycles per step were not spent issuing).  Two issuers take the pipeline steps alternately (even / odd
-    // global step index): while one polls and commits, the other's MMAs keep the pipe busy.  Accumulation
-    // order inside a tile is irrelevant except for the very first (overwriting) MMA, which is ordered by the
-    // astart barrier; each issuer commits the slots it consumed, and both commit the tile's accumulator
-    // (afull count 2).
-    const int me = warp - WARP_MMA;  // 0 or 1
+    // =========================== MMA issuers (p.issuers threads) ===========================
+    // A tcgen05.mma instruction blocks its issuing thread while the tensor pipe's short queue (2-3 MMAs) is
+    // full, one thread cannot queue MMAs faster than ~80 cycles apiece (the pipe retires an N=64 MMA in 32), and
+    // every pipeline step costs its issuer ~400 cycles of mbarrier polling, tcgen05.commit and loop overhead
+    // during which the pipe drains (NVS_TC_DEBUG timeline, tools/tc_timeline.py).  Several issuers therefore
+    // take the pipeline steps round-robin (global step index mod p.issuers): their MMAs interleave in the
+    // pipe at its full rate and their overheads overlap.  Accumulation order inside a tile is irrelevant
+    // except for the very first (overwriting) MMA, which is ordered by the astart barrier; each issuer commits
+    // the slots it consumed, and all of them commit the tile's accumulator (afull count p.issuers).
+    const int me = warp - WARP_MMA;
     if (lane == 0 && my_tiles > 0 && me < p.issuers) {
       const int nis = p.issuers;
       const int steps = 9 * chunks;
@@ -402,20 +488,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       int last_tile_synced = -1;
       for (int g = me; g < total; g += nis) {
-        const int acc = tile & 1;
-        const uint32_t aph = (uint32_t)(tile >> 1) & 1u;
+        const int acc = tile % ACC_STAGES;
+        const uint32_t aph = (uint32_t)(tile / ACC_STAGES) & 1u;
         const int sl = g % NS;
         const uint32_t sph = (uint32_t)(g / NS) & 1u;
         if (last_tile_synced != tile) {  // my first step in this tile
           mbar_wait(aempty(acc), aph ^ 1);
-          if (ks != 0) mbar_wait(astart(acc), aph);  // the other issuer queued the tile's first MMA
+          if (ks != 0) mbar_wait(astart(acc), aph);  // another issuer queued the tile's first MMA
           last_tile_synced = tile;
         }
+#ifdef NVS_TC_DEBUG
+        const long long c0 = clock64();
+#endif
         mbar_wait(sfull(sl), sph);
         tc_fence_after();
+#ifdef NVS_TC_DEBUG
+        const long long c1 = clock64();
+#endif
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS);
         const uint32_t a_hi = a0 + (uint32_t)(sl * C::A_COLS), a_lo = a_hi + KC;
         const uint64_t w_hi = wdesc0 + (uint64_t)((sl * C::W_STAGE) >> 4), w_lo = w_hi + (uint64_t)(C::W_BYTES >> 4);
+        if (NVS_KNOCK(1)) {
+          if (ks == 0) mbar_arrive(astart(acc));
+        } else
 #pragma unroll
         for (int k = 0; k < C::KSTEPS; ++k) {
           // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
@@ -431,8 +526,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_lo + o, C::IDESC, 1u);
           }
         }
+#ifdef NVS_TC_DEBUG
+        const long long c2 = clock64();
+#endif
         tc_commit(sempty(sl));  // weight stage + TMEM A slot are free once these MMAs retire
         if (ks >= steps - nis) tc_commit(afull(acc));  // my last step of this tile
+#ifdef NVS_TC_DEBUG
+        if (p.dbg && blockIdx.x == 0 && g < 512) {
+          long long* d = p.dbg + g * 4;
+          d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64();
+        }
+#endif
         ks += nis;
         while (ks >= steps) {
           ks -= steps;
@@ -453,7 +557,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (int cc = 0; cc < COUT / 32; ++cc) {
+      for (int cc = 0; cc < (NVS_KNOCK(4) ? 0 : COUT / 32); ++cc) {
         float v[32];
         __syncwarp();
         tmem_ld32(taddr + (uint32_t)(cc * 32), v);
@@ -528,7 +632,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(aempty(acc));
-      if (++acc == 2) {
+      if (++acc == ACC_STAGES) {
         acc = 0;
         aph ^= 1;
       }
@@ -609,13 +713,16 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
     done = true;
   }
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  conv_tc_kernel<COUT, KC><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, p);
+  Params q = p;
+  while (C::NS % q.issuers != 0) --q.issuers;  // a slot must always be consumed by the same issuer
+  conv_tc_kernel<COUT, KC><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
 
 #ifdef NVS_TC_DEBUG
 static long long* g_dbg = nullptr;
+static int g_knock = 0;
 #endif
 
 static inline int pick_kc(int c0, int c1) {
@@ -675,8 +782,18 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.act = a->act;
   p.tiles_x = (a->W + tc::TX - 1) / tc::TX; p.tiles_y = (a->H + tc::TY - 1) / tc::TY;
   p.n_tiles = p.tiles_x * p.tiles_y * a->B;
-  p.issuers = (a->flags & 1) ? 1 : 2;
+  {
+    static int default_issuers = 0;
+    if (!default_issuers) {
+      const char* e = getenv("NVS_TC_ISSUERS");
+      default_issuers = e ? atoi(e) : 4;
+      // a slot must always be consumed by the same issuer (parity waits tolerate no lapping): issuers | ring size
+      if (default_issuers < 1 || default_issuers > tc::MAX_ISSUERS) default_issuers = tc::MAX_ISSUERS;
+    }
+    p.issuers = (a->flags & 1) ? 1 : default_issuers;
+  }
   p.dbg = nullptr;
+  p.knock = 0;
   pl->cout_tpl = cpad;
   pl->kc = kc;
   pl->magic = tc::PLAN_MAGIC;
@@ -693,6 +810,7 @@ extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float*
   if (p.dst_mode == 3 && (!p.dst || !p.dst_pool)) return NVS_ERR_ARG;
 #ifdef NVS_TC_DEBUG
   p.dbg = tc::g_dbg;
+  p.knock = tc::g_knock;
 #endif
   if (p.dst_mode != 0 && !p.dst) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -707,4 +825,8 @@ extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float*
 
 #ifdef NVS_TC_DEBUG
 extern "C" void nvs_conv_tc_set_debug(long long* dev_buf) { nvs::tc::g_dbg = dev_buf; }
+extern "C" void nvs_conv_tc_set_knock(int bits) { nvs::tc::g_knock = bits; }
+extern "C" void nvs_conv_tc_set_timeout_log(long long* dev_buf) {
+  cudaMemcpyToSymbol(nvs::tc::g_timeout_log, &dev_buf, sizeof(dev_buf));
+}
 #endif

@@ -509,8 +509,10 @@ class _KP2DTinyBase(nn.Module):
                 e0.record()
                 if st[0] == "conv":
                     run_conv(st[1])
-                else:
+                elif st[0] == "tc":
                     st[1].run(outs[st[2]] if st[2] is not None else None, outs[st[3]] if st[3] is not None else None)
+                else:
+                    st[1](outs, *st[2])
                 e1.record()
                 prof["events"].append((e0, e1))
             elif st[0] == "conv":
