@@ -115,7 +115,10 @@ typedef struct NvsConvTcArgs {
   int32_t dst_c_total, dst_c_off, dst_layout, dst_mode;
   int32_t pool_c_total, pool_c_off;
   int32_t B, H, W, cout, act;
-  int32_t flags; /* bit 0: single MMA issuer = fixed fp32 accumulation order (bit-reproducible, ~15 % slower) */
+  int32_t flags; /* bit 0: single MMA issuer = fixed fp32 accumulation order (bit-reproducible, slower);
+                    bit 1: c0 == 16, c1 == 0, cout <= 32 only -- w_hi / w_lo are given in the paired-tap layout
+                    [5][cout_pad][32], K row of step t = [tap 2t ch 0-15 | tap 2t+1 ch 0-15], tenth tap zero:
+                    a tile then takes 5 pipeline steps instead of 9 */
 } NvsConvTcArgs;
 int32_t nvs_conv_tc_cout_pad(int32_t cout);
 int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout);

@@ -49,10 +49,17 @@ constexpr int ACC_STAGES = 2;      // accumulator stages in TMEM: the epilogue o
 constexpr int WARP_MMA = WARP_W + 1;      // first of MAX_ISSUERS MMA-issuing warps (they take pipeline steps round-robin)
 constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
 
-template <int COUT, int KC>
+// PAIR: 16-channel inputs (the stem's second conv).  One pipeline step then carries TWO taps: the K = 32 operand
+// row is [tap 2t channels 0-15 | tap 2t+1 channels 0-15] (weights packed that way by the host, zero for the
+// missing tenth tap), so a tile takes 5 steps instead of 9 -- the per-step cost is fixed overhead, not MMA time.
+template <int COUT, int KC, bool PAIR = false>
 struct Cfg {
-  static constexpr int ROW_BYTES = KC * 4;                                 // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
-  static constexpr int HALO_BYTES = ((HX * HY * ROW_BYTES + 1023) / 1024) * 1024;
+  static constexpr int HC = PAIR ? 16 : KC;                                // channels per halo-box row
+  static constexpr int TAPS = PAIR ? 5 : 9;                                // pipeline steps per (tile, chunk)
+  static constexpr int ROW_BYTES = KC * 4;                                 // weight / A row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr int HALO_ROW_BYTES = HC * 4;
+  static constexpr int HALO_BYTES = ((HX * HY * HALO_ROW_BYTES + 1023) / 1024) * 1024;
+  static_assert(!PAIR || KC == 32, "paired taps fill a 32-wide K row");
   static constexpr int W_BYTES = COUT * ROW_BYTES;                         // one of W_hi / W_lo
   static constexpr int W_STAGE = 2 * W_BYTES;
   static constexpr bool CONCAT = COUT <= 64;
@@ -264,12 +271,12 @@ __device__ __forceinline__ uint64_t make_wdesc(uint32_t smem_addr) {
   return d;
 }
 
-template <int COUT, int KC>
+template <int COUT, int KC, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const Params p) {
-  using C = Cfg<COUT, KC>;
+  using C = Cfg<COUT, KC, PAIR>;
   constexpr int NH = C::NH, NS = C::NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -294,7 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
     for (int i = 0; i < NH; ++i) {
       mbar_init(hfull(i), 1);
-      mbar_init(hempty(i), 9 * 4);  // one elected lane per converter warp per tap releases the box
+      mbar_init(hempty(i), C::TAPS * 4);  // one elected lane per converter warp per tap releases the box
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(sfull(i), 4 + 1);   // 4 converter warps (A slot written) + the weight producer's expect_tx arrive
@@ -333,11 +340,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (NVS_KNOCK(64)) {
             mbar_arrive(hfull(hb));
           } else {
-          mbar_expect_tx(hfull(hb), HX * HY * C::ROW_BYTES);
+          mbar_expect_tx(hfull(hb), HX * HY * C::HALO_ROW_BYTES);
           if (ch < p.c0_chunks)
-            tma_load_4d(base + hb * C::HALO_BYTES, &map_a0, hfull(hb), p.c0_off + ch * KC, tx * TX - 1, ty * TY - 1, b);
+            tma_load_4d(base + hb * C::HALO_BYTES, &map_a0, hfull(hb), p.c0_off + ch * C::HC, tx * TX - 1, ty * TY - 1, b);
           else
-            tma_load_4d(base + hb * C::HALO_BYTES, &map_a1, hfull(hb), p.c1_off + (ch - p.c0_chunks) * KC,
+            tma_load_4d(base + hb * C::HALO_BYTES, &map_a1, hfull(hb), p.c1_off + (ch - p.c0_chunks) * C::HC,
                         tx * TX - 1, ty * TY - 1, b);
           }
           if (++hb == NH) {
@@ -354,7 +361,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       uint32_t ph = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int ch = 0; ch < chunks; ++ch) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < C::TAPS; ++tap) {
             mbar_wait(sempty(sl), ph ^ 1);
             const uint32_t dst = base + C::SM_W + sl * C::W_STAGE;
             if (NVS_KNOCK(32)) {
@@ -384,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // measured slower: the two barrier waits, the tcgen05.wait::st and the fences are per warp and step.
     for (int t = 0; t < my_tiles; ++t) {
       for (int ch = 0; ch < chunks; ++ch) {
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < C::TAPS; ++tap) {
           const bool mine = turn == grp;
           if (++turn == CONV_GROUPS) turn = 0;
           if (mine) {
@@ -395,18 +402,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #ifdef NVS_TC_DEBUG
             const long long k1 = clock64();
 #endif
-            const int ky = tap / 3, kx = tap - ky * 3;
-            const int rh = (ly + ky) * HX + lx + kx;  // row of the halo box
-            const uint8_t* rowp = sm + hb * C::HALO_BYTES + rh * C::ROW_BYTES;
-            // 16-byte chunk c of row rh sits at chunk (c ^ key): SWIZZLE_128B key = rh & 7, SWIZZLE_64B key = (rh >> 1) & 3.
-            // Consecutive pixels of a quarter-warp read consecutive rows -> distinct keys -> conflict-free LDS.128.
-            const int key = KC == 32 ? (rh & 7) : ((rh >> 1) & 3);
+            // 16-byte chunk c of halo row rh sits at chunk (c ^ key): SWIZZLE_128B key = rh & 7, SWIZZLE_64B key =
+            // (rh >> 1) & 3.  Consecutive pixels of a quarter-warp read consecutive rows -> distinct keys ->
+            // conflict-free LDS.128.
+            const uint8_t* hbase = sm + hb * C::HALO_BYTES;
+            const int ky = PAIR ? 0 : tap / 3, kx = PAIR ? 0 : tap - ky * 3;
+            const int rh = (ly + ky) * HX + lx + kx;  // row of the halo box (single-tap steps)
+            const uint8_t* rowp = hbase + rh * C::HALO_ROW_BYTES;
+            const int key = C::HC == 32 ? (rh & 7) : ((rh >> 1) & 3);
             uint32_t hi[KC], lo[KC];
             if (!NVS_KNOCK(2)) {
 #pragma unroll
               for (int c = 0; c < KC / 4; ++c) {
-                const float4 v = NVS_KNOCK(16) ? make_float4(1.f * tap, 2.f, 3.f * lane, 4.f)
-                                               : *reinterpret_cast<const float4*>(rowp + ((c ^ key) << 4));
+                float4 v;
+                if (PAIR) {  // chunks 0-3: tap 2*tap, chunks 4-7: tap 2*tap + 1 (the tenth tap is all zero)
+                  const int t2 = 2 * tap + (c >> 2);
+                  const int ky2 = t2 / 3, kx2 = t2 - ky2 * 3;
+                  const int rh2 = (ly + ky2) * HX + lx + kx2;
+                  v = t2 < 9 ? *reinterpret_cast<const float4*>(hbase + rh2 * C::HALO_ROW_BYTES +
+                                                                (((c & 3) ^ ((rh2 >> 1) & 3)) << 4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                  v = NVS_KNOCK(16) ? make_float4(1.f * tap, 2.f, 3.f * lane, 4.f)
+                                    : *reinterpret_cast<const float4*>(rowp + ((c ^ key) << 4));
+                }
                 const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -477,7 +496,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int me = warp - WARP_MMA;
     if (lane == 0 && my_tiles > 0 && me < p.issuers) {
       const int nis = p.issuers;
-      const int steps = 9 * chunks;
+      const int steps = C::TAPS * chunks;
       const int total = my_tiles * steps;
       const uint64_t wdesc0 = make_wdesc<KC>(base + C::SM_W);
       const uint32_t a0 = tmem_base + (uint32_t)C::ACC_COLS;
@@ -666,7 +685,7 @@ static EncodeTiledFn get_encode() {
 struct alignas(64) Plan {
   CUtensorMap a0, a1, whi, wlo;
   Params p;
-  int cout_tpl, kc;
+  int cout_tpl, kc, pair;
   int magic;
 };
 constexpr int PLAN_MAGIC = 0x7C0DE6;
@@ -685,10 +704,10 @@ static int encode_act(CUtensorMap* m, const float* ptr, int B, int H, int W, int
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
 // packed weights [9][cout_pad][cin]: box = (kc, cout_pad, 1)
-static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int kc) {
+static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int kc, int taps = 9) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
-  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, 9};
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cout_pad * cin * 4};
   cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)cout_pad, 1};
   cuuint32_t es[3] = {1, 1, 1};
@@ -698,16 +717,16 @@ static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
 
-template <int COUT, int KC>
+template <int COUT, int KC, bool PAIR = false>
 static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
-  using C = Cfg<COUT, KC>;
+  using C = Cfg<COUT, KC, PAIR>;
   static bool done = false;
   static int sms = 0;
   if (!done) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<COUT, KC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return nvs_set_cuda_error(e);
     done = true;
@@ -715,7 +734,7 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
   while (C::NS % q.issuers != 0) --q.issuers;  // a slot must always be consumed by the same issuer
-  conv_tc_kernel<COUT, KC><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
+  conv_tc_kernel<COUT, KC, PAIR><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
@@ -765,14 +784,16 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   tc::Plan* pl = reinterpret_cast<tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   const int cpad = nvs_conv_tc_cout_pad(a->cout);
   const int cin = a->c0 + a->c1;
+  const int pair = (a->flags & 2) ? 1 : 0;  // weights given in the paired-tap layout [5][cout_pad][32] (c0 = 16, no src1)
+  if (pair && (a->c0 != 16 || a->c1 != 0 || cpad != 32)) return NVS_ERR_ARG;
   const int kc = tc::pick_kc(a->c0, a->c1);
   int rc = tc::encode_act(&pl->a0, a->src0, a->B, a->H, a->W, a->c0_total, kc);
   if (rc != NVS_OK) return rc;
   rc = tc::encode_act(&pl->a1, a->c1 > 0 ? a->src1 : a->src0, a->B, a->H, a->W, a->c1 > 0 ? a->c1_total : a->c0_total, kc);
   if (rc != NVS_OK) return rc;
-  rc = tc::encode_w(&pl->whi, a->w_hi, cin, cpad, kc);
+  rc = pair ? tc::encode_w(&pl->whi, a->w_hi, 32, cpad, 32, 5) : tc::encode_w(&pl->whi, a->w_hi, cin, cpad, kc);
   if (rc != NVS_OK) return rc;
-  rc = tc::encode_w(&pl->wlo, a->w_lo, cin, cpad, kc);
+  rc = pair ? tc::encode_w(&pl->wlo, a->w_lo, 32, cpad, 32, 5) : tc::encode_w(&pl->wlo, a->w_lo, cin, cpad, kc);
   if (rc != NVS_OK) return rc;
   tc::Params& p = pl->p;
   p.bias = a->bias; p.dst = a->dst; p.dst_pool = a->dst_pool;
@@ -796,6 +817,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.knock = 0;
   pl->cout_tpl = cpad;
   pl->kc = kc;
+  pl->pair = pair;
   pl->magic = tc::PLAN_MAGIC;
   return NVS_OK;
 }
@@ -814,6 +836,7 @@ extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float*
 #endif
   if (p.dst_mode != 0 && !p.dst) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl->pair) return tc::launch<32, 32, true>(*pl, p, st);
   if (pl->kc == 16) return pl->cout_tpl == 32 ? tc::launch<32, 16>(*pl, p, st) : NVS_ERR_UNSUPPORTED;
   switch (pl->cout_tpl) {
     case 32: return tc::launch<32, 32>(*pl, p, st);

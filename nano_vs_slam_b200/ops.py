@@ -368,7 +368,7 @@ def _fold(weight, bias, bn, eps):
 
 
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
-                 eps: float = 1e-5, cin_segments=None):
+                 eps: float = 1e-5, cin_segments=None, pair_taps: bool = True):
     """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc.
 
     w_hi = w rounded to tf32 (10 explicit mantissa bits), w_lo = tf32-rounded (w - w_hi).
@@ -392,6 +392,12 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
     assert cpad > 0, cout
     wt = torch.zeros(9, cpad, cin, dtype=torch.float32, device=w.device)
     wt[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    if cin == 16 and cpad == 32 and pair_taps:
+        # paired-tap layout for 16-channel inputs (NvsConvTcArgs.flags bit 1): K row of step t =
+        # [tap 2t, channels 0-15 | tap 2t+1, channels 0-15]; the tenth tap is zero
+        wp = torch.zeros(10, cpad, 16, dtype=torch.float32, device=w.device)
+        wp[:9] = wt
+        wt = wp.view(5, 2, cpad, 16).permute(0, 2, 1, 3).reshape(5, cpad, 32).contiguous()
     # hi = w rounded to the nearest tf32 value, lo = (w - hi) rounded to the nearest tf32 value (the tensor core
     # truncates operands to tf32; pre-rounding makes the residual error unbiased)
     hi = ((wt.view(torch.int32) + 0x1000) & -8192).view(torch.float32).contiguous()
@@ -456,7 +462,9 @@ class TcConv(object):
             a.c1 = src1.shape[3] - c1_off if c1 is None else c1
         else:
             a.src1, a.c1_total, a.c1_off, a.c1 = None, 0, 0, 0
-        assert hi.shape[2] == a.c0 + a.c1, (hi.shape, a.c0, a.c1)
+        paired = hi.shape[0] == 5  # pack_conv_tc's paired-tap layout for 16-channel inputs
+        assert (hi.shape[2] == 32 and a.c0 == 16 and a.c1 == 0) if paired else hi.shape[2] == a.c0 + a.c1, \
+            (hi.shape, a.c0, a.c1)
         a.dst = _ptr(dst)
         a.dst_pool = _ptr(dst_pool)
         if dst_c_total is None:
@@ -468,7 +476,7 @@ class TcConv(object):
         a.pool_c_total = dst_pool.shape[3] if (dst_pool is not None and dst_mode != 3) else 0
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
-        a.flags = 1 if deterministic else 0
+        a.flags = (1 if deterministic else 0) | (2 if paired else 0)
         if dst is not None:
             if dst_mode == 1 and dst_layout == 0:
                 assert tuple(dst.shape[:3]) == (B, H, W)

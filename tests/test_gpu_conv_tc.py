@@ -15,7 +15,8 @@ def _nhwc(t):
 @pytest.mark.parametrize("cin,cout,H,W,act", [
     (64, 64, 60, 80, 1), (32, 32, 24, 40, 1), (64, 128, 15, 20, 0), (96, 64, 33, 50, 1), (32, 64, 17, 31, 2),
     (64, 28, 20, 28, 0), (64, 32, 9, 19, 0), (128, 64, 8, 16, 1),
-    (16, 32, 40, 56, 1),   # 64-byte-row (SWIZZLE_64B) variant used by the stem layer conv1b
+    (16, 32, 40, 56, 1),   # stem layer conv1b: paired-tap steps (two taps per K = 32 row, 64-byte halo rows)
+    (16, 24, 21, 37, 0),   # ... with padded output channels (N letters)
     (64, 64, 7, 5, 1),     # tile larger than the image
 ])
 def test_conv_tc_plain_nhwc_and_nchw(cin, cout, H, W, act):
@@ -41,6 +42,24 @@ def test_conv_tc_plain_nhwc_and_nchw(cin, cout, H, W, act):
     op.run(dst_override=out2)
     torch.cuda.synchronize()
     assert rel_err(out2, ref) < 2e-5, rel_err(out2, ref)
+
+
+def test_conv_tc_16_channels_single_tap_steps():
+    """The SWIZZLE_64B single-tap variant (pack_conv_tc(pair_taps=False)) stays available and agrees."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(16)
+    B, H, W = 2, 30, 44
+    x = torch.randn(B, 16, H, W, generator=g)
+    w = torch.randn(32, 16, 3, 3, generator=g) * 0.1
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    for pair in (False, True):
+        packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), pair_taps=pair)
+        assert packed[0].shape[0] == (5 if pair else 9)
+        out = torch.zeros(B, H, W, 32, device="cuda")
+        ops.TcConv(_nhwc(x).cuda(), packed, 32, act=1, dst=out).run()
+        assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5, (pair, rel_err(out.permute(0, 3, 1, 2), ref))
 
 
 def test_conv_tc_pool_shuffle_concat_slice():
