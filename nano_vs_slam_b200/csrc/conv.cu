@@ -359,6 +359,99 @@ static int dispatch_ct(const ConvP& p, int B, int ct, cudaStream_t st) {
   return NVS_ERR_UNSUPPORTED;
 }
 
+
+// ------------------------------------------------------------------ stem layer (3 -> 16, NCHW image -> NHWC)
+// backbone.conv1a (encoders.py:105-107): K = 27 is too thin for the tiled kernel above (one 4-channel chunk,
+// all overhead) and for a TMA row of the tensor-core kernel.  Dedicated direct kernel: a 64x8 pixel tile per
+// 128-thread CTA, the 3x10x66 input window and the 27x16 weights in shared memory; every thread computes all 16
+// output channels of FOUR consecutive pixels of a row: the 6 inputs of a (channel, ky) row segment are loaded
+// once and reused by the 3 kx taps, and each broadcast weight LDS.128 feeds 8 packed FFMA2.
+constexpr int STEM_TX = 64, STEM_TY = 8, STEM_CO = 16, STEM_PX = 4;
+__global__ void __launch_bounds__(128) stem_conv_kernel(ConvP p) {
+  // every input value is stored twice, (v, v): it is the packed FFMA2 operand as loaded, no register MOVs
+  // (the buffer is reused afterwards to stage the results)
+  __shared__ __align__(16) unsigned char smem_raw[STEM_TY * STEM_TX * STEM_CO * 4];
+  static_assert(sizeof(smem_raw) >= 3 * (STEM_TY + 2) * (STEM_TX + 4) * sizeof(float2), "input window fits");
+  float2 (*tile)[STEM_TY + 2][STEM_TX + 4] = reinterpret_cast<float2 (*)[STEM_TY + 2][STEM_TX + 4]>(smem_raw);  // pitch 68
+  __shared__ __align__(16) float ws[27][STEM_CO];
+  const int b = blockIdx.z, x0 = blockIdx.x * STEM_TX, y0 = blockIdx.y * STEM_TY;
+  const float* src = p.src0 + ((size_t)b * p.c0_total + p.c0_off) * p.H * p.W;
+  for (int i = threadIdx.x; i < 3 * (STEM_TY + 2) * (STEM_TX + 2); i += 128) {
+    const int c = i / ((STEM_TY + 2) * (STEM_TX + 2)), r = i - c * (STEM_TY + 2) * (STEM_TX + 2);
+    const int yy = r / (STEM_TX + 2), xx = r - yy * (STEM_TX + 2);
+    const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+    const float v = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? src[((size_t)c * p.H + gy) * p.W + gx] : 0.f;
+    tile[c][yy][xx] = make_float2(v, v);
+  }
+  for (int i = threadIdx.x; i < 27 * STEM_CO; i += 128) {
+    const int k = i / STEM_CO, co = i - k * STEM_CO;  // k = ci * 9 + tap; packed weights are [cin_pad][9][cout_pad]
+    ws[k][co] = p.w[(size_t)k * p.cout_pad + co];
+  }
+  __syncthreads();
+  const int lx = (threadIdx.x & 15) * STEM_PX, ly = threadIdx.x >> 4;  // pixels (lx .. lx+3, ly)
+  float2 acc[STEM_PX][STEM_CO / 2];
+#pragma unroll
+  for (int j = 0; j < STEM_CO / 2; ++j) {
+    const float2 bj = make_float2(p.bias[2 * j], p.bias[2 * j + 1]);
+#pragma unroll
+    for (int i = 0; i < STEM_PX; ++i) acc[i][j] = bj;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      float2 in[STEM_PX + 2];
+#pragma unroll
+      for (int i = 0; i < (STEM_PX + 2) / 2; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(&tile[c][ly + ky][lx + 2 * i]);
+        in[2 * i] = make_float2(t.x, t.y);
+        in[2 * i + 1] = make_float2(t.z, t.w);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int k = c * 9 + ky * 3 + kx;
+#pragma unroll
+        for (int q = 0; q < STEM_CO / 4; ++q) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][4 * q]);
+          const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+#pragma unroll
+          for (int i = 0; i < STEM_PX; ++i) {
+            acc[i][2 * q] = __ffma2_rn(in[i + kx], wa, acc[i][2 * q]);
+            acc[i][2 * q + 1] = __ffma2_rn(in[i + kx], wb, acc[i][2 * q + 1]);
+          }
+        }
+      }
+    }
+  // stage the tile's results (XOR-swizzled 16-byte chunks) and write them out as fully coalesced 16-byte
+  // chunks: a thread owns 256 contiguous bytes of NHWC output, which as direct stores is 32 partial sectors
+  // per instruction
+  float4 (*stage)[STEM_TX][STEM_CO / 4] = reinterpret_cast<float4 (*)[STEM_TX][STEM_CO / 4]>(smem_raw);
+  __syncthreads();  // every thread is done reading the input window
+  const float neg_slope = p.act == NVS_ACT_NONE ? 1.f : (p.act == NVS_ACT_LRELU ? 0.01f : 0.f);
+#pragma unroll
+  for (int i = 0; i < STEM_PX; ++i) {
+    const int x = lx + i;
+#pragma unroll
+    for (int q = 0; q < STEM_CO / 4; ++q) {
+      float o[4] = {acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f) + neg_slope * fminf(o[e], 0.f);  // none / LeakyReLU / ReLU
+      stage[ly][x][q ^ ((x >> 2) & 3)] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  constexpr int CH = STEM_CO / 4;
+  for (int idx = threadIdx.x; idx < STEM_TY * STEM_TX * CH; idx += 128) {
+    const int row = idx / (STEM_TX * CH), rem = idx - row * (STEM_TX * CH);
+    const int x = rem / CH, q = rem - x * CH;
+    const int gy = y0 + row, gx = x0 + x;
+    if (gy < p.H && gx < p.W) {
+      float4* d = reinterpret_cast<float4*>(p.dst + (((size_t)b * p.H + gy) * p.W + gx) * p.dst_c_total + p.dst_c_off);
+      d[q] = stage[row][x][q ^ ((x >> 2) & 3)];
+    }
+  }
+}
+
 }  // namespace nvs
 
 extern "C" int nvs_conv_cout_tile(int32_t cout) {
@@ -412,6 +505,14 @@ extern "C" int nvs_conv(const NvsConvArgs* a, void* stream) {
   if (a->out_mode == NVS_OUT_SHUFFLE && a->dst_nhwc) return NVS_ERR_UNSUPPORTED;
   p.tiles_x = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->ksize == 3 && cin == 3 && a->c1 == 0 && a->in_mode == NVS_IN_PLAIN && a->out_mode == NVS_OUT_PLAIN &&
+      a->dst_nhwc && a->cout == STEM_CO && (a->dst_c_total % 4) == 0 && (a->dst_c_off % 4) == 0 &&
+      (a->act == NVS_ACT_NONE || a->act == NVS_ACT_LRELU || a->act == NVS_ACT_RELU)) {
+    dim3 grid((a->W + STEM_TX - 1) / STEM_TX, (a->H + STEM_TY - 1) / STEM_TY, a->B);
+    stem_conv_kernel<<<grid, 128, 0, st>>>(p);
+    NVS_CHECK_LAUNCH();
+    return NVS_OK;
+  }
   if (a->ksize == 3) {
     return ck == 4 ? dispatch_ct<3, 4>(p, a->B, ct, st) : dispatch_ct<3, 8>(p, a->B, ct, st);
   }

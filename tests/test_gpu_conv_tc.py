@@ -136,3 +136,24 @@ def test_conv_small_and_ffma_nhwc_store():
     full, pooled = ops.conv(x16.cuda(), wp, bp, 32, act=1, out_mode=ops.OUT_BOTH, dst_nhwc=True, dst2_nhwc=True)
     assert rel_err(full.permute(0, 3, 1, 2), ref) < 2e-5
     assert rel_err(pooled.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
+
+
+@pytest.mark.parametrize("H,W,act", [(21, 37, 1), (8, 32, 0), (40, 70, 2)])
+def test_stem_conv_3_to_16_nhwc(H, W, act):
+    """backbone.conv1a on the dedicated stem kernel (NCHW image -> 16-channel NHWC), incl. ragged tiles."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(H * W)
+    B = 3
+    x = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    w = torch.randn(16, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(16, generator=g) * 0.1
+    ref = F.conv2d(x, w, b, padding=1)
+    ref = F.leaky_relu(ref, 0.01) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    wp, bp = ops.pack_conv(w.cuda(), bias=b.cuda())
+    out = ops.conv(x.cuda(), wp, bp, 16, act=act, dst_nhwc=True)
+    out = out[0] if isinstance(out, (tuple, list)) else out
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 1e-5, rel_err(out.permute(0, 3, 1, 2), ref)
+    plain = ops.conv(x.cuda(), wp, bp, 16, act=act)  # NCHW store: the generic tiled kernel
+    plain = plain[0] if isinstance(plain, (tuple, list)) else plain
+    assert rel_err(plain, ref) < 1e-5
