@@ -296,12 +296,13 @@ def main():
     fps_gpu = value / world
     ach_gbs = heavy_meta["bytes"] / (kern_ms / 1e3) / 1e9
     ach_tf = heavy_meta["flops"] / (kern_ms / 1e3) / 1e12
-    traffic = None
+    traffic, traffic_batch = None, None
     tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
     if os.path.exists(tpath) and "96->64 k3 @120x160" in heavy_meta["shape"]:
         with open(tpath) as fh:
             tr = json.load(fh)["conv_tc_96_64_120x160"]
-        traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]  # ncu capture at batch 64, linear in batch
+        traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]  # ncu capture at batch 256, linear in batch
+        traffic_batch = tr["batch"]
     if "tcgen05" in heavy_meta["shape"]:
         # 3xTF32: every algorithmic FLOP costs three tf32 tensor-core FLOPs; tf32 runs at half the bf16 rate, so
         # the ceiling for ALGORITHMIC FLOP/s is (measured bf16 dense peak) / 2 / 3.
@@ -309,7 +310,8 @@ def main():
         roofline = {
             "kernel": f"conv_tc_kernel {heavy_meta['shape']} (B={B})", "bound": "tensor",
             "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
-            "traffic_note": "DRAM bytes/launch from ncu --set full at batch 64 (profiles/r1_traffic.json) x B/64; "
+            "traffic_note": (f"DRAM bytes/launch from ncu --set full at batch {traffic_batch} "
+                             f"(profiles/r1_traffic.json) x B/{traffic_batch}; " if traffic is not None else "") +
                             f"algorithmic bytes/launch = {heavy_meta['bytes']:.0f}",
             "peak_source": which + " bf16 sustained / 2 (tf32) / 3 (3xTF32 split)", "kernel_ms": kern_ms,
             "mma_tflops_executed": 3.0 * ach_tf, "tf32_peak_tflops": bf16_peak / 2.0,
