@@ -157,6 +157,19 @@ size_t nvs_netvlad_workspace_bytes(int32_t B, int32_t C, int32_t K, int32_t S);
 int nvs_netvlad(const float* x, const float* w_assign, const float* centroids, float* vlad,
                 void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t K, int32_t S,
                 void* stream);
+
+/* GeM over PixelUnshuffle(4) (modules/aggregators/gem.py:21-33, VPRHead method "gem", vpr.py:70-72):
+ * x (B,C,H,W) with H, W multiples of 4 -> out (B, 16*C), out[b, c*16 + (y%4)*4 + x%4] =
+ * (mean over the 4x4-strided cells of max(x, eps)^p)^(1/p).  No final normalisation (the reference has none). */
+int nvs_gem(const float* x, float* out, int32_t B, int32_t C, int32_t H, int32_t W, float p, float eps, void* stream);
+
+/* ConvAP (modules/aggregators/convap.py:29-37, VPRHead method "convap", vpr.py:73-76): 1x1 conv Cin->Cout with bias,
+ * AdaptiveAvgPool2d((s1,s2)), flatten channel-major, L2 normalise (eps 1e-12).  weight (Cout,Cin), out (B, Cout*s1*s2).
+ * workspace: nvs_convap_workspace_bytes(B,Cin,s1,s2) bytes. */
+size_t nvs_convap_workspace_bytes(int32_t B, int32_t Cin, int32_t s1, int32_t s2);
+int nvs_convap(const float* x, const float* weight, const float* bias, float* out, void* workspace,
+               size_t workspace_bytes, int32_t B, int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t s1,
+               int32_t s2, void* stream);
 /* L2 normalisation over channels (VPRHead only_encoder path, decoders/vpr.py:85-86). */
 int nvs_l2norm_channels(const float* src, float* dst, int32_t B, int32_t C, int32_t HW, void* stream);
 

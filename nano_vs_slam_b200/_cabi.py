@@ -64,6 +64,9 @@ SIGNATURES = {
     "nvs_attention": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nvs_netvlad_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "nvs_netvlad": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _i32, _i32, _vp]),
+    "nvs_gem": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
+    "nvs_convap_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "nvs_convap": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nvs_l2norm_channels": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "nvs_decode": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 9 + [_f32, _vp]),
     "nvs_seg_argmax": (_i32, [_vp, _vp, _vp] + [_i32] * 8 + [_vp]),

@@ -222,6 +222,26 @@ class _NetVLAD(nn.Module):  # modules/aggregators/netvlad.py:19-48
         self.conv.weight = nn.Parameter(torch.from_numpy(alpha * assign).unsqueeze(2).unsqueeze(3).to(dev))
 
 
+class _GeM(nn.Module):  # modules/aggregators/gem.py:8-33 (parameter holder; the math is nvs_gem)
+    def __init__(self, c, p=3, eps=1e-6, unshuffle=4):
+        super().__init__()
+        if unshuffle != 4:
+            raise NotImplementedError("GeM: VPRHead always uses unshuffle=4 (vpr.py:71)")
+        self.p = nn.Parameter(torch.ones(1) * p)
+        self.eps = eps
+        self.f = unshuffle * unshuffle
+
+    def get_factor(self):
+        return self.f
+
+
+class _ConvAP(nn.Module):  # modules/aggregators/convap.py:19-27 (parameter holder; the math is nvs_convap)
+    def __init__(self, in_channels, out_channels=512, s1=2, s2=2):
+        super().__init__()
+        self.channel_pool = nn.Conv2d(in_channels, out_channels, kernel_size=1, bias=True)
+        self.s1, self.s2 = s1, s2
+
+
 class _VPRHead(nn.Module):  # modules/decoders/vpr.py:8-76
     def __init__(self, c_in, encoder_dim, num_clusters, bn_momentum, remove_netvlad, method):
         super().__init__()
@@ -229,14 +249,21 @@ class _VPRHead(nn.Module):  # modules/decoders/vpr.py:8-76
         self.convlad2 = _ConvBnAct(encoder_dim, encoder_dim, bn_momentum)
         self.convlad3 = _ConvBnAct(encoder_dim, encoder_dim, bn_momentum)
         self.remove_netvlad = remove_netvlad
-        if method != "netvlad":
-            raise NotImplementedError(
-                f"global_descriptor_method={method!r}: only 'netvlad' is on the B200 hot path (GeM/ConvAP: SURVEY §8(f))")
-        if not remove_netvlad:
-            self.netvlad = _NetVLAD(num_clusters, encoder_dim)
-            self.global_desc_dim = self.netvlad.get_desc_size()
+        self.method = method
+        if method == "netvlad":
+            if not remove_netvlad:
+                self.netvlad = _NetVLAD(num_clusters, encoder_dim)
+                self.global_desc_dim = self.netvlad.get_desc_size()
+            else:
+                self.global_desc_dim = 0
+        elif method == "gem":  # vpr.py:70-72
+            self.netvlad = _GeM(encoder_dim, unshuffle=4)
+            self.global_desc_dim = encoder_dim * self.netvlad.get_factor()
+        elif method == "convap":  # vpr.py:73-76
+            self.netvlad = _ConvAP(encoder_dim, encoder_dim, 4, 4)
+            self.global_desc_dim = encoder_dim * 16
         else:
-            self.global_desc_dim = 0
+            raise ValueError(f"global_descriptor_method={method!r}")
 
 
 def _p32(c: int) -> int:
@@ -325,6 +352,9 @@ class _KP2DTinyBase(nn.Module):
             raise NotImplementedError("upscale_method='convtranspose' (to_mcu) is MCU-export only (SURVEY §2 #2)")
         if self.depth:
             raise NotImplementedError("depth heads are outside the hot path (SURVEY §8(f))")
+        if self.use_attention and self.channel_dims[4] // 4 not in (12, 16):
+            raise NotImplementedError("attention seg head: head_dim 12 / 16 only (letters S_A, N_A); the large "
+                                      "attention letters D (V2) and D_A (V3) are listed under SURVEY §8(f)")
         self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
         # conv backend: "tc" = tcgen05 3xTF32 implicit GEMM on channels-last maps (needs 32-channel multiples:
         # the S letters), "ffma" = exact fp32 direct conv (any channel count: the N letters).
@@ -460,8 +490,15 @@ class _KP2DTinyBase(nn.Module):
             P["vlad." + n] = self._pk_block(getattr(vh, n), tc=tc)
         if not vh.remove_netvlad:
             nv = vh.netvlad
-            P["vlad.assign"] = nv.conv.weight.detach().reshape(nv.num_clusters, nv.dim).contiguous().float()
-            P["vlad.cent"] = nv.centroids.detach().contiguous().float()
+            if vh.method == "netvlad":
+                P["vlad.assign"] = nv.conv.weight.detach().reshape(nv.num_clusters, nv.dim).contiguous().float()
+                P["vlad.cent"] = nv.centroids.detach().contiguous().float()
+            elif vh.method == "gem":
+                P["vlad.gem_p"] = float(nv.p.detach().float().cpu())
+            else:
+                cp = nv.channel_pool
+                P["vlad.cap_w"] = cp.weight.detach().reshape(cp.out_channels, cp.in_channels).contiguous().float()
+                P["vlad.cap_b"] = cp.bias.detach().contiguous().float()
         self._pack_heads(P)
         return P
 
@@ -557,6 +594,31 @@ class _KP2DTinyBase(nn.Module):
         result["seg"] = outs["seg"]
         return result
 
+    def _plan_aggregator(self, pl: _Plan, P, v3: torch.Tensor, B: int, enc: int, H4: int, W4: int):
+        """Global-descriptor aggregator on the (B, enc, H/4, W/4) NCHW encoder map (vpr.py:84-88)."""
+        vh = self.vlad_head
+        if vh.remove_netvlad:
+            return
+        if vh.method == "netvlad":
+            K = vh.netvlad.num_clusters
+            pl.out_shapes["vlad"] = (B, K * enc)
+            ws = torch.empty(ops.netvlad_workspace_bytes(B, enc, K, H4 * W4), dtype=torch.uint8, device=pl.device)
+            pl.bufs["vlad_ws"] = ws
+            pl.call(lambda outs, v3=v3, ws=ws: ops.netvlad(v3, P["vlad.assign"], P["vlad.cent"], out=outs["vlad"],
+                                                            workspace=ws))
+        elif vh.method == "gem":
+            if H4 % 4 or W4 % 4:
+                raise ValueError(f"GeM: PixelUnshuffle(4) needs the {H4}x{W4} encoder map to be a multiple of 4 "
+                                 "(the reference raises here too, gem.py:23)")
+            pl.out_shapes["vlad"] = (B, 16 * enc)
+            pl.call(lambda outs, v3=v3: ops.gem(v3, P["vlad.gem_p"], vh.netvlad.eps, out=outs["vlad"]))
+        else:
+            pl.out_shapes["vlad"] = (B, 16 * enc)
+            ws = torch.empty(int(ops.lib().nvs_convap_workspace_bytes(B, enc, 4, 4)), dtype=torch.uint8, device=pl.device)
+            pl.bufs["vlad_ws"] = ws
+            pl.call(lambda outs, v3=v3, ws=ws: ops.convap(v3, P["vlad.cap_w"], P["vlad.cap_b"], 4, 4, out=outs["vlad"],
+                                                           workspace=ws))
+
     # --- plan construction ------------------------------------------------------------------------
     def _build_plan(self, pl: _Plan):
         if self.conv_backend == "tc":
@@ -633,13 +695,7 @@ class _KP2DTinyBase(nn.Module):
         pl.conv(P["vlad.convlad2"], v1, enc, act=act, dst=v2)
         v3 = pl.buf("v3", enc, H4, W4)
         pl.conv(P["vlad.convlad3"], v2, enc, act=act, dst=v3)
-        if not self.vlad_head.remove_netvlad:
-            K = self.vlad_head.netvlad.num_clusters
-            pl.out_shapes["vlad"] = (B, K * enc)
-            ws = torch.empty(ops.netvlad_workspace_bytes(B, enc, K, H4 * W4), dtype=torch.uint8, device=pl.device)
-            pl.bufs["vlad_ws"] = ws
-            pl.call(lambda outs, v3=v3, ws=ws: ops.netvlad(v3, P["vlad.assign"], P["vlad.cent"], out=outs["vlad"],
-                                                           workspace=ws))
+        self._plan_aggregator(pl, P, v3, B, enc, H4, W4)
 
     def _build_plan_tc(self, pl: _Plan):
         """Same graph as _build_plan_ffma with channels-last intermediates and tcgen05 convs (csrc/conv_tc.cu).
@@ -719,13 +775,7 @@ class _KP2DTinyBase(nn.Module):
         pl.tc(P["vlad.convlad2"], v1, encp, act=act, dst=v2)
         v3 = pl.buf("v3", enc, H4, W4)  # NCHW, real channels, for the NetVLAD kernel
         pl.tc(P["vlad.convlad3"], v2, enc, act=act, dst=v3, dst_layout=1)
-        if not self.vlad_head.remove_netvlad:
-            K = self.vlad_head.netvlad.num_clusters
-            pl.out_shapes["vlad"] = (B, K * enc)
-            ws = torch.empty(ops.netvlad_workspace_bytes(B, enc, K, H4 * W4), dtype=torch.uint8, device=pl.device)
-            pl.bufs["vlad_ws"] = ws
-            pl.call(lambda outs, v3=v3, ws=ws: ops.netvlad(v3, P["vlad.assign"], P["vlad.cent"], out=outs["vlad"],
-                                                           workspace=ws))
+        self._plan_aggregator(pl, P, v3, B, enc, H4, W4)
 
     def _plan_att(self, pl: _Plan, A: dict, x: torch.Tensor, C: int, h: int, w: int, tag: str,
                   pooled_out: Optional[torch.Tensor] = None, plain_out: Optional[torch.Tensor] = None,

@@ -242,6 +242,31 @@ def netvlad(x, w_assign, centroids, out=None, workspace=None):
     return out
 
 
+def gem(x, p: float, eps: float = 1e-6, out=None):
+    """x (B,C,h,w), h and w multiples of 4 -> (B, 16*C): GeM over PixelUnshuffle(4) (aggregators/gem.py:21-33)."""
+    x = _req(x)
+    B, Cc, h, w = x.shape
+    out = torch.empty(B, 16 * Cc, device=x.device, dtype=torch.float32) if out is None else out
+    check(lib().nvs_gem(x.data_ptr(), out.data_ptr(), B, Cc, h, w, float(p), float(eps), _stream()), "nvs_gem")
+    LAUNCHES[0] += 1
+    return out
+
+
+def convap(x, weight, bias, s1: int = 4, s2: int = 4, out=None, workspace=None):
+    """x (B,Cin,h,w) -> (B, Cout*s1*s2): 1x1 conv + AdaptiveAvgPool2d + L2 norm (aggregators/convap.py:29-37)."""
+    x = _req(x)
+    B, cin, h, w = x.shape
+    cout = weight.shape[0]
+    nbytes = int(lib().nvs_convap_workspace_bytes(B, cin, s1, s2))
+    if workspace is None:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty(B, cout * s1 * s2, device=x.device, dtype=torch.float32) if out is None else out
+    check(lib().nvs_convap(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), workspace.data_ptr(),
+                           workspace.numel(), B, cin, cout, h, w, s1, s2, _stream()), "nvs_convap")
+    LAUNCHES[0] += 2
+    return out
+
+
 def decode(score, shift, feat, H: int, W: int, cell: int, cross_ratio: float = 2.0):
     """post_processing core (kp2dtiny.py:593-631): returns (score_masked, coord_px, feat_sampled_unit)."""
     score, shift = _req(score), _req(shift)

@@ -41,6 +41,8 @@ def spread_init(state_dict: Dict[str, torch.Tensor], seed: int = 1234) -> Dict[s
             out[key] = torch.randn(shape, generator=g) * 0.1
         elif leaf == "running_var":
             out[key] = torch.rand(shape, generator=g) + 0.5  # U(0.5, 1.5)
+        elif leaf == "p" and shape == (1,):
+            out[key] = 2.5 + torch.rand(shape, generator=g)  # GeM exponent (gem.py:11 default 3), kept positive
         elif leaf == "centroids":
             out[key] = torch.rand(shape, generator=g)  # netvlad.py:43 default
         elif parent == "norm" and leaf == "g":

@@ -35,6 +35,13 @@ CASES = [
     ("v3_S_A", "S_A", True, 28, 1, 32, 48, 1239, 5),
     ("v3_N", "N", True, 28, 2, 40, 56, 1240, 6),
     ("v3_N_A", "N_A", True, 19, 1, 40, 56, 1241, 7),
+    # alternative aggregators (vpr.py:70-76); GeM's PixelUnshuffle(4) needs H/4 and W/4 to be multiples of 4
+    ("v2_GEM_N", "GEM_N", False, 28, 2, 64, 80, 1242, 8),
+    ("v2_GEM_S_A", "GEM_S_A", False, 19, 1, 48, 64, 1243, 9),
+    ("v2_CONVAP_S_A", "CONVAP_S_A", False, 19, 1, 40, 56, 1244, 10),
+    ("v3_CONVAP_S_A", "CONVAP_S_A", True, 28, 2, 40, 56, 1245, 11),
+    # the large letter without attention (LARGE_D_V3: 64..512 channels, 128-d descriptors, ConvAP)
+    ("v3_D", "D", True, 19, 1, 40, 56, 1246, 12),
 ]
 
 

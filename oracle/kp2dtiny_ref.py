@@ -29,6 +29,7 @@ class Arch:
     use_attention: bool = False
     leaky_relu: bool = True
     downsample: int = 2
+    global_descriptor_method: str = "netvlad"  # "gem" / "convap": letters GEM_*, CONVAP_* (kp2dtiny.py:64-82, 135-144)
 
     @property
     def cell(self) -> int:
@@ -37,8 +38,15 @@ class Arch:
 
 def arch_for(letter: str, v3: bool, n_classes: int) -> Arch:
     """Letter -> numbers; mirrors TINY_S / TINY_N / V3_S / V3_N ... (kp2dtiny.py:46-166)."""
+    method = "netvlad"
+    for prefix, m in (("GEM_", "gem"), ("CONVAP_", "convap")):
+        if letter.startswith(prefix):
+            letter, method = letter[len(prefix):], m
     small = letter.startswith("S")
     att = letter.endswith("_A")
+    if letter in ("D", "D_A"):  # LARGE_D / LARGE_D_V3 / LARGE_D_A_V3 (kp2dtiny.py:168-196): ConvAP, 128-d descriptors
+        att = att or not v3     # V2 "D" has use_attention=True
+        return Arch(3 if v3 else 2, (64, 128, 128, 256, 256, 512), 128, n_classes, 128, 64, att, True, 2, "convap")
     if small:
         dims, enc = (16, 32, 32, 64, 64, 128), 64
     else:
@@ -46,7 +54,7 @@ def arch_for(letter: str, v3: bool, n_classes: int) -> Arch:
     # V2 'N'/'N_A' set num_clusters=32 (kp2dtiny.py:84-102); every other letter keeps the
     # constructor default of 64 (kp2dtiny.py:308, :690).
     k = 32 if (not small and not v3) else 64
-    return Arch(3 if v3 else 2, dims, 32, n_classes, enc, k, att, True, 2)
+    return Arch(3 if v3 else 2, dims, 32, n_classes, enc, k, att, True, 2, method)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -204,6 +212,22 @@ def netvlad_literal(x: Tensor, sd: SD, p: str = "vlad_head.netvlad") -> Tensor:
     return F.normalize(vlad.reshape(N, -1), p=2.0, dim=1)
 
 
+def gem(x: Tensor, sd: SD, p: str = "vlad_head.netvlad", eps: float = 1e-6) -> Tensor:
+    """modules/aggregators/gem.py:21-33 with unshuffle=4 (vpr.py:71): PixelUnshuffle(4), then
+    (avg over the whole map of clamp(x, eps)^p)^(1/p), flattened; no normalisation."""
+    pw = sd[p + ".p"]
+    x = F.pixel_unshuffle(x, 4)
+    return F.avg_pool2d(x.clamp(min=eps).pow(pw), (x.size(-2), x.size(-1))).pow(1.0 / pw).flatten(1)
+
+
+def convap(x: Tensor, sd: SD, p: str = "vlad_head.netvlad", s: int = 4) -> Tensor:
+    """modules/aggregators/convap.py:29-37 with s1 = s2 = 4 (vpr.py:74-75): biased 1x1 conv,
+    AdaptiveAvgPool2d((4,4)), flatten, L2 normalise."""
+    y = F.conv2d(x, sd[p + ".channel_pool.weight"], sd[p + ".channel_pool.bias"])
+    y = F.adaptive_avg_pool2d(y, (s, s))
+    return F.normalize(y.flatten(1), p=2.0, dim=1)
+
+
 def vpr_head(x: Tensor, sd: SD, a: Arch, only_encoder: bool = False) -> Tensor:
     """modules/decoders/vpr.py:78-89."""
     v = conv_bn_act(x, sd, "vlad_head.convlad1", a.leaky_relu)
@@ -211,6 +235,10 @@ def vpr_head(x: Tensor, sd: SD, a: Arch, only_encoder: bool = False) -> Tensor:
     v = conv_bn_act(v, sd, "vlad_head.convlad3", a.leaky_relu)
     if only_encoder:
         return F.normalize(v, p=2.0, dim=1)
+    if a.global_descriptor_method == "gem":
+        return gem(v, sd)
+    if a.global_descriptor_method == "convap":
+        return convap(v, sd)
     return netvlad(v, sd)
 
 

@@ -263,3 +263,36 @@ def test_match_large_random():
     # a handful of near-threshold ratio tests may flip with fp32 summation order
     got, ref = set(zip(i1[:n].cpu().tolist(), i2[:n].cpu().tolist())), set(zip(r1, r2))
     assert len(got ^ ref) <= max(2, len(ref) // 500)
+
+
+@pytest.mark.parametrize("B,C,h,w,p", [(2, 48, 16, 20, 3.0), (1, 64, 8, 12, 2.6), (3, 64, 60, 80, 3.3)])
+def test_gem_unshuffle4(B, C, h, w, p):
+    """GeM over PixelUnshuffle(4) (aggregators/gem.py:21-33) vs torch."""
+    import torch.nn.functional as F
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(B * C + h)
+    x = torch.randn(B, C, h, w, generator=g)
+    u = F.pixel_unshuffle(x, 4)
+    ref = F.avg_pool2d(u.clamp(min=1e-6).pow(p), (u.size(-2), u.size(-1))).pow(1.0 / p).flatten(1)
+    out = ops.gem(x.cuda(), p, 1e-6)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 2e-6, rel_err(out, ref)
+    with pytest.raises(Exception):
+        ops.gem(torch.randn(1, 8, 10, 14).cuda(), 3.0)  # PixelUnshuffle(4) needs multiples of 4
+
+
+@pytest.mark.parametrize("B,C,h,w", [(2, 64, 10, 14), (1, 48, 7, 5), (3, 128, 60, 80)])
+def test_convap(B, C, h, w):
+    """ConvAP (aggregators/convap.py:29-37): 1x1 conv + AdaptiveAvgPool2d((4,4)) + L2 norm, ragged bins."""
+    import torch.nn.functional as F
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(C + h)
+    x = torch.randn(B, C, h, w, generator=g)
+    wt = torch.randn(C, C, 1, 1, generator=g) * 0.2
+    b = torch.randn(C, generator=g) * 0.1
+    ref = F.normalize(F.adaptive_avg_pool2d(F.conv2d(x, wt, b), (4, 4)).flatten(1), p=2.0, dim=1)
+    out = ops.convap(x.cuda(), wt.view(C, C).contiguous().cuda(), b.cuda(), 4, 4)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 5e-6, rel_err(out, ref)
