@@ -12,10 +12,12 @@ constexpr int VP = 64;  // pixels per chunk
 
 template <int C, int K>
 struct VladCfg {
-  static constexpr int TK = K / 16;           // clusters per thread in the aggregation phase
   static constexpr int NCT = C / 4;           // channel tiles (4 channels each)
+  static constexpr int KG = 16 * NCT <= 256 ? 16 : 256 / NCT;  // cluster groups in the aggregation phase
+  static constexpr int TK = K / KG;           // clusters per thread in the aggregation phase
   static constexpr int NT = 256;
-  static constexpr int AGG_THREADS = 16 * NCT;  // <= 256
+  static constexpr int AGG_THREADS = KG * NCT;  // <= 256
+  static_assert(K % KG == 0 && AGG_THREADS <= 256 && C % 4 == 0 && K % 4 == 0, "NetVLAD tiling");
   static constexpr int KPT = K / 4;           // clusters per thread in the assignment phase
   static constexpr int XP = VP + 1;           // pitch of xs[c][p]
   static constexpr int AP = K + 1;            // pitch of as[p][k]
@@ -233,5 +235,6 @@ extern "C" int nvs_netvlad(const float* x, const float* w_assign, const float* c
   if (C == 48 && K == 32) return nvs::run_netvlad<48, 32>(x, w_assign, centroids, vlad, ws, B, S, st);
   if (C == 48 && K == 64) return nvs::run_netvlad<48, 64>(x, w_assign, centroids, vlad, ws, B, S, st);
   if (C == 64 && K == 32) return nvs::run_netvlad<64, 32>(x, w_assign, centroids, vlad, ws, B, S, st);
+  if (C == 128 && K == 64) return nvs::run_netvlad<128, 64>(x, w_assign, centroids, vlad, ws, B, S, st);  // letter F
   return NVS_ERR_UNSUPPORTED;
 }

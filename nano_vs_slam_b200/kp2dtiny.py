@@ -346,8 +346,8 @@ class _KP2DTinyBase(nn.Module):
         self._packed = None
         self._packed_key = None
         self._plans: Dict = {}
-        if self.downsample != 2:
-            raise NotImplementedError("downsample != 2 (config letters D/F cell 8) is listed under SURVEY §8(f)")
+        if self.downsample not in (2, 3):
+            raise NotImplementedError("downsample must be 2 (cell 4) or 3 (cell 8, letter F)")
         if self.upscale_method != "pixelshuffle":
             raise NotImplementedError("upscale_method='convtranspose' (to_mcu) is MCU-export only (SURVEY §2 #2)")
         if self.depth:
@@ -362,6 +362,7 @@ class _KP2DTinyBase(nn.Module):
         # (channel counts that are not multiples of 32 -- the N letters: 24/48/72/96 -- run on zero-padded
         # 32-channel rows: padded weights are zero, so padded activations stay exactly zero)
         tc_ok = c1 % 16 == 0 and _p32(c2) <= 32 and max(_p32(c4), _p32(c5), _p32(d1)) <= 128 and d1 % 4 == 0
+        tc_ok = tc_ok and self.downsample == 2  # cell 8 (letter F: 256 channels anyway) runs on the FFMA backend
         self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
         # batches up to this size replay a captured CUDA graph (0 disables)
         self.cuda_graph_max_batch = int(os.environ.get("NVS_CUDA_GRAPH_MAX_BATCH", "16"))
@@ -512,10 +513,11 @@ class _KP2DTinyBase(nn.Module):
         if not x.is_cuda:
             raise NanovsError("input must be a CUDA tensor: the sm_100a kernels are the only implementation")
         B, _, H, W = x.shape
-        if (H // 2) % 4 != 0 or (W // 2) % 4 != 0:
+        hs, ws = (H // 2, W // 2) if self.downsample == 2 else (H // 2 // 2, W // 2 // 2)  # skip-level map
+        if hs % 4 != 0 or ws % 4 != 0:
             # the reference fails in torch.cat when pool/pixel-shuffle sizes disagree
-            raise RuntimeError(f"input {H}x{W}: floor(H/2) and floor(W/2) must be multiples of 4 "
-                               "(pixel-shuffle/skip concat sizes would differ, as in the reference)")
+            raise RuntimeError(f"input {H}x{W}: the skip-level map {hs}x{ws} must have sides that are multiples "
+                               "of 4 (pixel-shuffle/skip concat sizes would differ, as in the reference)")
         return x.contiguous().float()
 
     @torch.no_grad()
@@ -630,7 +632,10 @@ class _KP2DTinyBase(nn.Module):
         B, H, W = pl.B, pl.H, pl.W
         c1, c2, c3, c4, c5, d1 = self.channel_dims
         act = ops.ACT_LRELU if self.leaky_relu else ops.ACT_RELU
-        H2, W2 = H // 2, W // 2
+        # downsample = 3 (letter F, cell 8) pools a second time after conv2b (encoders.py:116-117): from conv3a
+        # on every map is one level smaller, the graph is the same.  (H2,W2) = skip level, (H4,W4) = cell level.
+        H1, W1 = H // 2, W // 2
+        H2, W2 = (H1, W1) if self.downsample == 2 else (H1 // 2, W1 // 2)
         H4, W4 = H2 // 2, W2 // 2
         H8, W8 = H4 // 2, W4 // 2
         nf, ncls = self.nfeatures, self.nClasses
@@ -642,12 +647,15 @@ class _KP2DTinyBase(nn.Module):
         t1a = pl.buf("t1a", c1, H, W)
         pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a)
         pl.in_args = pl.steps[-1][1]
-        p1 = pl.buf("p1", c2, H2, W2)
+        p1 = pl.buf("p1", c2, H1, W1)
         pl.conv(P["bb.conv1b"], t1a, c2, act=act, out_mode=ops.OUT_POOL, dst2=p1)
-        t2a = pl.buf("t2a", c2, H2, W2)
+        t2a = pl.buf("t2a", c2, H1, W1)
         pl.conv(P["bb.conv2a"], p1, c2, act=act, dst=t2a)
         t2b = pl.buf("t2b", c3, H2, W2)
-        pl.conv(P["bb.conv2b"], t2a, c3, act=act, dst=t2b)
+        if self.downsample == 3:
+            pl.conv(P["bb.conv2b"], t2a, c3, act=act, out_mode=ops.OUT_POOL, dst2=t2b)
+        else:
+            pl.conv(P["bb.conv2b"], t2a, c3, act=act, dst=t2b)
         t3a = pl.buf("t3a", c3, H2, W2)
         pl.conv(P["bb.conv3a"], t2b, c3, act=act, dst=t3a)
         skip = pl.buf("skip", c4, H2, W2)

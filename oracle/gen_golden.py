@@ -42,6 +42,8 @@ CASES = [
     ("v3_CONVAP_S_A", "CONVAP_S_A", True, 28, 2, 40, 56, 1245, 11),
     # the large letter without attention (LARGE_D_V3: 64..512 channels, 128-d descriptors, ConvAP)
     ("v3_D", "D", True, 19, 1, 40, 56, 1246, 12),
+    # cell 8 (TINY_F: downsample = 3, 16..256 channels, 64-d descriptors): skip-level map = H/4 must be a multiple of 4
+    ("v2_F", "F", False, 19, 1, 64, 96, 1247, 13),
 ]
 
 

@@ -47,6 +47,8 @@ def arch_for(letter: str, v3: bool, n_classes: int) -> Arch:
     if letter in ("D", "D_A"):  # LARGE_D / LARGE_D_V3 / LARGE_D_A_V3 (kp2dtiny.py:168-196): ConvAP, 128-d descriptors
         att = att or not v3     # V2 "D" has use_attention=True
         return Arch(3 if v3 else 2, (64, 128, 128, 256, 256, 512), 128, n_classes, 128, 64, att, True, 2, "convap")
+    if letter == "F":  # TINY_F (kp2dtiny.py:112-118): cell 8, 64-d descriptors, encoder_dim defaults to c4, NetVLAD K = 64
+        return Arch(2, (16, 32, 64, 128, 128, 256), 64, n_classes, 128, 64, False, True, 3, "netvlad")
     if small:
         dims, enc = (16, 32, 32, 64, 64, 128), 64
     else:
