@@ -591,6 +591,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           float a = v[j] + bias_s[cc * 32 + j];
           if (p.act == NVS_ACT_LRELU) a = a > 0.f ? a : 0.01f * a;
           else if (p.act == NVS_ACT_RELU) a = fmaxf(a, 0.f);
+          else if (p.act == NVS_ACT_SIGMOID) a = 1.f / (1.f + expf(-a));  // depth heads (kp2dtiny.py:589, :956)
           v[j] = a;
         }
         const int cbase = cc * 32;
@@ -779,7 +780,8 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   if ((a->c0_total % 4) || (a->c0_off % 4) || (a->c1 > 0 && ((a->c1_total % 4) || (a->c1_off % 4)))) return NVS_ERR_ARG;
   if (a->dst_mode != 0 && ((a->dst_c_total % 4) || (a->dst_c_off % 4)) && a->dst_layout == 0) return NVS_ERR_ARG;
   if (a->dst_mode == 2 && (a->cout % 32) != 0) return NVS_ERR_UNSUPPORTED;
-  if (a->act != NVS_ACT_NONE && a->act != NVS_ACT_LRELU && a->act != NVS_ACT_RELU) return NVS_ERR_UNSUPPORTED;
+  if (a->act != NVS_ACT_NONE && a->act != NVS_ACT_LRELU && a->act != NVS_ACT_RELU && a->act != NVS_ACT_SIGMOID)
+    return NVS_ERR_UNSUPPORTED;
   if (a->dst_mode == 3 && (a->cout != 3 || a->act != NVS_ACT_NONE)) return NVS_ERR_ARG;
   tc::Plan* pl = reinterpret_cast<tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   const int cpad = nvs_conv_tc_cout_pad(a->cout);

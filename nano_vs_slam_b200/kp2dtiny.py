@@ -174,10 +174,14 @@ class _AttModule(nn.Module):  # modules/segformer.py:209-220
 class _SegHead(nn.Module):
     """The four segmentation heads (modules/decoders/segmentation.py:8,169,350,478) as one holder."""
 
-    def __init__(self, c_in, c_hidden, c_exp, c_out, d1, bn_momentum, attention, n_feat=None):
+    def __init__(self, c_in, c_hidden, c_exp, c_out, d1, bn_momentum, attention, n_feat=None, depth=False):
         super().__init__()
         fused = n_feat is not None  # V3: seg + feat from one trunk
         self.dim_split = c_hidden // 2
+        self.depth = bool(depth) and fused
+        # V3 with depth: the trunk's last block is three slices wide, the middle one feeds featD
+        # (segmentation.py:187-191, 515-519)
+        self.c_last = c_hidden + (self.dim_split if self.depth else 0)
         if fused:
             assert c_hidden % 2 == 0, "c_hidden must be divisible by 2"
         cb = lambda a, b: _ConvBnAct(a, b, bn_momentum)  # noqa: E731
@@ -185,11 +189,13 @@ class _SegHead(nn.Module):
             layers = [cb(c_in, c_hidden), _AttModule(c_hidden), _AttModule(c_hidden)]
         else:
             layers = [cb(c_in, c_hidden), cb(c_hidden, c_hidden), cb(c_hidden, c_hidden), cb(c_hidden, c_hidden)]
-        layers += [cb(c_hidden, d1), cb(c_hidden + d1 // 4, c_hidden), cb(c_hidden, d1), cb(c_exp, c_hidden),
+        layers += [cb(c_hidden, d1), cb(c_hidden + d1 // 4, c_hidden), cb(c_hidden, d1), cb(c_exp, self.c_last),
                    nn.Conv2d(self.dim_split if fused else c_hidden, c_out, 3, 1, 1)]
         self.convs = nn.ModuleList(layers)
         if fused:
             self.featB = nn.Conv2d(self.dim_split, n_feat, 3, 1, 1)
+        if self.depth:
+            self.featD = nn.Conv2d(self.dim_split, 1, 3, 1, 1, bias=False)  # segmentation.py:284-287
 
     def freeze(self, except_last_layer=False):  # segmentation.py:159-166
         for p in self.parameters():
@@ -350,8 +356,6 @@ class _KP2DTinyBase(nn.Module):
             raise NotImplementedError("downsample must be 2 (cell 4) or 3 (cell 8, letter F)")
         if self.upscale_method != "pixelshuffle":
             raise NotImplementedError("upscale_method='convtranspose' (to_mcu) is MCU-export only (SURVEY §2 #2)")
-        if self.depth:
-            raise NotImplementedError("depth heads are outside the hot path (SURVEY §8(f))")
         if self.use_attention and self.channel_dims[4] // 4 not in (12, 16):
             raise NotImplementedError("attention seg head: head_dim 12 / 16 only (letters S_A, N_A); the large "
                                       "attention letters D (V2) and D_A (V3) are listed under SURVEY §8(f)")
@@ -466,6 +470,19 @@ class _KP2DTinyBase(nn.Module):
             "pw": self._pk_conv(g[1].net[1]), "m3": self._pk_conv(g[3]), "heads": f.heads,
         }
 
+    def _pack_seg(self, P: dict, sh: "_SegHead", pre: str, tc: bool):
+        c1_, c2_, c3_, c4_, c5_, d1_ = self.channel_dims
+        n_convs = len(sh.convs)
+        for i, m in enumerate(sh.convs):
+            # the two concat convs read [pixel-shuffled d1/4 | x (c4)] and [pixel-shuffled d1/4 | skip (c4)]
+            seg = [d1_ // 4, c4_] if i in (n_convs - 4, n_convs - 2) else None
+            if isinstance(m, _ConvBnAct):
+                P[f"{pre}.{i}"] = self._pk_block(m, tc=tc, seg=seg)
+            elif isinstance(m, _AttModule):
+                P[f"{pre}.{i}"] = self._pack_att(m)
+            else:
+                P[f"{pre}.{i}"] = self._pk_conv(m, tc=tc)
+
     def _pack(self) -> dict:
         P = {}
         tc = self.conv_backend == "tc"
@@ -474,18 +491,7 @@ class _KP2DTinyBase(nn.Module):
             # the 3-channel stem layer stays on the FFMA kernel (K = 27 is too thin for a TMA row); conv1b
             # (16 channels) uses the 64-byte-row variant of the tensor-core kernel
             P["bb." + n] = self._pk_block(getattr(bb, n), tc=tc and n != "conv1a")
-        sh = self.seg_head
-        c1_, c2_, c3_, c4_, c5_, d1_ = self.channel_dims
-        n_convs = len(sh.convs)
-        for i, m in enumerate(sh.convs):
-            # the two concat convs read [pixel-shuffled d1/4 | x (c4)] and [pixel-shuffled d1/4 | skip (c4)]
-            seg = [d1_ // 4, c4_] if i in (n_convs - 4, n_convs - 2) else None
-            if isinstance(m, _ConvBnAct):
-                P[f"seg.{i}"] = self._pk_block(m, tc=tc, seg=seg)
-            elif isinstance(m, _AttModule):
-                P[f"seg.{i}"] = self._pack_att(m)
-            else:
-                P[f"seg.{i}"] = self._pk_conv(m, tc=tc)
+        self._pack_seg(P, self.seg_head, "seg", tc)
         vh = self.vlad_head
         for n in ("convlad1", "convlad2", "convlad3"):
             P["vlad." + n] = self._pk_block(getattr(vh, n), tc=tc)
@@ -594,6 +600,8 @@ class _KP2DTinyBase(nn.Module):
         else:
             result["vlad"] = plan.bufs["v3"].clone()  # remove_netvlad: raw encoder map (vpr.py:83-89)
         result["seg"] = outs["seg"]
+        if "depth" in outs:
+            result["depth"] = outs["depth"]  # already sigmoid-ed (kp2dtiny.py:589, :956)
         return result
 
     def _plan_aggregator(self, pl: _Plan, P, v3: torch.Tensor, B: int, enc: int, H4: int, W4: int):
@@ -670,30 +678,13 @@ class _KP2DTinyBase(nn.Module):
         self._plan_heads(pl, xb, skip, act)
 
         # ---- segmentation trunk (modules/decoders/segmentation.py) ----
-        s0 = pl.buf("s0", c5, H4, W4)
-        pl.conv(P["seg.0"], xb, c5, act=act, dst=s0)
-        sp3 = pl.buf("sp3", c5, H8, W8)
-        if self.use_attention:
-            sp = pl.buf("sp", c5, H8, W8)
-            self._plan_att(pl, P["seg.1"], s0, c5, H4, W4, "a1", pooled_out=sp)
-            self._plan_att(pl, P["seg.2"], sp, c5, H8, W8, "a2", plain_out=sp3)
-            nxt = 3
-        else:
-            sp = pl.buf("sp", c5, H8, W8)
-            pl.conv(P["seg.1"], s0, c5, act=act, out_mode=ops.OUT_POOL, dst2=sp)
-            s2 = pl.buf("s2", c5, H8, W8)
-            pl.conv(P["seg.2"], sp, c5, act=act, dst=s2)
-            pl.conv(P["seg.3"], s2, c5, act=act, dst=sp3)
-            nxt = 4
-        ps1 = pl.buf("ps1", d1 // 4, H4, W4)
-        pl.conv(P[f"seg.{nxt}"], sp3, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps1)
-        s5 = pl.buf("s5", c5, H4, W4)
-        pl.conv(P[f"seg.{nxt + 1}"], ps1, c5, act=act, src1=xb, dst=s5)
-        ps2 = pl.buf("ps2", d1 // 4, H2, W2)
-        pl.conv(P[f"seg.{nxt + 2}"], s5, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps2)
-        s7 = pl.buf("s7", c5, H2, W2)
-        pl.conv(P[f"seg.{nxt + 3}"], ps2, c5, act=act, src1=skip, dst=s7)
-        self._plan_seg_out(pl, s7, P[f"seg.{nxt + 4}"])
+        s7, last = self._plan_trunk_ffma(pl, "seg", "", self.seg_head, xb, skip, act)
+        self._plan_seg_out(pl, s7, last)
+        if self.depth and self.version == 2:  # second trunk, one output channel, sigmoid (kp2dtiny.py:588-590)
+            d7, dlast = self._plan_trunk_ffma(pl, "dep", "_d", self.depth_head, xb, skip, act)
+            pl.out_shapes["depth"] = (B, 1, H2, W2)
+            pl.conv(dlast, d7, 1, act=ops.ACT_SIGMOID, dst=torch.empty(B, 1, H2, W2, device=pl.device),
+                    out_name="depth")
 
         # ---- VPR head (modules/decoders/vpr.py:78-89) ----
         enc = self.encoder_dim
@@ -704,6 +695,40 @@ class _KP2DTinyBase(nn.Module):
         v3 = pl.buf("v3", enc, H4, W4)
         pl.conv(P["vlad.convlad3"], v2, enc, act=act, dst=v3)
         self._plan_aggregator(pl, P, v3, B, enc, H4, W4)
+
+    def _plan_trunk_ffma(self, pl: _Plan, pre: str, tag: str, head: "_SegHead", xb, skip, act):
+        """Segmentation trunk up to its last conv block (segmentation.py:126-152 / 314-334 / 442-463 / 588-608);
+        returns (last block's output, packed final conv).  ``pre`` selects the packed weights ("seg" / "dep"),
+        ``tag`` keeps the buffers of a second trunk apart."""
+        P = self._packed
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        _, _, H4, W4 = xb.shape
+        H2, W2 = skip.shape[2:]
+        H8, W8 = H4 // 2, W4 // 2
+        s0 = pl.buf("s0" + tag, c5, H4, W4)
+        pl.conv(P[pre + ".0"], xb, c5, act=act, dst=s0)
+        sp3 = pl.buf("sp3" + tag, c5, H8, W8)
+        if self.use_attention:
+            sp = pl.buf("sp" + tag, c5, H8, W8)
+            self._plan_att(pl, P[pre + ".1"], s0, c5, H4, W4, "a1" + tag, pooled_out=sp)
+            self._plan_att(pl, P[pre + ".2"], sp, c5, H8, W8, "a2" + tag, plain_out=sp3)
+            nxt = 3
+        else:
+            sp = pl.buf("sp" + tag, c5, H8, W8)
+            pl.conv(P[pre + ".1"], s0, c5, act=act, out_mode=ops.OUT_POOL, dst2=sp)
+            s2 = pl.buf("s2" + tag, c5, H8, W8)
+            pl.conv(P[pre + ".2"], sp, c5, act=act, dst=s2)
+            pl.conv(P[pre + ".3"], s2, c5, act=act, dst=sp3)
+            nxt = 4
+        ps1 = pl.buf("ps1" + tag, d1 // 4, H4, W4)
+        pl.conv(P[f"{pre}.{nxt}"], sp3, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps1)
+        s5 = pl.buf("s5" + tag, c5, H4, W4)
+        pl.conv(P[f"{pre}.{nxt + 1}"], ps1, c5, act=act, src1=xb, dst=s5)
+        ps2 = pl.buf("ps2" + tag, d1 // 4, H2, W2)
+        pl.conv(P[f"{pre}.{nxt + 2}"], s5, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps2)
+        s7 = pl.buf("s7" + tag, head.c_last, H2, W2)
+        pl.conv(P[f"{pre}.{nxt + 3}"], ps2, head.c_last, act=act, src1=skip, dst=s7)
+        return s7, P[f"{pre}.{nxt + 4}"]
 
     def _build_plan_tc(self, pl: _Plan):
         """Same graph as _build_plan_ffma with channels-last intermediates and tcgen05 convs (csrc/conv_tc.cu).
@@ -746,33 +771,12 @@ class _KP2DTinyBase(nn.Module):
         self._plan_heads_tc(pl, xb, skip, act)
 
         # ---- segmentation trunk ----
-        sp3 = pl.buf_nhwc("sp3", c5p, H8, W8)
-        if self.use_attention:
-            s0 = pl.buf("s0", c5, H4, W4)  # NCHW, real channels: the attention block's LN / projections read planes
-            pl.tc(P["seg.0"], xb, c5, act=act, dst=s0, dst_layout=1)
-            sp = pl.buf("sp", c5, H8, W8)
-            self._plan_att(pl, P["seg.1"], s0, c5, H4, W4, "a1", pooled_out=sp)
-            sp3.zero_()  # the FFMA 1x1 writes the real channels only; padding must read as zero
-            self._plan_att(pl, P["seg.2"], sp, c5, H8, W8, "a2", plain_out=sp3, plain_nhwc=True)
-            nxt = 3
-        else:
-            s0 = pl.buf_nhwc("s0", c5p, H4, W4)
-            pl.tc(P["seg.0"], xb, c5p, act=act, dst=s0)
-            sp = pl.buf_nhwc("sp", c5p, H8, W8)
-            pl.tc(P["seg.1"], s0, c5p, act=act, dst=None, dst_mode=0, dst_pool=sp)
-            s2 = pl.buf_nhwc("s2", c5p, H8, W8)
-            pl.tc(P["seg.2"], sp, c5p, act=act, dst=s2)
-            pl.tc(P["seg.3"], s2, c5p, act=act, dst=sp3)
-            nxt = 4
-        ps1 = pl.buf_nhwc("ps1", qp, H4, W4)
-        pl.tc(P[f"seg.{nxt}"], sp3, d1p, act=act, dst=ps1, dst_mode=2)
-        s5 = pl.buf_nhwc("s5", c5p, H4, W4)
-        pl.tc(P[f"seg.{nxt + 1}"], ps1, c5p, act=act, src1=xb, dst=s5)
-        ps2 = pl.buf_nhwc("ps2", qp, H2, W2)
-        pl.tc(P[f"seg.{nxt + 2}"], s5, d1p, act=act, dst=ps2, dst_mode=2)
-        s7 = pl.buf_nhwc("s7", c5p, H2, W2)
-        pl.tc(P[f"seg.{nxt + 3}"], ps2, c5p, act=act, src1=skip, dst=s7)
-        self._plan_seg_out_tc(pl, s7, P[f"seg.{nxt + 4}"])
+        s7, last = self._plan_trunk_tc(pl, "seg", "", self.seg_head, xb, skip, act)
+        self._plan_seg_out_tc(pl, s7, last)
+        if self.depth and self.version == 2:  # second trunk, one output channel, sigmoid (kp2dtiny.py:588-590)
+            d7, dlast = self._plan_trunk_tc(pl, "dep", "_d", self.depth_head, xb, skip, act)
+            pl.out_shapes["depth"] = (B, 1, H2, W2)
+            pl.tc(dlast, d7, 1, act=ops.ACT_SIGMOID, dst=None, dst_layout=1, dst_c_total=1, out_name="depth")
 
         # ---- VPR head ----
         enc = self.encoder_dim
@@ -784,6 +788,43 @@ class _KP2DTinyBase(nn.Module):
         v3 = pl.buf("v3", enc, H4, W4)  # NCHW, real channels, for the NetVLAD kernel
         pl.tc(P["vlad.convlad3"], v2, enc, act=act, dst=v3, dst_layout=1)
         self._plan_aggregator(pl, P, v3, B, enc, H4, W4)
+
+    def _plan_trunk_tc(self, pl: _Plan, pre: str, tag: str, head: "_SegHead", xb, skip, act):
+        """_plan_trunk_ffma on channels-last maps with tcgen05 convs."""
+        P = self._packed
+        c1, c2, c3, c4, c5, d1 = self.channel_dims
+        c5p, d1p, qp = _p32(c5), _p32(d1), _p32(d1 // 4)
+        _, H4, W4, _ = xb.shape
+        H2, W2 = skip.shape[1:3]
+        H8, W8 = H4 // 2, W4 // 2
+        sp3 = pl.buf_nhwc("sp3" + tag, c5p, H8, W8)
+        if self.use_attention:
+            s0 = pl.buf("s0" + tag, c5, H4, W4)  # NCHW, real channels: the attention block's LN / projections read planes
+            pl.tc(P[pre + ".0"], xb, c5, act=act, dst=s0, dst_layout=1)
+            sp = pl.buf("sp" + tag, c5, H8, W8)
+            self._plan_att(pl, P[pre + ".1"], s0, c5, H4, W4, "a1" + tag, pooled_out=sp)
+            sp3.zero_()  # the FFMA 1x1 writes the real channels only; padding must read as zero
+            self._plan_att(pl, P[pre + ".2"], sp, c5, H8, W8, "a2" + tag, plain_out=sp3, plain_nhwc=True)
+            nxt = 3
+        else:
+            s0 = pl.buf_nhwc("s0" + tag, c5p, H4, W4)
+            pl.tc(P[pre + ".0"], xb, c5p, act=act, dst=s0)
+            sp = pl.buf_nhwc("sp" + tag, c5p, H8, W8)
+            pl.tc(P[pre + ".1"], s0, c5p, act=act, dst=None, dst_mode=0, dst_pool=sp)
+            s2 = pl.buf_nhwc("s2" + tag, c5p, H8, W8)
+            pl.tc(P[pre + ".2"], sp, c5p, act=act, dst=s2)
+            pl.tc(P[pre + ".3"], s2, c5p, act=act, dst=sp3)
+            nxt = 4
+        ps1 = pl.buf_nhwc("ps1" + tag, qp, H4, W4)
+        pl.tc(P[f"{pre}.{nxt}"], sp3, d1p, act=act, dst=ps1, dst_mode=2)
+        s5 = pl.buf_nhwc("s5" + tag, c5p, H4, W4)
+        pl.tc(P[f"{pre}.{nxt + 1}"], ps1, c5p, act=act, src1=xb, dst=s5)
+        ps2 = pl.buf_nhwc("ps2" + tag, qp, H2, W2)
+        pl.tc(P[f"{pre}.{nxt + 2}"], s5, d1p, act=act, dst=ps2, dst_mode=2)
+        clp = _p32(head.c_last)
+        s7 = pl.buf_nhwc("s7" + tag, clp, H2, W2)
+        pl.tc(P[f"{pre}.{nxt + 3}"], ps2, clp, act=act, src1=skip, dst=s7)
+        return s7, P[f"{pre}.{nxt + 4}"]
 
     def _plan_att(self, pl: _Plan, A: dict, x: torch.Tensor, C: int, h: int, w: int, tag: str,
                   pooled_out: Optional[torch.Tensor] = None, plain_out: Optional[torch.Tensor] = None,
@@ -867,12 +908,16 @@ class KP2DTinyV2(_KP2DTinyBase):
         self.loc_head = _TaskHead(c4, c4, 2, bn_momentum)
         self.desc_head = _UpscaleHead(c4, c4, c3 * 4, c3 + c4, c4, nfeatures, bn_momentum)
         self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention)
+        if depth:  # a second segmentation head with one output channel (kp2dtiny.py:402-437)
+            self.depth_head = _SegHead(c4, c5, c4 + c3, 1, d1, bn_momentum, use_attention)
         self.vlad_head = _VPRHead(c4, self.encoder_dim, num_clusters, bn_momentum, remove_netvlad,
                                   global_descriptor_method)
         self._finish_init()
 
     def _pack_heads(self, P):
         tc = self.conv_backend == "tc"
+        if self.depth:
+            self._pack_seg(P, self.depth_head, "dep", tc)
         P["score.a"] = self._pk_block(self.score_head.convDa, tc=tc)
         P["loc.a"] = self._pk_block(self.loc_head.convDa, tc=tc)
         if tc:
@@ -971,7 +1016,8 @@ class KP2DTinyV3(_KP2DTinyBase):
         self.encoder_dim = encoder_dim if encoder_dim is not None else c4
         self.backbone = _BackBone(3, c1, c2, c3, c4, 0.1)
         self.score_loc_head = _TaskHead(c4, c4, 3, bn_momentum)
-        self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention, n_feat=nfeatures)
+        self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention, n_feat=nfeatures,
+                                 depth=depth)
         self.vlad_head = _VPRHead(c4, self.encoder_dim, num_clusters, bn_momentum, remove_netvlad,
                                   global_descriptor_method)
         self._finish_init()
@@ -988,6 +1034,8 @@ class KP2DTinyV3(_KP2DTinyBase):
             P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
             P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
         P["featB"] = self._pk_conv(self.seg_head.featB, tc=tc)
+        if self.depth:
+            P["featD"] = self._pk_conv(self.seg_head.featD, tc=tc)
 
     def _plan_heads(self, pl, xb, skip, act):
         P = self._packed
@@ -1002,10 +1050,14 @@ class KP2DTinyV3(_KP2DTinyBase):
 
     def _plan_seg_out(self, pl, s7, packed_last):
         # segmentation.py:337-347 / :609-619: feat from the first half of the trunk, seg from the last half
-        B, c5, H2, W2 = s7.shape
+        B, c5, H2, W2 = s7.shape  # c5 = width of the trunk's last block: 2 slices, 3 with depth
         ds = self.seg_head.dim_split
         pl.conv(self._packed["featB"], s7, self.nfeatures, c0_off=0, c0=ds,
                 dst=torch.empty(B, self.nfeatures, H2, W2, device=pl.device), out_name="feat")
+        if self.depth:  # middle slice -> featD -> sigmoid (segmentation.py:339-341, kp2dtiny.py:955-956)
+            pl.out_shapes["depth"] = (B, 1, H2, W2)
+            pl.conv(self._packed["featD"], s7, 1, c0_off=ds, c0=ds, act=ops.ACT_SIGMOID,
+                    dst=torch.empty(B, 1, H2, W2, device=pl.device), out_name="depth")
         if self.remove_softmax:
             pl.conv(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=ds,
                     dst=torch.empty(B, self.nClasses, H2, W2, device=pl.device), out_name="seg")
@@ -1024,11 +1076,15 @@ class KP2DTinyV3(_KP2DTinyBase):
 
     def _plan_seg_out_tc(self, pl, s7, packed_last):
         B, H2, W2, _ = s7.shape
-        c5 = self.channel_dims[4]
-        ds = self.seg_head.dim_split   # real channels per half; each conv reads a 32-channel (padded) window
+        c5 = self.seg_head.c_last      # real width of the trunk's last block: 2 slices, 3 with depth
+        ds = self.seg_head.dim_split   # real channels per slice; each conv reads a 32-channel (padded) window
         dsp = _p32(ds)
         pl.tc(self._packed["featB"], s7, self.nfeatures, c0_off=0, c0=dsp, dst=None, dst_layout=1,
               dst_c_total=self.nfeatures, out_name="feat")
+        if self.depth:
+            pl.out_shapes["depth"] = (B, 1, H2, W2)
+            pl.tc(self._packed["featD"], s7, 1, c0_off=ds, c0=dsp, act=ops.ACT_SIGMOID, dst=None, dst_layout=1,
+                  dst_c_total=1, out_name="depth")
         if self.remove_softmax:
             pl.tc(packed_last, s7, self.nClasses, c0_off=c5 - ds, c0=dsp, dst=None, dst_layout=1,
                   dst_c_total=self.nClasses, out_name="seg")

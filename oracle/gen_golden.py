@@ -44,6 +44,10 @@ CASES = [
     ("v3_D", "D", True, 19, 1, 40, 56, 1246, 12),
     # cell 8 (TINY_F: downsample = 3, 16..256 channels, 64-d descriptors): skip-level map = H/4 must be a multiple of 4
     ("v2_F", "F", False, 19, 1, 64, 96, 1247, 13),
+    # depth=True constructor kwarg: V2 second segmentation head (kp2dtiny.py:402-437), V3 middle slice + featD
+    ("v2_S_depth", "S", False, 19, 1, 40, 56, 1248, 14),
+    ("v3_N_depth", "N", True, 28, 2, 40, 56, 1249, 15),
+    ("v3_S_A_depth", "S_A", True, 19, 1, 32, 48, 1250, 16),
 ]
 
 
@@ -51,14 +55,20 @@ def load_reference():
     sys.path.insert(0, REF)
     sys.path.insert(0, os.path.join(REF, "src"))
     sys.dont_write_bytecode = True
-    from src.kp2dtiny.models.kp2dtiny import tiny_factory  # type: ignore
+    from src.kp2dtiny.models.kp2dtiny import KP2DTinyV2, KP2DTinyV3, get_config, tiny_factory  # type: ignore
 
-    return tiny_factory
+    def factory(letter, n_classes, v3=False, depth=False):
+        if not depth:
+            return tiny_factory(letter, n_classes, v3=v3)
+        cls = KP2DTinyV3 if v3 else KP2DTinyV2  # the callers' form: Cls(**get_config(...), nClasses=n, depth=True)
+        return cls(**dict(get_config(letter, v3=v3)), nClasses=n_classes, depth=True)
+
+    return factory
 
 
-def run_reference(tiny_factory, letter, v3, n_classes, B, H, W, wseed, xseed):
+def run_reference(tiny_factory, letter, v3, n_classes, B, H, W, wseed, xseed, depth=False):
     with contextlib.redirect_stdout(io.StringIO()):
-        m = tiny_factory(letter, n_classes, v3=v3)
+        m = tiny_factory(letter, n_classes, v3=v3, depth=depth)
     sd = spread_init(m.state_dict(), wseed)
     m.load_state_dict(sd, strict=True)
     m.eval()
@@ -76,8 +86,11 @@ def main():
     gold = os.path.join(REPO, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     for name, letter, v3, ncls, B, H, W, wseed, xseed in CASES:
-        fwd, post = run_reference(tiny_factory, letter, v3, ncls, B, H, W, wseed, xseed)
+        depth = name.endswith("_depth")
+        fwd, post = run_reference(tiny_factory, letter, v3, ncls, B, H, W, wseed, xseed, depth=depth)
         arrs = {"meta": np.array([int(v3), ncls, B, H, W, wseed, xseed], dtype=np.int64)}
+        if depth:
+            arrs["depth"] = np.array(1)
         arrs["letter"] = np.array(letter)
         for k, v in fwd.items():
             arrs["fwd_" + k] = v.numpy()

@@ -30,13 +30,20 @@ class Arch:
     leaky_relu: bool = True
     downsample: int = 2
     global_descriptor_method: str = "netvlad"  # "gem" / "convap": letters GEM_*, CONVAP_* (kp2dtiny.py:64-82, 135-144)
+    depth: bool = False  # constructor kwarg depth=True (kp2dtiny.py:315,402-437; segmentation.py:189-191,284-287)
 
     @property
     def cell(self) -> int:
         return 2 ** self.downsample  # kp2dtiny.py:455
 
 
-def arch_for(letter: str, v3: bool, n_classes: int) -> Arch:
+def arch_for(letter: str, v3: bool, n_classes: int, depth: bool = False) -> Arch:
+    import dataclasses
+
+    return dataclasses.replace(_arch_for(letter, v3, n_classes), depth=depth)
+
+
+def _arch_for(letter: str, v3: bool, n_classes: int) -> Arch:
     """Letter -> numbers; mirrors TINY_S / TINY_N / V3_S / V3_N ... (kp2dtiny.py:46-166)."""
     method = "netvlad"
     for prefix, m in (("GEM_", "gem"), ("CONVAP_", "convap")):
@@ -160,13 +167,13 @@ def segformer_attention_module(x: Tensor, sd: SD, p: str) -> Tensor:
     return x
 
 
-def seg_trunk(x: Tensor, skip: Tensor, sd: SD, a: Arch) -> Tensor:
+def seg_trunk(x: Tensor, skip: Tensor, sd: SD, a: Arch, head: str = "seg_head") -> Tensor:
     """Shared trunk of the four segmentation heads up to (and including) the last conv block.
 
     plain:     segmentation.py:126-152 (V2) / :314-334 (V3)   -> convs[0..7]
     attention: segmentation.py:442-463 (V2) / :588-608 (V3)   -> convs[0..6]
     """
-    lk, p = a.leaky_relu, "seg_head.convs."
+    lk, p = a.leaky_relu, head + ".convs."
     s = conv_bn_act(x, sd, p + "0", lk)
     if a.use_attention:
         s = segformer_attention_module(s, sd, p + "1")
@@ -259,6 +266,8 @@ def forward(x: Tensor, sd: SD, a: Arch) -> Dict[str, Tensor]:
         feat = upscale_head(xb, skip, sd, a)
         last = "seg_head.convs.7" if a.use_attention else "seg_head.convs.8"
         seg = conv_bias(seg_trunk(xb, skip, sd, a), sd, last)
+        if a.depth:  # a second segmentation head with one output channel, then sigmoid (kp2dtiny.py:402-437,588-590)
+            depth = conv_bias(seg_trunk(xb, skip, sd, a, "depth_head"), sd, last.replace("seg_head", "depth_head")).sigmoid()
     else:
         sl = simple_task_head(xb, sd, "score_loc_head", a)
         score, shift = sl[:, 0:1].sigmoid(), sl[:, 1:3].tanh()
@@ -268,8 +277,13 @@ def forward(x: Tensor, sd: SD, a: Arch) -> Dict[str, Tensor]:
         last = "seg_head.convs.7" if a.use_attention else "seg_head.convs.8"
         seg = conv_bias(t[:, -ds:], sd, last)
         seg = seg.softmax(dim=1)  # Softmax2d
+        if a.depth:  # the trunk's last block is 3*ds wide; the middle slice feeds featD (segmentation.py:339-341), :955-956
+            depth = F.conv2d(t[:, ds:2 * ds], sd["seg_head.featD.weight"], None, padding=1).sigmoid()
     vlad = vpr_head(xb, sd, a)
-    return {"score": score, "coord": shift, "feat": feat, "vlad": vlad, "seg": seg}
+    out = {"score": score, "coord": shift, "feat": feat, "vlad": vlad, "seg": seg}
+    if a.depth:
+        out["depth"] = depth
+    return out
 
 
 @torch.no_grad()

@@ -12,12 +12,11 @@ from util import POST_FEAT_TOL_TC, REL_TOL, golden_cases, load_golden, rel_err, 
 pytestmark = pytest.mark.gpu
 
 
-def _model(letter, n_classes, v3, wseed, backend=None):
-    from nano_vs_slam_b200 import tiny_factory
+def _model(letter, n_classes, v3, wseed, backend=None, depth=False):
     from nano_vs_slam_b200.synthetic import spread_init
+    from util import build_model
 
-    with contextlib.redirect_stdout(io.StringIO()):
-        m = tiny_factory(letter, n_classes, v3=v3)
+    m = build_model(letter, n_classes, v3, depth)
     if backend is not None:
         m.conv_backend = backend  # "tc" (tcgen05 3xTF32, default for S letters) or "ffma" (exact fp32)
     sd = spread_init(m.state_dict(), wseed)
@@ -33,10 +32,11 @@ def test_model_matches_reference_golden(path):
     from nano_vs_slam_b200.synthetic import synthetic_frames
 
     c = load_golden(path)
-    m, _ = _model(c["letter"], c["n_classes"], c["v3"], c["wseed"])
+    m, _ = _model(c["letter"], c["n_classes"], c["v3"], c["wseed"], depth=c["depth"])
     x = synthetic_frames(c["B"], c["H"], c["W"], c["xseed"]).cuda()
     out = m(x)
-    for k in ("score", "coord", "feat", "vlad", "seg"):
+    assert ("depth" in out) == c["depth"]
+    for k in ("score", "coord", "feat", "vlad", "seg") + (("depth",) if c["depth"] else ()):
         assert out[k].shape == c["fwd"][k].shape, k
         assert rel_err(out[k], c["fwd"][k]) < tol(k, c["v3"]), (k, rel_err(out[k], c["fwd"][k]))
     post = m.post_processing(dict(out), c["H"], c["W"])

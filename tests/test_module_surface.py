@@ -63,6 +63,24 @@ def test_state_dict_keys_equal_reference(letter, v3):
     ours.load_state_dict(ref, strict=True)  # a reference checkpoint loads unchanged
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="live reference not present")
+@pytest.mark.parametrize("letter,v3", [("S", False), ("S_A", False), ("N", True), ("S_A", True)])
+def test_state_dict_keys_equal_reference_with_depth(letter, v3):
+    """depth=True: V2 grows a second segmentation head, V3 a third trunk slice + featD (kp2dtiny.py:402-437)."""
+    sys.path[:0] = [REF, os.path.join(REF, "src")]
+    sys.dont_write_bytecode = True
+    from src.kp2dtiny.models import kp2dtiny as ref  # type: ignore
+    from util import build_model
+
+    cls = ref.KP2DTinyV3 if v3 else ref.KP2DTinyV2
+    rsd = _quiet(lambda: cls(**dict(ref.get_config(letter, v3=v3)), nClasses=19, depth=True)).state_dict()
+    ours = build_model(letter, 19, v3, depth=True)
+    sd = ours.state_dict()
+    assert list(sd.keys()) == list(rsd.keys())
+    for k in rsd:
+        assert tuple(sd[k].shape) == tuple(rsd[k].shape), k
+
+
 def test_load_state_dict_invalidates_packed_weights():
     from nano_vs_slam_b200 import tiny_factory
     from nano_vs_slam_b200.synthetic import spread_init

@@ -18,21 +18,21 @@ REF = "/root/reference"
 
 def _state_dict_for(case):
     # key names + shapes come from the product module tree (must equal the reference's)
-    from nano_vs_slam_b200.kp2dtiny import tiny_factory
+    from util import build_model
 
-    with contextlib.redirect_stdout(io.StringIO()):
-        m = tiny_factory(case["letter"], case["n_classes"], v3=case["v3"])
+    m = build_model(case["letter"], case["n_classes"], case["v3"], case["depth"])
     return spread_init(m.state_dict(), case["wseed"])
 
 
 @pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[6:-4])
 def test_oracle_matches_reference_golden(path):
     c = load_golden(path)
-    a = R.arch_for(c["letter"], c["v3"], c["n_classes"])
+    a = R.arch_for(c["letter"], c["v3"], c["n_classes"], depth=c["depth"])
     sd = _state_dict_for(c)
     x = synthetic_frames(c["B"], c["H"], c["W"], c["xseed"])
     out = R.forward(x, sd, a)
-    for k in ("score", "coord", "feat", "vlad", "seg"):
+    assert ("depth" in out) == c["depth"] == ("depth" in c["fwd"])
+    for k in ("score", "coord", "feat", "vlad", "seg") + (("depth",) if c["depth"] else ()):
         assert out[k].shape == c["fwd"][k].shape, k
         assert rel_err(out[k], c["fwd"][k]) < 2e-5, (k, rel_err(out[k], c["fwd"][k]))
     post = R.post_processing(dict(out), c["H"], c["W"], a)
