@@ -288,6 +288,32 @@ def main():
         e2e_ms = float(t)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
+    # the same stream fed with uint8 HWC camera frames (what the VO loop gets from the decoder,
+    # visual_odometry.py:281): 1/4 of the H2D bytes, /255 and (x-0.5)*2 fused into the stem kernel's load
+    host_u8 = [((hx.permute(0, 2, 3, 1) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+               for hx in host_x]
+
+    def run_stream_u8(n):
+        got = 0
+        for res in fe.stream((host_u8[i % 2] for i in range(n))):
+            got += int(res["count"][0] >= 0)
+        assert got == n
+
+    run_stream_u8(3)
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    run_stream_u8(args.steps)
+    u1.record()
+    barrier()
+    u8_ms = u0.elapsed_time(u1)
+    if world > 1:
+        t = torch.tensor([u8_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u8_ms = float(t)
+    e2e_u8 = {"value": world * B * args.steps / (u8_ms / 1e3), "unit": "frames/s",
+              "h2d_bytes_per_step": host_u8[0].numel(), "note": "uint8 HWC frames in, same outputs"}
+
     # ---- roofline of the dominant kernel + whole-step figures ----
     from nano_vs_slam_b200.synthetic import algorithmic_bytes_per_frame
     flops_frame = sum(m["flops"] for m in plan.meta.values()) / B  # conv FLOPs (97 % of the model)
@@ -361,6 +387,7 @@ def main():
                              "per step ~10 GB"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
+            "e2e_uint8_frames": e2e_u8,
             "gpu_launches": launches, "cuda_graph": bool(plan.graph is not None), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         line.update(extra)

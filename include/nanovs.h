@@ -51,6 +51,9 @@ extern "C" {
 /* how the conv reads its input */
 #define NVS_IN_PLAIN 0
 #define NVS_IN_S2D 1        /* 2x2 stride-2 conv expressed as 1x1 over space-to-depth(2): segformer.py:93-95 */
+#define NVS_IN_U8_HWC 2     /* src0 = uint8 (B,H,W,3) camera frames; value = (u8 / 255 - 0.5) * 2 on load
+                               (visual_odometry.py:283 + frontend.py:79).  Stem layer only: ksize 3, c0 = c0_total = 3,
+                               cout 16, NVS_OUT_PLAIN, dst_nhwc */
 
 const char* nvs_last_error(void);
 int nvs_abi_version(void);
@@ -157,6 +160,13 @@ size_t nvs_netvlad_workspace_bytes(int32_t B, int32_t C, int32_t K, int32_t S);
 int nvs_netvlad(const float* x, const float* w_assign, const float* centroids, float* vlad,
                 void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t K, int32_t S,
                 void* stream);
+
+/* Input side of the path (visual_odometry.py:281-291 process_image + frontend.py:79):
+ * uint8 HWC frames (B,Hin,Win,3) -> float / 255 -> bilinear resize to (Hout,Wout) when the sizes differ
+ * (kornia.geometry.transform.resize = F.interpolate(mode="bilinear", align_corners=False), no antialias)
+ * -> (x - 0.5) * 2 -> fp32 NCHW (B,3,Hout,Wout). */
+int nvs_preprocess_u8(const uint8_t* img, float* out, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
+                      void* stream);
 
 /* GeM over PixelUnshuffle(4) (modules/aggregators/gem.py:21-33, VPRHead method "gem", vpr.py:70-72):
  * x (B,C,H,W) with H, W multiples of 4 -> out (B, 16*C), out[b, c*16 + (y%4)*4 + x%4] =

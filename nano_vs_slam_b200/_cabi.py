@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libnanovs.so")
 NVS_OK = 0
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SIGMOID_TANH, ACT_GELU = range(7)
 OUT_PLAIN, OUT_POOL, OUT_BOTH, OUT_SHUFFLE = range(4)
-IN_PLAIN, IN_S2D = range(2)
+IN_PLAIN, IN_S2D, IN_U8_HWC = range(3)
 
 _vp, _i32, _f32, _f64, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_size_t, C.c_int64
 
@@ -64,6 +64,7 @@ SIGNATURES = {
     "nvs_attention": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nvs_netvlad_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "nvs_netvlad": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _i32, _i32, _vp]),
+    "nvs_preprocess_u8": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nvs_gem": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
     "nvs_convap_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "nvs_convap": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

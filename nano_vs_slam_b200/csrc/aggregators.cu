@@ -119,3 +119,44 @@ extern "C" int nvs_convap(const float* x, const float* weight, const float* bias
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
+
+namespace nvs {
+// torch's upsample_bilinear2d (align_corners=False): src = scale * (dst + 0.5) - 0.5 clamped at 0, i1 = i0 + 1 if
+// inside, weights (1 - l, l), rows first then columns:  h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char* __restrict__ img, float* __restrict__ out,
+                                                            int Hin, int Win, int Hout, int Wout, float sh, float sw) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= Hout * Wout) return;
+  const int oy = idx / Wout, ox = idx - oy * Wout;
+  const unsigned char* ib = img + (size_t)b * Hin * Win * 3 + c;
+  float v;
+  if (Hin == Hout && Win == Wout) {
+    v = __fdiv_rn((float)ib[((size_t)oy * Win + ox) * 3], 255.f);
+  } else {
+    const float fy = fmaxf(__fsub_rn(__fmul_rn(sh, (float)oy + 0.5f), 0.5f), 0.f);
+    const float fx = fmaxf(__fsub_rn(__fmul_rn(sw, (float)ox + 0.5f), 0.5f), 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float v00 = __fdiv_rn((float)ib[((size_t)y0 * Win + x0) * 3], 255.f);
+    const float v01 = __fdiv_rn((float)ib[((size_t)y0 * Win + x1) * 3], 255.f);
+    const float v10 = __fdiv_rn((float)ib[((size_t)y1 * Win + x0) * 3], 255.f);
+    const float v11 = __fdiv_rn((float)ib[((size_t)y1 * Win + x1) * 3], 255.f);
+    const float top = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
+    const float bot = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
+    v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+  }
+  out[(((size_t)b * 3 + c) * Hout + oy) * Wout + ox] = __fmul_rn(__fsub_rn(v, 0.5f), 2.f);
+}
+}  // namespace nvs
+
+extern "C" int nvs_preprocess_u8(const uint8_t* img, float* out, int32_t B, int32_t Hin, int32_t Win, int32_t Hout,
+                                 int32_t Wout, void* stream) {
+  if (!img || !out || B <= 0 || Hin <= 0 || Win <= 0 || Hout <= 0 || Wout <= 0 || B > 65535) return NVS_ERR_ARG;
+  const dim3 grid((Hout * Wout + 255) / 256, 3, B);
+  nvs::preprocess_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, out, Hin, Win, Hout, Wout, (float)Hin / (float)Hout, (float)Win / (float)Wout);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}

@@ -376,11 +376,19 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(ConvP p) {
   __shared__ __align__(16) float ws[27][STEM_CO];
   const int b = blockIdx.z, x0 = blockIdx.x * STEM_TX, y0 = blockIdx.y * STEM_TY;
   const float* src = p.src0 + ((size_t)b * p.c0_total + p.c0_off) * p.H * p.W;
+  // NVS_IN_U8_HWC: the frame is the camera's uint8 HWC image; /255 (visual_odometry.py:283) and (x - 0.5) * 2
+  // (frontend.py:79) happen here, in the same fp32 operations, so the fp32 NCHW copy of the input never exists
+  const unsigned char* src8 = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)b * p.H * p.W * 3;
+  const bool u8 = p.in_mode == NVS_IN_U8_HWC;
   for (int i = threadIdx.x; i < 3 * (STEM_TY + 2) * (STEM_TX + 2); i += 128) {
     const int c = i / ((STEM_TY + 2) * (STEM_TX + 2)), r = i - c * (STEM_TY + 2) * (STEM_TX + 2);
     const int yy = r / (STEM_TX + 2), xx = r - yy * (STEM_TX + 2);
     const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-    const float v = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? src[((size_t)c * p.H + gy) * p.W + gx] : 0.f;
+    float v = 0.f;
+    if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+      if (u8) v = __fmul_rn(__fsub_rn(__fdiv_rn((float)src8[((size_t)gy * p.W + gx) * 3 + c], 255.f), 0.5f), 2.f);
+      else v = src[((size_t)c * p.H + gy) * p.W + gx];
+    }
     tile[c][yy][xx] = make_float2(v, v);
   }
   for (int i = threadIdx.x; i < 27 * STEM_CO; i += 128) {
@@ -505,7 +513,12 @@ extern "C" int nvs_conv(const NvsConvArgs* a, void* stream) {
   if (a->out_mode == NVS_OUT_SHUFFLE && a->dst_nhwc) return NVS_ERR_UNSUPPORTED;
   p.tiles_x = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->ksize == 3 && cin == 3 && a->c1 == 0 && a->in_mode == NVS_IN_PLAIN && a->out_mode == NVS_OUT_PLAIN &&
+  if (a->in_mode == NVS_IN_U8_HWC &&
+      !(a->ksize == 3 && cin == 3 && a->c0_total == 3 && a->c0_off == 0 && a->c1 == 0 && a->out_mode == NVS_OUT_PLAIN &&
+        a->dst_nhwc && a->cout == STEM_CO))
+    return NVS_ERR_UNSUPPORTED;  // uint8 frames are read by the stem kernel only
+  if (a->ksize == 3 && cin == 3 && a->c1 == 0 && (a->in_mode == NVS_IN_PLAIN || a->in_mode == NVS_IN_U8_HWC) &&
+      a->out_mode == NVS_OUT_PLAIN &&
       a->dst_nhwc && a->cout == STEM_CO && (a->dst_c_total % 4) == 0 && (a->dst_c_off % 4) == 0 &&
       (a->act == NVS_ACT_NONE || a->act == NVS_ACT_LRELU || a->act == NVS_ACT_RELU)) {
     dim3 grid((a->W + STEM_TX - 1) / STEM_TX, (a->H + STEM_TY - 1) / STEM_TY, a->B);

@@ -568,6 +568,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int acc = 0;
     uint32_t aph = 0;
     const int ly = 2 * warp + (lane >> 4), lx = lane & 15;  // pixel inside the tile (TMEM lane = ly*16 + lx)
+    const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
       const int gx = tx * TX + lx, gy = ty * TY + ly;
@@ -586,13 +587,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         }
+        // none / LeakyReLU(0.01) / ReLU as max(a,0) + slope * min(a,0): branch free
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float a = v[j] + bias_s[cc * 32 + j];
-          if (p.act == NVS_ACT_LRELU) a = a > 0.f ? a : 0.01f * a;
-          else if (p.act == NVS_ACT_RELU) a = fmaxf(a, 0.f);
-          else if (p.act == NVS_ACT_SIGMOID) a = 1.f / (1.f + expf(-a));  // depth heads (kp2dtiny.py:589, :956)
-          v[j] = a;
+          const float a = v[j] + bias_s[cc * 32 + j];
+          v[j] = fmaxf(a, 0.f) + neg_slope * fminf(a, 0.f);
+        }
+        if (p.act == NVS_ACT_SIGMOID) {  // depth heads (kp2dtiny.py:589, :956): cout <= 4, kept off the common path
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
         }
         const int cbase = cc * 32;
         if (p.dst_mode == 3) {
@@ -783,6 +786,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   if (a->act != NVS_ACT_NONE && a->act != NVS_ACT_LRELU && a->act != NVS_ACT_RELU && a->act != NVS_ACT_SIGMOID)
     return NVS_ERR_UNSUPPORTED;
   if (a->dst_mode == 3 && (a->cout != 3 || a->act != NVS_ACT_NONE)) return NVS_ERR_ARG;
+  if (a->act == NVS_ACT_SIGMOID && a->cout > 4) return NVS_ERR_UNSUPPORTED;  // single-channel depth outputs only
   tc::Plan* pl = reinterpret_cast<tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   const int cpad = nvs_conv_tc_cout_pad(a->cout);
   const int cin = a->c0 + a->c1;

@@ -53,15 +53,26 @@ class KP2DtinyFrontend(object):
 
     @torch.no_grad()
     def run_batch(self, imgs: torch.Tensor, normalized: bool = False):
-        """imgs (B,3,H,W) in [0,1] (or already in [-1,1] if ``normalized``) on any device.
+        """imgs (B,3,H,W) in [0,1] (or already in [-1,1] if ``normalized``), or uint8 (B,H,W,3) camera frames,
+        on any device.
 
         Returns (sel, post): ``sel`` = dict(pts, desc, score, cell, label, count) device tensors from
         ops.select_keypoints, ``post`` = the post_processing dict (vlad, seg argmax, dense maps).
         """
         x = imgs.to(self.device, non_blocking=True)
-        if not normalized:
-            x = x.sub(0.5).mul(2.0)  # frontend.py:79
-        _, _, H, W = x.shape
+        if x.dtype == torch.uint8:
+            # camera frames (B,H,W,3) uint8: /255, resize to new_size and (x-0.5)*2 happen on the device, fused
+            # into the first conv's load stage when no resize is needed (visual_odometry.py:281-291)
+            B, Hi, Wi, _ = x.shape
+            if self.new_size is not None and tuple(self.new_size) != (Hi, Wi):
+                x = ops.preprocess_u8(x, self.new_size)
+                H, W = x.shape[2:]
+            else:
+                H, W = Hi, Wi
+        else:
+            if not normalized:
+                x = x.sub(0.5).mul(2.0)  # frontend.py:79
+            _, _, H, W = x.shape
         out = self.net.forward(x)
         post = self.net.post_processing(out, H, W)
         seg_cells = post["seg"] if self.apply_semantic_filer else None
@@ -135,8 +146,12 @@ class KP2DtinyFrontend(object):
             e.synchronize()
             yield h
 
-    def run(self, img: torch.Tensor):
-        """Reference signature (frontend.py:78-129): img (3,H,W) in [0,1] -> (pts (n,2), desc (n,D), seg)."""
+    def run(self, img):
+        """Reference signature (frontend.py:78-129): img (3,H,W) in [0,1] -> (pts (n,2), desc (n,D), seg).
+        Also accepts the raw camera frame, uint8 (H,W,3) numpy array or tensor (what VisualOdometry.process_image
+        receives, visual_odometry.py:281): conversion, resize to ``new_size`` and normalisation then run on the GPU."""
+        if isinstance(img, np.ndarray):
+            img = torch.from_numpy(np.ascontiguousarray(img))
         sel, post = self.run_batch(img.unsqueeze(0))
         n = int(sel["count"][0])
         pts = sel["pts"][0, :n].cpu().numpy()

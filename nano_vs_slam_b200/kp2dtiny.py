@@ -514,23 +514,37 @@ class _KP2DTinyBase(nn.Module):
         if self.training is not False:
             raise NanovsError("nano_vs_slam_b200 is inference only: call model.eval() and set model.training = False "
                               "as the reference callers do (eval_multitask.py:195-196, frontend.py:56-58)")
-        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
+        u8 = isinstance(x, torch.Tensor) and x.dtype == torch.uint8
+        if u8:
+            # camera frames as they come off the decoder: uint8 (B,H,W,3).  /255 and (x-0.5)*2 (visual_odometry.py:283,
+            # frontend.py:79) are applied by the stem kernel's load stage (tensor-core backend) or by
+            # nvs_preprocess_u8 (FFMA backend); the reference model itself only ever sees the fp32 tensor.
+            if x.dim() != 4 or x.shape[3] != 3:
+                raise ValueError("uint8 input must be shaped (B,H,W,3)")
+        elif not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected a (B,3,H,W) tensor")
         if not x.is_cuda:
             raise NanovsError("input must be a CUDA tensor: the sm_100a kernels are the only implementation")
-        B, _, H, W = x.shape
+        B, H, W = (x.shape[0], x.shape[1], x.shape[2]) if u8 else (x.shape[0], x.shape[2], x.shape[3])
         hs, ws = (H // 2, W // 2) if self.downsample == 2 else (H // 2 // 2, W // 2 // 2)  # skip-level map
         if hs % 4 != 0 or ws % 4 != 0:
             # the reference fails in torch.cat when pool/pixel-shuffle sizes disagree
             raise RuntimeError(f"input {H}x{W}: the skip-level map {hs}x{ws} must have sides that are multiples "
                                "of 4 (pixel-shuffle/skip concat sizes would differ, as in the reference)")
+        if u8:
+            x = x.contiguous()
+            return x if self.conv_backend == "tc" else ops.preprocess_u8(x)
         return x.contiguous().float()
 
     @torch.no_grad()
     def forward(self, x):
-        """Returns {'score','coord','feat','vlad','seg'} like kp2dtiny.py:552-591 / :906-957."""
+        """Returns {'score','coord','feat','vlad','seg'} like kp2dtiny.py:552-591 / :906-957.
+        ``x``: (B,3,H,W) fp32 in [-1,1] as in the reference, or uint8 (B,H,W,3) camera frames."""
         x = self._check_input(x)
-        B, _, H, W = x.shape
+        if x.dtype == torch.uint8:
+            B, H, W, _ = x.shape
+        else:
+            B, _, H, W = x.shape
         self._ensure_packed(x.device)
         key = (B, H, W, x.device)
         plan = self._plans.get(key)
@@ -546,6 +560,7 @@ class _KP2DTinyBase(nn.Module):
             for a in slots:
                 a.dst = outs[name].data_ptr()
         plan.in_args.src0 = x.data_ptr()
+        plan.in_args.in_mode = ops.IN_U8_HWC if x.dtype == torch.uint8 else ops.IN_PLAIN
         run_conv = ops.run_conv
         prof = plan.profile
         for i, st in enumerate(plan.steps):
@@ -574,7 +589,7 @@ class _KP2DTinyBase(nn.Module):
         # set the kernels' function attributes) the whole sequence is captured once into a CUDA graph with static
         # input/output buffers and replayed; results are copied out so callers still own fresh tensors.
         use_graph = (self.cuda_graph_max_batch > 0 and plan.B <= self.cuda_graph_max_batch and plan.profile is None
-                     and plan.runs > 2)
+                     and plan.runs > 2 and x.dtype != torch.uint8)  # (the captured graph reads the fp32 staging buffer)
         if use_graph:
             if plan.graph is None:
                 plan.graph_x = torch.empty_like(x)

@@ -12,7 +12,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMOID_TANH, ACT_TANH,  # noqa: F401
-                    IN_PLAIN, IN_S2D, OUT_BOTH, OUT_PLAIN, OUT_POOL, OUT_SHUFFLE, NvsConvArgs, check, lib)
+                    IN_PLAIN, IN_S2D, IN_U8_HWC, OUT_BOTH, OUT_PLAIN, OUT_POOL, OUT_SHUFFLE, NvsConvArgs, check, lib)
 
 
 # number of libnanovs kernels launched by this process (bench.py reports it as "gpu_launches")
@@ -239,6 +239,23 @@ def netvlad(x, w_assign, centroids, out=None, workspace=None):
     check(lib().nvs_netvlad(x.data_ptr(), w_assign.data_ptr(), centroids.data_ptr(), out.data_ptr(),
                             workspace.data_ptr(), workspace.numel(), B, Cc, K, S, _stream()), "nvs_netvlad")
     LAUNCHES[0] += 2
+    return out
+
+
+def preprocess_u8(img: torch.Tensor, size=None, out=None) -> torch.Tensor:
+    """uint8 HWC camera frames (B,H,W,3) [or (H,W,3)] on the device -> fp32 (B,3,H',W') in [-1,1]:
+    /255, optional bilinear resize to ``size`` = (H',W') (kornia resize == F.interpolate(bilinear,
+    align_corners=False)), (x - 0.5) * 2   (visual_odometry.py:281-291, frontend.py:79)."""
+    if img.dim() == 3:
+        img = img.unsqueeze(0)
+    if not (img.is_cuda and img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3):
+        raise NanovsError("preprocess_u8 expects a CUDA uint8 tensor shaped (B,H,W,3)")
+    img = img.contiguous()
+    B, H, W, _ = img.shape
+    Ho, Wo = (H, W) if size is None else (int(size[0]), int(size[1]))
+    out = torch.empty(B, 3, Ho, Wo, device=img.device, dtype=torch.float32) if out is None else out
+    check(lib().nvs_preprocess_u8(img.data_ptr(), out.data_ptr(), B, H, W, Ho, Wo, _stream()), "nvs_preprocess_u8")
+    LAUNCHES[0] += 1
     return out
 
 

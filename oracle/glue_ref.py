@@ -132,3 +132,17 @@ def merge_shard_topk(D_parts: Sequence[torch.Tensor], I_parts: Sequence[torch.Te
     I = torch.cat(list(I_parts), dim=1)
     dv, pos = torch.topk(D, k, dim=1, largest=False, sorted=True)
     return dv, torch.gather(I, 1, pos)
+
+
+def preprocess_u8(img_hwc_u8: np.ndarray, new_size=None):
+    """Input side of the VO loop as the reference does it on the host (visual_odometry.py:281-291, frontend.py:79):
+    kornia.image_to_tensor(image).float() / 255 -> kornia.geometry.transform.resize(size=new_size) (bilinear,
+    align_corners=None -> False, no antialias: a thin wrapper over F.interpolate; kornia is not installed here,
+    so this line of the restatement is UNPINNED) -> sub(0.5).mul(2).  Returns (3,H',W') float32."""
+    import torch
+    import torch.nn.functional as F
+
+    t = torch.from_numpy(np.ascontiguousarray(img_hwc_u8)).permute(2, 0, 1).float() / 255.0
+    if new_size is not None:
+        t = F.interpolate(t.unsqueeze(0), size=tuple(new_size), mode="bilinear", align_corners=False)[0]
+    return t.sub(0.5).mul(2.0).numpy()

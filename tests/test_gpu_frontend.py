@@ -76,3 +76,52 @@ def test_bf_feature_matcher_wrapper():
     mm = BfFeatureMatcher(cross_check=True)
     j1, j2, _ = mm.match(z["des1"], z["des2"])
     assert sorted(zip(j1, j2)) == sorted(map(tuple, z["cross"].tolist()))
+
+
+@pytest.mark.parametrize("size", [None, (96, 128), (120, 176), (33, 57)])
+def test_preprocess_u8_matches_oracle(size):
+    """uint8 HWC frame -> /255 -> bilinear resize -> (x-0.5)*2 (visual_odometry.py:281-291, frontend.py:79)."""
+    from oracle import glue_ref
+    from nano_vs_slam_b200 import ops
+
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(2, 75, 101, 3), dtype=np.uint8)
+    out = ops.preprocess_u8(torch.from_numpy(img).cuda(), size).cpu().numpy()
+    for b in range(2):
+        ref = glue_ref.preprocess_u8(img[b], size)
+        assert out[b].shape == ref.shape
+        assert np.abs(out[b] - ref).max() <= (0.0 if size is None else 2e-6), np.abs(out[b] - ref).max()
+
+
+def test_uint8_frames_through_model_and_frontend():
+    """uint8 camera frames: fused into the stem kernel's load stage (tensor-core backend), nvs_preprocess_u8 on the
+    FFMA backend; both equal the fp32 path fed with the host-side conversion of the reference."""
+    from oracle import glue_ref
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    H, W = 120, 160
+    fe, _ = _frontend(0.45, 150)
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, size=(3, H, W, 3), dtype=np.uint8)
+    x32 = torch.from_numpy(np.stack([glue_ref.preprocess_u8(f) for f in img])).cuda()
+    ref = fe.net(x32)
+    for backend in ("tc", "ffma"):
+        fe.net.conv_backend = backend
+        fe.net._invalidate()
+        ref = fe.net(x32)
+        got = fe.net(torch.from_numpy(img).cuda())
+        for k in ("score", "coord", "feat", "vlad", "seg"):
+            assert float((got[k] - ref[k]).abs().max()) <= 2e-5 * float(ref[k].abs().max()), (backend, k)
+    fe.net.conv_backend = "tc"
+    fe.net._invalidate()
+    # front-end: raw frame in, same keypoints as the reference-shaped call with the [0,1] tensor
+    img01 = torch.from_numpy(img[0]).permute(2, 0, 1).float() / 255.0
+    p0, d0, _ = fe.run(img01)
+    p1, d1, _ = fe.run(img[0])
+    assert p0.shape == p1.shape and np.abs(np.sort(p0, 0) - np.sort(p1, 0)).max() < 1e-3
+    # with new_size the resize happens on the device as well
+    fe.new_size = (96, 128)
+    p2, d2, _ = fe.run(img[0])
+    x_small = torch.from_numpy(glue_ref.preprocess_u8(img[0], (96, 128))).add(1).div(2)
+    p3, d3, _ = fe.run(x_small)
+    assert p2.shape == p3.shape and np.abs(np.sort(p2, 0) - np.sort(p3, 0)).max() < 1e-2
