@@ -43,3 +43,49 @@ class BfFeatureMatcher(object):
         i1, i2, dd, cnt = self.match_device(des1, des2, ratio_test)
         n = int(cnt)
         return i1[:n].cpu().tolist(), i2[:n].cpu().tolist(), dd[:n].cpu().tolist()
+
+
+@torch.no_grad()
+def match_selected(sel: dict, i: int, j: int, cross_check: bool = True, ratio_test: float = kRatioTest):
+    """Match the keypoints of frames ``i`` and ``j`` of ONE ``ops.select_keypoints`` result without leaving the
+    device, and bring the matched coordinates back in a single D2H copy.
+
+    This is the data flow of ``compute_homography`` / ``compute_matching_score`` (evaluation/descriptor.py:221-229:
+    select_k_best -> BFMatcher(crossCheck=True).match -> keypoints[matches]) and of the VO loop
+    (visual_odometry.py:314-322: BfFeatureMatcher.match -> kps[idx]) with the per-pair host round trips removed.
+    Returns numpy (m,2), (m,2), (m,): matched points of frame i, of frame j, descriptor distances."""
+    ni, nj = int(sel["count"][i]), int(sel["count"][j])
+    if ni == 0 or nj == 0:
+        z = np.zeros((0, 2), np.float32)
+        return z, z.copy(), np.zeros((0,), np.float32)
+    i1, i2, dd, cnt = ops.match(sel["desc"][i, :ni].contiguous(), sel["desc"][j, :nj].contiguous(), ratio=ratio_test,
+                                mode=1 if cross_check else 0)
+    # one packed tensor = one D2H: rows [x_i, y_i, x_j, y_j, dist], then the count in the last row
+    m = i1.shape[0]
+    packed = torch.empty(m + 1, 5, device=i1.device, dtype=torch.float32)
+    valid = torch.arange(m, device=i1.device) < cnt.reshape(-1)[0]  # entries past the count are unspecified
+    z = torch.zeros_like(i1)
+    packed[:m, 0:2] = sel["pts"][i][torch.where(valid, i1, z).long()]
+    packed[:m, 2:4] = sel["pts"][j][torch.where(valid, i2, z).long()]
+    packed[:m, 4] = dd
+    packed[m] = cnt.to(torch.float32)
+    host = packed.cpu().numpy()
+    n = int(host[m, 0])
+    return host[:n, 0:2].copy(), host[:n, 2:4].copy(), host[:n, 4].copy()
+
+
+@torch.no_grad()
+def lightglue_inputs(sel: dict, i: int, j: int, image_size):
+    """LightGlue hand-off (visual_odometry.py:207-227, 236-249): keypoints divided by (W, H), descriptors and the
+    image size as batch-1 device tensors, built from a select_keypoints result without a host round trip.
+    ``image_size`` = (H, W) as ``new_size`` in the reference."""
+    H, W = image_size
+    dev = sel["pts"].device
+    scale = torch.tensor([W, H], dtype=torch.float32, device=dev).unsqueeze(0)
+    size = torch.tensor([[W, H]], dtype=torch.float32, device=dev)
+    out = {}
+    for tag, f in (("0", i), ("1", j)):
+        n = int(sel["count"][f])
+        out["image" + tag] = {"keypoints": (sel["pts"][f, :n] / scale).unsqueeze(0),
+                              "descriptors": sel["desc"][f, :n].unsqueeze(0), "image_size": size}
+    return out

@@ -125,3 +125,29 @@ def test_uint8_frames_through_model_and_frontend():
     x_small = torch.from_numpy(glue_ref.preprocess_u8(img[0], (96, 128))).add(1).div(2)
     p3, d3, _ = fe.run(x_small)
     assert p2.shape == p3.shape and np.abs(np.sort(p2, 0) - np.sort(p3, 0)).max() < 1e-2
+
+
+def test_match_selected_pair_on_device():
+    """HPatches / VO pair flow (descriptor.py:221-229): top-k per frame, mutual-NN, matched coordinates, one D2H."""
+    from oracle import glue_ref
+    from nano_vs_slam_b200.matcher import lightglue_inputs, match_selected
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    H, W = 120, 160
+    fe, _ = _frontend(0.0, 200)  # threshold 0: pure select_k_best
+    x = synthetic_frames(1, H, W, 11)
+    x2 = torch.roll(x, shifts=(2, 3), dims=(2, 3)) + 0.01 * torch.randn(x.shape, generator=torch.Generator().manual_seed(1))
+    sel, _ = fe.run_batch(torch.cat([x, x2]).cuda(), normalized=True)
+    pa, pb, dist = match_selected(sel, 0, 1, cross_check=True)
+    n0, n1 = int(sel["count"][0]), int(sel["count"][1])
+    d0, d1 = sel["desc"][0, :n0].cpu().numpy(), sel["desc"][1, :n1].cpu().numpy()
+    ri, rj, rd = glue_ref.mutual_nn(d0, d1)
+    assert len(pa) == len(ri) > 10
+    p0, p1 = sel["pts"][0].cpu().numpy(), sel["pts"][1].cpu().numpy()
+    got = {(tuple(np.round(a, 3)), tuple(np.round(b, 3))) for a, b in zip(pa, pb)}
+    ref = {(tuple(np.round(p0[i], 3)), tuple(np.round(p1[j], 3))) for i, j in zip(ri, rj)}
+    assert got == ref
+    assert abs(float(np.sort(dist)[0]) - float(np.sort(rd)[0])) < 1e-5
+    lg = lightglue_inputs(sel, 0, 1, (H, W))
+    assert lg["image0"]["keypoints"].shape == (1, n0, 2) and lg["image1"]["descriptors"].shape == (1, n1, 32)
+    assert float(lg["image0"]["keypoints"].max()) <= 1.0 and lg["image0"]["image_size"].tolist() == [[W, H]]
