@@ -119,9 +119,37 @@ class _TaskHead(nn.Module):  # modules/decoders/heads.py:7-35
         self.convDb = nn.Conv2d(c_hidden, c_out, 3, 1, 1)
 
 
-class _UpscaleHead(nn.Module):  # modules/decoders/heads.py:38-104
-    def __init__(self, c0, c1, c2, c3, c4, c5, bn_momentum):
+class _TransposedConvUp(nn.Module):  # modules/base.py:80-117 (to_mcu upsampling; parameter holder)
+    def __init__(self, c, bn_momentum=0.1):
         super().__init__()
+        self.transposed_conv = nn.ConvTranspose2d(c, c // 4, kernel_size=3, stride=2, padding=1, output_padding=1,
+                                                  bias=False)
+        self.bn = nn.BatchNorm2d(c // 4, momentum=bn_momentum)
+
+    def equivalent_conv(self, eps: float = 1e-5):
+        """(weight (c, c, 3, 3), bias (c,)) of the 3x3 / pad-1 conv whose PixelShuffle(2) equals this layer with the
+        BatchNorm folded in.  Stride-2 / k=3 / p=1 / op=1 transposed conv: out[2y+i, 2x+j] sums in[y+dy, x+dx] *
+        W[k(i,dy), k(j,dx)] with k(0,0) = 1, k(1,0) = 2, k(1,1) = 0 (even outputs have a single tap); the 2x2
+        footprint sits at rows/cols 1..2 of a centred 3x3 kernel, output channel co*4 + 2i + j is sub-pixel (i, j)."""
+        W = self.transposed_conv.weight.detach().to(torch.float64)  # (cin, c/4, 3, 3)
+        cin, c4 = W.shape[:2]
+        bn = self.bn
+        sc = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + eps)
+        sh = bn.bias.detach().double() - bn.running_mean.detach().double() * sc
+        W3 = torch.zeros(c4 * 4, cin, 3, 3, dtype=torch.float64, device=W.device)
+        kmap = {(0, 0): 1, (1, 0): 2, (1, 1): 0}
+        rows = torch.arange(c4, device=W.device) * 4
+        for (i, dy), ky in kmap.items():
+            for (j, dx), kx in kmap.items():
+                W3[rows + 2 * i + j, :, 1 + dy, 1 + dx] = (W[:, :, ky, kx] * sc.view(1, -1)).t()
+        return W3.to(torch.float32), sh.repeat_interleave(4).to(torch.float32)
+
+
+class _UpscaleHead(nn.Module):  # modules/decoders/heads.py:38-104
+    def __init__(self, c0, c1, c2, c3, c4, c5, bn_momentum, upscale_method="pixelshuffle"):
+        super().__init__()
+        if upscale_method == "convtranspose":  # defined first in the reference (heads.py:53-56): state_dict order
+            self.upsample = _TransposedConvUp(c2, bn_momentum)
         self.convA = _ConvBnAct(c0, c1, bn_momentum)
         self.convB = nn.Conv2d(c1, c2, 3, 1, 1)
         self.confAa = _ConvBnAct(c3, c4, bn_momentum)
@@ -174,7 +202,8 @@ class _AttModule(nn.Module):  # modules/segformer.py:209-220
 class _SegHead(nn.Module):
     """The four segmentation heads (modules/decoders/segmentation.py:8,169,350,478) as one holder."""
 
-    def __init__(self, c_in, c_hidden, c_exp, c_out, d1, bn_momentum, attention, n_feat=None, depth=False):
+    def __init__(self, c_in, c_hidden, c_exp, c_out, d1, bn_momentum, attention, n_feat=None, depth=False,
+                 upscale_method="pixelshuffle"):
         super().__init__()
         fused = n_feat is not None  # V3: seg + feat from one trunk
         self.dim_split = c_hidden // 2
@@ -196,6 +225,9 @@ class _SegHead(nn.Module):
             self.featB = nn.Conv2d(self.dim_split, n_feat, 3, 1, 1)
         if self.depth:
             self.featD = nn.Conv2d(self.dim_split, 1, 3, 1, 1, bias=False)  # segmentation.py:284-287
+        if upscale_method == "convtranspose":  # segmentation.py:116-118, 295-297, 432-434, 569-571
+            self.upsample = _TransposedConvUp(d1, bn_momentum)
+            self.upsample2 = _TransposedConvUp(d1, bn_momentum)
 
     def freeze(self, except_last_layer=False):  # segmentation.py:159-166
         for p in self.parameters():
@@ -354,8 +386,8 @@ class _KP2DTinyBase(nn.Module):
         self._plans: Dict = {}
         if self.downsample not in (2, 3):
             raise NotImplementedError("downsample must be 2 (cell 4) or 3 (cell 8, letter F)")
-        if self.upscale_method != "pixelshuffle":
-            raise NotImplementedError("upscale_method='convtranspose' (to_mcu) is MCU-export only (SURVEY §2 #2)")
+        if self.upscale_method not in ("pixelshuffle", "convtranspose"):
+            raise NotImplementedError("Upscale method not implemented")  # heads.py:58, segmentation.py:120
         if self.use_attention and self.channel_dims[4] // 4 not in (12, 16):
             raise NotImplementedError("attention seg head: head_dim 12 / 16 only (letters S_A, N_A); the large "
                                       "attention letters D (V2) and D_A (V3) are listed under SURVEY §8(f)")
@@ -470,7 +502,17 @@ class _KP2DTinyBase(nn.Module):
             "pw": self._pk_conv(g[1].net[1]), "m3": self._pk_conv(g[3]), "heads": f.heads,
         }
 
+    def _pk_up(self, m: "_TransposedConvUp", tc: bool):
+        """to_mcu upsampling layer as its equivalent 3x3 conv (+ PixelShuffle epilogue), BatchNorm folded."""
+        w3, b3 = m.equivalent_conv()
+        if tc:
+            return ops.pack_conv_tc(w3, bias=b3, cin_segments=[(w3.shape[1], _p32(w3.shape[1]))])
+        return ops.pack_conv(w3, bias=b3)
+
     def _pack_seg(self, P: dict, sh: "_SegHead", pre: str, tc: bool):
+        if self.upscale_method == "convtranspose":
+            P[pre + ".up1"] = self._pk_up(sh.upsample, tc)
+            P[pre + ".up2"] = self._pk_up(sh.upsample2, tc)
         c1_, c2_, c3_, c4_, c5_, d1_ = self.channel_dims
         n_convs = len(sh.convs)
         for i, m in enumerate(sh.convs):
@@ -736,11 +778,22 @@ class _KP2DTinyBase(nn.Module):
             pl.conv(P[pre + ".3"], s2, c5, act=act, dst=sp3)
             nxt = 4
         ps1 = pl.buf("ps1" + tag, d1 // 4, H4, W4)
-        pl.conv(P[f"{pre}.{nxt}"], sp3, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps1)
+        mcu = self.upscale_method == "convtranspose"  # to_mcu: conv -> [transposed conv + BN + act] instead of a shuffle
+        if mcu:
+            u1 = pl.buf("u1" + tag, d1, H8, W8)
+            pl.conv(P[f"{pre}.{nxt}"], sp3, d1, act=act, dst=u1)
+            pl.conv(P[pre + ".up1"], u1, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps1)
+        else:
+            pl.conv(P[f"{pre}.{nxt}"], sp3, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps1)
         s5 = pl.buf("s5" + tag, c5, H4, W4)
         pl.conv(P[f"{pre}.{nxt + 1}"], ps1, c5, act=act, src1=xb, dst=s5)
         ps2 = pl.buf("ps2" + tag, d1 // 4, H2, W2)
-        pl.conv(P[f"{pre}.{nxt + 2}"], s5, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps2)
+        if mcu:
+            u2 = pl.buf("u2" + tag, d1, H4, W4)
+            pl.conv(P[f"{pre}.{nxt + 2}"], s5, d1, act=act, dst=u2)
+            pl.conv(P[pre + ".up2"], u2, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps2)
+        else:
+            pl.conv(P[f"{pre}.{nxt + 2}"], s5, d1, act=act, out_mode=ops.OUT_SHUFFLE, dst=ps2)
         s7 = pl.buf("s7" + tag, head.c_last, H2, W2)
         pl.conv(P[f"{pre}.{nxt + 3}"], ps2, head.c_last, act=act, src1=skip, dst=s7)
         return s7, P[f"{pre}.{nxt + 4}"]
@@ -831,11 +884,22 @@ class _KP2DTinyBase(nn.Module):
             pl.tc(P[pre + ".3"], s2, c5p, act=act, dst=sp3)
             nxt = 4
         ps1 = pl.buf_nhwc("ps1" + tag, qp, H4, W4)
-        pl.tc(P[f"{pre}.{nxt}"], sp3, d1p, act=act, dst=ps1, dst_mode=2)
+        mcu = self.upscale_method == "convtranspose"
+        if mcu:
+            u1 = pl.buf_nhwc("u1" + tag, d1p, H8, W8)
+            pl.tc(P[f"{pre}.{nxt}"], sp3, d1p, act=act, dst=u1)
+            pl.tc(P[pre + ".up1"], u1, d1p, act=act, dst=ps1, dst_mode=2)
+        else:
+            pl.tc(P[f"{pre}.{nxt}"], sp3, d1p, act=act, dst=ps1, dst_mode=2)
         s5 = pl.buf_nhwc("s5" + tag, c5p, H4, W4)
         pl.tc(P[f"{pre}.{nxt + 1}"], ps1, c5p, act=act, src1=xb, dst=s5)
         ps2 = pl.buf_nhwc("ps2" + tag, qp, H2, W2)
-        pl.tc(P[f"{pre}.{nxt + 2}"], s5, d1p, act=act, dst=ps2, dst_mode=2)
+        if mcu:
+            u2 = pl.buf_nhwc("u2" + tag, d1p, H4, W4)
+            pl.tc(P[f"{pre}.{nxt + 2}"], s5, d1p, act=act, dst=u2)
+            pl.tc(P[pre + ".up2"], u2, d1p, act=act, dst=ps2, dst_mode=2)
+        else:
+            pl.tc(P[f"{pre}.{nxt + 2}"], s5, d1p, act=act, dst=ps2, dst_mode=2)
         clp = _p32(head.c_last)
         s7 = pl.buf_nhwc("s7" + tag, clp, H2, W2)
         pl.tc(P[f"{pre}.{nxt + 3}"], ps2, clp, act=act, src1=skip, dst=s7)
@@ -921,10 +985,12 @@ class KP2DTinyV2(_KP2DTinyBase):
         self.backbone = _BackBone(3, c1, c2, c3, c4, bn_momentum)
         self.score_head = _TaskHead(c4, c4, 1, bn_momentum)
         self.loc_head = _TaskHead(c4, c4, 2, bn_momentum)
-        self.desc_head = _UpscaleHead(c4, c4, c3 * 4, c3 + c4, c4, nfeatures, bn_momentum)
-        self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention)
+        self.desc_head = _UpscaleHead(c4, c4, c3 * 4, c3 + c4, c4, nfeatures, bn_momentum, upscale_method)
+        self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention,
+                                 upscale_method=upscale_method)
         if depth:  # a second segmentation head with one output channel (kp2dtiny.py:402-437)
-            self.depth_head = _SegHead(c4, c5, c4 + c3, 1, d1, bn_momentum, use_attention)
+            self.depth_head = _SegHead(c4, c5, c4 + c3, 1, d1, bn_momentum, use_attention,
+                                       upscale_method=upscale_method)
         self.vlad_head = _VPRHead(c4, self.encoder_dim, num_clusters, bn_momentum, remove_netvlad,
                                   global_descriptor_method)
         self._finish_init()
@@ -947,6 +1013,8 @@ class KP2DTinyV2(_KP2DTinyBase):
         P["desc.B"] = self._pk_conv(d.convB, tc=tc)
         P["desc.Aa"] = self._pk_block(d.confAa, tc=tc, seg=[self.channel_dims[2], self.channel_dims[3]])
         P["desc.Bb"] = self._pk_conv(d.confBb, tc=tc)
+        if self.upscale_method == "convtranspose":
+            P["desc.up"] = self._pk_up(d.upsample, tc)
 
     def _plan_heads(self, pl, xb, skip, act):
         P = self._packed
@@ -966,7 +1034,12 @@ class KP2DTinyV2(_KP2DTinyBase):
         da = pl.buf("da", c4, H4, W4)
         pl.conv(P["desc.A"], xb, c4, act=act, dst=da)
         dps = pl.buf("dps", c3, H2, W2)
-        pl.conv(P["desc.B"], da, 4 * c3, out_mode=ops.OUT_SHUFFLE, dst=dps)
+        if self.upscale_method == "convtranspose":
+            db = pl.buf("db", 4 * c3, H4, W4)
+            pl.conv(P["desc.B"], da, 4 * c3, dst=db)
+            pl.conv(P["desc.up"], db, 4 * c3, act=act, out_mode=ops.OUT_SHUFFLE, dst=dps)
+        else:
+            pl.conv(P["desc.B"], da, 4 * c3, out_mode=ops.OUT_SHUFFLE, dst=dps)
         dA = pl.buf("dA", c4, H2, W2)
         pl.conv(P["desc.Aa"], dps, c4, act=act, src1=skip, dst=dA)
         pl.conv(P["desc.Bb"], dA, self.nfeatures, dst=torch.empty(B, self.nfeatures, H2, W2, device=pl.device),
@@ -993,7 +1066,12 @@ class KP2DTinyV2(_KP2DTinyBase):
         da = pl.buf_nhwc("da", c4p, H4, W4)
         pl.tc(P["desc.A"], xb, c4p, act=act, dst=da)
         dps = pl.buf_nhwc("dps", c3p, H2, W2)
-        pl.tc(P["desc.B"], da, 4 * c3p, dst=dps, dst_mode=2)
+        if self.upscale_method == "convtranspose":
+            db = pl.buf_nhwc("db", _p32(4 * c3), H4, W4)
+            pl.tc(P["desc.B"], da, _p32(4 * c3), dst=db)
+            pl.tc(P["desc.up"], db, 4 * c3p, act=act, dst=dps, dst_mode=2)
+        else:
+            pl.tc(P["desc.B"], da, 4 * c3p, dst=dps, dst_mode=2)
         dA = pl.buf_nhwc("dA", c4p, H2, W2)
         pl.tc(P["desc.Aa"], dps, c4p, act=act, src1=skip, dst=dA)
         pl.tc(P["desc.Bb"], dA, self.nfeatures, dst=None, dst_layout=1, dst_c_total=self.nfeatures, out_name="feat")
@@ -1032,7 +1110,7 @@ class KP2DTinyV3(_KP2DTinyBase):
         self.backbone = _BackBone(3, c1, c2, c3, c4, 0.1)
         self.score_loc_head = _TaskHead(c4, c4, 3, bn_momentum)
         self.seg_head = _SegHead(c4, c5, c4 + c3, nClasses, d1, bn_momentum, use_attention, n_feat=nfeatures,
-                                 depth=depth)
+                                 depth=depth, upscale_method=upscale_method)
         self.vlad_head = _VPRHead(c4, self.encoder_dim, num_clusters, bn_momentum, remove_netvlad,
                                   global_descriptor_method)
         self._finish_init()

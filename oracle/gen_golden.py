@@ -48,6 +48,11 @@ CASES = [
     ("v2_S_depth", "S", False, 19, 1, 40, 56, 1248, 14),
     ("v3_N_depth", "N", True, 28, 2, 40, 56, 1249, 15),
     ("v3_S_A_depth", "S_A", True, 19, 1, 32, 48, 1250, 16),
+    # to_mcu=True: ConvTranspose upsampling + ReLU (kp2dtiny.py:271-274).  KEEP THESE LAST: the reference's
+    # get_config mutates its shared config dicts, every later model of the same letter would be an MCU model too.
+    ("v2_S_mcu", "S", False, 19, 1, 40, 56, 1251, 17),
+    ("v3_N_mcu", "N", True, 28, 1, 40, 56, 1252, 18),
+    ("v2_S_A_mcu", "S_A", False, 19, 1, 32, 48, 1253, 19),
 ]
 
 
@@ -57,7 +62,9 @@ def load_reference():
     sys.dont_write_bytecode = True
     from src.kp2dtiny.models.kp2dtiny import KP2DTinyV2, KP2DTinyV3, get_config, tiny_factory  # type: ignore
 
-    def factory(letter, n_classes, v3=False, depth=False):
+    def factory(letter, n_classes, v3=False, depth=False, to_mcu=False):
+        if to_mcu:
+            return tiny_factory(letter, n_classes, to_mcu=True, v3=v3)
         if not depth:
             return tiny_factory(letter, n_classes, v3=v3)
         cls = KP2DTinyV3 if v3 else KP2DTinyV2  # the callers' form: Cls(**get_config(...), nClasses=n, depth=True)
@@ -66,9 +73,9 @@ def load_reference():
     return factory
 
 
-def run_reference(tiny_factory, letter, v3, n_classes, B, H, W, wseed, xseed, depth=False):
+def run_reference(tiny_factory, letter, v3, n_classes, B, H, W, wseed, xseed, depth=False, to_mcu=False):
     with contextlib.redirect_stdout(io.StringIO()):
-        m = tiny_factory(letter, n_classes, v3=v3, depth=depth)
+        m = tiny_factory(letter, n_classes, v3=v3, depth=depth, to_mcu=to_mcu)
     sd = spread_init(m.state_dict(), wseed)
     m.load_state_dict(sd, strict=True)
     m.eval()
@@ -86,11 +93,13 @@ def main():
     gold = os.path.join(REPO, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     for name, letter, v3, ncls, B, H, W, wseed, xseed in CASES:
-        depth = name.endswith("_depth")
-        fwd, post = run_reference(tiny_factory, letter, v3, ncls, B, H, W, wseed, xseed, depth=depth)
+        depth, mcu = name.endswith("_depth"), name.endswith("_mcu")
+        fwd, post = run_reference(tiny_factory, letter, v3, ncls, B, H, W, wseed, xseed, depth=depth, to_mcu=mcu)
         arrs = {"meta": np.array([int(v3), ncls, B, H, W, wseed, xseed], dtype=np.int64)}
         if depth:
             arrs["depth"] = np.array(1)
+        if mcu:
+            arrs["to_mcu"] = np.array(1)
         arrs["letter"] = np.array(letter)
         for k, v in fwd.items():
             arrs["fwd_" + k] = v.numpy()

@@ -31,16 +31,31 @@ class Arch:
     downsample: int = 2
     global_descriptor_method: str = "netvlad"  # "gem" / "convap": letters GEM_*, CONVAP_* (kp2dtiny.py:64-82, 135-144)
     depth: bool = False  # constructor kwarg depth=True (kp2dtiny.py:315,402-437; segmentation.py:189-191,284-287)
+    upscale_method: str = "pixelshuffle"  # "convtranspose" with to_mcu=True, which also sets leaky_relu=False (:271-274)
 
     @property
     def cell(self) -> int:
         return 2 ** self.downsample  # kp2dtiny.py:455
 
 
-def arch_for(letter: str, v3: bool, n_classes: int, depth: bool = False) -> Arch:
+def arch_for(letter: str, v3: bool, n_classes: int, depth: bool = False, to_mcu: bool = False) -> Arch:
     import dataclasses
 
-    return dataclasses.replace(_arch_for(letter, v3, n_classes), depth=depth)
+    a = dataclasses.replace(_arch_for(letter, v3, n_classes), depth=depth)
+    if to_mcu:  # get_config(to_mcu=True), kp2dtiny.py:271-274
+        a = dataclasses.replace(a, upscale_method="convtranspose", leaky_relu=False)
+    return a
+
+
+def upsample(x: Tensor, sd: SD, p: str, a: Arch) -> Tensor:
+    """PixelShuffle(2), or TransposedConvUpsampleModel (modules/base.py:80-117): ConvTranspose2d(c, c/4, 3, stride 2,
+    padding 1, output_padding 1, no bias) -> BN(eval) -> LeakyReLU | ReLU."""
+    if a.upscale_method == "pixelshuffle":
+        return F.pixel_shuffle(x, 2)
+    y = F.conv_transpose2d(x, sd[p + ".transposed_conv.weight"], None, stride=2, padding=1, output_padding=1)
+    y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"],
+                     sd[p + ".bn.bias"], training=False, eps=1e-5)
+    return F.leaky_relu(y, 0.01) if a.leaky_relu else F.relu(y)
 
 
 def _arch_for(letter: str, v3: bool, n_classes: int) -> Arch:
@@ -118,7 +133,7 @@ def upscale_head(x: Tensor, skip: Tensor, sd: SD, a: Arch) -> Tensor:
     p = "desc_head"
     y = conv_bn_act(x, sd, p + ".convA", a.leaky_relu)
     y = conv_bias(y, sd, p + ".convB")
-    y = F.pixel_shuffle(y, 2)
+    y = upsample(y, sd, p + ".upsample", a)
     y = torch.cat([y, skip], dim=1)
     y = conv_bn_act(y, sd, p + ".confAa", a.leaky_relu)
     return conv_bias(y, sd, p + ".confBb")
@@ -187,10 +202,10 @@ def seg_trunk(x: Tensor, skip: Tensor, sd: SD, a: Arch, head: str = "seg_head") 
         s = conv_bn_act(s, sd, p + "3", lk)
         nxt = 4
     s = conv_bn_act(s, sd, p + str(nxt), lk)  # -> d1
-    s = torch.cat([F.pixel_shuffle(s, 2), x], dim=1)
+    s = torch.cat([upsample(s, sd, head + ".upsample", a), x], dim=1)
     s = conv_bn_act(s, sd, p + str(nxt + 1), lk)
     s = conv_bn_act(s, sd, p + str(nxt + 2), lk)  # -> d1
-    s = torch.cat([F.pixel_shuffle(s, 2), skip], dim=1)
+    s = torch.cat([upsample(s, sd, head + ".upsample2", a), skip], dim=1)
     return conv_bn_act(s, sd, p + str(nxt + 3), lk)
 
 

@@ -12,11 +12,11 @@ from util import POST_FEAT_TOL_TC, REL_TOL, golden_cases, load_golden, rel_err, 
 pytestmark = pytest.mark.gpu
 
 
-def _model(letter, n_classes, v3, wseed, backend=None, depth=False):
+def _model(letter, n_classes, v3, wseed, backend=None, depth=False, to_mcu=False):
     from nano_vs_slam_b200.synthetic import spread_init
     from util import build_model
 
-    m = build_model(letter, n_classes, v3, depth)
+    m = build_model(letter, n_classes, v3, depth, to_mcu)
     if backend is not None:
         m.conv_backend = backend  # "tc" (tcgen05 3xTF32, default for S letters) or "ffma" (exact fp32)
     sd = spread_init(m.state_dict(), wseed)
@@ -32,7 +32,7 @@ def test_model_matches_reference_golden(path):
     from nano_vs_slam_b200.synthetic import synthetic_frames
 
     c = load_golden(path)
-    m, _ = _model(c["letter"], c["n_classes"], c["v3"], c["wseed"], depth=c["depth"])
+    m, _ = _model(c["letter"], c["n_classes"], c["v3"], c["wseed"], depth=c["depth"], to_mcu=c["to_mcu"])
     x = synthetic_frames(c["B"], c["H"], c["W"], c["xseed"]).cuda()
     out = m(x)
     assert ("depth" in out) == c["depth"]

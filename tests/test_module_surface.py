@@ -81,6 +81,32 @@ def test_state_dict_keys_equal_reference_with_depth(letter, v3):
         assert tuple(sd[k].shape) == tuple(rsd[k].shape), k
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="live reference not present")
+@pytest.mark.parametrize("letter,v3", [("S", False), ("N_A", False), ("N", True), ("S_A", True)])
+def test_state_dict_keys_equal_reference_to_mcu(letter, v3):
+    """to_mcu=True: ConvTranspose upsampling modules appear (desc_head.upsample first, seg_head.upsample{,2} last)."""
+    import copy
+
+    sys.path[:0] = [REF, os.path.join(REF, "src")]
+    sys.dont_write_bytecode = True
+    from src.kp2dtiny.models import kp2dtiny as ref  # type: ignore
+    from nano_vs_slam_b200 import tiny_factory
+
+    saved = copy.deepcopy((ref.KP2DTINY_CONFIGS, ref.KP2DTINYV3_CONFIGS))
+    try:  # the reference's get_config mutates its shared dicts (kp2dtiny.py:271-274): restore them afterwards
+        rsd = _quiet(ref.tiny_factory, letter, 19, to_mcu=True, v3=v3).state_dict()
+    finally:
+        for dst, src in zip((ref.KP2DTINY_CONFIGS, ref.KP2DTINYV3_CONFIGS), saved):
+            dst.clear()
+            dst.update(src)
+    ours = _quiet(tiny_factory, letter, 19, to_mcu=True, v3=v3)
+    assert ours.upscale_method == "convtranspose" and ours.leaky_relu is False
+    sd = ours.state_dict()
+    assert list(sd.keys()) == list(rsd.keys())
+    for k in rsd:
+        assert tuple(sd[k].shape) == tuple(rsd[k].shape), k
+
+
 def test_load_state_dict_invalidates_packed_weights():
     from nano_vs_slam_b200 import tiny_factory
     from nano_vs_slam_b200.synthetic import spread_init

@@ -20,14 +20,14 @@ def _state_dict_for(case):
     # key names + shapes come from the product module tree (must equal the reference's)
     from util import build_model
 
-    m = build_model(case["letter"], case["n_classes"], case["v3"], case["depth"])
+    m = build_model(case["letter"], case["n_classes"], case["v3"], case["depth"], case["to_mcu"])
     return spread_init(m.state_dict(), case["wseed"])
 
 
 @pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[6:-4])
 def test_oracle_matches_reference_golden(path):
     c = load_golden(path)
-    a = R.arch_for(c["letter"], c["v3"], c["n_classes"], depth=c["depth"])
+    a = R.arch_for(c["letter"], c["v3"], c["n_classes"], depth=c["depth"], to_mcu=c["to_mcu"])
     sd = _state_dict_for(c)
     x = synthetic_frames(c["B"], c["H"], c["W"], c["xseed"])
     out = R.forward(x, sd, a)

@@ -41,14 +41,14 @@ def load_golden(path):
     fwd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("fwd_")}
     post = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("post_")}
     return dict(letter=letter, v3=bool(v3), n_classes=ncls, B=B, H=H, W=W, wseed=wseed, xseed=xseed,
-                fwd=fwd, post=post, depth="depth" in z.files)
+                fwd=fwd, post=post, depth="depth" in z.files, to_mcu="to_mcu" in z.files)
 
 
 def argmax_agreement(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.cpu() == b.cpu()).float().mean())
 
 
-def build_model(letter, n_classes, v3=False, depth=False):
+def build_model(letter, n_classes, v3=False, depth=False, to_mcu=False):
     """tiny_factory, or the callers' explicit form when depth=True (Cls(**get_config(...), nClasses=n, depth=True))."""
     import contextlib
     import io
@@ -56,6 +56,8 @@ def build_model(letter, n_classes, v3=False, depth=False):
     from nano_vs_slam_b200 import KP2DTinyV2, KP2DTinyV3, get_config, tiny_factory
 
     with contextlib.redirect_stdout(io.StringIO()):
+        if to_mcu:
+            return tiny_factory(letter, n_classes, to_mcu=True, v3=v3)
         if not depth:
             return tiny_factory(letter, n_classes, v3=v3)
         return (KP2DTinyV3 if v3 else KP2DTinyV2)(**get_config(letter, v3=v3), nClasses=n_classes, depth=True)
