@@ -8,24 +8,25 @@
 // limits instead: every thread owns TWO queries (K/V rows are warp-broadcast LDS.128, so two queries halve the
 // shared-memory instructions per FMA) and all multiply-adds are packed FFMA2 (fma.rn.f32x2, two fp32 FMAs per
 // issue slot on sm_100) so the FMA pipe, not the issue port, is the bound; exp2 with pre-scaled logits.
+// The large letters (D, D_A: C = 256, head_dim 64) use the same kernel with one query per thread and 64-key
+// blocks (the query and output rows alone are 128 registers).
 #include "common.cuh"
 
 namespace nvs {
 
 constexpr int ATT_THREADS = 128;              // threads per CTA
-constexpr int ATT_QPT = 2;                    // queries per thread
-constexpr int ATT_QPB = ATT_THREADS * ATT_QPT;  // queries per CTA
-constexpr int ATT_KB = 256;                   // keys staged per block
 constexpr int ATT_G = 8;                      // keys per online-softmax group
 
-template <int D>
+// ATT_QPT queries per thread, ATT_KB keys staged per block
+template <int D, int ATT_QPT, int ATT_KB>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __restrict__ q,
                                                                 const float* __restrict__ kv,
                                                                 float* __restrict__ out, int C, int Nq,
                                                                 int Nk, float scale_log2e) {
-  constexpr int DP = 20;  // row pitch: 16-byte aligned rows, 4-way (not 16-way) conflicts on the fill
+  constexpr int ATT_QPB = ATT_THREADS * ATT_QPT;  // queries per CTA
+  constexpr int DP = D + 4;  // row pitch: 16-byte aligned rows, 4-way (not 16-way) conflicts on the fill
   constexpr int H = D / 2;
-  static_assert(D <= 16 && D % 4 == 0, "head_dim 12 or 16");
+  static_assert(D % 4 == 0 && 2 * ATT_KB * DP * 4 <= 48 * 1024, "head_dim multiple of 4; K/V block fits static smem");
   __shared__ __align__(16) float ks[ATT_KB][DP];
   __shared__ __align__(16) float vs[ATT_KB][DP];
   const int head = blockIdx.y, b = blockIdx.z;
@@ -138,11 +139,13 @@ extern "C" int nvs_attention(const float* q, const float* kv, float* out, int32_
   if (C % heads != 0 || B > 65535) return NVS_ERR_ARG;
   const int d = C / heads;
   const float scale_log2e = (float)(1.0 / sqrt((double)d) * 1.4426950408889634);
-  dim3 grid((Nq + ATT_QPB - 1) / ATT_QPB, heads, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int qpb = ATT_THREADS * (d <= 16 ? 2 : 1);
+  dim3 grid((Nq + qpb - 1) / qpb, heads, B);
   switch (d) {
-    case 16: attention_kernel<16><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
-    case 12: attention_kernel<12><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
+    case 16: attention_kernel<16, 2, 256><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
+    case 12: attention_kernel<12, 2, 256><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
+    case 64: attention_kernel<64, 1, 64><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
     default: return NVS_ERR_UNSUPPORTED;
   }
   NVS_CHECK_LAUNCH();

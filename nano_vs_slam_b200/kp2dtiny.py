@@ -388,9 +388,8 @@ class _KP2DTinyBase(nn.Module):
             raise NotImplementedError("downsample must be 2 (cell 4) or 3 (cell 8, letter F)")
         if self.upscale_method not in ("pixelshuffle", "convtranspose"):
             raise NotImplementedError("Upscale method not implemented")  # heads.py:58, segmentation.py:120
-        if self.use_attention and self.channel_dims[4] // 4 not in (12, 16):
-            raise NotImplementedError("attention seg head: head_dim 12 / 16 only (letters S_A, N_A); the large "
-                                      "attention letters D (V2) and D_A (V3) are listed under SURVEY §8(f)")
+        if self.use_attention and self.channel_dims[4] // 4 not in (12, 16, 64):
+            raise NotImplementedError("attention seg head: head_dim 12 / 16 / 64 (letters S_A, N_A, D, D_A)")
         self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
         # conv backend: "tc" = tcgen05 3xTF32 implicit GEMM on channels-last maps (needs 32-channel multiples:
         # the S letters), "ffma" = exact fp32 direct conv (any channel count: the N letters).

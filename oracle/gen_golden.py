@@ -42,6 +42,9 @@ CASES = [
     ("v3_CONVAP_S_A", "CONVAP_S_A", True, 28, 2, 40, 56, 1245, 11),
     # the large letter without attention (LARGE_D_V3: 64..512 channels, 128-d descriptors, ConvAP)
     ("v3_D", "D", True, 19, 1, 40, 56, 1246, 12),
+    # the large attention letters (head_dim 64): V2 "D" and V3 "D_A"
+    ("v2_D", "D", False, 19, 1, 32, 48, 1254, 20),
+    ("v3_D_A", "D_A", True, 19, 1, 32, 48, 1255, 21),
     # cell 8 (TINY_F: downsample = 3, 16..256 channels, 64-d descriptors): skip-level map = H/4 must be a multiple of 4
     ("v2_F", "F", False, 19, 1, 64, 96, 1247, 13),
     # depth=True constructor kwarg: V2 second segmentation head (kp2dtiny.py:402-437), V3 middle slice + featD

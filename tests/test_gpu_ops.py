@@ -124,7 +124,8 @@ def test_small_ops():
     assert rel_err(y, F.conv2d(x, w, b, padding=1, groups=64)) < 1e-5
 
 
-@pytest.mark.parametrize("C,h,w", [(64, 16, 20), (48, 10, 14), (64, 5, 7), (64, 30, 40)])
+@pytest.mark.parametrize("C,h,w", [(64, 16, 20), (48, 10, 14), (64, 5, 7), (64, 30, 40),
+                                   (256, 12, 18), (256, 30, 40)])  # head_dim 64: letters D / D_A
 def test_attention(C, h, w):
     ops = _ops()
     g = torch.Generator().manual_seed(C + h)

@@ -35,8 +35,7 @@ def test_config_tables_and_factory():
     assert sum(p.numel() for p in _quiet(tiny_factory, "S", 28).parameters()) == 928079  # V2-S
     info = m.gather_info()
     assert info["netvlad_dim"] == 3072 and info["total_params"] == 404639
-    with pytest.raises(NotImplementedError):  # attention with head_dim 64: SURVEY §8(f)
-        _quiet(tiny_factory, "D", 28)
+    assert _quiet(tiny_factory, "D", 28).get_global_desc_dim() == 128 * 16  # ConvAP, attention head_dim 64
     f = _quiet(tiny_factory, "F", 28)  # cell 8
     assert f.cell == 8 and f.encoder_dim == 128 and f.get_global_desc_dim() == 64 * 128
     assert _quiet(tiny_factory, "GEM_N", 28).get_global_desc_dim() == 48 * 16        # vpr.py:72
@@ -47,7 +46,7 @@ def test_config_tables_and_factory():
 @pytest.mark.skipif(not os.path.isdir(REF), reason="live reference not present")
 @pytest.mark.parametrize("letter,v3", [(l, v) for v in (False, True) for l in ("S", "S_A", "N", "N_A")] +
                          [("GEM_N", False), ("GEM_S_A", False), ("CONVAP_S_A", False), ("CONVAP_S_A", True), ("D", True),
-                          ("F", False)])
+                          ("D", False), ("D_A", True), ("F", False)])
 def test_state_dict_keys_equal_reference(letter, v3):
     sys.path[:0] = [REF, os.path.join(REF, "src")]
     sys.dont_write_bytecode = True
