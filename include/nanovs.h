@@ -122,6 +122,9 @@ typedef struct NvsConvTcArgs {
                     bit 1: c0 == 16, c1 == 0, cout <= 32 only -- w_hi / w_lo are given in the paired-tap layout
                     [5][cout_pad][32], K row of step t = [tap 2t ch 0-15 | tap 2t+1 ch 0-15], tenth tap zero:
                     a tile then takes 5 pipeline steps instead of 9 */
+  int32_t c0_real, c1_real; /* 0, or the number of leading channels of the c0 / c1 window that can be non-zero (the
+                    rest is zero padding with zero weights, e.g. 24 real channels in a 32-channel row for the N
+                    letters): MMA k-steps that would only multiply padding are skipped */
 } NvsConvTcArgs;
 int32_t nvs_conv_tc_cout_pad(int32_t cout);
 int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout);

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libnanovs.so")
+# NVS_LIB_PATH: load another build of the same library (A/B timing of kernel variants, debug builds)
+LIB_PATH = os.environ.get("NVS_LIB_PATH") or os.path.join(HERE, "lib", "libnanovs.so")
 
 NVS_OK = 0
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SIGMOID_TANH, ACT_GELU = range(7)
@@ -41,6 +42,7 @@ class NvsConvTcArgs(C.Structure):
         ("dst_c_total", _i32), ("dst_c_off", _i32), ("dst_layout", _i32), ("dst_mode", _i32),
         ("pool_c_total", _i32), ("pool_c_off", _i32),
         ("B", _i32), ("H", _i32), ("W", _i32), ("cout", _i32), ("act", _i32), ("flags", _i32),
+        ("c0_real", _i32), ("c1_real", _i32),
     ]
 
 

@@ -102,7 +102,8 @@ struct Params {
   int pool_c_total, pool_c_off;
   int B, H, W, cout, act;
   int tiles_x, tiles_y, n_tiles;
-  int issuers;     // 2 (default) or 1: a single MMA issuer gives a fixed fp32 accumulation order (bit-reproducible)
+  int nk_last0, nk_last1;  // MMA k-steps (8 channels each) in the LAST chunk of source 0 / 1: skips all-padding k-steps
+  int issuers;     // MMA-issuing threads; 1 gives a fixed fp32 accumulation order (bit-reproducible)
   long long* dbg;  // optional timeline dump of CTA 0 (NVS_TC_DEBUG builds only)
   int knock;       // NVS_TC_DEBUG builds: stage knock-out bits for bottleneck experiments (results are then garbage)
 };
@@ -527,11 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS);
         const uint32_t a_hi = a0 + (uint32_t)(sl * C::A_COLS), a_lo = a_hi + KC;
         const uint64_t w_hi = wdesc0 + (uint64_t)((sl * C::W_STAGE) >> 4), w_lo = w_hi + (uint64_t)(C::W_BYTES >> 4);
-        if (NVS_KNOCK(1)) {
-          if (ks == 0) mbar_arrive(astart(acc));
-        } else
-#pragma unroll
-        for (int k = 0; k < C::KSTEPS; ++k) {
+        auto issue_kstep = [&](int k) {
           // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
           const uint64_t o = (uint64_t)(2 * k);
           if (C::CONCAT) {
@@ -544,6 +541,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_lo + o, C::IDESC, 1u);
           }
+        };
+        // k-steps of this chunk that can be non-zero: the last chunk of a zero-padded source (N letters: 24 real
+        // channels in a 32-channel row ...) skips its all-padding k-steps.  The full chunk is the straight-line
+        // common path: the issuing thread's instruction count per MMA is what this kernel is most sensitive to.
+        int nk = C::KSTEPS;
+        if (p.nk_last0 != C::KSTEPS || p.nk_last1 != C::KSTEPS) {
+          const int chk = ks / C::TAPS;
+          nk = chk == p.c0_chunks - 1 ? p.nk_last0 : (chk == chunks - 1 ? p.nk_last1 : C::KSTEPS);
+        }
+        if (NVS_KNOCK(1)) {
+          if (ks == 0) mbar_arrive(astart(acc));
+        } else if (nk == C::KSTEPS) {
+#pragma unroll
+          for (int k = 0; k < C::KSTEPS; ++k) issue_kstep(k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < C::KSTEPS; ++k)
+            if (k < nk) issue_kstep(k);
         }
 #ifdef NVS_TC_DEBUG
         const long long c2 = clock64();
@@ -818,6 +833,20 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
       if (default_issuers < 1 || default_issuers > tc::MAX_ISSUERS) default_issuers = tc::MAX_ISSUERS;
     }
     p.issuers = (a->flags & 1) ? 1 : default_issuers;
+  }
+  {
+    // real channels of the last chunk of each source -> k-steps worth issuing (paired-tap rows interleave two taps:
+    // all four k-steps carry data)
+    const int ksteps = (pair ? 32 : kc) / 8;
+    auto last_nk = [&](int c, int real) {
+      if (pair || real <= 0 || real >= c) return ksteps;
+      const int in_last = real - (c / kc - 1) * kc;  // real channels that fall into the last chunk
+      if (in_last <= 0) return ksteps;               // (a whole chunk of padding is not expected; keep it exact)
+      return (in_last + 7) / 8;
+    };
+    p.nk_last0 = last_nk(a->c0, a->c0_real);
+    p.nk_last1 = a->c1 > 0 ? last_nk(a->c1, a->c1_real) : ksteps;
+    if (a->c1 == 0) p.nk_last1 = p.nk_last0;  // single source: its last chunk is the last chunk
   }
   p.dbg = nullptr;
   p.knock = 0;

@@ -447,6 +447,8 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
     lo = ((lo.view(torch.int32) + 0x1000) & -8192).view(torch.float32).contiguous()
     bp = torch.zeros(cpad, dtype=torch.float32, device=w.device)
     bp[:cout] = b
+    # (real, padded) channels per source: lets the kernel skip MMA k-steps that only see zero weights
+    hi.nvs_segments = list(cin_segments) if cin_segments is not None else None
     return hi, lo, bp
 
 
@@ -519,6 +521,12 @@ class TcConv(object):
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
         a.flags = (1 if deterministic else 0) | (2 if paired else 0)
+        segs = getattr(hi, "nvs_segments", None)
+        a.c0_real = a.c1_real = 0
+        if segs is not None and len(segs) == (2 if src1 is not None else 1) and not paired:
+            if segs[0][1] == a.c0 and (src1 is None or segs[1][1] == a.c1):
+                a.c0_real = segs[0][0]
+                a.c1_real = segs[1][0] if src1 is not None else 0
         if dst is not None:
             if dst_mode == 1 and dst_layout == 0:
                 assert tuple(dst.shape[:3]) == (B, H, W)
