@@ -1,13 +1,13 @@
 #!/bin/bash
-# Build the library with conv_tc.cu taken from a git revision: tools/libnanovs_<name>.so (A/B timing on one box:
-# NVS_LIB_PATH=tools/libnanovs_<name>.so python bench.py ...).  usage: tools/build_variant.sh <name> <git-rev>
+# Build the library with one kernel file (default conv_tc.cu) taken from a git revision: tools/libnanovs_<name>.so (A/B timing on one box:
+# NVS_LIB_PATH=tools/libnanovs_<name>.so python bench.py ...).  usage: tools/build_variant.sh <name> <git-rev> [file.cu]
 set -e
 cd "$(dirname "$0")/.."
-name=$1; rev=$2
+name=$1; rev=$2; file=${3:-conv_tc.cu}
 d=/tmp/nvs_variant_$name; rm -rf $d; mkdir -p $d/pkg/csrc $d/include
 cp include/*.h $d/include/
 cp nano_vs_slam_b200/csrc/* $d/pkg/csrc/
-git show $rev:nano_vs_slam_b200/csrc/conv_tc.cu > $d/pkg/csrc/conv_tc.cu
+git show $rev:nano_vs_slam_b200/csrc/$file > $d/pkg/csrc/$file
 OBJS=""
 for f in $d/pkg/csrc/*.cu; do
   o=$d/$(basename ${f%.cu}).o
