@@ -476,6 +476,25 @@ class _KP2DTinyBase(nn.Module):
             return ops.pack_conv_tc(m.conv.weight, bn=bn, eps=m.bn.eps, cin_segments=self._segs(m.conv, seg))
         return ops.pack_conv(m.conv.weight, bn=bn, eps=m.bn.eps)
 
+    def _pk_block_pair(self, ma: _ConvBnAct, mb: _ConvBnAct):
+        """Two conv+BN blocks that read the SAME input as ONE tensor-core conv with their output channels side by
+        side (each padded to a multiple of 32): the kernel's cost per pipeline step is nearly flat in N up to 128
+        (DESIGN 5.1), so 64 -> 2x64 costs ~1.4x one 64 -> 64 conv instead of 2x."""
+        ws, bs = [], []
+        for m in (ma, mb):
+            bn = {"weight": m.bn.weight, "bias": m.bn.bias, "running_mean": m.bn.running_mean,
+                  "running_var": m.bn.running_var}
+            w, b = ops._fold(m.conv.weight, None, bn, m.bn.eps)
+            cp = _p32(w.shape[0])
+            ws.append(torch.cat([w, w.new_zeros(cp - w.shape[0], *w.shape[1:])], 0))
+            bs.append(torch.cat([b, b.new_zeros(cp - b.shape[0])], 0))
+        return ops.pack_conv_tc(torch.cat(ws, 0), bias=torch.cat(bs, 0), cin_segments=self._segs(ma.conv, None))
+
+    def _merge_head_convs(self) -> bool:
+        """The first convs of the heads all read the backbone output: pair them up when two fit one 128-wide conv."""
+        c4p = _p32(self.channel_dims[3])
+        return self.conv_backend == "tc" and 2 * c4p <= 128 and _p32(self.encoder_dim) == c4p
+
     def _pk_conv(self, m: nn.Conv2d, s2d=False, tc: bool = False, seg=None):
         if tc:
             return ops.pack_conv_tc(m.weight, bias=m.bias, cin_segments=self._segs(m, seg))
@@ -848,10 +867,13 @@ class _KP2DTinyBase(nn.Module):
         # ---- VPR head ----
         enc = self.encoder_dim
         encp = _p32(enc)
-        v1 = pl.buf_nhwc("v1", encp, H4, W4)
-        pl.tc(P["vlad.convlad1"], xb, encp, act=act, dst=v1)
         v2 = pl.buf_nhwc("v2", encp, H4, W4)
-        pl.tc(P["vlad.convlad2"], v1, encp, act=act, dst=v2)
+        if "v1_in_dva" in pl.bufs:  # convlad1 ran merged with a head conv (see _plan_heads_tc): channels [encp, 2*encp)
+            pl.tc(P["vlad.convlad2"], pl.bufs["v1_in_dva"], encp, c0_off=encp, c0=encp, act=act, dst=v2)
+        else:
+            v1 = pl.buf_nhwc("v1", encp, H4, W4)
+            pl.tc(P["vlad.convlad1"], xb, encp, act=act, dst=v1)
+            pl.tc(P["vlad.convlad2"], v1, encp, act=act, dst=v2)
         v3 = pl.buf("v3", enc, H4, W4)  # NCHW, real channels, for the NetVLAD kernel
         pl.tc(P["vlad.convlad3"], v2, enc, act=act, dst=v3, dst_layout=1)
         self._plan_aggregator(pl, P, v3, B, enc, H4, W4)
@@ -998,8 +1020,12 @@ class KP2DTinyV2(_KP2DTinyBase):
         tc = self.conv_backend == "tc"
         if self.depth:
             self._pack_seg(P, self.depth_head, "dep", tc)
-        P["score.a"] = self._pk_block(self.score_head.convDa, tc=tc)
-        P["loc.a"] = self._pk_block(self.loc_head.convDa, tc=tc)
+        if self._merge_head_convs():
+            P["kp.a"] = self._pk_block_pair(self.score_head.convDa, self.loc_head.convDa)
+            P["dv.a"] = self._pk_block_pair(self.desc_head.convA, self.vlad_head.convlad1)
+        else:
+            P["score.a"] = self._pk_block(self.score_head.convDa, tc=tc)
+            P["loc.a"] = self._pk_block(self.loc_head.convDa, tc=tc)
         if tc:
             P["kp.b"] = ops.pack_head_pair_tc(self.score_head.convDb.weight, self.score_head.convDb.bias,
                                               self.loc_head.convDb.weight, self.loc_head.convDb.bias,
@@ -1008,7 +1034,8 @@ class KP2DTinyV2(_KP2DTinyBase):
             P["score.b"] = self._pk_conv(self.score_head.convDb)
             P["loc.b"] = self._pk_conv(self.loc_head.convDb)
         d = self.desc_head
-        P["desc.A"] = self._pk_block(d.convA, tc=tc)
+        if not self._merge_head_convs():
+            P["desc.A"] = self._pk_block(d.convA, tc=tc)
         P["desc.B"] = self._pk_conv(d.convB, tc=tc)
         P["desc.Aa"] = self._pk_block(d.confAa, tc=tc, seg=[self.channel_dims[2], self.channel_dims[3]])
         P["desc.Bb"] = self._pk_conv(d.confBb, tc=tc)
@@ -1055,22 +1082,35 @@ class KP2DTinyV2(_KP2DTinyBase):
         c3p, c4p = _p32(c3), _p32(c4)
         B, H4, W4, _ = xb.shape
         H2, W2 = skip.shape[1:3]
-        sh = pl.buf_nhwc("sh", c4p, H4, W4)
-        pl.tc(P["score.a"], xb, c4p, act=act, dst=sh)
-        lh = pl.buf_nhwc("lh", c4p, H4, W4)
-        pl.tc(P["loc.a"], xb, c4p, act=act, dst=lh)
+        merged = self._merge_head_convs()
+        if merged:
+            # score.convDa | loc.convDa and desc.convA | vlad.convlad1 as two 2*c4-wide convs of the backbone output
+            kpa = pl.buf_nhwc("kpa", 2 * c4p, H4, W4)
+            pl.tc(P["kp.a"], xb, 2 * c4p, act=act, dst=kpa)
+            sh, lh, sl_off = kpa, kpa, c4p
+            dva = pl.buf_nhwc("dva", 2 * c4p, H4, W4)
+            pl.tc(P["dv.a"], xb, 2 * c4p, act=act, dst=dva)
+            da = dva
+            pl.bufs["v1_in_dva"] = dva  # the VPR head continues from channels [c4p, 2*c4p) of this buffer
+        else:
+            sh = pl.buf_nhwc("sh", c4p, H4, W4)
+            pl.tc(P["score.a"], xb, c4p, act=act, dst=sh)
+            lh = pl.buf_nhwc("lh", c4p, H4, W4)
+            pl.tc(P["loc.a"], xb, c4p, act=act, dst=lh)
+            sl_off = 0
+            da = pl.buf_nhwc("da", c4p, H4, W4)
+            pl.tc(P["desc.A"], xb, c4p, act=act, dst=da)
         # both 1- and 2-channel output convs as one tensor-core launch (block-diagonal weight over [sh | lh]),
         # sigmoid / tanh and the split into the two NCHW outputs happen in its epilogue
-        pl.tc(P["kp.b"], sh, 3, src1=lh, dst=None, dst_mode=3, dst_layout=1, out_name="score", out2_name="coord")
-        da = pl.buf_nhwc("da", c4p, H4, W4)
-        pl.tc(P["desc.A"], xb, c4p, act=act, dst=da)
+        pl.tc(P["kp.b"], sh, 3, src1=lh, c0_off=0, c0=c4p, c1_off=sl_off, c1=c4p, dst=None, dst_mode=3, dst_layout=1,
+              out_name="score", out2_name="coord")
         dps = pl.buf_nhwc("dps", c3p, H2, W2)
         if self.upscale_method == "convtranspose":
             db = pl.buf_nhwc("db", _p32(4 * c3), H4, W4)
-            pl.tc(P["desc.B"], da, _p32(4 * c3), dst=db)
+            pl.tc(P["desc.B"], da, _p32(4 * c3), c0_off=0, c0=c4p, dst=db)
             pl.tc(P["desc.up"], db, 4 * c3p, act=act, dst=dps, dst_mode=2)
         else:
-            pl.tc(P["desc.B"], da, 4 * c3p, dst=dps, dst_mode=2)
+            pl.tc(P["desc.B"], da, 4 * c3p, c0_off=0, c0=c4p, dst=dps, dst_mode=2)
         dA = pl.buf_nhwc("dA", c4p, H2, W2)
         pl.tc(P["desc.Aa"], dps, c4p, act=act, src1=skip, dst=dA)
         pl.tc(P["desc.Bb"], dA, self.nfeatures, dst=None, dst_layout=1, dst_c_total=self.nfeatures, out_name="feat")
@@ -1117,7 +1157,10 @@ class KP2DTinyV3(_KP2DTinyBase):
     def _pack_heads(self, P):
         h = self.score_loc_head
         tc = self.conv_backend == "tc"
-        P["sl.a"] = self._pk_block(h.convDa, tc=tc)
+        if self._merge_head_convs():
+            P["sv.a"] = self._pk_block_pair(h.convDa, self.vlad_head.convlad1)
+        else:
+            P["sl.a"] = self._pk_block(h.convDa, tc=tc)
         # convDb (c4 -> 3) is launched as two tiny convs so that score (ch 0, sigmoid) and shift (ch 1:3, tanh)
         # land directly in their own output tensors (kp2dtiny.py:927-935) without a slicing copy.
         if tc:
@@ -1162,9 +1205,16 @@ class KP2DTinyV3(_KP2DTinyBase):
         P = self._packed
         c4p = _p32(self.channel_dims[3])
         B, H4, W4, _ = xb.shape
-        sl = pl.buf_nhwc("sl", c4p, H4, W4)
-        pl.tc(P["sl.a"], xb, c4p, act=act, dst=sl)
-        pl.tc(P["kp.b"], sl, 3, dst=None, dst_mode=3, dst_layout=1, out_name="score", out2_name="coord")
+        if self._merge_head_convs():  # score_loc_head.convDa | vlad_head.convlad1 as one conv of the backbone output
+            sva = pl.buf_nhwc("sva", 2 * c4p, H4, W4)
+            pl.tc(P["sv.a"], xb, 2 * c4p, act=act, dst=sva)
+            pl.bufs["v1_in_dva"] = sva
+            sl = sva
+        else:
+            sl = pl.buf_nhwc("sl", c4p, H4, W4)
+            pl.tc(P["sl.a"], xb, c4p, act=act, dst=sl)
+        pl.tc(P["kp.b"], sl, 3, c0_off=0, c0=c4p, dst=None, dst_mode=3, dst_layout=1, out_name="score",
+              out2_name="coord")
 
     def _plan_seg_out_tc(self, pl, s7, packed_last):
         B, H2, W2, _ = s7.shape
