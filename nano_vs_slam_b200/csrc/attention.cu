@@ -10,6 +10,8 @@
 // issue slot on sm_100) so the FMA pipe, not the issue port, is the bound; exp2 with pre-scaled logits.
 // The large letters (D, D_A: C = 256, head_dim 64) use the same kernel with one query per thread and 64-key
 // blocks (the query and output rows alone are 128 registers).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nvs {
@@ -140,8 +142,24 @@ extern "C" int nvs_attention(const float* q, const float* kv, float* out, int32_
   const int d = C / heads;
   const float scale_log2e = (float)(1.0 / sqrt((double)d) * 1.4426950408889634);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int qpb = ATT_THREADS * (d <= 16 ? 2 : 1);
+  // queries per thread for head_dim 12 / 16: 4 halves the K/V shared-memory loads per FMA again (+7 % at 32 k
+  // tokens, config 4) but leaves too few CTAs for the small maps (4800 tokens: -2 %)
+  static int qpt_env = -1;
+  if (qpt_env < 0) {
+    const char* e = getenv("NVS_ATT_QPT");
+    qpt_env = e ? atoi(e) : 0;
+    if (qpt_env != 2 && qpt_env != 4) qpt_env = 0;
+  }
+  const int qpt_small = qpt_env ? qpt_env : (Nq >= 16384 ? 4 : 2);
+  const int qpb = ATT_THREADS * (d <= 16 ? qpt_small : 1);
   dim3 grid((Nq + qpb - 1) / qpb, heads, B);
+  if (d <= 16 && qpt_small == 4) {
+    if (d == 16) attention_kernel<16, 4, 256><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e);
+    else if (d == 12) attention_kernel<12, 4, 256><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e);
+    else return NVS_ERR_UNSUPPORTED;
+    NVS_CHECK_LAUNCH();
+    return NVS_OK;
+  }
   switch (d) {
     case 16: attention_kernel<16, 2, 256><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
     case 12: attention_kernel<12, 2, 256><<<grid, ATT_THREADS, 0, st>>>(q, kv, out, C, Nq, Nk, scale_log2e); break;
