@@ -606,7 +606,7 @@ class _KP2DTinyBase(nn.Module):
         else:
             B, _, H, W = x.shape
         self._ensure_packed(x.device)
-        key = (B, H, W, x.device)
+        key = (B, H, W, x.device, x.dtype == torch.uint8)  # uint8 frames: own plan (own CUDA graph + staging buffer)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 4:
@@ -649,7 +649,7 @@ class _KP2DTinyBase(nn.Module):
         # set the kernels' function attributes) the whole sequence is captured once into a CUDA graph with static
         # input/output buffers and replayed; results are copied out so callers still own fresh tensors.
         use_graph = (self.cuda_graph_max_batch > 0 and plan.B <= self.cuda_graph_max_batch and plan.profile is None
-                     and plan.runs > 2 and x.dtype != torch.uint8)  # (the captured graph reads the fp32 staging buffer)
+                     and plan.runs > 2)
         if use_graph:
             if plan.graph is None:
                 plan.graph_x = torch.empty_like(x)
@@ -976,8 +976,10 @@ class _KP2DTinyBase(nn.Module):
     def only_encoder(self, x):
         """L2-normalised VPR encoder map (kp2dtiny.py:515-518, vpr.py:85-86)."""
         x = self._check_input(x)
+        if x.dtype == torch.uint8:
+            x = ops.preprocess_u8(x)
         self.forward(x)
-        plan = self._plans[(x.shape[0], x.shape[2], x.shape[3], x.device)]
+        plan = self._plans[(x.shape[0], x.shape[2], x.shape[3], x.device, False)]
         return ops.l2norm_channels(plan.bufs["v3"])
 
 
