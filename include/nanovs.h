@@ -225,6 +225,17 @@ int nvs_match(const float* des1, const float* des2, int32_t n1, int32_t n2, int3
               int32_t mode, int32_t* out_idx1, int32_t* out_idx2, float* out_dist, int32_t* out_count,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched matcher: P pairs of frames in one call.  des (F, kmax, D): the descriptors of all frames as written by
+ * nvs_select_keypoints (rows >= counts[f] are ignored); counts (F), pair_a / pair_b (P) are DEVICE arrays, so nothing
+ * returns to the host between selection and matching (visual_odometry.py:314-322 matches frame t with t-1;
+ * evaluation/descriptor.py:221-229 matches an image with its warped copy).  mode 0 / 1 as nvs_match.  Outputs are
+ * (P, kmax) with out_count (P); a pair whose train frame has fewer than 2 keypoints yields no match in mode 0. */
+size_t nvs_match_batch_workspace_bytes(int32_t n_pairs, int32_t kmax);
+int nvs_match_batch(const float* des, const int32_t* counts, int32_t n_frames, int32_t kmax, int32_t D,
+                    const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, double ratio, int32_t mode,
+                    int32_t* out_idx1, int32_t* out_idx2, float* out_dist, int32_t* out_count, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ---- exact L2 top-k retrieval = faiss.IndexFlatL2.add / .search (evaluation/global_descriptor.py:55-60) ----
  * add:    nvs_flat_prepare converts the fp32 rows (n,d) to bf16 rows padded to nvs_flat_padded_dim(d)
  *         columns (the tcgen05 GEMM operand) and stores |x|^2 (fp32).  Caller owns all three buffers.

@@ -77,6 +77,9 @@ SIGNATURES = {
                                     _i32, _i32, _i32, _vp]),
     "nvs_match_workspace_bytes": (_sz, [_i32, _i32]),
     "nvs_match": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nvs_match_batch_workspace_bytes": (_sz, [_i32, _i32]),
+    "nvs_match_batch": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _sz,
+                                _vp]),
     "nvs_flat_padded_dim": (_i32, [_i32]),
     "nvs_flat_prepare": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "nvs_flat_search_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),

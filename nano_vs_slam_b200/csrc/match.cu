@@ -16,12 +16,41 @@ namespace nvs {
 constexpr int KNN_T = 128;   // queries per CTA
 constexpr int KNN_TT = 64;   // train rows per shared tile
 
+// Batched form (nvs_match_batch): blockIdx.z = pair; descriptors of all frames live in one (F, kmax, D) tensor and
+// the per-frame keypoint counts stay on the device (no host round trip between selection and matching).
+// counts == nullptr: the single-pair entry points, sizes come from the scalar arguments.
+struct MatchBatch {
+  const int32_t* counts;  // [F] keypoints per frame
+  const int32_t* pa;      // [P] query frame of every pair
+  const int32_t* pb;      // [P] train frame of every pair
+  int kmax;               // rows per frame in the descriptor tensor = pitch of all per-pair arrays
+  int swap;               // 1: roles of a and b exchanged (the reverse 2-NN of the mutual test)
+};
+__device__ __forceinline__ void batch_sizes(const MatchBatch& mb, int pair, int& n1, int& n2, int& fa, int& fb) {
+  fa = mb.pa[pair];
+  fb = mb.pb[pair];
+  if (mb.swap) { const int t = fa; fa = fb; fb = t; }
+  n1 = mb.counts[fa];
+  n2 = mb.counts[fb];
+}
+
 template <int D>
 __global__ void __launch_bounds__(KNN_T) knn2_partial_kernel(const float* __restrict__ des1,
                                                              const float* __restrict__ des2,
                                                              float* __restrict__ pd, int32_t* __restrict__ pi,
-                                                             int n1, int n2, int per_split) {
+                                                             int n1, int n2, int per_split, MatchBatch mb) {
   __shared__ __align__(16) float ts[KNN_TT][D];
+  if (mb.counts) {
+    int fa, fb;
+    batch_sizes(mb, blockIdx.z, n1, n2, fa, fb);
+    if ((int)(blockIdx.x * KNN_T) >= n1) return;  // whole CTA past this pair's queries
+    des1 += (size_t)fa * mb.kmax * D;
+    des2 += (size_t)fb * mb.kmax * D;
+    pd += (size_t)blockIdx.z * gridDim.y * mb.kmax * 2;
+    pi += (size_t)blockIdx.z * gridDim.y * mb.kmax * 2;
+    per_split = (n2 + (int)gridDim.y - 1) / (int)gridDim.y;
+    if (per_split < 1) per_split = 1;
+  }
   const int q = blockIdx.x * KNN_T + threadIdx.x;
   const int split = blockIdx.y;
   const int t_begin = split * per_split, t_end = min(n2, t_begin + per_split);
@@ -59,13 +88,24 @@ __global__ void __launch_bounds__(KNN_T) knn2_partial_kernel(const float* __rest
     }
   }
   if (q < n1) {
-    const size_t o = ((size_t)split * n1 + q) * 2;
+    const size_t o = ((size_t)split * (mb.counts ? mb.kmax : n1) + q) * 2;
     pd[o] = d0; pd[o + 1] = d1; pi[o] = i0; pi[o + 1] = i1;
   }
 }
 
 __global__ void knn2_merge_kernel(const float* __restrict__ pd, const int32_t* __restrict__ pi,
-                                  int32_t* __restrict__ idx, float* __restrict__ dist, int n1, int nsplit) {
+                                  int32_t* __restrict__ idx, float* __restrict__ dist, int n1, int nsplit,
+                                  MatchBatch mb) {
+  int pitch = n1;
+  if (mb.counts) {
+    int n2, fa, fb;
+    batch_sizes(mb, blockIdx.y, n1, n2, fa, fb);
+    pitch = mb.kmax;
+    pd += (size_t)blockIdx.y * nsplit * mb.kmax * 2;
+    pi += (size_t)blockIdx.y * nsplit * mb.kmax * 2;
+    idx += (size_t)blockIdx.y * mb.kmax * 2;
+    dist += (size_t)blockIdx.y * mb.kmax * 2;
+  }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n1) return;
   float d0 = INFINITY, d1 = INFINITY;
@@ -73,8 +113,8 @@ __global__ void knn2_merge_kernel(const float* __restrict__ pd, const int32_t* _
   for (int s = 0; s < nsplit; ++s) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const float d = pd[((size_t)s * n1 + q) * 2 + j];
-      const int i = pi[((size_t)s * n1 + q) * 2 + j];
+      const float d = pd[((size_t)s * pitch + q) * 2 + j];
+      const int i = pi[((size_t)s * pitch + q) * 2 + j];
       if (i < 0) continue;
       if (d < d1) {
         if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = i; }
@@ -120,9 +160,20 @@ __global__ void __launch_bounds__(1024) one_to_one_kernel(const int32_t* __restr
                                                           double ratio, int32_t* first_q,
                                                           int32_t* last_q,
                                                           int32_t* __restrict__ out1, int32_t* __restrict__ out2,
-                                                          float* __restrict__ outd, int32_t* __restrict__ out_count) {
+                                                          float* __restrict__ outd, int32_t* __restrict__ out_count,
+                                                          MatchBatch mb) {
   __shared__ int warp_tot[32];
   const int tid = threadIdx.x;
+  if (mb.counts) {
+    int fa, fb;
+    batch_sizes(mb, blockIdx.x, n1, n2, fa, fb);
+    const size_t o = (size_t)blockIdx.x * mb.kmax;
+    idx += o * 2; dist += o * 2; first_q += o; last_q += o; out1 += o; out2 += o; outd += o; out_count += blockIdx.x;
+    if (n1 < 1 || n2 < 2) {  // knnMatch(k=2) needs two train rows: no matches for this pair
+      if (tid == 0) *out_count = 0;
+      return;
+    }
+  }
   for (int t = tid; t < n2; t += 1024) { first_q[t] = INT_MAX; last_q[t] = -1; }
   __syncthreads();
   for (int q = tid; q < n1; q += 1024) {
@@ -164,9 +215,17 @@ __global__ void __launch_bounds__(1024) mutual_kernel(const int32_t* __restrict_
                                                       const float* __restrict__ dist12,
                                                       const int32_t* __restrict__ idx21, int n1,
                                                       int32_t* __restrict__ out1, int32_t* __restrict__ out2,
-                                                      float* __restrict__ outd, int32_t* __restrict__ out_count) {
+                                                      float* __restrict__ outd, int32_t* __restrict__ out_count,
+                                                      MatchBatch mb) {
   __shared__ int warp_tot[32];
   const int tid = threadIdx.x;
+  if (mb.counts) {
+    int n2, fa, fb;
+    batch_sizes(mb, blockIdx.x, n1, n2, fa, fb);
+    const size_t o = (size_t)blockIdx.x * mb.kmax;
+    idx12 += o * 2; dist12 += o * 2; idx21 += o * 2; out1 += o; out2 += o; outd += o; out_count += blockIdx.x;
+    if (n2 < 1) n1 = 0;
+  }
   int base = 0;
   for (int q0 = 0; q0 < n1; q0 += 1024) {
     const int q = q0 + tid;
@@ -198,14 +257,32 @@ static int run_knn2(const float* des1, const float* des2, int32_t* idx, float* d
   const int ns = knn_splits(n2);
   int per = (n2 + ns - 1) / ns;
   dim3 grid((n1 + KNN_T - 1) / KNN_T, ns);
+  const MatchBatch none{nullptr, nullptr, nullptr, 0, 0};
   switch (D) {
-    case 32: knn2_partial_kernel<32><<<grid, KNN_T, 0, st>>>(des1, des2, pd, pi, n1, n2, per); break;
-    case 64: knn2_partial_kernel<64><<<grid, KNN_T, 0, st>>>(des1, des2, pd, pi, n1, n2, per); break;
-    case 128: knn2_partial_kernel<128><<<grid, KNN_T, 0, st>>>(des1, des2, pd, pi, n1, n2, per); break;
+    case 32: knn2_partial_kernel<32><<<grid, KNN_T, 0, st>>>(des1, des2, pd, pi, n1, n2, per, none); break;
+    case 64: knn2_partial_kernel<64><<<grid, KNN_T, 0, st>>>(des1, des2, pd, pi, n1, n2, per, none); break;
+    case 128: knn2_partial_kernel<128><<<grid, KNN_T, 0, st>>>(des1, des2, pd, pi, n1, n2, per, none); break;
     default: return NVS_ERR_UNSUPPORTED;
   }
   NVS_CHECK_LAUNCH();
-  knn2_merge_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(pd, pi, idx, dist, n1, ns);
+  knn2_merge_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(pd, pi, idx, dist, n1, ns, none);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+// all pairs in one launch each: grid.z / grid.y / grid.x = pair
+static int run_knn2_batch(const float* des, int32_t* idx, float* dist, int D, float* pd, int32_t* pi, int n_pairs,
+                          const MatchBatch& mb, cudaStream_t st) {
+  const int ns = knn_splits(mb.kmax);
+  dim3 grid((mb.kmax + KNN_T - 1) / KNN_T, ns, n_pairs);
+  switch (D) {
+    case 32: knn2_partial_kernel<32><<<grid, KNN_T, 0, st>>>(des, des, pd, pi, 0, 0, 0, mb); break;
+    case 64: knn2_partial_kernel<64><<<grid, KNN_T, 0, st>>>(des, des, pd, pi, 0, 0, 0, mb); break;
+    case 128: knn2_partial_kernel<128><<<grid, KNN_T, 0, st>>>(des, des, pd, pi, 0, 0, 0, mb); break;
+    default: return NVS_ERR_UNSUPPORTED;
+  }
+  NVS_CHECK_LAUNCH();
+  knn2_merge_kernel<<<dim3((mb.kmax + 127) / 128, n_pairs), 128, 0, st>>>(pd, pi, idx, dist, 0, ns, mb);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
@@ -248,11 +325,12 @@ extern "C" int nvs_match(const float* des1, const float* des2, int32_t n1, int32
   if (rc != NVS_OK) return rc;
   if (mode == 0) {
     one_to_one_kernel<<<1, 1024, 0, st>>>(idx12, dist12, n1, n2, ratio, first_q, last_q, out_idx1, out_idx2,
-                                          out_dist, out_count);
+                                          out_dist, out_count, MatchBatch{nullptr, nullptr, nullptr, 0, 0});
   } else if (mode == 1) {
     rc = run_knn2(des2, des1, idx21, dist21, n2, n1, D, pd, pi, st);
     if (rc != NVS_OK) return rc;
-    mutual_kernel<<<1, 1024, 0, st>>>(idx12, dist12, idx21, n1, out_idx1, out_idx2, out_dist, out_count);
+    mutual_kernel<<<1, 1024, 0, st>>>(idx12, dist12, idx21, n1, out_idx1, out_idx2, out_dist, out_count,
+                                      MatchBatch{nullptr, nullptr, nullptr, 0, 0});
   } else if (mode == 2) {
     // raw 2-NN: out_idx1 (n1,2) = idx, out_dist (n1,2) = dist; out_idx2 unused
     cudaError_t e = cudaMemcpyAsync(out_idx1, idx12, (size_t)n1 * 8, cudaMemcpyDeviceToDevice, st);
@@ -261,6 +339,53 @@ extern "C" int nvs_match(const float* des1, const float* des2, int32_t n1, int32
     return NVS_OK;
   } else {
     return NVS_ERR_ARG;
+  }
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
+
+// ---- batched: P pairs of frames out of one (F, kmax, D) descriptor tensor, counts on the device
+// workspace per pair: [partials d][partials i] (16 splits x kmax x 2), [idx12][dist12][idx21][dist21] (kmax x 2),
+// [first_q][last_q] (kmax)
+extern "C" size_t nvs_match_batch_workspace_bytes(int32_t n_pairs, int32_t kmax) {
+  if (n_pairs <= 0 || kmax <= 0) return 0;
+  const size_t per = 2 * (size_t)16 * kmax * 2 * 4 + 4 * (size_t)kmax * 2 * 4 + 2 * (size_t)kmax * 4;
+  return align256(per * n_pairs) + 256;
+}
+
+extern "C" int nvs_match_batch(const float* des, const int32_t* counts, int32_t n_frames, int32_t kmax, int32_t D,
+                               const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, double ratio,
+                               int32_t mode, int32_t* out_idx1, int32_t* out_idx2, float* out_dist,
+                               int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!des || !counts || !pair_a || !pair_b || !out_idx1 || !out_idx2 || !out_dist || !out_count || !workspace)
+    return NVS_ERR_ARG;
+  if (n_frames <= 0 || kmax <= 0 || n_pairs <= 0 || n_pairs > 65535) return NVS_ERR_ARG;
+  if (mode != 0 && mode != 1) return NVS_ERR_ARG;
+  if (workspace_bytes < nvs_match_batch_workspace_bytes(n_pairs, kmax)) return NVS_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t P = (size_t)n_pairs, K = (size_t)kmax;
+  char* w = static_cast<char*>(workspace);
+  float* pd = reinterpret_cast<float*>(w); w += P * 16 * K * 2 * 4;
+  int32_t* pi = reinterpret_cast<int32_t*>(w); w += P * 16 * K * 2 * 4;
+  int32_t* idx12 = reinterpret_cast<int32_t*>(w); w += P * K * 2 * 4;
+  float* dist12 = reinterpret_cast<float*>(w); w += P * K * 2 * 4;
+  int32_t* idx21 = reinterpret_cast<int32_t*>(w); w += P * K * 2 * 4;
+  float* dist21 = reinterpret_cast<float*>(w); w += P * K * 2 * 4;
+  int32_t* first_q = reinterpret_cast<int32_t*>(w); w += P * K * 4;
+  int32_t* last_q = reinterpret_cast<int32_t*>(w);
+  MatchBatch mb{counts, pair_a, pair_b, kmax, 0};
+  int rc = run_knn2_batch(des, idx12, dist12, D, pd, pi, n_pairs, mb, st);
+  if (rc != NVS_OK) return rc;
+  if (mode == 0) {
+    one_to_one_kernel<<<n_pairs, 1024, 0, st>>>(idx12, dist12, 0, 0, ratio, first_q, last_q, out_idx1, out_idx2,
+                                                out_dist, out_count, mb);
+  } else {
+    MatchBatch rev = mb;
+    rev.swap = 1;
+    rc = run_knn2_batch(des, idx21, dist21, D, pd, pi, n_pairs, rev, st);
+    if (rc != NVS_OK) return rc;
+    mutual_kernel<<<n_pairs, 1024, 0, st>>>(idx12, dist12, idx21, 0, out_idx1, out_idx2, out_dist, out_count, mb);
   }
   NVS_CHECK_LAUNCH();
   return NVS_OK;

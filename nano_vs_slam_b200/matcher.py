@@ -89,3 +89,14 @@ def lightglue_inputs(sel: dict, i: int, j: int, image_size):
         out["image" + tag] = {"keypoints": (sel["pts"][f, :n] / scale).unsqueeze(0),
                               "descriptors": sel["desc"][f, :n].unsqueeze(0), "image_size": size}
     return out
+
+
+@torch.no_grad()
+def match_consecutive(sel: dict, cross_check: bool = False, ratio_test: float = kRatioTest):
+    """VO data flow for a batch of consecutive frames (visual_odometry.py:314-322 matches frame t against t-1):
+    every frame i+1 (query) against frame i (train) in ONE batched launch sequence, counts read on the device.
+    Returns device tensors (idx_cur (B-1,k), idx_prev (B-1,k), dist (B-1,k), count (B-1,))."""
+    B = sel["desc"].shape[0]
+    dev = sel["desc"].device
+    a = torch.arange(1, B, device=dev, dtype=torch.int32)
+    return ops.match_batch(sel["desc"], sel["count"], a, a - 1, ratio=ratio_test, mode=1 if cross_check else 0)

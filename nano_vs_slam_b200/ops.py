@@ -388,6 +388,32 @@ def match(des1, des2, ratio: float = 0.7, mode: int = 0):
     return i1, i2, dd, cnt
 
 
+def match_batch(desc: torch.Tensor, counts: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor,
+                ratio: float = 0.7, mode: int = 0, workspace: Optional[torch.Tensor] = None):
+    """All pairs in one call, nothing returns to the host: ``desc`` (F,kmax,D) and ``counts`` (F,) int32 as written
+    by select_keypoints, ``pair_a`` / ``pair_b`` (P,) int32 frame indices on the device.
+    Returns (idx1 (P,kmax), idx2 (P,kmax), dist (P,kmax), count (P,)); rows >= count[p] are unspecified."""
+    desc = _req(desc)
+    F_, kmax, D = desc.shape
+    dev = desc.device
+    counts = counts.to(device=dev, dtype=torch.int32).contiguous()
+    pair_a = pair_a.to(device=dev, dtype=torch.int32).contiguous()
+    pair_b = pair_b.to(device=dev, dtype=torch.int32).contiguous()
+    P = pair_a.numel()
+    nbytes = int(lib().nvs_match_batch_workspace_bytes(P, kmax))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    i1 = torch.empty(P, kmax, device=dev, dtype=torch.int32)
+    i2 = torch.empty(P, kmax, device=dev, dtype=torch.int32)
+    dd = torch.empty(P, kmax, device=dev, dtype=torch.float32)
+    cnt = torch.empty(P, device=dev, dtype=torch.int32)
+    check(lib().nvs_match_batch(desc.data_ptr(), counts.data_ptr(), F_, kmax, D, pair_a.data_ptr(), pair_b.data_ptr(), P,
+                                float(ratio), mode, i1.data_ptr(), i2.data_ptr(), dd.data_ptr(), cnt.data_ptr(),
+                                workspace.data_ptr(), workspace.numel(), _stream()), "nvs_match_batch")
+    LAUNCHES[0] += 3 if mode == 0 else 5
+    return i1, i2, dd, cnt
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor-core conv (csrc/conv_tc.cu): channels-last activations, 3xTF32 weights
 # ----------------------------------------------------------------------------------------------

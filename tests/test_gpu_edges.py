@@ -100,3 +100,28 @@ def test_model_smallest_and_ragged_frames():
                 assert rel_err(out[k], ref[k]) < tol(k, v3), (letter, H, W, k, rel_err(out[k], ref[k]))
         with pytest.raises(RuntimeError):
             m(synthetic_frames(1, 36, 36, 0).cuda())   # floor(H/2) % 4 != 0: the reference fails in torch.cat
+
+
+def test_match_batch_equals_per_pair_calls():
+    """nvs_match_batch (all pairs, device-side counts) against nvs_match pair by pair, incl. empty / tiny frames."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    F_, kmax, D = 6, 300, 32
+    base = F.normalize(torch.randn(kmax, D, generator=g), dim=1)
+    desc = torch.stack([F.normalize(base + 0.15 * f * torch.randn(kmax, D, generator=g), dim=1) for f in range(F_)]).cuda()
+    counts = torch.tensor([300, 257, 1, 0, 129, 300], dtype=torch.int32).cuda()
+    pa = torch.tensor([1, 0, 4, 5, 2, 3, 0], dtype=torch.int32).cuda()
+    pb = torch.tensor([0, 1, 5, 4, 1, 0, 2], dtype=torch.int32).cuda()
+    for mode in (0, 1):
+        i1, i2, dd, cnt = ops.match_batch(desc, counts, pa, pb, ratio=0.8, mode=mode)
+        for p in range(pa.numel()):
+            a, b = int(pa[p]), int(pb[p])
+            n1, n2 = int(counts[a]), int(counts[b])
+            n = int(cnt[p])
+            if n1 < 1 or n2 < (2 if mode == 0 else 1):
+                assert n == 0, (mode, p, n)
+                continue
+            r1, r2, rd, rc = ops.match(desc[a, :n1].contiguous(), desc[b, :n2].contiguous(), ratio=0.8, mode=mode)
+            assert n == int(rc), (mode, p)
+            assert torch.equal(i1[p, :n], r1[:n]) and torch.equal(i2[p, :n], r2[:n]) and torch.equal(dd[p, :n], rd[:n])
