@@ -13,10 +13,13 @@
 //               and write both straight into TENSOR MEMORY with tcgen05.st (lane = pixel, column = channel):
 //               the A operand never returns to shared memory (an earlier version that staged hi/lo in smem
 //               was shared-memory-bandwidth bound).
-//   weights:    packed [tap][Cout][Cin] (hi and lo parts), 3-D TMA box (KC, Cout, 1) per tap into a 6-8 deep
-//               ring, canonical K-major swizzled layout for the UMMA descriptor.
-//   MMA:        one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, K=8) with A from TMEM and B from
-//               shared memory.  An instruction costs max(N/2, ~50) cycles (profiles/microbench/mma_rate.cu), so
+//   weights:    packed [tap][Cout][Cin] (hi and lo parts), 3-D TMA box (KC, Cout, 1) per tap into the slot ring
+//               (4 or 8 slots = weight stage + TMEM A slot), canonical K-major swizzled layout for the UMMA
+//               descriptor.
+//   MMA:        up to four threads (one per issuer warp, steps round-robin) issue tcgen05.mma.cta_group::1.kind::tf32
+//               (M=128, K=8) with A from TMEM and B from shared memory.  From one thread an instruction costs
+//               max(N/2, ~50) cycles (profiles/microbench/mma_rate.cu); in the running kernel ~86 cycles each
+//               whatever N <= 128 is (the measured sustained tensor rate of this pool), so
 //               for Cout <= 64 the two products sharing a_hi are ONE instruction with N = 2*Cout against the
 //               contiguous [W_hi ; W_lo] tile; columns [0,Cout) collect a_hi w_hi + a_lo w_hi, columns
 //               [Cout,2Cout) collect a_hi w_lo and the epilogue adds the halves.
@@ -25,7 +28,7 @@
 //               pixel-shuffled NHWC.
 //
 // Warp roles: 0-3 epilogue (TMEM lane quadrants), CONV_GROUPS x 4 converter warps (groups take pipeline steps
-// round-robin), halo producer warp, weight producer warp, TMEM-allocator + MMA-issuer warp.
+// round-robin), halo producer warp, weight producer warp, MAX_ISSUERS MMA-issuer warps (the first allocates TMEM).
 // Persistent CTAs, static round-robin over (frame, tile_y, tile_x).  Four mbarrier rings: halo boxes
 // (producer <-> converters), weight tiles (producer <-> MMA), TMEM A slots (converters <-> MMA), accumulators
 // (MMA <-> epilogue).

@@ -515,7 +515,7 @@ class TcConv(object):
                  dst_pool: Optional[torch.Tensor] = None, pool_c_off: int = 0,
                  deterministic: Optional[bool] = None):
         """``deterministic``: one MMA-issuing thread instead of two -> fixed fp32 accumulation order, results
-        bit-reproducible run to run (default: env NVS_DETERMINISTIC=1, else the faster two-issuer schedule whose
+        bit-reproducible run to run (default: env NVS_DETERMINISTIC=1, else the faster multi-issuer schedule whose
         last-ulp rounding depends on timing)."""
         import os
         hi, lo, bp = packed

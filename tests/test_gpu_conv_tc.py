@@ -79,7 +79,7 @@ def test_conv_tc_pool_shuffle_concat_slice():
     assert rel_err(pooled.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
     only = torch.zeros_like(pooled)
     ops.TcConv(_nhwc(x).cuda(), packed, 64, act=1, dst=None, dst_mode=0, dst_pool=only).run()
-    assert rel_err(only, pooled) < 2e-6  # two MMA issuers: accumulation order (last ulp) is timing dependent
+    assert rel_err(only, pooled) < 2e-6  # several MMA issuers: accumulation order (last ulp) is timing dependent
     # the single-issuer schedule is bit-reproducible
     d1, d2 = torch.zeros_like(pooled), torch.zeros_like(pooled)
     for d in (d1, d2):

@@ -141,7 +141,7 @@ def test_cuda_graph_replay_matches_eager():
     assert plan.graph is not None
     for e, g in zip(eager, graphed):
         for k in ("score", "coord", "feat", "vlad", "seg"):
-            assert rel_err(g[k], e[k]) < 2e-5, k   # two MMA issuers: run-to-run rounding differences only
+            assert rel_err(g[k], e[k]) < 2e-5, k   # several MMA issuers: run-to-run rounding differences only
     a = m(xs[0])
     b = m(xs[1])
     assert a["feat"].data_ptr() != b["feat"].data_ptr()  # callers own their outputs
