@@ -456,7 +456,8 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
         w = torch.cat(parts, 1)
     cout, cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
-    cpad = int(lib().nvs_conv_tc_cout_pad(cout))
+    # more than 128 output channels: padded to a multiple of 128 and run as several launches (TcConvSplit)
+    cpad = int(lib().nvs_conv_tc_cout_pad(cout)) if cout <= 128 else (cout + 127) // 128 * 128
     assert cpad > 0, cout
     wt = torch.zeros(9, cpad, cin, dtype=torch.float32, device=w.device)
     wt[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
@@ -574,6 +575,41 @@ class TcConv(object):
         check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _ptr(dst2_override), _stream()),
               "nvs_conv_tc_run")
         LAUNCHES[0] += 1
+
+
+class TcConvSplit(object):
+    """A tensor-core conv with more than 128 output channels (letters D / F: 256- and 512-channel layers) as one
+    TcConv per 128-channel slice of the weights: each launch writes its channel range of the shared outputs."""
+
+    def __init__(self, src0: torch.Tensor, packed, cout: int, **kw):
+        hi, lo, bp = packed
+        assert hi.shape[0] == 9, "paired-tap packing is for 32-channel outputs only"
+        mode = kw.get("dst_mode", 1)
+        assert mode in (0, 1, 2), "the keypoint-head split epilogue has 3 output channels"
+        if kw.get("dst") is None and kw.get("dst_c_total") is None and mode != 0:
+            kw["dst_c_total"] = cout // 4 if mode == 2 else cout
+        self.ops = []
+        for j in range((cout + 127) // 128):
+            cj = min(128, cout - 128 * j)
+            hj = hi[:, 128 * j:128 * (j + 1)].contiguous()
+            hj.nvs_segments = getattr(hi, "nvs_segments", None)
+            sub = (hj, lo[:, 128 * j:128 * (j + 1)].contiguous(), bp[128 * j:128 * (j + 1)].contiguous())
+            kj = dict(kw)
+            kj["dst_c_off"] = kw.get("dst_c_off", 0) + (32 if mode == 2 else 128) * j
+            if kw.get("dst_pool") is not None:
+                kj["pool_c_off"] = kw.get("pool_c_off", 0) + 128 * j
+            self.ops.append(TcConv(src0, sub, cj, **kj))
+        self.flops = sum(o.flops for o in self.ops)
+        self.shape = self.ops[0].shape.replace(f"->{min(128, cout)} ", f"->{cout} ") + f" x{len(self.ops)}"
+
+    def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
+        for o in self.ops:
+            o.run(dst_override, dst2_override)
+
+
+def tc_conv(src0: torch.Tensor, packed, cout: int, **kw):
+    """TcConv, or TcConvSplit when the packed weights carry more than 128 (padded) output channels."""
+    return (TcConvSplit if packed[2].numel() > 128 else TcConv)(src0, packed, cout, **kw)
 
 
 def conv_small(src_nhwc: torch.Tensor, packed, act: int = ACT_NONE, out: Optional[torch.Tensor] = None):

@@ -157,3 +157,31 @@ def test_stem_conv_3_to_16_nhwc(H, W, act):
     plain = ops.conv(x.cuda(), wp, bp, 16, act=act)  # NCHW store: the generic tiled kernel
     plain = plain[0] if isinstance(plain, (tuple, list)) else plain
     assert rel_err(plain, ref) < 1e-5
+
+
+def test_conv_tc_more_than_128_output_channels():
+    """Layers wider than 128 channels (letter F: 256) run as one launch per 128-channel weight slice."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    B, H, W, cin, cout = 2, 18, 26, 64, 256
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    assert packed[2].numel() == 256
+    xs = _nhwc(x).cuda()
+    full = torch.zeros(B, H, W, cout, device="cuda")
+    pooled = torch.zeros(B, H // 2, W // 2, cout, device="cuda")
+    op = ops.tc_conv(xs, packed, cout, act=1, dst=full, dst_pool=pooled)
+    assert isinstance(op, ops.TcConvSplit) and len(op.ops) == 2
+    op.run()
+    assert rel_err(full.permute(0, 3, 1, 2), ref) < 2e-5
+    assert rel_err(pooled.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
+    shuf = torch.zeros(B, 2 * H, 2 * W, cout // 4, device="cuda")
+    ops.tc_conv(xs, packed, cout, act=1, dst=shuf, dst_mode=2).run()
+    assert rel_err(shuf.permute(0, 3, 1, 2), F.pixel_shuffle(ref, 2)) < 2e-5
+    nchw = torch.zeros(B, cout, H, W, device="cuda")
+    ops.tc_conv(xs, packed, cout, act=1, dst=None, dst_layout=1, dst_c_total=cout).run(dst_override=nchw)
+    assert rel_err(nchw, ref) < 2e-5
