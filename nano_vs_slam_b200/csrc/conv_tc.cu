@@ -537,7 +537,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (C::CONCAT) {
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC2, (ks | k) != 0 ? 1u : 0u);  // x [W_hi;W_lo]
             if (k == 0 && ks == 0) mbar_arrive(astart(acc));
-            tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
+            // a_lo w_hi goes to the SECOND half as well: the tensor core's fp32 adder truncates, one (biased)
+            // rounding per accumulation, so the big a_hi w_hi sums take half as many of them and the small
+            // correction terms are rounded at their own, 2^-11 times smaller, magnitude
+            tc_mma_tf32_ts(d_tmem + (uint32_t)COUT, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
           } else {
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
             if (k == 0 && ks == 0) mbar_arrive(astart(acc));
