@@ -125,3 +125,33 @@ def test_match_batch_equals_per_pair_calls():
             r1, r2, rd, rc = ops.match(desc[a, :n1].contiguous(), desc[b, :n2].contiguous(), ratio=0.8, mode=mode)
             assert n == int(rc), (mode, p)
             assert torch.equal(i1[p, :n], r1[:n]) and torch.equal(i2[p, :n], r2[:n]) and torch.equal(dd[p, :n], rd[:n])
+
+
+@pytest.mark.parametrize("letter,v3", [("S", False), ("N", True), ("N_A", False), ("F", False)])
+def test_no_dependence_on_uninitialised_buffers(letter, v3):
+    """Plan buffers come from torch.empty: fill the allocator's cache with NaNs first, the outputs must not change
+    (zero-padded channel rows of the N letters, pooled / shuffled intermediates ... are all fully written)."""
+    import contextlib
+    import io
+
+    from nano_vs_slam_b200 import tiny_factory
+    from nano_vs_slam_b200.synthetic import spread_init, synthetic_frames
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = tiny_factory(letter, 19, v3=v3)
+    m.load_state_dict(spread_init(m.state_dict(), 5))
+    m.eval()
+    m.training = False
+    m = m.cuda()
+    x = synthetic_frames(2, 64, 96, 1).cuda()
+    ref = {k: v.clone() for k, v in m(x).items()}
+    m._plans.clear()
+    torch.cuda.synchronize()
+    # NaNs into the caching allocator's large AND small pools (plan buffers of this size are mostly < 1 MiB)
+    junk = [torch.full((64 << 20,), float("nan"), device="cuda") for _ in range(4)]
+    junk += [torch.full((n,), float("nan"), device="cuda") for n in (1 << 10, 8 << 10, 64 << 10, 200 << 10) for _ in range(400)]
+    del junk
+    out = m(x)
+    for k in ("score", "coord", "feat", "vlad", "seg"):
+        assert torch.isfinite(out[k]).all(), k
+        assert float((out[k] - ref[k]).abs().max()) <= 2e-5 * float(ref[k].abs().max()), k
