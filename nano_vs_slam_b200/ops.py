@@ -581,35 +581,42 @@ class TcConvSplit(object):
     """A tensor-core conv with more than 128 output channels (letters D / F: 256- and 512-channel layers) as one
     TcConv per 128-channel slice of the weights: each launch writes its channel range of the shared outputs."""
 
-    def __init__(self, src0: torch.Tensor, packed, cout: int, **kw):
+    def __init__(self, src0: torch.Tensor, packed, cout: int, slice_width: int = 128, **kw):
         hi, lo, bp = packed
         assert hi.shape[0] == 9, "paired-tap packing is for 32-channel outputs only"
         mode = kw.get("dst_mode", 1)
         assert mode in (0, 1, 2), "the keypoint-head split epilogue has 3 output channels"
         if kw.get("dst") is None and kw.get("dst_c_total") is None and mode != 0:
             kw["dst_c_total"] = cout // 4 if mode == 2 else cout
+        import os
+        # slice width: 128 (fewest launches) or 64 (the 64-wide kernel keeps the small correction products in their
+        # own accumulator half: lower rounding error, see DESIGN 3)
+        sw = int(os.environ.get("NVS_TC_SPLIT", str(slice_width)))
+        assert sw in (64, 128)
         self.ops = []
-        for j in range((cout + 127) // 128):
-            cj = min(128, cout - 128 * j)
-            hj = hi[:, 128 * j:128 * (j + 1)].contiguous()
+        for j in range((cout + sw - 1) // sw):
+            cj = min(sw, cout - sw * j)
+            hj = hi[:, sw * j:sw * (j + 1)].contiguous()
             hj.nvs_segments = getattr(hi, "nvs_segments", None)
-            sub = (hj, lo[:, 128 * j:128 * (j + 1)].contiguous(), bp[128 * j:128 * (j + 1)].contiguous())
+            sub = (hj, lo[:, sw * j:sw * (j + 1)].contiguous(), bp[sw * j:sw * (j + 1)].contiguous())
             kj = dict(kw)
-            kj["dst_c_off"] = kw.get("dst_c_off", 0) + (32 if mode == 2 else 128) * j
+            kj["dst_c_off"] = kw.get("dst_c_off", 0) + (sw // 4 if mode == 2 else sw) * j
             if kw.get("dst_pool") is not None:
-                kj["pool_c_off"] = kw.get("pool_c_off", 0) + 128 * j
+                kj["pool_c_off"] = kw.get("pool_c_off", 0) + sw * j
             self.ops.append(TcConv(src0, sub, cj, **kj))
         self.flops = sum(o.flops for o in self.ops)
-        self.shape = self.ops[0].shape.replace(f"->{min(128, cout)} ", f"->{cout} ") + f" x{len(self.ops)}"
+        self.shape = self.ops[0].shape.replace(f"->{min(sw, cout)} ", f"->{cout} ") + f" x{len(self.ops)}"
 
     def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
         for o in self.ops:
             o.run(dst_override, dst2_override)
 
 
-def tc_conv(src0: torch.Tensor, packed, cout: int, **kw):
-    """TcConv, or TcConvSplit when the packed weights carry more than 128 (padded) output channels."""
-    return (TcConvSplit if packed[2].numel() > 128 else TcConv)(src0, packed, cout, **kw)
+def tc_conv(src0: torch.Tensor, packed, cout: int, slice_width: int = 128, **kw):
+    """TcConv, or TcConvSplit when the packed weights carry more than ``slice_width`` (padded) output channels."""
+    if packed[2].numel() > slice_width and packed[0].shape[0] == 9 and kw.get("dst_mode", 1) != 3:
+        return TcConvSplit(src0, packed, cout, slice_width=slice_width, **kw)
+    return TcConv(src0, packed, cout, **kw)
 
 
 def conv_small(src_nhwc: torch.Tensor, packed, act: int = ACT_NONE, out: Optional[torch.Tensor] = None):
