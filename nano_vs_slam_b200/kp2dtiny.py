@@ -404,7 +404,7 @@ class _KP2DTinyBase(nn.Module):
         # letters (D, D_A) measured 1.2e-4 .. 1.9e-4 with 128-wide launches and <= 8e-5 when every layer runs as
         # 64-wide slices (the 64-wide kernel keeps the small correction products in their own accumulator half), so
         # those letters use 64-wide slices: 4.4x the FFMA backend's frame rate, inside the 1e-4 tolerance.
-        self.tc_slice = 64 if max(c4, c5) > 128 else 128
+        self.tc_slice = int(os.environ.get("NVS_TC_SLICE", "64" if max(c4, c5) > 128 else "128"))
         self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
         # batches up to this size replay a captured CUDA graph (0 disables)
         self.cuda_graph_max_batch = int(os.environ.get("NVS_CUDA_GRAPH_MAX_BATCH", "16"))
