@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
                                                      const float* __restrict__ xnorm, const int32_t* __restrict__ ci,
                                                      int kk, int k, int d, long long id_offset,
                                                      float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  extern __shared__ float sq[];  // [d] query, then [kk] distances
+  extern __shared__ __align__(16) float sq[];  // [d] query, then [kk] distances
   float* dist = sq + d;
   __shared__ float qn_s;
   const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -471,7 +471,30 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
     if (id >= 0) {
       const float* xr = x + (size_t)id * d;
       float dot = 0.f;
-      for (int e = lane; e < d; e += 32) dot = fmaf(sq[e], __ldg(xr + e), dot);
+      if ((d & 3) == 0) {
+        // 16 KB row per candidate at d = 4096: 128-bit loads, four rows of the loop in flight per lane (the
+        // kernel is a gather of kk random rows per query: latency, not arithmetic)
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        const int n4 = d >> 2;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int e = lane;
+        for (; e + 96 < n4; e += 128) {
+          const float4 v0 = __ldg(x4 + e), v1 = __ldg(x4 + e + 32), v2 = __ldg(x4 + e + 64), v3 = __ldg(x4 + e + 96);
+          const float4 w0 = q4[e], w1 = q4[e + 32], w2 = q4[e + 64], w3 = q4[e + 96];
+          a0 = fmaf(w0.x, v0.x, fmaf(w0.y, v0.y, fmaf(w0.z, v0.z, fmaf(w0.w, v0.w, a0))));
+          a1 = fmaf(w1.x, v1.x, fmaf(w1.y, v1.y, fmaf(w1.z, v1.z, fmaf(w1.w, v1.w, a1))));
+          a2 = fmaf(w2.x, v2.x, fmaf(w2.y, v2.y, fmaf(w2.z, v2.z, fmaf(w2.w, v2.w, a2))));
+          a3 = fmaf(w3.x, v3.x, fmaf(w3.y, v3.y, fmaf(w3.z, v3.z, fmaf(w3.w, v3.w, a3))));
+        }
+        for (; e < n4; e += 32) {
+          const float4 v = __ldg(x4 + e), w = q4[e];
+          a0 = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, a0))));
+        }
+        dot = (a0 + a1) + (a2 + a3);
+      } else {
+        for (int e = lane; e < d; e += 32) dot = fmaf(sq[e], __ldg(xr + e), dot);
+      }
       dot = warp_sum(dot);
       dv = qn_s + xnorm[id] - 2.f * dot;
     }
