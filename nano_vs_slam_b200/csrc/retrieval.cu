@@ -589,8 +589,15 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   L.n_mblk = (nq + BM - 1) / BM;
   L.qpad = L.n_mblk * BM;
   L.n_tiles = (int)((n_db + BN - 1) / BN);
-  int tps = 16;
-  while ((L.n_tiles + tps - 1) / tps > 256) tps *= 2;  // at most 256 strips -> <= 256*k candidates per query
+  // Strips (each (strip, query-block pair) is one work unit of a CTA pair and yields k candidates per query):
+  // enough units for ~32 rounds over the 74 clusters of a B200 (load balance to ~2 %), no more -- every strip
+  // restarts its per-row lists and adds k candidates per query to the selection pass -- at most 256, at least
+  // 16 tiles (4096 rows) each.
+  const int n_mpair = (L.n_mblk + 1) / 2;
+  int want = (32 * 74 + n_mpair - 1) / n_mpair;
+  if (want > 256) want = 256;
+  int tps = (L.n_tiles + want - 1) / want;
+  if (tps < 16) tps = 16;
   L.tiles_per_strip = tps;
   L.n_strips = (L.n_tiles + tps - 1) / tps;
   L.kk = 2 * k > k + 32 ? 2 * k : k + 32;  // candidates re-ranked exactly
