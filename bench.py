@@ -277,7 +277,10 @@ def main():
         assert got == n
         return d2h_bytes
 
+    import gc
     run_stream(3)
+    gc.collect()
+    gc.disable()  # no collector pauses inside the host-driven timed regions below
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -315,6 +318,7 @@ def main():
         t = torch.tensor([u8_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         u8_ms = float(t)
+    gc.enable()
     e2e_u8 = {"value": world * B * args.steps / (u8_ms / 1e3), "unit": "frames/s",
               "h2d_bytes_per_step": host_u8[0].numel(), "note": "uint8 HWC frames in, same outputs"}
 

@@ -94,7 +94,9 @@ class KP2DtinyFrontend(object):
         dev = torch.device(self.device)
         comp = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        host_sets: list = []
+        # two pinned result sets, alternated and kept across stream() calls (cudaHostAlloc of ~80 MB costs tens of
+        # milliseconds); a yielded dict stays valid until two more batches have been yielded
+        host_sets: list = self.__dict__.setdefault("_host_sets", [])
 
         def upload(hb):
             with torch.cuda.stream(h2d):
@@ -125,9 +127,15 @@ class KP2DtinyFrontend(object):
                        "vlad": post["vlad"]}
             if with_seg:
                 dev_out["seg"] = post["seg"]
-            if len(host_sets) < 2:  # two pinned result sets, alternated
-                host_sets.append({k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_out.items()})
-            host = host_sets[step % 2]
+            slot = step % 2
+            if len(host_sets) <= slot or any(k not in host_sets[slot] or host_sets[slot][k].shape != v.shape or
+                                             host_sets[slot][k].dtype != v.dtype for k, v in dev_out.items()):
+                fresh = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_out.items()}
+                if len(host_sets) <= slot:
+                    host_sets.append(fresh)
+                else:
+                    host_sets[slot] = fresh
+            host = host_sets[slot]
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
                 for k, v in dev_out.items():
