@@ -97,17 +97,30 @@ class KP2DtinyFrontend(object):
         # two pinned result sets, alternated and kept across stream() calls (cudaHostAlloc of ~80 MB costs tens of
         # milliseconds); a yielded dict stays valid until two more batches have been yielded
         host_sets: list = self.__dict__.setdefault("_host_sets", [])
+        # three device input buffers, rotated and kept across calls: nothing on this path goes through
+        # record_stream (which defers block reuse and makes the caching allocator fall back to cudaMalloc /
+        # cudaFree -- a device-wide stall -- every now and then)
+        dev_in: list = self.__dict__.setdefault("_dev_in", [])
+        slot_free: list = [None, None, None]  # compute-stream event after which input slot i may be overwritten
 
-        def upload(hb):
+        def upload(hb, slot):
+            if len(dev_in) <= slot or dev_in[slot].shape != hb.shape or dev_in[slot].dtype != hb.dtype:
+                buf = torch.empty(hb.shape, dtype=hb.dtype, device=dev)
+                if len(dev_in) <= slot:
+                    dev_in.append(buf)
+                else:
+                    dev_in[slot] = buf
             with torch.cuda.stream(h2d):
-                x = hb.to(dev, non_blocking=True)
+                if slot_free[slot] is not None:
+                    h2d.wait_event(slot_free[slot])
+                dev_in[slot].copy_(hb, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(h2d)
-            return x, ev
+            return dev_in[slot], ev
 
         it = iter(host_batches)
         try:
-            nxt = upload(next(it))
+            nxt = upload(next(it), 0)
         except StopIteration:
             return
         pending: deque = deque()
@@ -115,14 +128,14 @@ class KP2DtinyFrontend(object):
         while nxt is not None:
             x, ev = nxt
             try:
-                nxt = upload(next(it))  # prefetch the next batch while this one computes
+                nxt = upload(next(it), (step + 1) % 3)  # prefetch the next batch while this one computes
             except StopIteration:
                 nxt = None
             comp.wait_event(ev)
             sel, post = self.run_batch(x, normalized=normalized)
-            x.record_stream(comp)
             done = torch.cuda.Event()
             done.record(comp)
+            slot_free[step % 3] = done
             dev_out = {"pts": sel["pts"], "desc": sel["desc"], "score": sel["score"], "count": sel["count"],
                        "vlad": post["vlad"]}
             if with_seg:
@@ -140,17 +153,16 @@ class KP2DtinyFrontend(object):
                 d2h.wait_event(done)
                 for k, v in dev_out.items():
                     host[k].copy_(v, non_blocking=True)
-                    v.record_stream(d2h)
                 fin = torch.cuda.Event()
                 fin.record(d2h)
-            pending.append((host, fin))
+            pending.append((host, fin, dev_out))  # dev_out stays referenced until its copy has finished
             step += 1
             if len(pending) > 1:
-                h, e = pending.popleft()
+                h, e, _keep = pending.popleft()
                 e.synchronize()
                 yield h
         while pending:
-            h, e = pending.popleft()
+            h, e, _keep = pending.popleft()
             e.synchronize()
             yield h
 
