@@ -1,0 +1,44 @@
+"""Static checks on the product tree: the oracle is test infrastructure only, and the hot path has no compiler /
+multi-backend layer."""
+import os
+import re
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "nano_vs_slam_b200")
+
+
+def _sources(exts):
+    for root, _, files in os.walk(PKG):
+        if os.sep + "lib" in root:
+            continue
+        for f in files:
+            if f.endswith(exts):
+                yield os.path.join(root, f)
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    pat = re.compile(r"^\s*(from|import)\s+(oracle|src\.|baseline)", re.M)
+    for path in _sources((".py",)):
+        if os.sep + "compat" + os.sep in path:
+            continue  # the import-path shim re-exports nano_vs_slam_b200 under the reference's module name
+        text = open(path).read()
+        assert not pat.search(text), path
+        assert "/root/reference" not in text, path
+
+
+def test_no_compiler_or_multi_backend_layer_in_the_hot_path():
+    banned = ("import triton", "torch.compile", "tilelang", "torch.jit.script")
+    for path in _sources((".py",)):
+        text = open(path).read()
+        for b in banned:
+            assert b not in text, (path, b)
+
+
+def test_every_kernel_file_is_sm100a_cuda_and_the_build_targets_it():
+    cu = list(_sources((".cu",)))
+    assert len(cu) >= 9
+    build = open(os.path.join(PKG, "build.py")).read()
+    assert "arch=compute_100a,code=sm_100a" in build and "-lineinfo" in build
+    tc = open(os.path.join(PKG, "csrc", "conv_tc.cu")).read() + open(os.path.join(PKG, "csrc", "retrieval.cu")).read()
+    for needle in ("tcgen05.mma", "tcgen05.alloc", "tcgen05.commit", "cp.async.bulk.tensor", "mbarrier.try_wait"):
+        assert needle in tc, needle
