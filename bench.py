@@ -26,7 +26,12 @@ import sys
 import threading
 import time
 
-import torch
+# ~1.5 GB of fresh output tensors per step go through the caching allocator; with fixed-size segments a new stream
+# occasionally needs a cudaMalloc of that size in the middle of the timed region (a 40 ms stall seen in the per-batch
+# trace).  Expandable segments grow in place instead.  (Must be set before CUDA is initialised.)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+import torch  # noqa: E402
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
@@ -269,9 +274,16 @@ def main():
     host_x = [synthetic_frames(B, H, W, XSEED + 100 * rank + i).pin_memory() for i in range(2)]
     h2d = host_x[0].numel() * 4
 
+    trace = os.environ.get("NVS_BENCH_TRACE") == "1"  # per-batch host arrival times of the e2e stream, to stderr
+
     def run_stream(n):
         d2h_bytes, got = 0, 0
+        t_prev = time.perf_counter()
         for res in fe.stream((host_x[i % 2] for i in range(n)), normalized=True):
+            if trace:
+                t_now = time.perf_counter()
+                print(f"[e2e] batch {got}: +{1e3 * (t_now - t_prev):.1f} ms", file=sys.stderr)
+                t_prev = t_now
             got += int(res["count"][0] >= 0)  # the host reads the results of every batch
             d2h_bytes = sum(t.numel() * t.element_size() for t in res.values())
         assert got == n
