@@ -90,7 +90,9 @@ class KP2DtinyFrontend(object):
         (frontend.py:81-116).  Here the same three phases are software-pipelined over three CUDA streams
         (H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i; B200 has independent copy
         engines per direction), so the host always gets every batch's results, one batch behind the GPU.
-        Yields, per batch: pts (B,k,2), desc (B,k,D), score (B,k), count (B,), vlad (B,G) [, seg (B,1,H/2,W/2)]."""
+        Yields, per batch: pts (B,k,2), desc (B,k,D), score (B,k), count (B,), vlad (B,G) [, seg (B,1,H/2,W/2)].
+        The yielded tensors are views of two pinned buffers owned by this object: a result stays valid until two more
+        batches have been yielded (also across stream() calls) -- copy what must live longer."""
         dev = torch.device(self.device)
         comp = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
