@@ -112,6 +112,9 @@ class KP2DtinyFrontend(object):
                     dev_in.append(buf)
                 else:
                     dev_in[slot] = buf
+                # the block comes from the compute stream's pool and may have been freed by tensors whose kernels
+                # are still queued there: the first copy into it must wait for them (once per slot and shape)
+                h2d.wait_stream(comp)
             with torch.cuda.stream(h2d):
                 if slot_free[slot] is not None:
                     h2d.wait_event(slot_free[slot])
@@ -125,6 +128,15 @@ class KP2DtinyFrontend(object):
             nxt = upload(next(it), 0)
         except StopIteration:
             return
+        try:
+            yield from self._stream_loop(it, nxt, upload, slot_free, host_sets, comp, d2h, normalized, with_seg)
+        finally:
+            # a consumer that abandons the generator leaves a prefetch in flight: the persistent input buffers
+            # must be quiescent before the next call (or the allocator) touches them
+            h2d.synchronize()
+            d2h.synchronize()
+
+    def _stream_loop(self, it, nxt, upload, slot_free, host_sets, comp, d2h, normalized, with_seg):
         pending: deque = deque()
         step = 0
         while nxt is not None:

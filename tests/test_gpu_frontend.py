@@ -56,7 +56,10 @@ def test_frontend_stream_equals_run_batch_and_semantic_filter():
         assert torch.equal(g["count"], r["count"])
         for b in range(3):
             n = int(r["count"][b])
-            assert torch.allclose(g["pts"][b, :n], r["pts"][b, :n]) and torch.allclose(g["desc"][b, :n], r["desc"][b, :n], atol=1e-5)
+            # two separate forward executions: the multi-issuer MMA schedule rounds differently run to run (<= 7e-6 on
+            # the dense maps, tools/hunt_sporadic.py), amplified by the descriptor normalisation
+            assert torch.allclose(g["pts"][b, :n], r["pts"][b, :n], atol=1e-3)
+            assert torch.allclose(g["desc"][b, :n], r["desc"][b, :n], atol=1e-4)
         assert torch.allclose(g["vlad"], r["vlad"], atol=1e-6)
     # semantic filter path (sample_segmentation=True, labels per cell)
     fe2, _ = _frontend(0.4, 50, semantic_filter=True, classes_to_filter=[0, 1, 2, 3, 4, 5])
@@ -151,3 +154,55 @@ def test_match_selected_pair_on_device():
     lg = lightglue_inputs(sel, 0, 1, (H, W))
     assert lg["image0"]["keypoints"].shape == (1, n0, 2) and lg["image1"]["descriptors"].shape == (1, n1, 32)
     assert float(lg["image0"]["keypoints"].max()) <= 1.0 and lg["image0"]["image_size"].tolist() == [[W, H]]
+
+
+def test_stream_twice_and_uint8_batches_reuse_buffers():
+    """stream() keeps its pinned result sets / device input slots across calls; a second call and uint8 batches
+    give the same results as run_batch."""
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    fe, _ = _frontend(0.3, 64)
+    xs = [synthetic_frames(2, 64, 96, s).pin_memory() for s in (1, 2, 3)]
+    ref = [fe.run_batch(x.cuda(), normalized=True) for x in xs]
+    for _ in range(2):
+        got = [{k: v.clone() for k, v in r.items()} for r in fe.stream(iter(xs), normalized=True)]
+        assert len(got) == 3
+        for g, (sel, post) in zip(got, ref):
+            assert torch.equal(g["count"], sel["count"].cpu())
+            n = int(g["count"][0])
+            assert float((g["pts"][0, :n] - sel["pts"][0, :n].cpu()).abs().max()) < 1e-3
+            assert float((g["vlad"] - post["vlad"].cpu()).abs().max()) < 1e-5
+    u8 = [((x.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory() for x in xs]
+    got8 = [{k: v.clone() for k, v in r.items()} for r in fe.stream(iter(u8))]
+    ref8 = [fe.run_batch(u.cuda()) for u in u8]
+    for g, (sel, post) in zip(got8, ref8):
+        assert torch.equal(g["count"], sel["count"].cpu())
+        assert float((g["vlad"] - post["vlad"].cpu()).abs().max()) < 1e-5
+
+
+def test_stream_input_buffers_wait_for_queued_compute_work():
+    """Regression: stream() allocates its device input slots from the compute stream's pool; a block freed by tensors
+    whose kernels are still queued must not be overwritten by the copy stream before they ran (seen as a whole batch
+    of wrong keypoints when the allocator cache held recently freed blocks of the right size)."""
+    from nano_vs_slam_b200.synthetic import synthetic_frames
+
+    for trial in range(3):
+        fe0, _ = _frontend(0.45, 150)
+        fe0.run((synthetic_frames(1, 120, 160, 3)[0] + 1) / 2)
+        del fe0
+        junk = [torch.randn(16 << 20, device="cuda") for _ in range(12)]
+        junk += [torch.randn(n, device="cuda") for n in (1 << 10, 8 << 10, 64 << 10, 200 << 10) for _ in range(400)]
+        del junk
+        fe, _ = _frontend(0.4, 50)
+        batches = [synthetic_frames(3, 64, 96, s).pin_memory() for s in range(4)]
+        ref = []
+        for hb in batches:
+            sel, _post = fe.run_batch(hb.cuda(), normalized=True)
+            ref.append({k: sel[k].cpu().clone() for k in ("pts", "score", "count")})
+        got = [{k: v.clone() for k, v in r.items()} for r in fe.stream(iter(batches), normalized=True)]
+        for g, r in zip(got, ref):
+            assert torch.equal(g["count"], r["count"])
+            for b in range(3):
+                n = int(r["count"][b])
+                assert float((g["pts"][b, :n] - r["pts"][b, :n]).abs().max()) < 1e-3, trial
+                assert float((g["score"][b, :n] - r["score"][b, :n]).abs().max()) < 1e-4, trial
