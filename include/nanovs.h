@@ -236,6 +236,25 @@ int nvs_match_batch(const float* des, const int32_t* counts, int32_t n_frames, i
                     int32_t* out_idx1, int32_t* out_idx2, float* out_dist, int32_t* out_count, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---- batched relative pose (visual_odometry.py:383-412: cv2.findEssentialMat + cv2.recoverPose per pair) ----
+ * For each of P frame pairs: matched keypoints are unprojected with the pinhole intrinsics ((u-cx)/fx, (v-cy)/fy,
+ * camera.unproject_points; pass fx=fy=1, cx=cy=0 for normalised coordinates), `iters` five-point (Nister) hypotheses
+ * are drawn with a counter-based generator from `seed`, scored by the truncated squared Sampson distance
+ * (inlier iff <= threshold^2, the reference passes 0.0003), and the best E is decomposed; the (R, t) whose
+ * triangulated points lie in front of both cameras for most matches is returned (x_b ~ R x_a + t, |t| = 1).
+ * Inputs are what nvs_select_keypoints / nvs_match_batch leave on the device: pts (F, kmax, 2); pair_a (current
+ * frame) / pair_b (reference frame) (P); idx1 / idx2 (P, kmax) = match m -> keypoint index in frame a / b (both
+ * NULL = identity, i.e. pts rows are already matched); count (P) matches per pair.  All DEVICE arrays.
+ * Outputs: out_E (P,9) row-major with p_b^T E p_a = 0, out_R (P,9), out_t (P,3), out_mask (P,kmax) uint8,
+ * out_inliers (P).  A pair with fewer than 5 matches yields E = 0, R = I, t = 0 and no inliers.
+ * Deterministic for a given seed (integer score accumulation).  workspace: nvs_pose_workspace_bytes, 256-aligned. */
+size_t nvs_pose_workspace_bytes(int32_t n_pairs, int32_t kmax, int32_t iters);
+int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a, const int32_t* pair_b,
+                   const int32_t* idx1, const int32_t* idx2, const int32_t* count, int32_t n_pairs, float fx,
+                   float fy, float cx, float cy, float threshold, int32_t iters, uint64_t seed, float* out_E,
+                   float* out_R, float* out_t, uint8_t* out_mask, int32_t* out_inliers, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- exact L2 top-k retrieval = faiss.IndexFlatL2.add / .search (evaluation/global_descriptor.py:55-60) ----
  * add:    nvs_flat_prepare converts the fp32 rows (n,d) to bf16 rows padded to nvs_flat_padded_dim(d)
  *         columns (the tcgen05 GEMM operand) and stores |x|^2 (fp32).  Caller owns all three buffers.

@@ -18,6 +18,7 @@ OUT_PLAIN, OUT_POOL, OUT_BOTH, OUT_SHUFFLE = range(4)
 IN_PLAIN, IN_S2D, IN_U8_HWC = range(3)
 
 _vp, _i32, _f32, _f64, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_size_t, C.c_int64
+_u64 = C.c_uint64
 
 
 class NvsConvArgs(C.Structure):
@@ -80,6 +81,9 @@ SIGNATURES = {
     "nvs_match_batch_workspace_bytes": (_sz, [_i32, _i32]),
     "nvs_match_batch": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _sz,
                                 _vp]),
+    "nvs_pose_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "nvs_pose_batch": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _i32, _u64,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nvs_flat_padded_dim": (_i32, [_i32]),
     "nvs_flat_prepare": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "nvs_flat_search_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),

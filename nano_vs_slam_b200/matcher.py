@@ -100,3 +100,46 @@ def match_consecutive(sel: dict, cross_check: bool = False, ratio_test: float = 
     dev = sel["desc"].device
     a = torch.arange(1, B, device=dev, dtype=torch.int32)
     return ops.match_batch(sel["desc"], sel["count"], a, a - 1, ratio=ratio_test, mode=1 if cross_check else 0)
+
+
+def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_test: float = kRatioTest,
+                     threshold: float = 0.0003, iters: int = 512, seed: int = 0):
+    """Matching AND relative pose for a batch of consecutive frames without a host round trip
+    (visual_odometry.py:314-345: match frame t against t-1, then estimatePose :383-412).
+
+    ``intrinsics`` = (fx, fy, cx, cy).  Returns (matches, pose): ``matches`` as match_consecutive, ``pose`` =
+    dict(E, R, t, mask, inliers) per pair with x_prev ~ R x_cur + t (the reference's kpn_cur -> kpn_ref order)."""
+    B = sel["desc"].shape[0]
+    dev = sel["desc"].device
+    a = torch.arange(1, B, device=dev, dtype=torch.int32)
+    i1, i2, dd, cnt = ops.match_batch(sel["desc"], sel["count"], a, a - 1, ratio=ratio_test,
+                                      mode=1 if cross_check else 0)
+    pose = ops.pose_batch(sel["pts"], a, a - 1, cnt, i1, i2, intrinsics=intrinsics, threshold=threshold, iters=iters,
+                          seed=seed)
+    return (i1, i2, dd, cnt), pose
+
+
+class PoseEstimator(object):
+    """Reference-shaped pose step: ``estimatePose(kps_ref, kps_cur) -> (R, t)`` with ``mask_match`` set, as
+    VisualOdometry.estimatePose (visual_odometry.py:383-412).  ``cam`` is any object with fx, fy, cx, cy (the
+    reference's PinholeCamera); lens distortion is not handled here (KITTI frames are rectified: D = 0)."""
+
+    def __init__(self, cam, threshold: float = 0.0003, iters: int = 512, seed: int = 0, device: str = "cuda"):
+        self.cam = cam
+        self.threshold, self.iters, self.seed, self.device = threshold, iters, seed, device
+        self.mask_match = None
+        self.E = None
+
+    def estimatePose(self, kps_ref, kps_cur):
+        kps_ref = np.ascontiguousarray(kps_ref, dtype=np.float32).reshape(-1, 2)
+        kps_cur = np.ascontiguousarray(kps_cur, dtype=np.float32).reshape(-1, 2)
+        n = kps_ref.shape[0]
+        assert kps_cur.shape[0] == n
+        pts = torch.from_numpy(np.stack([kps_cur, kps_ref])).to(self.device)  # frame 0 = current, 1 = reference
+        zero = torch.zeros(1, dtype=torch.int32, device=self.device)
+        out = ops.pose_batch(pts, zero, zero + 1, torch.full((1,), n, dtype=torch.int32, device=self.device),
+                             intrinsics=(self.cam.fx, self.cam.fy, self.cam.cx, self.cam.cy),
+                             threshold=self.threshold, iters=self.iters, seed=self.seed)
+        self.mask_match = out["mask"][0].cpu().numpy().reshape(-1, 1)
+        self.E = out["E"][0].cpu().numpy().astype(np.float64)
+        return out["R"][0].cpu().numpy().astype(np.float64), out["t"][0].cpu().numpy().astype(np.float64).reshape(3, 1)

@@ -414,6 +414,47 @@ def match_batch(desc: torch.Tensor, counts: torch.Tensor, pair_a: torch.Tensor, 
     return i1, i2, dd, cnt
 
 
+def pose_batch(pts: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor, count: torch.Tensor,
+               idx1: Optional[torch.Tensor] = None, idx2: Optional[torch.Tensor] = None,
+               intrinsics: Sequence[float] = (1.0, 1.0, 0.0, 0.0), threshold: float = 0.0003, iters: int = 512,
+               seed: int = 0, workspace: Optional[torch.Tensor] = None):
+    """Relative pose of P frame pairs in one call (visual_odometry.py:383-412: findEssentialMat + recoverPose).
+
+    ``pts`` (F,kmax,2) keypoint coordinates as written by select_keypoints, ``pair_a`` (current) / ``pair_b``
+    (reference) (P,) frame indices, ``idx1`` / ``idx2`` / ``count`` as returned by match_batch (both idx None: the
+    rows of ``pts`` are already matched).  ``intrinsics`` = (fx, fy, cx, cy) of the pinhole camera.
+    Returns dict(E (P,3,3), R (P,3,3), t (P,3), mask (P,kmax) uint8, inliers (P,) int32): x_ref ~ R x_cur + t."""
+    pts = _req(pts)
+    F_, kmax, two = pts.shape
+    assert two == 2
+    dev = pts.device
+    pair_a = pair_a.to(device=dev, dtype=torch.int32).contiguous()
+    pair_b = pair_b.to(device=dev, dtype=torch.int32).contiguous()
+    count = count.to(device=dev, dtype=torch.int32).contiguous()
+    P = pair_a.numel()
+    if (idx1 is None) != (idx2 is None):
+        raise ValueError("idx1 and idx2 go together")
+    if idx1 is not None:
+        idx1, idx2 = _req(idx1, torch.int32), _req(idx2, torch.int32)
+        assert idx1.shape == (P, kmax) and idx2.shape == (P, kmax)
+    nbytes = int(lib().nvs_pose_workspace_bytes(P, kmax, iters))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    E = torch.empty(P, 3, 3, device=dev, dtype=torch.float32)
+    R = torch.empty(P, 3, 3, device=dev, dtype=torch.float32)
+    t = torch.empty(P, 3, device=dev, dtype=torch.float32)
+    mask = torch.empty(P, kmax, device=dev, dtype=torch.uint8)
+    inl = torch.empty(P, device=dev, dtype=torch.int32)
+    fx, fy, cx, cy = (float(v) for v in intrinsics)
+    check(lib().nvs_pose_batch(pts.data_ptr(), F_, kmax, pair_a.data_ptr(), pair_b.data_ptr(), _ptr(idx1), _ptr(idx2),
+                               count.data_ptr(), P, fx, fy, cx, cy, float(threshold), int(iters),
+                               int(seed) & 0xFFFFFFFFFFFFFFFF, E.data_ptr(), R.data_ptr(), t.data_ptr(),
+                               mask.data_ptr(), inl.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()),
+          "nvs_pose_batch")
+    LAUNCHES[0] += 4
+    return {"E": E, "R": R, "t": t, "mask": mask, "inliers": inl}
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor-core conv (csrc/conv_tc.cu): channels-last activations, 3xTF32 weights
 # ----------------------------------------------------------------------------------------------
