@@ -247,12 +247,16 @@ int nvs_match_batch(const float* des, const int32_t* counts, int32_t n_frames, i
  * NULL = identity, i.e. pts rows are already matched); count (P) matches per pair.  All DEVICE arrays.
  * Outputs: out_E (P,9) row-major with p_b^T E p_a = 0, out_R (P,9), out_t (P,3), out_mask (P,kmax) uint8,
  * out_inliers (P).  A pair with fewer than 5 matches yields E = 0, R = I, t = 0 and no inliers.
+ * refine = 0: the result is the best minimal-sample model (what cv2.RANSAC returns); refine = n > 0: up to n
+ * Gauss-Newton steps on the essential manifold over the consensus set, kept while the truncated cost decreases (the
+ * role of local optimisation + final polishing in cv2.USAC_MSAC, the method the reference asks for first), after
+ * which mask and inlier count are those of the refined E.
  * Deterministic for a given seed (integer score accumulation).  workspace: nvs_pose_workspace_bytes, 256-aligned. */
 size_t nvs_pose_workspace_bytes(int32_t n_pairs, int32_t kmax, int32_t iters);
 int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a, const int32_t* pair_b,
                    const int32_t* idx1, const int32_t* idx2, const int32_t* count, int32_t n_pairs, float fx,
-                   float fy, float cx, float cy, float threshold, int32_t iters, uint64_t seed, float* out_E,
-                   float* out_R, float* out_t, uint8_t* out_mask, int32_t* out_inliers, void* workspace,
+                   float fy, float cx, float cy, float threshold, int32_t iters, uint64_t seed, int32_t refine,
+                   float* out_E, float* out_R, float* out_t, uint8_t* out_mask, int32_t* out_inliers, void* workspace,
                    size_t workspace_bytes, void* stream);
 
 /* ---- exact L2 top-k retrieval = faiss.IndexFlatL2.add / .search (evaluation/global_descriptor.py:55-60) ----

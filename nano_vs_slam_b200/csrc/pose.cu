@@ -13,6 +13,7 @@
 //                      per-point costs are quantised to 2^-30 of the squared threshold and summed as integers, so the score
 //                      does not depend on the reduction order (deterministic arg-min, lowest index wins ties)
 //   select_kernel      one CTA per pair: arg-min, inlier mask, decomposition, cheirality vote, outputs
+//   refine_kernel      (refine > 0) one CTA per pair: Gauss-Newton polish of (R, t) on the consensus set
 #include "common.cuh"
 #include "pose_math.h"
 
@@ -212,6 +213,106 @@ __global__ void __launch_bounds__(SELECT_T) pose_select_kernel(const float2* __r
   }
 }
 
+// Optional local optimisation (the role LO + final polishing play in OpenCV's USAC): Gauss-Newton on the essential
+// manifold over the consensus set of the selected model, keeping the pose with the lowest truncated cost.  One CTA per
+// pair; the 22 sums of the normal equations are reduced in fp64 (warp shuffles, then shared memory).
+constexpr int REFINE_T = 256;
+
+__global__ void __launch_bounds__(REFINE_T) pose_refine_kernel(const float2* __restrict__ cur, const float2* __restrict__ ref,
+                                                               const int32_t* __restrict__ count, int kmax, float thr2,
+                                                               int refine, float* __restrict__ out_E,
+                                                               float* __restrict__ out_R, float* __restrict__ out_t,
+                                                               uint8_t* __restrict__ out_mask,
+                                                               int32_t* __restrict__ out_inliers) {
+  __shared__ double s_Es[6][9];
+  __shared__ double s_red[REFINE_T / 32][POSE_NACC];
+  __shared__ double s_Rc[9], s_tc[3], s_Rb[9], s_tb[3];
+  __shared__ double s_best;
+  __shared__ int s_stop, s_cnt;
+  __shared__ float s_Ef[9];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (out_inliers[p] <= 0) return;  // no model for this pair (block-uniform)
+  int n = count[p];
+  n = n > kmax ? kmax : n;
+  if (tid == 0) {
+    for (int e = 0; e < 9; ++e) s_Rc[e] = s_Rb[e] = out_R[p * 9 + e];
+    for (int e = 0; e < 3; ++e) s_tc[e] = s_tb[e] = out_t[p * 3 + e];
+    s_best = -1.0;
+    s_stop = 0;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  const double thr2d = (double)thr2;
+  for (int iter = 0; iter <= refine; ++iter) {
+    if (tid == 0) refine_stencil(s_Rc, s_tc, s_Es);
+    __syncthreads();
+    double acc[POSE_NACC];
+#pragma unroll
+    for (int k = 0; k < POSE_NACC; ++k) acc[k] = 0.0;
+    for (int i = tid; i < n; i += REFINE_T) {
+      const float2 a = cur[(size_t)p * kmax + i], b = ref[(size_t)p * kmax + i];
+      refine_accumulate(s_Es, a.x, a.y, b.x, b.y, thr2d, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < POSE_NACC; ++k) {
+      double v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double tot[POSE_NACC];
+      for (int k = 0; k < POSE_NACC; ++k) {
+        double v = 0.0;
+        for (int w = 0; w < REFINE_T / 32; ++w) v += s_red[w][k];
+        tot[k] = v;
+      }
+      const double cost = tot[POSE_NACC - 1];
+      if (s_best >= 0.0 && !(cost < s_best)) {
+        s_stop = 1;
+      } else {
+        s_best = cost;
+        for (int e = 0; e < 9; ++e) s_Rb[e] = s_Rc[e];
+        for (int e = 0; e < 3; ++e) s_tb[e] = s_tc[e];
+        double d[POSE_NPAR], R2[9], t2[3];
+        if (iter == refine || !refine_solve(tot, d)) {
+          s_stop = 1;
+        } else {
+          perturb_pose(s_Rc, s_tc, d, R2, t2);
+          for (int e = 0; e < 9; ++e) s_Rc[e] = R2[e];
+          for (int e = 0; e < 3; ++e) s_tc[e] = t2[e];
+        }
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;
+  }
+  if (tid == 0) {
+    double E[9], nrm = 0.0;
+    essential_from_pose(s_Rb, s_tb, E);
+    for (int e = 0; e < 9; ++e) nrm += E[e] * E[e];
+    nrm = sqrt(2.0 / nrm);
+    for (int e = 0; e < 9; ++e) {
+      s_Ef[e] = (float)(E[e] * nrm);
+      out_E[p * 9 + e] = s_Ef[e];
+      out_R[p * 9 + e] = (float)s_Rb[e];
+    }
+    for (int e = 0; e < 3; ++e) out_t[p * 3 + e] = (float)s_tb[e];
+  }
+  __syncthreads();
+  int ninl = 0;
+  for (int i = tid; i < n; i += REFINE_T) {
+    const float2 a = cur[(size_t)p * kmax + i], b = ref[(size_t)p * kmax + i];
+    const uint8_t m = sampson_sq<float>(s_Ef, a.x, a.y, b.x, b.y) <= thr2;
+    out_mask[(size_t)p * kmax + i] = m;
+    ninl += m;
+  }
+  atomicAdd(&s_cnt, ninl);
+  __syncthreads();
+  if (tid == 0) out_inliers[p] = s_cnt;
+}
+
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace nvs
@@ -228,13 +329,14 @@ extern "C" size_t nvs_pose_workspace_bytes(int32_t n_pairs, int32_t kmax, int32_
 extern "C" int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a,
                               const int32_t* pair_b, const int32_t* idx1, const int32_t* idx2, const int32_t* count,
                               int32_t n_pairs, float fx, float fy, float cx, float cy, float threshold, int32_t iters,
-                              uint64_t seed, float* out_E, float* out_R, float* out_t, uint8_t* out_mask,
-                              int32_t* out_inliers, void* workspace, size_t workspace_bytes, void* stream) {
+                              uint64_t seed, int32_t refine, float* out_E, float* out_R, float* out_t,
+                              uint8_t* out_mask, int32_t* out_inliers, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   if (!pts || !pair_a || !pair_b || !count || !out_E || !out_R || !out_t || !out_mask || !out_inliers || !workspace)
     return NVS_ERR_ARG;
   if ((idx1 == nullptr) != (idx2 == nullptr)) return NVS_ERR_ARG;
   if (n_frames <= 0 || kmax <= 0 || n_pairs <= 0 || n_pairs > 65535 || iters <= 0 || iters > 65535) return NVS_ERR_ARG;
-  if (!(threshold > 0.f) || fx == 0.f || fy == 0.f) return NVS_ERR_ARG;
+  if (!(threshold > 0.f) || fx == 0.f || fy == 0.f || refine < 0 || refine > 100) return NVS_ERR_ARG;
   if (workspace_bytes < nvs_pose_workspace_bytes(n_pairs, kmax, iters)) return NVS_ERR_ARG;
   if (((uintptr_t)workspace & 255) != 0) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -256,5 +358,10 @@ extern "C" int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, 
   pose_select_kernel<<<n_pairs, SELECT_T, 0, st>>>(cur, ref, count, kmax, iters, thr2, cand, score, out_E, out_R, out_t,
                                                    out_mask, out_inliers);
   NVS_CHECK_LAUNCH();
+  if (refine > 0) {
+    pose_refine_kernel<<<n_pairs, REFINE_T, 0, st>>>(cur, ref, count, kmax, thr2, refine, out_E, out_R, out_t, out_mask,
+                                                     out_inliers);
+    NVS_CHECK_LAUNCH();
+  }
   return NVS_OK;
 }

@@ -387,4 +387,117 @@ NVS_HD bool in_front(const double* R, const double* t, double x1, double y1, dou
   return l1 > 0.0 && l2 > 0.0 && l1 < far_ && l2 < far_;
 }
 
+// ---- local refinement on the essential manifold -------------------------------------------------------------------
+// E = [t]x R with 5 degrees of freedom: R <- exp([w]x) R (w in R^3), t <- normalise(t + a b1 + b b2) with (b1, b2) an
+// orthonormal basis of the tangent plane of the unit sphere at t.  Gauss-Newton on the signed Sampson distances of the
+// current consensus set, Jacobian by forward differences (the kernels and the host harness run the same sequence).
+constexpr int POSE_NPAR = 5;
+constexpr int POSE_NACC = 1 + POSE_NPAR + POSE_NPAR * (POSE_NPAR + 1) / 2 + 1;  // cost, J^T r, upper J^T J, MSAC cost
+#define POSE_FD_EPS 1e-6
+
+NVS_HD void rodrigues_mul(const double* w, const double* R, double* out) {  // out = exp([w]x) R
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double a, b;  // exp = I + a K + b K^2, K = [w]x
+  if (th < 1e-8) { a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; } else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+  const double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double K2[9], Ex[9];
+  mat3_mul(K, K, K2);
+  for (int e = 0; e < 9; ++e) Ex[e] = (e % 4 == 0 ? 1.0 : 0.0) + a * K[e] + b * K2[e];
+  mat3_mul(Ex, R, out);
+}
+
+NVS_HD void essential_from_pose(const double* R, const double* t, double* E) {  // [t]x R
+  const double T[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+  mat3_mul(T, R, E);
+}
+
+NVS_HD void tangent_basis(const double* t, double* b1, double* b2) {
+  int k = 0;  // coordinate axis least aligned with t
+  if (fabs(t[1]) < fabs(t[k])) k = 1;
+  if (fabs(t[2]) < fabs(t[k])) k = 2;
+  double ax[3] = {0, 0, 0};
+  ax[k] = 1.0;
+  cross3(t, ax, b1);
+  const double n = 1.0 / sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+  for (int i = 0; i < 3; ++i) b1[i] *= n;
+  cross3(t, b1, b2);
+}
+
+NVS_HD void perturb_pose(const double* R, const double* t, const double* d, double* R2, double* t2) {
+  double b1[3], b2[3];
+  tangent_basis(t, b1, b2);
+  rodrigues_mul(d, R, R2);
+  double n = 0.0;
+  for (int i = 0; i < 3; ++i) { t2[i] = t[i] + d[3] * b1[i] + d[4] * b2[i]; n += t2[i] * t2[i]; }
+  n = 1.0 / sqrt(n);
+  for (int i = 0; i < 3; ++i) t2[i] *= n;
+}
+
+// base E and its five forward-difference neighbours, Es[6][9]
+NVS_HD void refine_stencil(const double* R, const double* t, double Es[6][9]) {
+  essential_from_pose(R, t, Es[0]);
+  for (int k = 0; k < POSE_NPAR; ++k) {
+    double d[POSE_NPAR] = {0, 0, 0, 0, 0}, R2[9], t2[3];
+    d[k] = POSE_FD_EPS;
+    perturb_pose(R, t, d, R2, t2);
+    essential_from_pose(R2, t2, Es[1 + k]);
+  }
+}
+
+NVS_HD double sampson_signed(const double* E, double x1, double y1, double x2, double y2) {
+  const double a0 = E[0] * x1 + E[1] * y1 + E[2], a1 = E[3] * x1 + E[4] * y1 + E[5], a2 = E[6] * x1 + E[7] * y1 + E[8];
+  const double b0 = E[0] * x2 + E[3] * y2 + E[6], b1 = E[1] * x2 + E[4] * y2 + E[7];
+  return (x2 * a0 + y2 * a1 + a2) / sqrt(a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1);
+}
+
+// one correspondence's contribution to the normal equations (acc[POSE_NACC]); thr2 = squared inlier threshold
+NVS_HD void refine_accumulate(const double Es[6][9], double x1, double y1, double x2, double y2, double thr2,
+                              double* acc) {
+  const double r0 = sampson_signed(Es[0], x1, y1, x2, y2);
+  const double e = r0 * r0;
+  acc[POSE_NACC - 1] += e <= thr2 ? e : thr2;
+  if (!(e <= thr2)) return;
+  double J[POSE_NPAR];
+  for (int k = 0; k < POSE_NPAR; ++k) J[k] = (sampson_signed(Es[1 + k], x1, y1, x2, y2) - r0) * (1.0 / POSE_FD_EPS);
+  acc[0] += e;
+  int o = 1 + POSE_NPAR;
+  for (int k = 0; k < POSE_NPAR; ++k) {
+    acc[1 + k] += J[k] * r0;
+    for (int l = k; l < POSE_NPAR; ++l) acc[o++] += J[k] * J[l];
+  }
+}
+
+// solve (J^T J + lambda diag) d = -J^T r; false if singular
+NVS_HD bool refine_solve(const double* acc, double* d) {
+  double A[POSE_NPAR][POSE_NPAR + 1];
+  int o = 1 + POSE_NPAR;
+  for (int k = 0; k < POSE_NPAR; ++k)
+    for (int l = k; l < POSE_NPAR; ++l) { A[k][l] = acc[o]; A[l][k] = acc[o]; ++o; }
+  for (int k = 0; k < POSE_NPAR; ++k) {
+    A[k][k] *= 1.0 + 1e-6;
+    A[k][POSE_NPAR] = -acc[1 + k];
+  }
+  for (int k = 0; k < POSE_NPAR; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < POSE_NPAR; ++i)
+      if (fabs(A[i][k]) > fabs(A[piv][k])) piv = i;
+    if (!(fabs(A[piv][k]) > 1e-300)) return false;
+    if (piv != k)
+      for (int j = 0; j <= POSE_NPAR; ++j) { double tt = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = tt; }
+    for (int i = k + 1; i < POSE_NPAR; ++i) {
+      const double f = A[i][k] / A[k][k];
+      for (int j = k; j <= POSE_NPAR; ++j) A[i][j] -= f * A[k][j];
+    }
+  }
+  for (int k = POSE_NPAR - 1; k >= 0; --k) {
+    double v = A[k][POSE_NPAR];
+    for (int j = k + 1; j < POSE_NPAR; ++j) v -= A[k][j] * d[j];
+    d[k] = v / A[k][k];
+  }
+  for (int k = 0; k < POSE_NPAR; ++k)
+    if (!isfinite(d[k])) return false;
+  return true;
+}
+
 }  // namespace nvs_pose

@@ -103,7 +103,7 @@ def match_consecutive(sel: dict, cross_check: bool = False, ratio_test: float = 
 
 
 def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_test: float = kRatioTest,
-                     threshold: float = 0.0003, iters: int = 512, seed: int = 0):
+                     threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0):
     """Matching AND relative pose for a batch of consecutive frames without a host round trip
     (visual_odometry.py:314-345: match frame t against t-1, then estimatePose :383-412).
 
@@ -115,7 +115,7 @@ def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_tes
     i1, i2, dd, cnt = ops.match_batch(sel["desc"], sel["count"], a, a - 1, ratio=ratio_test,
                                       mode=1 if cross_check else 0)
     pose = ops.pose_batch(sel["pts"], a, a - 1, cnt, i1, i2, intrinsics=intrinsics, threshold=threshold, iters=iters,
-                          seed=seed)
+                          seed=seed, refine=refine)
     return (i1, i2, dd, cnt), pose
 
 
@@ -124,9 +124,10 @@ class PoseEstimator(object):
     VisualOdometry.estimatePose (visual_odometry.py:383-412).  ``cam`` is any object with fx, fy, cx, cy (the
     reference's PinholeCamera); lens distortion is not handled here (KITTI frames are rectified: D = 0)."""
 
-    def __init__(self, cam, threshold: float = 0.0003, iters: int = 512, seed: int = 0, device: str = "cuda"):
+    def __init__(self, cam, threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0,
+                 device: str = "cuda"):
         self.cam = cam
-        self.threshold, self.iters, self.seed, self.device = threshold, iters, seed, device
+        self.threshold, self.iters, self.seed, self.refine, self.device = threshold, iters, seed, refine, device
         self.mask_match = None
         self.E = None
 
@@ -139,7 +140,7 @@ class PoseEstimator(object):
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
         out = ops.pose_batch(pts, zero, zero + 1, torch.full((1,), n, dtype=torch.int32, device=self.device),
                              intrinsics=(self.cam.fx, self.cam.fy, self.cam.cx, self.cam.cy),
-                             threshold=self.threshold, iters=self.iters, seed=self.seed)
+                             threshold=self.threshold, iters=self.iters, seed=self.seed, refine=self.refine)
         self.mask_match = out["mask"][0].cpu().numpy().reshape(-1, 1)
         self.E = out["E"][0].cpu().numpy().astype(np.float64)
         return out["R"][0].cpu().numpy().astype(np.float64), out["t"][0].cpu().numpy().astype(np.float64).reshape(3, 1)

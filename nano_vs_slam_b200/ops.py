@@ -417,12 +417,14 @@ def match_batch(desc: torch.Tensor, counts: torch.Tensor, pair_a: torch.Tensor, 
 def pose_batch(pts: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor, count: torch.Tensor,
                idx1: Optional[torch.Tensor] = None, idx2: Optional[torch.Tensor] = None,
                intrinsics: Sequence[float] = (1.0, 1.0, 0.0, 0.0), threshold: float = 0.0003, iters: int = 512,
-               seed: int = 0, workspace: Optional[torch.Tensor] = None):
+               seed: int = 0, refine: int = 0, workspace: Optional[torch.Tensor] = None):
     """Relative pose of P frame pairs in one call (visual_odometry.py:383-412: findEssentialMat + recoverPose).
 
     ``pts`` (F,kmax,2) keypoint coordinates as written by select_keypoints, ``pair_a`` (current) / ``pair_b``
     (reference) (P,) frame indices, ``idx1`` / ``idx2`` / ``count`` as returned by match_batch (both idx None: the
     rows of ``pts`` are already matched).  ``intrinsics`` = (fx, fy, cx, cy) of the pinhole camera.
+    ``refine`` = 0 returns the best minimal-sample model (cv2.RANSAC behaviour); n > 0 adds up to n Gauss-Newton steps on
+    the consensus set (the local optimisation / polishing of cv2.USAC_MSAC).
     Returns dict(E (P,3,3), R (P,3,3), t (P,3), mask (P,kmax) uint8, inliers (P,) int32): x_ref ~ R x_cur + t."""
     pts = _req(pts)
     F_, kmax, two = pts.shape
@@ -448,10 +450,10 @@ def pose_batch(pts: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor, co
     fx, fy, cx, cy = (float(v) for v in intrinsics)
     check(lib().nvs_pose_batch(pts.data_ptr(), F_, kmax, pair_a.data_ptr(), pair_b.data_ptr(), _ptr(idx1), _ptr(idx2),
                                count.data_ptr(), P, fx, fy, cx, cy, float(threshold), int(iters),
-                               int(seed) & 0xFFFFFFFFFFFFFFFF, E.data_ptr(), R.data_ptr(), t.data_ptr(),
+                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(refine), E.data_ptr(), R.data_ptr(), t.data_ptr(),
                                mask.data_ptr(), inl.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()),
           "nvs_pose_batch")
-    LAUNCHES[0] += 4
+    LAUNCHES[0] += 5 if refine > 0 else 4
     return {"E": E, "R": R, "t": t, "mask": mask, "inliers": inl}
 
 

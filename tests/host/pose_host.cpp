@@ -19,7 +19,7 @@ extern "C" int nvs_host_real_roots(const double* p, int deg, double* roots) { re
 
 // cur / ref: (n,2) float normalised image coordinates.  Returns the inlier count; E, R (row-major), t, mask out.
 extern "C" int nvs_host_pose(const float* cur, const float* ref, int n, float thr, int iters, uint64_t seed, int pair,
-                             float* E_out, float* R_out, float* t_out, uint8_t* mask) {
+                             float* E_out, float* R_out, float* t_out, uint8_t* mask, int refine) {
   if (n < 5) return -1;
   const float thr2 = thr * thr;
   const float inv = 1.0f / thr2;
@@ -69,7 +69,45 @@ extern "C" int nvs_host_pose(const float* cur, const float* ref, int n, float th
     if (good[c] > good[b]) b = c;
   const double* R = (b & 1) ? R2 : R1;
   const double* tt = (b & 2) ? tn : t;
-  for (int e = 0; e < 9; ++e) R_out[e] = float(R[e]);
-  for (int e = 0; e < 3; ++e) t_out[e] = float(tt[e]);
+  double Rb[9], tb[3];
+  for (int e = 0; e < 9; ++e) Rb[e] = R[e];
+  for (int e = 0; e < 3; ++e) tb[e] = tt[e];
+  if (refine > 0) {
+    // Gauss-Newton on the consensus set, keeping the pose with the lowest truncated cost (same sequence as
+    // pose_refine_kernel)
+    double Rc[9], tc[3], best_cost = -1.0;
+    for (int e = 0; e < 9; ++e) Rc[e] = Rb[e];
+    for (int e = 0; e < 3; ++e) tc[e] = tb[e];
+    const double thr2d = double(thr2);
+    for (int iter = 0; iter <= refine; ++iter) {
+      double Es[6][9], acc[POSE_NACC];
+      for (int k = 0; k < POSE_NACC; ++k) acc[k] = 0.0;
+      refine_stencil(Rc, tc, Es);
+      for (int i = 0; i < n; ++i) refine_accumulate(Es, cur[2 * i], cur[2 * i + 1], ref[2 * i], ref[2 * i + 1], thr2d, acc);
+      const double cost = acc[POSE_NACC - 1];
+      if (best_cost >= 0.0 && !(cost < best_cost)) break;
+      best_cost = cost;
+      for (int e = 0; e < 9; ++e) Rb[e] = Rc[e];
+      for (int e = 0; e < 3; ++e) tb[e] = tc[e];
+      double d[POSE_NPAR], R2[9], t2[3];
+      if (iter == refine || !refine_solve(acc, d)) break;
+      perturb_pose(Rc, tc, d, R2, t2);
+      for (int e = 0; e < 9; ++e) Rc[e] = R2[e];
+      for (int e = 0; e < 3; ++e) tc[e] = t2[e];
+    }
+    double Ed2[9];
+    essential_from_pose(Rb, tb, Ed2);
+    double nrm = 0.0;
+    for (int e = 0; e < 9; ++e) nrm += Ed2[e] * Ed2[e];
+    nrm = sqrt(2.0 / nrm);
+    ninl = 0;
+    for (int e = 0; e < 9; ++e) { Eb[e] = float(Ed2[e] * nrm); E_out[e] = Eb[e]; }
+    for (int i = 0; i < n; ++i) {
+      mask[i] = sampson_sq<float>(Eb, cur[2 * i], cur[2 * i + 1], ref[2 * i], ref[2 * i + 1]) <= thr2;
+      ninl += mask[i];
+    }
+  }
+  for (int e = 0; e < 9; ++e) R_out[e] = float(Rb[e]);
+  for (int e = 0; e < 3; ++e) t_out[e] = float(tb[e]);
   return ninl;
 }

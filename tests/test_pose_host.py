@@ -80,7 +80,7 @@ def test_pose_matches_opencv_golden():
         dR, dt = rot_angle_deg(o["R"], z[f"R_cv{i}"]), dir_angle_deg(o["t"], z[f"t_cv{i}"])
         if float(z[f"noise{i}"]) == 0.0:
             assert np.array_equal(mo, mc), i                     # identical consensus set
-            assert dR < 0.02 and dt < 0.01, (i, dR, dt)
+            assert dR < 2e-3 and dt < 0.01, (i, dR, dt)
         else:
             # minimal-sample estimates under noise above the threshold: same order of accuracy as OpenCV's
             assert dR < 0.2 and dt < 3.0, (i, dR, dt)
@@ -104,3 +104,22 @@ def test_pose_is_deterministic_per_seed_and_handles_general_motion():
 def test_pose_too_few_matches():
     x1, x2, _, _ = _scene(4, 0)
     assert host_pose(x1, x2)["inliers"] == -1
+
+
+def test_refinement_lowers_truncated_cost_and_keeps_the_geometry():
+    """refine > 0: Gauss-Newton on the consensus set (the LO / polishing role of USAC_MSAC).  The truncated Sampson
+    cost of the returned E never increases, more matches become inliers under noise, the pose stays near the truth."""
+    z = np.load(GOLD)
+    thr2 = 0.0003 ** 2
+    for i in range(int(z["n_cases"])):
+        cur, ref = z[f"cur{i}"], z[f"ref{i}"]
+        a = host_pose(cur, ref, seed=7, pair=i)
+        b = host_pose(cur, ref, seed=7, pair=i, refine=10)
+        ca = np.minimum(sampson_sq(a["E"], cur, ref), thr2).sum()
+        cb = np.minimum(sampson_sq(b["E"], cur, ref), thr2).sum()
+        assert cb <= ca * (1 + 1e-6), (i, ca, cb)
+        assert abs(np.linalg.det(b["R"].astype(np.float64)) - 1) < 1e-5 and abs(np.linalg.norm(b["t"]) - 1) < 1e-5
+        assert b["inliers"] >= a["inliers"] - 1, (i, a["inliers"], b["inliers"])
+        assert rot_angle_deg(b["R"], z[f"R_true{i}"]) < 0.1 and dir_angle_deg(b["t"], z[f"t_true{i}"]) < 1.5, i
+        if float(z[f"noise{i}"]) == 0.0:
+            assert rot_angle_deg(b["R"], z[f"R_cv{i}"]) < 0.02 and dir_angle_deg(b["t"], z[f"t_cv{i}"]) < 0.02

@@ -19,14 +19,15 @@ pts = torch.from_numpy(np.concatenate([cur, ref]).astype(np.float32)).cuda()
 a = torch.arange(P, dtype=torch.int32, device="cuda")
 cnt = torch.full((P,), kmax, dtype=torch.int32, device="cuda")
 ws = torch.empty(int(ops.lib().nvs_pose_workspace_bytes(P, kmax, iters)), dtype=torch.uint8, device="cuda")
-for _ in range(3):
-    o = ops.pose_batch(pts, a, a + P, cnt, iters=iters, workspace=ws)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10):
-    o = ops.pose_batch(pts, a, a + P, cnt, iters=iters, workspace=ws)
-e1.record()
-torch.cuda.synchronize()
-print("pose_batch %d pairs x %d matches x %d samples: %.3f ms per call, inliers %s" %
-      (P, kmax, iters, e0.elapsed_time(e1) / 10, o["inliers"][:4].tolist()))
+for refine in (0, 10):
+    for _ in range(3):
+        o = ops.pose_batch(pts, a, a + P, cnt, iters=iters, refine=refine, workspace=ws)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        o = ops.pose_batch(pts, a, a + P, cnt, iters=iters, refine=refine, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    print("pose_batch %d pairs x %d matches x %d samples, refine %d: %.3f ms per call, inliers %s" %
+          (P, kmax, iters, refine, e0.elapsed_time(e1) / 10, o["inliers"][:4].tolist()))
