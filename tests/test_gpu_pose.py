@@ -57,6 +57,13 @@ def test_pose_batch_matches_host_harness_and_opencv():
         else:
             assert dR < 0.2 and dt < 3.0, (i, dR, dt)
             assert 0.85 < inl[p] / z[f"mask_cv{i}"].sum() < 1.15
+        if i in (2, 6):
+            # the independent numpy oracle (action-matrix five-point, DLT cheirality) at the same seed
+            from oracle import pose_ref as O
+
+            o = O.ransac_pose(cur, ref, seed=7, pair=p)
+            assert (o["mask"] != mask[p, :n].astype(bool)).mean() < 5e-3 and abs(o["inliers"] - int(inl[p])) <= 1
+            assert rot_angle_deg(R[p], o["R"]) < 5e-3 and dir_angle_deg(t[p], o["t"]) < 1e-2, i
 
 
 def test_pose_pixel_coordinates_indices_and_degenerate_pairs():

@@ -123,3 +123,53 @@ def test_refinement_lowers_truncated_cost_and_keeps_the_geometry():
         assert rot_angle_deg(b["R"], z[f"R_true{i}"]) < 0.1 and dir_angle_deg(b["t"], z[f"t_true{i}"]) < 1.5, i
         if float(z[f"noise{i}"]) == 0.0:
             assert rot_angle_deg(b["R"], z[f"R_cv{i}"]) < 0.02 and dir_angle_deg(b["t"], z[f"t_cv{i}"]) < 0.02
+
+
+# ---- the numpy oracle (oracle/pose_ref.py): pinned to OpenCV, then used to check the product algebra -----------------
+def test_oracle_consensus_rule_and_recover_pose_equal_opencv():
+    """Given OpenCV's own E: its mask is exactly `squared Sampson distance <= threshold^2`, and the oracle's
+    recoverPose restatement (SVD decomposition, DLT triangulation, depth test) returns OpenCV's R and t."""
+    from oracle import pose_ref as O
+
+    z = np.load(GOLD)
+    for i in range(int(z["n_cases"])):
+        cur, ref, E = z[f"cur{i}"], z[f"ref{i}"], z[f"E_cv{i}"]
+        err = O.sampson_sq(E, cur, ref)
+        mc = z[f"mask_cv{i}"].astype(bool)
+        border = np.abs(err - 0.0003 ** 2) < 1e-12          # cv2 evaluates in float; skip exact-threshold ties
+        assert np.array_equal((err <= 0.0003 ** 2)[~border], mc[~border]), i
+        if len(cur) <= 1500:
+            R, t, good = O.recover_pose(E, cur, ref)
+            assert rot_angle_deg(R, z[f"R_cv{i}"]) < 1e-5 and dir_angle_deg(t, z[f"t_cv{i}"]) < 1e-5, i
+
+
+def test_five_point_equals_oracle_action_matrix_solver():
+    """Two independent routes to the same solution set: tenth-degree polynomial (product) vs action-matrix eigenvectors."""
+    from oracle import pose_ref as O
+
+    def canon(E):
+        E = E / np.linalg.norm(E)
+        return E * np.sign(E.flat[np.argmax(np.abs(E))])
+
+    n_checked = 0
+    for seed in range(30):
+        x1, x2, _, _ = _scene(5, 100 + seed)
+        a = sorted((canon(E) for E in five_point(x1, x2)), key=lambda m: tuple(np.round(m.ravel(), 5)))
+        b = sorted((canon(E) for E in O.five_point(x1, x2)), key=lambda m: tuple(np.round(m.ravel(), 5)))
+        if len(a) != len(b):
+            continue  # a near-double root may be split by one solver and merged by the other
+        n_checked += 1
+        assert max(np.abs(p - q).max() for p, q in zip(a, b)) < 1e-6, seed
+    assert n_checked >= 25
+
+
+def test_same_seed_pipeline_equals_oracle():
+    from oracle import pose_ref as O
+
+    z = np.load(GOLD)
+    for i in (2, 5, 6):
+        cur, ref = z[f"cur{i}"], z[f"ref{i}"]
+        o = O.ransac_pose(cur, ref, seed=7, pair=i)
+        h = host_pose(cur, ref, seed=7, pair=i)
+        assert (o["mask"] != h["mask"].astype(bool)).mean() < 5e-3 and abs(o["inliers"] - h["inliers"]) <= 1
+        assert rot_angle_deg(o["R"], h["R"]) < 1e-3 and dir_angle_deg(o["t"], h["t"]) < 5e-3, i
