@@ -42,3 +42,29 @@ def test_every_kernel_file_is_sm100a_cuda_and_the_build_targets_it():
     tc = open(os.path.join(PKG, "csrc", "conv_tc.cu")).read() + open(os.path.join(PKG, "csrc", "retrieval.cu")).read()
     for needle in ("tcgen05.mma", "tcgen05.alloc", "tcgen05.commit", "cp.async.bulk.tensor", "mbarrier.try_wait"):
         assert needle in tc, needle
+
+
+def test_ops_refuse_cpu_tensors_instead_of_falling_back():
+    """No CPU fallback: every wrapper that takes tensors raises on host tensors before touching the library."""
+    import pytest
+    import torch
+
+    from nano_vs_slam_b200 import _cabi, ops
+
+    i32 = torch.zeros(1, dtype=torch.int32)
+    with pytest.raises(_cabi.NanovsError):
+        ops.pose_batch(torch.zeros(2, 8, 2), i32, i32 + 1, i32 + 8)
+    with pytest.raises(_cabi.NanovsError):
+        ops.match(torch.zeros(4, 32), torch.zeros(4, 32))
+    with pytest.raises(_cabi.NanovsError):
+        ops.select_keypoints(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4), torch.zeros(1, 32, 4, 4), 0.5, 4)
+
+
+def test_host_harness_is_test_infrastructure_only():
+    """tests/host/pose_host.cpp compiles the product's algebra header for CPU checks; nothing in the product tree
+    refers to it, and the library sources contain no host implementation of the pose pipeline."""
+    for path in _sources((".py", ".cu", ".cuh", ".h")):
+        text = open(path).read()
+        if path.endswith("pose_math.h"):
+            continue  # its header comment says who else compiles it
+        assert "pose_host" not in text and "nvs_host_" not in text, path
