@@ -173,3 +173,33 @@ def test_same_seed_pipeline_equals_oracle():
         h = host_pose(cur, ref, seed=7, pair=i)
         assert (o["mask"] != h["mask"].astype(bool)).mean() < 5e-3 and abs(o["inliers"] - h["inliers"]) <= 1
         assert rot_angle_deg(o["R"], h["R"]) < 1e-3 and dir_angle_deg(o["t"], h["t"]) < 5e-3, i
+
+
+def test_planar_scene_and_large_rotation():
+    """A dominant plane (road / facade) plus some structure off it, large inter-frame rotation.  (A purely planar scene
+    has two essential matrices that explain every match -- the twisted-pair of the plane homography -- so only scenes
+    with some depth relief determine the pose; minimal samples drawn entirely from the plane still produce the correct
+    E among their candidates, which the consensus over the off-plane matches then selects.)"""
+    rng = np.random.default_rng(11)
+    n = 500
+    # all points on the plane z = 8 + 0.3 x (a road / facade), sideways + forward motion, 12 degree rotation
+    X = np.c_[rng.uniform(-4, 4, n), rng.uniform(-2, 2, n), np.zeros(n)]
+    X[:, 2] = 8.0 + 0.3 * X[:, 0]
+    off = rng.random(n) < 0.2
+    X[off, 2] += rng.uniform(-3, 6, int(off.sum()))
+    w = np.array([0.05, 0.2, -0.03])
+    th = np.linalg.norm(w)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+    t = np.array([0.8, 0.1, 0.59])
+    t /= np.linalg.norm(t)
+    x1 = X[:, :2] / X[:, 2:3]
+    X2 = (R @ X.T).T + t
+    x2 = X2[:, :2] / X2[:, 2:3]
+    out = rng.random(n) < 0.3
+    x2[out] = rng.uniform(-0.6, 0.6, (int(out.sum()), 2))
+    for refine in (0, 10):
+        o = host_pose(x1, x2, seed=5, refine=refine)
+        assert abs(o["inliers"] - int((~out).sum())) <= 3
+        assert rot_angle_deg(o["R"], R) < 0.01 and dir_angle_deg(o["t"], t) < 0.05, refine
