@@ -53,3 +53,17 @@ for _ in range(10):
 e1.record(); torch.cuda.synchronize()
 print(f"match_consecutive alone: {e0.elapsed_time(e1) / 10:.3f} ms for {B - 1} pairs of 4000 keypoints; "
       f"matches/pair {float(cnt.float().mean()):.0f}")
+
+# whole tail of the VO front-end: select -> batched matching -> batched relative pose, no host round trip
+from nano_vs_slam_b200.matcher import pose_consecutive
+
+K = (718.856, 718.856, 607.19, 185.22)  # KITTI sequence 00 pinhole intrinsics
+for refine in (0, 10):
+    for _ in range(3):
+        pose_consecutive(sel, K, refine=refine)
+    e0.record()
+    for _ in range(10):
+        (_, _, _, cnt), pose = pose_consecutive(sel, K, refine=refine)
+    e1.record(); torch.cuda.synchronize()
+    print(f"match + pose (refine {refine}): {e0.elapsed_time(e1) / 10:.3f} ms for {B - 1} pairs; "
+          f"inliers/pair {float(pose['inliers'].float().mean()):.0f} of {float(cnt.float().mean()):.0f} matches")
