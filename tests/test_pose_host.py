@@ -8,7 +8,6 @@ minimal-sample estimate and are compared through their distance to each other an
 import os
 
 import numpy as np
-import pytest
 
 from pose_util import dir_angle_deg, five_point, host_pose, real_roots, rot_angle_deg, sampson_sq
 
