@@ -202,3 +202,28 @@ def test_planar_scene_and_large_rotation():
         o = host_pose(x1, x2, seed=5, refine=refine)
         assert abs(o["inliers"] - int((~out).sum())) <= 3
         assert rot_angle_deg(o["R"], R) < 0.01 and dir_angle_deg(o["t"], t) < 0.05, refine
+
+
+def test_five_point_degenerate_samples_stay_finite():
+    """Duplicated / collinear / coincident / tiny minimal samples: never a hang, never a non-finite candidate, every
+    returned E satisfies the five epipolar constraints; stationary frames give 'no model' (kernel: R = I, t = 0)."""
+    rng = np.random.default_rng(123)
+    for trial in range(1200):
+        kind = trial % 6
+        p1, p2 = rng.uniform(-1, 1, (5, 2)), rng.uniform(-1, 1, (5, 2))
+        if kind == 1:
+            p2 = p1.copy()
+        elif kind == 2:
+            p1[1], p2[1] = p1[0], p2[0]
+        elif kind == 3:
+            p1[:, 1], p2[:, 1] = 0.3 * p1[:, 0], 0.3 * p2[:, 0]
+        elif kind == 4:
+            p1, p2 = p1 * 1e-4, p2 * 1e-4
+        elif kind == 5:
+            p2 = p1 + 1e-9 * rng.normal(size=(5, 2))
+        Es = five_point(p1, p2)
+        assert len(Es) <= 10 and np.isfinite(Es).all()
+        for E in Es:
+            assert max(abs(np.r_[p2[k], 1] @ E @ np.r_[p1[k], 1]) for k in range(5)) < 1e-6, (trial, kind)
+    a = rng.uniform(-1, 1, (200, 2)).astype(np.float32)
+    assert host_pose(a, a.copy(), seed=1)["inliers"] == -2
