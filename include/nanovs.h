@@ -246,7 +246,8 @@ int nvs_match_batch(const float* des, const int32_t* counts, int32_t n_frames, i
  * frame) / pair_b (reference frame) (P); idx1 / idx2 (P, kmax) = match m -> keypoint index in frame a / b (both
  * NULL = identity, i.e. pts rows are already matched); count (P) matches per pair.  All DEVICE arrays.
  * Outputs: out_E (P,9) row-major with p_b^T E p_a = 0, out_R (P,9), out_t (P,3), out_mask (P,kmax) uint8,
- * out_inliers (P).  A pair with fewer than 5 matches yields E = 0, R = I, t = 0 and no inliers.
+ * out_inliers (P).  A pair with fewer than 5 matches, or one whose samples are all degenerate
+ * (two identical frames: every [t]x fits), yields E = 0, R = I, t = 0 and no inliers.
  * refine = 0: the result is the best minimal-sample model (what cv2.RANSAC returns); refine = n > 0: up to n
  * Gauss-Newton steps on the essential manifold over the consensus set, kept while the truncated cost decreases (the
  * role of local optimisation + final polishing in cv2.USAC_MSAC, the method the reference asks for first), after
