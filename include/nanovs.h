@@ -54,6 +54,8 @@ extern "C" {
 #define NVS_IN_U8_HWC 2     /* src0 = uint8 (B,H,W,3) camera frames; value = (u8 / 255 - 0.5) * 2 on load
                                (visual_odometry.py:283 + frontend.py:79).  Stem layer only: ksize 3, c0 = c0_total = 3,
                                cout 16, NVS_OUT_PLAIN, dst_nhwc */
+#define NVS_IN_UNIT 3       /* src0 = fp32 NCHW frames in [0,1]; value = (x - 0.5) * 2 on load (frontend.py:79).  Stem
+                               layer only, same constraints as NVS_IN_U8_HWC */
 
 const char* nvs_last_error(void);
 int nvs_abi_version(void);

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("NVS_LIB_PATH") or os.path.join(HERE, "lib", "libnanov
 NVS_OK = 0
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SIGMOID_TANH, ACT_GELU = range(7)
 OUT_PLAIN, OUT_POOL, OUT_BOTH, OUT_SHUFFLE = range(4)
-IN_PLAIN, IN_S2D, IN_U8_HWC = range(3)
+IN_PLAIN, IN_S2D, IN_U8_HWC, IN_UNIT = range(4)
 
 _vp, _i32, _f32, _f64, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_size_t, C.c_int64
 _u64 = C.c_uint64

@@ -34,3 +34,16 @@ extern "C" int nvs_device_ok(void) {
   }
   return NVS_OK;
 }
+
+// SM count of the current device, cached per device ordinal (a process may drive several GPUs).
+int nvs_sm_count(void) {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int v = __atomic_load_n(&cache[dev & 63], __ATOMIC_RELAXED);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    __atomic_store_n(&cache[dev & 63], v, __ATOMIC_RELAXED);
+  }
+  return v;
+}

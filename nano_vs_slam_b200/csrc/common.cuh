@@ -12,6 +12,22 @@
   } while (0)
 
 int nvs_set_cuda_error(cudaError_t e);  // cabi.cu: records the message, returns NVS_ERR_CUDA
+int nvs_sm_count(void);                 // cabi.cu: SM count of the CURRENT device (cached per device)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: opt in once per (kernel, device).
+// One 64-bit mask per call site (bit = device ordinal); the benign race just repeats an idempotent call.
+#define NVS_OPT_IN_SMEM(kernel, bytes)                                                              \
+  do {                                                                                              \
+    static unsigned long long done_mask__ = 0ull;                                                   \
+    int dev__ = 0;                                                                                  \
+    cudaGetDevice(&dev__);                                                                          \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                          \
+    if (!(__atomic_load_n(&done_mask__, __ATOMIC_ACQUIRE) & bit__)) {                               \
+      cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      if (e__ != cudaSuccess) return nvs_set_cuda_error(e__);                                       \
+      __atomic_fetch_or(&done_mask__, bit__, __ATOMIC_RELEASE);                                     \
+    }                                                                                               \
+  } while (0)
 
 namespace nvs {
 

@@ -322,12 +322,7 @@ static int launch_conv(const ConvP& p0, int B, cudaStream_t st) {
   const int tiles_y = (p.H + C::TH - 1) / C::TH;
   dim3 grid(p.tiles_x * tiles_y, p.cout_pad / C::CT, B);
   auto kern = conv_kernel<KS, CK, WN, WM, NARROW>;
-  static bool attr_done = false;  // benign race: idempotent
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return nvs_set_cuda_error(e);
-    attr_done = true;
-  }
+  NVS_OPT_IN_SMEM(kern, C::SMEM);
   kern<<<grid, C::NT, C::SMEM, st>>>(p);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
@@ -380,6 +375,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(ConvP p) {
   // (frontend.py:79) happen here, in the same fp32 operations, so the fp32 NCHW copy of the input never exists
   const unsigned char* src8 = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)b * p.H * p.W * 3;
   const bool u8 = p.in_mode == NVS_IN_U8_HWC;
+  const bool unit = p.in_mode == NVS_IN_UNIT;  // fp32 frames in [0,1]: x.sub(0.5).mul(2.0) of frontend.py:79 on load
   for (int i = threadIdx.x; i < 3 * (STEM_TY + 2) * (STEM_TX + 2); i += 128) {
     const int c = i / ((STEM_TY + 2) * (STEM_TX + 2)), r = i - c * (STEM_TY + 2) * (STEM_TX + 2);
     const int yy = r / (STEM_TX + 2), xx = r - yy * (STEM_TX + 2);
@@ -388,6 +384,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(ConvP p) {
     if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
       if (u8) v = __fmul_rn(__fsub_rn(__fdiv_rn((float)src8[((size_t)gy * p.W + gx) * 3 + c], 255.f), 0.5f), 2.f);
       else v = src[((size_t)c * p.H + gy) * p.W + gx];
+      if (unit) v = __fmul_rn(__fsub_rn(v, 0.5f), 2.f);
     }
     tile[c][yy][xx] = make_float2(v, v);
   }
@@ -513,11 +510,12 @@ extern "C" int nvs_conv(const NvsConvArgs* a, void* stream) {
   if (a->out_mode == NVS_OUT_SHUFFLE && a->dst_nhwc) return NVS_ERR_UNSUPPORTED;
   p.tiles_x = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->in_mode == NVS_IN_U8_HWC &&
+  if ((a->in_mode == NVS_IN_U8_HWC || a->in_mode == NVS_IN_UNIT) &&
       !(a->ksize == 3 && cin == 3 && a->c0_total == 3 && a->c0_off == 0 && a->c1 == 0 && a->out_mode == NVS_OUT_PLAIN &&
         a->dst_nhwc && a->cout == STEM_CO))
-    return NVS_ERR_UNSUPPORTED;  // uint8 frames are read by the stem kernel only
-  if (a->ksize == 3 && cin == 3 && a->c1 == 0 && (a->in_mode == NVS_IN_PLAIN || a->in_mode == NVS_IN_U8_HWC) &&
+    return NVS_ERR_UNSUPPORTED;  // uint8 / [0,1] frames are read by the stem kernel only
+  if (a->ksize == 3 && cin == 3 && a->c1 == 0 &&
+      (a->in_mode == NVS_IN_PLAIN || a->in_mode == NVS_IN_U8_HWC || a->in_mode == NVS_IN_UNIT) &&
       a->out_mode == NVS_OUT_PLAIN &&
       a->dst_nhwc && a->cout == STEM_CO && (a->dst_c_total % 4) == 0 && (a->dst_c_off % 4) == 0 &&
       (a->act == NVS_ACT_NONE || a->act == NVS_ACT_LRELU || a->act == NVS_ACT_RELU)) {

@@ -745,17 +745,9 @@ static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int
 template <int COUT, int KC, bool PAIR = false>
 static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   using C = Cfg<COUT, KC, PAIR>;
-  static bool done = false;
-  static int sms = 0;
-  if (!done) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<COUT, KC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
-    if (e != cudaSuccess) return nvs_set_cuda_error(e);
-    done = true;
-  }
+  auto kern = conv_tc_kernel<COUT, KC, PAIR>;
+  NVS_OPT_IN_SMEM(kern, C::SMEM_BYTES);
+  const int sms = nvs_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
   while (C::NS % q.issuers != 0) --q.issuers;  // a slot must always be consumed by the same issuer

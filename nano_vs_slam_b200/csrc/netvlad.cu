@@ -203,12 +203,7 @@ static int run_netvlad(const float* x, const float* w, const float* cent, float*
   int per = (S + splits - 1) / splits;
   per = (per + VP - 1) / VP * VP;
   auto kern = netvlad_partial_kernel<C, K>;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e != cudaSuccess) return nvs_set_cuda_error(e);
-    done = true;
-  }
+  NVS_OPT_IN_SMEM(kern, Cfg::SMEM);
   kern<<<dim3(splits, B), 256, Cfg::SMEM, st>>>(x, w, ws, S, per);
   NVS_CHECK_LAUNCH();
   netvlad_finish_kernel<<<B, 256, sizeof(float) * K * C, st>>>(ws, cent, vlad, C, K, splits);

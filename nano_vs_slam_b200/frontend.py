@@ -14,7 +14,7 @@ from typing import Dict, Iterable, Iterator, Optional, Sequence
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, torch_ops
 from .kp2dtiny import tiny_factory
 
 
@@ -65,20 +65,20 @@ class KP2DtinyFrontend(object):
             # into the first conv's load stage when no resize is needed (visual_odometry.py:281-291)
             B, Hi, Wi, _ = x.shape
             if self.new_size is not None and tuple(self.new_size) != (Hi, Wi):
-                x = ops.preprocess_u8(x, self.new_size)
+                x = torch.ops.nanovs.preprocess_u8(x, list(self.new_size))
                 H, W = x.shape[2:]
             else:
                 H, W = Hi, Wi
+            unit = False
         else:
-            if not normalized:
-                x = x.sub(0.5).mul(2.0)  # frontend.py:79
+            unit = not normalized  # [0,1] frames: x.sub(0.5).mul(2.0) (frontend.py:79) happens in the stem kernel's load
             _, _, H, W = x.shape
-        out = self.net.forward(x)
+        out = self.net.forward(x, unit_input=unit)
         post = self.net.post_processing(out, H, W)
         seg_cells = post["seg"] if self.apply_semantic_filer else None
-        sel = ops.select_keypoints(post["score"], post["coord"], post["feat"], self.nn_thresh, self.top_k,
-                                   seg_cells=seg_cells,
-                                   classes_to_filter=self.classes_to_filter if self.apply_semantic_filer else None)
+        sel = torch_ops.select_keypoints(post["score"], post["coord"], post["feat"], self.nn_thresh, self.top_k,
+                                         seg_cells=seg_cells,
+                                         classes_to_filter=self.classes_to_filter if self.apply_semantic_filer else None)
         return sel, post
 
     @torch.no_grad()
@@ -91,13 +91,15 @@ class KP2DtinyFrontend(object):
         (H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i; B200 has independent copy
         engines per direction), so the host always gets every batch's results, one batch behind the GPU.
         Yields, per batch: pts (B,k,2), desc (B,k,D), score (B,k), count (B,), vlad (B,G) [, seg (B,1,H/2,W/2)].
-        The yielded tensors are views of two pinned buffers owned by this object: a result stays valid until two more
-        batches have been yielded (also across stream() calls) -- copy what must live longer."""
+        The yielded tensors are views of three pinned result sets owned by this object and used in rotation: the
+        device-to-host copy of batch s+3 reuses the set of batch s and is enqueued when the consumer asks for the
+        batch after s+1, so a result may be held across ONE further next() (a = next(g); b = next(g); use(a) is
+        safe), not longer (also across stream() calls) -- copy what must live longer."""
         dev = torch.device(self.device)
         comp = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        # two pinned result sets, alternated and kept across stream() calls (cudaHostAlloc of ~80 MB costs tens of
-        # milliseconds); a yielded dict stays valid until two more batches have been yielded
+        # three pinned result sets, rotated and kept across stream() calls (cudaHostAlloc of ~80 MB costs tens of
+        # milliseconds): one being filled, one just yielded, one the consumer may still hold from the yield before
         host_sets: list = self.__dict__.setdefault("_host_sets", [])
         # three device input buffers, rotated and kept across calls: nothing on this path goes through
         # record_stream (which defers block reuse and makes the caching allocator fall back to cudaMalloc /
@@ -154,7 +156,8 @@ class KP2DtinyFrontend(object):
                        "vlad": post["vlad"]}
             if with_seg:
                 dev_out["seg"] = post["seg"]
-            slot = step % 2
+            slot = self.__dict__.get("_host_rr", 0)  # rotation continues across stream() calls
+            self._host_rr = (slot + 1) % 3
             if len(host_sets) <= slot or any(k not in host_sets[slot] or host_sets[slot][k].shape != v.shape or
                                              host_sets[slot][k].dtype != v.dtype for k, v in dev_out.items()):
                 fresh = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_out.items()}

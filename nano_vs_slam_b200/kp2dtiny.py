@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, torch_ops
 from ._cabi import NanovsError
 
 # ----------------------------------------------------------------------------------------------
@@ -327,6 +327,7 @@ class _Plan:
         self.graph_x = None
         self.graph_outs: Optional[Dict[str, torch.Tensor]] = None
         self.runs = 0
+        self.in_mode = ops.IN_PLAIN       # how the stem layer reads its input (IN_PLAIN / IN_U8_HWC / IN_UNIT)
         model._build_plan(self)
 
     def buf(self, name: str, c: int, h: int, w: int) -> torch.Tensor:
@@ -385,6 +386,7 @@ class _KP2DTinyBase(nn.Module):
         self._packed = None
         self._packed_key = None
         self._plans: Dict = {}
+        self._handle = None  # torch.ops.nanovs.kp2dtiny_forward handle (torch_ops.register_model)
         if self.downsample not in (2, 3):
             raise NotImplementedError("downsample must be 2 (cell 4) or 3 (cell 8, letter F)")
         if self.upscale_method not in ("pixelshuffle", "convtranspose"):
@@ -600,26 +602,66 @@ class _KP2DTinyBase(nn.Module):
                                "of 4 (pixel-shuffle/skip concat sizes would differ, as in the reference)")
         if u8:
             x = x.contiguous()
-            fused = self.conv_backend == "tc" and self.channel_dims[0] == 16  # the stem kernel (3 -> 16) reads uint8
-            return x if fused else ops.preprocess_u8(x)
+            return x if self._stem_fuses_input() else ops.preprocess_u8(x)
         return x.contiguous().float()
 
+    def _forward_keys(self):
+        """Order of the tensors returned by torch.ops.nanovs.kp2dtiny_forward."""
+        return ("score", "coord", "feat", "vlad", "seg") + (("depth",) if self.depth else ())
+
+    def _forward_shapes(self, B: int, H: int, W: int):
+        """Output shapes of forward for a (B,3,H,W) input, in _forward_keys order (fake / meta implementation)."""
+        H1, W1 = H // 2, W // 2
+        H2, W2 = (H1, W1) if self.downsample == 2 else (H1 // 2, W1 // 2)
+        H4, W4 = H2 // 2, W2 // 2
+        vh = self.vlad_head
+        vlad = (B, self.encoder_dim, H4, W4) if vh.remove_netvlad else (B, self.global_desc_dim)
+        shapes = [(B, 1, H4, W4), (B, 2, H4, W4), (B, self.nfeatures, H2, W2), vlad, (B, self.nClasses, H2, W2)]
+        if self.depth:
+            shapes.append((B, 1, H2, W2))
+        return shapes
+
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, unit_input: bool = False):
         """Returns {'score','coord','feat','vlad','seg'} like kp2dtiny.py:552-591 / :906-957.
-        ``x``: (B,3,H,W) fp32 in [-1,1] as in the reference, or uint8 (B,H,W,3) camera frames."""
+        ``x``: (B,3,H,W) fp32 in [-1,1] as in the reference, or uint8 (B,H,W,3) camera frames.
+        ``unit_input``: ``x`` is fp32 in [0,1] and the ``x.sub(0.5).mul(2.0)`` of the reference's own callers
+        (frontend.py:79) is applied by the first kernel's load stage instead of a separate pass over the batch.
+        The work is ONE custom operator, torch.ops.nanovs.kp2dtiny_forward (CUDA dispatch key only), whose
+        implementation replays this module's launch plan through the C ABI."""
+        if self.training is not False or not isinstance(x, torch.Tensor) or not x.is_cuda:
+            self._check_input(x)  # raises the reference-facing error (training mode / CPU tensor / bad shape)
+        if self._handle != id(self):  # first call, or a deepcopy that inherited the original's handle
+            self._handle = torch_ops.register_model(self)
+        outs = torch.ops.nanovs.kp2dtiny_forward(x, self._handle, bool(unit_input))
+        return dict(zip(self._forward_keys(), outs))
+
+    def _stem_fuses_input(self) -> bool:
+        """The stem kernel (3 -> 16, tensor-core backend) converts uint8 / [0,1] frames in its load stage."""
+        return self.conv_backend == "tc" and self.channel_dims[0] == 16
+
+    @torch.no_grad()
+    def _forward_impl(self, x, unit_input: bool = False):
         x = self._check_input(x)
         if x.dtype == torch.uint8:
             B, H, W, _ = x.shape
+            in_mode = ops.IN_U8_HWC
         else:
             B, _, H, W = x.shape
+            in_mode = ops.IN_PLAIN
+            if unit_input and self._stem_fuses_input():
+                in_mode = ops.IN_UNIT
+            elif unit_input:
+                x = x.sub(0.5).mul(2.0)  # the reference's own line (frontend.py:79); FFMA backend / wide stems only
         self._ensure_packed(x.device)
-        key = (B, H, W, x.device, x.dtype == torch.uint8)  # uint8 frames: own plan (own CUDA graph + staging buffer)
+        # uint8 / [0,1] frames: own plan (own CUDA graph with the input mode baked in + own staging buffer)
+        key = (B, H, W, x.device, in_mode)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 4:
                 self._plans.clear()
             plan = self._plans[key] = _Plan(self, B, H, W, x.device)
+            plan.in_mode = in_mode
         return self._run(plan, x)
 
     def _launch_all(self, plan: _Plan, x: torch.Tensor, outs: Dict[str, torch.Tensor]) -> None:
@@ -628,7 +670,7 @@ class _KP2DTinyBase(nn.Module):
             for a in slots:
                 a.dst = outs[name].data_ptr()
         plan.in_args.src0 = x.data_ptr()
-        plan.in_args.in_mode = ops.IN_U8_HWC if x.dtype == torch.uint8 else ops.IN_PLAIN
+        plan.in_args.in_mode = plan.in_mode
         run_conv = ops.run_conv
         prof = plan.profile
         for i, st in enumerate(plan.steps):
@@ -973,11 +1015,12 @@ class _KP2DTinyBase(nn.Module):
         if not score.is_cuda:
             raise NanovsError("post_processing needs CUDA tensors (no CPU fallback)")
         sample = self.training is False
-        o_s, o_c, o_f = ops.decode(score, shift, feat if sample else None, H, W, self.cell, self.cross_ratio)
+        o_s, o_c, o_f = torch.ops.nanovs.decode(score, shift, feat if sample else None, H, W, self.cell,
+                                                self.cross_ratio)
         if sample:
             seg = out["seg"]
             # V2: argmax(softmax(logits)) == argmax(logits); V3: forward already returned probabilities
-            out["seg"] = ops.seg_argmax(seg, o_c if self.sample_segmentation else None, H, W)
+            out["seg"] = torch.ops.nanovs.seg_argmax(seg, o_c if self.sample_segmentation else None, H, W)
             out["feat"] = o_f
         else:
             out["feat"] = feat
@@ -991,7 +1034,7 @@ class _KP2DTinyBase(nn.Module):
         if x.dtype == torch.uint8:
             x = ops.preprocess_u8(x)
         self.forward(x)
-        plan = self._plans[(x.shape[0], x.shape[2], x.shape[3], x.device, False)]
+        plan = self._plans[(x.shape[0], x.shape[2], x.shape[3], x.device, ops.IN_PLAIN)]
         return ops.l2norm_channels(plan.bufs["v3"])
 
 

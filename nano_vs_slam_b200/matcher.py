@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, torch_ops  # noqa: F401  (torch_ops registers torch.ops.nanovs.*)
 
 kRatioTest = 0.7  # feature_matcher.py:26
 NORM_L2 = 4       # cv2.NORM_L2
@@ -33,11 +33,12 @@ class BfFeatureMatcher(object):
     def match_device(self, des1, des2, ratio_test=None):
         ratio = self.ratio_test if ratio_test is None else ratio_test
         mode = 1 if self.cross_check else 0
-        return ops.match(self._dev(des1), self._dev(des2), ratio=ratio, mode=mode)
+        return torch.ops.nanovs.match(self._dev(des1), self._dev(des2), float(ratio), mode)
 
     def knn_match(self, des1, des2):
         """cv2.BFMatcher.knnMatch(des1, des2, k=2) as (idx (n1,2), dist (n1,2)) device tensors."""
-        return ops.match(self._dev(des1), self._dev(des2), mode=2)
+        idx, _, dist, _ = torch.ops.nanovs.match(self._dev(des1), self._dev(des2), kRatioTest, 2)
+        return idx, dist
 
     def match(self, des1, des2, ratio_test=None):
         i1, i2, dd, cnt = self.match_device(des1, des2, ratio_test)
@@ -58,8 +59,8 @@ def match_selected(sel: dict, i: int, j: int, cross_check: bool = True, ratio_te
     if ni == 0 or nj == 0:
         z = np.zeros((0, 2), np.float32)
         return z, z.copy(), np.zeros((0,), np.float32)
-    i1, i2, dd, cnt = ops.match(sel["desc"][i, :ni].contiguous(), sel["desc"][j, :nj].contiguous(), ratio=ratio_test,
-                                mode=1 if cross_check else 0)
+    i1, i2, dd, cnt = torch.ops.nanovs.match(sel["desc"][i, :ni].contiguous(), sel["desc"][j, :nj].contiguous(),
+                                             float(ratio_test), 1 if cross_check else 0)
     # one packed tensor = one D2H: rows [x_i, y_i, x_j, y_j, dist], then the count in the last row
     m = i1.shape[0]
     packed = torch.empty(m + 1, 5, device=i1.device, dtype=torch.float32)
@@ -99,7 +100,7 @@ def match_consecutive(sel: dict, cross_check: bool = False, ratio_test: float = 
     B = sel["desc"].shape[0]
     dev = sel["desc"].device
     a = torch.arange(1, B, device=dev, dtype=torch.int32)
-    return ops.match_batch(sel["desc"], sel["count"], a, a - 1, ratio=ratio_test, mode=1 if cross_check else 0)
+    return torch.ops.nanovs.match_batch(sel["desc"], sel["count"], a, a - 1, float(ratio_test), 1 if cross_check else 0)
 
 
 def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_test: float = kRatioTest,
@@ -112,10 +113,10 @@ def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_tes
     B = sel["desc"].shape[0]
     dev = sel["desc"].device
     a = torch.arange(1, B, device=dev, dtype=torch.int32)
-    i1, i2, dd, cnt = ops.match_batch(sel["desc"], sel["count"], a, a - 1, ratio=ratio_test,
-                                      mode=1 if cross_check else 0)
-    pose = ops.pose_batch(sel["pts"], a, a - 1, cnt, i1, i2, intrinsics=intrinsics, threshold=threshold, iters=iters,
-                          seed=seed, refine=refine)
+    i1, i2, dd, cnt = torch.ops.nanovs.match_batch(sel["desc"], sel["count"], a, a - 1, float(ratio_test),
+                                                   1 if cross_check else 0)
+    pose = torch_ops.pose_batch(sel["pts"], a, a - 1, cnt, i1, i2, intrinsics=intrinsics, threshold=threshold,
+                                iters=iters, seed=seed, refine=refine)
     return (i1, i2, dd, cnt), pose
 
 
@@ -138,9 +139,9 @@ class PoseEstimator(object):
         assert kps_cur.shape[0] == n
         pts = torch.from_numpy(np.stack([kps_cur, kps_ref])).to(self.device)  # frame 0 = current, 1 = reference
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
-        out = ops.pose_batch(pts, zero, zero + 1, torch.full((1,), n, dtype=torch.int32, device=self.device),
-                             intrinsics=(self.cam.fx, self.cam.fy, self.cam.cx, self.cam.cy),
-                             threshold=self.threshold, iters=self.iters, seed=self.seed, refine=self.refine)
+        out = torch_ops.pose_batch(pts, zero, zero + 1, torch.full((1,), n, dtype=torch.int32, device=self.device),
+                                   intrinsics=(self.cam.fx, self.cam.fy, self.cam.cx, self.cam.cy),
+                                   threshold=self.threshold, iters=self.iters, seed=self.seed, refine=self.refine)
         self.mask_match = out["mask"][0].cpu().numpy().reshape(-1, 1)
         self.E = out["E"][0].cpu().numpy().astype(np.float64)
         return out["R"][0].cpu().numpy().astype(np.float64), out["t"][0].cpu().numpy().astype(np.float64).reshape(3, 1)

@@ -12,7 +12,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMOID_TANH, ACT_TANH,  # noqa: F401
-                    IN_PLAIN, IN_S2D, IN_U8_HWC, OUT_BOTH, OUT_PLAIN, OUT_POOL, OUT_SHUFFLE, NvsConvArgs, check, lib)
+                    IN_PLAIN, IN_S2D, IN_U8_HWC, IN_UNIT, OUT_BOTH, OUT_PLAIN, OUT_POOL, OUT_SHUFFLE, NvsConvArgs, check, lib)
 
 
 # number of libnanovs kernels launched by this process (bench.py reports it as "gpu_launches")

@@ -17,7 +17,7 @@ from typing import Callable, Optional, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, torch_ops
 from ._cabi import check, lib
 
 KMAX = 31
@@ -54,7 +54,16 @@ class IndexFlatL2(object):
         self.ntotal = n
 
     def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0, gemm_events=None):
-        """``gemm_events``: optional (start, stop) torch.cuda.Event pair recorded around the GEMM kernel."""
+        """``gemm_events``: optional (start, stop) torch.cuda.Event pair recorded around the GEMM kernel.
+        Runs as the custom operator torch.ops.nanovs.flat_l2_search (CUDA dispatch key only)."""
+        self._gemm_events = gemm_events
+        try:
+            return torch.ops.nanovs.flat_l2_search(q, torch_ops.register_index(self), int(k), int(id_offset))
+        finally:
+            self._gemm_events = None
+
+    def _search_impl(self, q: torch.Tensor, k: int, id_offset: int = 0):
+        gemm_events = getattr(self, "_gemm_events", None)
         assert self.ntotal > 0, "empty index"
         if k > KMAX:
             raise NotImplementedError(f"k <= {KMAX} (per-row top-k list lives in shared memory)")
@@ -87,6 +96,10 @@ class IndexFlatL2(object):
 
 def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor):
     """(parts, Q, k) sorted partial results -> (Q, k) global top-k (csrc/retrieval.cu merge_parts_kernel)."""
+    return torch.ops.nanovs.topk_merge(D_parts, I_parts)
+
+
+def _merge_topk_impl(D_parts: torch.Tensor, I_parts: torch.Tensor):
     parts, nq, k = D_parts.shape
     D_parts, I_parts = D_parts.contiguous(), I_parts.contiguous()
     D = torch.empty(nq, k, dtype=torch.float32, device=D_parts.device)

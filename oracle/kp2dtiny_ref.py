@@ -159,8 +159,13 @@ def efficient_self_attention(x: Tensor, sd: SD, p: str, heads: int = 4) -> Tenso
         return t.reshape(b, heads, d, hh * ww).permute(0, 1, 3, 2).reshape(b * heads, hh * ww, d)
 
     q, k, v = split(q), split(k), split(v)
-    sim = torch.matmul(q, k.transpose(-2, -1)) * (d ** -0.5)
-    out = torch.matmul(sim.softmax(dim=-1), v)  # (b h) n d
+    # softmax is per query row, so the rows can be processed in blocks: the same arithmetic as the reference's
+    # single matmul, without its (b h) x n x m temporary (4.3 GB per 512x1024 frame)
+    rows = max(1, (1 << 26) // max(1, k.shape[1]))
+    out = torch.empty_like(q)
+    for r0 in range(0, q.shape[1], rows):
+        sim = torch.matmul(q[:, r0:r0 + rows], k.transpose(-2, -1)) * (d ** -0.5)
+        out[:, r0:r0 + rows] = torch.matmul(sim.softmax(dim=-1), v)  # (b h) n d
     out = out.reshape(B, heads, h * w, d).permute(0, 1, 3, 2).reshape(B, C, h, w)
     return F.conv2d(out, sd[p + ".to_out.weight"])
 

@@ -75,16 +75,30 @@ def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W, backend):
     assert float((post["coord"].cpu() - rpost["coord"]).abs().max()) < 1e-3
     assert rel_err(post["feat"], rpost["feat"]) < (POST_FEAT_TOL_TC if m.conv_backend == "tc" else REL_TOL)
     assert (post["seg"].cpu() == rpost["seg"]).float().mean() >= 0.999
-    # keypoint sets (threshold + top-k), per frame, Jaccard >= 99.9 %
-    thr = float(rpost["score"].flatten().kthvalue(int(0.8 * rpost["score"].numel())).values)  # ~20 % pass
-    sel = ops.select_keypoints(post["score"], post["coord"], post["feat"], thr, 300)
+    # keypoint sets (threshold + top-k), per frame: Jaccard >= 99.9 % (north_star), coordinates of the common
+    # keypoints within 1e-3 px.  k = 1000 at 240x320-class frames, 4000 at KITTI size (the reference's own settings,
+    # descriptor.py:31-35 / frontend.py top_k), so that 0.1 % is more than one keypoint.  The threshold sits in the
+    # middle of the widest gap between consecutive reference scores near the 80 % quantile (~20 % of the cells pass):
+    # a threshold placed ON a score value would make that one cell a coin flip.
+    top_k = 4000 if H * W > 240 * 320 else 1000
+    flat = rpost["score"].flatten().sort().values
+    i0 = int(0.8 * flat.numel())
+    win = flat[i0 - 16:i0 + 17]
+    j = int((win[1:] - win[:-1]).argmax())
+    thr = float((win[j] + win[j + 1]) / 2)
+    sel = ops.select_keypoints(post["score"], post["coord"], post["feat"], thr, top_k)
     for b in range(B):
         one = {k: rpost[k][b:b + 1] for k in ("score", "coord", "feat", "seg")}
-        pts, desc, _, cells = glue_ref.frontend_decode(one, 32, thr, 300)
+        pts, desc, _, cells = glue_ref.frontend_decode(one, 32, thr, top_k)
         n = int(sel["count"][b])
-        got = set(sel["cell"][b, :n].cpu().tolist())
-        jac = len(got & set(cells.tolist())) / max(1, len(got | set(cells.tolist())))
-        assert jac >= 0.99, jac  # single near-threshold flips allowed at k=300 (1/300 > 0.1 %)
+        got_cells = sel["cell"][b, :n].cpu().tolist()
+        got, want = set(got_cells), set(cells.tolist())
+        jac = len(got & want) / max(1, len(got | want))
+        assert jac >= 0.999, (jac, n, len(want))
+        ref_xy = {int(c): p for c, p in zip(cells.tolist(), pts)}
+        got_xy = sel["pts"][b, :n].cpu().numpy()
+        worst = max((abs(got_xy[i] - ref_xy[c]).max() for i, c in enumerate(got_cells) if c in ref_xy), default=0.0)
+        assert worst < 1e-3, worst
 
 
 @pytest.mark.parametrize("letter,v3", [("S", False), ("S_A", True), ("N", True), ("N_A", False)])

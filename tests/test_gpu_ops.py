@@ -144,6 +144,33 @@ def test_attention(C, h, w):
     assert rel_err(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("C,h,w", [(64, 130, 134), (48, 128, 130)])
+def test_attention_large_maps_four_queries_per_thread(C, h, w):
+    """Nq >= 16384 selects the 4-queries-per-thread instantiations (attention.cu, the 512x1024 S_A workload of
+    BASELINE config 4); head_dim 16 and 12, ragged Nq (not a multiple of 512) and Nk (not a multiple of 256 or 8).
+    The CPU reference is the literal softmax(q k^T d^-1/2) v of segformer.py:113-133, evaluated in query blocks."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + h)
+    heads, d = 4, C // 4
+    Nq, Nk = h * w, (h // 2) * (w // 2)
+    assert Nq >= 16384 and Nq % 512 != 0 and Nk % 8 != 0
+    q = torch.randn(1, C, h, w, generator=g)
+    kv = torch.randn(1, 2 * C, h // 2, w // 2, generator=g)
+    out = ops.attention(q.cuda(), kv.cuda(), heads)
+
+    def split(t):
+        b, _, hh, ww = t.shape
+        return t.reshape(b, heads, d, hh * ww).permute(0, 1, 3, 2)
+
+    qq, kk, vv = split(q), split(kv[:, :C]), split(kv[:, C:])
+    ref = torch.empty_like(qq)
+    for r0 in range(0, Nq, 4096):
+        sim = torch.matmul(qq[:, :, r0:r0 + 4096], kk.transpose(-1, -2)) * d ** -0.5
+        ref[:, :, r0:r0 + 4096] = torch.matmul(sim.softmax(-1), vv)
+    ref = ref.permute(0, 1, 3, 2).reshape(1, C, h, w)
+    assert rel_err(out, ref) < 2e-5
+
+
 @pytest.mark.parametrize("C,K,h,w,B", [(64, 64, 15, 20, 2), (48, 32, 10, 14, 3), (48, 64, 60, 80, 1), (64, 64, 7, 9, 5)])
 def test_netvlad(C, K, h, w, B):
     ops = _ops()
