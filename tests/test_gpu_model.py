@@ -55,6 +55,7 @@ def test_model_matches_reference_golden(path):
     ("S", False, 19, 1, 376, 1241, None),     # config 3 KITTI shape (odd W, odd W/8), tensor-core backend
     ("S", False, 19, 1, 376, 1241, "ffma"),   # ... and the exact-fp32 backend
     ("S_A", False, 19, 1, 128, 256, None),    # config 4 model at a size the CPU oracle finishes quickly
+    ("S_A", False, 19, 1, 512, 1024, None),   # config 4 itself: 32768 x 8192 attention (4-queries-per-thread kernels)
     ("N_A", True, 28, 1, 240, 320, None),
 ])
 def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W, backend):
