@@ -123,7 +123,11 @@ typedef struct NvsConvTcArgs {
   int32_t flags; /* bit 0: single MMA issuer = fixed fp32 accumulation order (bit-reproducible, slower);
                     bit 1: c0 == 16, c1 == 0, cout <= 32 only -- w_hi / w_lo are given in the paired-tap layout
                     [5][cout_pad][32], K row of step t = [tap 2t ch 0-15 | tap 2t+1 ch 0-15], tenth tap zero:
-                    a tile then takes 5 pipeline steps instead of 9 */
+                    a tile then takes 5 pipeline steps instead of 9;
+                    bit 2: cout <= 32, c0 and c1 multiples of 32, dst_mode 1 or 3, no pooled output -- the
+                    row-stationary kernel: a pipeline step is one kernel ROW, its three taps are one N = 3 x 32 MMA
+                    operand ([9][32][cin] weights read as [3][96][cin]) and the epilogue sums the three shifted
+                    partial results; 3 pipeline steps per tile and chunk instead of 9 */
   int32_t c0_real, c1_real; /* 0, or the number of leading channels of the c0 / c1 window that can be non-zero (the
                     rest is zero padding with zero weights, e.g. 24 real channels in a 32-channel row for the N
                     letters): MMA k-steps that would only multiply padding are skipped */

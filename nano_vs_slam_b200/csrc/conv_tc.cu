@@ -40,9 +40,7 @@
 namespace nvs {
 namespace tc {
 
-constexpr int TM = 128;            // pixels per tile
-constexpr int TX = 16, TY = 8;     // tile shape
-constexpr int HX = TX + 2, HY = TY + 2;   // halo box
+constexpr int TM = 128;            // GEMM rows (TMEM lanes) per tile
 constexpr int CONV_GROUPS = 2;     // converter warp groups (4 warps each); group g takes the steps with index % CONV_GROUPS == g
 constexpr int WARP_HALO = 4 + 4 * CONV_GROUPS;
 constexpr int WARP_W = WARP_HALO + 1;
@@ -55,18 +53,29 @@ constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
 // PAIR: 16-channel inputs (the stem's second conv).  One pipeline step then carries TWO taps: the K = 32 operand
 // row is [tap 2t channels 0-15 | tap 2t+1 channels 0-15] (weights packed that way by the host, zero for the
 // missing tenth tap), so a tile takes 5 steps instead of 9 -- the per-step cost is fixed overhead, not MMA time.
-template <int COUT, int KC, bool PAIR = false>
+// ROW3 (output channels <= 32): "row-stationary" formulation.  The three taps of one kernel ROW share their A operand:
+// GEMM row = input position, N = [kx = 0 | kx = 1 | kx = 2] x Cout, so a pipeline step is one kernel row (3 steps per
+// tile and chunk instead of 9) and its MMAs are N = 192 ([W_hi ; W_lo] of three taps) and N = 96 wide -- wide enough
+// to cost their nominal time instead of the ~86-cycle floor a narrow MMA pays.  The tile is 4 image rows x 32
+// consecutive positions (one row per TMEM lane quadrant = per warp); D[position j][kx block] is w[ky,kx] . in[j] summed
+// over ky and channels, and the output at position i is D_0[i-1] + D_1[i] + D_2[i+1]: two warp shuffles per channel
+// in the epilogue, lanes 0 and 31 are halo positions (30 valid outputs per strip of 32).
+template <int COUT, int KC, bool PAIR = false, bool ROW3 = false>
 struct Cfg {
+  static constexpr int TX = ROW3 ? 30 : 16, TY = ROW3 ? 4 : 8;             // output pixels per tile
+  static constexpr int HX = ROW3 ? 32 : TX + 2, HY = TY + 2;               // halo box (ROW3: its 32 columns ARE the GEMM rows)
   static constexpr int HC = PAIR ? 16 : KC;                                // channels per halo-box row
-  static constexpr int TAPS = PAIR ? 5 : 9;                                // pipeline steps per (tile, chunk)
+  static constexpr int TAPS = ROW3 ? 3 : (PAIR ? 5 : 9);                   // pipeline steps per (tile, chunk)
   static constexpr int ROW_BYTES = KC * 4;                                 // weight / A row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr int HALO_ROW_BYTES = HC * 4;
   static constexpr int HALO_BYTES = ((HX * HY * HALO_ROW_BYTES + 1023) / 1024) * 1024;
   static_assert(!PAIR || KC == 32, "paired taps fill a 32-wide K row");
-  static constexpr int W_BYTES = COUT * ROW_BYTES;                         // one of W_hi / W_lo
+  static_assert(!ROW3 || (COUT == 32 && KC == 32 && !PAIR), "row-stationary variant: 32 output channels, 32-channel chunks");
+  static constexpr int NW = ROW3 ? 3 * COUT : COUT;                        // GEMM N of one of W_hi / W_lo
+  static constexpr int W_BYTES = NW * ROW_BYTES;                           // one of W_hi / W_lo
   static constexpr int W_STAGE = 2 * W_BYTES;
   static constexpr bool CONCAT = COUT <= 64;
-  static constexpr int ACC_STAGE_COLS = CONCAT ? 2 * COUT : COUT;
+  static constexpr int ACC_STAGE_COLS = CONCAT ? 2 * NW : NW;
   static constexpr int ACC_COLS = ACC_STAGES * ACC_STAGE_COLS;
   static constexpr int A_COLS = 2 * KC;                                    // TMEM slot: KC columns hi + KC columns lo
   // One ring of NS "slots": slot s = weight stage s in shared memory + A slot s in tensor memory, guarded by ONE
@@ -78,7 +87,7 @@ struct Cfg {
   static constexpr int NS_TMEM = (512 - ACC_COLS) / A_COLS;
   static constexpr int NS_SMEM = (227 * 1024 - 4096 - 3 * HALO_BYTES) / W_STAGE;
   static constexpr int NS_FIT = NS_TMEM < NS_SMEM ? NS_TMEM : NS_SMEM;
-  static constexpr int NS = NS_FIT >= 8 ? 8 : (NS_FIT >= 6 ? 6 : 4);
+  static constexpr int NS = NS_FIT >= 8 ? 8 : (NS_FIT >= 6 ? 6 : (NS_FIT >= 4 ? 4 : 2));
   static constexpr int NH = 3;                                             // halo boxes in flight
   static constexpr int KSTEPS = KC / 8;                                    // MMAs (K = 8 tf32) per operand pair
   static constexpr int SM_W = NH * HALO_BYTES;
@@ -92,8 +101,8 @@ struct Cfg {
   static constexpr uint32_t idesc_n(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   }
-  static constexpr uint32_t IDESC = idesc_n(COUT);
-  static constexpr uint32_t IDESC2 = idesc_n(2 * COUT);
+  static constexpr uint32_t IDESC = idesc_n(NW);
+  static constexpr uint32_t IDESC2 = idesc_n(2 * NW);
 };
 
 struct Params {
@@ -251,6 +260,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 16-column loads (e.g. the two accumulator halves of the same channels), one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, float* a, float* b) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr_a)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+        "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr_b)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(q[i]);
+  }
+}
 // K-major SWIZZLE_128B descriptor: 128-byte rows, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -275,13 +308,14 @@ __device__ __forceinline__ uint64_t make_wdesc(uint32_t smem_addr) {
   return d;
 }
 
-template <int COUT, int KC, bool PAIR>
+template <int COUT, int KC, bool PAIR, bool ROW3>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const Params p) {
-  using C = Cfg<COUT, KC, PAIR>;
+  using C = Cfg<COUT, KC, PAIR, ROW3>;
   constexpr int NH = C::NH, NS = C::NS;
+  constexpr int TX = C::TX, TY = C::TY, HX = C::HX, HY = C::HY;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -387,8 +421,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // =========================== converters: halo window -> hi / lo -> TMEM ===========================
     const int cw = warp & 3;            // TMEM lane quadrant this warp may write (warp % 4)
     const int grp = (warp - 4) >> 2;    // converter group: handles pipeline steps with (index % CONV_GROUPS == grp)
-    const int r = cw * 32 + lane;       // output pixel inside the tile == TMEM lane
-    const int ly = r >> 4, lx = r & 15;
+    const int r = cw * 32 + lane;       // GEMM row inside the tile == TMEM lane
+    // 8 x 16 output pixels, or (ROW3) 4 image rows x 32 positions of the halo box (position 0 / 31 = halo columns)
+    const int ly = ROW3 ? cw : (r >> 4), lx = ROW3 ? lane : (r & 15);
     int hb = 0, sl = 0, turn = 0;
     uint32_t hph = 0, sph = 0;
     // Splitting the channels of every step over both groups instead (half the latency per step, same work) was
@@ -410,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             // (rh >> 1) & 3.  Consecutive pixels of a quarter-warp read consecutive rows -> distinct keys ->
             // conflict-free LDS.128.
             const uint8_t* hbase = sm + hb * C::HALO_BYTES;
-            const int ky = PAIR ? 0 : tap / 3, kx = PAIR ? 0 : tap - ky * 3;
+            const int ky = PAIR ? 0 : (ROW3 ? tap : tap / 3), kx = (PAIR || ROW3) ? 0 : tap - ky * 3;
             const int rh = (ly + ky) * HX + lx + kx;  // row of the halo box (single-tap steps)
             const uint8_t* rowp = hbase + rh * C::HALO_ROW_BYTES;
             const int key = C::HC == 32 ? (rh & 7) : ((rh >> 1) & 3);
@@ -468,7 +503,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
 #ifdef NVS_TC_DEBUG
             {
-              const int gs = (t * chunks + ch) * 9 + tap;
+              const int gs = (t * chunks + ch) * C::TAPS + tap;
               if (p.dbg && blockIdx.x == 0 && warp == 4 + 4 * grp && lane == 0 && gs < 480) {
                 long long* d = p.dbg + 2048 + gs * 4;
                 d[0] = k0; d[1] = k1; d[2] = k2; d[3] = clock64();
@@ -540,7 +575,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             // a_lo w_hi goes to the SECOND half as well: the tensor core's fp32 adder truncates, one (biased)
             // rounding per accumulation, so the big a_hi w_hi sums take half as many of them and the small
             // correction terms are rounded at their own, 2^-11 times smaller, magnitude
-            tc_mma_tf32_ts(d_tmem + (uint32_t)COUT, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
+            tc_mma_tf32_ts(d_tmem + (uint32_t)C::NW, a_lo + 8 * k, w_hi + o, C::IDESC, 1u);
           } else {
             tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, w_hi + o, C::IDESC, (ks | k) != 0 ? 1u : 0u);
             if (k == 0 && ks == 0) mbar_arrive(astart(acc));
@@ -582,6 +617,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           ks -= steps;
           ++tile;
         }
+      }
+    }
+  } else if (warp < 4 && ROW3) {
+    // =========================== epilogue, row-stationary variant ===========================
+    // warp = image row of the tile, lane = position of the 32-wide strip (lane 0 / 31: halo positions).  Accumulator
+    // columns of a stage: [kx0 | kx1 | kx2] x 32 channels of a_hi w_hi, then the same three blocks of the correction
+    // products.  out[i] = D_0[i-1] + D_1[i] + D_2[i+1].
+    int acc = 0;
+    uint32_t aph = 0;
+    const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+      const int gx = tx * TX - 1 + lane, gy = ty * TY + warp;
+      const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
+      mbar_wait(afull(acc), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int h = 0; h < (NVS_KNOCK(4) ? 0 : COUT / 16); ++h) {  // 16 output channels at a time
+        float o[16], u[16], w[16];
+        __syncwarp();
+        tmem_ld16x2(taddr + (uint32_t)(16 * h), taddr + (uint32_t)(C::NW + 16 * h), u, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = __shfl_up_sync(0xffffffffu, u[j] + w[j], 1);
+        tmem_ld16x2(taddr + (uint32_t)(COUT + 16 * h), taddr + (uint32_t)(C::NW + COUT + 16 * h), u, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] += u[j] + w[j];
+        tmem_ld16x2(taddr + (uint32_t)(2 * COUT + 16 * h), taddr + (uint32_t)(C::NW + 2 * COUT + 16 * h), u, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] += __shfl_down_sync(0xffffffffu, u[j] + w[j], 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = o[j] + bias_s[16 * h + j];
+          o[j] = fmaxf(a, 0.f) + neg_slope * fminf(a, 0.f);
+        }
+        if (p.act == NVS_ACT_SIGMOID && h == 0) {  // depth heads: cout <= 4
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = 1.f / (1.f + expf(-o[j]));
+        }
+        const int cbase = 16 * h;
+        if (p.dst_mode == 3) {  // keypoint heads: sigmoid -> score, tanh -> centre shift (see the other epilogue)
+          if (valid && h == 0) {
+            const size_t plane = (size_t)p.H * p.W, pix = (size_t)gy * p.W + gx;
+            p.dst[(size_t)b * plane + pix] = 1.f / (1.f + expf(-o[0]));
+            p.dst_pool[((size_t)b * 2 + 0) * plane + pix] = tanhf(o[1]);
+            p.dst_pool[((size_t)b * 2 + 1) * plane + pix] = tanhf(o[2]);
+          }
+          continue;
+        }
+        if (valid) {
+          if (p.dst_layout == 0) {  // NHWC
+            float4* d = reinterpret_cast<float4*>(
+                p.dst + (((size_t)b * p.H + gy) * p.W + gx) * p.dst_c_total + p.dst_c_off + cbase);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (cbase + 4 * q < p.cout) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          } else {  // NCHW: a warp writes 30 consecutive x of one channel row
+            float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cbase) * p.H + gy) * p.W + gx;
+            const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cbase + j < p.cout) d[j * plane] = o[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(aempty(acc));
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        aph ^= 1;
       }
     }
   } else if (warp < 4) {
@@ -710,25 +816,27 @@ static EncodeTiledFn get_encode() {
 struct alignas(64) Plan {
   CUtensorMap a0, a1, whi, wlo;
   Params p;
-  int cout_tpl, kc, pair;
+  int cout_tpl, kc, pair, row3;
   int magic;
 };
 constexpr int PLAN_MAGIC = 0x7C0DE6;
 
-// NHWC activations (B,H,W,Ct): box = (kc channels, 18 x, 10 y, 1 frame) = output tile + 1-pixel halo
-static int encode_act(CUtensorMap* m, const float* ptr, int B, int H, int W, int Ct, int kc) {
+// NHWC activations (B,H,W,Ct): box = (kc channels, hx, hy, 1 frame) = output tile + 1-pixel halo (18 x 10, or 32 x 6
+// for the row-stationary variant)
+static int encode_act(CUtensorMap* m, const float* ptr, int B, int H, int W, int Ct, int kc, int hx, int hy) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
   cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)Ct * 4, (cuuint64_t)W * Ct * 4, (cuuint64_t)H * W * Ct * 4};
-  cuuint32_t box[4] = {(cuuint32_t)kc, HX, HY, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)hx, (cuuint32_t)hy, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
-// packed weights [9][cout_pad][cin]: box = (kc, cout_pad, 1)
+// packed weights [taps][rows][cin]: box = (kc, rows, 1); rows = cout_pad, or 3 * cout_pad ([kx][cout]) with taps = 3
+// kernel rows for the row-stationary variant
 static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int kc, int taps = 9) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
@@ -742,16 +850,16 @@ static int encode_w(CUtensorMap* m, const float* ptr, int cin, int cout_pad, int
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
 
-template <int COUT, int KC, bool PAIR = false>
+template <int COUT, int KC, bool PAIR = false, bool ROW3 = false>
 static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
-  using C = Cfg<COUT, KC, PAIR>;
-  auto kern = conv_tc_kernel<COUT, KC, PAIR>;
+  using C = Cfg<COUT, KC, PAIR, ROW3>;
+  auto kern = conv_tc_kernel<COUT, KC, PAIR, ROW3>;
   NVS_OPT_IN_SMEM(kern, C::SMEM_BYTES);
   const int sms = nvs_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
   while (C::NS % q.issuers != 0) --q.issuers;  // a slot must always be consumed by the same issuer
-  conv_tc_kernel<COUT, KC, PAIR><<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
+  kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
@@ -806,13 +914,23 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   const int pair = (a->flags & 2) ? 1 : 0;  // weights given in the paired-tap layout [5][cout_pad][32] (c0 = 16, no src1)
   if (pair && (a->c0 != 16 || a->c1 != 0 || cpad != 32)) return NVS_ERR_ARG;
   const int kc = tc::pick_kc(a->c0, a->c1);
-  int rc = tc::encode_act(&pl->a0, a->src0, a->B, a->H, a->W, a->c0_total, kc);
+  // bit 2: weights given in the row-stationary layout [3 ky][3 kx * cout_pad][cin] (see Cfg: ROW3)
+  const int row3 = (a->flags & 4) ? 1 : 0;
+  if (row3 && (pair || cpad != 32 || kc != 32 || (a->dst_pool != nullptr && a->dst_mode != 3) ||
+               (a->dst_mode != 1 && a->dst_mode != 3)))
+    return NVS_ERR_ARG;
+  using R3 = tc::Cfg<32, 32, false, true>;
+  using R9 = tc::Cfg<32, 32, false, false>;
+  const int hx = row3 ? R3::HX : R9::HX, hy = row3 ? R3::HY : R9::HY;
+  int rc = tc::encode_act(&pl->a0, a->src0, a->B, a->H, a->W, a->c0_total, kc, hx, hy);
   if (rc != NVS_OK) return rc;
-  rc = tc::encode_act(&pl->a1, a->c1 > 0 ? a->src1 : a->src0, a->B, a->H, a->W, a->c1 > 0 ? a->c1_total : a->c0_total, kc);
+  rc = tc::encode_act(&pl->a1, a->c1 > 0 ? a->src1 : a->src0, a->B, a->H, a->W, a->c1 > 0 ? a->c1_total : a->c0_total, kc,
+                      hx, hy);
   if (rc != NVS_OK) return rc;
-  rc = pair ? tc::encode_w(&pl->whi, a->w_hi, 32, cpad, 32, 5) : tc::encode_w(&pl->whi, a->w_hi, cin, cpad, kc);
+  const int wrows = row3 ? 3 * cpad : cpad, wtaps = row3 ? 3 : 9;
+  rc = pair ? tc::encode_w(&pl->whi, a->w_hi, 32, cpad, 32, 5) : tc::encode_w(&pl->whi, a->w_hi, cin, wrows, kc, wtaps);
   if (rc != NVS_OK) return rc;
-  rc = pair ? tc::encode_w(&pl->wlo, a->w_lo, 32, cpad, 32, 5) : tc::encode_w(&pl->wlo, a->w_lo, cin, cpad, kc);
+  rc = pair ? tc::encode_w(&pl->wlo, a->w_lo, 32, cpad, 32, 5) : tc::encode_w(&pl->wlo, a->w_lo, cin, wrows, kc, wtaps);
   if (rc != NVS_OK) return rc;
   tc::Params& p = pl->p;
   p.bias = a->bias; p.dst = a->dst; p.dst_pool = a->dst_pool;
@@ -820,7 +938,8 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.dst_c_total = a->dst_c_total; p.dst_c_off = a->dst_c_off; p.dst_layout = a->dst_layout; p.dst_mode = a->dst_mode;
   p.pool_c_total = a->pool_c_total; p.pool_c_off = a->pool_c_off;
   p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.act = a->act;
-  p.tiles_x = (a->W + tc::TX - 1) / tc::TX; p.tiles_y = (a->H + tc::TY - 1) / tc::TY;
+  const int tile_x = row3 ? R3::TX : R9::TX, tile_y = row3 ? R3::TY : R9::TY;
+  p.tiles_x = (a->W + tile_x - 1) / tile_x; p.tiles_y = (a->H + tile_y - 1) / tile_y;
   p.n_tiles = p.tiles_x * p.tiles_y * a->B;
   {
     static int default_issuers = 0;
@@ -851,6 +970,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   pl->cout_tpl = cpad;
   pl->kc = kc;
   pl->pair = pair;
+  pl->row3 = row3;
   pl->magic = tc::PLAN_MAGIC;
   return NVS_OK;
 }
@@ -869,6 +989,7 @@ extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float*
 #endif
   if (p.dst_mode != 0 && !p.dst) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl->row3) return tc::launch<32, 32, false, true>(*pl, p, st);
   if (pl->pair) return tc::launch<32, 32, true>(*pl, p, st);
   if (pl->kc == 16) return pl->cout_tpl == 32 ? tc::launch<32, 16>(*pl, p, st) : NVS_ERR_UNSUPPORTED;
   switch (pl->cout_tpl) {

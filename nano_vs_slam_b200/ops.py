@@ -590,7 +590,12 @@ class TcConv(object):
         a.pool_c_total = dst_pool.shape[3] if (dst_pool is not None and dst_mode != 3) else 0
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
-        a.flags = (1 if deterministic else 0) | (2 if paired else 0)
+        # row-stationary kernel (conv_tc.cu Cfg: ROW3) for layers with <= 32 output channels on 32-channel rows: the
+        # packed [9][32][cin] weights ARE its [3 ky][3 kx x 32][cin] layout, so only the flag differs
+        row3 = (os.environ.get("NVS_TC_ROW3", "1") != "0" and bp.numel() == 32 and not paired and a.c0 % 32 == 0
+                and a.c1 % 32 == 0 and dst_mode in (1, 3) and (dst_pool is None or dst_mode == 3))
+        self.row3 = row3
+        a.flags = (1 if deterministic else 0) | (2 if paired else 0) | (4 if row3 else 0)
         segs = getattr(hi, "nvs_segments", None)
         a.c0_real = a.c1_real = 0
         if segs is not None and len(segs) == (2 if src1 is not None else 1) and not paired:
@@ -612,7 +617,7 @@ class TcConv(object):
         self._mem = C.create_string_buffer(int(lib().nvs_conv_tc_plan_bytes()))
         check(lib().nvs_conv_tc_plan_init(self._mem, C.byref(a)), "nvs_conv_tc_plan_init")
         self.flops = 2.0 * 9 * (a.c0 + a.c1) * cout * H * W * B
-        self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05"
+        self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05" + (" row3" if row3 else "")
 
     def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
         check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _ptr(dst2_override), _stream()),

@@ -185,3 +185,57 @@ def test_conv_tc_more_than_128_output_channels():
     nchw = torch.zeros(B, cout, H, W, device="cuda")
     ops.tc_conv(xs, packed, cout, act=1, dst=None, dst_layout=1, dst_c_total=cout).run(dst_override=nchw)
     assert rel_err(nchw, ref) < 2e-5
+
+
+@pytest.mark.parametrize("c0,c1,cout,H,W,layout", [
+    (32, 0, 32, 24, 61, 0),    # three strips, the last one with a single valid column
+    (32, 0, 32, 13, 30, 0),    # exactly one strip, ragged rows (13 % 4 != 0)
+    (64, 0, 28, 16, 31, 1),    # segmentation output conv: 28 classes, NCHW store
+    (32, 64, 32, 10, 45, 1),   # two sources (concat read), three chunks
+    (96, 0, 24, 7, 90, 0),     # N letters: padded output channels
+])
+def test_conv_tc_row_stationary_variant(c0, c1, cout, H, W, layout, monkeypatch):
+    """Layers with <= 32 output channels take the row-stationary kernel (ROW3: one pipeline step per kernel row, the
+    epilogue sums three shifted partial results); it must agree with fp32 and with the 9-step kernel it replaces."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(c0 + c1 + cout + W)
+    B, cin = 3, c0 + c1
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    s0 = _nhwc(x[:, :c0]).cuda()
+    s1 = _nhwc(x[:, c0:]).cuda() if c1 else None
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NVS_TC_ROW3", flag)
+        cpad = packed[2].numel()
+        out = torch.zeros((B, H, W, cpad) if layout == 0 else (B, cout, H, W), device="cuda")
+        op = ops.TcConv(s0, packed, cout, act=1, src1=s1, dst=out, dst_layout=layout)
+        assert op.row3 == (flag == "1")
+        op.run()
+        torch.cuda.synchronize()
+        outs[flag] = out[..., :cout].permute(0, 3, 1, 2) if layout == 0 else out
+        assert rel_err(outs[flag], ref) < 2e-5, (flag, rel_err(outs[flag], ref))
+    assert rel_err(outs["1"], outs["0"]) < 1e-5
+
+
+def test_conv_tc_row_stationary_keypoint_heads(monkeypatch):
+    """The fused keypoint-head conv (score | location trunks -> 3 channels, sigmoid / tanh split) on the ROW3 kernel."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(77)
+    B, C, H, W = 2, 64, 15, 47
+    sh, lh = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ws, bs = torch.randn(1, C, 3, 3, generator=g) * 0.05, torch.randn(1, generator=g) * 0.1
+    wl, bl = torch.randn(2, C, 3, 3, generator=g) * 0.05, torch.randn(2, generator=g) * 0.1
+    packed = ops.pack_head_pair_tc(ws.cuda(), bs.cuda(), wl.cuda(), bl.cuda())
+    score = torch.zeros(B, 1, H, W, device="cuda")
+    shift = torch.zeros(B, 2, H, W, device="cuda")
+    op = ops.TcConv(_nhwc(sh).cuda(), packed, 3, src1=_nhwc(lh).cuda(), dst=score, dst_mode=3, dst_layout=1, dst_pool=shift)
+    assert op.row3
+    op.run()
+    assert rel_err(score, F.conv2d(sh, ws, bs, padding=1).sigmoid()) < 2e-5
+    assert rel_err(shift, F.conv2d(lh, wl, bl, padding=1).tanh()) < 2e-5
