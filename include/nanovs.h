@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NVS_ABI_VERSION 1
+#define NVS_ABI_VERSION 2
 
 #define NVS_OK 0
 #define NVS_ERR_ARG (-1)         /* bad shape / null pointer / unsupported size */
@@ -267,24 +267,32 @@ int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32
                    size_t workspace_bytes, void* stream);
 
 /* ---- exact L2 top-k retrieval = faiss.IndexFlatL2.add / .search (evaluation/global_descriptor.py:55-60) ----
- * add:    nvs_flat_prepare converts the fp32 rows (n,d) to bf16 rows padded to nvs_flat_padded_dim(d)
- *         columns (the tcgen05 GEMM operand) and stores |x|^2 (fp32).  Caller owns all three buffers.
- * search: d2 = |q|^2 + |x|^2 - 2 q.x; bf16 tcgen05/TMEM GEMM with a fused per-row running top-k selects
- *         candidates, which are re-ranked with the fp32 formula; out_D (nq,k) ascending, out_I (nq,k) int64
- *         = row index + id_offset (id_offset = first global row of this shard).  k <= 31.
+ * add:    nvs_flat_prepare converts the fp32 rows (n,d) to fp16 rows padded to nvs_flat_padded_dim(d) columns (the
+ *         tcgen05 GEMM operand; one power-of-two scale for the whole shard), stores |x|^2 (fp32) and four shard
+ *         statistics (max |x|^2, max |x - fp16(x)|^2, scale exponent, max |component|) that the search turns into a
+ *         proven bound of the half-precision error.  Caller owns all four buffers (stats: 4 floats).
+ * search: d2 = |q|^2 + |x|^2 - 2 q.x.  A fp16 tcgen05/TMEM GEMM with a fused per-row running list screens the rows;
+ *         every row whose screened value is within the error bound of the k-th smallest is re-ranked with the fp32
+ *         formula, and a query whose lists could have dropped such a row is answered by an exact fp32 scan instead
+ *         (csrc/retrieval.cu header): the result is the fp32 result, independent of scheduling.
+ *         out_D (nq,k) ascending, ties -> lower id; out_I (nq,k) int64 = row index + id_offset (id_offset = first
+ *         global row of this shard); fewer than k reachable rows (NaN query) -> (+inf, -1).  k <= nvs_flat_max_k().
  *         ev_gemm_start / ev_gemm_stop: optional cudaEvent_t (may be NULL) recorded on `stream` around the
- *         GEMM+top-k kernel so callers can time it (bench.py roofline).
- * merge:  nvs_topk_merge combines `parts` (<= 16) sorted (nq,k) lists laid out [parts][nq][k] (the NCCL
- *         allgather buffer of a sharded index) into the global top-k. */
+ *         GEMM+list kernel so callers can time it (bench.py roofline).
+ * merge:  nvs_topk_merge combines `parts` (<= 16) sorted (nq,k) lists into the global top-k.  Part s of the distances
+ *         starts part_stride_d floats after part s-1, part s of the labels part_stride_i int64s (0 = nq*k: the plain
+ *         [parts][nq][k] layout); with strides, distances and labels may live in ONE gathered buffer, i.e. one NCCL
+ *         allgather per search. */
 int32_t nvs_flat_padded_dim(int32_t d);
-int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_bf16, float* norms, void* stream);
+int32_t nvs_flat_max_k(void);
+int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_f16, float* norms, float* stats, void* stream);
 size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int32_t d, int32_t k);
-int nvs_flat_search(const float* db, const void* db_bf16, const float* db_norms, int64_t n_db, const float* q,
-                    int32_t nq, int32_t d, int32_t k, int64_t id_offset, float* out_D, int64_t* out_I,
+int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, const float* db_stats, int64_t n_db,
+                    const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset, float* out_D, int64_t* out_I,
                     void* workspace, size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop,
                     void* stream);
 int nvs_topk_merge(const float* D_parts, const int64_t* I_parts, int32_t parts, int32_t nq, int32_t k,
-                   float* out_D, int64_t* out_I, void* stream);
+                   int64_t part_stride_d, int64_t part_stride_i, float* out_D, int64_t* out_I, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,7 +70,7 @@ struct Cfg {
   static constexpr int HALO_ROW_BYTES = HC * 4;
   static constexpr int HALO_BYTES = ((HX * HY * HALO_ROW_BYTES + 1023) / 1024) * 1024;
   static_assert(!PAIR || KC == 32, "paired taps fill a 32-wide K row");
-  static_assert(!ROW3 || (COUT == 32 && KC == 32 && !PAIR), "row-stationary variant: 32 output channels, 32-channel chunks");
+  static_assert(!ROW3 || (COUT == 32 && !PAIR), "row-stationary variant: 32 output channels, 32- or 16-channel chunks");
   static constexpr int NW = ROW3 ? 3 * COUT : COUT;                        // GEMM N of one of W_hi / W_lo
   static constexpr int W_BYTES = NW * ROW_BYTES;                           // one of W_hi / W_lo
   static constexpr int W_STAGE = 2 * W_BYTES;
@@ -92,7 +92,9 @@ struct Cfg {
   static constexpr int KSTEPS = KC / 8;                                    // MMAs (K = 8 tf32) per operand pair
   static constexpr int SM_W = NH * HALO_BYTES;
   static constexpr int SM_BIAS = SM_W + NS * W_STAGE;
-  static constexpr int SM_BAR = SM_BIAS + COUT * 4;
+  static constexpr int POOL_BYTES = ROW3 ? 2 * 2 * 15 * 16 * 4 : 0;        // ROW3 max-pool: rows of a pair live in two warps
+  static constexpr int SM_POOL = SM_BIAS + COUT * 4;
+  static constexpr int SM_BAR = SM_POOL + ((POOL_BYTES + 7) / 8) * 8;
   static constexpr int N_BARS = 2 * NH + 2 * NS + 6;
   static constexpr int SMEM_BYTES = SM_BAR + 8 * N_BARS + 16 + 1024;
   static_assert(NS <= NS_FIT && NS % CONV_GROUPS == 0, "TMEM budget / converter ring");
@@ -666,7 +668,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
           continue;
         }
-        if (valid) {
+        if (p.dst_pool != nullptr) {
+          // MaxPool2d(2,2): x partner = next lane (strips start at even x, so pairs are lanes (1,2), (3,4), ...),
+          // y partner = the next warp's row: odd warps hand their x-pooled values to the even warp below them
+          // through shared memory (two buffers alternate with h, so the pair's next write never meets a pending read)
+          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + ((h & 1) * 2 + (warp >> 1)) * (15 * 16);
+          float m[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = fmaxf(o[j], __shfl_down_sync(0xffffffffu, o[j], 1));
+          const int pc = (lane - 1) >> 1;  // pooled column inside the strip, odd lanes 1..29 -> 0..14
+          const bool owner = (lane & 1) && lane <= 29;
+          if ((warp & 1) && owner) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              reinterpret_cast<float4*>(ps + pc * 16)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp >> 1)) : "memory");
+          const int qx = gx >> 1, qy = gy >> 1;
+          if (!(warp & 1) && owner && qx < (p.W >> 1) && qy < (p.H >> 1)) {
+            float4* d = reinterpret_cast<float4*>(
+                p.dst_pool + (((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx) * p.pool_c_total + p.pool_c_off + cbase);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 r = reinterpret_cast<const float4*>(ps + pc * 16)[q];
+              if (cbase + 4 * q < p.cout)
+                d[q] = make_float4(fmaxf(m[4 * q], r.x), fmaxf(m[4 * q + 1], r.y), fmaxf(m[4 * q + 2], r.z),
+                                   fmaxf(m[4 * q + 3], r.w));
+            }
+          }
+        }
+        if (valid && p.dst_mode == 1) {
           if (p.dst_layout == 0) {  // NHWC
             float4* d = reinterpret_cast<float4*>(
                 p.dst + (((size_t)b * p.H + gy) * p.W + gx) * p.dst_c_total + p.dst_c_off + cbase);
@@ -913,11 +944,11 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   const int cin = a->c0 + a->c1;
   const int pair = (a->flags & 2) ? 1 : 0;  // weights given in the paired-tap layout [5][cout_pad][32] (c0 = 16, no src1)
   if (pair && (a->c0 != 16 || a->c1 != 0 || cpad != 32)) return NVS_ERR_ARG;
-  const int kc = tc::pick_kc(a->c0, a->c1);
-  // bit 2: weights given in the row-stationary layout [3 ky][3 kx * cout_pad][cin] (see Cfg: ROW3)
+  int kc = tc::pick_kc(a->c0, a->c1);
+  // bit 2: the row-stationary kernel (see Cfg: ROW3); bit 3: ... with 16-channel chunks (four A slots instead of two)
   const int row3 = (a->flags & 4) ? 1 : 0;
-  if (row3 && (pair || cpad != 32 || kc != 32 || (a->dst_pool != nullptr && a->dst_mode != 3) ||
-               (a->dst_mode != 1 && a->dst_mode != 3)))
+  if (row3 && (a->flags & 8) && kc != 0) kc = 16;
+  if (row3 && (pair || cpad != 32 || kc == 0 || a->dst_mode == 2 || (a->dst_mode == 0 && a->dst_pool == nullptr)))
     return NVS_ERR_ARG;
   using R3 = tc::Cfg<32, 32, false, true>;
   using R9 = tc::Cfg<32, 32, false, false>;
@@ -989,7 +1020,7 @@ extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float*
 #endif
   if (p.dst_mode != 0 && !p.dst) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (pl->row3) return tc::launch<32, 32, false, true>(*pl, p, st);
+  if (pl->row3) return pl->kc == 16 ? tc::launch<32, 16, false, true>(*pl, p, st) : tc::launch<32, 32, false, true>(*pl, p, st);
   if (pl->pair) return tc::launch<32, 32, true>(*pl, p, st);
   if (pl->kc == 16) return pl->cout_tpl == 32 ? tc::launch<32, 16>(*pl, p, st) : NVS_ERR_UNSUPPORTED;
   switch (pl->cout_tpl) {

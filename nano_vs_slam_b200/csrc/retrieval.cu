@@ -1,46 +1,67 @@
 // Exact L2 top-k retrieval = faiss.IndexFlatL2.add / search (src/evaluation/global_descriptor.py:55-60).
 //
-//   d2(q, x) = |q|^2 + |x|^2 - 2 q.x ,  k smallest, ascending, int64 labels.
+//   d2(q, x) = |q|^2 + |x|^2 - 2 q.x  in fp32,  k smallest, ascending, ties -> lower id, int64 labels.
 //
 // The Q x N x D contraction is the one genuinely tensor-core shaped piece of the hot path
-// (10k x 1M x 4096 = 8.2e13 FLOP): it runs as a warp-specialised tcgen05 GEMM
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages bf16 tiles of queries (A, 128 x 64) and
-//     database rows (B, 256 x 64) into a 4-deep shared-memory ring.  The kernel is bound by the L2->SM
-//     fabric (~42 B/cycle/SM chip-wide), so CTAs run as clusters of two that work on the same database
-//     tiles for two different query blocks: each CTA fetches HALF of every B tile and TMA-multicasts it
-//     into both CTAs' shared memory (48 -> 32 KB of L2 reads per CTA per stage),
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) into a
-//     double-buffered 128 x 256 fp32 accumulator in TMEM (2 x 256 columns),
-//   * four epilogue warps read the accumulator with tcgen05.ld, form |x|^2 - 2 q.x and keep a running
-//     per-row top-k in shared memory -- the score matrix never leaves the SM,
-// followed by a small candidate merge and an fp32 re-rank with the literal formula above, so the
-// reported distances and the order are those of an fp32 implementation (bf16 is only a filter).
+// (10k x 1M x 4096 = 8.2e13 FLOP).  It runs in half precision as a SCREEN with a proven error bound, and everything
+// the screen cannot decide is re-ranked with the literal fp32 formula, so the result is the fp32 result:
+//
+//   add     rows -> fp16 (scaled by one power of two so the largest component sits in [2^14, 2^15); fp16 subnormals
+//           are flushed here, not by the hardware) + |x|^2 + per-shard max |x| and max |x - fp16(x)| (the residual).
+//   search  queries -> fp16 (per-row power-of-two scale) with |q|, |q - fp16(q)|.  By Cauchy-Schwarz
+//             |q.x - q~.x~| <= |q - q~| |x| + |q~| |x - x~|
+//           which, with the fp32 accumulation of the tensor core and of the re-rank bounded generously, gives a
+//           per-query eps with |s~ - s| <= eps for every row, s = |x|^2 - 2 q.x.  If tau~ is ANY upper bound of the
+//           k-th smallest s~, every row of the true top-k has s~ <= tau~ + 2 eps.  So:
+//   GEMM    warp-specialised tcgen05 kernel (TMA SWIZZLE_128B -> smem ring -> tcgen05.mma kind::f16 128x256x16 ->
+//           2 x 256-column TMEM accumulators; CTA pairs share every database tile by TMA multicast).  The epilogue
+//           keeps, per query row and database strip, the L >= k smallest s~ that are <= (published bound + 2 eps)
+//           in shared memory; a finished strip publishes its k-th smallest (an upper bound of tau~).
+//   select  per query: exact k-th smallest s~ over all strips by radix select = tau~; candidates = everything with
+//           s~ <= tau~ + 2 eps (as many as the data puts there, not a constant).  A query is FLAGGED when the proof
+//           has a hole: a strip list that is full with all entries inside the slack (it may have dropped a row), or
+//           more candidates than the re-rank buffer holds.
+//   rerank  exact fp32 distances of the candidates, k smallest by (distance, id).
+//   scan    flagged queries only (normally none): exact fp32 distances against EVERY row, merged into the result
+//           under a per-query lock.  Slow, never wrong: dense near-ties or duplicate rows cost time, not exactness.
+//
+// The answer therefore does not depend on how the strips were scheduled, and equals an fp32 IndexFlatL2 wherever the
+// fp32 distances themselves are distinct.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <limits.h>
+#include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace nvs {
 namespace rt {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;       // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int THREADS = 256;                // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
-constexpr int KMAX = 31;                    // per-row list length limit (odd pitch, conflict free)
+constexpr int KMAX = 64;                    // largest k served
+constexpr int CAP = 256;                    // candidates re-ranked exactly per query (more -> exact scan)
+constexpr int MAX_CAND = 12288;             // n_strips * L the selection kernel holds in shared memory (96 KiB)
 
-// shared memory map (dynamic, 1024-byte aligned base)
-constexpr int SM_TILES = 0;
-constexpr int SM_LIST_D = STAGES * STAGE_BYTES;                // float [128][KP]
-constexpr int SM_LIST_I = SM_LIST_D + BM * KMAX * 4;           // int   [128][KP]
-constexpr int SM_XN = SM_LIST_I + BM * KMAX * 4;               // float [2][256]
-constexpr int SM_BAR = SM_XN + ACC_STAGES * BN * 4;            // mbarriers
-constexpr int SM_TOTAL = SM_BAR + 256;
-constexpr int SMEM_BYTES = SM_TOTAL + 1024;                    // slack for manual 1024 B alignment
+// shared memory map (dynamic, 1024-byte aligned base): STAGES operand stages, then the per-row lists.
+// 4 stages leave room for lists of 31 entries, 3 stages for 79 (odd pitch: conflict-free row-per-thread access).
+template <int STAGES>
+struct Smem {
+  static constexpr int LMAX = STAGES == 4 ? 31 : 79;
+  static constexpr int LIST_D = STAGES * STAGE_BYTES;               // float [128][LMAX]
+  static constexpr int LIST_I = LIST_D + BM * LMAX * 4;             // int   [128][LMAX]
+  static constexpr int XN = LIST_I + BM * LMAX * 4;                 // float [2][256]
+  static constexpr int BAR = XN + ACC_STAGES * BN * 4;              // mbarriers
+  static constexpr int TOTAL = BAR + 256;
+  static constexpr int BYTES = TOTAL + 1024;                        // slack for manual 1024 B alignment
+  static_assert(BYTES <= 227 * 1024, "shared memory budget");
+};
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -105,7 +126,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -143,35 +164,39 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D = f32 (bit 4), A = B = fp16 (format 0), both K-major, N = 256, M = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct Params {
-  const float* xnorm;   // [N]   |x|^2 (fp32, from the fp32 rows)
-  float* gbound;        // [Qpad] running upper bound of each query's k-th smallest (|x|^2 - 2 q.x), init +inf
-  float* cand_d;        // [Qpad][n_strips][k]  approximate |x|^2 - 2 q.x
-  int32_t* cand_i;      // [Qpad][n_strips][k]  row index inside this shard (-1 = empty)
+  const float* xnorm;   // [N]    |x|^2 (fp32, from the fp32 rows)
+  const float* qcoef;   // [Qpad] -2 / (query scale * database scale): accumulator -> -2 q~.x~
+  const float* qslack;  // [Qpad] 2 eps of the query
+  float* gbound;        // [Qpad] running upper bound of each query's k-th smallest s~, init +inf
+  float* cand_d;        // [Qpad][n_strips][L]  s~ = |x|^2 - 2 q~.x~
+  int32_t* cand_i;      // [Qpad][n_strips][L]  row index inside this shard (-1 = empty)
   int Q, N, kblocks;    // kblocks = Dpad / 64
-  int k, kp;            // list length and its (odd) pitch
+  int k, L, lp;         // neighbours wanted, list length (>= k), its (odd) pitch
   int n_mblk, n_strips, tiles_per_strip, n_tiles;
   int n_mpair;          // ceil(n_mblk / 2): a cluster of two CTAs owns query blocks (2*pair, 2*pair + 1)
 };
 
+template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                     const Params p) {
+  using S = Smem<STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  float* list_d = reinterpret_cast<float*>(sm + SM_LIST_D);
-  int32_t* list_i = reinterpret_cast<int32_t*>(sm + SM_LIST_I);
-  float* xn_s = reinterpret_cast<float*>(sm + SM_XN);
-  const uint32_t bar0 = base + SM_BAR;
+  float* list_d = reinterpret_cast<float*>(sm + S::LIST_D);
+  int32_t* list_i = reinterpret_cast<int32_t*>(sm + S::LIST_I);
+  float* xn_s = reinterpret_cast<float*>(sm + S::XN);
+  const uint32_t bar0 = base + S::BAR;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S::BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();          // 0 / 1 inside the CTA pair
@@ -218,7 +243,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int t = t_begin; t < t_end; ++t) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t a_dst = base + SM_TILES + stage * STAGE_BYTES;
+            const uint32_t a_dst = base + stage * STAGE_BYTES;
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);  // own A + own half of B + the peer's half of B
             tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BK, mblk * BM);  // (rows past Q: zero filled)
             // my half (128 rows) of the 256-row database tile, delivered to BOTH CTAs of the pair
@@ -248,14 +273,14 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t a_addr = base + SM_TILES + stage * STAGE_BYTES;
+            const uint32_t a_addr = base + stage * STAGE_BYTES;
             const uint64_t adesc = make_sdesc(a_addr);
             const uint64_t bdesc = make_sdesc(a_addr + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in (addr >> 4)
-              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
-                          (kb | k) != 0 ? 1u : 0u);
+              // advance 16 halves = 32 bytes along K inside the 128-byte swizzle span: +2 in (addr >> 4)
+              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                         (kb | k) != 0 ? 1u : 0u);
             }
             tc_commit_mc(empty_bar(stage), (uint16_t)0x3);  // frees this stage in BOTH CTAs when these MMAs retire
             if (++stage == STAGES) {
@@ -272,27 +297,30 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: running per-row top-k =================
+    // ================= epilogue: running per-row list of the L smallest s~ =================
     const int ew = warp - 4;            // == warp % 4: TMEM lane quadrant this warp may read
     const int row = ew * 32 + lane;     // accumulator row (query inside the block)
     const int et = threadIdx.x - 128;   // 0..127
-    float* my_d = list_d + row * p.kp;
-    int32_t* my_i = list_i + row * p.kp;
+    float* my_d = list_d + row * p.lp;
+    int32_t* my_i = list_i + row * p.lp;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = cluster_id; u < n_units; u += n_clusters) {
       const int strip = u / p.n_mpair, mblk = 2 * (u - strip * p.n_mpair) + (int)crank;
       const int t_begin = strip * p.tiles_per_strip;
       const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
-      for (int j = 0; j < p.k; ++j) {
+      for (int j = 0; j < p.L; ++j) {
         my_d[j] = INFINITY;
         my_i[j] = -1;
       }
-      float thr = INFINITY;
+      float thr = INFINITY;  // largest list entry: +inf until the list is full
       int pmax = 0;
       const int qrow = mblk * BM + row;
-      // upper bound on this query's final k-th distance, published by units that finished earlier
-      const float gbound = qrow < p.Q ? __ldcg(p.gbound + qrow) : INFINITY;
+      const bool live = qrow < p.Q;
+      const float coef = live ? __ldg(p.qcoef + qrow) : 0.f;
+      // upper bound of the query's k-th smallest s~ published by strips that finished earlier, plus the slack: a row
+      // above it cannot be one of the k nearest (see the header); +inf while nothing is published
+      const float gb2 = live ? __ldcg(p.gbound + qrow) + __ldg(p.qslack + qrow) : -INFINITY;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = t * BN;
         // stage |x|^2 of this tile (+inf past the end of the shard so padded columns never enter a list)
@@ -313,15 +341,14 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_ld32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float d = fmaf(-2.f, v[j], xs[c * 32 + j]);
-            // two filters: the row's own k-th best so far (strict) and the bound published by strips that
-            // already finished for this query (<=, ties must survive); insertions are rare after warm-up
-            if (d < thr && d <= gbound) {
+            const float d = fmaf(coef, v[j], xs[c * 32 + j]);
+            // keep the L smallest (strict: the first row seen wins a tie) among the rows the published bound allows
+            if (d < thr && d <= gb2) {
               my_d[pmax] = d;
               my_i[pmax] = n0 + c * 32 + j;
               thr = my_d[0];
               pmax = 0;
-              for (int q = 1; q < p.k; ++q) {
+              for (int q = 1; q < p.L; ++q) {
                 const float w = my_d[q];
                 if (w > thr) {
                   thr = w;
@@ -339,14 +366,28 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           acc_phase ^= 1;
         }
       }
-      // flush this (query block, strip) candidate list; a full list tightens the published bound
-      if (qrow < p.Q) {
-        if (thr < INFINITY) {
-          if (thr >= 0.f) atomicMin(reinterpret_cast<int*>(p.gbound + qrow), __float_as_int(thr));
-          else atomicMax(reinterpret_cast<unsigned int*>(p.gbound + qrow), __float_as_uint(thr));
+      // flush this (query block, strip) list; its k-th smallest entry tightens the published bound
+      if (live) {
+        float kth = INFINITY;
+        if (p.L == p.k) {
+          kth = thr;
+        } else {
+          for (int a = 0; a < p.L; ++a) {  // entry of rank k-1 (ties ordered by slot)
+            const float da = my_d[a];
+            int rank = 0;
+            for (int b = 0; b < p.L; ++b) {
+              const float db = my_d[b];
+              rank += (db < da || (db == da && b < a)) ? 1 : 0;
+            }
+            if (rank == p.k - 1) kth = da;
+          }
         }
-        const size_t o = ((size_t)qrow * p.n_strips + strip) * p.k;
-        for (int j = 0; j < p.k; ++j) {
+        if (kth < INFINITY) {
+          if (kth >= 0.f) atomicMin(reinterpret_cast<int*>(p.gbound + qrow), __float_as_int(kth));
+          else atomicMax(reinterpret_cast<unsigned int*>(p.gbound + qrow), __float_as_uint(kth));
+        }
+        const size_t o = ((size_t)qrow * p.n_strips + strip) * p.L;
+        for (int j = 0; j < p.L; ++j) {
           p.cand_d[o + j] = my_d[j];
           p.cand_i[o + j] = my_i[j];
         }
@@ -365,22 +406,108 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 }
 
 // ---------------------------------------------------------------- helpers around the GEMM
-// fp32 rows -> bf16 rows padded to dpad (multiple of 64) + fp32 squared norms.  One warp per row.
-__global__ void to_bf16_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
-                                    float* __restrict__ norms, long long n, int d, int dpad) {
+// fp16 conversion with one power-of-two scale per database / per query row: v -> fp16(v * 2^e).  Values whose scaled
+// magnitude falls below the fp16 normal range are flushed to zero HERE (their whole value lands in the residual), so
+// the error bound does not depend on how the tensor core treats fp16 subnormals.
+__device__ __forceinline__ int scale_exp(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 0;
+  int e = 14 - ilogbf(amax);  // amax * 2^e in [2^14, 2^15)
+  return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+__device__ __forceinline__ __half to_half_scaled(float v, float sc, float inv, float* resid) {
+  const float s = v * sc;
+  __half h = fabsf(s) < 6.103515625e-05f ? __float2half_rn(0.f) : __float2half_rn(s);  // 2^-14: smallest normal
+  *resid = v - __half2float(h) * inv;
+  return h;
+}
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) {  // v >= 0
+  atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, long long total, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float a = fabsf(x[i]);
+    m = a > m ? a : m;  // NaN never wins
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomic_max_pos(out, m);
+}
+
+// database rows -> fp16 rows padded to dpad (multiple of 64) + |x|^2; stats[0] = max |x|^2, stats[1] = max |x - x~|^2,
+// stats[2] = scale exponent, stats[3] = max |component| (filled by absmax_kernel before).  One warp per row.
+__global__ void db_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ xh, float* __restrict__ norms,
+                                 float* __restrict__ stats, long long n, int d, int dpad) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
+  const int e = scale_exp(stats[3]);
+  const float sc = ldexpf(1.f, e), inv = ldexpf(1.f, -e);
   const float* xr = x + row * d;
-  __nv_bfloat16* br = xb + row * dpad;
-  float ss = 0.f;
+  __half* br = xh + row * dpad;
+  float ss = 0.f, rr = 0.f;
   for (int c = lane; c < dpad; c += 32) {
     const float v = c < d ? xr[c] : 0.f;
+    float r;
+    br[c] = to_half_scaled(v, sc, inv, &r);
     ss = fmaf(v, v, ss);
-    br[c] = __float2bfloat16_rn(v);
+    rr = fmaf(r, r, rr);
   }
   ss = warp_sum(ss);
-  if (lane == 0) norms[row] = ss;
+  rr = warp_sum(rr);
+  if (lane == 0) {
+    norms[row] = ss;
+    atomic_max_pos(stats + 0, ss);
+    atomic_max_pos(stats + 1, rr);
+    if (row == 0) stats[2] = (float)e;
+  }
+}
+
+// queries -> fp16 rows (own scale per row), |q|^2, the accumulator coefficient and the slack 2 eps of the header.
+__global__ void q_to_f16_kernel(const float* __restrict__ q, __half* __restrict__ qh, float* __restrict__ qn,
+                                float* __restrict__ qcoef, float* __restrict__ qslack,
+                                const float* __restrict__ db_stats, int nq, int d, int dpad) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  const float* qr = q + (size_t)row * d;
+  __half* br = qh + (size_t)row * dpad;
+  float amax = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float a = fabsf(qr[c]);
+    amax = a > amax ? a : amax;
+  }
+  amax = warp_max(amax);
+  const int e = scale_exp(amax);
+  const float sc = ldexpf(1.f, e), inv = ldexpf(1.f, -e);
+  float ss = 0.f, rr = 0.f;
+  for (int c = lane; c < dpad; c += 32) {
+    const float v = c < d ? qr[c] : 0.f;
+    float r;
+    br[c] = to_half_scaled(v, sc, inv, &r);
+    ss = fmaf(v, v, ss);
+    rr = fmaf(r, r, rr);
+  }
+  ss = warp_sum(ss);
+  rr = warp_sum(rr);
+  if (lane == 0) {
+    qn[row] = ss;
+    const float up = 1.f + 1e-5f;  // the sums above carry ~d * 2^-24 relative rounding
+    const float xmax = sqrtf(db_stats[0]) * up, rxmax = sqrtf(db_stats[1]) * up;
+    const int ex = (int)db_stats[2];
+    const float nq_ = sqrtf(ss) * up, rq = sqrtf(rr) * up;
+    qcoef[row] = ldexpf(-2.f, -(e + ex));
+    // |q.x - q~.x~| <= |q - q~| |x| + |q~| |x - x~|,  |q~| <= |q| + |q - q~|
+    const float e_round = rq * xmax + (nq_ + rq) * rxmax;
+    // fp32 accumulation inside the tensor core: products of two fp16 are exact in fp32; every one of the dpad/16
+    // accumulations (and the 16-term sum in front of it) is allowed two units of 2^-23 of the magnitude sum
+    const float gamma = (float)(dpad / 16 + 32) * 2.384185791015625e-07f;
+    const float e_acc = gamma * (nq_ + rq) * (xmax + rxmax);
+    // fp32 evaluation of s~ here and of the exact distance in the re-rank (64 ulp of the largest term: generous)
+    const float e_f32 = 64.f * 5.9604644775390625e-08f * (ss + xmax * xmax + 2.f * nq_ * xmax);
+    const float eps = 2.f * (e_round + e_acc) * 1.001f + e_f32;
+    qslack[row] = 2.f * eps;
+  }
 }
 
 __global__ void fill_inf_kernel(float* p, int n) {
@@ -388,67 +515,128 @@ __global__ void fill_inf_kernel(float* p, int n) {
   if (i < n) p[i] = INFINITY;
 }
 
-// Per query: keep the kk smallest of n_cand (approximate distance, index) pairs, ascending (d, i).
+__device__ __forceinline__ uint32_t ord_key(float f) {  // unsigned order == float order (no NaNs in the lists)
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Per query: tau~ = exact k-th smallest s~ over the n_strips * L listed rows (radix select on the ordered bit
+// pattern), candidates = every listed row with s~ <= tau~ + 2 eps, flag = the lists may be missing a row that also
+// satisfies that (a strip list full of such rows) or there are more candidates than CAP.
 __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __restrict__ cand_d,
-                                                                const int32_t* __restrict__ cand_i, int n_cand,
-                                                                int kk, float* __restrict__ out_d,
-                                                                int32_t* __restrict__ out_i) {
+                                                                const int32_t* __restrict__ cand_i, int n_strips,
+                                                                int L, int k, const float* __restrict__ qslack,
+                                                                int32_t* __restrict__ sel_i, int32_t* __restrict__ sel_n,
+                                                                int32_t* __restrict__ flag_count,
+                                                                int32_t* __restrict__ flag_list) {
   extern __shared__ uint8_t sraw[];
+  const int n_cand = n_strips * L;
   float* sd = reinterpret_cast<float*>(sraw);
   int32_t* si = reinterpret_cast<int32_t*>(sraw) + n_cand;
-  __shared__ float rd[8];
-  __shared__ int ri[8], rp[8];
-  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining, s_valid, s_cnt, s_flag;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) { s_valid = 0; s_cnt = 0; s_flag = 0; s_prefix = 0; }
+  __syncthreads();
+  int nv = 0;
   for (int i = tid; i < n_cand; i += 256) {
-    sd[i] = cand_d[(size_t)q * n_cand + i];
-    si[i] = cand_i[(size_t)q * n_cand + i];
+    const float d = cand_d[(size_t)q * n_cand + i];
+    const int id = cand_i[(size_t)q * n_cand + i];
+    sd[i] = d;
+    si[i] = id;
+    nv += id >= 0 ? 1 : 0;
+  }
+  nv = (int)warp_sum((float)nv);  // exact: counts are far below 2^24
+  if ((tid & 31) == 0) atomicAdd(&s_valid, nv);
+  __syncthreads();
+  float T = INFINITY;
+  if (s_valid > k) {
+    if (tid == 0) s_remaining = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int i = tid; i < n_cand; i += 256) {
+        if (si[i] < 0) continue;
+        const uint32_t key = ord_key(sd[i]);
+        if ((key & mask) == (prefix & mask)) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining, b = 0;
+        while (b < 255 && hist[b] < rem) rem -= hist[b++];
+        s_remaining = rem;
+        s_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+    }
+    T = ord_float(s_prefix) + qslack[q];
+  }
+  // candidates inside the slack (order irrelevant: the re-rank orders by exact distance, then id)
+  for (int i = tid; i < n_cand; i += 256) {
+    if (si[i] >= 0 && sd[i] <= T) {
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < CAP) sel_i[(size_t)q * CAP + pos] = si[i];
+    }
+  }
+  // a strip list that is full and lies entirely inside the slack may have dropped a row that belongs there too
+  for (int s = tid; s < n_strips; s += 256) {
+    bool full_inside = true;
+    for (int j = 0; j < L; ++j) {
+      const int i = s * L + j;
+      if (si[i] < 0 || !(sd[i] <= T)) { full_inside = false; break; }
+    }
+    if (full_inside) s_flag = 1;
   }
   __syncthreads();
-  for (int r = 0; r < kk; ++r) {
-    float bd = INFINITY;
-    int bi = INT_MAX, bp = -1;
-    for (int i = tid; i < n_cand; i += 256) {
-      const float d = sd[i];
-      const int id = si[i];
-      if (id >= 0 && (d < bd || (d == bd && id < bi))) {
-        bd = d; bi = id; bp = i;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (op >= 0 && (bp < 0 || od < bd || (od == bd && oi < bi))) {
-        bd = od; bi = oi; bp = op;
-      }
-    }
-    if (lane == 0) { rd[warp] = bd; ri[warp] = bi; rp[warp] = bp; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < 8; ++w)
-        if (rp[w] >= 0 && (rp[0] < 0 || rd[w] < rd[0] || (rd[w] == rd[0] && ri[w] < ri[0]))) {
-          rd[0] = rd[w]; ri[0] = ri[w]; rp[0] = rp[w];
-        }
-      out_d[(size_t)q * kk + r] = rp[0] >= 0 ? rd[0] : INFINITY;
-      out_i[(size_t)q * kk + r] = rp[0] >= 0 ? ri[0] : -1;
-      if (rp[0] >= 0) si[rp[0]] = -1;  // consume
-    }
-    __syncthreads();
+  if (tid == 0) {
+    const int cnt = s_cnt;
+    sel_n[q] = cnt < CAP ? cnt : CAP;
+    if (s_flag || cnt > CAP) flag_list[atomicAdd(flag_count, 1)] = q;
   }
 }
 
-// Per query: exact fp32 d2 = |q|^2 + |x|^2 - 2 q.x for kk candidates (one warp per candidate), then the k
-// smallest ascending (ties -> lower id) with global int64 labels.
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const float* __restrict__ x,
-                                                     const float* __restrict__ xnorm, const int32_t* __restrict__ ci,
-                                                     int kk, int k, int d, long long id_offset,
-                                                     float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  extern __shared__ __align__(16) float sq[];  // [d] query, then [kk] distances
-  float* dist = sq + d;
-  __shared__ float qn_s;
-  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* qr = q + (size_t)qi * d;
+// Exact fp32 q.x of one row by one warp (all lanes return the sum).  The summation order is part of the result: the
+// re-rank and the exact scan both use this function, so a row gets the same distance on either path.
+__device__ __forceinline__ float exact_dot(const float* __restrict__ sq, const float* __restrict__ xr, int d, int lane) {
+  float dot = 0.f;
+  if ((d & 3) == 0) {
+    // 16 KB row at d = 4096: 128-bit loads, four rows of the loop in flight per lane (a gather: latency, not math)
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    const int n4 = d >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int e = lane;
+    for (; e + 96 < n4; e += 128) {
+      const float4 v0 = __ldg(x4 + e), v1 = __ldg(x4 + e + 32), v2 = __ldg(x4 + e + 64), v3 = __ldg(x4 + e + 96);
+      const float4 w0 = q4[e], w1 = q4[e + 32], w2 = q4[e + 64], w3 = q4[e + 96];
+      a0 = fmaf(w0.x, v0.x, fmaf(w0.y, v0.y, fmaf(w0.z, v0.z, fmaf(w0.w, v0.w, a0))));
+      a1 = fmaf(w1.x, v1.x, fmaf(w1.y, v1.y, fmaf(w1.z, v1.z, fmaf(w1.w, v1.w, a1))));
+      a2 = fmaf(w2.x, v2.x, fmaf(w2.y, v2.y, fmaf(w2.z, v2.z, fmaf(w2.w, v2.w, a2))));
+      a3 = fmaf(w3.x, v3.x, fmaf(w3.y, v3.y, fmaf(w3.z, v3.z, fmaf(w3.w, v3.w, a3))));
+    }
+    for (; e < n4; e += 32) {
+      const float4 v = __ldg(x4 + e), w = q4[e];
+      a0 = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, a0))));
+    }
+    dot = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int e = lane; e < d; e += 32) dot = fmaf(sq[e], __ldg(xr + e), dot);
+  }
+  return warp_sum(dot);
+}
+__device__ __forceinline__ float exact_d2(float qn, float xn, float dot) {
+  return __fmaf_rn(-2.f, dot, __fadd_rn(qn, xn));  // |q|^2 + |x|^2 - 2 q.x, one fixed evaluation order
+}
+// |q|^2 of a query staged in shared memory by a 256-thread block (same order wherever it is used)
+__device__ __forceinline__ float block_query_norm(const float* __restrict__ qr, float* __restrict__ sq, int d,
+                                                  float* wsum /* [8] shared */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float ss = 0.f;
   for (int c = tid; c < d; c += 256) {
     const float v = qr[c];
@@ -456,71 +644,132 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
     ss = fmaf(v, v, ss);
   }
   ss = warp_sum(ss);
-  __shared__ float wsum[8];
   if (lane == 0) wsum[warp] = ss;
   __syncthreads();
-  if (tid == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += wsum[w];
-    qn_s = t;
+  float t = 0.f;
+  for (int w = 0; w < 8; ++w) t += wsum[w];
+  __syncthreads();
+  return t;
+}
+
+// Per query: exact fp32 distances of its candidates (one warp per candidate), then the k smallest ascending
+// (ties -> lower id) with global int64 labels; ranks past the candidate count are filled with (+inf, -1).
+__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const float* __restrict__ x,
+                                                     const float* __restrict__ xnorm, const int32_t* __restrict__ sel_i,
+                                                     const int32_t* __restrict__ sel_n, int k, int d,
+                                                     long long id_offset, float* __restrict__ out_d,
+                                                     int64_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) float sq[];  // [d] query, then [CAP] distances
+  float* dist = sq + d;
+  __shared__ float wsum[8];
+  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = sel_n[qi];
+  const int32_t* ci = sel_i + (size_t)qi * CAP;
+  const float qn = block_query_norm(q + (size_t)qi * d, sq, d, wsum);
+  for (int c = warp; c < n; c += 8) {
+    const int id = ci[c];
+    const float dot = exact_dot(sq, x + (size_t)id * d, d, lane);
+    if (lane == 0) dist[c] = exact_d2(qn, xnorm[id], dot);
   }
   __syncthreads();
-  for (int c = warp; c < kk; c += 8) {
-    const int id = ci[(size_t)qi * kk + c];
-    float dv = INFINITY;
-    if (id >= 0) {
-      const float* xr = x + (size_t)id * d;
-      float dot = 0.f;
-      if ((d & 3) == 0) {
-        // 16 KB row per candidate at d = 4096: 128-bit loads, four rows of the loop in flight per lane (the
-        // kernel is a gather of kk random rows per query: latency, not arithmetic)
-        const float4* x4 = reinterpret_cast<const float4*>(xr);
-        const float4* q4 = reinterpret_cast<const float4*>(sq);
-        const int n4 = d >> 2;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int e = lane;
-        for (; e + 96 < n4; e += 128) {
-          const float4 v0 = __ldg(x4 + e), v1 = __ldg(x4 + e + 32), v2 = __ldg(x4 + e + 64), v3 = __ldg(x4 + e + 96);
-          const float4 w0 = q4[e], w1 = q4[e + 32], w2 = q4[e + 64], w3 = q4[e + 96];
-          a0 = fmaf(w0.x, v0.x, fmaf(w0.y, v0.y, fmaf(w0.z, v0.z, fmaf(w0.w, v0.w, a0))));
-          a1 = fmaf(w1.x, v1.x, fmaf(w1.y, v1.y, fmaf(w1.z, v1.z, fmaf(w1.w, v1.w, a1))));
-          a2 = fmaf(w2.x, v2.x, fmaf(w2.y, v2.y, fmaf(w2.z, v2.z, fmaf(w2.w, v2.w, a2))));
-          a3 = fmaf(w3.x, v3.x, fmaf(w3.y, v3.y, fmaf(w3.z, v3.z, fmaf(w3.w, v3.w, a3))));
-        }
-        for (; e < n4; e += 32) {
-          const float4 v = __ldg(x4 + e), w = q4[e];
-          a0 = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, a0))));
-        }
-        dot = (a0 + a1) + (a2 + a3);
-      } else {
-        for (int e = lane; e < d; e += 32) dot = fmaf(sq[e], __ldg(xr + e), dot);
-      }
-      dot = warp_sum(dot);
-      dv = qn_s + xnorm[id] - 2.f * dot;
-    }
-    if (lane == 0) dist[c] = dv;
-  }
-  __syncthreads();
-  if (tid < kk) {
-    // rank of candidate tid among the kk (stable by (distance, id)); ranks < k are written
+  if (tid < n) {
+    // rank of candidate tid among the n (by distance, then id); ranks < k are written
     const float dm = dist[tid];
-    const int im = ci[(size_t)qi * kk + tid];
+    const int im = ci[tid];
     int rank = 0;
-    for (int j = 0; j < kk; ++j) {
+    for (int j = 0; j < n; ++j) {
       const float dj = dist[j];
-      const int ij = ci[(size_t)qi * kk + j];
-      if (ij >= 0 && (dj < dm || (dj == dm && (ij < im || (ij == im && j < tid))))) ++rank;
+      const int ij = ci[j];
+      if (dj < dm || (dj == dm && ij < im)) ++rank;
     }
-    if (im >= 0 && rank < k) {
+    if (rank < k) {
       out_d[(size_t)qi * k + rank] = dm;
       out_i[(size_t)qi * k + rank] = (int64_t)im + id_offset;
+    }
+  }
+  for (int r = n + tid; r < k; r += 256) {
+    out_d[(size_t)qi * k + r] = INFINITY;
+    out_i[(size_t)qi * k + r] = -1;
+  }
+}
+
+// Flagged queries only: exact distances against every row of the shard.  A row that beats the query's current k-th
+// result (by distance, then id) is merged into the sorted result under a per-query lock; the re-ranked candidates
+// are the starting point, so in the normal flagged case only the few rows the lists dropped are ever inserted.
+constexpr int SCAN_FQ = 4;  // flagged queries staged per pass (shared memory: FQ * d floats)
+__global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict__ q, const float* __restrict__ x,
+                                                         const float* __restrict__ xnorm, long long n_db, int d,
+                                                         int k, long long id_offset, int fq,
+                                                         const int32_t* __restrict__ flag_count,
+                                                         const int32_t* __restrict__ flag_list, int* __restrict__ locks,
+                                                         float* out_d, int64_t* out_i) {
+  extern __shared__ __align__(16) float sq[];  // [fq][d]
+  __shared__ float wsum[8];
+  __shared__ float s_qn[SCAN_FQ], s_bd[SCAN_FQ];
+  __shared__ long long s_bi[SCAN_FQ];
+  __shared__ int s_q[SCAN_FQ];
+  const int nf = *flag_count;
+  if (nf == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long chunk = (n_db + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * chunk, r1 = r0 + chunk < n_db ? r0 + chunk : n_db;
+  for (int g0 = 0; g0 < nf; g0 += fq) {
+    const int ng = nf - g0 < fq ? nf - g0 : fq;
+    __syncthreads();
+    for (int j = 0; j < ng; ++j) {
+      const int qi = flag_list[g0 + j];
+      const float qn = block_query_norm(q + (size_t)qi * d, sq + (size_t)j * d, d, wsum);
+      if (tid == 0) {
+        s_q[j] = qi;
+        s_qn[j] = qn;
+        s_bd[j] = *(volatile float*)(out_d + (size_t)qi * k + k - 1);
+        s_bi[j] = *(volatile long long*)(out_i + (size_t)qi * k + k - 1);
+      }
+    }
+    __syncthreads();
+    for (long long row = r0 + warp; row < r1; row += 8) {
+      const float xn = xnorm[row];
+      const long long gid = row + id_offset;
+      for (int j = 0; j < ng; ++j) {
+        const float dv = exact_d2(s_qn[j], xn, exact_dot(sq + (size_t)j * d, x + (size_t)row * d, d, lane));
+        const float bd = *(volatile float*)&s_bd[j];
+        const long long bi = *(volatile long long*)&s_bi[j];
+        // beats the current k-th result?  (an empty slot is (+inf, -1): anything finite beats it)
+        if (!(dv < bd || (dv == bd && (bi < 0 || gid <= bi)))) continue;
+        if (lane == 0) {
+          const int qi = s_q[j];
+          while (atomicCAS(&locks[qi], 0, 1) != 0) {}
+          __threadfence();
+          volatile float* D = out_d + (size_t)qi * k;
+          volatile long long* I = reinterpret_cast<volatile long long*>(out_i) + (size_t)qi * k;
+          bool dup = false;
+          for (int t = 0; t < k; ++t) dup |= I[t] == gid;
+          if (!dup) {
+            int pos = k;
+            for (int t = 0; t < k; ++t)
+              if (I[t] < 0 || dv < D[t] || (dv == D[t] && gid < I[t])) { pos = t; break; }
+            if (pos < k) {
+              for (int t = k - 1; t > pos; --t) { D[t] = D[t - 1]; I[t] = I[t - 1]; }
+              D[pos] = dv;
+              I[pos] = gid;
+            }
+          }
+          *(volatile float*)&s_bd[j] = D[k - 1];   // any value ever read here is a valid (possibly stale) bound
+          *(volatile long long*)&s_bi[j] = I[k - 1];
+          __threadfence();
+          atomicExch(&locks[qi], 0);
+        }
+        __syncwarp();
+      }
     }
   }
 }
 
 // Merge `parts` sorted (Q,k) lists (e.g. one per GPU shard after the NCCL allgather) into the global top-k.
+// Part s starts stride_d floats / stride_i int64s after part s-1 (so D and I may share one gathered buffer).
 __global__ void merge_parts_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int parts, int Q,
-                                   int k, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+                                   int k, long long stride_d, long long stride_i, float* __restrict__ out_d,
+                                   int64_t* __restrict__ out_i) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   int head[16];
@@ -531,9 +780,9 @@ __global__ void merge_parts_kernel(const float* __restrict__ D, const int64_t* _
     int bs = -1;
     for (int s = 0; s < parts; ++s) {
       if (head[s] >= k) continue;
-      const size_t o = ((size_t)s * Q + q) * k + head[s];
-      const float d = D[o];
-      const int64_t id = I[o];
+      const size_t o = (size_t)q * k + head[s];
+      const float d = D[(size_t)s * stride_d + o];
+      const int64_t id = I[(size_t)s * stride_i + o];
       if (id < 0) continue;
       if (bs < 0 || d < bd || (d == bd && id < bi)) {
         bd = d; bi = id; bs = s;
@@ -561,7 +810,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 [rows][dpad] row-major, box = 64 columns (128 bytes) x box_rows, SWIZZLE_128B, OOB rows -> zeros
+// fp16 [rows][dpad] row-major, box = 64 columns (128 bytes) x box_rows, SWIZZLE_128B, OOB rows -> zeros
 static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t dpad, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
@@ -569,7 +818,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t dpa
   cuuint64_t strides[1] = {dpad * 2};
   cuuint32_t box[2] = {BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
@@ -579,9 +828,19 @@ static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 static inline int dpad_of(int d) { return (d + BK - 1) / BK * BK; }
 
 struct Layout {
-  int dpad, n_mblk, n_tiles, tiles_per_strip, n_strips, kk, qpad;
-  size_t off_qb, off_qn, off_gb, off_cd, off_ci, off_sd, off_si, total;
+  int dpad, n_mblk, n_tiles, tiles_per_strip, n_strips, qpad, L, stages;
+  size_t off_qb, off_qn, off_qc, off_qs, off_gb, off_cd, off_ci, off_si, off_sn, off_fl, off_lk, total;
 };
+
+static int forced_stages() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVS_RETR_STAGES");
+    v = e ? atoi(e) : 0;
+    if (v != 3 && v != 4) v = 0;
+  }
+  return v;
+}
 
 static Layout make_layout(long long n_db, int nq, int d, int k) {
   Layout L;
@@ -589,30 +848,52 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   L.n_mblk = (nq + BM - 1) / BM;
   L.qpad = L.n_mblk * BM;
   L.n_tiles = (int)((n_db + BN - 1) / BN);
-  // Strips (each (strip, query-block pair) is one work unit of a CTA pair and yields k candidates per query):
+  // per-row list length: k plus room for rows inside the slack (a list that fills up with them flags the query for
+  // the exact scan); the 4-stage kernel holds 31 entries per row, the 3-stage one 79
+  int want_l = k + (k / 4 > 6 ? k / 4 : 6);
+  const int fs = forced_stages();
+  L.stages = fs ? fs : (want_l <= Smem<4>::LMAX ? 4 : 3);
+  const int lmax = L.stages == 4 ? Smem<4>::LMAX : Smem<3>::LMAX;
+  if (k > lmax) L.stages = 3;
+  const int lmax2 = L.stages == 4 ? Smem<4>::LMAX : Smem<3>::LMAX;
+  L.L = want_l < lmax2 ? want_l : lmax2;
+  // Strips (each (strip, query-block pair) is one work unit of a CTA pair and yields L listed rows per query):
   // enough units for ~32 rounds over the 74 clusters of a B200 (load balance to ~2 %), no more -- every strip
-  // restarts its per-row lists and adds k candidates per query to the selection pass -- at most 256, at least
-  // 16 tiles (4096 rows) each.
+  // restarts its per-row lists -- at most 256 (and what the selection kernel can hold), at least 16 tiles
+  // (4096 rows) each.
   const int n_mpair = (L.n_mblk + 1) / 2;
   int want = (32 * 74 + n_mpair - 1) / n_mpair;
   if (want > 256) want = 256;
+  if (want > MAX_CAND / L.L) want = MAX_CAND / L.L;
   int tps = (L.n_tiles + want - 1) / want;
   if (tps < 16) tps = 16;
   L.tiles_per_strip = tps;
   L.n_strips = (L.n_tiles + tps - 1) / tps;
-  L.kk = 2 * k > k + 32 ? 2 * k : k + 32;  // candidates re-ranked exactly
-  if (L.kk > L.n_strips * k) L.kk = L.n_strips * k;
-  if (L.kk > 256) L.kk = 256;
   size_t o = 0;
   L.off_qb = o; o += al256((size_t)L.qpad * L.dpad * 2);
   L.off_qn = o; o += al256((size_t)L.qpad * 4);
+  L.off_qc = o; o += al256((size_t)L.qpad * 4);
+  L.off_qs = o; o += al256((size_t)L.qpad * 4);
   L.off_gb = o; o += al256((size_t)L.qpad * 4);
-  L.off_cd = o; o += al256((size_t)L.qpad * L.n_strips * k * 4);
-  L.off_ci = o; o += al256((size_t)L.qpad * L.n_strips * k * 4);
-  L.off_sd = o; o += al256((size_t)nq * L.kk * 4);
-  L.off_si = o; o += al256((size_t)nq * L.kk * 4);
+  L.off_cd = o; o += al256((size_t)L.qpad * L.n_strips * L.L * 4);
+  L.off_ci = o; o += al256((size_t)L.qpad * L.n_strips * L.L * 4);
+  L.off_si = o; o += al256((size_t)nq * CAP * 4);
+  L.off_sn = o; o += al256((size_t)nq * 4);
+  L.off_fl = o; o += al256((size_t)(nq + 1) * 4);   // flag_count, then flag_list
+  L.off_lk = o; o += al256((size_t)nq * 4);
   L.total = o;
   return L;
+}
+
+template <int STAGES>
+static int launch_gemm(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, int n_units, cudaStream_t st) {
+  auto kern = flat_l2_topk_kernel<STAGES>;
+  NVS_OPT_IN_SMEM(kern, Smem<STAGES>::BYTES);
+  const int sms = nvs_sm_count();
+  const int grid = 2 * (n_units < sms / 2 ? n_units : sms / 2);  // clusters of two CTAs
+  kern<<<grid, THREADS, Smem<STAGES>::BYTES, st>>>(mq, mx, p);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
 }
 
 }  // namespace rt
@@ -623,99 +904,109 @@ using namespace nvs::rt;
 
 extern "C" int32_t nvs_flat_padded_dim(int32_t d) { return d > 0 ? dpad_of(d) : 0; }
 
-extern "C" int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_bf16, float* norms, void* stream) {
-  if (!x || !x_bf16 || !norms || n <= 0 || d <= 0) return NVS_ERR_ARG;
+extern "C" int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_f16, float* norms, float* stats,
+                                void* stream) {
+  if (!x || !x_f16 || !norms || !stats || n <= 0 || d <= 0) return NVS_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dp = dpad_of(d);
+  cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(float), st);
+  if (e != cudaSuccess) return nvs_set_cuda_error(e);
+  const long long total = (long long)n * d;
+  const long long want = (total + 255) / 256;
+  absmax_kernel<<<(unsigned)(want < 4096 ? want : 4096), 256, 0, st>>>(x, total, stats + 3);
+  NVS_CHECK_LAUNCH();
   const long long blocks = (n + 7) / 8;
-  to_bf16_norm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)x_bf16, norms, n, d, dp);
+  db_to_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (__half*)x_f16, norms, stats, n, d, dp);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
 
+extern "C" int32_t nvs_flat_max_k(void) { return KMAX; }
+
 extern "C" size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int32_t d, int32_t k) {
-  if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0) return 0;
+  if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > KMAX) return 0;
   return make_layout(n_db, nq, d, k).total;
 }
 
-extern "C" int nvs_flat_search(const float* db, const void* db_bf16, const float* db_norms, int64_t n_db,
-                               const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset, float* out_D,
-                               int64_t* out_I, void* workspace, size_t workspace_bytes, void* ev_gemm_start,
-                               void* ev_gemm_stop, void* stream) {
-  if (!db || !db_bf16 || !db_norms || !q || !out_D || !out_I || !workspace) return NVS_ERR_ARG;
+extern "C" int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,
+                               int64_t n_db, const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset,
+                               float* out_D, int64_t* out_I, void* workspace, size_t workspace_bytes,
+                               void* ev_gemm_start, void* ev_gemm_stop, void* stream) {
+  if (!db || !db_f16 || !db_norms || !db_stats || !q || !out_D || !out_I || !workspace) return NVS_ERR_ARG;
   if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0) return NVS_ERR_ARG;
-  if (k > KMAX) return NVS_ERR_UNSUPPORTED;   // per-row list lives in shared memory
+  if (k > KMAX) return NVS_ERR_UNSUPPORTED;   // per-row lists live in shared memory
   if (k > n_db) return NVS_ERR_ARG;
   if (n_db > 0x7fffffffLL - BN) return NVS_ERR_UNSUPPORTED;
+  if ((size_t)(d + CAP) * 4 > 96 * 1024) return NVS_ERR_UNSUPPORTED;  // query row staged in shared memory
   const Layout L = make_layout(n_db, nq, d, k);
   if (workspace_bytes < L.total) return NVS_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + L.off_qb);
+  __half* qb = reinterpret_cast<__half*>(ws + L.off_qb);
   float* qn = reinterpret_cast<float*>(ws + L.off_qn);
+  float* qc = reinterpret_cast<float*>(ws + L.off_qc);
+  float* qs = reinterpret_cast<float*>(ws + L.off_qs);
   float* gb = reinterpret_cast<float*>(ws + L.off_gb);
   float* cd = reinterpret_cast<float*>(ws + L.off_cd);
   int32_t* ci = reinterpret_cast<int32_t*>(ws + L.off_ci);
-  float* sd = reinterpret_cast<float*>(ws + L.off_sd);
   int32_t* si = reinterpret_cast<int32_t*>(ws + L.off_si);
+  int32_t* sn = reinterpret_cast<int32_t*>(ws + L.off_sn);
+  int32_t* fl = reinterpret_cast<int32_t*>(ws + L.off_fl);
+  int* lk = reinterpret_cast<int*>(ws + L.off_lk);
 
-  // queries -> bf16 (rows past nq stay zero: they only feed padded accumulator rows that are never flushed)
+  // queries -> fp16 (rows past nq stay zero: they only feed padded accumulator rows that are never flushed);
+  // flag counter + list and the scan locks (adjacent in the workspace) start at zero
   cudaError_t e = cudaMemsetAsync(qb, 0, (size_t)L.qpad * L.dpad * 2, st);
   if (e != cudaSuccess) return nvs_set_cuda_error(e);
-  to_bf16_norm_kernel<<<(nq + 7) / 8, 256, 0, st>>>(q, qb, qn, nq, d, L.dpad);
+  e = cudaMemsetAsync(fl, 0, (L.off_lk - L.off_fl) + al256((size_t)nq * 4), st);
+  if (e != cudaSuccess) return nvs_set_cuda_error(e);
+  q_to_f16_kernel<<<(nq + 7) / 8, 256, 0, st>>>(q, qb, qn, qc, qs, db_stats, nq, d, L.dpad);
   NVS_CHECK_LAUNCH();
   fill_inf_kernel<<<(L.qpad + 255) / 256, 256, 0, st>>>(gb, L.qpad);
   NVS_CHECK_LAUNCH();
 
   CUtensorMap mq, mx;
   if (make_map(&mq, qb, (uint64_t)L.qpad, (uint64_t)L.dpad, BM) != NVS_OK) return NVS_ERR_CUDA;
-  if (make_map(&mx, db_bf16, (uint64_t)n_db, (uint64_t)L.dpad, BN / 2) != NVS_OK) return NVS_ERR_CUDA;  // half tiles
+  if (make_map(&mx, db_f16, (uint64_t)n_db, (uint64_t)L.dpad, BN / 2) != NVS_OK) return NVS_ERR_CUDA;  // half tiles
 
   Params p;
-  p.xnorm = db_norms; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
+  p.xnorm = db_norms; p.qcoef = qc; p.qslack = qs; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
   p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
-  p.k = k; p.kp = k | 1;
+  p.k = k; p.L = L.L; p.lp = L.L | 1;
   p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;
   p.n_mpair = (L.n_mblk + 1) / 2;
+  const int n_units = p.n_mpair * L.n_strips;  // work units of CTA pairs
 
-  static int sm_count = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaFuncSetAttribute(flat_l2_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return nvs_set_cuda_error(e);
-    attr_done = true;
-  }
-  const int n_units = ((L.n_mblk + 1) / 2) * L.n_strips;           // work units of CTA pairs
-  int grid = 2 * (n_units < sm_count / 2 ? n_units : sm_count / 2);  // clusters of two CTAs
   if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
-  flat_l2_topk_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mq, mx, p);
-  NVS_CHECK_LAUNCH();
+  int rc = L.stages == 4 ? launch_gemm<4>(mq, mx, p, n_units, st) : launch_gemm<3>(mq, mx, p, n_units, st);
+  if (rc != NVS_OK) return rc;
   if (ev_gemm_stop) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_stop), st);
 
-  const int n_cand = L.n_strips * k;
-  static bool sel_attr = false;
-  if (!sel_attr) {
-    e = cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return nvs_set_cuda_error(e);
-    e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return nvs_set_cuda_error(e);
-    sel_attr = true;
-  }
-  if ((size_t)n_cand * 8 > 96 * 1024 || (size_t)(d + L.kk) * 4 > 96 * 1024) return NVS_ERR_UNSUPPORTED;
-  select_candidates_kernel<<<nq, 256, (size_t)n_cand * 8, st>>>(cd, ci, n_cand, L.kk, sd, si);
+  const int n_cand = L.n_strips * L.L;
+  NVS_OPT_IN_SMEM(select_candidates_kernel, 96 * 1024);
+  NVS_OPT_IN_SMEM(rerank_kernel, 96 * 1024);
+  NVS_OPT_IN_SMEM(exact_scan_kernel, 96 * 1024);
+  select_candidates_kernel<<<nq, 256, (size_t)n_cand * 8, st>>>(cd, ci, L.n_strips, L.L, k, qs, si, sn, fl, fl + 1);
   NVS_CHECK_LAUNCH();
-  rerank_kernel<<<nq, 256, (size_t)(d + L.kk) * 4, st>>>(q, db, db_norms, si, L.kk, k, d, (long long)id_offset,
-                                                         out_D, out_I);
+  rerank_kernel<<<nq, 256, (size_t)(d + CAP) * 4, st>>>(q, db, db_norms, si, sn, k, d, (long long)id_offset, out_D, out_I);
+  NVS_CHECK_LAUNCH();
+  int fq = 16384 / d;
+  fq = fq < 1 ? 1 : (fq > SCAN_FQ ? SCAN_FQ : fq);
+  exact_scan_kernel<<<2 * nvs_sm_count(), 256, (size_t)fq * d * 4, st>>>(q, db, db_norms, (long long)n_db, d, k,
+                                                                        (long long)id_offset, fq, fl, fl + 1, lk,
+                                                                        out_D, out_I);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
 
 extern "C" int nvs_topk_merge(const float* D_parts, const int64_t* I_parts, int32_t parts, int32_t nq, int32_t k,
-                              float* out_D, int64_t* out_I, void* stream) {
+                              int64_t part_stride_d, int64_t part_stride_i, float* out_D, int64_t* out_I,
+                              void* stream) {
   if (!D_parts || !I_parts || !out_D || !out_I || parts <= 0 || parts > 16 || nq <= 0 || k <= 0) return NVS_ERR_ARG;
-  merge_parts_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(D_parts, I_parts, parts, nq, k, out_D, out_I);
+  const long long sd = part_stride_d > 0 ? part_stride_d : (long long)nq * k;
+  const long long si = part_stride_i > 0 ? part_stride_i : (long long)nq * k;
+  merge_parts_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(D_parts, I_parts, parts, nq, k, sd, si, out_D,
+                                                                         out_I);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }

@@ -478,8 +478,16 @@ def _fold(weight, bias, bn, eps):
     return w.to(torch.float32), b.to(torch.float32)
 
 
+def row3_mode() -> int:
+    """Which variant of the row-stationary tensor-core conv serves layers with <= 32 output channels (env
+    NVS_TC_ROW3): 0 = none (nine single-tap pipeline steps), 32 = 32-channel chunks, 16 = 16-channel chunks."""
+    import os
+    v = os.environ.get("NVS_TC_ROW3", "32")
+    return {"0": 0, "1": 32, "32": 32, "16": 16}.get(v, 32)
+
+
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
-                 eps: float = 1e-5, cin_segments=None, pair_taps: bool = True):
+                 eps: float = 1e-5, cin_segments=None, pair_taps: Optional[bool] = None):
     """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc.
 
     w_hi = w rounded to tf32 (10 explicit mantissa bits), w_lo = tf32-rounded (w - w_hi).
@@ -504,6 +512,8 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
     assert cpad > 0, cout
     wt = torch.zeros(9, cpad, cin, dtype=torch.float32, device=w.device)
     wt[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    if pair_taps is None:  # 16-channel inputs: paired taps unless the 16-channel row-stationary kernel takes the layer
+        pair_taps = row3_mode() != 16
     if cin == 16 and cpad == 32 and pair_taps:
         # paired-tap layout for 16-channel inputs (NvsConvTcArgs.flags bit 1): K row of step t =
         # [tap 2t, channels 0-15 | tap 2t+1, channels 0-15]; the tenth tap is zero
@@ -590,12 +600,16 @@ class TcConv(object):
         a.pool_c_total = dst_pool.shape[3] if (dst_pool is not None and dst_mode != 3) else 0
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
-        # row-stationary kernel (conv_tc.cu Cfg: ROW3) for layers with <= 32 output channels on 32-channel rows: the
-        # packed [9][32][cin] weights ARE its [3 ky][3 kx x 32][cin] layout, so only the flag differs
-        row3 = (os.environ.get("NVS_TC_ROW3", "1") != "0" and bp.numel() == 32 and not paired and a.c0 % 32 == 0
-                and a.c1 % 32 == 0 and dst_mode in (1, 3) and (dst_pool is None or dst_mode == 3))
+        # row-stationary kernel (conv_tc.cu Cfg: ROW3) for layers with <= 32 output channels: the packed [9][32][cin]
+        # weights ARE its [3 ky][3 kx x 32][cin] layout, so only the flag differs.  Mode 32: 32-channel chunks (two A
+        # slots in tensor memory); mode 16: 16-channel chunks (four slots, also serves 16-channel inputs).
+        mode = row3_mode()
+        chunk = 16 if mode == 16 else 32
+        row3 = (mode != 0 and bp.numel() == 32 and not paired and a.c0 % chunk == 0 and a.c1 % chunk == 0
+                and dst_mode != 2 and (dst_mode != 0 or dst_pool is not None))
         self.row3 = row3
-        a.flags = (1 if deterministic else 0) | (2 if paired else 0) | (4 if row3 else 0)
+        a.flags = ((1 if deterministic else 0) | (2 if paired else 0) | (4 if row3 else 0) |
+                   (8 if row3 and mode == 16 else 0))
         segs = getattr(hi, "nvs_segments", None)
         a.c0_real = a.c1_real = 0
         if segs is not None and len(segs) == (2 if src1 is not None else 1) and not paired:
@@ -617,7 +631,7 @@ class TcConv(object):
         self._mem = C.create_string_buffer(int(lib().nvs_conv_tc_plan_bytes()))
         check(lib().nvs_conv_tc_plan_init(self._mem, C.byref(a)), "nvs_conv_tc_plan_init")
         self.flops = 2.0 * 9 * (a.c0 + a.c1) * cout * H * W * B
-        self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05" + (" row3" if row3 else "")
+        self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05" + (f" row3/{chunk}" if row3 else "")
 
     def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
         check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _ptr(dst2_override), _stream()),

@@ -2,13 +2,15 @@
 
     index = IndexFlatL2(d); index.add(db); D, I = index.search(q, k)
 
-``add`` keeps the fp32 rows resident in HBM and builds the bf16 GEMM operand + squared norms once;
-``search`` runs the tcgen05/TMEM GEMM with fused per-row top-k and the fp32 re-rank (csrc/retrieval.cu).
+``add`` keeps the fp32 rows resident in HBM and builds the fp16 GEMM operand, squared norms and the shard statistics
+behind the screen's error bound once; ``search`` runs the tcgen05/TMEM GEMM with fused per-row lists, the selection
+of everything inside the error bound, the fp32 re-rank and (for queries the lists cannot decide) the exact scan
+(csrc/retrieval.cu): the result is the fp32 result.
 numpy in -> numpy out (like faiss); CUDA tensors in -> CUDA tensors out.
 
 ShardedIndexFlatL2 row-shards the database over the ranks of a torch.distributed process group: every rank
-searches its shard with global ids, one all_gather moves the (Q,k) partial results (NCCL over NVLink on GPUs),
-and every rank merges world_size*k candidates per query.
+searches its shard with global ids, ONE all_gather moves the packed (Q,k) distances + labels (NCCL over NVLink on
+GPUs), and every rank merges world_size*k candidates per query.
 """
 from __future__ import annotations
 
@@ -20,7 +22,7 @@ import torch
 from . import ops, torch_ops
 from ._cabi import check, lib
 
-KMAX = 31
+KMAX = 64  # nvs_flat_max_k(): per-row lists live in shared memory
 
 
 def _as_dev(x, device) -> Tuple[torch.Tensor, bool]:
@@ -36,8 +38,9 @@ class IndexFlatL2(object):
         self.device = torch.device(device)
         self.ntotal = 0
         self._x = None       # fp32 rows (re-rank operand, exact distances)
-        self._xb = None      # bf16 rows padded to a multiple of 64 columns (GEMM operand)
+        self._xb = None      # fp16 rows padded to a multiple of 64 columns (GEMM operand), one scale per shard
         self._xn = None      # |x|^2
+        self._st = None      # max |x|^2, max |x - fp16(x)|^2, scale exponent, max |component|
         self._ws = None
 
     def add(self, x) -> None:
@@ -46,30 +49,38 @@ class IndexFlatL2(object):
         self._x = x if self._x is None else torch.cat([self._x, x], 0)
         n = self._x.shape[0]
         dpad = int(lib().nvs_flat_padded_dim(self.d))
-        self._xb = torch.empty(n, dpad, dtype=torch.bfloat16, device=self.device)
+        self._xb = torch.empty(n, dpad, dtype=torch.float16, device=self.device)
         self._xn = torch.empty(n, dtype=torch.float32, device=self.device)
+        self._st = torch.empty(4, dtype=torch.float32, device=self.device)
         check(lib().nvs_flat_prepare(self._x.data_ptr(), n, self.d, self._xb.data_ptr(), self._xn.data_ptr(),
-                                     ops._stream()), "nvs_flat_prepare")
-        ops.LAUNCHES[0] += 1
+                                     self._st.data_ptr(), ops._stream()), "nvs_flat_prepare")
+        ops.LAUNCHES[0] += 2
         self.ntotal = n
 
-    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0, gemm_events=None):
+    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0, gemm_events=None, out=None):
         """``gemm_events``: optional (start, stop) torch.cuda.Event pair recorded around the GEMM kernel.
+        ``out``: optional (D (nq,k) float32, I (nq,k) int64) tensors that receive the result.
         Runs as the custom operator torch.ops.nanovs.flat_l2_search (CUDA dispatch key only)."""
-        self._gemm_events = gemm_events
+        self._gemm_events, self._out = gemm_events, out
         try:
             return torch.ops.nanovs.flat_l2_search(q, torch_ops.register_index(self), int(k), int(id_offset))
         finally:
-            self._gemm_events = None
+            self._gemm_events = self._out = None
 
     def _search_impl(self, q: torch.Tensor, k: int, id_offset: int = 0):
         gemm_events = getattr(self, "_gemm_events", None)
         assert self.ntotal > 0, "empty index"
         if k > KMAX:
-            raise NotImplementedError(f"k <= {KMAX} (per-row top-k list lives in shared memory)")
+            raise NotImplementedError(f"k <= {KMAX} (per-row lists live in shared memory)")
+        if k > self.ntotal:
+            raise ValueError(f"k = {k} > ntotal = {self.ntotal}")
         nq = q.shape[0]
-        D = torch.empty(nq, k, dtype=torch.float32, device=self.device)
-        I = torch.empty(nq, k, dtype=torch.int64, device=self.device)
+        out = getattr(self, "_out", None)  # caller-provided (D, I) views, e.g. of one packed all_gather buffer
+        if out is not None:
+            D, I = out
+        else:
+            D = torch.empty(nq, k, dtype=torch.float32, device=self.device)
+            I = torch.empty(nq, k, dtype=torch.int64, device=self.device)
         nbytes = int(lib().nvs_flat_search_workspace_bytes(self.ntotal, nq, self.d, k))
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -78,11 +89,11 @@ class IndexFlatL2(object):
             for ev in gemm_events:
                 ev.record()  # forces creation of the underlying cudaEvent_t; re-recorded inside the library
             e0, e1 = gemm_events[0].cuda_event, gemm_events[1].cuda_event
-        check(lib().nvs_flat_search(self._x.data_ptr(), self._xb.data_ptr(), self._xn.data_ptr(), self.ntotal,
-                                    q.data_ptr(), nq, self.d, k, id_offset, D.data_ptr(), I.data_ptr(),
+        check(lib().nvs_flat_search(self._x.data_ptr(), self._xb.data_ptr(), self._xn.data_ptr(), self._st.data_ptr(),
+                                    self.ntotal, q.data_ptr(), nq, self.d, k, id_offset, D.data_ptr(), I.data_ptr(),
                                     self._ws.data_ptr(), self._ws.numel(), e0, e1, ops._stream()),
               "nvs_flat_search")
-        ops.LAUNCHES[0] += 4
+        ops.LAUNCHES[0] += 6  # query conversion, bound fill, GEMM + lists, selection, re-rank, exact scan
         return D, I
 
     def search(self, q, k: int):
@@ -101,11 +112,17 @@ def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor):
 
 def _merge_topk_impl(D_parts: torch.Tensor, I_parts: torch.Tensor):
     parts, nq, k = D_parts.shape
-    D_parts, I_parts = D_parts.contiguous(), I_parts.contiguous()
+    # any layout whose (nq, k) blocks are contiguous is read in place: e.g. views of one gathered buffer
+    def _ok(t):
+        return t.stride(2) == 1 and t.stride(1) == k and t.stride(0) >= nq * k
+    if not _ok(D_parts):
+        D_parts = D_parts.contiguous()
+    if not _ok(I_parts):
+        I_parts = I_parts.contiguous()
     D = torch.empty(nq, k, dtype=torch.float32, device=D_parts.device)
     I = torch.empty(nq, k, dtype=torch.int64, device=D_parts.device)
-    check(lib().nvs_topk_merge(D_parts.data_ptr(), I_parts.data_ptr(), parts, nq, k, D.data_ptr(), I.data_ptr(),
-                               ops._stream()), "nvs_topk_merge")
+    check(lib().nvs_topk_merge(D_parts.data_ptr(), I_parts.data_ptr(), parts, nq, k, D_parts.stride(0),
+                               I_parts.stride(0), D.data_ptr(), I.data_ptr(), ops._stream()), "nvs_topk_merge")
     ops.LAUNCHES[0] += 1
     return D, I
 
@@ -148,18 +165,37 @@ class ShardedIndexFlatL2(object):
         else:
             self._shard = x_shard
 
+    @staticmethod
+    def _packed_views(buf: torch.Tensor, parts: int, nq: int, k: int):
+        """(parts, stride) int64 words -> D (parts,nq,k) float32 and I (parts,nq,k) int64 views: a part is nq*k labels
+        followed by nq*k distances (two per word)."""
+        n = nq * k
+        stride = buf.shape[1]
+        I = buf.as_strided((parts, nq, k), (stride, k, 1), 0)
+        D = buf.view(torch.float32).as_strided((parts, nq, k), (2 * stride, k, 1), 2 * n)
+        return D, I
+
     def search(self, q: torch.Tensor, k: int, gemm_events=None):
+        nq = q.shape[0]
+        if self.world == 1:
+            if self._index is not None:
+                return self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo,
+                                                 gemm_events=gemm_events)
+            return self._local_search(self._shard, q, k, self.lo)
+        # ONE packed buffer per rank (labels, then distances) -> ONE all_gather; the shard search writes straight
+        # into this rank's send buffer and the merge kernel reads the gathered parts in place
+        words = nq * k + (nq * k + 1) // 2
+        dev = self.device if self._index is not None else q.device
+        mine = torch.empty(1, words, dtype=torch.int64, device=dev)
+        Dm, Im = self._packed_views(mine, 1, nq, k)
         if self._index is not None:
-            D, I = self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo,
-                                             gemm_events=gemm_events)
+            self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo,
+                                      gemm_events=gemm_events, out=(Dm[0], Im[0]))
         else:
             D, I = self._local_search(self._shard, q, k, self.lo)
-        if self.world == 1:
-            return D, I
-        nq = D.shape[0]
-        # rank-major concatenation along dim 0 == the [parts][nq][k] layout nvs_topk_merge expects
-        Dg = torch.empty(self.world * nq, k, dtype=D.dtype, device=D.device)
-        Ig = torch.empty(self.world * nq, k, dtype=I.dtype, device=I.device)
-        self.dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
-        return self._merge(Dg.view(self.world, nq, k), Ig.view(self.world, nq, k))
+            Dm[0].copy_(D)
+            Im[0].copy_(I)
+        gathered = torch.empty(self.world, words, dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        Dg, Ig = self._packed_views(gathered, self.world, nq, k)
+        return self._merge(Dg, Ig)

@@ -18,8 +18,13 @@ def test_reference_arm_json_line():
     assert d["metric"] == "KP2DTiny-S frames/s @240x320" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
+    # the config object is the native arm's, verbatim (the driver compares the two arms' configs)
+    assert set(d["config"]) == {"workload", "batch_per_gpu", "global_batch", "parallelism", "conv_backend", "l2"}
+    assert d["config"]["parallelism"] == "frame-dp1" and d["config"]["batch_per_gpu"] == 256
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    staged = os.path.isdir(os.path.join(REPO, "oracle", "_ref", "src", "kp2dtiny"))
+    assert cb["kind"] == ("reference" if staged else "port")  # the reference's own modules when oracle/_ref is staged
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -209,22 +209,54 @@ def test_conv_tc_row_stationary_variant(c0, c1, cout, H, W, layout, monkeypatch)
     s0 = _nhwc(x[:, :c0]).cuda()
     s1 = _nhwc(x[:, c0:]).cuda() if c1 else None
     outs = {}
-    for flag in ("1", "0"):
+    for flag in ("32", "16", "0"):  # 32- / 16-channel chunks / the nine-step kernel
         monkeypatch.setenv("NVS_TC_ROW3", flag)
         cpad = packed[2].numel()
         out = torch.zeros((B, H, W, cpad) if layout == 0 else (B, cout, H, W), device="cuda")
         op = ops.TcConv(s0, packed, cout, act=1, src1=s1, dst=out, dst_layout=layout)
-        assert op.row3 == (flag == "1")
+        assert op.row3 == (flag != "0")
         op.run()
         torch.cuda.synchronize()
         outs[flag] = out[..., :cout].permute(0, 3, 1, 2) if layout == 0 else out
         assert rel_err(outs[flag], ref) < 2e-5, (flag, rel_err(outs[flag], ref))
-    assert rel_err(outs["1"], outs["0"]) < 1e-5
+    assert rel_err(outs["32"], outs["0"]) < 1e-5 and rel_err(outs["16"], outs["0"]) < 1e-5
 
 
-def test_conv_tc_row_stationary_keypoint_heads(monkeypatch):
+@pytest.mark.parametrize("cin,H,W,mode", [(16, 40, 56, "16"), (16, 22, 62, "16"), (32, 24, 40, "32"), (32, 18, 33, "16")])
+def test_conv_tc_row_stationary_max_pool(cin, H, W, mode, monkeypatch):
+    """MaxPool2d(2,2) in the ROW3 epilogue (the two rows of a pooling pair live in different warps): pooled-only output
+    (backbone conv1b, encoders.py:111) and full + pooled, odd and even sizes, 16-channel inputs on the 16-channel-chunk
+    variant."""
+    from nano_vs_slam_b200 import ops
+
+    monkeypatch.setenv("NVS_TC_ROW3", mode)
+    g = torch.Generator().manual_seed(cin + H + W)
+    B = 3
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(32, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    assert packed[0].shape[0] == 9  # not the paired-tap layout
+    xs = _nhwc(x).cuda()
+    only = torch.zeros(B, H // 2, W // 2, 32, device="cuda")
+    op = ops.TcConv(xs, packed, 32, act=1, dst=None, dst_mode=0, dst_pool=only)
+    assert op.row3
+    op.run()
+    assert rel_err(only.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
+    full = torch.zeros(B, H, W, 32, device="cuda")
+    both = torch.zeros_like(only)
+    ops.TcConv(xs, packed, 32, act=1, dst=full, dst_pool=both).run()
+    assert rel_err(full.permute(0, 3, 1, 2), ref) < 2e-5
+    assert rel_err(both.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["32", "16"])
+def test_conv_tc_row_stationary_keypoint_heads(mode, monkeypatch):
     """The fused keypoint-head conv (score | location trunks -> 3 channels, sigmoid / tanh split) on the ROW3 kernel."""
     from nano_vs_slam_b200 import ops
+
+    monkeypatch.setenv("NVS_TC_ROW3", mode)
 
     g = torch.Generator().manual_seed(77)
     B, C, H, W = 2, 64, 15, 47

@@ -45,11 +45,15 @@ def _worker(rank, world, port, n_db, nq, d, k, out):
     dist.destroy_process_group()
 
 
-def test_sharded_index_world2_gloo():
+import pytest
+
+
+@pytest.mark.parametrize("nq,k", [(24, 7), (23, 5)])  # nq*k even / odd: the packed (labels | distances) buffer pads
+def test_sharded_index_world2_gloo(nq, k):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), 1001, 24, 256, 7, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 1001, nq, 256, k, out), nprocs=world, join=True)
     assert dict(out) == {0: 1, 1: 1}
 
 
