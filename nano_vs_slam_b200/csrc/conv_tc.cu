@@ -889,7 +889,10 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   const int sms = nvs_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
-  while (C::NS % q.issuers != 0) --q.issuers;  // a slot must always be consumed by the same issuer
+  // a slot must always be consumed by the same issuer, and every issuer needs a step in every tile (all of them commit
+  // the tile's accumulator): issuers | ring size, issuers <= steps per tile
+  const int steps = C::TAPS * (p.c0_chunks + p.c1_chunks);
+  while (q.issuers > 1 && (C::NS % q.issuers != 0 || q.issuers > steps)) --q.issuers;
   kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;

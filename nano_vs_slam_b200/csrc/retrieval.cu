@@ -50,10 +50,10 @@ constexpr int CAP = 256;                    // candidates re-ranked exactly per 
 constexpr int MAX_CAND = 12288;             // n_strips * L the selection kernel holds in shared memory (96 KiB)
 
 // shared memory map (dynamic, 1024-byte aligned base): STAGES operand stages, then the per-row lists.
-// 4 stages leave room for lists of 31 entries, 3 stages for 79 (odd pitch: conflict-free row-per-thread access).
+// 4 stages leave room for lists of 31 entries, 3 stages for 79, 2 for 127 (odd pitch: conflict-free row-per-thread access).
 template <int STAGES>
 struct Smem {
-  static constexpr int LMAX = STAGES == 4 ? 31 : 79;
+  static constexpr int LMAX = STAGES == 4 ? 31 : (STAGES == 3 ? 79 : 127);
   static constexpr int LIST_D = STAGES * STAGE_BYTES;               // float [128][LMAX]
   static constexpr int LIST_I = LIST_D + BM * LMAX * 4;             // int   [128][LMAX]
   static constexpr int XN = LIST_I + BM * LMAX * 4;                 // float [2][256]
@@ -697,6 +697,9 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
 // result (by distance, then id) is merged into the sorted result under a per-query lock; the re-ranked candidates
 // are the starting point, so in the normal flagged case only the few rows the lists dropped are ever inserted.
 constexpr int SCAN_FQ = 4;  // flagged queries staged per pass (shared memory: FQ * d floats)
+__device__ __forceinline__ unsigned long long pack_bound(float d, int row) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)row;
+}
 __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict__ q, const float* __restrict__ x,
                                                          const float* __restrict__ xnorm, long long n_db, int d,
                                                          int k, long long id_offset, int fq,
@@ -705,8 +708,10 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
                                                          float* out_d, int64_t* out_i) {
   extern __shared__ __align__(16) float sq[];  // [fq][d]
   __shared__ float wsum[8];
-  __shared__ float s_qn[SCAN_FQ], s_bd[SCAN_FQ];
-  __shared__ long long s_bi[SCAN_FQ];
+  __shared__ float s_qn[SCAN_FQ];
+  // the query's current k-th result as ONE 64-bit word (distance bits << 32 | shard-local row): warps update it
+  // concurrently, and a reader must never pair one update's distance with another's row
+  __shared__ unsigned long long s_bound[SCAN_FQ];
   __shared__ int s_q[SCAN_FQ];
   const int nf = *flag_count;
   if (nf == 0) return;
@@ -722,8 +727,14 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
       if (tid == 0) {
         s_q[j] = qi;
         s_qn[j] = qn;
-        s_bd[j] = *(volatile float*)(out_d + (size_t)qi * k + k - 1);
-        s_bi[j] = *(volatile long long*)(out_i + (size_t)qi * k + k - 1);
+        // other CTAs may already be merging rows into this query's result: read the (distance, label) pair under the lock
+        while (atomicCAS(&locks[qi], 0, 1) != 0) {}
+        __threadfence();
+        const float bd0 = *(volatile float*)(out_d + (size_t)qi * k + k - 1);
+        const long long bi0 = *(volatile long long*)(out_i + (size_t)qi * k + k - 1);
+        __threadfence();
+        atomicExch(&locks[qi], 0);
+        s_bound[j] = pack_bound(bd0, bi0 < 0 ? -1 : (int)(bi0 - id_offset));
       }
     }
     __syncthreads();
@@ -732,10 +743,11 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
       const long long gid = row + id_offset;
       for (int j = 0; j < ng; ++j) {
         const float dv = exact_d2(s_qn[j], xn, exact_dot(sq + (size_t)j * d, x + (size_t)row * d, d, lane));
-        const float bd = *(volatile float*)&s_bd[j];
-        const long long bi = *(volatile long long*)&s_bi[j];
+        const unsigned long long bw = *(volatile unsigned long long*)&s_bound[j];
+        const float bd = __uint_as_float((unsigned)(bw >> 32));
+        const int bi = (int)(unsigned)(bw & 0xffffffffull);
         // beats the current k-th result?  (an empty slot is (+inf, -1): anything finite beats it)
-        if (!(dv < bd || (dv == bd && (bi < 0 || gid <= bi)))) continue;
+        if (!(dv < bd || (dv == bd && (bi < 0 || row <= (long long)bi)))) continue;
         if (lane == 0) {
           const int qi = s_q[j];
           while (atomicCAS(&locks[qi], 0, 1) != 0) {}
@@ -754,8 +766,9 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const float* __restrict
               I[pos] = gid;
             }
           }
-          *(volatile float*)&s_bd[j] = D[k - 1];   // any value ever read here is a valid (possibly stale) bound
-          *(volatile long long*)&s_bi[j] = I[k - 1];
+          // any word ever stored here is some past k-th result of the query: a valid (possibly stale) bound
+          const long long ik = I[k - 1];
+          *(volatile unsigned long long*)&s_bound[j] = pack_bound(D[k - 1], ik < 0 ? -1 : (int)(ik - id_offset));
           __threadfence();
           atomicExch(&locks[qi], 0);
         }
@@ -837,7 +850,7 @@ static int forced_stages() {
   if (v < 0) {
     const char* e = getenv("NVS_RETR_STAGES");
     v = e ? atoi(e) : 0;
-    if (v != 3 && v != 4) v = 0;
+    if (v != 2 && v != 3 && v != 4) v = 0;
   }
   return v;
 }
@@ -851,12 +864,13 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   // per-row list length: k plus room for rows inside the slack (a list that fills up with them flags the query for
   // the exact scan); the 4-stage kernel holds 31 entries per row, the 3-stage one 79
   int want_l = k + (k / 4 > 6 ? k / 4 : 6);
+  // three operand stages: measured 10 % faster than four at 10k x 1M x 4096 (98.2 vs 109.0 ms, same lists) and room
+  // for lists of 79; NVS_RETR_STAGES = 2 / 3 / 4 for A/B runs
+  auto lmax_of = [](int st) { return st == 4 ? Smem<4>::LMAX : (st == 3 ? Smem<3>::LMAX : Smem<2>::LMAX); };
   const int fs = forced_stages();
-  L.stages = fs ? fs : (want_l <= Smem<4>::LMAX ? 4 : 3);
-  const int lmax = L.stages == 4 ? Smem<4>::LMAX : Smem<3>::LMAX;
-  if (k > lmax) L.stages = 3;
-  const int lmax2 = L.stages == 4 ? Smem<4>::LMAX : Smem<3>::LMAX;
-  L.L = want_l < lmax2 ? want_l : lmax2;
+  L.stages = fs ? fs : 3;
+  if (k > lmax_of(L.stages)) L.stages = 3;
+  L.L = want_l < lmax_of(L.stages) ? want_l : lmax_of(L.stages);
   // Strips (each (strip, query-block pair) is one work unit of a CTA pair and yields L listed rows per query):
   // enough units for ~32 rounds over the 74 clusters of a B200 (load balance to ~2 %), no more -- every strip
   // restarts its per-row lists -- at most 256 (and what the selection kernel can hold), at least 16 tiles
@@ -978,7 +992,8 @@ extern "C" int nvs_flat_search(const float* db, const void* db_f16, const float*
   const int n_units = p.n_mpair * L.n_strips;  // work units of CTA pairs
 
   if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
-  int rc = L.stages == 4 ? launch_gemm<4>(mq, mx, p, n_units, st) : launch_gemm<3>(mq, mx, p, n_units, st);
+  int rc = L.stages == 4 ? launch_gemm<4>(mq, mx, p, n_units, st)
+                         : (L.stages == 3 ? launch_gemm<3>(mq, mx, p, n_units, st) : launch_gemm<2>(mq, mx, p, n_units, st));
   if (rc != NVS_OK) return rc;
   if (ev_gemm_stop) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_stop), st);
 

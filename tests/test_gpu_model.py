@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import POST_FEAT_TOL_TC, REL_TOL, golden_cases, load_golden, rel_err, tol
+from util import REL_TOL, golden_cases, load_golden, post_feat_errors, rel_err, tol
 
 pytestmark = pytest.mark.gpu
 
@@ -43,7 +43,8 @@ def test_model_matches_reference_golden(path):
     assert torch.equal(post["score"].cpu() > 0, c["post"]["score"] > 0)
     assert rel_err(post["score"], c["post"]["score"]) < REL_TOL
     assert float((post["coord"].cpu() - c["post"]["coord"]).abs().max()) < 1e-3
-    assert rel_err(post["feat"], c["post"]["feat"]) < (POST_FEAT_TOL_TC if m.conv_backend == "tc" else REL_TOL)
+    e_same, excess, _ = post_feat_errors(post, c["post"])
+    assert e_same < REL_TOL and excess <= 0, (e_same, excess)
     assert post["seg"].dtype == torch.int64
     assert (post["seg"].cpu() == c["post"]["seg"]).float().mean() >= 0.999
     assert torch.equal(post["vlad"], out["vlad"])
@@ -74,7 +75,11 @@ def test_model_matches_oracle_at_size(letter, v3, ncls, B, H, W, backend):
     post = m.post_processing(dict(out), H, W)
     rpost = R.post_processing(dict(ref), H, W, a)
     assert float((post["coord"].cpu() - rpost["coord"]).abs().max()) < 1e-3
-    assert rel_err(post["feat"], rpost["feat"]) < (POST_FEAT_TOL_TC if m.conv_backend == "tc" else REL_TOL)
+    # sampled unit descriptors: 1e-4 where the decoded coordinate is bit-identical, and no more than the displacement
+    # can explain where the fp32 coordinate differs by an ulp or two (tests/util.py: post_feat_errors) -- one criterion
+    # for both conv backends
+    e_same, excess, frac_same = post_feat_errors(post, rpost)
+    assert e_same < REL_TOL and excess <= 0, (e_same, excess, frac_same)
     assert (post["seg"].cpu() == rpost["seg"]).float().mean() >= 0.999
     # keypoint sets (threshold + top-k), per frame: Jaccard >= 99.9 % (north_star), coordinates of the common
     # keypoints within 1e-3 px.  k = 1000 at 240x320-class frames, 4000 at KITTI size (the reference's own settings,

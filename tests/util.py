@@ -10,18 +10,39 @@ REL_TOL = 1e-4  # fp32 features / descriptors / VLAD: 1e-4 relative (north_star)
 
 
 def tol(key: str, v3: bool) -> float:
-    """Tolerance per forward output.  north_star gates features / descriptors / VLAD at 1e-4 relative and the
-    segmentation on its ARGMAX (>= 99.9 % identical).  V3 returns Softmax2d probabilities under 'seg'
-    (kp2dtiny.py:942-943): p(1-p) * d(logit) with |logit| ~ 20 amplifies the logit error, so that one tensor is
-    held to 2e-4 (measured worst case over 20 runs on the tensor-core backend: 9.2e-5)."""
-    return 2e-4 if (key == "seg" and v3) else REL_TOL
+    """Tolerance per forward output: 1e-4 relative for every tensor on every backend (north_star).  V3 returns Softmax2d
+    probabilities under 'seg' (kp2dtiny.py:942-943); they are held to the same 1e-4 (measured worst case of the default
+    tensor-core backend over the golden configs: 5e-5, profiles/r2_parity_margins_slice128.txt)."""
+    return REL_TOL
 
 
-# Sampled + L2-normalised descriptors (post_processing 'feat'): dividing by the descriptor norm amplifies the dense
-# map's error at low-norm pixels.  The tensor-core backend accumulates in TMEM with the tensor core's
-# round-toward-zero adder (a systematic ~2e-6 per layer vs the FFMA backend's round-to-nearest), which lands the
-# worst component at 1.0e-4 for 376x1241 frames; the exact-fp32 FFMA backend stays below 1e-4 and is tested so.
-POST_FEAT_TOL_TC = 2e-4
+# Sampled + L2-normalised descriptors (post_processing 'feat') are a function of the decoded keypoint coordinate, and
+# that coordinate is an fp32 number of up to ~1240 px: one ulp is 1.2e-4 px beyond x = 1024.  A shift difference of a few
+# 1e-6 (well inside every tolerance) can round the coordinate to the neighbouring fp32 value, the descriptor is then
+# sampled 6e-5 feature-map pixels away, and that alone moves its components by ~1e-4 -- on ANY backend (measured:
+# exact-fp32 FFMA backend 1.15e-4 / 1.27e-4, tensor-core backend 1.13e-4 / 1.23e-4 at 376x1241, every worst cell with a
+# coordinate difference of exactly one ulp; tools/kitti_margin.py).  So descriptors are compared where the coordinate
+# is bit-identical (1e-4, the north_star bound), and cells whose coordinate differs (by <= 1e-3 px, the north_star
+# coordinate tolerance) are bounded by what that displacement can do: 1e-4 + |d coord| in feature-map pixels x the largest
+# neighbour-to-neighbour step of the reference descriptor map.
+def post_feat_errors(post: dict, rpost: dict):
+    """-> (relative error over cells with bit-identical coordinates, worst excess over the displacement bound elsewhere,
+    fraction of cells with identical coordinates)."""
+    f, rf = post["feat"].detach().float().cpu(), rpost["feat"].detach().float().cpu()
+    c, rc = post["coord"].detach().float().cpu(), rpost["coord"].detach().float().cpu()
+    dc = (c - rc).abs().amax(dim=1)                    # (B, Hc, Wc) pixels
+    same = dc == 0
+    scale = rf.abs().max().clamp_min(1e-30)
+    err = (f - rf).abs().amax(dim=1) / scale           # (B, Hc, Wc)
+    e_same = float(err[same].max()) if bool(same.any()) else 0.0
+    # neighbour-to-neighbour variation of the reference's unit descriptors (cells are 4 px apart; the sampled map has
+    # half the image resolution): a conservative per-feature-pixel slope
+    gx = (rf[..., :, 1:] - rf[..., :, :-1]).abs().max() if rf.shape[-1] > 1 else rf.new_zeros(())
+    gy = (rf[..., 1:, :] - rf[..., :-1, :]).abs().max() if rf.shape[-2] > 1 else rf.new_zeros(())
+    slope = float(torch.maximum(gx, gy) / scale)
+    bound = 1e-4 + 0.5 * dc * slope
+    excess = float((err - bound)[~same].max()) if bool((~same).any()) else -1.0
+    return e_same, excess, float(same.float().mean())
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:

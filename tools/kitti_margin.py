@@ -6,7 +6,7 @@ import contextlib, io, os, sys, torch
 import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from util import rel_err
+from util import post_feat_errors, rel_err
 from nano_vs_slam_b200 import tiny_factory
 from nano_vs_slam_b200.synthetic import spread_init, synthetic_frames
 from oracle import kp2dtiny_ref as R
@@ -26,7 +26,9 @@ for backend in ("tc", "ffma"):
         post = m.post_processing(dict(out), H, W)
         e = {k: rel_err(out[k], ref[k]) for k in ("score", "coord", "feat", "vlad", "seg")}
         e["post_feat"] = rel_err(post["feat"], rpost["feat"])
-        print(backend, seed, {k: f"{v:.2e}" for k, v in e.items()})
+        print(backend, seed, {k: f"{v:.2e}" for k, v in e.items()},
+              "| cells with identical coord: err %.2e, excess over the displacement bound elsewhere %.2e, identical %.3f"
+              % post_feat_errors(post, rpost))
         # un-normalised sampled descriptors of the reference: grid_sample at the reference coordinates
         cn = rpost["coord"].clone()
         cn[:, 0] = cn[:, 0] / ((W - 1) / 2.0) - 1.0
