@@ -64,6 +64,17 @@ def _peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def _tf32_peak(bf16_peak: float):
+    """Dense TF32 tensor peak: measured on this pool with cuBLAS (tools/measure_tf32_peak.py ->
+    profiles/r2_tf32_peak.json, the sustained figure: kernels here are timed inside a long step), else bf16 / 2."""
+    path = os.path.join(REPO, "profiles", "r2_tf32_peak.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return d["tf32_tflops_sustained"], "measured cuBLAS tf32 sustained (profiles/r2_tf32_peak.json)"
+    return bf16_peak / 2.0, "bf16 sustained / 2 (tf32 not measured)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -301,7 +312,8 @@ def run_other_configs(dev, world, rank, hbm_peak, bf16_peak, which):
             flops += 4.0 * c5 * (n1 * (n1 // 4) + n2 * (n2 // 4))
         fps = world * b * sp["steps"] / (ms / 1e3)
         fps_gpu = fps / world
-        peak = bf16_peak / 6.0
+        tf32_peak, tf32_src = _tf32_peak(bf16_peak)
+        peak = tf32_peak / 3.0
         out.append({
             "config": sp["config"], "value": fps, "unit": "frames/s", "ms_per_step": ms / sp["steps"],
             "steps": sp["steps"], "warmup": 3, "batch_per_gpu": b,
@@ -311,7 +323,7 @@ def run_other_configs(dev, world, rank, hbm_peak, bf16_peak, which):
                            if sp.get("vo") else "") + f", batch {b} x {h}x{w} per GPU",
             "roofline": {"bound": "tensor", "achieved": fps_gpu * flops / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": fps_gpu * flops / 1e12 / peak, "traffic": None,
-                         "peak_source": which + " bf16 sustained / 2 (tf32) / 3 (3xTF32 split)",
+                         "peak_source": tf32_src + " / 3 (3xTF32 split)",
                          "note": "whole step: algorithmic conv" + (" + attention" if m.use_attention else "") +
                                  " FLOPs per frame x frames/s (the attention core and the first layer run on the fp32 "
                                  "pipe, so the tensor ceiling is an upper bound for them)",
@@ -548,17 +560,19 @@ def main():
         traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]  # ncu capture at batch 256, linear in batch
         traffic_batch = tr["batch"]
     if "tcgen05" in heavy_meta["shape"]:
-        # 3xTF32: every algorithmic FLOP costs three tf32 tensor-core FLOPs; tf32 runs at half the bf16 rate, so
-        # the ceiling for ALGORITHMIC FLOP/s is (measured bf16 dense peak) / 2 / 3.
-        peak_tf = bf16_peak / 2.0 / 3.0
+        # 3xTF32: every algorithmic FLOP costs three tf32 tensor-core FLOPs, so the ceiling for ALGORITHMIC FLOP/s
+        # is the (measured) dense tf32 peak / 3.
+        tf32_peak, tf32_src = _tf32_peak(bf16_peak)
+        peak_tf = tf32_peak / 3.0
         roofline = {
             "kernel": f"conv_tc_kernel {heavy_meta['shape']} (B={B})", "bound": "tensor",
             "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
             "traffic_note": (f"DRAM bytes/launch from ncu --set full at batch {traffic_batch} "
                              f"(profiles/r1_traffic.json) x B/{traffic_batch}; " if traffic is not None else "") +
                             f"algorithmic bytes/launch = {heavy_meta['bytes']:.0f}",
-            "peak_source": which + " bf16 sustained / 2 (tf32) / 3 (3xTF32 split)", "kernel_ms": kern_ms,
-            "mma_tflops_executed": 3.0 * ach_tf, "tf32_peak_tflops": bf16_peak / 2.0,
+            "peak_source": tf32_src + " / 3 (3xTF32 split)", "kernel_ms": kern_ms,
+            "mma_tflops_executed": 3.0 * ach_tf, "tf32_peak_tflops": tf32_peak,
+            "frac_of_bf16_sustained_over_6": ach_tf / (bf16_peak / 6.0),
             "hbm_gbs_at_algorithmic_bytes": ach_gbs, "hbm_frac_at_algorithmic_bytes": ach_gbs / hbm_peak,
             "note": "implicit-GEMM conv on tcgen05 (kind::tf32, A via TMEM, 3xTF32 for fp32-grade accuracy); "
                     "achieved = algorithmic conv FLOPs / kernel time",

@@ -85,18 +85,23 @@ struct Cfg {
   // NS is a multiple of MAX_ISSUERS: slot s is then always consumed by issuer s % issuers, which keeps every
   // parity wait at most one phase behind (with 3 issuers on 4 slots an issuer lapped a slow converter warp).
   static constexpr int NS_TMEM = (512 - ACC_COLS) / A_COLS;
-  static constexpr int NS_SMEM = (227 * 1024 - 4096 - 3 * HALO_BYTES) / W_STAGE;
+  static constexpr int NS_SMEM = (227 * 1024 - 8192 - 3 * HALO_BYTES) / W_STAGE;
   static constexpr int NS_FIT = NS_TMEM < NS_SMEM ? NS_TMEM : NS_SMEM;
   static constexpr int NS = NS_FIT >= 8 ? 8 : (NS_FIT >= 6 ? 6 : (NS_FIT >= 4 ? 4 : 2));
   static constexpr int NH = 3;                                             // halo boxes in flight
   static constexpr int KSTEPS = KC / 8;                                    // MMAs (K = 8 tf32) per operand pair
-  static constexpr int SM_W = NH * HALO_BYTES;
-  static constexpr int SM_BIAS = SM_W + NS * W_STAGE;
+  // shared memory: halo boxes | bias, pool exchange, mbarriers, TMEM slot | weight stages (last: their number is a
+  // launch parameter -- the NS-deep ring, or EVERY (chunk, tap) tile of the layer when the weights stay resident)
+  static constexpr int SM_BIAS = NH * HALO_BYTES;
   static constexpr int POOL_BYTES = ROW3 ? 2 * 2 * 15 * 16 * 4 : 0;        // ROW3 max-pool: rows of a pair live in two warps
   static constexpr int SM_POOL = SM_BIAS + COUT * 4;
   static constexpr int SM_BAR = SM_POOL + ((POOL_BYTES + 7) / 8) * 8;
-  static constexpr int N_BARS = 2 * NH + 2 * NS + 6;
-  static constexpr int SMEM_BYTES = SM_BAR + 8 * N_BARS + 16 + 1024;
+  static constexpr int N_BARS = 2 * NH + 2 * NS + 7;
+  static constexpr int SM_W = ((SM_BAR + 8 * N_BARS + 16 + 1023) / 1024) * 1024;
+  static constexpr int smem_bytes(int w_stages) { return SM_W + w_stages * W_STAGE + 1024; }
+  static constexpr int SMEM_BYTES = smem_bytes(NS);
+  // weight tiles that fit next to the halo boxes when they stay resident for the whole kernel
+  static constexpr int MAX_W_RESIDENT = (227 * 1024 - 1024 - SM_W) / W_STAGE;
   static_assert(NS <= NS_FIT && NS % CONV_GROUPS == 0, "TMEM budget / converter ring");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
   static_assert(W_BYTES % 1024 == 0 || (KC == 16 && W_BYTES % 512 == 0), "[W_hi;W_lo] must keep the swizzle phase");
@@ -118,6 +123,8 @@ struct Params {
   int tiles_x, tiles_y, n_tiles;
   int nk_last0, nk_last1;  // MMA k-steps (8 channels each) in the LAST chunk of source 0 / 1: skips all-padding k-steps
   int issuers;     // MMA-issuing threads; 1 gives a fixed fp32 accumulation order (bit-reproducible)
+  int w_res;       // 1: every (chunk, tap) weight tile of the layer is loaded once and stays in shared memory (the
+                   // slot ring then only carries the TMEM A slots); 0: weight tiles stream through the slot ring
   long long* dbg;  // optional timeline dump of CTA 0 (NVS_TC_DEBUG builds only)
   int knock;       // NVS_TC_DEBUG builds: stage knock-out bits for bottleneck experiments (results are then garbage)
 };
@@ -330,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto afull = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + i); };
   auto aempty = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + 2 + i); };
   auto astart = [&](int i) { return bar0 + 8u * (2 * NH + 2 * NS + 4 + i); };
+  const uint32_t wres = bar0 + 8u * (2 * NH + 2 * NS + 6);  // resident weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::SM_BAR + 8 * C::N_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -344,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(hempty(i), C::TAPS * 4);  // one elected lane per converter warp per tap releases the box
     }
     for (int i = 0; i < NS; ++i) {
-      mbar_init(sfull(i), 4 + 1);   // 4 converter warps (A slot written) + the weight producer's expect_tx arrive
+      mbar_init(sfull(i), p.w_res ? 4 : 4 + 1);   // 4 converter warps (A slot written) [+ the weight TMA's expect_tx arrive]
       mbar_init(sempty(i), 1);      // tcgen05.commit of the step that used the slot
     }
     for (int i = 0; i < 2; ++i) {
@@ -352,6 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(aempty(i), 4);
       mbar_init(astart(i), 1);  // the issuer of a tile's first step has queued the overwriting (accumulate=0) MMA
     }
+    mbar_init(wres, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -396,7 +405,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp == WARP_W) {
     // =========================== weight producer: one [W_hi;W_lo] tile per (chunk, tap) ===========================
-    if (lane == 0) {
+    if (lane == 0 && p.w_res) {
+      // resident weights: every (chunk, tap) tile once, one barrier for all of them
+      if (my_tiles > 0) {
+        mbar_expect_tx(wres, (uint32_t)(chunks * C::TAPS * C::W_STAGE));
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int tap = 0; tap < C::TAPS; ++tap) {
+            const uint32_t dst = base + C::SM_W + (ch * C::TAPS + tap) * C::W_STAGE;
+            tma_load_3d(dst, &map_whi, wres, ch * KC, 0, tap);
+            tma_load_3d(dst + C::W_BYTES, &map_wlo, wres, ch * KC, 0, tap);
+          }
+      }
+    } else if (lane == 0) {
       int sl = 0;
       uint32_t ph = 0;
       for (int t = 0; t < my_tiles; ++t) {
@@ -547,6 +567,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         ++tile;
       }
       int last_tile_synced = -1;
+      if (p.w_res) mbar_wait(wres, 0);
       for (int g = me; g < total; g += nis) {
         const int acc = tile % ACC_STAGES;
         const uint32_t aph = (uint32_t)(tile / ACC_STAGES) & 1u;
@@ -567,7 +588,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #endif
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS);
         const uint32_t a_hi = a0 + (uint32_t)(sl * C::A_COLS), a_lo = a_hi + KC;
-        const uint64_t w_hi = wdesc0 + (uint64_t)((sl * C::W_STAGE) >> 4), w_lo = w_hi + (uint64_t)(C::W_BYTES >> 4);
+        // weight tile: stage sl of the ring, or (resident) the tile of this step = (chunk, tap) = ks
+        const uint64_t w_hi = wdesc0 + (uint64_t)((((p.w_res ? ks : sl)) * C::W_STAGE) >> 4),
+                       w_lo = w_hi + (uint64_t)(C::W_BYTES >> 4);
         auto issue_kstep = [&](int k) {
           // A: 8 tf32 = 8 TMEM columns; B: 8 tf32 = 32 bytes along K = +2 in the descriptor's (addr >> 4)
           const uint64_t o = (uint64_t)(2 * k);
@@ -885,15 +908,21 @@ template <int COUT, int KC, bool PAIR = false, bool ROW3 = false>
 static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   using C = Cfg<COUT, KC, PAIR, ROW3>;
   auto kern = conv_tc_kernel<COUT, KC, PAIR, ROW3>;
-  NVS_OPT_IN_SMEM(kern, C::SMEM_BYTES);
+  NVS_OPT_IN_SMEM(kern, 227 * 1024);
   const int sms = nvs_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
+  // ROW3: a tile lasts ~1 us, far too short to hide a 24 KB weight TMA behind two slots, and the whole layer's weights
+  // (3 tiles per 32-channel chunk) usually fit next to the halo boxes: load them once per CTA
+  const int w_tiles = C::TAPS * (p.c0_chunks + p.c1_chunks);
+  static const bool allow_res = getenv("NVS_TC_WRES") == nullptr || atoi(getenv("NVS_TC_WRES")) != 0;
+  q.w_res = (ROW3 && allow_res && w_tiles <= C::MAX_W_RESIDENT) ? 1 : 0;
+  const int smem = C::smem_bytes(q.w_res ? w_tiles : C::NS);
   // a slot must always be consumed by the same issuer, and every issuer needs a step in every tile (all of them commit
   // the tile's accumulator): issuers | ring size, issuers <= steps per tile
   const int steps = C::TAPS * (p.c0_chunks + p.c1_chunks);
   while (q.issuers > 1 && (C::NS % q.issuers != 0 || q.issuers > steps)) --q.issuers;
-  kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
+  kern<<<grid, THREADS, smem, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
@@ -1001,6 +1030,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   }
   p.dbg = nullptr;
   p.knock = 0;
+  p.w_res = 0;  // decided per launch (tc::launch)
   pl->cout_tpl = cpad;
   pl->kc = kc;
   pl->pair = pair;

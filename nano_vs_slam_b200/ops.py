@@ -478,12 +478,14 @@ def _fold(weight, bias, bn, eps):
     return w.to(torch.float32), b.to(torch.float32)
 
 
-def row3_mode() -> int:
+def row3_mode() -> str:
     """Which variant of the row-stationary tensor-core conv serves layers with <= 32 output channels (env
-    NVS_TC_ROW3): 0 = none (nine single-tap pipeline steps), 32 = 32-channel chunks, 16 = 16-channel chunks."""
+    NVS_TC_ROW3): "0" = none (nine single-tap pipeline steps), "auto" (default, also "1") = 16-channel chunks for a
+    16-channel input (the stem's second conv), 32-channel chunks otherwise, "32" = 32-channel chunks only (16-channel
+    inputs keep the paired-tap kernel), "16" = 16-channel chunks everywhere."""
     import os
-    v = os.environ.get("NVS_TC_ROW3", "32")
-    return {"0": 0, "1": 32, "32": 32, "16": 16}.get(v, 32)
+    v = os.environ.get("NVS_TC_ROW3", "auto")
+    return {"0": "0", "1": "auto", "auto": "auto", "32": "32", "16": "16"}.get(v, "auto")
 
 
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
@@ -513,7 +515,7 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
     wt = torch.zeros(9, cpad, cin, dtype=torch.float32, device=w.device)
     wt[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
     if pair_taps is None:  # 16-channel inputs: paired taps unless the 16-channel row-stationary kernel takes the layer
-        pair_taps = row3_mode() != 16
+        pair_taps = row3_mode() in ("0", "32")
     if cin == 16 and cpad == 32 and pair_taps:
         # paired-tap layout for 16-channel inputs (NvsConvTcArgs.flags bit 1): K row of step t =
         # [tap 2t, channels 0-15 | tap 2t+1, channels 0-15]; the tenth tap is zero
@@ -601,15 +603,14 @@ class TcConv(object):
         a.pool_c_off = pool_c_off
         a.B, a.H, a.W, a.cout, a.act = B, H, W, cout, act
         # row-stationary kernel (conv_tc.cu Cfg: ROW3) for layers with <= 32 output channels: the packed [9][32][cin]
-        # weights ARE its [3 ky][3 kx x 32][cin] layout, so only the flag differs.  Mode 32: 32-channel chunks (two A
-        # slots in tensor memory); mode 16: 16-channel chunks (four slots, also serves 16-channel inputs).
+        # weights ARE its [3 ky][3 kx x 32][cin] layout, so only the flag differs (chunk width: see row3_mode).
         mode = row3_mode()
-        chunk = 16 if mode == 16 else 32
-        row3 = (mode != 0 and bp.numel() == 32 and not paired and a.c0 % chunk == 0 and a.c1 % chunk == 0
+        chunk = 16 if (mode == "16" or (mode == "auto" and a.c0 == 16 and a.c1 == 0)) else 32
+        row3 = (mode != "0" and bp.numel() == 32 and not paired and a.c0 % chunk == 0 and a.c1 % chunk == 0
                 and dst_mode != 2 and (dst_mode != 0 or dst_pool is not None))
         self.row3 = row3
         a.flags = ((1 if deterministic else 0) | (2 if paired else 0) | (4 if row3 else 0) |
-                   (8 if row3 and mode == 16 else 0))
+                   (8 if row3 and chunk == 16 else 0))
         segs = getattr(hi, "nvs_segments", None)
         a.c0_real = a.c1_real = 0
         if segs is not None and len(segs) == (2 if src1 is not None else 1) and not paired:

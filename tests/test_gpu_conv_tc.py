@@ -44,9 +44,13 @@ def test_conv_tc_plain_nhwc_and_nchw(cin, cout, H, W, act):
     assert rel_err(out2, ref) < 2e-5, rel_err(out2, ref)
 
 
-def test_conv_tc_16_channels_single_tap_steps():
-    """The SWIZZLE_64B single-tap variant (pack_conv_tc(pair_taps=False)) stays available and agrees."""
+def test_conv_tc_16_channels_single_tap_steps(monkeypatch):
+    """The nine-step kernels for 16-channel inputs stay available and agree: SWIZZLE_64B single-tap steps
+    (pack_conv_tc(pair_taps=False)) and paired taps (the default of round 1; the row-stationary kernel with 16-channel
+    chunks serves this layer now, NVS_TC_ROW3=auto)."""
     from nano_vs_slam_b200 import ops
+
+    monkeypatch.setenv("NVS_TC_ROW3", "32")  # 16-channel inputs stay on the nine-step kernels
 
     g = torch.Generator().manual_seed(16)
     B, H, W = 2, 30, 44

@@ -66,9 +66,10 @@ def test_retrieval_single_query_small_db_and_incremental_add():
     assert torch.equal(I.cpu(), Ir) and torch.equal(I.cpu(), planted.cpu())
     np.testing.assert_allclose(D.cpu().numpy(), Dr.numpy(), rtol=1e-4, atol=2e-6)
     with pytest.raises(NotImplementedError):
-        idx.search(q, 32)       # k above the fused top-k list length
-    D31, I31 = idx.search(q, 31)
-    assert torch.equal(I31.cpu(), glue_ref.flat_l2_search(db.cpu(), q.cpu(), 31)[1])
+        idx.search(q, 65)       # k above nvs_flat_max_k() (the per-row lists live in shared memory)
+    for kk in (31, 64):         # 64 == ntotal: every row is returned, in order
+        Dk, Ik = idx.search(q, kk)
+        assert torch.equal(Ik.cpu(), glue_ref.flat_l2_search(db.cpu(), q.cpu(), kk)[1])
 
 
 def test_model_smallest_and_ragged_frames():
