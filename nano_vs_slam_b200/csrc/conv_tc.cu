@@ -49,6 +49,8 @@ constexpr int ACC_STAGES = 2;      // accumulator stages in TMEM: the epilogue o
                                    // (1 stage frees columns for 6 slots instead of 4: measured no faster)
 constexpr int WARP_MMA = WARP_W + 1;      // first of MAX_ISSUERS MMA-issuing warps (they take pipeline steps round-robin)
 constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
+constexpr int WARP_EPI2 = WARP_MMA + MAX_ISSUERS;  // ROW3 only: four more epilogue warps (the second 16 channels)
+constexpr int THREADS_ROW3 = THREADS + 128;
 
 // PAIR: 16-channel inputs (the stem's second conv).  One pipeline step then carries TWO taps: the K = 32 operand
 // row is [tap 2t channels 0-15 | tap 2t+1 channels 0-15] (weights packed that way by the host, zero for the
@@ -108,6 +110,8 @@ struct Cfg {
   static constexpr uint32_t idesc_n(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   }
+  static constexpr int N_THREADS = ROW3 ? THREADS_ROW3 : THREADS;
+  static constexpr int EPI_WARPS = ROW3 ? 8 : 4;                           // arrivals that free an accumulator stage
   static constexpr uint32_t IDESC = idesc_n(NW);
   static constexpr uint32_t IDESC2 = idesc_n(2 * NW);
 };
@@ -318,7 +322,7 @@ __device__ __forceinline__ uint64_t make_wdesc(uint32_t smem_addr) {
 }
 
 template <int COUT, int KC, bool PAIR, bool ROW3>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__((Cfg<COUT, KC, PAIR, ROW3>::N_THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const Params p) {
@@ -342,7 +346,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < COUT; i += THREADS) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < COUT; i += C::N_THREADS) bias_s[i] = p.bias[i];
   if (warp == WARP_HALO && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
@@ -357,7 +361,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(afull(i), p.issuers);   // every MMA issuer commits its share of the tile
-      mbar_init(aempty(i), 4);
+      mbar_init(aempty(i), C::EPI_WARPS);
       mbar_init(astart(i), 1);  // the issuer of a tile's first step has queued the overwriting (accumulate=0) MMA
     }
     mbar_init(wres, 1);
@@ -377,7 +381,111 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int chunks = p.c0_chunks + p.c1_chunks;
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
-  if (warp == WARP_HALO) {
+  if (ROW3 && (warp < 4 || warp >= WARP_EPI2)) {
+    // =========================== epilogue, row-stationary variant ===========================
+    // Eight warps: TMEM lane quadrant (= image row of the tile) warp % 4, channel half h = 0 (warps 0-3) / 1 (warps
+    // 18-21): a tile's epilogue -- six TMEM loads, two shuffles per channel -- is what bounds this kernel, so it is
+    // split over twice the warps.  lane = position of the 32-wide strip (lane 0 / 31: halo positions).  Accumulator
+    // columns of a stage: [kx0 | kx1 | kx2] x 32 channels of a_hi w_hi, then the same three blocks of the correction
+    // products.  out[i] = D_0[i-1] + D_1[i] + D_2[i+1].
+    int acc = 0;
+    uint32_t aph = 0;
+    const int quad = warp & 3, h = warp >= WARP_EPI2 ? 1 : 0;
+    const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+      const int gx = tx * TX - 1 + lane, gy = ty * TY + quad;
+      const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
+      mbar_wait(afull(acc), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS) + ((uint32_t)(quad * 32) << 16);
+      if (!NVS_KNOCK(4) && !(p.dst_mode == 3 && h == 1)) {  // 16 output channels per warp (keypoint heads: 3 in all)
+        float o[16], u[16], w[16];
+        tmem_ld16x2(taddr + (uint32_t)(16 * h), taddr + (uint32_t)(C::NW + 16 * h), u, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = __shfl_up_sync(0xffffffffu, u[j] + w[j], 1);
+        tmem_ld16x2(taddr + (uint32_t)(COUT + 16 * h), taddr + (uint32_t)(C::NW + COUT + 16 * h), u, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] += u[j] + w[j];
+        tmem_ld16x2(taddr + (uint32_t)(2 * COUT + 16 * h), taddr + (uint32_t)(C::NW + 2 * COUT + 16 * h), u, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] += __shfl_down_sync(0xffffffffu, u[j] + w[j], 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = o[j] + bias_s[16 * h + j];
+          o[j] = fmaxf(a, 0.f) + neg_slope * fminf(a, 0.f);
+        }
+        if (p.act == NVS_ACT_SIGMOID && h == 0) {  // depth heads: cout <= 4
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = 1.f / (1.f + expf(-o[j]));
+        }
+        const int cbase = 16 * h;
+        if (p.dst_mode == 3) {  // keypoint heads: sigmoid -> score, tanh -> centre shift (see the other epilogue)
+          if (valid) {
+            const size_t plane = (size_t)p.H * p.W, pix = (size_t)gy * p.W + gx;
+            p.dst[(size_t)b * plane + pix] = 1.f / (1.f + expf(-o[0]));
+            p.dst_pool[((size_t)b * 2 + 0) * plane + pix] = tanhf(o[1]);
+            p.dst_pool[((size_t)b * 2 + 1) * plane + pix] = tanhf(o[2]);
+          }
+        } else {
+          if (p.dst_pool != nullptr) {
+            // MaxPool2d(2,2): x partner = next lane (strips start at even x, so pairs are lanes (1,2), (3,4), ...),
+            // y partner = the row of the next quadrant's warp: odd quadrants hand their x-pooled values to the even
+            // quadrant below them through shared memory (one buffer and one named barrier per (h, quadrant pair);
+            // the pair's second barrier keeps the next tile's write behind this tile's read)
+            float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + (h * 2 + (quad >> 1)) * (15 * 16);
+            const int bar_id = 2 + h * 2 + (quad >> 1);
+            float m[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m[j] = fmaxf(o[j], __shfl_down_sync(0xffffffffu, o[j], 1));
+            const int pc = (lane - 1) >> 1;  // pooled column inside the strip, odd lanes 1..29 -> 0..14
+            const bool owner = (lane & 1) && lane <= 29;
+            if ((quad & 1) && owner) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(ps + pc * 16)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const int qx = gx >> 1, qy = gy >> 1;
+            if (!(quad & 1) && owner && qx < (p.W >> 1) && qy < (p.H >> 1)) {
+              float4* d = reinterpret_cast<float4*>(
+                  p.dst_pool + (((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx) * p.pool_c_total + p.pool_c_off + cbase);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 r = reinterpret_cast<const float4*>(ps + pc * 16)[q];
+                if (cbase + 4 * q < p.cout)
+                  d[q] = make_float4(fmaxf(m[4 * q], r.x), fmaxf(m[4 * q + 1], r.y), fmaxf(m[4 * q + 2], r.z),
+                                     fmaxf(m[4 * q + 3], r.w));
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          }
+          if (valid && p.dst_mode == 1) {
+            if (p.dst_layout == 0) {  // NHWC
+              float4* d = reinterpret_cast<float4*>(
+                  p.dst + (((size_t)b * p.H + gy) * p.W + gx) * p.dst_c_total + p.dst_c_off + cbase);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (cbase + 4 * q < p.cout) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            } else {  // NCHW: a warp writes 30 consecutive x of one channel row
+              float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cbase) * p.H + gy) * p.W + gx;
+              const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cbase + j < p.cout) d[j * plane] = o[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(aempty(acc));
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        aph ^= 1;
+      }
+    }
+  } else if (warp == WARP_HALO) {
     // =========================== halo producer: one box per (tile, chunk) ===========================
     if (lane == 0) {
       int hb = 0;
@@ -644,106 +752,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp < 4 && ROW3) {
-    // =========================== epilogue, row-stationary variant ===========================
-    // warp = image row of the tile, lane = position of the 32-wide strip (lane 0 / 31: halo positions).  Accumulator
-    // columns of a stage: [kx0 | kx1 | kx2] x 32 channels of a_hi w_hi, then the same three blocks of the correction
-    // products.  out[i] = D_0[i-1] + D_1[i] + D_2[i+1].
-    int acc = 0;
-    uint32_t aph = 0;
-    const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-      const int gx = tx * TX - 1 + lane, gy = ty * TY + warp;
-      const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
-      mbar_wait(afull(acc), aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_STAGE_COLS) + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-      for (int h = 0; h < (NVS_KNOCK(4) ? 0 : COUT / 16); ++h) {  // 16 output channels at a time
-        float o[16], u[16], w[16];
-        __syncwarp();
-        tmem_ld16x2(taddr + (uint32_t)(16 * h), taddr + (uint32_t)(C::NW + 16 * h), u, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = __shfl_up_sync(0xffffffffu, u[j] + w[j], 1);
-        tmem_ld16x2(taddr + (uint32_t)(COUT + 16 * h), taddr + (uint32_t)(C::NW + COUT + 16 * h), u, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] += u[j] + w[j];
-        tmem_ld16x2(taddr + (uint32_t)(2 * COUT + 16 * h), taddr + (uint32_t)(C::NW + 2 * COUT + 16 * h), u, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] += __shfl_down_sync(0xffffffffu, u[j] + w[j], 1);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = o[j] + bias_s[16 * h + j];
-          o[j] = fmaxf(a, 0.f) + neg_slope * fminf(a, 0.f);
-        }
-        if (p.act == NVS_ACT_SIGMOID && h == 0) {  // depth heads: cout <= 4
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = 1.f / (1.f + expf(-o[j]));
-        }
-        const int cbase = 16 * h;
-        if (p.dst_mode == 3) {  // keypoint heads: sigmoid -> score, tanh -> centre shift (see the other epilogue)
-          if (valid && h == 0) {
-            const size_t plane = (size_t)p.H * p.W, pix = (size_t)gy * p.W + gx;
-            p.dst[(size_t)b * plane + pix] = 1.f / (1.f + expf(-o[0]));
-            p.dst_pool[((size_t)b * 2 + 0) * plane + pix] = tanhf(o[1]);
-            p.dst_pool[((size_t)b * 2 + 1) * plane + pix] = tanhf(o[2]);
-          }
-          continue;
-        }
-        if (p.dst_pool != nullptr) {
-          // MaxPool2d(2,2): x partner = next lane (strips start at even x, so pairs are lanes (1,2), (3,4), ...),
-          // y partner = the next warp's row: odd warps hand their x-pooled values to the even warp below them
-          // through shared memory (two buffers alternate with h, so the pair's next write never meets a pending read)
-          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + ((h & 1) * 2 + (warp >> 1)) * (15 * 16);
-          float m[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = fmaxf(o[j], __shfl_down_sync(0xffffffffu, o[j], 1));
-          const int pc = (lane - 1) >> 1;  // pooled column inside the strip, odd lanes 1..29 -> 0..14
-          const bool owner = (lane & 1) && lane <= 29;
-          if ((warp & 1) && owner) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<float4*>(ps + pc * 16)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-          }
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp >> 1)) : "memory");
-          const int qx = gx >> 1, qy = gy >> 1;
-          if (!(warp & 1) && owner && qx < (p.W >> 1) && qy < (p.H >> 1)) {
-            float4* d = reinterpret_cast<float4*>(
-                p.dst_pool + (((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx) * p.pool_c_total + p.pool_c_off + cbase);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 r = reinterpret_cast<const float4*>(ps + pc * 16)[q];
-              if (cbase + 4 * q < p.cout)
-                d[q] = make_float4(fmaxf(m[4 * q], r.x), fmaxf(m[4 * q + 1], r.y), fmaxf(m[4 * q + 2], r.z),
-                                   fmaxf(m[4 * q + 3], r.w));
-            }
-          }
-        }
-        if (valid && p.dst_mode == 1) {
-          if (p.dst_layout == 0) {  // NHWC
-            float4* d = reinterpret_cast<float4*>(
-                p.dst + (((size_t)b * p.H + gy) * p.W + gx) * p.dst_c_total + p.dst_c_off + cbase);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (cbase + 4 * q < p.cout) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          } else {  // NCHW: a warp writes 30 consecutive x of one channel row
-            float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cbase) * p.H + gy) * p.W + gx;
-            const size_t plane = (size_t)p.H * p.W;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (cbase + j < p.cout) d[j * plane] = o[j];
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(aempty(acc));
-      if (++acc == ACC_STAGES) {
-        acc = 0;
-        aph ^= 1;
-      }
-    }
   } else if (warp < 4) {
     // =========================== epilogue ===========================
     int acc = 0;
@@ -922,7 +930,7 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   // the tile's accumulator): issuers | ring size, issuers <= steps per tile
   const int steps = C::TAPS * (p.c0_chunks + p.c1_chunks);
   while (q.issuers > 1 && (C::NS % q.issuers != 0 || q.issuers > steps)) --q.issuers;
-  kern<<<grid, THREADS, smem, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
+  kern<<<grid, C::N_THREADS, smem, st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
