@@ -132,6 +132,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
   }
 }
 
+// attention_tc.cu: Q.K^T on the tensor cores (head_dim 12 / 16)
+int attention_tc_launch(const float* q, const float* kv, float* out, int B, int C, int heads, int Nq, int Nk,
+                        float scale_log2e, cudaStream_t st);
+
 }  // namespace nvs
 
 extern "C" int nvs_attention(const float* q, const float* kv, float* out, int32_t B, int32_t C, int32_t heads,
@@ -142,6 +146,14 @@ extern "C" int nvs_attention(const float* q, const float* kv, float* out, int32_
   const int d = C / heads;
   const float scale_log2e = (float)(1.0 / sqrt((double)d) * 1.4426950408889634);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // head_dim 12 / 16: logits on the tensor cores (attention_tc.cu); NVS_ATT_BACKEND=ffma keeps the all-FFMA kernels
+  // below for A/B measurements (they remain the path of head_dim 64)
+  static int tc_env = -1;
+  if (tc_env < 0) {
+    const char* e = getenv("NVS_ATT_BACKEND");
+    tc_env = (e && e[0] == 'f') ? 0 : 1;
+  }
+  if (tc_env && (d == 12 || d == 16)) return attention_tc_launch(q, kv, out, B, C, heads, Nq, Nk, scale_log2e, st);
   // queries per thread for head_dim 12 / 16: 4 halves the K/V shared-memory loads per FMA again (+7 % at 32 k
   // tokens, config 4) but leaves too few CTAs for the small maps (4800 tokens: -2 %)
   static int qpt_env = -1;
