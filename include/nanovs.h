@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NVS_ABI_VERSION 2
+#define NVS_ABI_VERSION 3
 
 #define NVS_OK 0
 #define NVS_ERR_ARG (-1)         /* bad shape / null pointer / unsupported size */
@@ -127,15 +127,23 @@ typedef struct NvsConvTcArgs {
                     bit 2: cout <= 32, c0 and c1 multiples of 32, dst_mode 1 or 3, no pooled output -- the
                     row-stationary kernel: a pipeline step is one kernel ROW, its three taps are one N = 3 x 32 MMA
                     operand ([9][32][cin] weights read as [3][96][cin]) and the epilogue sums the three shifted
-                    partial results; 3 pipeline steps per tile and chunk instead of 9 */
+                    partial results; 3 pipeline steps per tile and chunk instead of 9;
+                    bit 4: the "3xFP16" row-stationary kernel (csrc/conv_rs.cu), cout <= 64, c0 and c1 multiples of 32
+                    (or c0 == c0_total == 16, c1 == 0): w_hi / w_lo point to FP16 arrays [3 ky][3 kx x cout_pad][cin]
+                    (cout_pad = 32 or 64, cin = c0 + c1 with a 16-channel source padded to 32) holding the fp16 hi /
+                    lo parts of w * 2^t, and w_scale = 2^-t; any dst_mode / dst_layout / dst_pool combination */
   int32_t c0_real, c1_real; /* 0, or the number of leading channels of the c0 / c1 window that can be non-zero (the
                     rest is zero padding with zero weights, e.g. 24 real channels in a 32-channel row for the N
                     letters): MMA k-steps that would only multiply padding are skipped */
+  float w_scale; /* flags bit 4 only: factor applied to the accumulator before the bias (undoes the weights' 2^t) */
 } NvsConvTcArgs;
 int32_t nvs_conv_tc_cout_pad(int32_t cout);
 int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout);
 size_t nvs_conv_tc_plan_bytes(void);
 int nvs_conv_tc_plan_init(void* plan, const NvsConvTcArgs* args);
+/* flags bit 4 kernels only: 1 if an activation written since the last reset left the fp16 range (|x| >= 60000: the next
+ * layer's operands were then not finite; rerun with the 3xTF32 kernels), 0 if not, -1 on error.  Synchronises. */
+int nvs_conv_rs_range_flag(int32_t reset);
 /* dst_override / dst2_override (may be NULL) replace dst / dst_pool of the plan for this launch. */
 int nvs_conv_tc_run(const void* plan, float* dst_override, float* dst2_override, void* stream);
 

@@ -43,7 +43,7 @@ class NvsConvTcArgs(C.Structure):
         ("dst_c_total", _i32), ("dst_c_off", _i32), ("dst_layout", _i32), ("dst_mode", _i32),
         ("pool_c_total", _i32), ("pool_c_off", _i32),
         ("B", _i32), ("H", _i32), ("W", _i32), ("cout", _i32), ("act", _i32), ("flags", _i32),
-        ("c0_real", _i32), ("c1_real", _i32),
+        ("c0_real", _i32), ("c1_real", _i32), ("w_scale", C.c_float),
     ]
 
 
@@ -60,6 +60,7 @@ SIGNATURES = {
     "nvs_conv_tc_plan_bytes": (_sz, []),
     "nvs_conv_tc_plan_init": (_i32, [_vp, C.POINTER(NvsConvTcArgs)]),
     "nvs_conv_tc_run": (_i32, [_vp, _vp, _vp, _vp]),
+    "nvs_conv_rs_range_flag": (_i32, [_i32]),
     "nvs_conv_small": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nvs_dwconv3x3": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "nvs_channel_layernorm": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),

@@ -28,7 +28,7 @@ namespace nvs {
 namespace att {
 
 constexpr int KB = 64;                 // keys per block = N of one MMA
-constexpr int NST = 4;                 // K/V stages
+constexpr int NST_MAX = 4;             // K/V stages (4 with two CTAs per SM, 3 with three)
 constexpr int DK = 16;                 // contraction length (head_dim 12 is zero padded)
 constexpr int QT = 128;                // queries per tile (TMEM lanes)
 constexpr int QPB = 2 * QT;            // queries per CTA
@@ -37,10 +37,9 @@ constexpr int Q_BYTES = QT * DK * 4;   // one of q_hi / q_lo of one tile
 constexpr int K_BYTES = KB * DK * 4;   // one of k_hi / k_lo / v of one block
 constexpr int SM_Q = 0;                              // [tile][hi, lo]
 constexpr int SM_KV = SM_Q + 4 * Q_BYTES;            // [stage][k_hi, k_lo, v]
-constexpr int SM_BAR = SM_KV + NST * 3 * K_BYTES;
-constexpr int N_BARS = 2 * NST + 4 + 1;
-constexpr int SMEM_BYTES = SM_BAR + 8 * N_BARS + 16 + 1024;
-constexpr uint32_t TMEM_COLS = 256;    // 2 S stages x 2 tiles x 64 keys
+constexpr int N_BARS = 2 * NST_MAX + 4 + 1;
+constexpr int sm_bar(int nst) { return SM_KV + nst * 3 * K_BYTES; }
+constexpr int smem_bytes(int nst) { return sm_bar(nst) + 8 * N_BARS + 16 + 1024; }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -64,6 +63,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000LL) __trap();  // never hang the box on a protocol bug
+  }
+}
+// the same for the single-thread roles (K/V producer, MMA issuer), whose waits are long and have slack: back off
+// between polls so that the spin does not take issue slots from the softmax warp on the same scheduler (ncu: the
+// issuer's try_wait loop alone executed a quarter as many instructions as all FFMA2 of the kernel)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (++spins > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -93,29 +103,25 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t smem_addr) {
 }
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KB >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
 
-// two 16-column loads (the same 16 keys of the two query tiles), one wait
-__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, float* a, float* b) {
-  uint32_t r[16], q[16];
+// 16 logits of one query tile: tcgen05.ld is asynchronous -- the registers may only be read after tmem_ld_wait, which
+// takes them as read-write operands so that neither compiler moves a use above it
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr_a)
+      : "r"(taddr)
       : "memory");
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
-        "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-      : "r"(taddr_b)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    a[i] = __uint_as_float(r[i]);
-    b[i] = __uint_as_float(q[i]);
-  }
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* a, uint32_t* b) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -131,13 +137,22 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // byte offset of 16-byte chunk c of row r inside a K-major SWIZZLE_64B tile (64-byte rows)
 __device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
-template <int D>
-__global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* __restrict__ q,
+// CTAS = CTAs per SM the variant is sized for: 2 -> two S stages (256 TMEM columns), four K/V stages; 3 -> one S stage
+// (128 columns), three K/V stages, <= 113 registers: the MMAs of a block then wait for the softmax warps to drain the
+// previous one, which the two other CTAs cover (measured slower: 57.7 vs 67.3 TFLOP/s at 32k x 8k tokens).
+// PREFETCH: the TMEM loads of the next 16-key chunk are in flight while a chunk is processed (168 registers).
+template <int D, int CTAS, bool PREFETCH>
+__global__ void __launch_bounds__(THREADS, CTAS) attention_tc_kernel(const float* __restrict__ q,
                                                                   const float* __restrict__ kv,
                                                                   float* __restrict__ out, int C, int Nq, int Nk,
                                                                   float scale_log2e) {
   static_assert(D == 12 || D == 16, "head_dim 12 / 16");
+  static_assert(CTAS == 2 || CTAS == 3, "CTAs per SM");
   constexpr int H = D / 2;
+  constexpr int NST = CTAS == 2 ? 4 : 3;
+  constexpr int SS = CTAS == 2 ? 2 : 1;             // S stages
+  constexpr uint32_t TMEM_COLS = SS * 2 * KB;       // stages x 2 tiles x 64 keys
+  constexpr int SM_BAR = sm_bar(NST);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* _
       mbar_init(kv_full(i), 32);   // the producer warp's lanes
       mbar_init(kv_empty(i), 4);   // the softmax warps (their arrival also implies the block's MMAs have retired)
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < SS; ++i) {
       mbar_init(s_full(i), 1);     // tcgen05.commit
       mbar_init(s_empty(i), 4);
     }
@@ -213,22 +228,30 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* _
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
 
     for (int i = 0; i < n_blocks; ++i) {
-      const int st = i % NST, ss = i & 1;
+      const int st = i % NST, ss = i % SS;
       const int nvalid = min(KB, Nk - i * KB);
       const int n_chunks = (nvalid + 15) >> 4;
       mbar_wait(kv_full(st), (uint32_t)(i / NST) & 1u);  // V rows of this block (acquire of the producer's stores)
-      mbar_wait(s_full(ss), (uint32_t)(i >> 1) & 1u);    // logits of this block
+      mbar_wait(s_full(ss), (uint32_t)(i / SS) & 1u);    // logits of this block
       tc_fence_after();
       const float4* vrow = reinterpret_cast<const float4*>(sm + SM_KV + (st * 3 + 2) * K_BYTES);
       const uint32_t s_addr = lane_addr + (uint32_t)(ss * 2 * KB);
-#pragma unroll 1
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      // one chunk = 16 keys of both queries; the TMEM load of chunk ch + 1 is in flight while chunk ch is processed
+      auto issue = [&](uint32_t* ra, uint32_t* rb, int ch) {
+        tmem_ld16_issue(s_addr + (uint32_t)(ch * 16), ra);
+        tmem_ld16_issue(s_addr + (uint32_t)(KB + ch * 16), rb);
+      };
+      auto release_s = [&]() {  // every logit of this stage is in registers: the MMAs of block i + 2 may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(ss));
+      };
+      auto process = [&](const uint32_t* ra, const uint32_t* rb, int ch) {
         float s0[16], s1[16];
-        tmem_ld16x2(s_addr + (uint32_t)(ch * 16), s_addr + (uint32_t)(KB + ch * 16), s0, s1);
-        if (ch == n_chunks - 1) {  // every logit of this stage is in registers: the MMAs of block i + 2 may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty(ss));
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          s0[g] = __uint_as_float(ra[g]);
+          s1[g] = __uint_as_float(rb[g]);
         }
         const int left = nvalid - ch * 16;
         if (left < 16) {
@@ -278,6 +301,33 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* _
             o1[c] = __ffma2_rn(bq, vv[c], o1[c]);
           }
         }
+      };
+      if (PREFETCH) {
+        uint32_t a0[16], a1[16], b0[16], b1[16];
+        issue(a0, a1, 0);
+#pragma unroll 1
+        for (int ch = 0; ch < n_chunks; ch += 2) {
+          tmem_ld_wait(a0, a1);
+          const bool more1 = ch + 1 < n_chunks;
+          if (more1) issue(b0, b1, ch + 1);
+          else release_s();
+          process(a0, a1, ch);
+          if (more1) {
+            tmem_ld_wait(b0, b1);
+            if (ch + 2 < n_chunks) issue(a0, a1, ch + 2);
+            else release_s();
+            process(b0, b1, ch + 1);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          uint32_t a0[16], a1[16];
+          issue(a0, a1, ch);
+          tmem_ld_wait(a0, a1);
+          if (ch == n_chunks - 1) release_s();
+          process(a0, a1, ch);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(kv_empty(st));
@@ -313,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* _
         v0[c] = (c < D && ok0) ? vb[(size_t)c * Nk + j0] : 0.f;
         v1[c] = (c < D && ok1) ? vb[(size_t)c * Nk + j1] : 0.f;
       }
-      mbar_wait(kv_empty(st), ((uint32_t)(i / NST) & 1u) ^ 1u);
+      mbar_wait_relaxed(kv_empty(st), ((uint32_t)(i / NST) & 1u) ^ 1u);
       uint8_t* kh = sm + SM_KV + (st * 3) * K_BYTES;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -337,12 +387,12 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* _
     }
   } else if (lane == 0) {
     // =========================== MMA issuer ===========================
-    mbar_wait(q_full, 0);
+    mbar_wait_relaxed(q_full, 0);
     tc_fence_after();
     for (int i = 0; i < n_blocks; ++i) {
-      const int st = i % NST, ss = i & 1;
-      mbar_wait(kv_full(st), (uint32_t)(i / NST) & 1u);
-      mbar_wait(s_empty(ss), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      const int st = i % NST, ss = i % SS;
+      mbar_wait_relaxed(kv_full(st), (uint32_t)(i / NST) & 1u);
+      mbar_wait_relaxed(s_empty(ss), ((uint32_t)(i / SS) & 1u) ^ 1u);
       tc_fence_after();
       const uint64_t k_hi = make_desc64(base + SM_KV + (st * 3) * K_BYTES), k_lo = k_hi + (uint64_t)(K_BYTES >> 4);
 #pragma unroll
@@ -371,24 +421,38 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(const float* _
 
 }  // namespace att
 
+template <int D, int CTAS, bool PF>
+static int launch_tc(const float* q, const float* kv, float* out, int B, int C, int heads, int Nq, int Nk,
+                     float scale_log2e, cudaStream_t st) {
+  constexpr int smem = att::smem_bytes(CTAS == 2 ? 4 : 3);
+  auto kern = att::attention_tc_kernel<D, CTAS, PF>;
+  NVS_OPT_IN_SMEM(kern, smem);
+  dim3 grid((Nq + att::QPB - 1) / att::QPB, heads, B);
+  kern<<<grid, att::THREADS, smem, st>>>(q, kv, out, C, Nq, Nk, scale_log2e);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+
 // called by nvs_attention (attention.cu) for head_dim 12 / 16
 int attention_tc_launch(const float* q, const float* kv, float* out, int B, int C, int heads, int Nq, int Nk,
                         float scale_log2e, cudaStream_t st) {
   const int d = C / heads;
-  dim3 grid((Nq + att::QPB - 1) / att::QPB, heads, B);
-  if (d == 16) {
-    auto kern = att::attention_tc_kernel<16>;
-    NVS_OPT_IN_SMEM(kern, att::SMEM_BYTES);
-    kern<<<grid, att::THREADS, att::SMEM_BYTES, st>>>(q, kv, out, C, Nq, Nk, scale_log2e);
-  } else if (d == 12) {
-    auto kern = att::attention_tc_kernel<12>;
-    NVS_OPT_IN_SMEM(kern, att::SMEM_BYTES);
-    kern<<<grid, att::THREADS, att::SMEM_BYTES, st>>>(q, kv, out, C, Nq, Nk, scale_log2e);
-  } else {
-    return NVS_ERR_UNSUPPORTED;
+  // variant: NVS_ATT_CTAS = 2 (default) | 3 CTAs per SM, NVS_ATT_PREFETCH = 0 (default) | 1 (two CTAs only)
+  static int ctas = 0, pf = 0;
+  if (!ctas) {
+    const char* e = getenv("NVS_ATT_CTAS");
+    const char* f = getenv("NVS_ATT_PREFETCH");
+    pf = (f && atoi(f) == 1) ? 1 : 0;
+    ctas = (e && atoi(e) == 3) ? 3 : 2;
   }
-  NVS_CHECK_LAUNCH();
-  return NVS_OK;
+#define NVS_ATT_GO(D_) \
+  return ctas == 3 ? launch_tc<D_, 3, false>(q, kv, out, B, C, heads, Nq, Nk, scale_log2e, st) \
+       : (pf ? launch_tc<D_, 2, true>(q, kv, out, B, C, heads, Nq, Nk, scale_log2e, st) \
+             : launch_tc<D_, 2, false>(q, kv, out, B, C, heads, Nq, Nk, scale_log2e, st))
+  if (d == 16) { NVS_ATT_GO(16); }
+  if (d == 12) { NVS_ATT_GO(12); }
+#undef NVS_ATT_GO
+  return NVS_ERR_UNSUPPORTED;
 }
 
 }  // namespace nvs

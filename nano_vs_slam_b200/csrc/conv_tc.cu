@@ -949,6 +949,15 @@ static inline int pick_kc(int c0, int c1) {
 }  // namespace tc
 }  // namespace nvs
 
+namespace nvs {
+namespace rs {  // conv_rs.cu: the "3xFP16" row-stationary kernel (NvsConvTcArgs.flags bit 4)
+size_t plan_bytes();
+bool is_plan(const void* plan_mem);
+int plan_init(void* plan_mem, const NvsConvTcArgs* a);
+int run(const void* plan_mem, float* dst_override, float* dst2_override, cudaStream_t st);
+}  // namespace rs
+}  // namespace nvs
+
 using namespace nvs;
 
 extern "C" int32_t nvs_conv_tc_cout_pad(int32_t cout) {
@@ -965,10 +974,25 @@ extern "C" int32_t nvs_conv_tc_supported(int32_t c0, int32_t c1, int32_t cout) {
   return 1;
 }
 
-extern "C" size_t nvs_conv_tc_plan_bytes(void) { return sizeof(tc::Plan) + 64; }
+extern "C" size_t nvs_conv_tc_plan_bytes(void) {
+  const size_t a = sizeof(tc::Plan) + 64, b = rs::plan_bytes();
+  return a > b ? a : b;
+}
 
 extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   if (!plan_mem || !a || !a->src0 || !a->w_hi || !a->w_lo || !a->bias) return NVS_ERR_ARG;
+  if (a->flags & 16) {  // "3xFP16" row-stationary kernel
+    if (a->c1 > 0 && !a->src1) return NVS_ERR_ARG;
+    if (a->B <= 0 || a->H <= 0 || a->W <= 0) return NVS_ERR_ARG;
+    if ((a->c0_total % 4) || (a->c0_off % 4) || (a->c1 > 0 && ((a->c1_total % 4) || (a->c1_off % 4)))) return NVS_ERR_ARG;
+    if (a->dst_mode != 0 && ((a->dst_c_total % 4) || (a->dst_c_off % 4)) && a->dst_layout == 0) return NVS_ERR_ARG;
+    if (a->act != NVS_ACT_NONE && a->act != NVS_ACT_LRELU && a->act != NVS_ACT_RELU && a->act != NVS_ACT_SIGMOID)
+      return NVS_ERR_UNSUPPORTED;
+    if (a->dst_mode == 3 && (a->cout != 3 || a->act != NVS_ACT_NONE)) return NVS_ERR_ARG;
+    if (a->act == NVS_ACT_SIGMOID && a->cout > 4) return NVS_ERR_UNSUPPORTED;
+    if (a->dst_mode == 0 && a->dst_pool == nullptr) return NVS_ERR_ARG;
+    return rs::plan_init(plan_mem, a);
+  }
   if (!nvs_conv_tc_supported(a->c0, a->c1, a->cout)) return NVS_ERR_UNSUPPORTED;
   if (a->c1 > 0 && !a->src1) return NVS_ERR_ARG;
   if (a->B <= 0 || a->H <= 0 || a->W <= 0) return NVS_ERR_ARG;
@@ -1049,6 +1073,7 @@ extern "C" int nvs_conv_tc_plan_init(void* plan_mem, const NvsConvTcArgs* a) {
 
 extern "C" int nvs_conv_tc_run(const void* plan_mem, float* dst_override, float* dst2_override, void* stream) {
   if (!plan_mem) return NVS_ERR_ARG;
+  if (rs::is_plan(plan_mem)) return rs::run(plan_mem, dst_override, dst2_override, static_cast<cudaStream_t>(stream));
   const tc::Plan* pl = reinterpret_cast<const tc::Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
   if (pl->magic != tc::PLAN_MAGIC) return NVS_ERR_ARG;
   tc::Params p = pl->p;

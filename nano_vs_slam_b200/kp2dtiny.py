@@ -354,7 +354,9 @@ class _Plan:
             self.out_slots.setdefault(out_name, []).append(args)
 
     def buf_nhwc(self, name: str, c: int, h: int, w: int) -> torch.Tensor:
-        t = torch.empty(self.B, h, w, c, device=self.device, dtype=torch.float32)
+        # zero-initialised: padding channels no launch writes (N letters) are multiplied by zero weights, which only
+        # gives zero if they are finite -- and the fp16 operands of the 3xFP16 convs overflow above 65504
+        t = torch.zeros(self.B, h, w, c, device=self.device, dtype=torch.float32)
         self.bufs[name] = t
         return t
 

@@ -488,14 +488,82 @@ def row3_mode() -> str:
     return {"0": "0", "1": "auto", "auto": "auto", "32": "32", "16": "16"}.get(v, "auto")
 
 
+def conv_math() -> str:
+    """Arithmetic of the tensor-core 3x3 convs (env NVS_CONV_MATH): "f16" (default) = the row-stationary "3xFP16" kernel
+    of csrc/conv_rs.cu (fp16 hi / lo operand pairs, K = 16 per MMA, operands from shared memory); "tf32" = the 3xTF32
+    kernels of csrc/conv_tc.cu (TMEM-fed, 8-bit exponent: no restriction on the activation range)."""
+    import os
+    v = os.environ.get("NVS_CONV_MATH", "f16").lower()
+    return "tf32" if v in ("tf32", "3xtf32") else "f16"
+
+
+class RsPacked(object):
+    """Weights of one 3x3 conv for the "3xFP16" kernel: per slice of <= 64 output channels the fp16 hi / lo parts of
+    w * 2^t in the layout [3 ky][3 kx x cout_pad][cin] (cout_pad = 32 or 64), the fp32 bias [cout_pad] and 2^-t."""
+
+    def __init__(self, slices, cout: int, cin: int, segments):
+        self.slices = slices          # [(hi16, lo16, bias32, w_scale, cout_slice)]
+        self.cout, self.cin = cout, cin
+        self.nvs_segments = segments  # [(real, padded)] per source, or None
+
+
+def pack_conv_rs(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
+                 eps: float = 1e-5, cin_segments=None) -> RsPacked:
+    """OIHW 3x3 weight (+BN) -> RsPacked for nvs_conv_tc with flags bit 4 (csrc/conv_rs.cu).
+
+    The folded fp32 weights are scaled by 2^t (one exponent per layer, exact) so that the largest magnitude lands in
+    [2^13, 2^14): hi = fp16(w 2^t), lo = fp16(w 2^t - hi) -- both normal fp16 numbers for every weight down to
+    2^-27 of the largest; the kernel multiplies its accumulator by 2^-t.  Input-channel segments as in pack_conv_tc; a
+    16-channel input (the stem's output) is padded to one 32-channel chunk."""
+    w, b = _fold(weight, bias, bn, eps)
+    if cin_segments is not None:
+        assert sum(r for r, _ in cin_segments) == w.shape[1], (cin_segments, w.shape)
+        parts, at = [], 0
+        for real, padded in cin_segments:
+            seg = w[:, at:at + real]
+            if padded > real:
+                seg = torch.cat([seg, torch.zeros(w.shape[0], padded - real, 3, 3, dtype=w.dtype, device=w.device)], 1)
+            parts.append(seg)
+            at += real
+        w = torch.cat(parts, 1)
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    if cin == 16:
+        w = torch.cat([w, torch.zeros(cout, 16, 3, 3, dtype=w.dtype, device=w.device)], 1)
+        cin = 32
+    assert cin % 32 == 0, cin
+    amax = float(w.abs().max())
+    t = 0 if amax == 0.0 else int(torch.floor(torch.log2(torch.tensor(16383.0 / amax))).item())
+    t = max(-14, min(t, 40))
+    ws = w.double() * (2.0 ** t)
+    slices = []
+    for j in range(0, cout, 64):
+        cj = min(64, cout - j)
+        cpad = 32 if cj <= 32 else 64
+        wt = torch.zeros(3, 3, cpad, cin, dtype=torch.float64, device=w.device)     # [ky][kx][co][ci]
+        wt[:, :, :cj] = ws[j:j + cj].permute(2, 3, 0, 1)
+        wt = wt.reshape(3, 3 * cpad, cin)
+        hi = wt.to(torch.float16)
+        lo = (wt - hi.double()).to(torch.float16)
+        bp = torch.zeros(cpad, dtype=torch.float32, device=w.device)
+        bp[:cj] = b[j:j + cj]
+        slices.append((hi.contiguous(), lo.contiguous(), bp, float(2.0 ** -t), cj))
+    return RsPacked(slices, cout, cin, list(cin_segments) if cin_segments is not None else None)
+
+
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None,
-                 eps: float = 1e-5, cin_segments=None, pair_taps: Optional[bool] = None):
-    """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc.
+                 eps: float = 1e-5, cin_segments=None, pair_taps: Optional[bool] = None, math: Optional[str] = None):
+    """OIHW 3x3 weight (+BN) -> (w_hi, w_lo) [9][cout_pad][cin] and bias [cout_pad] for nvs_conv_tc -- or, with
+    ``math`` "f16" (the default, see conv_math), the RsPacked weights of the "3xFP16" kernel.
 
     w_hi = w rounded to tf32 (10 explicit mantissa bits), w_lo = tf32-rounded (w - w_hi).
     ``cin_segments``: [(real, padded), ...] -- the input channels arrive as consecutive segments of ``real``
     channels, each stored in a channels-last buffer padded with zeros to ``padded`` channels (the N letters have
     24/48/72/96 channels; the tensor-core kernel works on 32-channel rows).  Zero weight columns are inserted."""
+    if math is None:
+        math = conv_math()
+    if math == "f16" and pair_taps is None:
+        return pack_conv_rs(weight, bias=bias, bn=bn, eps=eps, cin_segments=cin_segments)
     w, b = _fold(weight, bias, bn, eps)
     if cin_segments is not None:
         assert sum(r for r, _ in cin_segments) == w.shape[1], (cin_segments, w.shape)
@@ -535,7 +603,7 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
 
 
 def pack_head_pair_tc(w_score: torch.Tensor, b_score: torch.Tensor, w_shift: Optional[torch.Tensor] = None,
-                      b_shift: Optional[torch.Tensor] = None, cpad: Optional[int] = None):
+                      b_shift: Optional[torch.Tensor] = None, cpad: Optional[int] = None, math: Optional[str] = None):
     """Keypoint-head output conv(s) as ONE tensor-core conv with 3 output channels.
 
     V2: score_head.convDb (1, C, 3, 3) reads the score trunk and loc_head.convDb (2, C, 3, 3) reads the location
@@ -544,12 +612,12 @@ def pack_head_pair_tc(w_score: torch.Tensor, b_score: torch.Tensor, w_shift: Opt
     c = w_score.shape[1]
     cpad = c if cpad is None else cpad
     if w_shift is None:
-        return pack_conv_tc(w_score, bias=b_score, cin_segments=[(c, cpad)])
+        return pack_conv_tc(w_score, bias=b_score, cin_segments=[(c, cpad)], math=math)
     w = torch.zeros(3, 2 * c, 3, 3, dtype=torch.float32, device=w_score.device)
     w[0:1, :c] = w_score.detach().float()
     w[1:3, c:] = w_shift.detach().float()
     return pack_conv_tc(w, bias=torch.cat([b_score.detach().float(), b_shift.detach().float()]),
-                        cin_segments=[(c, cpad), (c, cpad)])
+                        cin_segments=[(c, cpad), (c, cpad)], math=math)
 
 
 def pack_conv_small(weight: torch.Tensor, bias: torch.Tensor):
@@ -569,7 +637,7 @@ class TcConv(object):
                  c1: Optional[int] = None, dst: Optional[torch.Tensor] = None, dst_layout: int = 0,
                  dst_mode: int = 1, dst_c_off: int = 0, dst_c_total: Optional[int] = None,
                  dst_pool: Optional[torch.Tensor] = None, pool_c_off: int = 0,
-                 deterministic: Optional[bool] = None):
+                 deterministic: Optional[bool] = None, rs_scale: Optional[float] = None, rs_segments=None):
         """``deterministic``: one MMA-issuing thread instead of two -> fixed fp32 accumulation order, results
         bit-reproducible run to run (default: env NVS_DETERMINISTIC=1, else the faster multi-issuer schedule whose
         last-ulp rounding depends on timing)."""
@@ -588,9 +656,14 @@ class TcConv(object):
             a.c1 = src1.shape[3] - c1_off if c1 is None else c1
         else:
             a.src1, a.c1_total, a.c1_off, a.c1 = None, 0, 0, 0
-        paired = hi.shape[0] == 5  # pack_conv_tc's paired-tap layout for 16-channel inputs
-        assert (hi.shape[2] == 32 and a.c0 == 16 and a.c1 == 0) if paired else hi.shape[2] == a.c0 + a.c1, \
-            (hi.shape, a.c0, a.c1)
+        rs = rs_scale is not None  # one slice of an RsPacked: the "3xFP16" row-stationary kernel (flags bit 4)
+        paired = (not rs) and hi.shape[0] == 5  # pack_conv_tc's paired-tap layout for 16-channel inputs
+        if rs:
+            assert hi.dtype == torch.float16 and hi.shape[0] == 3 and hi.shape[1] == 3 * bp.numel(), hi.shape
+            assert hi.shape[2] == (32 if (a.c0 == 16 and a.c1 == 0) else a.c0 + a.c1), (hi.shape, a.c0, a.c1)
+        else:
+            assert (hi.shape[2] == 32 and a.c0 == 16 and a.c1 == 0) if paired else hi.shape[2] == a.c0 + a.c1, \
+                (hi.shape, a.c0, a.c1)
         a.dst = _ptr(dst)
         a.dst_pool = _ptr(dst_pool)
         if dst_c_total is None:
@@ -607,11 +680,12 @@ class TcConv(object):
         mode = row3_mode()
         chunk = 16 if (mode == "16" or (mode == "auto" and a.c0 == 16 and a.c1 == 0)) else 32
         row3 = (mode != "0" and bp.numel() == 32 and not paired and a.c0 % chunk == 0 and a.c1 % chunk == 0
-                and dst_mode != 2 and (dst_mode != 0 or dst_pool is not None))
+                and dst_mode != 2 and (dst_mode != 0 or dst_pool is not None) and not rs)
         self.row3 = row3
         a.flags = ((1 if deterministic else 0) | (2 if paired else 0) | (4 if row3 else 0) |
-                   (8 if row3 and chunk == 16 else 0))
-        segs = getattr(hi, "nvs_segments", None)
+                   (8 if row3 and chunk == 16 else 0) | (16 if rs else 0))
+        a.w_scale = float(rs_scale) if rs else 1.0
+        segs = rs_segments if rs else getattr(hi, "nvs_segments", None)
         a.c0_real = a.c1_real = 0
         if segs is not None and len(segs) == (2 if src1 is not None else 1) and not paired:
             if segs[0][1] == a.c0 and (src1 is None or segs[1][1] == a.c1):
@@ -632,7 +706,9 @@ class TcConv(object):
         self._mem = C.create_string_buffer(int(lib().nvs_conv_tc_plan_bytes()))
         check(lib().nvs_conv_tc_plan_init(self._mem, C.byref(a)), "nvs_conv_tc_plan_init")
         self.flops = 2.0 * 9 * (a.c0 + a.c1) * cout * H * W * B
-        self.shape = f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05" + (f" row3/{chunk}" if row3 else "")
+        self.cout_ = cout
+        self.shape = (f"{a.c0 + a.c1}->{cout} k3 @{H}x{W} tcgen05" + (f" row3/{chunk}" if row3 else "") +
+                      (" rs/f16" if rs else ""))
 
     def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
         check(lib().nvs_conv_tc_run(self._mem, _ptr(dst_override), _ptr(dst2_override), _stream()),
@@ -675,8 +751,68 @@ class TcConvSplit(object):
             o.run(dst_override, dst2_override)
 
 
+def conv_rs_range_flag(reset: bool = False) -> int:
+    """1 if a "3xFP16" conv on the current device wrote an activation beyond the fp16 range since the last reset (the
+    following layer's operands were then not finite: switch that model to NVS_CONV_MATH=tf32).  Synchronises."""
+    v = int(lib().nvs_conv_rs_range_flag(1 if reset else 0))
+    if v < 0:
+        raise NanovsError("nvs_conv_rs_range_flag failed")
+    return v
+
+
+class RsConv(object):
+    """A 3x3 conv on the "3xFP16" row-stationary kernel: one launch per <= 64-channel slice of an RsPacked, each writing
+    its channel range of the shared outputs (same contract as TcConv / TcConvSplit)."""
+
+    def __init__(self, src0: torch.Tensor, packed: RsPacked, cout: int, **kw):
+        mode = kw.get("dst_mode", 1)
+        n = len(packed.slices)
+        assert mode != 3 or n == 1, "the keypoint-head split epilogue has 3 output channels"
+        if n > 1 and kw.get("dst") is None and kw.get("dst_c_total") is None and mode != 0:
+            kw["dst_c_total"] = cout // 4 if mode == 2 else cout
+        kw.pop("deterministic", None)  # single MMA issuer: always bit-reproducible
+        self.ops = []
+        covered = 0
+        for j, (hi, lo, bp, scale, _real) in enumerate(packed.slices):
+            # ``cout`` may count zero-weight padding channels (N letters: 24 real channels in a 32-channel buffer)
+            cj = min(bp.numel(), cout - 64 * j)
+            if cj <= 0:
+                break
+            kj = dict(kw)
+            kj["dst_c_off"] = kw.get("dst_c_off", 0) + (16 if mode == 2 else 64) * j
+            if kw.get("dst_pool") is not None and mode != 3:
+                kj["pool_c_off"] = kw.get("pool_c_off", 0) + 64 * j
+            self.ops.append(TcConv(src0, (hi, lo, bp), cj, rs_scale=scale, rs_segments=packed.nvs_segments, **kj))
+            covered = 64 * j + cj
+        if covered < cout:
+            # the caller's (padded) channel count exceeds the packed slices (N letters: 4 x 24 real channels requested
+            # as 4 x 32): the remaining channels are zero weights + zero bias = exact zeros, written once here into the
+            # persistent plan buffers instead of by a launch
+            assert mode in (1, 2) or kw.get("dst_pool") is not None
+            dst, pool = kw.get("dst"), kw.get("dst_pool")
+            assert (dst is not None or mode == 0) and kw.get("dst_layout", 0) == 0, "padding channels need a plan buffer"
+            if dst is not None:
+                off = kw.get("dst_c_off", 0)
+                if mode == 2:
+                    dst[..., off + covered // 4: off + cout // 4].zero_()
+                else:
+                    dst[..., off + covered: off + cout].zero_()
+            if pool is not None:
+                off = kw.get("pool_c_off", 0)
+                pool[..., off + covered: off + cout].zero_()
+        self.flops = sum(o.flops for o in self.ops)
+        self.shape = self.ops[0].shape.replace(f"->{self.ops[0].cout_} ", f"->{cout} ") + (f" x{len(self.ops)}" if n > 1 else "")
+
+    def run(self, dst_override: Optional[torch.Tensor] = None, dst2_override: Optional[torch.Tensor] = None) -> None:
+        for o in self.ops:
+            o.run(dst_override, dst2_override)
+
+
 def tc_conv(src0: torch.Tensor, packed, cout: int, slice_width: int = 128, **kw):
-    """TcConv, or TcConvSplit when the packed weights carry more than ``slice_width`` (padded) output channels."""
+    """TcConv, or TcConvSplit when the packed weights carry more than ``slice_width`` (padded) output channels; RsConv
+    for RsPacked weights (NVS_CONV_MATH=f16, the default)."""
+    if isinstance(packed, RsPacked):
+        return RsConv(src0, packed, cout, **kw)
     if packed[2].numel() > slice_width and packed[0].shape[0] == 9 and kw.get("dst_mode", 1) != 3:
         return TcConvSplit(src0, packed, cout, slice_width=slice_width, **kw)
     return TcConv(src0, packed, cout, **kw)

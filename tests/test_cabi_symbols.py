@@ -33,7 +33,7 @@ def test_pure_host_entry_points():
     from nano_vs_slam_b200 import _cabi
 
     lib = _cabi.lib()
-    assert lib.nvs_abi_version() == 2
+    assert lib.nvs_abi_version() == 3
     assert [lib.nvs_conv_cout_tile(c) for c in (1, 3, 16, 19, 28, 32, 48, 64, 96, 128)] == \
         [8, 8, 16, 24, 32, 32, 48, 64, 48, 64]
     assert lib.nvs_conv_cin_chunk(3) == 4 and lib.nvs_conv_cin_chunk(96) == 8

@@ -29,7 +29,7 @@ def test_conv_tc_plain_nhwc_and_nchw(cin, cout, H, W, act):
     b = torch.randn(cout, generator=g) * 0.1
     ref = F.conv2d(x, w, b, padding=1)
     ref = F.leaky_relu(ref, 0.01) if act == 1 else (F.relu(ref) if act == 2 else ref)
-    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), math="tf32")
     xs = _nhwc(x).cuda()
     cpad = packed[2].numel()
     if cout % 4 == 0:
@@ -59,7 +59,7 @@ def test_conv_tc_16_channels_single_tap_steps(monkeypatch):
     b = torch.randn(32, generator=g) * 0.1
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
     for pair in (False, True):
-        packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), pair_taps=pair)
+        packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), pair_taps=pair, math="tf32")
         assert packed[0].shape[0] == (5 if pair else 9)
         out = torch.zeros(B, H, W, 32, device="cuda")
         ops.TcConv(_nhwc(x).cuda(), packed, 32, act=1, dst=out).run()
@@ -75,7 +75,7 @@ def test_conv_tc_pool_shuffle_concat_slice():
     w = torch.randn(64, 32, 3, 3, generator=g) * 0.08
     b = torch.randn(64, generator=g) * 0.1
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
-    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), math="tf32")
     full = torch.zeros(B, H, W, 64, device="cuda")
     pooled = torch.zeros(B, H // 2, W // 2, 64, device="cuda")
     ops.TcConv(_nhwc(x).cuda(), packed, 64, act=1, dst=full, dst_pool=pooled).run()
@@ -95,7 +95,7 @@ def test_conv_tc_pool_shuffle_concat_slice():
         w2 = torch.randn(128, 64, 3, 3, generator=g) * 0.05
         b2 = torch.randn(128, generator=g) * 0.1
         out = torch.zeros(B, 2 * hh, 2 * ww, 32, device="cuda")
-        ops.TcConv(_nhwc(xs).cuda(), ops.pack_conv_tc(w2.cuda(), bias=b2.cuda()), 128, dst=out, dst_mode=2).run()
+        ops.TcConv(_nhwc(xs).cuda(), ops.pack_conv_tc(w2.cuda(), bias=b2.cuda(), math="tf32"), 128, dst=out, dst_mode=2).run()
         assert rel_err(out.permute(0, 3, 1, 2), F.pixel_shuffle(F.conv2d(xs, w2, b2, padding=1), 2)) < 2e-5
     # two sources (concat) + channel slice + BN fold
     a = torch.randn(B, 32, H, W, generator=g)
@@ -107,13 +107,13 @@ def test_conv_tc_pool_shuffle_concat_slice():
         ref = F.leaky_relu(bn(conv(torch.cat([a, s], 1))), 0.01)
     bnd = {k: getattr(bn, k).cuda() for k in ("weight", "bias", "running_mean", "running_var")}
     out = torch.zeros(B, H, W, 64, device="cuda")
-    ops.TcConv(_nhwc(a).cuda(), ops.pack_conv_tc(conv.weight.detach().cuda(), bn=bnd), 64, act=1, src1=_nhwc(s).cuda(),
+    ops.TcConv(_nhwc(a).cuda(), ops.pack_conv_tc(conv.weight.detach().cuda(), bn=bnd, math="tf32"), 64, act=1, src1=_nhwc(s).cuda(),
                dst=out).run()
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5
     w3 = torch.randn(32, 32, 3, 3, generator=g) * 0.08
     b3 = torch.randn(32, generator=g) * 0.1
     out = torch.zeros(B, 32, H, W, device="cuda")
-    ops.TcConv(_nhwc(s).cuda(), ops.pack_conv_tc(w3.cuda(), bias=b3.cuda()), 32, c0_off=32, c0=32, dst=out,
+    ops.TcConv(_nhwc(s).cuda(), ops.pack_conv_tc(w3.cuda(), bias=b3.cuda(), math="tf32"), 32, c0_off=32, c0=32, dst=out,
                dst_layout=1).run()
     assert rel_err(out, F.conv2d(s[:, 32:], w3, b3, padding=1)) < 2e-5
 
@@ -173,7 +173,7 @@ def test_conv_tc_more_than_128_output_channels():
     w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
-    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), math="tf32")
     assert packed[2].numel() == 256
     xs = _nhwc(x).cuda()
     full = torch.zeros(B, H, W, cout, device="cuda")
@@ -209,7 +209,7 @@ def test_conv_tc_row_stationary_variant(c0, c1, cout, H, W, layout, monkeypatch)
     w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
-    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), math="tf32")
     s0 = _nhwc(x[:, :c0]).cuda()
     s1 = _nhwc(x[:, c0:]).cuda() if c1 else None
     outs = {}
@@ -240,7 +240,7 @@ def test_conv_tc_row_stationary_max_pool(cin, H, W, mode, monkeypatch):
     w = torch.randn(32, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
     b = torch.randn(32, generator=g) * 0.1
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
-    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    packed = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), math="tf32")
     assert packed[0].shape[0] == 9  # not the paired-tap layout
     xs = _nhwc(x).cuda()
     only = torch.zeros(B, H // 2, W // 2, 32, device="cuda")
@@ -267,7 +267,7 @@ def test_conv_tc_row_stationary_keypoint_heads(mode, monkeypatch):
     sh, lh = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
     ws, bs = torch.randn(1, C, 3, 3, generator=g) * 0.05, torch.randn(1, generator=g) * 0.1
     wl, bl = torch.randn(2, C, 3, 3, generator=g) * 0.05, torch.randn(2, generator=g) * 0.1
-    packed = ops.pack_head_pair_tc(ws.cuda(), bs.cuda(), wl.cuda(), bl.cuda())
+    packed = ops.pack_head_pair_tc(ws.cuda(), bs.cuda(), wl.cuda(), bl.cuda(), math="tf32")
     score = torch.zeros(B, 1, H, W, device="cuda")
     shift = torch.zeros(B, 2, H, W, device="cuda")
     op = ops.TcConv(_nhwc(sh).cuda(), packed, 3, src1=_nhwc(lh).cuda(), dst=score, dst_mode=3, dst_layout=1, dst_pool=shift)

@@ -130,7 +130,7 @@ def test_conv_tc_op_matches_fp32_conv(cin, cout, pool):
     x = torch.randn(2, cin, 24, 40, generator=g)
     w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
-    hi, lo, bp = ops.pack_conv_tc(w.cuda(), bias=b.cuda())
+    hi, lo, bp = ops.pack_conv_tc(w.cuda(), bias=b.cuda(), math="tf32")
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     dst, pooled = torch.ops.nanovs.conv_tc(x_nhwc, None, hi, lo, bp, cout, ops.ACT_LRELU, 1, 1, pool)
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)

@@ -42,7 +42,7 @@ for cin, cout, H, W, B in cases:
     w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
     b = torch.zeros(cout, device="cuda")
     out = torch.zeros(B, H, W, cout, device="cuda")
-    op = ops.TcConv(x, ops.pack_conv_tc(w, bias=b), cout, act=1, dst=out)
+    op = ops.TcConv(x, ops.pack_conv_tc(w, bias=b, math="tf32"), cout, act=1, dst=out)
     steps = 9 * ((cin + 31) // 32) if cin >= 32 else 9
     tiles = B * ((H + 7) // 8) * ((W + 15) // 16)
     print(f"== {cin}->{cout} @{H}x{W} B={B}: {tiles} tiles, {steps} steps/tile")

@@ -16,7 +16,7 @@ x = torch.randn(B, H, W, cin, device="cuda")
 w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
 b = torch.zeros(cout, device="cuda")
 out = torch.zeros(B, H, W, cout, device="cuda")
-op = ops.TcConv(x, ops.pack_conv_tc(w, bias=b), cout, act=1, dst=out)
+op = ops.TcConv(x, ops.pack_conv_tc(w, bias=b, math="tf32"), cout, act=1, dst=out)
 for _ in range(3):
     dbg.zero_(); op.run()
 torch.cuda.synchronize()
