@@ -144,6 +144,9 @@ int nvs_conv_tc_plan_init(void* plan, const NvsConvTcArgs* args);
 /* flags bit 4 kernels only: 1 if an activation written since the last reset left the fp16 range (|x| >= 60000: the next
  * layer's operands were then not finite; rerun with the 3xTF32 kernels), 0 if not, -1 on error.  Synchronises. */
 int nvs_conv_rs_range_flag(int32_t reset);
+/* debugging aid: CTA 0 of every following flags-bit-4 launch writes 3 x 256 clock64 stamps (epilogue tiles, converter
+ * rows, MMA chunks) into dev_buf (768 int64, device memory); NULL switches it off */
+void nvs_conv_rs_debug_buffer(long long* dev_buf);
 /* dst_override / dst2_override (may be NULL) replace dst / dst_pool of the plan for this launch. */
 int nvs_conv_tc_run(const void* plan, float* dst_override, float* dst2_override, void* stream);
 

@@ -27,8 +27,8 @@
 //   * weights stay resident in shared memory for the whole kernel when the layer's 3 x chunks tiles fit (up to
 //     64 input channels at Cout = 64), else they stream through a ring.
 //
-// Warps: 0-7 epilogue (quadrant = warp % 4, channel half = warp / 4), 8-10 converters (box rows round-robin),
-// 11 activation TMA, 12 weight TMA, 13 MMA issuer (allocates TMEM).  Persistent CTAs, one per SM.
+// Warps: 0-7 epilogue (quadrant = warp % 4, channel half = warp / 4), 8-10 converters (box rows round-robin; each also
+// issues the TMA loads of its rows), 11 MMA issuer (allocates TMEM), 12 weight TMA.  Persistent CTAs, one per SM.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -51,7 +51,10 @@ constexpr int ROW_BYTES = HX * KC * 4;   // one fp32 box row: 32 positions x 128
 constexpr int NB = NVS_RS_NB;            // box rows in flight
 constexpr int A_HALF = HX * HY * KC * 2; // one of the hi / lo operand matrices: 192 rows x 64 B
 constexpr int A_BYTES = 2 * A_HALF;
-constexpr int NA = 2;                    // converted chunks in flight
+#ifndef NVS_RS_NA
+#define NVS_RS_NA 2
+#endif
+constexpr int NA = NVS_RS_NA;            // converted chunks in flight
 constexpr int ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;
 // NB is a multiple of CONV_WARPS: a ring slot is then always read by the same converter warp, so a warp can never wait
@@ -59,8 +62,9 @@ constexpr int EPI_WARPS = 8;
 // "already complete": with 4 warps on 6 slots a fast warp read a row that had not landed yet)
 constexpr int WARP_CONV = EPI_WARPS, CONV_WARPS = NVS_RS_CONV_WARPS;
 static_assert(NB % CONV_WARPS == 0 && HY >= CONV_WARPS, "row ring / converter warps");
-constexpr int WARP_TMA_A = WARP_CONV + CONV_WARPS, WARP_TMA_W = WARP_TMA_A + 1, WARP_MMA = WARP_TMA_W + 1;
-constexpr int THREADS = 32 * (WARP_MMA + 1);
+constexpr int WARP_MMA = WARP_CONV + CONV_WARPS, WARP_TMA_W = WARP_MMA + 1;
+constexpr int THREADS = 32 * (WARP_TMA_W + 1);
+constexpr int ROWS_AHEAD = NB / CONV_WARPS;  // row loads a converter warp keeps in flight (its slots of the ring)
 constexpr unsigned long long PLAN_MAGIC = 0x7273506C616E0001ull;  // first word of an rs::Plan
 
 template <int CO>
@@ -102,6 +106,9 @@ struct Params {
   int nk_last0, nk_last1;  // k-steps (16 channels) of the last chunk of source 0 / 1 that can be non-zero
   int w_stages;            // weight ring depth; >= 3 * chunks means resident (every tile loaded once)
   float w_scale;           // 2^-t: undoes the weights' power-of-two scale
+  long long* dbg;          // env NVS_RS_DBG=1: per-role clock64 stamps of CTA 0 (nvs_conv_rs_debug_buffer), 256 per role
+  int knock;               // bottleneck experiments (env NVS_RS_KNOCK, results are then garbage): 1 converters only
+                           // pass barriers, 2 epilogue only passes barriers, 4 no MMAs, 8 no activation TMA
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -137,8 +144,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   if (mbar_try_wait(bar, parity)) return;
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifndef NVS_RS_NO_SLEEP
     __nanosleep(64);
-    if (++spins > (1u << 26)) __trap();
+#endif
+    if (++spins > (1u << 28)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -231,7 +240,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   float* bias_s = reinterpret_cast<float*>(sm + C::SM_BIAS);
   const uint32_t bar0 = base + C::SM_BAR;
   auto rfull = [&](int i) { return bar0 + 8u * i; };
-  auto rempty = [&](int i) { return bar0 + 8u * (NB + i); };
   auto afull = [&](int i) { return bar0 + 8u * (2 * NB + i); };
   auto aempty = [&](int i) { return bar0 + 8u * (2 * NB + NA + i); };
   auto wfull = [&](int i) { return bar0 + 8u * (2 * NB + 2 * NA + i); };
@@ -253,10 +261,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
     for (int i = 0; i < NB; ++i) {
       mbar_init(rfull(i), 1);
-      mbar_init(rempty(i), 1);          // lane 0 of the converter warp that read the row
     }
     for (int i = 0; i < NA; ++i) {
+#ifdef NVS_RS_WARP_ARRIVE
+      mbar_init(afull(i), HY);          // lane 0 of the converter warp, after every lane's proxy fence and a warp barrier
+#else
       mbar_init(afull(i), HY * 32);     // every converter lane, after its own proxy fence
+#endif
       mbar_init(aempty(i), 1);          // tcgen05.commit of the chunk's MMAs
     }
     for (int i = 0; i < C::MAX_WS; ++i) {
@@ -290,15 +301,17 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int quad = warp & 3, h = warp >> 2;
     const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
     float seen_max = 0.f;
+    int dbg_i = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && dbg_i < 256) p.dbg[dbg_i++] = clock64();
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
       const int gx = tx * TX - 1 + lane, gy = ty * TY + quad;
       const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
-      mbar_wait(accfull(acc), aph);
+      if (!(p.knock & 32)) mbar_wait(accfull(acc), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int part = 0; part < C::CW / 16; ++part) {
+      for (int part = 0; part < ((p.knock & 2) ? 0 : C::CW / 16); ++part) {
         const int cbase = C::CW * h + 16 * part;  // first of this pass's 16 output channels
         if (p.dst_mode == 3 && cbase != 0) continue;  // keypoint heads: 3 channels in all
         if (cbase >= p.cout) continue;
@@ -408,7 +421,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(accempty(acc));
+      if (lane == 0 && !(p.knock & 32)) mbar_arrive(accempty(acc));
       if (++acc == ACC_STAGES) {
         acc = 0;
         aph ^= 1;
@@ -419,18 +432,81 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       seen_max = warp_max(seen_max);
       if (lane == 0 && !(seen_max < 60000.f)) atomicOr(p.range_flag, 1);
     }
-  } else if (warp < WARP_TMA_A) {
+  } else if (warp < WARP_MMA) {
     // =========================== converters: fp32 box row -> fp16 hi / lo rows of the A tile ===========================
     const int cw = warp - WARP_CONV;
-    const long long total_rows = (long long)my_tiles * chunks * HY;
-    for (long long q = cw; q < total_rows; q += CONV_WARPS) {
-      const int rs = (int)(q % NB);
-      const uint32_t rph = (uint32_t)((q / NB) & 1);
-      const long long cidx = q / HY;            // chunk counter of this CTA
-      const int row = (int)(q - cidx * HY);
-      const int as = (int)(cidx % NA);
-      const uint32_t aph = (uint32_t)((cidx / NA) & 1);
+    // ring positions are kept incrementally (no divisions: the single-thread roles are latency critical, and a 64-bit
+    // division by a run-time value costs hundreds of cycles).  This warp takes rows cw, cw + CONV_WARPS, ... of the
+    // CTA's row sequence; a chunk has HY rows, a row slot ring NB entries, the A ring NA entries.
+    int rs = cw % NB, row = cw % HY, as = 0;
+    uint32_t rph = 0, aph = 0;
+    const int my_chunks = my_tiles * chunks;
+    int cdone = 0;
+    auto advance = [&]() {  // to this warp's next row
+      rs += CONV_WARPS;
+      if (rs >= NB) {
+        rs -= NB;
+        rph ^= 1;
+      }
+      row += CONV_WARPS;
+      if (row >= HY) {       // next chunk (CONV_WARPS <= HY: at most one chunk boundary per step)
+        row -= HY;
+        ++cdone;
+        if (++as == NA) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    };
+    // The warp also LOADS its rows: lane 0 issues the TMA of the row that will use a slot next as soon as the warp has
+    // read the slot (a separate producer thread needs a round trip through an "empty" barrier per row, and one thread
+    // issuing six loads per chunk plus their address arithmetic was the slowest stage of the kernel).
+    int p_row = cw % HY, p_ch = 0, p_t = blockIdx.x, p_cdone = 0;
+    int p_tx = p_t % p.tiles_x, p_ty = (p_t / p.tiles_x) % p.tiles_y, p_b = p_t / (p.tiles_x * p.tiles_y);
+    auto issue_next = [&](int slot) {  // lane 0: load this warp's next not yet requested row into `slot`
+      if (p_cdone >= my_chunks) return;
+      if (p.knock & 8) {
+        mbar_arrive(rfull(slot));
+      } else {
+        mbar_expect_tx(rfull(slot), ROW_BYTES);
+        const uint32_t dst = base + C::SM_ROWS + slot * ROW_BYTES;
+        if (p_ch < p.c0_chunks)
+          tma_load_4d(dst, &map_a0, rfull(slot), p.c0_off + p_ch * KC, p_tx * TX - 1, p_ty * TY - 1 + p_row, p_b);
+        else
+          tma_load_4d(dst, &map_a1, rfull(slot), p.c1_off + (p_ch - p.c0_chunks) * KC, p_tx * TX - 1,
+                      p_ty * TY - 1 + p_row, p_b);
+      }
+      p_row += CONV_WARPS;
+      if (p_row >= HY) {
+        p_row -= HY;
+        ++p_cdone;
+        if (++p_ch == chunks) {
+          p_ch = 0;
+          p_t += gridDim.x;
+          p_tx = p_t % p.tiles_x;
+          p_ty = (p_t / p.tiles_x) % p.tiles_y;
+          p_b = p_t / (p.tiles_x * p.tiles_y);
+        }
+      }
+    };
+    if (lane == 0) {
+#pragma unroll 1
+      for (int d = 0; d < ROWS_AHEAD; ++d) issue_next((cw + d * CONV_WARPS) % NB);
+    }
+    int dbg_i = 0;
+    while (cdone < my_chunks) {
+      if (p.dbg && blockIdx.x == 0 && cw == 0 && lane == 0 && dbg_i < 256) p.dbg[256 + dbg_i++] = clock64();
       mbar_wait(rfull(rs), rph);
+      if (p.knock & 1) {
+        if (!(p.knock & 16)) {
+          if (row < CONV_WARPS) mbar_wait(aempty(as), aph ^ 1);
+          mbar_arrive(afull(as));
+        }
+        __syncwarp();
+        if (lane == 0) issue_next(rs);
+        advance();
+        continue;
+      }
       // position `lane` of the row: 128 bytes, 16-byte chunk c at (c ^ (lane & 7)) (SWIZZLE_128B)
       const uint8_t* src = sm + C::SM_ROWS + rs * ROW_BYTES + lane * 128;
       uint32_t hi[16], lo[16];
@@ -458,68 +534,59 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
       }
       proxy_fence();            // generic-proxy stores -> visible to the tensor core's operand reads
+#ifdef NVS_RS_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) mbar_arrive(afull(as));
+#else
       mbar_arrive(afull(as));
       __syncwarp();
-      if (lane == 0) mbar_arrive(rempty(rs));
-    }
-  } else if (warp == WARP_TMA_A) {
-    // =========================== activation producer: one box row (32 positions x 32 channels) per load ===============
-    if (lane == 0) {
-      long long q = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-        for (int ch = 0; ch < chunks; ++ch) {
-          for (int row = 0; row < HY; ++row, ++q) {
-            const int rs = (int)(q % NB);
-            mbar_wait_relaxed(rempty(rs), (uint32_t)((q / NB) & 1) ^ 1u);
-            mbar_expect_tx(rfull(rs), ROW_BYTES);
-            const uint32_t dst = base + C::SM_ROWS + rs * ROW_BYTES;
-            if (ch < p.c0_chunks)
-              tma_load_4d(dst, &map_a0, rfull(rs), p.c0_off + ch * KC, tx * TX - 1, ty * TY - 1 + row, b);
-            else
-              tma_load_4d(dst, &map_a1, rfull(rs), p.c1_off + (ch - p.c0_chunks) * KC, tx * TX - 1, ty * TY - 1 + row, b);
-          }
-        }
-      }
+#endif
+      if (lane == 0) issue_next(rs);  // every lane's reads of the slot precede its proxy fence and the warp barrier above
+      advance();
     }
   } else if (warp == WARP_TMA_W) {
     // =========================== weight producer: [W_hi ; W_lo] of one (chunk, ky) per stage ===========================
-    if (lane == 0 && my_tiles > 0) {
-      const long long total = w_resident ? w_tiles : (long long)my_tiles * w_tiles;
-      for (long long g = 0; g < total; ++g) {
-        const int ws = (int)(g % p.w_stages);
-        const int wt = (int)(g % w_tiles), ch = wt / 3, ky = wt - 3 * ch;
-        if (!w_resident) mbar_wait_relaxed(wempty(ws), (uint32_t)((g / p.w_stages) & 1) ^ 1u);
-        const uint32_t dst = base + C::SM_W + ws * C::W_STAGE;
-        mbar_expect_tx(wfull(ws), C::W_STAGE);
-        tma_load_3d(dst, &map_whi, wfull(ws), ch * KC, 0, ky);
-        tma_load_3d(dst + C::W_HALF, &map_wlo, wfull(ws), ch * KC, 0, ky);
-      }
+    if (lane == 0 && my_tiles > 0 && !(p.knock & 64)) {
+      const int rounds = w_resident ? 1 : my_tiles;
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int r = 0; r < rounds; ++r)
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int ky = 0; ky < 3; ++ky) {
+            if (!w_resident) mbar_wait_relaxed(wempty(ws), wph ^ 1u);
+            const uint32_t dst = base + C::SM_W + ws * C::W_STAGE;
+            mbar_expect_tx(wfull(ws), C::W_STAGE);
+            tma_load_3d(dst, &map_whi, wfull(ws), ch * KC, 0, ky);
+            tma_load_3d(dst + C::W_HALF, &map_wlo, wfull(ws), ch * KC, 0, ky);
+            if (++ws == p.w_stages) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
     }
   } else if (lane == 0 && my_tiles > 0) {
     // =========================== MMA issuer ===========================
-    long long g = 0;     // (chunk, ky) step counter -> weight stage
-    long long cidx = 0;  // chunk counter -> A slot
+    int dbg_i = 0;
+    int ws = 0, as = 0, acc = 0;        // weight stage, A slot, accumulator stage: kept incrementally
+    uint32_t wph = 0, aph = 0, cph = 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
-      const int acc = tl % ACC_STAGES;
-      mbar_wait(accempty(acc), ((uint32_t)(tl / ACC_STAGES) & 1u) ^ 1u);
+      if (!(p.knock & 32)) mbar_wait(accempty(acc), cph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_COLS);
-      for (int ch = 0; ch < chunks; ++ch, ++cidx) {
-        const int as = (int)(cidx % NA);
-        mbar_wait(afull(as), (uint32_t)((cidx / NA) & 1));
+      for (int ch = 0; ch < chunks; ++ch) {
+        if (p.dbg && blockIdx.x == 0 && dbg_i < 256) p.dbg[512 + dbg_i++] = clock64();
+        if (!(p.knock & 16)) mbar_wait(afull(as), aph);
         tc_fence_after();
         const uint32_t a_base = base + C::SM_A + as * A_BYTES;
         const int nk = ch == p.c0_chunks - 1 ? p.nk_last0 : (ch == chunks - 1 ? p.nk_last1 : 2);
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky, ++g) {
-          const int ws = (int)(g % p.w_stages);
-          if (!w_resident || tl == 0) mbar_wait(wfull(ws), (uint32_t)((g / p.w_stages) & 1));
+        for (int ky = 0; ky < 3; ++ky) {
+          if ((!w_resident || tl == 0) && !(p.knock & 64)) mbar_wait(wfull(ws), wph);
           const uint64_t a_hi = make_desc64(a_base + ky * (HX * 64)), a_lo = a_hi + (uint64_t)(A_HALF >> 4);
           const uint64_t w_hi = make_desc64(base + C::SM_W + ws * C::W_STAGE), w_lo = w_hi + (uint64_t)(C::W_HALF >> 4);
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            if (k < nk) {
+            if (k < nk && !(p.knock & 4)) {
               const uint64_t o = (uint64_t)(2 * k);  // 16 fp16 = 32 bytes along K = +2 in the (address >> 4) field
               const uint32_t first = (ch | ky | k) != 0 ? 1u : 0u;
               if (C::CONCAT) {
@@ -532,11 +599,23 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               }
             }
           }
-          if (!w_resident) tc_commit(wempty(ws));
+          if (!w_resident && !(p.knock & 64)) tc_commit(wempty(ws));
+          if (++ws == p.w_stages) {
+            ws = 0;
+            wph ^= 1;
+          }
         }
-        tc_commit(aempty(as));
+        if (!(p.knock & 16)) tc_commit(aempty(as));
+        if (++as == NA) {
+          as = 0;
+          aph ^= 1;
+        }
       }
-      tc_commit(accfull(acc));
+      if (!(p.knock & 32)) tc_commit(accfull(acc));
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        cph ^= 1;
+      }
     }
   }
 
@@ -599,6 +678,8 @@ static int encode_w(CUtensorMap* m, const void* ptr, int cin, int rows) {
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
 
+static long long* g_dbg = nullptr;  // nvs_conv_rs_debug_buffer
+
 template <int CO>
 static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   using C = Cfg<CO>;
@@ -609,6 +690,11 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   Params q = p;
   const int w_tiles = 3 * (p.c0_chunks + p.c1_chunks);
   q.w_stages = w_tiles <= C::MAX_W_STAGES ? w_tiles : C::MAX_W_STAGES;
+  {
+    const char* e = getenv("NVS_RS_KNOCK");
+    q.knock = e ? atoi(e) : 0;
+    q.dbg = g_dbg;
+  }
   kern<<<grid, THREADS, C::smem_bytes(q.w_stages), st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
@@ -673,6 +759,8 @@ int plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.nk_last1 = a->c1 > 0 ? last_nk(a->c1, a->c1_real) : p.nk_last0;
   p.w_stages = 0;
   p.w_scale = a->w_scale;
+  p.knock = 0;
+  p.dbg = nullptr;
   pl->cout_tpl = cpad;
   pl->magic = PLAN_MAGIC;
   return NVS_OK;
@@ -693,6 +781,9 @@ int run(const void* plan_mem, float* dst_override, float* dst2_override, cudaStr
 
 // 1 if any row-stationary conv on the current device has written an activation beyond the fp16 range since the last
 // reset (the following layer's operands were then infinite: rerun with NVS_CONV_MATH=tf32); *synchronises the device*.
+// debugging aid (tools/rs_timeline.py): device buffer of 768 clock64 stamps written by CTA 0 of every following launch
+extern "C" void nvs_conv_rs_debug_buffer(long long* dev_buf) { nvs::rs::g_dbg = dev_buf; }
+
 extern "C" int nvs_conv_rs_range_flag(int32_t reset) {
   int* f = nvs::rs::range_flag_ptr();
   if (!f) return -1;
