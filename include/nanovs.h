@@ -89,7 +89,10 @@ typedef struct NvsConvArgs {
   int32_t act;     /* NVS_ACT_* */
   int32_t out_mode;/* NVS_OUT_* */
   int32_t in_mode; /* NVS_IN_* */
-  int32_t dst_nhwc;  /* 1: dst is (B,H,W,dst_c_total) channels-last (input layout of nvs_conv_tc_*), else NCHW */
+  int32_t dst_nhwc;  /* 0: NCHW; 1: dst is (B,H,W,dst_c_total) fp32 channels-last (input layout of the 3xTF32 nvs_conv_tc
+                        kernels); 2: the SPLIT channels-last format of the 3xFP16 kernels (NvsConvTcArgs.flags bit 4):
+                        same footprint, per pixel dst_c_total fp16 values a_hi = fp16(a) followed by dst_c_total fp16
+                        values a_lo = fp16(a - a_hi); plain outputs only, dst_c_total and dst_c_off multiples of 8 */
   int32_t dst2_nhwc; /* same for the pooled output */
 } NvsConvArgs;
 
@@ -131,7 +134,11 @@ typedef struct NvsConvTcArgs {
                     bit 4: the "3xFP16" row-stationary kernel (csrc/conv_rs.cu), cout <= 64, c0 and c1 multiples of 32
                     (or c0 == c0_total == 16, c1 == 0): w_hi / w_lo point to FP16 arrays [3 ky][3 kx x cout_pad][cin]
                     (cout_pad = 32 or 64, cin = c0 + c1 with a 16-channel source padded to 32) holding the fp16 hi /
-                    lo parts of w * 2^t, and w_scale = 2^-t; any dst_mode / dst_layout / dst_pool combination */
+                    lo parts of w * 2^t, and w_scale = 2^-t; any dst_mode / dst_layout / dst_pool combination.
+                    src0 / src1 and every channels-last output (dst with dst_layout 0, dst_pool) are in the SPLIT
+                    format (see NvsConvArgs.dst_nhwc = 2, nvs_split16): per pixel c_total fp16 a_hi, then c_total
+                    fp16 a_lo, in the 4 c_total bytes of the fp32 layout; NCHW outputs stay fp32.  bit 0 then selects
+                    one MMA-issuing thread instead of three (bit-reproducible) */
   int32_t c0_real, c1_real; /* 0, or the number of leading channels of the c0 / c1 window that can be non-zero (the
                     rest is zero padding with zero weights, e.g. 24 real channels in a 32-channel row for the N
                     letters): MMA k-steps that would only multiply padding are skipped */
@@ -144,8 +151,12 @@ int nvs_conv_tc_plan_init(void* plan, const NvsConvTcArgs* args);
 /* flags bit 4 kernels only: 1 if an activation written since the last reset left the fp16 range (|x| >= 60000: the next
  * layer's operands were then not finite; rerun with the 3xTF32 kernels), 0 if not, -1 on error.  Synchronises. */
 int nvs_conv_rs_range_flag(int32_t reset);
+/* fp32 channels-last (n_pixels, C) <-> split format, C a multiple of 8 (tests, and callers that feed a 3xFP16 conv from
+ * their own fp32 data); in and out must be different buffers */
+int nvs_split16(const float* in, float* out, int64_t n_pixels, int32_t C, void* stream);
+int nvs_unsplit16(const float* in, float* out, int64_t n_pixels, int32_t C, void* stream);
 /* debugging aid: CTA 0 of every following flags-bit-4 launch writes 3 x 256 clock64 stamps (epilogue tiles, converter
- * rows, MMA chunks) into dev_buf (768 int64, device memory); NULL switches it off */
+ * (unused), MMA chunks) into dev_buf (768 int64, device memory); NULL switches it off */
 void nvs_conv_rs_debug_buffer(long long* dev_buf);
 /* dst_override / dst2_override (may be NULL) replace dst / dst_pool of the plan for this launch. */
 int nvs_conv_tc_run(const void* plan, float* dst_override, float* dst2_override, void* stream);

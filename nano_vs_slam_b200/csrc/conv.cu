@@ -14,9 +14,21 @@
 //   CTA    : WM pixel-warps stacked in y  x  WN channel-warps (8 channels each): CT = 8*WN channels
 //   K loop : input channels in chunks of CK (4 or 8), double buffered in shared memory:
 //            s_in[2][CK][TH+2][PITCH] (halo tile, zero filled = conv padding) and s_w[2][CK][taps][CT]
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace nvs {
+
+// split channels-last format of the 3xFP16 tensor-core convs (conv_rs.cu): (x, y) -> packed fp16 pair of the values
+// rounded to fp16 and packed fp16 pair of the exact remainders
+__device__ __forceinline__ void split_pair16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 struct ConvP {
   const float* src0;
@@ -32,7 +44,8 @@ struct ConvP {
   int H, W, inH, inW;
   int cin_pad, cout, cout_pad;
   int act, out_mode, in_mode;
-  int dst_nhwc, dst2_nhwc;  // store layout of dst / dst2: 0 = NCHW planes, 1 = NHWC (feeds the tensor-core convs)
+  int dst_nhwc, dst2_nhwc;  // store layout of dst / dst2: 0 = NCHW planes, 1 = NHWC fp32 (feeds the 3xTF32 convs),
+                            // 2 (dst only) = split fp16 hi / lo channels-last (feeds the 3xFP16 convs, conv_rs.cu)
   int tiles_x;
 };
 
@@ -214,7 +227,18 @@ __global__ void __launch_bounds__(32 * WN * WM, 2) conv_kernel(const ConvP p) {
       for (int c = 0; c < 2; ++c) {
         if (c == 1 && !x1ok) break;
         float* d = p.dst + (((size_t)b * p.H + gy0 + r) * p.W + gx0 + c) * p.dst_c_total + p.dst_c_off + co0;
-        if (full8) {
+        if (p.dst_nhwc == 2) {  // split format: 8 fp16 a_hi at channel offset c, 8 fp16 a_lo at c_total + c (host checks % 8)
+          uint8_t* px = reinterpret_cast<uint8_t*>(p.dst) +
+                        (((size_t)b * p.H + gy0 + r) * p.W + gx0 + c) * (size_t)p.dst_c_total * 4;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const float v0 = co0 + 2 * o < p.cout ? acc[r][c][2 * o] : 0.f, v1 = co0 + 2 * o + 1 < p.cout ? acc[r][c][2 * o + 1] : 0.f;
+            split_pair16(v0, v1, hi[o], lo[o]);
+          }
+          *reinterpret_cast<uint4*>(px + (p.dst_c_off + co0) * 2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(px + (p.dst_c_total + p.dst_c_off + co0) * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else if (full8) {
           reinterpret_cast<float4*>(d)[0] = make_float4(acc[r][c][0], acc[r][c][1], acc[r][c][2], acc[r][c][3]);
           reinterpret_cast<float4*>(d)[1] = make_float4(acc[r][c][4], acc[r][c][5], acc[r][c][6], acc[r][c][7]);
         } else {
@@ -441,7 +465,18 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(ConvP p) {
       float o[4] = {acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y};
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f) + neg_slope * fminf(o[e], 0.f);  // none / LeakyReLU / ReLU
-      stage[ly][x][q ^ ((x >> 2) & 3)] = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.dst_nhwc == 2) {
+        // split format, 16 channels: bytes [0, 32) of the pixel = 16 fp16 a_hi, bytes [32, 64) = 16 fp16 a_lo
+        uint32_t h0, l0, h1, l1;
+        split_pair16(o[0], o[1], h0, l0);
+        split_pair16(o[2], o[3], h1, l1);
+        uint2* ch_hi = reinterpret_cast<uint2*>(&stage[ly][x][(q >> 1) ^ ((x >> 2) & 3)]);
+        uint2* ch_lo = reinterpret_cast<uint2*>(&stage[ly][x][(2 + (q >> 1)) ^ ((x >> 2) & 3)]);
+        ch_hi[q & 1] = make_uint2(h0, h1);
+        ch_lo[q & 1] = make_uint2(l0, l1);
+      } else {
+        stage[ly][x][q ^ ((x >> 2) & 3)] = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
   __syncthreads();
@@ -508,6 +543,9 @@ extern "C" int nvs_conv(const NvsConvArgs* a, void* stream) {
   p.act = a->act; p.out_mode = a->out_mode; p.in_mode = a->in_mode;
   p.dst_nhwc = a->dst_nhwc; p.dst2_nhwc = a->dst2_nhwc;
   if (a->out_mode == NVS_OUT_SHUFFLE && a->dst_nhwc) return NVS_ERR_UNSUPPORTED;
+  // dst_nhwc == 2: split channels-last format (16-byte stores of 8 fp16 channels); plain outputs only
+  if (a->dst_nhwc == 2 && ((a->dst_c_total % 8) || (a->dst_c_off % 8) || a->out_mode != NVS_OUT_PLAIN)) return NVS_ERR_ARG;
+  if (a->dst2_nhwc == 2) return NVS_ERR_UNSUPPORTED;
   p.tiles_x = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((a->in_mode == NVS_IN_U8_HWC || a->in_mode == NVS_IN_UNIT) &&

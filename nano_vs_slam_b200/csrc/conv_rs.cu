@@ -10,25 +10,30 @@
 // sticky device flag when an output it writes does not), and the remainder of a small activation is quantised at
 // 2^-25 ABSOLUTE, far below the 1e-4-of-the-map's-maximum the outputs are held to.
 //
-// Row-stationary formulation (the ROW3 variant of conv_tc.cu, here for every layer): the GEMM row is an input position,
-// the three taps of a kernel row are one N = 3 x Cout operand ([kx = 0 | 1 | 2] x Cout) and
-// out[i] = D_0[i-1] + D_1[i] + D_2[i+1] is formed by two warp shuffles per channel in the epilogue.  Tile = 4 image
-// rows x 30 columns (32 positions per row with the halo columns, one row per TMEM lane quadrant).  What is new:
+// ACTIVATION FORMAT ("split" channels-last, NVS_NHWC_SPLIT16): between these layers an activation tensor (B,H,W,C) keeps
+// its fp32 footprint (4 C bytes per pixel) but holds, per pixel, C fp16 values a_hi followed by C fp16 values a_lo.
+// The producing layer's epilogue (or the stem / 1x1 FFMA kernels of conv.cu) performs the split once per value; the
+// consuming layer's TMA loads then deliver MMA-ready operand tiles: no conversion pass, no staging buffer.
 //
-//   * the A operand is read from SHARED memory (SS-mode MMA).  The 6 x 32 halo box of a 32-channel chunk is one
-//     contiguous K-major matrix of 192 rows, and the operand of kernel row ky is simply its rows [32 ky, 32 ky + 128):
-//     every input value is converted ONCE per tile and chunk (the TMEM-fed kernels convert it once per tap, 9x / 3x),
-//     by three converter warps that read the fp32 box rows TMA delivered and write the fp16 hi / lo tiles in the
-//     canonical SWIZZLE_64B layout;
-//   * all three products go to ONE accumulator (no scaled correction half): 3 x Cout columns per stage, two stages;
-//     Cout = 32 layers issue a_hi x [W_hi ; W_lo] as one N = 192 instruction (the epilogue adds the halves);
-//   * one MMA-issuing thread (N = 192 MMAs cost their nominal 96 cycles, more than a thread needs to queue one):
-//     the accumulation order is fixed, results are bit-reproducible run to run;
-//   * weights stay resident in shared memory for the whole kernel when the layer's 3 x chunks tiles fit (up to
-//     64 input channels at Cout = 64), else they stream through a ring.
+// Row-stationary formulation: the GEMM row is an input position, the three taps of a kernel row are one N = 3 x Cout
+// operand ([kx = 0 | 1 | 2] x Cout) and out[i] = D_0[i-1] + D_1[i] + D_2[i+1] is formed by two warp shuffles per
+// channel in the epilogue.  Tile = 4 image rows x 30 columns (32 positions per row with the halo columns, one row per
+// TMEM lane quadrant).  The 6 x 32 halo box of a 32-channel chunk is ONE TMA box per operand part (fp16, 64-byte rows,
+// SWIZZLE_64B): a contiguous K-major matrix of 192 rows, and the A operand of kernel row ky is its rows
+// [32 ky, 32 ky + 128) -- a descriptor offset.  All three products go to one accumulator (3 x Cout columns per stage,
+// two stages); Cout = 32 layers issue a_hi x [W_hi ; W_lo] as one N = 192 instruction (the epilogue adds the halves).
+// A 16-channel tensor (the stem's output) stores [hi | lo] in one 64-byte row: one box, a_lo is the second k-step.
 //
-// Warps: 0-7 epilogue (quadrant = warp % 4, channel half = warp / 4), 8-10 converters (box rows round-robin; each also
-// issues the TMA loads of its rows), 11 MMA issuer (allocates TMEM), 12 weight TMA.  Persistent CTAs, one per SM.
+// A thread issues dependent instructions at ~8 cycles apiece, so the single-thread roles are instruction-latency bound
+// (measured with the clock64 timeline, tools/rs_timeline.py: one MMA thread needed ~3100 cycles per chunk for 1700
+// cycles of MMA time).  Hence: three MMA-issuing threads (one per kernel row; issuer 0 queues the tile's first,
+// overwriting MMA and releases the others through the astart barrier), descriptors advanced by 32-bit immediates, ring
+// positions kept incrementally (no divisions).  flags bit 0 selects one issuer: fixed accumulation order,
+// bit-reproducible results.  Weights stay resident in shared memory for the whole kernel when the layer's 3 x chunks
+// tiles fit (up to 64 input channels at Cout = 64), else they stream through a ring.
+//
+// Warps: 0-7 epilogue (quadrant = warp % 4, channel half = warp / 4), 8 activation TMA, 9 weight TMA, 10-12 MMA issuers
+// (warp 10 allocates TMEM).  Persistent CTAs, one per SM.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -41,31 +46,18 @@ namespace rs {
 constexpr int TX = 30, TY = 4;           // output pixels per tile
 constexpr int HX = 32, HY = 6;           // halo box: positions per row (= GEMM rows per quadrant), rows
 constexpr int KC = 32;                   // input channels per chunk
-constexpr int ROW_BYTES = HX * KC * 4;   // one fp32 box row: 32 positions x 128 B
-#ifndef NVS_RS_NB
-#define NVS_RS_NB 6
-#endif
-#ifndef NVS_RS_CONV_WARPS
-#define NVS_RS_CONV_WARPS 3
-#endif
-constexpr int NB = NVS_RS_NB;            // box rows in flight
 constexpr int A_HALF = HX * HY * KC * 2; // one of the hi / lo operand matrices: 192 rows x 64 B
 constexpr int A_BYTES = 2 * A_HALF;
 #ifndef NVS_RS_NA
-#define NVS_RS_NA 2
+#define NVS_RS_NA 3
 #endif
-constexpr int NA = NVS_RS_NA;            // converted chunks in flight
+constexpr int NA = NVS_RS_NA;            // activation chunks in flight
 constexpr int ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;
-// NB is a multiple of CONV_WARPS: a ring slot is then always read by the same converter warp, so a warp can never wait
-// for a phase of a row barrier that is two ahead of the barrier's current one (a parity wait cannot tell that from
-// "already complete": with 4 warps on 6 slots a fast warp read a row that had not landed yet)
-constexpr int WARP_CONV = EPI_WARPS, CONV_WARPS = NVS_RS_CONV_WARPS;
-static_assert(NB % CONV_WARPS == 0 && HY >= CONV_WARPS, "row ring / converter warps");
-constexpr int WARP_MMA = WARP_CONV + CONV_WARPS, WARP_TMA_W = WARP_MMA + 1;
-constexpr int THREADS = 32 * (WARP_TMA_W + 1);
-constexpr int ROWS_AHEAD = NB / CONV_WARPS;  // row loads a converter warp keeps in flight (its slots of the ring)
-constexpr unsigned long long PLAN_MAGIC = 0x7273506C616E0001ull;  // first word of an rs::Plan
+constexpr int MAX_ISSUERS = 3;
+constexpr int WARP_TMA_A = EPI_WARPS, WARP_TMA_W = WARP_TMA_A + 1, WARP_MMA = WARP_TMA_W + 1;
+constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
+constexpr unsigned long long PLAN_MAGIC = 0x7273506C616E0002ull;  // first word of an rs::Plan
 
 template <int CO>
 struct Cfg {
@@ -76,18 +68,18 @@ struct Cfg {
   static constexpr bool CONCAT = CO == 32;          // a_hi x [W_hi ; W_lo] as one N = 2 NW instruction
   static constexpr int ACC_COLS = 192;              // per stage: CONCAT 2 x 96, else 192
   static constexpr int CW = CO / 2;                 // output channels per epilogue warp
-  static constexpr int SM_ROWS = 0;
-  static constexpr int SM_A = SM_ROWS + NB * ROW_BYTES;
+  static constexpr int SM_A = 0;
   static constexpr int SM_BIAS = SM_A + NA * A_BYTES;
   static constexpr int SM_POOL = SM_BIAS + CO * 4;
   static constexpr int POOL_BYTES = 2 * 2 * 15 * 16 * 4;   // max-pool exchange: (channel half, quadrant pair) x 15 x 16
   static constexpr int SM_BAR = SM_POOL + POOL_BYTES;
   static constexpr int MAX_WS = 16;                  // barrier slots reserved for the weight ring
-  static constexpr int N_BARS = 2 * NB + 2 * NA + 2 * MAX_WS + 4 + 1;
+  static constexpr int N_BARS = 2 * NA + 2 * MAX_WS + 6 + 1;
   static constexpr int SM_W = ((SM_BAR + 8 * N_BARS + 16 + 1023) / 1024) * 1024;
-  static constexpr int MAX_W_STAGES = (227 * 1024 - 1024 - SM_W) / W_STAGE;
+  static constexpr int MAX_W_STAGES_FIT = (227 * 1024 - 1024 - SM_W) / W_STAGE;
+  static constexpr int MAX_W_STAGES = MAX_W_STAGES_FIT < MAX_WS ? MAX_W_STAGES_FIT : MAX_WS;
   static constexpr int smem_bytes(int w_stages) { return SM_W + w_stages * W_STAGE + 1024; }
-  static_assert(MAX_W_STAGES >= 3 && MAX_W_STAGES <= MAX_WS, "weight ring");
+  static_assert(MAX_W_STAGES >= 3, "weight ring");
   static constexpr uint32_t idesc(int n) {  // kind::f16: D fp32, A / B fp16, both K-major
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   }
@@ -99,16 +91,19 @@ struct Params {
   float* dst_pool;
   int* range_flag;   // sticky: set when an output written in an activation layout exceeds the fp16 range
   int c0_off, c0_chunks, c1_off, c1_chunks;
+  int c0_lo, c1_lo;  // channel coordinate of a source's a_lo block (= its total channel count); unused when pair16
+  int pair16;        // source 0 is a 16-channel tensor: [hi | lo] in one 64-byte row, one box, a_lo = second k-step
   int dst_c_total, dst_c_off, dst_layout, dst_mode;
   int pool_c_total, pool_c_off;
   int B, H, W, cout, act;
   int tiles_x, tiles_y, n_tiles;
   int nk_last0, nk_last1;  // k-steps (16 channels) of the last chunk of source 0 / 1 that can be non-zero
   int w_stages;            // weight ring depth; >= 3 * chunks means resident (every tile loaded once)
+  int issuers;             // MMA-issuing threads: 3, or 1 (fixed accumulation order)
   float w_scale;           // 2^-t: undoes the weights' power-of-two scale
-  long long* dbg;          // env NVS_RS_DBG=1: per-role clock64 stamps of CTA 0 (nvs_conv_rs_debug_buffer), 256 per role
-  int knock;               // bottleneck experiments (env NVS_RS_KNOCK, results are then garbage): 1 converters only
-                           // pass barriers, 2 epilogue only passes barriers, 4 no MMAs, 8 no activation TMA
+  long long* dbg;          // nvs_conv_rs_debug_buffer: per-role clock64 stamps of CTA 0, 256 per role
+  int knock;               // bottleneck experiments (env NVS_RS_KNOCK, results are then garbage): 2 epilogue only
+                           // passes barriers, 4 no MMAs, 8 no activation TMA, 64 no weight TMA
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -226,7 +221,40 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, 
     b[i] = __uint_as_float(q[i]);
   }
 }
+// one lane of the (converged) warp; the compiler then knows the guarded code is single-threaded AND that warp-uniform
+// values stay uniform, so tcgen05 operands move to uniform registers without a per-lane election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// (x, y) -> packed fp16 pair of the values rounded to fp16 and packed fp16 pair of the exact remainders
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 f = __half22float2(h);
+  hi = h2_bits(h);
+  lo = h2_bits(__floats2half2_rn(x - f.x, y - f.y));
+}
+// 16 consecutive channels [c, c + 16) of one pixel of a split-format tensor with c_total channels: a_hi as 32 bytes at
+// (pixel * 4 c_total + 2 c), a_lo 2 c_total bytes further; only the leading n_valid channels (in steps of 8) are written
+__device__ __forceinline__ void store_split16(float* basep, size_t pixel, int c_total, int c, const float* v, int n_valid) {
+  uint8_t* px = reinterpret_cast<uint8_t*>(basep) + pixel * (size_t)c_total * 4;
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    if (8 * q < n_valid) {
+      *reinterpret_cast<uint4*>(px + (c + 8 * q) * 2) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      *reinterpret_cast<uint4*>(px + (c_total + c + 8 * q) * 2) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+}
 
 template <int CO>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -239,13 +267,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(sm + C::SM_BIAS);
   const uint32_t bar0 = base + C::SM_BAR;
-  auto rfull = [&](int i) { return bar0 + 8u * i; };
-  auto afull = [&](int i) { return bar0 + 8u * (2 * NB + i); };
-  auto aempty = [&](int i) { return bar0 + 8u * (2 * NB + NA + i); };
-  auto wfull = [&](int i) { return bar0 + 8u * (2 * NB + 2 * NA + i); };
-  auto wempty = [&](int i) { return bar0 + 8u * (2 * NB + 2 * NA + C::MAX_WS + i); };
-  auto accfull = [&](int i) { return bar0 + 8u * (2 * NB + 2 * NA + 2 * C::MAX_WS + i); };
-  auto accempty = [&](int i) { return bar0 + 8u * (2 * NB + 2 * NA + 2 * C::MAX_WS + 2 + i); };
+  auto afull = [&](int i) { return bar0 + 8u * i; };
+  auto aempty = [&](int i) { return bar0 + 8u * (NA + i); };
+  auto wfull = [&](int i) { return bar0 + 8u * (2 * NA + i); };
+  auto wempty = [&](int i) { return bar0 + 8u * (2 * NA + C::MAX_WS + i); };
+  auto accfull = [&](int i) { return bar0 + 8u * (2 * NA + 2 * C::MAX_WS + i); };
+  auto accempty = [&](int i) { return bar0 + 8u * (2 * NA + 2 * C::MAX_WS + 2 + i); };
+  auto astart = [&](int i) { return bar0 + 8u * (2 * NA + 2 * C::MAX_WS + 4 + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::SM_BAR + 8 * C::N_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,24 +287,18 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
-    for (int i = 0; i < NB; ++i) {
-      mbar_init(rfull(i), 1);
-    }
     for (int i = 0; i < NA; ++i) {
-#ifdef NVS_RS_WARP_ARRIVE
-      mbar_init(afull(i), HY);          // lane 0 of the converter warp, after every lane's proxy fence and a warp barrier
-#else
-      mbar_init(afull(i), HY * 32);     // every converter lane, after its own proxy fence
-#endif
-      mbar_init(aempty(i), 1);          // tcgen05.commit of the chunk's MMAs
+      mbar_init(afull(i), 1);           // the activation TMA's expect_tx arrive
+      mbar_init(aempty(i), p.issuers);  // tcgen05.commit of every issuer's MMAs of the chunk
     }
     for (int i = 0; i < C::MAX_WS; ++i) {
       mbar_init(wfull(i), 1);
-      mbar_init(wempty(i), 1);
+      mbar_init(wempty(i), 1);          // the issuer that used the stage
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(accfull(i), 1);
+      mbar_init(accfull(i), p.issuers);
       mbar_init(accempty(i), EPI_WARPS);
+      mbar_init(astart(i), 1);          // issuer 0 has queued the tile's first (overwriting) MMA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -307,7 +329,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
       const int gx = tx * TX - 1 + lane, gy = ty * TY + quad;
       const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
-      if (!(p.knock & 32)) mbar_wait(accfull(acc), aph);
+      mbar_wait(accfull(acc), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
@@ -380,25 +402,22 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
           const int qx = gx >> 1, qy = gy >> 1;
           if (!(quad & 1) && owner && qx < (p.W >> 1) && qy < (p.H >> 1)) {
-            float4* d = reinterpret_cast<float4*>(
-                p.dst_pool + (((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx) * p.pool_c_total + p.pool_c_off + cbase);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 r = reinterpret_cast<const float4*>(ps + pc * 16)[q];
-              if (cbase + 4 * q < p.cout)
-                d[q] = make_float4(fmaxf(m[4 * q], r.x), fmaxf(m[4 * q + 1], r.y), fmaxf(m[4 * q + 2], r.z),
-                                   fmaxf(m[4 * q + 3], r.w));
+              m[4 * q] = fmaxf(m[4 * q], r.x);
+              m[4 * q + 1] = fmaxf(m[4 * q + 1], r.y);
+              m[4 * q + 2] = fmaxf(m[4 * q + 2], r.z);
+              m[4 * q + 3] = fmaxf(m[4 * q + 3], r.w);
             }
+            store_split16(p.dst_pool, ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx, p.pool_c_total, p.pool_c_off + cbase,
+                          m, p.cout - cbase);
           }
           asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         }
         if (valid && p.dst_mode == 1) {
-          if (p.dst_layout == 0) {  // NHWC
-            float4* d = reinterpret_cast<float4*>(
-                p.dst + (((size_t)b * p.H + gy) * p.W + gx) * p.dst_c_total + p.dst_c_off + cbase);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (cbase + 4 * q < p.cout) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          if (p.dst_layout == 0) {  // channels-last, split format
+            store_split16(p.dst, ((size_t)b * p.H + gy) * p.W + gx, p.dst_c_total, p.dst_c_off + cbase, o, p.cout - cbase);
           } else {  // NCHW: a warp writes 30 consecutive x of one channel row
             float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cbase) * p.H + gy) * p.W + gx;
             const size_t plane = (size_t)p.H * p.W;
@@ -406,22 +425,28 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int j = 0; j < 16; ++j)
               if (cbase + j < p.cout) d[j * plane] = o[j];
           }
-        } else if (valid && p.dst_mode == 2) {  // PixelShuffle(2) -> NHWC (B, 2H, 2W, cout/4): channel c -> (c%4/2, c%2, c/4)
+        } else if (valid && p.dst_mode == 2) {
+          // PixelShuffle(2) -> channels-last (B, 2H, 2W, cout/4), split format: channel c -> (c%4/2, c%2, c/4)
           const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              float4* d = reinterpret_cast<float4*>(
-                  p.dst + (((size_t)b * H2 + 2 * gy + i) * W2 + 2 * gx + j) * p.dst_c_total + p.dst_c_off + cbase / 4);
               const int s = 2 * i + j;
-              d[0] = make_float4(o[s], o[4 + s], o[8 + s], o[12 + s]);
+              uint8_t* px = reinterpret_cast<uint8_t*>(p.dst) +
+                            (((size_t)b * H2 + 2 * gy + i) * W2 + 2 * gx + j) * (size_t)p.dst_c_total * 4;
+              const int c = p.dst_c_off + cbase / 4;
+              uint32_t hi2[2], lo2[2];
+              split_pair(o[s], o[4 + s], hi2[0], lo2[0]);
+              split_pair(o[8 + s], o[12 + s], hi2[1], lo2[1]);
+              *reinterpret_cast<uint2*>(px + c * 2) = make_uint2(hi2[0], hi2[1]);
+              *reinterpret_cast<uint2*>(px + (p.dst_c_total + c) * 2) = make_uint2(lo2[0], lo2[1]);
             }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0 && !(p.knock & 32)) mbar_arrive(accempty(acc));
+      if (lane == 0) mbar_arrive(accempty(acc));
       if (++acc == ACC_STAGES) {
         acc = 0;
         aph ^= 1;
@@ -432,117 +457,38 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       seen_max = warp_max(seen_max);
       if (lane == 0 && !(seen_max < 60000.f)) atomicOr(p.range_flag, 1);
     }
-  } else if (warp < WARP_MMA) {
-    // =========================== converters: fp32 box row -> fp16 hi / lo rows of the A tile ===========================
-    const int cw = warp - WARP_CONV;
-    // ring positions are kept incrementally (no divisions: the single-thread roles are latency critical, and a 64-bit
-    // division by a run-time value costs hundreds of cycles).  This warp takes rows cw, cw + CONV_WARPS, ... of the
-    // CTA's row sequence; a chunk has HY rows, a row slot ring NB entries, the A ring NA entries.
-    int rs = cw % NB, row = cw % HY, as = 0;
-    uint32_t rph = 0, aph = 0;
-    const int my_chunks = my_tiles * chunks;
-    int cdone = 0;
-    auto advance = [&]() {  // to this warp's next row
-      rs += CONV_WARPS;
-      if (rs >= NB) {
-        rs -= NB;
-        rph ^= 1;
-      }
-      row += CONV_WARPS;
-      if (row >= HY) {       // next chunk (CONV_WARPS <= HY: at most one chunk boundary per step)
-        row -= HY;
-        ++cdone;
-        if (++as == NA) {
-          as = 0;
-          aph ^= 1;
-        }
-      }
-    };
-    // The warp also LOADS its rows: lane 0 issues the TMA of the row that will use a slot next as soon as the warp has
-    // read the slot (a separate producer thread needs a round trip through an "empty" barrier per row, and one thread
-    // issuing six loads per chunk plus their address arithmetic was the slowest stage of the kernel).
-    int p_row = cw % HY, p_ch = 0, p_t = blockIdx.x, p_cdone = 0;
-    int p_tx = p_t % p.tiles_x, p_ty = (p_t / p.tiles_x) % p.tiles_y, p_b = p_t / (p.tiles_x * p.tiles_y);
-    auto issue_next = [&](int slot) {  // lane 0: load this warp's next not yet requested row into `slot`
-      if (p_cdone >= my_chunks) return;
-      if (p.knock & 8) {
-        mbar_arrive(rfull(slot));
-      } else {
-        mbar_expect_tx(rfull(slot), ROW_BYTES);
-        const uint32_t dst = base + C::SM_ROWS + slot * ROW_BYTES;
-        if (p_ch < p.c0_chunks)
-          tma_load_4d(dst, &map_a0, rfull(slot), p.c0_off + p_ch * KC, p_tx * TX - 1, p_ty * TY - 1 + p_row, p_b);
-        else
-          tma_load_4d(dst, &map_a1, rfull(slot), p.c1_off + (p_ch - p.c0_chunks) * KC, p_tx * TX - 1,
-                      p_ty * TY - 1 + p_row, p_b);
-      }
-      p_row += CONV_WARPS;
-      if (p_row >= HY) {
-        p_row -= HY;
-        ++p_cdone;
-        if (++p_ch == chunks) {
-          p_ch = 0;
-          p_t += gridDim.x;
-          p_tx = p_t % p.tiles_x;
-          p_ty = (p_t / p.tiles_x) % p.tiles_y;
-          p_b = p_t / (p.tiles_x * p.tiles_y);
-        }
-      }
-    };
+  } else if (warp == WARP_TMA_A) {
+    // =========================== activation producer: the hi and the lo box of one chunk per A slot ===============
     if (lane == 0) {
-#pragma unroll 1
-      for (int d = 0; d < ROWS_AHEAD; ++d) issue_next((cw + d * CONV_WARPS) % NB);
-    }
-    int dbg_i = 0;
-    while (cdone < my_chunks) {
-      if (p.dbg && blockIdx.x == 0 && cw == 0 && lane == 0 && dbg_i < 256) p.dbg[256 + dbg_i++] = clock64();
-      mbar_wait(rfull(rs), rph);
-      if (p.knock & 1) {
-        if (!(p.knock & 16)) {
-          if (row < CONV_WARPS) mbar_wait(aempty(as), aph ^ 1);
-          mbar_arrive(afull(as));
+      int as = 0;
+      uint32_t aph = 0;
+      const uint32_t bytes = p.pair16 ? A_HALF : A_BYTES;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * TX - 1, y0 = ty * TY - 1;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait_relaxed(aempty(as), aph ^ 1u);
+          const uint32_t dst = base + C::SM_A + as * A_BYTES;
+          if (p.knock & 8) {
+            mbar_arrive(afull(as));
+          } else {
+            mbar_expect_tx(afull(as), bytes);
+            if (ch < p.c0_chunks) {
+              const int c = p.c0_off + ch * KC;
+              tma_load_4d(dst, &map_a0, afull(as), c, x0, y0, b);
+              if (!p.pair16) tma_load_4d(dst + A_HALF, &map_a0, afull(as), p.c0_lo + c, x0, y0, b);
+            } else {
+              const int c = p.c1_off + (ch - p.c0_chunks) * KC;
+              tma_load_4d(dst, &map_a1, afull(as), c, x0, y0, b);
+              tma_load_4d(dst + A_HALF, &map_a1, afull(as), p.c1_lo + c, x0, y0, b);
+            }
+          }
+          if (++as == NA) {
+            as = 0;
+            aph ^= 1;
+          }
         }
-        __syncwarp();
-        if (lane == 0) issue_next(rs);
-        advance();
-        continue;
       }
-      // position `lane` of the row: 128 bytes, 16-byte chunk c at (c ^ (lane & 7)) (SWIZZLE_128B)
-      const uint8_t* src = sm + C::SM_ROWS + rs * ROW_BYTES + lane * 128;
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(src + ((c ^ (lane & 7)) << 4));
-        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        hi[2 * c] = h2_bits(h0);
-        hi[2 * c + 1] = h2_bits(h1);
-        lo[2 * c] = h2_bits(__floats2half2_rn(v.x - f0.x, v.y - f0.y));
-        lo[2 * c + 1] = h2_bits(__floats2half2_rn(v.z - f1.x, v.w - f1.y));
-      }
-      // a warp's first row of a chunk is one of the chunk's first CONV_WARPS rows: the MMAs that last read this A
-      // slot (two chunks ago) must have retired before it is overwritten
-      if (row < CONV_WARPS) mbar_wait(aempty(as), aph ^ 1);
-      // A tile row r = 32 * row + lane: 64 bytes, 16-byte chunk j (8 channels) at (j ^ ((r >> 1) & 3)) (SWIZZLE_64B)
-      const int r = 32 * row + lane;
-      uint8_t* dh = sm + C::SM_A + as * A_BYTES + r * 64;
-      const int key = (r >> 1) & 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        *reinterpret_cast<uint4*>(dh + ((j ^ key) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        *reinterpret_cast<uint4*>(dh + A_HALF + ((j ^ key) << 4)) =
-            make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-      }
-      proxy_fence();            // generic-proxy stores -> visible to the tensor core's operand reads
-#ifdef NVS_RS_WARP_ARRIVE
-      __syncwarp();
-      if (lane == 0) mbar_arrive(afull(as));
-#else
-      mbar_arrive(afull(as));
-      __syncwarp();
-#endif
-      if (lane == 0) issue_next(rs);  // every lane's reads of the slot precede its proxy fence and the warp barrier above
-      advance();
     }
   } else if (warp == WARP_TMA_W) {
     // =========================== weight producer: [W_hi ; W_lo] of one (chunk, ky) per stage ===========================
@@ -564,54 +510,78 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
           }
     }
-  } else if (lane == 0 && my_tiles > 0) {
-    // =========================== MMA issuer ===========================
+  } else if (my_tiles > 0 && warp - WARP_MMA < p.issuers) {
+    // =========================== MMA issuers ===========================
+    // Issuer `me` of `nis` takes the kernel rows ky = me, me + nis, ... of every chunk.  Descriptors: the upper word is
+    // the same constant for every operand (64-byte rows, SWIZZLE_64B, 8-row groups 512 B apart); the lower word is
+    // (address >> 4) | LBO and is advanced by 32-bit adds of compile-time constants.  The whole warp runs the loop
+    // (converged); one elected lane executes the tcgen05 / mbarrier-arrive instructions.
+    const int me = __shfl_sync(0xffffffffu, warp, 0) - WARP_MMA, nis = p.issuers;
+    constexpr uint32_t DESC_HI = (uint32_t)(512u >> 4) | (1u << 14) | (4u << 29);
+    auto desc = [](uint32_t lo32) { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo32; };
+    const uint32_t a_lo0 = (((base + C::SM_A) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t w_lo0 = (((base + C::SM_W) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t lo_part = p.pair16 ? 2u : (uint32_t)(A_HALF >> 4);  // a_lo relative to a_hi
     int dbg_i = 0;
-    int ws = 0, as = 0, acc = 0;        // weight stage, A slot, accumulator stage: kept incrementally
+    int ws = me, as = 0, acc = 0;  // weight stage of my next kernel row, A slot, accumulator stage
     uint32_t wph = 0, aph = 0, cph = 0;
+    while (ws >= p.w_stages) {  // (w_stages >= 3 > me: never taken; keeps the invariant explicit)
+      ws -= p.w_stages;
+      wph ^= 1;
+    }
     for (int tl = 0; tl < my_tiles; ++tl) {
-      if (!(p.knock & 32)) mbar_wait(accempty(acc), cph ^ 1u);
+      mbar_wait(accempty(acc), cph ^ 1u);
+      if (me != 0) mbar_wait(astart(acc), cph);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_COLS);
       for (int ch = 0; ch < chunks; ++ch) {
-        if (p.dbg && blockIdx.x == 0 && dbg_i < 256) p.dbg[512 + dbg_i++] = clock64();
-        if (!(p.knock & 16)) mbar_wait(afull(as), aph);
+        if (p.dbg && blockIdx.x == 0 && me == 0 && lane == 0 && dbg_i < 256) p.dbg[512 + dbg_i] = clock64();
+        ++dbg_i;
+        mbar_wait(afull(as), aph);
         tc_fence_after();
-        const uint32_t a_base = base + C::SM_A + as * A_BYTES;
-        const int nk = ch == p.c0_chunks - 1 ? p.nk_last0 : (ch == chunks - 1 ? p.nk_last1 : 2);
+        const int nk = p.pair16 ? 1 : (ch == p.c0_chunks - 1 ? p.nk_last0 : (ch == chunks - 1 ? p.nk_last1 : 2));
+        const uint32_t a_slot = a_lo0 + (uint32_t)as * (uint32_t)(A_BYTES >> 4);
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky) {
-          if ((!w_resident || tl == 0) && !(p.knock & 64)) mbar_wait(wfull(ws), wph);
-          const uint64_t a_hi = make_desc64(a_base + ky * (HX * 64)), a_lo = a_hi + (uint64_t)(A_HALF >> 4);
-          const uint64_t w_hi = make_desc64(base + C::SM_W + ws * C::W_STAGE), w_lo = w_hi + (uint64_t)(C::W_HALF >> 4);
+        for (int ky = me; ky < 3; ky += nis) {
+          if (!w_resident || tl == 0) mbar_wait(wfull(ws), wph);
+          const uint32_t a_hi = a_slot + (uint32_t)ky * (uint32_t)((HX * 64) >> 4), a_lo = a_hi + lo_part;
+          const uint32_t w_hi = w_lo0 + (uint32_t)ws * (uint32_t)(C::W_STAGE >> 4), w_lo = w_hi + (uint32_t)(C::W_HALF >> 4);
+          if (!(p.knock & 4) && elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (k < nk && !(p.knock & 4)) {
-              const uint64_t o = (uint64_t)(2 * k);  // 16 fp16 = 32 bytes along K = +2 in the (address >> 4) field
-              const uint32_t first = (ch | ky | k) != 0 ? 1u : 0u;
-              if (C::CONCAT) {
-                tc_mma_f16(d_tmem, a_hi + o, w_hi + o, C::idesc(2 * C::NW), first);            // x [W_hi ; W_lo]
-                tc_mma_f16(d_tmem + (uint32_t)C::NW, a_lo + o, w_hi + o, C::idesc(C::NW), 1u);
-              } else {
-                tc_mma_f16(d_tmem, a_hi + o, w_hi + o, C::idesc(C::NW), first);
-                tc_mma_f16(d_tmem, a_hi + o, w_lo + o, C::idesc(C::NW), 1u);
-                tc_mma_f16(d_tmem, a_lo + o, w_hi + o, C::idesc(C::NW), 1u);
+            for (int k = 0; k < 2; ++k) {
+              if (k < nk) {
+                const uint32_t o = 2u * k;  // 16 fp16 = 32 bytes along K = +2 in the (address >> 4) field
+                const uint32_t accum = (ch | ky | k) != 0 ? 1u : 0u;
+                if (C::CONCAT) {
+                  tc_mma_f16(d_tmem, desc(a_hi + o), desc(w_hi + o), C::idesc(2 * C::NW), accum);  // x [W_hi ; W_lo]
+                  if (accum == 0u) mbar_arrive(astart(acc));
+                  tc_mma_f16(d_tmem + (uint32_t)C::NW, desc(a_lo + o), desc(w_hi + o), C::idesc(C::NW), 1u);
+                } else {
+                  tc_mma_f16(d_tmem, desc(a_hi + o), desc(w_hi + o), C::idesc(C::NW), accum);
+                  if (accum == 0u) mbar_arrive(astart(acc));
+                  tc_mma_f16(d_tmem, desc(a_hi + o), desc(w_lo + o), C::idesc(C::NW), 1u);
+                  tc_mma_f16(d_tmem, desc(a_lo + o), desc(w_hi + o), C::idesc(C::NW), 1u);
+                }
               }
             }
+          } else if ((p.knock & 4) && ch == 0 && ky == 0) {
+            if (elect_one()) mbar_arrive(astart(acc));
           }
-          if (!w_resident && !(p.knock & 64)) tc_commit(wempty(ws));
-          if (++ws == p.w_stages) {
-            ws = 0;
+          __syncwarp();
+          if (!w_resident && elect_one()) tc_commit(wempty(ws));
+          ws += nis;
+          if (ws >= p.w_stages) {
+            ws -= p.w_stages;
             wph ^= 1;
           }
         }
-        if (!(p.knock & 16)) tc_commit(aempty(as));
+        if (elect_one()) tc_commit(aempty(as));
         if (++as == NA) {
           as = 0;
           aph ^= 1;
         }
       }
-      if (!(p.knock & 32)) tc_commit(accfull(acc));
+      if (elect_one()) tc_commit(accfull(acc));
       if (++acc == ACC_STAGES) {
         acc = 0;
         cph ^= 1;
@@ -650,17 +620,18 @@ struct alignas(64) Plan {
   Params p;
 };
 
-// NHWC fp32 activations (B,H,W,Ct): box = (32 channels, 32 positions, 1 row, 1 frame); channels beyond Ct (the
-// 16-channel stem output) and positions outside the image are zero filled by TMA
+// split-format activations (B,H,W,Ct): per pixel Ct fp16 a_hi then Ct fp16 a_lo (4 Ct bytes).  As an fp16 tensor with
+// 2 Ct "channels": box = (32 channels, 32 positions, 6 rows, 1 frame) = one operand part of a chunk's halo box;
+// positions outside the image are zero filled by TMA = the convolution's zero padding
 static int encode_act(CUtensorMap* m, const float* ptr, int B, int H, int W, int Ct) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return NVS_ERR_CUDA;
-  cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t dims[4] = {(cuuint64_t)2 * Ct, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)Ct * 4, (cuuint64_t)W * Ct * 4, (cuuint64_t)H * W * Ct * 4};
-  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)HX, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)HX, (cuuint32_t)HY, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<float*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NVS_OK : NVS_ERR_CUDA;
 }
@@ -724,8 +695,11 @@ bool is_plan(const void* plan_mem) {
 
 int plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   if (a->cout <= 0 || a->cout > 64) return NVS_ERR_UNSUPPORTED;
-  const int c0 = a->c0 == 16 ? 32 : a->c0;  // a 16-channel source is read as one chunk whose upper half TMA zero-fills
+  const int c0 = a->c0 == 16 ? 32 : a->c0;  // a 16-channel source ([hi | lo] in one 64-byte row) is one chunk
   if (a->c0 == 16 && (a->c1 != 0 || a->c0_off != 0 || a->c0_total != 16)) return NVS_ERR_ARG;
+  // split-format outputs: 16-byte stores of 8 fp16 channels (pixel shuffle: 8-byte stores of 4)
+  if (a->dst_mode == 1 && a->dst_layout == 0 && ((a->dst_c_total % 8) || (a->dst_c_off % 8))) return NVS_ERR_ARG;
+  if (a->dst_pool && a->dst_mode != 3 && ((a->pool_c_total % 8) || (a->pool_c_off % 8))) return NVS_ERR_ARG;
   if ((c0 % KC) || (a->c1 % KC)) return NVS_ERR_UNSUPPORTED;
   if (!(a->w_scale > 0.f)) return NVS_ERR_ARG;
   Plan* pl = reinterpret_cast<Plan*>(((uintptr_t)plan_mem + 63) & ~(uintptr_t)63);
@@ -744,6 +718,15 @@ int plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.bias = a->bias; p.dst = a->dst; p.dst_pool = a->dst_pool;
   p.range_flag = range_flag_ptr();
   p.c0_off = a->c0_off; p.c0_chunks = c0 / KC; p.c1_off = a->c1_off; p.c1_chunks = a->c1 / KC;
+  p.c0_lo = a->c0_total; p.c1_lo = a->c1_total; p.pair16 = a->c0 == 16 ? 1 : 0;
+  {
+    static int default_issuers = 0;
+    if (!default_issuers) {
+      const char* e = getenv("NVS_RS_ISSUERS");
+      default_issuers = (e && atoi(e) == 3) ? MAX_ISSUERS : 1;
+    }
+    p.issuers = (a->flags & 1) ? 1 : default_issuers;
+  }
   p.dst_c_total = a->dst_c_total; p.dst_c_off = a->dst_c_off; p.dst_layout = a->dst_layout; p.dst_mode = a->dst_mode;
   p.pool_c_total = a->pool_c_total; p.pool_c_off = a->pool_c_off;
   p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.act = a->act;
@@ -781,6 +764,60 @@ int run(const void* plan_mem, float* dst_override, float* dst2_override, cudaStr
 
 // 1 if any row-stationary conv on the current device has written an activation beyond the fp16 range since the last
 // reset (the following layer's operands were then infinite: rerun with NVS_CONV_MATH=tf32); *synchronises the device*.
+namespace nvs {
+namespace rs {
+// thread = 8 channels of one pixel
+__global__ void split16_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_pixels, int C, int fwd) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = C / 8;
+  if (i >= n_pixels * groups) return;
+  const long long px = i / groups;
+  const int g = (int)(i - px * groups);
+  if (fwd) {
+    const float4 a = reinterpret_cast<const float4*>(in + px * C + 8 * g)[0], b = reinterpret_cast<const float4*>(in + px * C + 8 * g)[1];
+    uint32_t hi[4], lo[4];
+    split_pair(a.x, a.y, hi[0], lo[0]);
+    split_pair(a.z, a.w, hi[1], lo[1]);
+    split_pair(b.x, b.y, hi[2], lo[2]);
+    split_pair(b.z, b.w, hi[3], lo[3]);
+    uint8_t* o = reinterpret_cast<uint8_t*>(out) + px * (long long)C * 4;
+    *reinterpret_cast<uint4*>(o + 16 * g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(o + 2 * C + 16 * g) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  } else {
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(in) + px * (long long)C * 4;
+    const uint4 h = *reinterpret_cast<const uint4*>(s + 16 * g), l = *reinterpret_cast<const uint4*>(s + 2 * C + 16 * g);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+      const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+      v[2 * j] = fh.x + fl.x;
+      v[2 * j + 1] = fh.y + fl.y;
+    }
+    reinterpret_cast<float4*>(out + px * C + 8 * g)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(out + px * C + 8 * g)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+static int split_launch(const float* in, float* out, long long n_pixels, int C, int fwd, cudaStream_t st) {
+  if (!in || !out || n_pixels < 0 || C <= 0 || (C % 8)) return NVS_ERR_ARG;
+  if (n_pixels == 0) return NVS_OK;
+  if (in == out) return NVS_ERR_ARG;  // a pixel's groups are read and written by different threads
+  const long long n = n_pixels * (C / 8);
+  split16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n_pixels, C, fwd);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
+}
+}  // namespace rs
+}  // namespace nvs
+
+extern "C" int nvs_split16(const float* in, float* out, int64_t n_pixels, int32_t C, void* stream) {
+  return nvs::rs::split_launch(in, out, n_pixels, C, 1, static_cast<cudaStream_t>(stream));
+}
+extern "C" int nvs_unsplit16(const float* in, float* out, int64_t n_pixels, int32_t C, void* stream) {
+  return nvs::rs::split_launch(in, out, n_pixels, C, 0, static_cast<cudaStream_t>(stream));
+}
+
 // debugging aid (tools/rs_timeline.py): device buffer of 768 clock64 stamps written by CTA 0 of every following launch
 extern "C" void nvs_conv_rs_debug_buffer(long long* dev_buf) { nvs::rs::g_dbg = dev_buf; }
 

@@ -557,6 +557,9 @@ class _KP2DTinyBase(nn.Module):
     def _pack(self) -> dict:
         P = {}
         tc = self.conv_backend == "tc"
+        # channels-last store mode of the kernels that feed tensor-core convs: 2 = split fp16 hi / lo format of the
+        # 3xFP16 kernels (NVS_CONV_MATH=f16, the default), 1 = fp32 (3xTF32 kernels)
+        self._nhwc_mode = 2 if ops.conv_math() == "f16" else 1
         bb = self.backbone
         for n in ("conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"):
             # the 3-channel stem layer stays on the FFMA kernel (K = 27 is too thin for a TMA row); conv1b
@@ -888,7 +891,7 @@ class _KP2DTinyBase(nn.Module):
         # ---- stem layer on the FFMA kernel: NCHW in, channels-last out ----
         xin = torch.empty(B, 3, H, W, device=pl.device)
         t1a = pl.buf_nhwc("t1a", c1, H, W)
-        pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a, dst_nhwc=True)
+        pl.conv(P["bb.conv1a"], xin, c1, act=act, dst=t1a, dst_nhwc=self._nhwc_mode)
         pl.in_args = pl.steps[-1][1]
         # ---- backbone on tensor cores ----
         p1 = pl.buf_nhwc("p1", c2p, H1, W1)
@@ -1008,7 +1011,7 @@ class _KP2DTinyBase(nn.Module):
         if pooled_out is not None:
             pl.conv(A["m3"], m2, C, ksize=1, out_mode=ops.OUT_POOL, dst2=pooled_out)
         else:
-            pl.conv(A["m3"], m2, C, ksize=1, dst=plain_out, dst_nhwc=plain_nhwc)
+            pl.conv(A["m3"], m2, C, ksize=1, dst=plain_out, dst_nhwc=self._nhwc_mode if plain_nhwc else 0)
 
     # --- post_processing (kp2dtiny.py:593-647 / :959-1015) ------------------------------------------
     @torch.no_grad()

@@ -95,8 +95,10 @@ def make_conv_args(src0: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, cout:
                    src1: Optional[torch.Tensor] = None, dst: Optional[torch.Tensor] = None,
                    dst2: Optional[torch.Tensor] = None, c0_off: int = 0, c0: Optional[int] = None,
                    c1_off: int = 0, c1: Optional[int] = None, dst_c_off: int = 0, dst2_c_off: int = 0,
-                   dst_nhwc: bool = False, dst2_nhwc: bool = False) -> NvsConvArgs:
-    """Fill an NvsConvArgs for (B, C, H, W) tensors; shapes are validated here, once, at plan time."""
+                   dst_nhwc: int = 0, dst2_nhwc: bool = False) -> NvsConvArgs:
+    """Fill an NvsConvArgs for (B, C, H, W) tensors; shapes are validated here, once, at plan time.
+    ``dst_nhwc``: 0 / False = NCHW, 1 / True = fp32 channels-last, 2 = the split channels-last format of the 3xFP16
+    tensor-core convs (nanovs.h: NvsConvArgs.dst_nhwc)."""
     B, c0_total, inH, inW = src0.shape
     c0 = c0_total - c0_off if c0 is None else c0
     if in_mode == IN_S2D:
@@ -751,6 +753,27 @@ class TcConvSplit(object):
             o.run(dst_override, dst2_override)
 
 
+def split16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 channels-last (..., C) -> the split format the 3xFP16 convs read and write: same shape and dtype as a
+    container, per pixel C fp16 values a_hi = fp16(a) followed by C fp16 values a_lo = fp16(a - a_hi)."""
+    x = _req(x)
+    assert x.shape[-1] % 8 == 0, x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nvs_split16(x.data_ptr(), out.data_ptr(), x.numel() // x.shape[-1], x.shape[-1], _stream()), "nvs_split16")
+    LAUNCHES[0] += 1
+    return out
+
+
+def unsplit16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Split channels-last format -> fp32 (a_hi + a_lo)."""
+    x = _req(x)
+    assert x.shape[-1] % 8 == 0, x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(lib().nvs_unsplit16(x.data_ptr(), out.data_ptr(), x.numel() // x.shape[-1], x.shape[-1], _stream()), "nvs_unsplit16")
+    LAUNCHES[0] += 1
+    return out
+
+
 def conv_rs_range_flag(reset: bool = False) -> int:
     """1 if a "3xFP16" conv on the current device wrote an activation beyond the fp16 range since the last reset (the
     following layer's operands were then not finite: switch that model to NVS_CONV_MATH=tf32).  Synchronises."""
@@ -770,7 +793,6 @@ class RsConv(object):
         assert mode != 3 or n == 1, "the keypoint-head split epilogue has 3 output channels"
         if n > 1 and kw.get("dst") is None and kw.get("dst_c_total") is None and mode != 0:
             kw["dst_c_total"] = cout // 4 if mode == 2 else cout
-        kw.pop("deterministic", None)  # single MMA issuer: always bit-reproducible
         self.ops = []
         covered = 0
         for j, (hi, lo, bp, scale, _real) in enumerate(packed.slices):
