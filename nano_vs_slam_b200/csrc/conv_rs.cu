@@ -32,8 +32,8 @@
 // bit-reproducible results.  Weights stay resident in shared memory for the whole kernel when the layer's 3 x chunks
 // tiles fit (up to 64 input channels at Cout = 64), else they stream through a ring.
 //
-// Warps: 0-7 epilogue (quadrant = warp % 4, channel half = warp / 4), 8 activation TMA, 9 weight TMA, 10-12 MMA issuers
-// (warp 10 allocates TMEM).  Persistent CTAs, one per SM.
+// Warps: Cout / 4 epilogue warps (quadrant = warp % 4, group of 16 channels = warp / 4), then the activation TMA warp,
+// the weight TMA warp and up to three MMA-issuer warps (the first allocates TMEM).  Persistent CTAs, one per SM.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -48,15 +48,9 @@ constexpr int HX = 32, HY = 6;           // halo box: positions per row (= GEMM 
 constexpr int KC = 32;                   // input channels per chunk
 constexpr int A_HALF = HX * HY * KC * 2; // one of the hi / lo operand matrices: 192 rows x 64 B
 constexpr int A_BYTES = 2 * A_HALF;
-#ifndef NVS_RS_NA
-#define NVS_RS_NA 3
-#endif
-constexpr int NA = NVS_RS_NA;            // activation chunks in flight
+constexpr int NA_MAX = 3;                // activation chunks in flight: 3, or 2 when that lets the weights stay resident
 constexpr int ACC_STAGES = 2;
-constexpr int EPI_WARPS = 8;
 constexpr int MAX_ISSUERS = 3;
-constexpr int WARP_TMA_A = EPI_WARPS, WARP_TMA_W = WARP_TMA_A + 1, WARP_MMA = WARP_TMA_W + 1;
-constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
 constexpr unsigned long long PLAN_MAGIC = 0x7273506C616E0002ull;  // first word of an rs::Plan
 
 template <int CO>
@@ -67,19 +61,29 @@ struct Cfg {
   static constexpr int W_STAGE = 2 * W_HALF;
   static constexpr bool CONCAT = CO == 32;          // a_hi x [W_hi ; W_lo] as one N = 2 NW instruction
   static constexpr int ACC_COLS = 192;              // per stage: CONCAT 2 x 96, else 192
-  static constexpr int CW = CO / 2;                 // output channels per epilogue warp
-  static constexpr int SM_A = 0;
-  static constexpr int SM_BIAS = SM_A + NA * A_BYTES;
+  // epilogue warps: TMEM lane quadrant (image row of the tile) x group of 16 output channels.  The epilogue is a chain
+  // of long-latency steps (TMEM loads, shuffles, scattered stores): it needs warps, not instructions per warp
+  static constexpr int EPI_WARPS = CO / 4;
+  static constexpr int WARP_TMA_A = EPI_WARPS, WARP_TMA_W = WARP_TMA_A + 1, WARP_MMA = WARP_TMA_W + 1;
+  static constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
+  // output staging: per TMEM lane quadrant one operand part (a_hi or a_lo, CO fp16 per position) of its 30 outputs
+  static constexpr int ROW_OUT = CO * 2;
+  static constexpr int QSTG_BYTES = ((TX * ROW_OUT + 127) / 128) * 128;
+  static constexpr int STG_BYTES = ((4 * QSTG_BYTES + 1023) / 1024) * 1024;
+  static constexpr int SM_STG = 0;
+  static constexpr int SM_BIAS = SM_STG + STG_BYTES;
   static constexpr int SM_POOL = SM_BIAS + CO * 4;
-  static constexpr int POOL_BYTES = 2 * 2 * 15 * 16 * 4;   // max-pool exchange: (channel half, quadrant pair) x 15 x 16
+  static constexpr int POOL_BYTES = (EPI_WARPS / 4) * 2 * 15 * 16 * 4;  // max-pool exchange: (channel group, quadrant pair) x 15 x 16
   static constexpr int SM_BAR = SM_POOL + POOL_BYTES;
   static constexpr int MAX_WS = 16;                  // barrier slots reserved for the weight ring
-  static constexpr int N_BARS = 2 * NA + 2 * MAX_WS + 6 + 1;
-  static constexpr int SM_W = ((SM_BAR + 8 * N_BARS + 16 + 1023) / 1024) * 1024;
-  static constexpr int MAX_W_STAGES_FIT = (227 * 1024 - 1024 - SM_W) / W_STAGE;
-  static constexpr int MAX_W_STAGES = MAX_W_STAGES_FIT < MAX_WS ? MAX_W_STAGES_FIT : MAX_WS;
-  static constexpr int smem_bytes(int w_stages) { return SM_W + w_stages * W_STAGE + 1024; }
-  static_assert(MAX_W_STAGES >= 3, "weight ring");
+  static constexpr int N_BARS = 2 * NA_MAX + 2 * MAX_WS + 6 + 1;
+  static constexpr int SM_A = ((SM_BAR + 8 * N_BARS + 16 + 1023) / 1024) * 1024;   // then `na` A slots, then the weight stages
+  static constexpr int SMEM_MAX = 227 * 1024 - 1024;
+  static constexpr int max_w_stages(int na) {
+    return (SMEM_MAX - SM_A - na * A_BYTES) / W_STAGE < MAX_WS ? (SMEM_MAX - SM_A - na * A_BYTES) / W_STAGE : MAX_WS;
+  }
+  static constexpr int smem_bytes(int na, int w_stages) { return SM_A + na * A_BYTES + w_stages * W_STAGE + 1024; }
+  static_assert(max_w_stages(NA_MAX) >= 3, "weight ring");
   static constexpr uint32_t idesc(int n) {  // kind::f16: D fp32, A / B fp16, both K-major
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   }
@@ -99,6 +103,10 @@ struct Params {
   int tiles_x, tiles_y, n_tiles;
   int nk_last0, nk_last1;  // k-steps (16 channels) of the last chunk of source 0 / 1 that can be non-zero
   int w_stages;            // weight ring depth; >= 3 * chunks means resident (every tile loaded once)
+  int na;                  // A slots (2 or 3)
+  int store_nhwc, store_pool;  // channels-last output / pooled output (split format)
+  int staged;                  // 1: through the quadrant staging buffers (coalesced lines, two barriers per part); 0:
+                               // one 32-byte store per thread and part (no barriers: better for one-chunk tiles)
   int issuers;             // MMA-issuing threads: 3, or 1 (fixed accumulation order)
   float w_scale;           // 2^-t: undoes the weights' power-of-two scale
   long long* dbg;          // nvs_conv_rs_debug_buffer: per-role clock64 stamps of CTA 0, 256 per role
@@ -184,8 +192,11 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* a) {
-  uint32_t r[16];
+// tcgen05.ld is asynchronous: tmem_ld16_issue starts a 16-column load, tmem_ld_wait waits for every load of the thread,
+// and tmem_pin (an empty volatile asm that takes the registers as read-write operands, ordered after the wait like every
+// volatile asm) keeps either compiler from moving a use of the loaded registers above the wait.  Several loads are
+// issued back to back and waited for once: a load-wait pair costs a few hundred cycles of latency.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -193,33 +204,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* a) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
 }
-// two 16-column loads (the two accumulator halves of the same channels), one wait
-__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, float* a, float* b) {
-  uint32_t r[16], q[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr_a)
-      : "memory");
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
-        "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-      : "r"(taddr_b)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    a[i] = __uint_as_float(r[i]);
-    b[i] = __uint_as_float(q[i]);
-  }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_pin(uint32_t* r) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 // one lane of the (converged) warp; the compiler then knows the guarded code is single-threaded AND that warp-uniform
 // values stay uniform, so tcgen05 operands move to uniform registers without a per-lane election loop
@@ -256,8 +248,23 @@ __device__ __forceinline__ void store_split16(float* basep, size_t pixel, int c_
     }
 }
 
+// 16 consecutive channels [c, c + 16) of one pixel of a split-format tensor, straight from registers: a_hi as ONE 32-byte
+// store (a full sector; st.global.v8.b32 is new with sm_100), a_lo as another
+__device__ __forceinline__ void store_split16_256(float* basep, size_t pixel, int c_total, int c, const float* v) {
+  uint8_t* px = reinterpret_cast<uint8_t*>(basep) + pixel * (size_t)c_total * 4;
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(px + c * 2), "r"(hi[0]), "r"(hi[1]),
+               "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
+               : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(px + (c_total + c) * 2), "r"(lo[0]),
+               "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
+               : "memory");
+}
+
 template <int CO>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__((Cfg<CO>::THREADS), 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const Params p) {
@@ -268,12 +275,14 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   float* bias_s = reinterpret_cast<float*>(sm + C::SM_BIAS);
   const uint32_t bar0 = base + C::SM_BAR;
   auto afull = [&](int i) { return bar0 + 8u * i; };
-  auto aempty = [&](int i) { return bar0 + 8u * (NA + i); };
-  auto wfull = [&](int i) { return bar0 + 8u * (2 * NA + i); };
-  auto wempty = [&](int i) { return bar0 + 8u * (2 * NA + C::MAX_WS + i); };
-  auto accfull = [&](int i) { return bar0 + 8u * (2 * NA + 2 * C::MAX_WS + i); };
-  auto accempty = [&](int i) { return bar0 + 8u * (2 * NA + 2 * C::MAX_WS + 2 + i); };
-  auto astart = [&](int i) { return bar0 + 8u * (2 * NA + 2 * C::MAX_WS + 4 + i); };
+  auto aempty = [&](int i) { return bar0 + 8u * (NA_MAX + i); };
+  auto wfull = [&](int i) { return bar0 + 8u * (2 * NA_MAX + i); };
+  auto wempty = [&](int i) { return bar0 + 8u * (2 * NA_MAX + C::MAX_WS + i); };
+  auto accfull = [&](int i) { return bar0 + 8u * (2 * NA_MAX + 2 * C::MAX_WS + i); };
+  auto accempty = [&](int i) { return bar0 + 8u * (2 * NA_MAX + 2 * C::MAX_WS + 2 + i); };
+  auto astart = [&](int i) { return bar0 + 8u * (2 * NA_MAX + 2 * C::MAX_WS + 4 + i); };
+  const int NA = p.na;
+  const uint32_t sm_w = (uint32_t)(C::SM_A + NA * A_BYTES);  // first weight stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::SM_BAR + 8 * C::N_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -282,12 +291,12 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int w_tiles = 3 * chunks;                 // (chunk, ky) weight tiles of the layer
   const bool w_resident = p.w_stages >= w_tiles;  // every tile has its own stage: loaded once
 
-  for (int i = threadIdx.x; i < CO; i += THREADS) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < CO; i += C::THREADS) bias_s[i] = p.bias[i];
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
-    for (int i = 0; i < NA; ++i) {
+    for (int i = 0; i < NA_MAX; ++i) {
       mbar_init(afull(i), 1);           // the activation TMA's expect_tx arrive
       mbar_init(aempty(i), p.issuers);  // tcgen05.commit of every issuer's MMAs of the chunk
     }
@@ -297,12 +306,12 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(accfull(i), p.issuers);
-      mbar_init(accempty(i), EPI_WARPS);
+      mbar_init(accempty(i), C::EPI_WARPS);
       mbar_init(astart(i), 1);          // issuer 0 has queued the tile's first (overwriting) MMA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == WARP_MMA) {
+  if (warp == C::WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512u)
                  : "memory");
@@ -313,9 +322,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < EPI_WARPS) {
+  if (warp < C::EPI_WARPS) {
     // =========================== epilogue ===========================
-    // quadrant (= image row of the tile) warp % 4, channel half h = warp / 4; lane = position of the 32-wide strip
+    // quadrant (= image row of the tile) warp % 4, channel group h = warp / 4 (16 channels); lane = position of the 32-wide strip
     // (lane 0 / 31 are halo positions).  Accumulator columns of a stage: [kx 0 | kx 1 | kx 2] x CO channels (CONCAT:
     // then the same three blocks of a_hi w_lo + a_lo w_hi).  out[i] = D_0[i-1] + D_1[i] + D_2[i+1].
     int acc = 0;
@@ -324,6 +333,45 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
     float seen_max = 0.f;
     int dbg_i = 0;
+    // Channels-last outputs go through a small staging buffer per TMEM lane quadrant (= image row of the tile), one
+    // operand part at a time (a_hi, then a_lo).  Written straight from the registers a warp store instruction would hit
+    // 32 different 128-byte lines with 16 bytes each (thread = pixel, pixels 4 C bytes apart): the stores, not the math,
+    // bounded the epilogue and with it most layers.  Instead the warps of a quadrant (one per 16 channels) write their
+    // 32 bytes per position into the swizzled staging rows, meet at the quadrant's named barrier, and copy the rows out
+    // with consecutive threads on consecutive 16-byte chunks: full lines.  `v`: this thread's 16 channels, `row`: its
+    // position in the staged row set (n_rows positions), `px0`: pixel index of staged row 0, `x_lim`: rows >= x_lim lie
+    // outside the image.
+    constexpr int QWARPS = C::EPI_WARPS / 4, QTHREADS = QWARPS * 32, CH = C::ROW_OUT / 16;
+    uint8_t* stg_q = sm + C::SM_STG + quad * C::QSTG_BYTES;
+    const int qtid = h * 32 + lane;
+    auto staged_store = [&](float* dstp, const float* v, bool writes, int row, int n_rows, int c_off, int c_total,
+                            size_t px0, int x_lim, bool row_ok) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+      auto key = [](int r) { return C::ROW_OUT == 128 ? (r & 7) : ((r >> 1) & 3); };
+      uint8_t* r0 = stg_q + row * C::ROW_OUT;
+      const int k0 = key(row);
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        const uint32_t* w = part ? lo : hi;
+        if (writes) {
+          *reinterpret_cast<uint4*>(r0 + (((2 * h) ^ k0) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(r0 + (((2 * h + 1) ^ k0) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
+        if (row_ok) {
+          uint8_t* gbase = reinterpret_cast<uint8_t*>(dstp) + px0 * (size_t)c_total * 4 + (size_t)(c_off + part * c_total) * 2;
+          for (int idx = qtid; idx < n_rows * CH; idx += QTHREADS) {
+            const int r = idx / CH, j = idx - r * CH;
+            if (r < x_lim)
+              *reinterpret_cast<uint4*>(gbase + (size_t)r * c_total * 4 + j * 16) =
+                  *reinterpret_cast<const uint4*>(stg_q + r * C::ROW_OUT + ((j ^ key(r)) << 4));
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
+      }
+    };
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && dbg_i < 256) p.dbg[dbg_i++] = clock64();
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
@@ -333,32 +381,39 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int part = 0; part < ((p.knock & 2) ? 0 : C::CW / 16); ++part) {
-        const int cbase = C::CW * h + 16 * part;  // first of this pass's 16 output channels
+      for (int part = 0; part < ((p.knock & 2) ? 0 : 1); ++part) {
+        const int cbase = 16 * h;  // first of this warp's 16 output channels
         if (p.dst_mode == 3 && cbase != 0) continue;  // keypoint heads: 3 channels in all
-        if (cbase >= p.cout) continue;
-        float o[16], u[16];
-        if (C::CONCAT) {
-          float w[16];
-          tmem_ld16x2(taddr + (uint32_t)cbase, taddr + (uint32_t)(C::NW + cbase), u, w);
+        // (channels beyond cout are zero weights + zero bias: a staged store writes them, as exact zeros, with the rest)
+        if (cbase >= p.cout && !(p.store_nhwc | p.store_pool)) continue;
+        float o[16];
+        {
+          uint32_t u0[16], u1[16], u2[16];
+          tmem_ld16_issue(taddr + (uint32_t)cbase, u0);
+          tmem_ld16_issue(taddr + (uint32_t)(CO + cbase), u1);
+          tmem_ld16_issue(taddr + (uint32_t)(2 * CO + cbase), u2);
+          if (C::CONCAT) {  // ... and the same three blocks of a_hi w_lo + a_lo w_hi
+            uint32_t w0[16], w1[16], w2[16];
+            tmem_ld16_issue(taddr + (uint32_t)(C::NW + cbase), w0);
+            tmem_ld16_issue(taddr + (uint32_t)(C::NW + CO + cbase), w1);
+            tmem_ld16_issue(taddr + (uint32_t)(C::NW + 2 * CO + cbase), w2);
+            tmem_ld_wait();
+            tmem_pin(u0); tmem_pin(u1); tmem_pin(u2); tmem_pin(w0); tmem_pin(w1); tmem_pin(w2);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = __shfl_up_sync(0xffffffffu, u[j] + w[j], 1);
-          tmem_ld16x2(taddr + (uint32_t)(CO + cbase), taddr + (uint32_t)(C::NW + CO + cbase), u, w);
+            for (int j = 0; j < 16; ++j) {
+              const float d0 = __uint_as_float(u0[j]) + __uint_as_float(w0[j]);
+              const float d1 = __uint_as_float(u1[j]) + __uint_as_float(w1[j]);
+              const float d2 = __uint_as_float(u2[j]) + __uint_as_float(w2[j]);
+              o[j] = __shfl_up_sync(0xffffffffu, d0, 1) + d1 + __shfl_down_sync(0xffffffffu, d2, 1);
+            }
+          } else {
+            tmem_ld_wait();
+            tmem_pin(u0); tmem_pin(u1); tmem_pin(u2);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += u[j] + w[j];
-          tmem_ld16x2(taddr + (uint32_t)(2 * CO + cbase), taddr + (uint32_t)(C::NW + 2 * CO + cbase), u, w);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += __shfl_down_sync(0xffffffffu, u[j] + w[j], 1);
-        } else {
-          tmem_ld16(taddr + (uint32_t)cbase, u);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = __shfl_up_sync(0xffffffffu, u[j], 1);
-          tmem_ld16(taddr + (uint32_t)(CO + cbase), u);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += u[j];
-          tmem_ld16(taddr + (uint32_t)(2 * CO + cbase), u);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += __shfl_down_sync(0xffffffffu, u[j], 1);
+            for (int j = 0; j < 16; ++j)
+              o[j] = __shfl_up_sync(0xffffffffu, __uint_as_float(u0[j]), 1) + __uint_as_float(u1[j]) +
+                     __shfl_down_sync(0xffffffffu, __uint_as_float(u2[j]), 1);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -382,6 +437,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) seen_max = fmaxf(seen_max, fabsf(o[j]));
         }
+        if (p.knock & 128) continue;  // experiment: everything but the stores (seen_max keeps the math alive)
         if (p.dst_pool != nullptr) {
           // MaxPool2d(2,2): x partner = next lane (strips start at even x, so pairs are lanes (1,2), (3,4), ...),
           // y partner = the row of the next quadrant's warp: odd quadrants hand their x-pooled values to the even
@@ -400,8 +456,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               reinterpret_cast<float4*>(ps + pc * 16)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
           }
           asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-          const int qx = gx >> 1, qy = gy >> 1;
-          if (!(quad & 1) && owner && qx < (p.W >> 1) && qy < (p.H >> 1)) {
+          const bool pool_owner = !(quad & 1) && owner;
+          if (pool_owner) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 r = reinterpret_cast<const float4*>(ps + pc * 16)[q];
@@ -410,14 +466,21 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               m[4 * q + 2] = fmaxf(m[4 * q + 2], r.z);
               m[4 * q + 3] = fmaxf(m[4 * q + 3], r.w);
             }
-            store_split16(p.dst_pool, ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx, p.pool_c_total, p.pool_c_off + cbase,
-                          m, p.cout - cbase);
+          }
+          // pooled row (15 positions) of the even quadrants; the odd ones have nothing to store
+          if (p.staged == 0) {
+            const int qx = gx >> 1, qy = gy >> 1;
+            if (pool_owner && qx < (p.W >> 1) && qy < (p.H >> 1))
+              store_split16_256(p.dst_pool, ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx, p.pool_c_total, p.pool_c_off + cbase, m);
+          } else if (!(quad & 1)) {
+            const int Hp = p.H >> 1, Wp = p.W >> 1, qy = gy >> 1, qx0 = tx * (TX / 2);
+            staged_store(p.dst_pool, m, owner, pc, TX / 2, p.pool_c_off + cbase - 16 * h, p.pool_c_total,
+                         ((size_t)b * Hp + qy) * Wp + qx0, Wp - qx0, qy < Hp);
           }
           asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         }
         if (valid && p.dst_mode == 1) {
-          if (p.dst_layout == 0) {  // channels-last, split format
-            store_split16(p.dst, ((size_t)b * p.H + gy) * p.W + gx, p.dst_c_total, p.dst_c_off + cbase, o, p.cout - cbase);
+          if (p.dst_layout == 0) {  // channels-last, split format: through the staging buffer (below)
           } else {  // NCHW: a warp writes 30 consecutive x of one channel row
             float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cbase) * p.H + gy) * p.W + gx;
             const size_t plane = (size_t)p.H * p.W;
@@ -425,7 +488,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int j = 0; j < 16; ++j)
               if (cbase + j < p.cout) d[j * plane] = o[j];
           }
-        } else if (valid && p.dst_mode == 2) {
+        }
+        if (p.store_nhwc && p.staged == 0) {
+          if (valid) store_split16_256(p.dst, ((size_t)b * p.H + gy) * p.W + gx, p.dst_c_total, p.dst_c_off + cbase, o);
+        } else if (p.store_nhwc)  // this quadrant's image row: 30 positions
+          staged_store(p.dst, o, lane >= 1 && lane <= TX, lane - 1, TX, p.dst_c_off + cbase - 16 * h, p.dst_c_total,
+                       ((size_t)b * p.H + gy) * p.W + tx * TX, p.W - tx * TX, gy < p.H);
+        if (valid && p.dst_mode == 2) {
           // PixelShuffle(2) -> channels-last (B, 2H, 2W, cout/4), split format: channel c -> (c%4/2, c%2, c/4)
           const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
@@ -457,7 +526,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       seen_max = warp_max(seen_max);
       if (lane == 0 && !(seen_max < 60000.f)) atomicOr(p.range_flag, 1);
     }
-  } else if (warp == WARP_TMA_A) {
+  } else if (warp == C::WARP_TMA_A) {
     // =========================== activation producer: the hi and the lo box of one chunk per A slot ===============
     if (lane == 0) {
       int as = 0;
@@ -490,7 +559,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp == WARP_TMA_W) {
+  } else if (warp == C::WARP_TMA_W) {
     // =========================== weight producer: [W_hi ; W_lo] of one (chunk, ky) per stage ===========================
     if (lane == 0 && my_tiles > 0 && !(p.knock & 64)) {
       const int rounds = w_resident ? 1 : my_tiles;
@@ -500,7 +569,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int ch = 0; ch < chunks; ++ch)
           for (int ky = 0; ky < 3; ++ky) {
             if (!w_resident) mbar_wait_relaxed(wempty(ws), wph ^ 1u);
-            const uint32_t dst = base + C::SM_W + ws * C::W_STAGE;
+            const uint32_t dst = base + sm_w + ws * C::W_STAGE;
             mbar_expect_tx(wfull(ws), C::W_STAGE);
             tma_load_3d(dst, &map_whi, wfull(ws), ch * KC, 0, ky);
             tma_load_3d(dst + C::W_HALF, &map_wlo, wfull(ws), ch * KC, 0, ky);
@@ -510,17 +579,17 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
           }
     }
-  } else if (my_tiles > 0 && warp - WARP_MMA < p.issuers) {
+  } else if (my_tiles > 0 && warp - C::WARP_MMA < p.issuers) {
     // =========================== MMA issuers ===========================
     // Issuer `me` of `nis` takes the kernel rows ky = me, me + nis, ... of every chunk.  Descriptors: the upper word is
     // the same constant for every operand (64-byte rows, SWIZZLE_64B, 8-row groups 512 B apart); the lower word is
     // (address >> 4) | LBO and is advanced by 32-bit adds of compile-time constants.  The whole warp runs the loop
     // (converged); one elected lane executes the tcgen05 / mbarrier-arrive instructions.
-    const int me = __shfl_sync(0xffffffffu, warp, 0) - WARP_MMA, nis = p.issuers;
+    const int me = __shfl_sync(0xffffffffu, warp, 0) - C::WARP_MMA, nis = p.issuers;
     constexpr uint32_t DESC_HI = (uint32_t)(512u >> 4) | (1u << 14) | (4u << 29);
     auto desc = [](uint32_t lo32) { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo32; };
     const uint32_t a_lo0 = (((base + C::SM_A) & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t w_lo0 = (((base + C::SM_W) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t w_lo0 = (((base + sm_w) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t lo_part = p.pair16 ? 2u : (uint32_t)(A_HALF >> 4);  // a_lo relative to a_hi
     int dbg_i = 0;
     int ws = me, as = 0, acc = 0;  // weight stage of my next kernel row, A slot, accumulator stage
@@ -591,7 +660,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == WARP_MMA) {
+  if (warp == C::WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -659,14 +728,34 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   const int sms = nvs_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
+  // three A slots, or two when that is what lets every weight tile of the layer stay resident (64 -> 64 channels)
   const int w_tiles = 3 * (p.c0_chunks + p.c1_chunks);
-  q.w_stages = w_tiles <= C::MAX_W_STAGES ? w_tiles : C::MAX_W_STAGES;
+  if (w_tiles <= C::max_w_stages(3)) {
+    q.na = 3;
+    q.w_stages = w_tiles;
+  } else if (w_tiles <= C::max_w_stages(2)) {
+    q.na = 2;
+    q.w_stages = w_tiles;
+  } else {
+    q.na = 3;
+    q.w_stages = C::max_w_stages(3);
+  }
+  {
+    // staged stores pay off when a tile has enough MMA work to hide the quadrant barriers (measured: 96 -> 64 channels
+    // 1.62 -> 1.46 ms, but 32 -> 32 0.50 -> 0.60 ms); NVS_RS_STORE = 1 / 2 forces staged / direct
+    static int mode = -1;
+    if (mode < 0) {
+      const char* e = getenv("NVS_RS_STORE");
+      mode = e ? atoi(e) : 0;
+    }
+    q.staged = mode == 1 ? 1 : (mode == 2 ? 0 : (p.c0_chunks + p.c1_chunks >= 3 ? 1 : 0));
+  }
   {
     const char* e = getenv("NVS_RS_KNOCK");
     q.knock = e ? atoi(e) : 0;
     q.dbg = g_dbg;
   }
-  kern<<<grid, THREADS, C::smem_bytes(q.w_stages), st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
+  kern<<<grid, C::THREADS, C::smem_bytes(q.na, q.w_stages), st>>>(pl.a0, pl.a1, pl.whi, pl.wlo, q);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
 }
@@ -716,6 +805,11 @@ int plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   if (rc != NVS_OK) return rc;
   Params& p = pl->p;
   p.bias = a->bias; p.dst = a->dst; p.dst_pool = a->dst_pool;
+  p.store_nhwc = (a->dst_mode == 1 && a->dst_layout == 0) ? 1 : 0;
+  p.store_pool = (a->dst_pool != nullptr && a->dst_mode != 3) ? 1 : 0;
+  // a staged store writes all cpad channels of the launch (padding channels as zeros)
+  if (p.store_nhwc && a->dst_c_off + cpad > a->dst_c_total) return NVS_ERR_ARG;
+  if (p.store_pool && a->pool_c_off + cpad > a->pool_c_total) return NVS_ERR_ARG;
   p.range_flag = range_flag_ptr();
   p.c0_off = a->c0_off; p.c0_chunks = c0 / KC; p.c1_off = a->c1_off; p.c1_chunks = a->c1 / KC;
   p.c0_lo = a->c0_total; p.c1_lo = a->c1_total; p.pair16 = a->c0 == 16 ? 1 : 0;
@@ -741,6 +835,8 @@ int plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.nk_last0 = a->c0 == 16 ? 1 : last_nk(c0, a->c0_real);
   p.nk_last1 = a->c1 > 0 ? last_nk(a->c1, a->c1_real) : p.nk_last0;
   p.w_stages = 0;
+  p.na = NA_MAX;
+  p.staged = 0;
   p.w_scale = a->w_scale;
   p.knock = 0;
   p.dbg = nullptr;

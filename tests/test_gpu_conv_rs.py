@@ -53,10 +53,12 @@ def test_conv_rs_plain_nhwc_and_nchw(cin, cout, H, W, act):
     assert isinstance(packed, ops.RsPacked)
     xs = _s(x)
     if cout % 8 == 0:
-        out = torch.zeros(B, H, W, cout, device="cuda")
-        ops.tc_conv(xs, packed, cout, act=act, dst=out, dst_layout=0).run()
+        cp = (cout + 31) // 32 * 32  # channels-last buffers are padded to 32 channels; the padding is written as zeros
+        out = torch.full((B, H, W, cp), 3.0, device="cuda")
+        ops.tc_conv(xs, packed, cp, act=act, dst=out, dst_layout=0).run()
         torch.cuda.synchronize()
-        assert rel_err(_u(out), ref) < 2e-5, rel_err(_u(out), ref)
+        assert rel_err(_u(out)[:, :cout], ref) < 2e-5, rel_err(_u(out)[:, :cout], ref)
+        assert cp == cout or float(_u(out)[:, cout:].abs().max()) == 0.0
     out2 = torch.zeros(B, cout, H, W, device="cuda")
     op = ops.tc_conv(xs, packed, cout, act=act, dst=None, dst_layout=1, dst_c_total=cout)
     op.run(dst_override=out2)
