@@ -75,6 +75,16 @@ def _tf32_peak(bf16_peak: float):
     return bf16_peak / 2.0, "bf16 sustained / 2 (tf32 not measured)"
 
 
+def _conv_tensor_peak(shape: str, bf16_peak: float):
+    """Ceiling for ALGORITHMIC conv FLOP/s of a tensor-core conv launch: every algorithmic FLOP costs three tensor-core
+    FLOPs (hi x hi + the two correction products).  "rs/f16" launches (csrc/conv_rs.cu) run kind::f16 MMAs: measured
+    cuBLAS bf16 sustained / 3; the 3xTF32 kernels (csrc/conv_tc.cu): measured cuBLAS tf32 sustained / 3."""
+    if "rs/f16" in shape:
+        return bf16_peak / 3.0, "measured cuBLAS bf16 sustained (MEASURED_PEAKS.json; fp16 MMAs run at the bf16 rate) / 3 (3xFP16 split)", "f16"
+    tf32_peak, tf32_src = _tf32_peak(bf16_peak)
+    return tf32_peak / 3.0, tf32_src + " / 3 (3xTF32 split)", "tf32"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -312,8 +322,8 @@ def run_other_configs(dev, world, rank, hbm_peak, bf16_peak, which):
             flops += 4.0 * c5 * (n1 * (n1 // 4) + n2 * (n2 // 4))
         fps = world * b * sp["steps"] / (ms / 1e3)
         fps_gpu = fps / world
-        tf32_peak, tf32_src = _tf32_peak(bf16_peak)
-        peak = tf32_peak / 3.0
+        tc_shapes = [v["shape"] for v in plan.meta.values() if "tcgen05" in v.get("shape", "")]
+        peak, peak_src, _ = _conv_tensor_peak(tc_shapes[0] if tc_shapes else "", bf16_peak)
         out.append({
             "config": sp["config"], "value": fps, "unit": "frames/s", "ms_per_step": ms / sp["steps"],
             "steps": sp["steps"], "warmup": 3, "batch_per_gpu": b,
@@ -323,7 +333,7 @@ def run_other_configs(dev, world, rank, hbm_peak, bf16_peak, which):
                            if sp.get("vo") else "") + f", batch {b} x {h}x{w} per GPU",
             "roofline": {"bound": "tensor", "achieved": fps_gpu * flops / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": fps_gpu * flops / 1e12 / peak, "traffic": None,
-                         "peak_source": tf32_src + " / 3 (3xTF32 split)",
+                         "peak_source": peak_src,
                          "note": "whole step: algorithmic conv" + (" + attention" if m.use_attention else "") +
                                  " FLOPs per frame x frames/s (the attention core and the first layer run on the fp32 "
                                  "pipe, so the tensor ceiling is an upper bound for them)",
@@ -555,27 +565,27 @@ def main():
     ach_gbs = heavy_meta["bytes"] / (kern_ms / 1e3) / 1e9
     ach_tf = heavy_meta["flops"] / (kern_ms / 1e3) / 1e12
     traffic, traffic_batch = None, None
-    tr = _traffic("conv_tc_96_64_120x160")
+    tr = _traffic("conv_rs_96_64_120x160" if "rs/f16" in heavy_meta["shape"] else "conv_tc_96_64_120x160")
     if tr and "96->64 k3 @120x160" in heavy_meta["shape"]:
         traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]  # ncu capture at batch 256, linear in batch
         traffic_batch = tr["batch"]
     if "tcgen05" in heavy_meta["shape"]:
-        # 3xTF32: every algorithmic FLOP costs three tf32 tensor-core FLOPs, so the ceiling for ALGORITHMIC FLOP/s
-        # is the (measured) dense tf32 peak / 3.
-        tf32_peak, tf32_src = _tf32_peak(bf16_peak)
-        peak_tf = tf32_peak / 3.0
+        # three tensor-core FLOPs per algorithmic FLOP: the ceiling for ALGORITHMIC FLOP/s is the measured dense peak
+        # of the MMA kind / 3
+        peak_tf, peak_src, kind = _conv_tensor_peak(heavy_meta["shape"], bf16_peak)
         roofline = {
-            "kernel": f"conv_tc_kernel {heavy_meta['shape']} (B={B})", "bound": "tensor",
+            "kernel": f"{'conv_rs_kernel' if kind == 'f16' else 'conv_tc_kernel'} {heavy_meta['shape']} (B={B})", "bound": "tensor",
             "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
             "traffic_note": (f"DRAM bytes/launch from ncu --set full at batch {traffic_batch} "
-                             f"(profiles/r1_traffic.json) x B/{traffic_batch}; " if traffic is not None else "") +
+                             f"(profiles/r{'2' if kind == 'f16' else '1'}_traffic.json) x B/{traffic_batch}; " if traffic is not None else "") +
                             f"algorithmic bytes/launch = {heavy_meta['bytes']:.0f}",
-            "peak_source": tf32_src + " / 3 (3xTF32 split)", "kernel_ms": kern_ms,
-            "mma_tflops_executed": 3.0 * ach_tf, "tf32_peak_tflops": tf32_peak,
-            "frac_of_bf16_sustained_over_6": ach_tf / (bf16_peak / 6.0),
+            "peak_source": peak_src, "kernel_ms": kern_ms,
+            "mma_tflops_executed": 3.0 * ach_tf, "mma_kind": kind, "mma_peak_tflops": 3.0 * peak_tf,
             "hbm_gbs_at_algorithmic_bytes": ach_gbs, "hbm_frac_at_algorithmic_bytes": ach_gbs / hbm_peak,
-            "note": "implicit-GEMM conv on tcgen05 (kind::tf32, A via TMEM, 3xTF32 for fp32-grade accuracy); "
-                    "achieved = algorithmic conv FLOPs / kernel time",
+            "note": ("row-stationary implicit-GEMM conv on tcgen05 (kind::f16, fp16 hi / lo operand pairs from shared "
+                     "memory, 3xFP16 for fp32-grade accuracy)" if kind == "f16" else
+                     "implicit-GEMM conv on tcgen05 (kind::tf32, A via TMEM, 3xTF32 for fp32-grade accuracy)") +
+                    "; achieved = algorithmic conv FLOPs / kernel time",
         }
     else:
         roofline = {
@@ -630,6 +640,9 @@ def main():
                          "ms_per_step": e2e_ms / args.steps}, **e2e_stats),
             "e2e_uint8_frames": e2e_u8,
             "gpu_launches": launches, "cuda_graph": bool(plan.graph is not None), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            # arithmetic of the tensor-core convs: "f16" = 3xFP16 row-stationary kernels (one MMA-issuing thread: results
+            # are bit-reproducible run to run), "tf32" = 3xTF32 kernels (NVS_CONV_MATH)
+            "conv_math": __import__("nano_vs_slam_b200.ops", fromlist=["conv_math"]).conv_math(),
         }
         line.update(extra)
         emit(line)

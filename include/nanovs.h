@@ -287,6 +287,18 @@ int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32
                    float fy, float cx, float cy, float threshold, int32_t iters, uint64_t seed, int32_t refine,
                    float* out_E, float* out_R, float* out_t, uint8_t* out_mask, int32_t* out_inliers, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* The same with a data-dependent sample count (cv2.findEssentialMat's prob = 0.999, visual_odometry.py:392): samples are
+ * drawn in rounds of round_size; after each round a pair whose sample count has reached log(1 - confidence) /
+ * log(1 - w^5) -- w = the inlier ratio implied by its best truncated cost so far (a lower bound) -- is finished and
+ * skipped by the following rounds, up to max_iters samples.  out_iters (P, may be NULL): samples evaluated per pair.
+ * Same sample sequence as nvs_pose_batch: a pair that stops after m samples returns what nvs_pose_batch returns with
+ * iters = m.  Workspace as nvs_pose_workspace_bytes(n_pairs, kmax, max_iters). */
+int nvs_pose_batch_adaptive(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a,
+                            const int32_t* pair_b, const int32_t* idx1, const int32_t* idx2, const int32_t* count,
+                            int32_t n_pairs, float fx, float fy, float cx, float cy, float threshold, int32_t max_iters,
+                            uint64_t seed, int32_t refine, float confidence, int32_t round_size, float* out_E,
+                            float* out_R, float* out_t, uint8_t* out_mask, int32_t* out_inliers, int32_t* out_iters,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- exact L2 top-k retrieval = faiss.IndexFlatL2.add / .search (evaluation/global_descriptor.py:55-60) ----
  * add:    nvs_flat_prepare converts the fp32 rows (n,d) to fp16 rows padded to nvs_flat_padded_dim(d) columns (the

@@ -88,6 +88,8 @@ SIGNATURES = {
     "nvs_pose_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "nvs_pose_batch": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _i32, _u64,
                                _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nvs_pose_batch_adaptive": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _i32,
+                                        _u64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nvs_flat_padded_dim": (_i32, [_i32]),
     "nvs_flat_max_k": (_i32, []),
     "nvs_flat_prepare": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),

@@ -54,10 +54,12 @@ __global__ void __launch_bounds__(256) pose_gather_kernel(PoseIn in, float2* __r
 __global__ void __launch_bounds__(32) pose_hypotheses_kernel(const float2* __restrict__ cur, const float2* __restrict__ ref,
                                                              const int32_t* __restrict__ count, int kmax, int iters,
                                                              unsigned long long seed, float* __restrict__ cand,
-                                                             int32_t* __restrict__ ncand) {
+                                                             int32_t* __restrict__ ncand, int it0, int it1,
+                                                             const int32_t* __restrict__ done) {
+  // samples [it0, it1) of every pair that has not reached its adaptive sample count yet (done == nullptr: all)
   const int p = blockIdx.y;
-  const int it = blockIdx.x * blockDim.x + threadIdx.x;
-  if (it >= iters) return;
+  const int it = it0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= it1 || (done != nullptr && done[p])) return;
   int n = count[p];
   n = n > kmax ? kmax : n;
   const size_t h = (size_t)p * iters + it;
@@ -84,10 +86,12 @@ __global__ void __launch_bounds__(SCORE_T) pose_score_kernel(const float2* __res
                                                              const int32_t* __restrict__ count, int kmax, int iters,
                                                              float thr2, const float* __restrict__ cand,
                                                              const int32_t* __restrict__ ncand,
-                                                             unsigned long long* __restrict__ score) {
+                                                             unsigned long long* __restrict__ score, int it0,
+                                                             const int32_t* __restrict__ done) {
   __shared__ float Es[POSE_MAX_CAND * 9];
   __shared__ unsigned long long red[SCORE_T / 32][POSE_MAX_CAND];
-  const int p = blockIdx.y, it = blockIdx.x;
+  const int p = blockIdx.y, it = it0 + blockIdx.x;
+  if (done != nullptr && done[p]) return;
   const size_t h = (size_t)p * iters + it;
   const int nc = ncand[h];
   unsigned long long* sc = score + h * POSE_MAX_CAND;
@@ -133,13 +137,57 @@ __global__ void __launch_bounds__(SCORE_T) pose_score_kernel(const float2* __res
   }
 }
 
+// Adaptive stopping (cv2.findEssentialMat's prob argument, visual_odometry.py:392: prob = 0.999): after the samples
+// [it0, it1) of a round have been scored, one CTA per pair updates the pair's best truncated cost; the inlier ratio is
+// bounded from below by w = 1 - cost / n (an inlier contributes less than one unit), the standard RANSAC sample count for
+// confidence c is N = log(1 - c) / log(1 - w^5), and the pair is finished once it1 >= N.  Finished pairs are skipped by
+// the following rounds (their hypotheses / score CTAs exit at once); `used` = samples the select step has to scan.
+__global__ void __launch_bounds__(128) pose_adapt_kernel(const int32_t* __restrict__ count, int kmax, int iters, int it0,
+                                                         int it1, float confidence,
+                                                         const unsigned long long* __restrict__ score,
+                                                         unsigned long long* __restrict__ best, int32_t* __restrict__ done,
+                                                         int32_t* __restrict__ used) {
+  __shared__ unsigned long long s_min[128];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  if (done[p]) return;
+  unsigned long long m = ~0ull;
+  for (int h = it0 * POSE_MAX_CAND + tid; h < it1 * POSE_MAX_CAND; h += 128) {
+    const unsigned long long s = score[(size_t)p * iters * POSE_MAX_CAND + h];
+    m = s < m ? s : m;
+  }
+  s_min[tid] = m;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o && s_min[tid + o] < s_min[tid]) s_min[tid] = s_min[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    unsigned long long b = best[p];
+    if (s_min[0] < b) b = s_min[0];
+    best[p] = b;
+    used[p] = it1;
+    int n = count[p];
+    n = n > kmax ? kmax : n;
+    if (n < 5) {
+      done[p] = 1;  // nothing to estimate
+    } else if (b != ~0ull) {
+      double w = 1.0 - (double)b / ((double)n * (double)POSE_SCORE_ONE);
+      w = w < 1e-3 ? 1e-3 : (w > 1.0 - 1e-9 ? 1.0 - 1e-9 : w);
+      const double w5 = w * w * w * w * w;
+      const double need = log(1.0 - (double)confidence) / log(1.0 - w5);
+      if ((double)it1 >= need) done[p] = 1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SELECT_T) pose_select_kernel(const float2* __restrict__ cur, const float2* __restrict__ ref,
                                                                const int32_t* __restrict__ count, int kmax, int iters,
                                                                float thr2, const float* __restrict__ cand,
                                                                const unsigned long long* __restrict__ score,
                                                                float* __restrict__ out_E, float* __restrict__ out_R,
                                                                float* __restrict__ out_t, uint8_t* __restrict__ out_mask,
-                                                               int32_t* __restrict__ out_inliers) {
+                                                               int32_t* __restrict__ out_inliers,
+                                                               const int32_t* __restrict__ used) {
   __shared__ unsigned long long s_best[SELECT_T];
   __shared__ int s_arg[SELECT_T];
   __shared__ float s_E[9];
@@ -149,10 +197,11 @@ __global__ void __launch_bounds__(SELECT_T) pose_select_kernel(const float2* __r
   const int p = blockIdx.x, tid = threadIdx.x;
   int n = count[p];
   n = n < 0 ? 0 : (n > kmax ? kmax : n);
-  const int total = iters * POSE_MAX_CAND;
+  const int total = iters * POSE_MAX_CAND;  // row pitch of the score / candidate arrays
+  const int scan = (used != nullptr ? used[p] : iters) * POSE_MAX_CAND;  // samples actually evaluated for this pair
   unsigned long long best = ~0ull;
   int arg = total;
-  for (int h = tid; h < total; h += SELECT_T) {
+  for (int h = tid; h < scan; h += SELECT_T) {
     const unsigned long long s = score[(size_t)p * total + h];
     if (s < best) { best = s; arg = h; }
   }
@@ -323,15 +372,15 @@ extern "C" size_t nvs_pose_workspace_bytes(int32_t n_pairs, int32_t kmax, int32_
   if (n_pairs <= 0 || kmax <= 0 || iters <= 0) return 0;
   const size_t P = (size_t)n_pairs, K = (size_t)kmax, I = (size_t)iters;
   return 2 * align256(P * K * 8) + align256(P * I * POSE_MAX_CAND * 9 * 4) + align256(P * I * 4) +
-         align256(P * I * POSE_MAX_CAND * 8) + 256;
+         align256(P * I * POSE_MAX_CAND * 8) + align256(P * 8) + 2 * align256(P * 4) + 256;
 }
 
-extern "C" int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a,
-                              const int32_t* pair_b, const int32_t* idx1, const int32_t* idx2, const int32_t* count,
-                              int32_t n_pairs, float fx, float fy, float cx, float cy, float threshold, int32_t iters,
-                              uint64_t seed, int32_t refine, float* out_E, float* out_R, float* out_t,
-                              uint8_t* out_mask, int32_t* out_inliers, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+static int pose_batch_impl(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a,
+                           const int32_t* pair_b, const int32_t* idx1, const int32_t* idx2, const int32_t* count,
+                           int32_t n_pairs, float fx, float fy, float cx, float cy, float threshold, int32_t iters,
+                           uint64_t seed, int32_t refine, float confidence, int32_t round_size, float* out_E, float* out_R,
+                           float* out_t, uint8_t* out_mask, int32_t* out_inliers, int32_t* out_iters, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   if (!pts || !pair_a || !pair_b || !count || !out_E || !out_R || !out_t || !out_mask || !out_inliers || !workspace)
     return NVS_ERR_ARG;
   if ((idx1 == nullptr) != (idx2 == nullptr)) return NVS_ERR_ARG;
@@ -346,17 +395,42 @@ extern "C" int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, 
   float2* ref = reinterpret_cast<float2*>(w); w += align256(P * K * 8);
   float* cand = reinterpret_cast<float*>(w); w += align256(P * I * POSE_MAX_CAND * 9 * 4);
   int32_t* ncand = reinterpret_cast<int32_t*>(w); w += align256(P * I * 4);
-  unsigned long long* score = reinterpret_cast<unsigned long long*>(w);
+  unsigned long long* score = reinterpret_cast<unsigned long long*>(w); w += align256(P * I * POSE_MAX_CAND * 8);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(w); w += align256(P * 8);
+  int32_t* done = reinterpret_cast<int32_t*>(w); w += align256(P * 4);
+  int32_t* used = reinterpret_cast<int32_t*>(w);
   PoseIn in{pts, pair_a, pair_b, idx1, idx2, count, kmax, fx, fy, cx, cy};
   pose_gather_kernel<<<dim3((kmax + 255) / 256, n_pairs), 256, 0, st>>>(in, cur, ref);
   NVS_CHECK_LAUNCH();
-  pose_hypotheses_kernel<<<dim3((iters + 31) / 32, n_pairs), 32, 0, st>>>(cur, ref, count, kmax, iters, seed, cand, ncand);
-  NVS_CHECK_LAUNCH();
   const float thr2 = threshold * threshold;
-  pose_score_kernel<<<dim3(iters, n_pairs), SCORE_T, 0, st>>>(cur, ref, count, kmax, iters, thr2, cand, ncand, score);
-  NVS_CHECK_LAUNCH();
+  const bool adaptive = confidence > 0.f;
+  if (!adaptive) {
+    pose_hypotheses_kernel<<<dim3((iters + 31) / 32, n_pairs), 32, 0, st>>>(cur, ref, count, kmax, iters, seed, cand, ncand,
+                                                                            0, iters, nullptr);
+    NVS_CHECK_LAUNCH();
+    pose_score_kernel<<<dim3(iters, n_pairs), SCORE_T, 0, st>>>(cur, ref, count, kmax, iters, thr2, cand, ncand, score, 0,
+                                                                nullptr);
+    NVS_CHECK_LAUNCH();
+  } else {
+    // rounds of `round_size` samples; a pair drops out once its sample count reaches the RANSAC bound for `confidence`
+    cudaMemsetAsync(best, 0xFF, P * 8, st);
+    cudaMemsetAsync(done, 0, P * 4, st);
+    cudaMemsetAsync(used, 0, P * 4, st);
+    for (int it0 = 0; it0 < iters; it0 += round_size) {
+      const int it1 = it0 + round_size < iters ? it0 + round_size : iters, r = it1 - it0;
+      pose_hypotheses_kernel<<<dim3((r + 31) / 32, n_pairs), 32, 0, st>>>(cur, ref, count, kmax, iters, seed, cand, ncand,
+                                                                        it0, it1, done);
+      NVS_CHECK_LAUNCH();
+      pose_score_kernel<<<dim3(r, n_pairs), SCORE_T, 0, st>>>(cur, ref, count, kmax, iters, thr2, cand, ncand, score, it0,
+                                                              done);
+      NVS_CHECK_LAUNCH();
+      pose_adapt_kernel<<<n_pairs, 128, 0, st>>>(count, kmax, iters, it0, it1, confidence, score, best, done, used);
+      NVS_CHECK_LAUNCH();
+    }
+    if (out_iters) cudaMemcpyAsync(out_iters, used, P * 4, cudaMemcpyDeviceToDevice, st);
+  }
   pose_select_kernel<<<n_pairs, SELECT_T, 0, st>>>(cur, ref, count, kmax, iters, thr2, cand, score, out_E, out_R, out_t,
-                                                   out_mask, out_inliers);
+                                                   out_mask, out_inliers, adaptive ? used : nullptr);
   NVS_CHECK_LAUNCH();
   if (refine > 0) {
     pose_refine_kernel<<<n_pairs, REFINE_T, 0, st>>>(cur, ref, count, kmax, thr2, refine, out_E, out_R, out_t, out_mask,
@@ -364,4 +438,28 @@ extern "C" int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, 
     NVS_CHECK_LAUNCH();
   }
   return NVS_OK;
+}
+
+extern "C" int nvs_pose_batch(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a,
+                              const int32_t* pair_b, const int32_t* idx1, const int32_t* idx2, const int32_t* count,
+                              int32_t n_pairs, float fx, float fy, float cx, float cy, float threshold, int32_t iters,
+                              uint64_t seed, int32_t refine, float* out_E, float* out_R, float* out_t,
+                              uint8_t* out_mask, int32_t* out_inliers, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  return pose_batch_impl(pts, n_frames, kmax, pair_a, pair_b, idx1, idx2, count, n_pairs, fx, fy, cx, cy, threshold, iters,
+                         seed, refine, 0.f, 0, out_E, out_R, out_t, out_mask, out_inliers, nullptr, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int nvs_pose_batch_adaptive(const float* pts, int32_t n_frames, int32_t kmax, const int32_t* pair_a,
+                                       const int32_t* pair_b, const int32_t* idx1, const int32_t* idx2,
+                                       const int32_t* count, int32_t n_pairs, float fx, float fy, float cx, float cy,
+                                       float threshold, int32_t max_iters, uint64_t seed, int32_t refine, float confidence,
+                                       int32_t round_size, float* out_E, float* out_R, float* out_t, uint8_t* out_mask,
+                                       int32_t* out_inliers, int32_t* out_iters, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  if (!(confidence > 0.f && confidence < 1.f) || round_size <= 0) return NVS_ERR_ARG;
+  return pose_batch_impl(pts, n_frames, kmax, pair_a, pair_b, idx1, idx2, count, n_pairs, fx, fy, cx, cy, threshold,
+                         max_iters, seed, refine, confidence, round_size, out_E, out_R, out_t, out_mask, out_inliers,
+                         out_iters, workspace, workspace_bytes, stream);
 }

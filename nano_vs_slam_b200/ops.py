@@ -419,8 +419,14 @@ def match_batch(desc: torch.Tensor, counts: torch.Tensor, pair_a: torch.Tensor, 
 def pose_batch(pts: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor, count: torch.Tensor,
                idx1: Optional[torch.Tensor] = None, idx2: Optional[torch.Tensor] = None,
                intrinsics: Sequence[float] = (1.0, 1.0, 0.0, 0.0), threshold: float = 0.0003, iters: int = 512,
-               seed: int = 0, refine: int = 0, workspace: Optional[torch.Tensor] = None):
+               seed: int = 0, refine: int = 0, workspace: Optional[torch.Tensor] = None, confidence: float = 0.0,
+               round_size: int = 64):
     """Relative pose of P frame pairs in one call (visual_odometry.py:383-412: findEssentialMat + recoverPose).
+
+    ``confidence`` > 0 (the reference passes prob = 0.999): data-dependent sample count -- samples are drawn in rounds of
+    ``round_size`` and a pair stops once its count reaches the RANSAC bound for its best consensus so far, at most
+    ``iters`` samples; the result then carries "iters" (P,) int32, the samples evaluated per pair.  0 (default): exactly
+    ``iters`` samples per pair (fixed cost; what bench.py times).
 
     ``pts`` (F,kmax,2) keypoint coordinates as written by select_keypoints, ``pair_a`` (current) / ``pair_b``
     (reference) (P,) frame indices, ``idx1`` / ``idx2`` / ``count`` as returned by match_batch (both idx None: the
@@ -450,6 +456,16 @@ def pose_batch(pts: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor, co
     mask = torch.empty(P, kmax, device=dev, dtype=torch.uint8)
     inl = torch.empty(P, device=dev, dtype=torch.int32)
     fx, fy, cx, cy = (float(v) for v in intrinsics)
+    if confidence > 0.0:
+        used = torch.empty(P, device=dev, dtype=torch.int32)
+        check(lib().nvs_pose_batch_adaptive(pts.data_ptr(), F_, kmax, pair_a.data_ptr(), pair_b.data_ptr(), _ptr(idx1),
+                                            _ptr(idx2), count.data_ptr(), P, fx, fy, cx, cy, float(threshold), int(iters),
+                                            int(seed) & 0xFFFFFFFFFFFFFFFF, int(refine), float(confidence),
+                                            int(round_size), E.data_ptr(), R.data_ptr(), t.data_ptr(), mask.data_ptr(),
+                                            inl.data_ptr(), used.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                            _stream()), "nvs_pose_batch_adaptive")
+        LAUNCHES[0] += 2 + 3 * ((iters + round_size - 1) // round_size) + (1 if refine > 0 else 0)
+        return {"E": E, "R": R, "t": t, "mask": mask, "inliers": inl, "iters": used}
     check(lib().nvs_pose_batch(pts.data_ptr(), F_, kmax, pair_a.data_ptr(), pair_b.data_ptr(), _ptr(idx1), _ptr(idx2),
                                count.data_ptr(), P, fx, fy, cx, cy, float(threshold), int(iters),
                                int(seed) & 0xFFFFFFFFFFFFFFFF, int(refine), E.data_ptr(), R.data_ptr(), t.data_ptr(),
