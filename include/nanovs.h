@@ -325,6 +325,19 @@ int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, 
                     const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset, float* out_D, int64_t* out_I,
                     void* workspace, size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop,
                     void* stream);
+/* The same search in two calls, for a database sharded over several GPUs (queries replicated): _begin runs the GEMM
+ * and publishes, per query, out_bound[q] = an upper bound of this shard's k-th smallest EXACT distance (+inf when fewer
+ * than k rows are listed); the caller reduces it with MIN over the shards (one allreduce of nq floats) and passes the
+ * result to _end, which re-ranks only the rows that can still be among the GLOBAL k nearest: the fp32 re-rank (a
+ * gather of whole rows) then shrinks with the number of shards like the GEMM does.  A shard that holds fewer than k such
+ * rows pads its list with (+inf, -1); nvs_topk_merge of the shard lists is the exact global result.  Same workspace
+ * for both calls (it carries the per-row lists), same stream order. */
+int nvs_flat_search_begin(const float* db, const void* db_f16, const float* db_norms, const float* db_stats, int64_t n_db,
+                          const float* q, int32_t nq, int32_t d, int32_t k, float* out_bound, void* workspace,
+                          size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop, void* stream);
+int nvs_flat_search_end(const float* db, const void* db_f16, const float* db_norms, const float* db_stats, int64_t n_db,
+                        const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset, const float* global_bound,
+                        float* out_D, int64_t* out_I, void* workspace, size_t workspace_bytes, void* stream);
 int nvs_topk_merge(const float* D_parts, const int64_t* I_parts, int32_t parts, int32_t nq, int32_t k,
                    int64_t part_stride_d, int64_t part_stride_i, float* out_D, int64_t* out_I, void* stream);
 

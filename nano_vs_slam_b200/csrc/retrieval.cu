@@ -526,12 +526,19 @@ __device__ __forceinline__ float ord_float(uint32_t k) {
 // Per query: tau~ = exact k-th smallest s~ over the n_strips * L listed rows (radix select on the ordered bit
 // pattern), candidates = every listed row with s~ <= tau~ + 2 eps, flag = the lists may be missing a row that also
 // satisfies that (a strip list full of such rows) or there are more candidates than CAP.
+// Sharded search: out_u != nullptr -> only publish u = tau~ + eps (this shard holds k rows with EXACT distance <= u, so
+// the global k-th exact distance is <= the minimum B of u over the shards) and return; ext_bound = that minimum B ->
+// a row of the global top-k has exact distance <= B, hence s~ <= B + eps: the cut becomes min(tau~ + 2 eps, B + eps)
+// and a shard re-ranks only what can still matter globally (on average k + a few rows over ALL shards instead of per
+// shard: the fp32 re-rank, a gather of 16 KB rows, is the part of a sharded search that does not shrink otherwise).
 __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __restrict__ cand_d,
                                                                 const int32_t* __restrict__ cand_i, int n_strips,
                                                                 int L, int k, const float* __restrict__ qslack,
                                                                 int32_t* __restrict__ sel_i, int32_t* __restrict__ sel_n,
                                                                 int32_t* __restrict__ flag_count,
-                                                                int32_t* __restrict__ flag_list) {
+                                                                int32_t* __restrict__ flag_list,
+                                                                const float* __restrict__ ext_bound,
+                                                                float* __restrict__ out_u) {
   extern __shared__ uint8_t sraw[];
   const int n_cand = n_strips * L;
   float* sd = reinterpret_cast<float*>(sraw);
@@ -577,6 +584,11 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __r
     }
     T = ord_float(s_prefix) + qslack[q];
   }
+  if (out_u != nullptr) {  // first phase of a sharded search
+    if (tid == 0) out_u[q] = T - 0.5f * qslack[q];  // tau~ + eps (+inf: fewer than k rows listed)
+    return;
+  }
+  if (ext_bound != nullptr) T = fminf(T, ext_bound[q] + 0.5f * qslack[q]);
   // candidates inside the slack (order irrelevant: the re-rank orders by exact distance, then id)
   for (int i = tid; i < n_cand; i += 256) {
     if (si[i] >= 0 && sd[i] <= T) {
@@ -942,11 +954,16 @@ extern "C" size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int3
   return make_layout(n_db, nq, d, k).total;
 }
 
-extern "C" int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,
-                               int64_t n_db, const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset,
-                               float* out_D, int64_t* out_I, void* workspace, size_t workspace_bytes,
-                               void* ev_gemm_start, void* ev_gemm_stop, void* stream) {
-  if (!db || !db_f16 || !db_norms || !db_stats || !q || !out_D || !out_I || !workspace) return NVS_ERR_ARG;
+// phase 1: query conversion, GEMM + per-row lists [, u = tau~ + eps per query]; phase 2: selection [inside the global
+// bound], fp32 re-rank, exact scan of flagged queries.  The workspace carries the lists between the phases.
+static int flat_search_impl(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,
+                            int64_t n_db, const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset,
+                            float* out_D, int64_t* out_I, void* workspace, size_t workspace_bytes, void* ev_gemm_start,
+                            void* ev_gemm_stop, void* stream, int phase /* 0 both, 1 begin, 2 end */, float* out_u,
+                            const float* ext_bound) {
+  if (!db || !db_f16 || !db_norms || !db_stats || !q || !workspace) return NVS_ERR_ARG;
+  if (phase != 1 && (!out_D || !out_I)) return NVS_ERR_ARG;
+  if (phase == 1 && !out_u) return NVS_ERR_ARG;
   if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0) return NVS_ERR_ARG;
   if (k > KMAX) return NVS_ERR_UNSUPPORTED;   // per-row lists live in shared memory
   if (k > n_db) return NVS_ERR_ARG;
@@ -967,41 +984,50 @@ extern "C" int nvs_flat_search(const float* db, const void* db_f16, const float*
   int32_t* sn = reinterpret_cast<int32_t*>(ws + L.off_sn);
   int32_t* fl = reinterpret_cast<int32_t*>(ws + L.off_fl);
   int* lk = reinterpret_cast<int*>(ws + L.off_lk);
-
-  // queries -> fp16 (rows past nq stay zero: they only feed padded accumulator rows that are never flushed);
-  // flag counter + list and the scan locks (adjacent in the workspace) start at zero
-  cudaError_t e = cudaMemsetAsync(qb, 0, (size_t)L.qpad * L.dpad * 2, st);
-  if (e != cudaSuccess) return nvs_set_cuda_error(e);
-  e = cudaMemsetAsync(fl, 0, (L.off_lk - L.off_fl) + al256((size_t)nq * 4), st);
-  if (e != cudaSuccess) return nvs_set_cuda_error(e);
-  q_to_f16_kernel<<<(nq + 7) / 8, 256, 0, st>>>(q, qb, qn, qc, qs, db_stats, nq, d, L.dpad);
-  NVS_CHECK_LAUNCH();
-  fill_inf_kernel<<<(L.qpad + 255) / 256, 256, 0, st>>>(gb, L.qpad);
-  NVS_CHECK_LAUNCH();
-
-  CUtensorMap mq, mx;
-  if (make_map(&mq, qb, (uint64_t)L.qpad, (uint64_t)L.dpad, BM) != NVS_OK) return NVS_ERR_CUDA;
-  if (make_map(&mx, db_f16, (uint64_t)n_db, (uint64_t)L.dpad, BN / 2) != NVS_OK) return NVS_ERR_CUDA;  // half tiles
-
-  Params p;
-  p.xnorm = db_norms; p.qcoef = qc; p.qslack = qs; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
-  p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
-  p.k = k; p.L = L.L; p.lp = L.L | 1;
-  p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;
-  p.n_mpair = (L.n_mblk + 1) / 2;
-  const int n_units = p.n_mpair * L.n_strips;  // work units of CTA pairs
-
-  if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
-  int rc = L.stages == 4 ? launch_gemm<4>(mq, mx, p, n_units, st)
-                         : (L.stages == 3 ? launch_gemm<3>(mq, mx, p, n_units, st) : launch_gemm<2>(mq, mx, p, n_units, st));
-  if (rc != NVS_OK) return rc;
-  if (ev_gemm_stop) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_stop), st);
-
   const int n_cand = L.n_strips * L.L;
   NVS_OPT_IN_SMEM(select_candidates_kernel, 96 * 1024);
+
+  if (phase != 2) {
+    // queries -> fp16 (rows past nq stay zero: they only feed padded accumulator rows that are never flushed);
+    // flag counter + list and the scan locks (adjacent in the workspace) start at zero
+    cudaError_t e = cudaMemsetAsync(qb, 0, (size_t)L.qpad * L.dpad * 2, st);
+    if (e != cudaSuccess) return nvs_set_cuda_error(e);
+    e = cudaMemsetAsync(fl, 0, (L.off_lk - L.off_fl) + al256((size_t)nq * 4), st);
+    if (e != cudaSuccess) return nvs_set_cuda_error(e);
+    q_to_f16_kernel<<<(nq + 7) / 8, 256, 0, st>>>(q, qb, qn, qc, qs, db_stats, nq, d, L.dpad);
+    NVS_CHECK_LAUNCH();
+    fill_inf_kernel<<<(L.qpad + 255) / 256, 256, 0, st>>>(gb, L.qpad);
+    NVS_CHECK_LAUNCH();
+
+    CUtensorMap mq, mx;
+    if (make_map(&mq, qb, (uint64_t)L.qpad, (uint64_t)L.dpad, BM) != NVS_OK) return NVS_ERR_CUDA;
+    if (make_map(&mx, db_f16, (uint64_t)n_db, (uint64_t)L.dpad, BN / 2) != NVS_OK) return NVS_ERR_CUDA;  // half tiles
+
+    Params p;
+    p.xnorm = db_norms; p.qcoef = qc; p.qslack = qs; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
+    p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
+    p.k = k; p.L = L.L; p.lp = L.L | 1;
+    p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;
+    p.n_mpair = (L.n_mblk + 1) / 2;
+    const int n_units = p.n_mpair * L.n_strips;  // work units of CTA pairs
+
+    if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
+    int rc = L.stages == 4 ? launch_gemm<4>(mq, mx, p, n_units, st)
+                           : (L.stages == 3 ? launch_gemm<3>(mq, mx, p, n_units, st) : launch_gemm<2>(mq, mx, p, n_units, st));
+    if (rc != NVS_OK) return rc;
+    if (ev_gemm_stop) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_stop), st);
+    if (phase == 1) {
+      select_candidates_kernel<<<nq, 256, (size_t)n_cand * 8, st>>>(cd, ci, L.n_strips, L.L, k, qs, si, sn, fl, fl + 1,
+                                                                    nullptr, out_u);
+      NVS_CHECK_LAUNCH();
+      return NVS_OK;
+    }
+  }
+
   NVS_OPT_IN_SMEM(rerank_kernel, 96 * 1024);
   NVS_OPT_IN_SMEM(exact_scan_kernel, 96 * 1024);
-  select_candidates_kernel<<<nq, 256, (size_t)n_cand * 8, st>>>(cd, ci, L.n_strips, L.L, k, qs, si, sn, fl, fl + 1);
+  select_candidates_kernel<<<nq, 256, (size_t)n_cand * 8, st>>>(cd, ci, L.n_strips, L.L, k, qs, si, sn, fl, fl + 1,
+                                                                ext_bound, nullptr);
   NVS_CHECK_LAUNCH();
   rerank_kernel<<<nq, 256, (size_t)(d + CAP) * 4, st>>>(q, db, db_norms, si, sn, k, d, (long long)id_offset, out_D, out_I);
   NVS_CHECK_LAUNCH();
@@ -1012,6 +1038,31 @@ extern "C" int nvs_flat_search(const float* db, const void* db_f16, const float*
                                                                         out_D, out_I);
   NVS_CHECK_LAUNCH();
   return NVS_OK;
+}
+
+extern "C" int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,
+                               int64_t n_db, const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset,
+                               float* out_D, int64_t* out_I, void* workspace, size_t workspace_bytes,
+                               void* ev_gemm_start, void* ev_gemm_stop, void* stream) {
+  return flat_search_impl(db, db_f16, db_norms, db_stats, n_db, q, nq, d, k, id_offset, out_D, out_I, workspace,
+                          workspace_bytes, ev_gemm_start, ev_gemm_stop, stream, 0, nullptr, nullptr);
+}
+
+extern "C" int nvs_flat_search_begin(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,
+                                     int64_t n_db, const float* q, int32_t nq, int32_t d, int32_t k, float* out_bound,
+                                     void* workspace, size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop,
+                                     void* stream) {
+  return flat_search_impl(db, db_f16, db_norms, db_stats, n_db, q, nq, d, k, 0, nullptr, nullptr, workspace,
+                          workspace_bytes, ev_gemm_start, ev_gemm_stop, stream, 1, out_bound, nullptr);
+}
+
+extern "C" int nvs_flat_search_end(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,
+                                   int64_t n_db, const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset,
+                                   const float* global_bound, float* out_D, int64_t* out_I, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!global_bound) return NVS_ERR_ARG;
+  return flat_search_impl(db, db_f16, db_norms, db_stats, n_db, q, nq, d, k, id_offset, out_D, out_I, workspace,
+                          workspace_bytes, nullptr, nullptr, stream, 2, nullptr, global_bound);
 }
 
 extern "C" int nvs_topk_merge(const float* D_parts, const int64_t* I_parts, int32_t parts, int32_t nq, int32_t k,

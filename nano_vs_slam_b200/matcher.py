@@ -104,7 +104,8 @@ def match_consecutive(sel: dict, cross_check: bool = False, ratio_test: float = 
 
 
 def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_test: float = kRatioTest,
-                     threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0):
+                     threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0,
+                     confidence: float = 0.0):
     """Matching AND relative pose for a batch of consecutive frames without a host round trip
     (visual_odometry.py:314-345: match frame t against t-1, then estimatePose :383-412).
 
@@ -116,7 +117,7 @@ def pose_consecutive(sel: dict, intrinsics, cross_check: bool = False, ratio_tes
     i1, i2, dd, cnt = torch.ops.nanovs.match_batch(sel["desc"], sel["count"], a, a - 1, float(ratio_test),
                                                    1 if cross_check else 0)
     pose = torch_ops.pose_batch(sel["pts"], a, a - 1, cnt, i1, i2, intrinsics=intrinsics, threshold=threshold,
-                                iters=iters, seed=seed, refine=refine)
+                                iters=iters, seed=seed, refine=refine, confidence=confidence)
     return (i1, i2, dd, cnt), pose
 
 
@@ -126,9 +127,12 @@ class PoseEstimator(object):
     reference's PinholeCamera); lens distortion is not handled here (KITTI frames are rectified: D = 0)."""
 
     def __init__(self, cam, threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0,
-                 device: str = "cuda"):
+                 device: str = "cuda", prob: float = 0.0):
+        """``prob`` > 0 (the reference passes 0.999, visual_odometry.py:392): stop sampling once the RANSAC confidence
+        bound for the best consensus so far is reached (at most ``iters`` samples); 0: always ``iters`` samples."""
         self.cam = cam
         self.threshold, self.iters, self.seed, self.refine, self.device = threshold, iters, seed, refine, device
+        self.prob = prob
         self.mask_match = None
         self.E = None
 
@@ -141,7 +145,8 @@ class PoseEstimator(object):
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
         out = torch_ops.pose_batch(pts, zero, zero + 1, torch.full((1,), n, dtype=torch.int32, device=self.device),
                                    intrinsics=(self.cam.fx, self.cam.fy, self.cam.cx, self.cam.cy),
-                                   threshold=self.threshold, iters=self.iters, seed=self.seed, refine=self.refine)
+                                   threshold=self.threshold, iters=self.iters, seed=self.seed, refine=self.refine,
+                                   confidence=self.prob)
         self.mask_match = out["mask"][0].cpu().numpy().reshape(-1, 1)
         self.E = out["E"][0].cpu().numpy().astype(np.float64)
         return out["R"][0].cpu().numpy().astype(np.float64), out["t"][0].cpu().numpy().astype(np.float64).reshape(3, 1)

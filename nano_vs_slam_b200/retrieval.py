@@ -8,9 +8,10 @@ of everything inside the error bound, the fp32 re-rank and (for queries the list
 (csrc/retrieval.cu): the result is the fp32 result.
 numpy in -> numpy out (like faiss); CUDA tensors in -> CUDA tensors out.
 
-ShardedIndexFlatL2 row-shards the database over the ranks of a torch.distributed process group: every rank
-searches its shard with global ids, ONE all_gather moves the packed (Q,k) distances + labels (NCCL over NVLink on
-GPUs), and every rank merges world_size*k candidates per query.
+ShardedIndexFlatL2 row-shards the database over the ranks of a torch.distributed process group: every rank runs the
+GEMM on its shard, an allreduce(MIN) of nq floats agrees on a bound of the global k-th distance, every rank re-ranks
+only its rows inside that bound (global ids), ONE all_gather moves the packed (Q,k) distances + labels (NCCL over NVLink
+on GPUs), and every rank merges world_size*k candidates per query.
 """
 from __future__ import annotations
 
@@ -95,6 +96,67 @@ class IndexFlatL2(object):
               "nvs_flat_search")
         ops.LAUNCHES[0] += 6  # query conversion, bound fill, GEMM + lists, selection, re-rank, exact scan
         return D, I
+
+    # --- two-phase search of one shard of a sharded database (nanovs.h: nvs_flat_search_begin / _end) -------------
+    def _workspace(self, nq: int, k: int) -> torch.Tensor:
+        nbytes = int(lib().nvs_flat_search_workspace_bytes(self.ntotal, nq, self.d, k))
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _begin_impl(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        gemm_events = getattr(self, "_gemm_events", None)
+        assert self.ntotal > 0, "empty index"
+        if k > KMAX:
+            raise NotImplementedError(f"k <= {KMAX} (per-row lists live in shared memory)")
+        if k > self.ntotal:
+            raise ValueError(f"k = {k} > ntotal = {self.ntotal}")
+        nq = q.shape[0]
+        ws = self._workspace(nq, k)
+        bound = torch.empty(nq, dtype=torch.float32, device=self.device)
+        e0 = e1 = None
+        if gemm_events is not None:
+            for ev in gemm_events:
+                ev.record()
+            e0, e1 = gemm_events[0].cuda_event, gemm_events[1].cuda_event
+        check(lib().nvs_flat_search_begin(self._x.data_ptr(), self._xb.data_ptr(), self._xn.data_ptr(), self._st.data_ptr(),
+                                          self.ntotal, q.data_ptr(), nq, self.d, k, bound.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), e0, e1, ops._stream()), "nvs_flat_search_begin")
+        ops.LAUNCHES[0] += 4  # query conversion, bound fill, GEMM + lists, k-th value per query
+        return bound
+
+    def _end_impl(self, q: torch.Tensor, k: int, bound: torch.Tensor, id_offset: int = 0):
+        nq = q.shape[0]
+        out = getattr(self, "_out", None)
+        if out is not None:
+            D, I = out
+        else:
+            D = torch.empty(nq, k, dtype=torch.float32, device=self.device)
+            I = torch.empty(nq, k, dtype=torch.int64, device=self.device)
+        ws = self._workspace(nq, k)
+        check(lib().nvs_flat_search_end(self._x.data_ptr(), self._xb.data_ptr(), self._xn.data_ptr(), self._st.data_ptr(),
+                                        self.ntotal, q.data_ptr(), nq, self.d, k, id_offset, bound.data_ptr(),
+                                        D.data_ptr(), I.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()),
+              "nvs_flat_search_end")
+        ops.LAUNCHES[0] += 3  # selection, re-rank, exact scan
+        return D, I
+
+    def search_begin(self, q: torch.Tensor, k: int, gemm_events=None) -> torch.Tensor:
+        """Phase 1 (torch.ops.nanovs.flat_l2_begin): GEMM + lists; returns, per query, an upper bound of this shard's
+        k-th smallest exact distance -- reduce it with MIN over the shards before search_end."""
+        self._gemm_events = gemm_events
+        try:
+            return torch.ops.nanovs.flat_l2_begin(q, torch_ops.register_index(self), int(k))
+        finally:
+            self._gemm_events = None
+
+    def search_end(self, q: torch.Tensor, k: int, bound: torch.Tensor, id_offset: int = 0, out=None):
+        """Phase 2 (torch.ops.nanovs.flat_l2_end): re-rank of the rows that can still be among the global k nearest."""
+        self._out = out
+        try:
+            return torch.ops.nanovs.flat_l2_end(q, bound, torch_ops.register_index(self), int(k), int(id_offset))
+        finally:
+            self._out = None
 
     def search(self, q, k: int):
         qd, was_np = _as_dev(q, self.device)
@@ -189,8 +251,11 @@ class ShardedIndexFlatL2(object):
         mine = torch.empty(1, words, dtype=torch.int64, device=dev)
         Dm, Im = self._packed_views(mine, 1, nq, k)
         if self._index is not None:
-            self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo,
-                                      gemm_events=gemm_events, out=(Dm[0], Im[0]))
+            # two phases around one tiny allreduce: every shard re-ranks only the rows inside the GLOBAL k-th bound
+            qd = q.to(self.device, torch.float32).contiguous()
+            bound = self._index.search_begin(qd, k, gemm_events=gemm_events)
+            self.dist.all_reduce(bound, op=self.dist.ReduceOp.MIN, group=self.group)
+            self._index.search_end(qd, k, bound, id_offset=self.lo, out=(Dm[0], Im[0]))
         else:
             D, I = self._local_search(self._shard, q, k, self.lo)
             Dm[0].copy_(D)

@@ -200,8 +200,33 @@ _define("pose_batch(Tensor pts, Tensor pair_a, Tensor pair_b, Tensor count, Tens
         "-> (Tensor, Tensor, Tensor, Tensor, Tensor)", _pose_cuda, _pose_fake)
 
 
+def _pose_adaptive_cuda(pts, pair_a, pair_b, count, idx1, idx2, intrinsics: Sequence[float], threshold: float, iters: int,
+                        seed: int, refine: int, confidence: float, round_size: int):
+    r = ops.pose_batch(pts, pair_a, pair_b, count, idx1, idx2, intrinsics=tuple(intrinsics), threshold=threshold,
+                       iters=iters, seed=seed, refine=refine, confidence=confidence, round_size=round_size)
+    return r["E"], r["R"], r["t"], r["mask"], r["inliers"], r["iters"]
+
+
+def _pose_adaptive_fake(pts, pair_a, pair_b, count, idx1, idx2, intrinsics: Sequence[float], threshold: float, iters: int,
+                        seed: int, refine: int, confidence: float, round_size: int):
+    P = pair_a.shape[0]
+    return _pose_fake(pts, pair_a, pair_b, count, idx1, idx2, intrinsics, threshold, iters, seed, refine) + \
+        (pts.new_empty(P, dtype=torch.int32),)
+
+
+_define("pose_batch_adaptive(Tensor pts, Tensor pair_a, Tensor pair_b, Tensor count, Tensor? idx1, Tensor? idx2, "
+        "float[] intrinsics, float threshold, int iters, int seed, int refine, float confidence, int round_size) "
+        "-> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", _pose_adaptive_cuda, _pose_adaptive_fake)
+
+
 def pose_batch(pts, pair_a, pair_b, count, idx1=None, idx2=None, intrinsics=(1.0, 1.0, 0.0, 0.0),
-               threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0) -> dict:
+               threshold: float = 0.0003, iters: int = 512, seed: int = 0, refine: int = 0, confidence: float = 0.0,
+               round_size: int = 64) -> dict:
+    if confidence > 0.0:
+        E, R, t, mask, inl, used = torch.ops.nanovs.pose_batch_adaptive(
+            pts, pair_a, pair_b, count, idx1, idx2, [float(v) for v in intrinsics], float(threshold), int(iters),
+            int(seed), int(refine), float(confidence), int(round_size))
+        return {"E": E, "R": R, "t": t, "mask": mask, "inliers": inl, "iters": used}
     E, R, t, mask, inl = torch.ops.nanovs.pose_batch(pts, pair_a, pair_b, count, idx1, idx2,
                                                      [float(v) for v in intrinsics], float(threshold), int(iters),
                                                      int(seed), int(refine))
@@ -242,6 +267,25 @@ def _merge_fake(D_parts, I_parts):
     return D_parts.new_empty(nq, k), I_parts.new_empty(nq, k)
 
 
+def _flat_begin_cuda(q, handle: int, k: int):
+    return _INDEXES[handle]._begin_impl(q, k)
+
+
+def _flat_begin_fake(q, handle: int, k: int):
+    return q.new_empty(q.shape[0])
+
+
+def _flat_end_cuda(q, bound, handle: int, k: int, id_offset: int):
+    return _INDEXES[handle]._end_impl(q, k, bound, id_offset)
+
+
+def _flat_end_fake(q, bound, handle: int, k: int, id_offset: int):
+    return q.new_empty(q.shape[0], k), q.new_empty(q.shape[0], k, dtype=torch.int64)
+
+
+_define("flat_l2_begin(Tensor q, int index, int k) -> Tensor", _flat_begin_cuda, _flat_begin_fake)
+_define("flat_l2_end(Tensor q, Tensor bound, int index, int k, int id_offset) -> (Tensor, Tensor)", _flat_end_cuda,
+        _flat_end_fake)
 _define("topk_merge(Tensor D_parts, Tensor I_parts) -> (Tensor, Tensor)", _merge_cuda, _merge_fake)
 
 
@@ -282,6 +326,45 @@ def _conv_tc_fake(src0, src1, w_hi, w_lo, bias, cout: int, act: int, dst_mode: i
 
 _define("conv_tc(Tensor src0, Tensor? src1, Tensor w_hi, Tensor w_lo, Tensor bias, int cout, int act, int dst_mode, "
         "int dst_layout, bool pool) -> (Tensor, Tensor)", _conv_tc_cuda, _conv_tc_fake)
+
+
+def _conv_rs_cuda(src0, src1, w_hi, w_lo, bias, w_scale: float, cout: int, act: int, dst_mode: int, dst_layout: int,
+                  pool: bool):
+    """One <= 64-channel slice of a 3x3 conv on the "3xFP16" row-stationary kernel (csrc/conv_rs.cu).  src0 / src1 and
+    the channels-last outputs are in the SPLIT format (nanovs::split16 / unsplit16); (w_hi, w_lo, bias, w_scale) = one
+    entry of ops.pack_conv_rs(...).slices.  dst_mode / dst_layout / pool as conv_tc."""
+    B, H, W, _ = src0.shape
+    cpad = bias.numel()
+    if dst_mode == 2:
+        dst = src0.new_zeros(B, 2 * H, 2 * W, (cout // 4 + 7) // 8 * 8)
+    elif dst_layout == 1:
+        dst = src0.new_empty(B, cout, H, W)
+    else:
+        dst = src0.new_zeros(B, H, W, cpad)
+    dpool = src0.new_zeros(B, H // 2, W // 2, cpad) if pool else None
+    op = ops.TcConv(src0, (w_hi, w_lo, bias), cout if dst_layout == 1 or dst_mode == 2 else cpad, act=act, src1=src1,
+                    dst=dst, dst_layout=dst_layout, dst_mode=dst_mode, dst_pool=dpool, rs_scale=w_scale)
+    op.run()
+    return dst, (dpool if pool else src0.new_empty(0))
+
+
+def _conv_rs_fake(src0, src1, w_hi, w_lo, bias, w_scale: float, cout: int, act: int, dst_mode: int, dst_layout: int,
+                  pool: bool):
+    B, H, W, _ = src0.shape
+    cpad = bias.numel()
+    if dst_mode == 2:
+        dst = src0.new_empty(B, 2 * H, 2 * W, (cout // 4 + 7) // 8 * 8)
+    elif dst_layout == 1:
+        dst = src0.new_empty(B, cout, H, W)
+    else:
+        dst = src0.new_empty(B, H, W, cpad)
+    return dst, (src0.new_empty(B, H // 2, W // 2, cpad) if pool else src0.new_empty(0))
+
+
+_define("conv_rs(Tensor src0, Tensor? src1, Tensor w_hi, Tensor w_lo, Tensor bias, float w_scale, int cout, int act, "
+        "int dst_mode, int dst_layout, bool pool) -> (Tensor, Tensor)", _conv_rs_cuda, _conv_rs_fake)
+_define("split16(Tensor x) -> Tensor", lambda x: ops.split16(x), lambda x: torch.empty_like(x))
+_define("unsplit16(Tensor x) -> Tensor", lambda x: ops.unsplit16(x), lambda x: torch.empty_like(x))
 
 
 def _conv_cuda(src, weight, bias, cout: int, ksize: int, act: int):

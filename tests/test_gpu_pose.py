@@ -156,3 +156,39 @@ def test_pose_refinement_matches_host_harness():
         c0 = np.minimum(sampson_sq(base["E"][p].cpu().numpy(), cur, ref), thr2).sum()
         c1 = np.minimum(sampson_sq(E[p], cur, ref), thr2).sum()
         assert c1 <= c0 * (1 + 1e-5), (i, c0, c1)
+
+
+def test_pose_adaptive_sample_count():
+    """confidence = 0.999 (the reference's prob): clean scenes stop after the first round(s), a pair that stops after m
+    samples returns exactly what the fixed-count call returns with iters = m (same sample sequence), and the estimate
+    stays within the golden tolerances."""
+    from nano_vs_slam_b200 import ops
+
+    z = np.load(GOLD)
+    idxs = list(range(int(z["n_cases"])))
+    P = len(idxs)
+    pts, cnt, kmax = _batch(z, idxs)
+    a = torch.arange(P, dtype=torch.int32, device="cuda")
+    out = ops.pose_batch(pts, a, a + P, cnt, threshold=0.0003, iters=512, seed=7, confidence=0.999, round_size=32)
+    used = out["iters"].cpu().numpy()
+    assert (used % 32 == 0).all() and (used >= 32).all() and (used <= 512).all()
+    assert used.min() < 512  # at least the noise-free scenes (>= 70 % inliers) finish early
+    again = ops.pose_batch(pts, a, a + P, cnt, threshold=0.0003, iters=512, seed=7, confidence=0.999, round_size=32)
+    for k in out:
+        assert torch.equal(out[k], again[k]), k
+    R, t, inl = out["R"].cpu().numpy(), out["t"].cpu().numpy(), out["inliers"].cpu().numpy()
+    for p, i in enumerate(idxs):
+        fixed = ops.pose_batch(pts, a, a + P, cnt, threshold=0.0003, iters=int(used[p]), seed=7)
+        for k in ("E", "R", "t", "mask", "inliers"):
+            assert torch.equal(out[k][p], fixed[k][p]), (i, k)
+        dR, dt = rot_angle_deg(R[p], z[f"R_cv{i}"]), dir_angle_deg(t[p], z[f"t_cv{i}"])
+        if float(z[f"noise{i}"]) == 0.0:
+            assert dR < 2e-3 and dt < 0.01, (i, dR, dt, used[p])
+        else:
+            assert dR < 0.3 and dt < 4.0, (i, dR, dt, used[p])
+            assert 0.8 < inl[p] / z[f"mask_cv{i}"].sum() < 1.2
+    # through the custom operator
+    from nano_vs_slam_b200 import torch_ops
+
+    o2 = torch_ops.pose_batch(pts, a, a + P, cnt, threshold=0.0003, iters=512, seed=7, confidence=0.999, round_size=32)
+    assert torch.equal(o2["iters"], out["iters"]) and torch.equal(o2["R"], out["R"])

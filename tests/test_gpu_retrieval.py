@@ -195,3 +195,51 @@ def test_flat_l2_numpy_api_and_sharded_merge():
     np.testing.assert_allclose(Dm.cpu().numpy(), Dr.numpy(), rtol=1e-4, atol=2e-6)
     Dc, Ic = merge_topk_device(Dg.contiguous(), Ig.contiguous())  # plain [parts][nq][k] layout
     assert torch.equal(Ic, Im) and torch.equal(Dc, Dm)
+
+
+@gpu
+@pytest.mark.parametrize("shards", [2, 5])
+def test_flat_l2_two_phase_sharded_search_is_exact(shards):
+    """nvs_flat_search_begin / _end (the per-shard path of ShardedIndexFlatL2 on GPUs): the shards agree on a bound of the
+    global k-th distance (MIN of their own bounds) and re-rank only what lies inside it; merged, the result is the
+    single-index result -- on planted data bit for bit, on clustered data (near ties across the shards) the exact set --
+    and each shard re-ranks far fewer rows than k."""
+    from nano_vs_slam_b200.retrieval import IndexFlatL2, merge_topk_device, shard_bounds
+    from nano_vs_slam_b200.synthetic import planted_retrieval_set
+
+    k = 25
+    for kind in ("planted", "cluster"):
+        if kind == "planted":
+            db, q, planted = planted_retrieval_set(40000, 300, 256, k, seed=3, device="cuda")
+        else:
+            g = torch.Generator(device="cuda").manual_seed(9)
+            cen = torch.nn.functional.normalize(torch.randn(300, 128, generator=g, device="cuda"), dim=1)
+            db = cen[torch.randint(0, 300, (30000,), generator=g, device="cuda")] + 1e-3 * torch.randn(30000, 128, generator=g, device="cuda")
+            q = cen[torch.randint(0, 300, (200,), generator=g, device="cuda")] + 2e-3 * torch.randn(200, 128, generator=g, device="cuda")
+        n, d = db.shape
+        whole = IndexFlatL2(d)
+        whole.add(db)
+        Dw, Iw = whole.search(q, k)
+        parts, bounds = [], []
+        for r in range(shards):
+            lo, hi = shard_bounds(n, shards, r)
+            ix = IndexFlatL2(d)
+            ix.add(db[lo:hi].contiguous())
+            parts.append((ix, lo))
+            bounds.append(ix.search_begin(q, k))
+        gb = torch.stack(bounds).min(0).values
+        Ds, Is = [], []
+        for ix, lo in parts:
+            D, I = ix.search_end(q, k, gb, id_offset=lo)
+            Ds.append(D)
+            Is.append(I)
+        Dm, Im = merge_topk_device(torch.stack(Ds), torch.stack(Is))
+        torch.cuda.synchronize()
+        if kind == "planted":
+            assert torch.equal(Im, Iw) and torch.equal(Im.cpu(), planted.cpu())
+            assert torch.equal(Dm, Dw)
+        else:
+            _check_exact(Im, Dm, _exact64(db, q), k, tol=2e-6)
+        # the point of the exchange: the shards together re-rank about k rows per query, not k each
+        kept = sum(int((I >= 0).sum()) for I in Is) / (q.shape[0] * k)
+        assert kept < 1.6, kept

@@ -11,8 +11,8 @@ import torch.nn.functional as F
 from util import rel_err
 
 EXPECTED = {"kp2dtiny_forward", "decode", "seg_argmax", "select_keypoints", "match", "match_batch", "pose_batch",
-            "flat_l2_search", "topk_merge", "conv_tc", "conv", "attention", "netvlad", "channel_layernorm", "dwconv3x3",
-            "softmax_channels", "preprocess_u8"}
+            "pose_batch_adaptive", "flat_l2_search", "flat_l2_begin", "flat_l2_end", "topk_merge", "conv_tc", "conv_rs", "split16", "unsplit16", "conv",
+            "attention", "netvlad", "channel_layernorm", "dwconv3x3", "softmax_channels", "preprocess_u8"}
 
 
 def _model(letter="S", ncls=28, v3=False):
@@ -139,6 +139,31 @@ def test_conv_tc_op_matches_fp32_conv(cin, cout, pool):
         assert rel_err(pooled.permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
     else:
         assert pooled.numel() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,pool", [(64, 64, False), (32, 32, True), (96, 64, False), (16, 32, True)])
+def test_conv_rs_op_matches_fp32_conv(cin, cout, pool):
+    """torch.ops.nanovs.conv_rs (3xFP16, split-format activations) vs F.conv2d in fp32."""
+    from nano_vs_slam_b200 import ops
+
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, 24, 40, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    hi, lo, bp, scale, _ = ops.pack_conv_rs(w.cuda(), bias=b.cuda()).slices[0]
+    xs = torch.ops.nanovs.split16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    dst, pooled = torch.ops.nanovs.conv_rs(xs, None, hi, lo, bp, scale, cout, ops.ACT_LRELU, 1, 1, pool)
+    assert rel_err(dst, ref) < 2e-5
+    dst2, _ = torch.ops.nanovs.conv_rs(xs, None, hi, lo, bp, scale, cout, ops.ACT_LRELU, 1, 0, False)
+    assert rel_err(torch.ops.nanovs.unsplit16(dst2).permute(0, 3, 1, 2), ref) < 2e-5
+    if pool:
+        assert rel_err(torch.ops.nanovs.unsplit16(pooled).permute(0, 3, 1, 2), F.max_pool2d(ref, 2, 2)) < 2e-5
+    else:
+        assert pooled.numel() == 0
+    with pytest.raises(NotImplementedError):
+        torch.ops.nanovs.split16(torch.zeros(1, 4, 4, 8))
 
 
 @pytest.mark.gpu
