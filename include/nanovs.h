@@ -326,15 +326,18 @@ int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, 
                     void* workspace, size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop,
                     void* stream);
 /* The same search in two calls, for a database sharded over several GPUs (queries replicated): _begin runs the GEMM
- * and publishes, per query, out_bound[q] = an upper bound of this shard's k-th smallest EXACT distance (+inf when fewer
- * than k rows are listed); the caller reduces it with MIN over the shards (one allreduce of nq floats) and passes the
- * result to _end, which re-ranks only the rows that can still be among the GLOBAL k nearest: the fp32 re-rank (a
- * gather of whole rows) then shrinks with the number of shards like the GEMM does.  A shard that holds fewer than k such
- * rows pads its list with (+inf, -1); nvs_topk_merge of the shard lists is the exact global result.  Same workspace
- * for both calls (it carries the per-row lists), same stream order. */
+ * and publishes, per query, out_bounds[q][0..k) = upper bounds of the EXACT distances of this shard's k best listed rows
+ * (unordered, +inf padding); the caller gathers them from all shards (one allgather of nq*k floats per shard) and
+ * nvs_flat_bound_merge takes the k-th smallest of the union per query: an upper bound of the GLOBAL k-th distance.
+ * _end then re-ranks only the rows that can still be among the global k nearest: the fp32 re-rank (a gather of whole
+ * rows) shrinks with the number of shards like the GEMM does.  A shard that holds fewer than k such rows pads its list
+ * with (+inf, -1); nvs_topk_merge of the shard lists is the exact global result.  Same workspace for _begin and _end
+ * (it carries the per-row lists), same stream order. */
 int nvs_flat_search_begin(const float* db, const void* db_f16, const float* db_norms, const float* db_stats, int64_t n_db,
-                          const float* q, int32_t nq, int32_t d, int32_t k, float* out_bound, void* workspace,
+                          const float* q, int32_t nq, int32_t d, int32_t k, float* out_bounds, void* workspace,
                           size_t workspace_bytes, void* ev_gemm_start, void* ev_gemm_stop, void* stream);
+int nvs_flat_bound_merge(const float* bounds /* (parts, nq, k) */, int32_t parts, int32_t nq, int32_t k,
+                         float* out_bound /* (nq) */, void* stream);
 int nvs_flat_search_end(const float* db, const void* db_f16, const float* db_norms, const float* db_stats, int64_t n_db,
                         const float* q, int32_t nq, int32_t d, int32_t k, int64_t id_offset, const float* global_bound,
                         float* out_D, int64_t* out_I, void* workspace, size_t workspace_bytes, void* stream);

@@ -97,6 +97,7 @@ SIGNATURES = {
     "nvs_flat_search": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _vp, _vp,
                                 _vp]),
     "nvs_flat_search_begin": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "nvs_flat_bound_merge": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "nvs_flat_search_end": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nvs_topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
 }

@@ -526,11 +526,13 @@ __device__ __forceinline__ float ord_float(uint32_t k) {
 // Per query: tau~ = exact k-th smallest s~ over the n_strips * L listed rows (radix select on the ordered bit
 // pattern), candidates = every listed row with s~ <= tau~ + 2 eps, flag = the lists may be missing a row that also
 // satisfies that (a strip list full of such rows) or there are more candidates than CAP.
-// Sharded search: out_u != nullptr -> only publish u = tau~ + eps (this shard holds k rows with EXACT distance <= u, so
-// the global k-th exact distance is <= the minimum B of u over the shards) and return; ext_bound = that minimum B ->
-// a row of the global top-k has exact distance <= B, hence s~ <= B + eps: the cut becomes min(tau~ + 2 eps, B + eps)
-// and a shard re-ranks only what can still matter globally (on average k + a few rows over ALL shards instead of per
-// shard: the fp32 re-rank, a gather of 16 KB rows, is the part of a sharded search that does not shrink otherwise).
+// Sharded search: out_u != nullptr -> only publish, per query, u_j = s~_j + eps for the shard's k smallest listed s~
+// (unordered; +inf padding) and return: every u_j is an upper bound of the EXACT distance of a distinct row, so the
+// k-th smallest B of the union of all shards' u (kth_union_kernel, after one all_gather of (nq,k) floats) is >= the
+// global k-th exact distance.  ext_bound = B: a row of the global top-k has exact distance <= B, hence s~ <= B + eps:
+// the cut becomes min(tau~ + 2 eps, B + eps) and a shard re-ranks only what can still matter globally (about k + a few
+// rows over ALL shards instead of per shard: the fp32 re-rank, a gather of 16 KB rows, is the part of a sharded
+// search that does not shrink otherwise).
 __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __restrict__ cand_d,
                                                                 const int32_t* __restrict__ cand_i, int n_strips,
                                                                 int L, int k, const float* __restrict__ qslack,
@@ -584,8 +586,19 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __r
     }
     T = ord_float(s_prefix) + qslack[q];
   }
-  if (out_u != nullptr) {  // first phase of a sharded search
-    if (tid == 0) out_u[q] = T - 0.5f * qslack[q];  // tau~ + eps (+inf: fewer than k rows listed)
+  if (out_u != nullptr) {  // first phase of a sharded search: the k smallest s~ (+ eps), unordered
+    const float eps = 0.5f * qslack[q];
+    const float tau = T - qslack[q];  // +inf: at most k rows listed, publish them all
+    float* o = out_u + (size_t)q * k;
+    for (int i = tid; i < n_cand; i += 256) {
+      if (si[i] >= 0 && sd[i] < tau) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < k) o[pos] = sd[i] + eps;
+      }
+    }
+    __syncthreads();
+    const int c = s_cnt < k ? s_cnt : k;  // strictly below tau~: at most k - 1; the rest of the k smallest equal tau~
+    for (int j = c + tid; j < k; j += 256) o[j] = tau + eps;
     return;
   }
   if (ext_bound != nullptr) T = fminf(T, ext_bound[q] + 0.5f * qslack[q]);
@@ -611,6 +624,38 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __r
     sel_n[q] = cnt < CAP ? cnt : CAP;
     if (s_flag || cnt > CAP) flag_list[atomicAdd(flag_count, 1)] = q;
   }
+}
+
+// Per query: B = k-th smallest of the parts * k published bounds (radix select, as above; +inf entries sort last).
+__global__ void __launch_bounds__(256) kth_union_kernel(const float* __restrict__ u, int parts, int nq, int k,
+                                                        float* __restrict__ out_b) {
+  extern __shared__ float su[];
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  const int q = blockIdx.x, tid = threadIdx.x, n = parts * k;
+  for (int i = tid; i < n; i += 256) su[i] = u[((size_t)(i / k) * nq + q) * k + (i % k)];
+  if (tid == 0) { s_prefix = 0; s_remaining = k; }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const uint32_t mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < n; i += 256) {
+      const uint32_t key = ord_key(su[i]);
+      if ((key & mask) == (prefix & mask)) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining, b = 0;
+      while (b < 255 && hist[b] < rem) rem -= hist[b++];
+      s_remaining = rem;
+      s_prefix = prefix | ((uint32_t)b << shift);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) out_b[q] = ord_float(s_prefix);
 }
 
 // Exact fp32 q.x of one row by one warp (all lanes return the sum).  The summation order is part of the result: the
@@ -1054,6 +1099,14 @@ extern "C" int nvs_flat_search_begin(const float* db, const void* db_f16, const 
                                      void* stream) {
   return flat_search_impl(db, db_f16, db_norms, db_stats, n_db, q, nq, d, k, 0, nullptr, nullptr, workspace,
                           workspace_bytes, ev_gemm_start, ev_gemm_stop, stream, 1, out_bound, nullptr);
+}
+
+extern "C" int nvs_flat_bound_merge(const float* bounds, int32_t parts, int32_t nq, int32_t k, float* out_bound,
+                                    void* stream) {
+  if (!bounds || !out_bound || parts <= 0 || parts > 64 || nq <= 0 || k <= 0 || k > KMAX) return NVS_ERR_ARG;
+  kth_union_kernel<<<nq, 256, (size_t)parts * k * 4, static_cast<cudaStream_t>(stream)>>>(bounds, parts, nq, k, out_bound);
+  NVS_CHECK_LAUNCH();
+  return NVS_OK;
 }
 
 extern "C" int nvs_flat_search_end(const float* db, const void* db_f16, const float* db_norms, const float* db_stats,

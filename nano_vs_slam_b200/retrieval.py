@@ -9,9 +9,9 @@ of everything inside the error bound, the fp32 re-rank and (for queries the list
 numpy in -> numpy out (like faiss); CUDA tensors in -> CUDA tensors out.
 
 ShardedIndexFlatL2 row-shards the database over the ranks of a torch.distributed process group: every rank runs the
-GEMM on its shard, an allreduce(MIN) of nq floats agrees on a bound of the global k-th distance, every rank re-ranks
-only its rows inside that bound (global ids), ONE all_gather moves the packed (Q,k) distances + labels (NCCL over NVLink
-on GPUs), and every rank merges world_size*k candidates per query.
+GEMM on its shard, a small all_gather ((Q,k) floats per rank) agrees on a bound of the global k-th distance, every rank
+re-ranks only its rows inside that bound (global ids), ONE all_gather moves the packed (Q,k) distances + labels (NCCL
+over NVLink on GPUs), and every rank merges world_size*k candidates per query.
 """
 from __future__ import annotations
 
@@ -113,7 +113,7 @@ class IndexFlatL2(object):
             raise ValueError(f"k = {k} > ntotal = {self.ntotal}")
         nq = q.shape[0]
         ws = self._workspace(nq, k)
-        bound = torch.empty(nq, dtype=torch.float32, device=self.device)
+        bound = torch.empty(nq, k, dtype=torch.float32, device=self.device)
         e0 = e1 = None
         if gemm_events is not None:
             for ev in gemm_events:
@@ -142,8 +142,8 @@ class IndexFlatL2(object):
         return D, I
 
     def search_begin(self, q: torch.Tensor, k: int, gemm_events=None) -> torch.Tensor:
-        """Phase 1 (torch.ops.nanovs.flat_l2_begin): GEMM + lists; returns, per query, an upper bound of this shard's
-        k-th smallest exact distance -- reduce it with MIN over the shards before search_end."""
+        """Phase 1 (torch.ops.nanovs.flat_l2_begin): GEMM + lists; returns (nq, k) upper bounds of the exact distances of
+        this shard's k best rows -- gather them from all shards and reduce with merge_bounds before search_end."""
         self._gemm_events = gemm_events
         try:
             return torch.ops.nanovs.flat_l2_begin(q, torch_ops.register_index(self), int(k))
@@ -165,6 +165,16 @@ class IndexFlatL2(object):
         if was_np:
             return D.cpu().numpy(), I.cpu().numpy()
         return D, I
+
+
+def merge_bounds(bounds: torch.Tensor) -> torch.Tensor:
+    """(parts, nq, k) per-shard bounds of IndexFlatL2.search_begin -> (nq,) bound of the global k-th distance."""
+    bounds = ops._req(bounds)
+    parts, nq, k = bounds.shape
+    out = torch.empty(nq, dtype=torch.float32, device=bounds.device)
+    check(lib().nvs_flat_bound_merge(bounds.data_ptr(), parts, nq, k, out.data_ptr(), ops._stream()), "nvs_flat_bound_merge")
+    ops.LAUNCHES[0] += 1
+    return out
 
 
 def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor):
@@ -253,9 +263,10 @@ class ShardedIndexFlatL2(object):
         if self._index is not None:
             # two phases around one tiny allreduce: every shard re-ranks only the rows inside the GLOBAL k-th bound
             qd = q.to(self.device, torch.float32).contiguous()
-            bound = self._index.search_begin(qd, k, gemm_events=gemm_events)
-            self.dist.all_reduce(bound, op=self.dist.ReduceOp.MIN, group=self.group)
-            self._index.search_end(qd, k, bound, id_offset=self.lo, out=(Dm[0], Im[0]))
+            mine_b = self._index.search_begin(qd, k, gemm_events=gemm_events)
+            all_b = torch.empty(self.world, nq, k, dtype=torch.float32, device=self.device)
+            self.dist.all_gather_into_tensor(all_b, mine_b, group=self.group)
+            self._index.search_end(qd, k, merge_bounds(all_b), id_offset=self.lo, out=(Dm[0], Im[0]))
         else:
             D, I = self._local_search(self._shard, q, k, self.lo)
             Dm[0].copy_(D)

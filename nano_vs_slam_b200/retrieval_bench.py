@@ -60,17 +60,30 @@ def run(dev, world: int, rank: int, n_db: int = None, n_q: int = None, dim: int 
     return {
         "metric": "NetVLAD VPR queries/s", "value": n_q / (ms / 1e3), "unit": "queries/s",
         "config": {"workload": f"{n_q} queries x {n_db} db rows x {dim}-d, top-{k}, {world} shard(s) of {hi - lo} rows, "
-                               "bf16 tcgen05 GEMM + fused top-k + fp32 re-rank" + (", NCCL all_gather merge" if world > 1 else "")},
+                               "fp16 tcgen05 GEMM (exact screen) + fused lists + fp32 re-rank" +
+                               (", global k-th bound exchange + NCCL all_gather merge" if world > 1 else "")},
         "ms_per_search": ms, "gemm_kernel_ms": gemm, "topk_bit_exact_vs_planted": exact, "scaling": "strong",
         "roofline": {"bound": "tensor", "achieved": flops_rank / (gemm / 1e3) / 1e12, "unit": "TFLOP/s",
-                     "kind": "bf16 tcgen05.mma cta_group::1 128x256x16"},
+                     "kind": "fp16 tcgen05.mma cta_group::1 128x256x16"},
     }
 
 
 if __name__ == "__main__":
+    # python -m nano_vs_slam_b200.retrieval_bench [n_db] [n_q]; under torchrun: one rank per GPU, sharded database
     import json
     import sys
 
     n_db = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
     n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
-    print(json.dumps(run(torch.device("cuda", 0), 1, 0, n_db=n_db, n_q=n_q, steps=2, warmup=1)))
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    r = run(dev, world, rank, n_db=n_db, n_q=n_q, steps=5 if world > 1 else 2, warmup=2 if world > 1 else 1)
+    if rank == 0:
+        print(json.dumps(r))
+    if world > 1:
+        dist.destroy_process_group()

@@ -272,7 +272,7 @@ def _flat_begin_cuda(q, handle: int, k: int):
 
 
 def _flat_begin_fake(q, handle: int, k: int):
-    return q.new_empty(q.shape[0])
+    return q.new_empty(q.shape[0], k)
 
 
 def _flat_end_cuda(q, bound, handle: int, k: int, id_offset: int):
