@@ -48,7 +48,8 @@ constexpr int HX = 32, HY = 6;           // halo box: positions per row (= GEMM 
 constexpr int KC = 32;                   // input channels per chunk
 constexpr int A_HALF = HX * HY * KC * 2; // one of the hi / lo operand matrices: 192 rows x 64 B
 constexpr int A_BYTES = 2 * A_HALF;
-constexpr int NA_MAX = 3;                // activation chunks in flight: 3, or 2 when that lets the weights stay resident
+constexpr int NA_MAX = 6;                // activation chunks in flight: as many as fit next to the weights (2 .. 6): a chunk
+                                         // load takes ~2 us to land, and a one-chunk tile has only ~0.5 us of MMA work
 constexpr int ACC_STAGES = 2;
 constexpr int MAX_ISSUERS = 3;
 constexpr unsigned long long PLAN_MAGIC = 0x7273506C616E0002ull;  // first word of an rs::Plan
@@ -61,9 +62,10 @@ struct Cfg {
   static constexpr int W_STAGE = 2 * W_HALF;
   static constexpr bool CONCAT = CO == 32;          // a_hi x [W_hi ; W_lo] as one N = 2 NW instruction
   static constexpr int ACC_COLS = 192;              // per stage: CONCAT 2 x 96, else 192
-  // epilogue warps: TMEM lane quadrant (image row of the tile) x group of 16 output channels.  The epilogue is a chain
+  // epilogue warps: TMEM lane quadrant (image row of the tile) x one of four channel groups.  The epilogue is a chain
   // of long-latency steps (TMEM loads, shuffles, scattered stores): it needs warps, not instructions per warp
-  static constexpr int EPI_WARPS = CO / 4;
+  static constexpr int EPI_WARPS = 16;
+  static constexpr int CPW = CO / 4;                // output channels per epilogue warp: 16 (Cout 64) or 8 (Cout 32)
   static constexpr int WARP_TMA_A = EPI_WARPS, WARP_TMA_W = WARP_TMA_A + 1, WARP_MMA = WARP_TMA_W + 1;
   static constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
   // output staging: per TMEM lane quadrant one operand part (a_hi or a_lo, CO fp16 per position) of its 30 outputs
@@ -73,7 +75,7 @@ struct Cfg {
   static constexpr int SM_STG = 0;
   static constexpr int SM_BIAS = SM_STG + STG_BYTES;
   static constexpr int SM_POOL = SM_BIAS + CO * 4;
-  static constexpr int POOL_BYTES = (EPI_WARPS / 4) * 2 * 15 * 16 * 4;  // max-pool exchange: (channel group, quadrant pair) x 15 x 16
+  static constexpr int POOL_BYTES = (EPI_WARPS / 4) * 2 * 15 * CPW * 4;  // max-pool exchange: (channel group, quadrant pair) x 15 x CPW
   static constexpr int SM_BAR = SM_POOL + POOL_BYTES;
   static constexpr int MAX_WS = 16;                  // barrier slots reserved for the weight ring
   static constexpr int N_BARS = 2 * NA_MAX + 2 * MAX_WS + 6 + 1;
@@ -83,7 +85,7 @@ struct Cfg {
     return (SMEM_MAX - SM_A - na * A_BYTES) / W_STAGE < MAX_WS ? (SMEM_MAX - SM_A - na * A_BYTES) / W_STAGE : MAX_WS;
   }
   static constexpr int smem_bytes(int na, int w_stages) { return SM_A + na * A_BYTES + w_stages * W_STAGE + 1024; }
-  static_assert(max_w_stages(NA_MAX) >= 3, "weight ring");
+  static_assert(max_w_stages(3) >= 3, "weight ring");
   static constexpr uint32_t idesc(int n) {  // kind::f16: D fp32, A / B fp16, both K-major
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   }
@@ -205,13 +207,26 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_pin(uint32_t* r) {
-  asm volatile(""
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
                : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t* r) {
+  static_assert(N == 8 || N == 16, "columns per load");
+  if (N == 16) tmem_ld16_issue(taddr, r);
+  else tmem_ld8_issue(taddr, r);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_pin8(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) : : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_pin(uint32_t* r) {
+  tmem_pin8(r);
+  if (N == 16) tmem_pin8(r + 8);
 }
 // one lane of the (converged) warp; the compiler then knows the guarded code is single-threaded AND that warp-uniform
 // values stay uniform, so tcgen05 operands move to uniform registers without a per-lane election loop
@@ -248,20 +263,46 @@ __device__ __forceinline__ void store_split16(float* basep, size_t pixel, int c_
     }
 }
 
-// 16 consecutive channels [c, c + 16) of one pixel of a split-format tensor, straight from registers: a_hi as ONE 32-byte
-// store (a full sector; st.global.v8.b32 is new with sm_100), a_lo as another
-__device__ __forceinline__ void store_split16_256(float* basep, size_t pixel, int c_total, int c, const float* v) {
+// N (16 or 8) consecutive channels [c, c + N) of one pixel of a split-format tensor, straight from registers: a_hi as ONE
+// store of 2 N bytes (N = 16: a full 32-byte sector with st.global.v8.b32, new with sm_100), a_lo as another
+template <int N>
+__device__ __forceinline__ void store_split_direct(float* basep, size_t pixel, int c_total, int c, const float* v) {
   uint8_t* px = reinterpret_cast<uint8_t*>(basep) + pixel * (size_t)c_total * 4;
-  uint32_t hi[8], lo[8];
+  uint32_t hi[N / 2], lo[N / 2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(px + c * 2), "r"(hi[0]), "r"(hi[1]),
-               "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
-               : "memory");
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(px + (c_total + c) * 2), "r"(lo[0]),
-               "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
-               : "memory");
+  for (int j = 0; j < N / 2; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  if (N == 16) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(px + c * 2), "r"(hi[0]), "r"(hi[1]),
+                 "r"(hi[2]), "r"(hi[3]), "r"(hi[4 % (N / 2)]), "r"(hi[5 % (N / 2)]), "r"(hi[6 % (N / 2)]), "r"(hi[7 % (N / 2)])
+                 : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(px + (c_total + c) * 2), "r"(lo[0]),
+                 "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4 % (N / 2)]), "r"(lo[5 % (N / 2)]), "r"(lo[6 % (N / 2)]),
+                 "r"(lo[7 % (N / 2)])
+                 : "memory");
+  } else {
+    *reinterpret_cast<uint4*>(px + c * 2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(px + (c_total + c) * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
+
+// (tx, ty, frame) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ... without a division per tile: three 32-bit divisions
+// by run-time values cost a thread ~300 cycles, a large part of a one-chunk tile's budget in every role
+struct TileIter {
+  int tx, ty, b, sx, sy, sb, nx, ny;
+  __device__ __forceinline__ TileIter(int t0, int step, int tiles_x, int tiles_y) : nx(tiles_x), ny(tiles_y) {
+    tx = t0 % tiles_x; ty = (t0 / tiles_x) % tiles_y; b = t0 / (tiles_x * tiles_y);
+    sx = step % tiles_x; sy = (step / tiles_x) % tiles_y; sb = step / (tiles_x * tiles_y);
+  }
+  __device__ __forceinline__ void next() {
+    tx += sx;
+    int carry = 0;
+    if (tx >= nx) { tx -= nx; carry = 1; }
+    ty += sy + carry;
+    carry = 0;
+    if (ty >= ny) { ty -= ny; carry = 1; }
+    b += sb + carry;
+  }
+};
 
 template <int CO>
 __global__ void __launch_bounds__((Cfg<CO>::THREADS), 1)
@@ -331,7 +372,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint32_t aph = 0;
     const int quad = warp & 3, h = warp >> 2;
     const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
-    float seen_max = 0.f;
+    int bad = 0, out_of_range = 0;
+    // channels-last outputs feed the next layer's fp16 operands: flag |x| >= 60000; other outputs: flag non-finite values
+    const float range_limit = (p.dst_layout == 0 && p.dst_mode != 3) ? 60000.f : 3.0e38f;
     int dbg_i = 0;
     // Channels-last outputs go through a small staging buffer per TMEM lane quadrant (= image row of the tile), one
     // operand part at a time (a_hi, then a_lo).  Written straight from the registers a warp store instruction would hit
@@ -341,23 +384,29 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // with consecutive threads on consecutive 16-byte chunks: full lines.  `v`: this thread's 16 channels, `row`: its
     // position in the staged row set (n_rows positions), `px0`: pixel index of staged row 0, `x_lim`: rows >= x_lim lie
     // outside the image.
+    constexpr int CPW = C::CPW;
     constexpr int QWARPS = C::EPI_WARPS / 4, QTHREADS = QWARPS * 32, CH = C::ROW_OUT / 16;
     uint8_t* stg_q = sm + C::SM_STG + quad * C::QSTG_BYTES;
     const int qtid = h * 32 + lane;
     auto staged_store = [&](float* dstp, const float* v, bool writes, int row, int n_rows, int c_off, int c_total,
                             size_t px0, int x_lim, bool row_ok) {
-      uint32_t hi[8], lo[8];
+      uint32_t hi[CPW / 2], lo[CPW / 2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+      for (int j = 0; j < CPW / 2; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
       auto key = [](int r) { return C::ROW_OUT == 128 ? (r & 7) : ((r >> 1) & 3); };
       uint8_t* r0 = stg_q + row * C::ROW_OUT;
       const int k0 = key(row);
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
         const uint32_t* w = part ? lo : hi;
-        if (writes) {
-          *reinterpret_cast<uint4*>(r0 + (((2 * h) ^ k0) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(r0 + (((2 * h + 1) ^ k0) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        if (writes) {  // this warp's channel group = 16-byte chunk(s) CPW / 8 * h ... of the row
+          if (CPW == 16) {
+            *reinterpret_cast<uint4*>(r0 + (((2 * h) ^ k0) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(r0 + (((2 * h + 1) ^ k0) << 4)) =
+                make_uint4(w[4 % (CPW / 2)], w[5 % (CPW / 2)], w[6 % (CPW / 2)], w[7 % (CPW / 2)]);
+          } else {
+            *reinterpret_cast<uint4*>(r0 + ((h ^ k0) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
         asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
         if (row_ok) {
@@ -372,9 +421,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
       }
     };
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    TileIter ti((int)blockIdx.x, (int)gridDim.x, p.tiles_x, p.tiles_y);
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ti.next()) {
       if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && dbg_i < 256) p.dbg[dbg_i++] = clock64();
-      const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+      const int tx = ti.tx, ty = ti.ty, b = ti.b;
       const int gx = tx * TX - 1 + lane, gy = ty * TY + quad;
       const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
       mbar_wait(accfull(acc), aph);
@@ -382,25 +432,25 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int part = 0; part < ((p.knock & 2) ? 0 : 1); ++part) {
-        const int cbase = 16 * h;  // first of this warp's 16 output channels
+        const int cbase = CPW * h;  // first of this warp's CPW output channels
         if (p.dst_mode == 3 && cbase != 0) continue;  // keypoint heads: 3 channels in all
         // (channels beyond cout are zero weights + zero bias: a staged store writes them, as exact zeros, with the rest)
         if (cbase >= p.cout && !(p.store_nhwc | p.store_pool)) continue;
-        float o[16];
+        float o[CPW];
         {
-          uint32_t u0[16], u1[16], u2[16];
-          tmem_ld16_issue(taddr + (uint32_t)cbase, u0);
-          tmem_ld16_issue(taddr + (uint32_t)(CO + cbase), u1);
-          tmem_ld16_issue(taddr + (uint32_t)(2 * CO + cbase), u2);
+          uint32_t u0[CPW], u1[CPW], u2[CPW];
+          tmem_ld_issue<CPW>(taddr + (uint32_t)cbase, u0);
+          tmem_ld_issue<CPW>(taddr + (uint32_t)(CO + cbase), u1);
+          tmem_ld_issue<CPW>(taddr + (uint32_t)(2 * CO + cbase), u2);
           if (C::CONCAT) {  // ... and the same three blocks of a_hi w_lo + a_lo w_hi
-            uint32_t w0[16], w1[16], w2[16];
-            tmem_ld16_issue(taddr + (uint32_t)(C::NW + cbase), w0);
-            tmem_ld16_issue(taddr + (uint32_t)(C::NW + CO + cbase), w1);
-            tmem_ld16_issue(taddr + (uint32_t)(C::NW + 2 * CO + cbase), w2);
+            uint32_t w0[CPW], w1[CPW], w2[CPW];
+            tmem_ld_issue<CPW>(taddr + (uint32_t)(C::NW + cbase), w0);
+            tmem_ld_issue<CPW>(taddr + (uint32_t)(C::NW + CO + cbase), w1);
+            tmem_ld_issue<CPW>(taddr + (uint32_t)(C::NW + 2 * CO + cbase), w2);
             tmem_ld_wait();
-            tmem_pin(u0); tmem_pin(u1); tmem_pin(u2); tmem_pin(w0); tmem_pin(w1); tmem_pin(w2);
+            tmem_pin<CPW>(u0); tmem_pin<CPW>(u1); tmem_pin<CPW>(u2); tmem_pin<CPW>(w0); tmem_pin<CPW>(w1); tmem_pin<CPW>(w2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CPW; ++j) {
               const float d0 = __uint_as_float(u0[j]) + __uint_as_float(w0[j]);
               const float d1 = __uint_as_float(u1[j]) + __uint_as_float(w1[j]);
               const float d2 = __uint_as_float(u2[j]) + __uint_as_float(w2[j]);
@@ -408,18 +458,24 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
           } else {
             tmem_ld_wait();
-            tmem_pin(u0); tmem_pin(u1); tmem_pin(u2);
+            tmem_pin<CPW>(u0); tmem_pin<CPW>(u1); tmem_pin<CPW>(u2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < CPW; ++j)
               o[j] = __shfl_up_sync(0xffffffffu, __uint_as_float(u0[j]), 1) + __uint_as_float(u1[j]) +
                      __shfl_down_sync(0xffffffffu, __uint_as_float(u2[j]), 1);
           }
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const float a = fmaf(o[j], p.w_scale, bias_s[cbase + j]);
+          // range check BEFORE the activation (max / min would turn a NaN into 0): an activation beyond fp16's range --
+          // or, in any output mode, a non-finite value (an operand of this layer was already out of range)
+          out_of_range |= !(fabsf(a) < range_limit);
           o[j] = fmaxf(a, 0.f) + neg_slope * fminf(a, 0.f);
         }
+        if (!valid) out_of_range = 0;  // halo positions / positions outside the image are never stored
+        bad |= out_of_range;
+        out_of_range = 0;
         if (p.act == NVS_ACT_SIGMOID && cbase == 0) {  // depth heads: cout <= 4
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = 1.f / (1.f + expf(-o[j]));
@@ -433,34 +489,34 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
           continue;
         }
-        if (valid) {
+        if (p.knock & 128) {  // experiment: everything but the stores (the dependency keeps the math alive)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) seen_max = fmaxf(seen_max, fabsf(o[j]));
+          for (int j = 0; j < CPW; ++j) bad |= o[j] == 12345.678f;
+          continue;
         }
-        if (p.knock & 128) continue;  // experiment: everything but the stores (seen_max keeps the math alive)
         if (p.dst_pool != nullptr) {
           // MaxPool2d(2,2): x partner = next lane (strips start at even x, so pairs are lanes (1,2), (3,4), ...),
           // y partner = the row of the next quadrant's warp: odd quadrants hand their x-pooled values to the even
           // quadrant below them through shared memory (one buffer and one named barrier per (h, quadrant pair);
           // the pair's second barrier keeps the next write behind this read)
-          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + (h * 2 + (quad >> 1)) * (15 * 16);
+          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + (h * 2 + (quad >> 1)) * (15 * CPW);
           const int bar_id = 2 + h * 2 + (quad >> 1);
-          float m[16];
+          float m[CPW];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = fmaxf(o[j], __shfl_down_sync(0xffffffffu, o[j], 1));
+          for (int j = 0; j < CPW; ++j) m[j] = fmaxf(o[j], __shfl_down_sync(0xffffffffu, o[j], 1));
           const int pc = (lane - 1) >> 1;  // pooled column inside the strip, odd lanes 1..29 -> 0..14
           const bool owner = (lane & 1) && lane <= 29;
           if ((quad & 1) && owner) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<float4*>(ps + pc * 16)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+            for (int q = 0; q < CPW / 4; ++q)
+              reinterpret_cast<float4*>(ps + pc * CPW)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
           }
           asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
           const bool pool_owner = !(quad & 1) && owner;
           if (pool_owner) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 r = reinterpret_cast<const float4*>(ps + pc * 16)[q];
+            for (int q = 0; q < CPW / 4; ++q) {
+              const float4 r = reinterpret_cast<const float4*>(ps + pc * CPW)[q];
               m[4 * q] = fmaxf(m[4 * q], r.x);
               m[4 * q + 1] = fmaxf(m[4 * q + 1], r.y);
               m[4 * q + 2] = fmaxf(m[4 * q + 2], r.z);
@@ -471,10 +527,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (p.staged == 0) {
             const int qx = gx >> 1, qy = gy >> 1;
             if (pool_owner && qx < (p.W >> 1) && qy < (p.H >> 1))
-              store_split16_256(p.dst_pool, ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx, p.pool_c_total, p.pool_c_off + cbase, m);
+              store_split_direct<CPW>(p.dst_pool, ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx, p.pool_c_total, p.pool_c_off + cbase, m);
           } else if (!(quad & 1)) {
             const int Hp = p.H >> 1, Wp = p.W >> 1, qy = gy >> 1, qx0 = tx * (TX / 2);
-            staged_store(p.dst_pool, m, owner, pc, TX / 2, p.pool_c_off + cbase - 16 * h, p.pool_c_total,
+            staged_store(p.dst_pool, m, owner, pc, TX / 2, p.pool_c_off, p.pool_c_total,
                          ((size_t)b * Hp + qy) * Wp + qx0, Wp - qx0, qy < Hp);
           }
           asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
@@ -485,14 +541,14 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             float* d = p.dst + (((size_t)b * p.dst_c_total + p.dst_c_off + cbase) * p.H + gy) * p.W + gx;
             const size_t plane = (size_t)p.H * p.W;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < CPW; ++j)
               if (cbase + j < p.cout) d[j * plane] = o[j];
           }
         }
         if (p.store_nhwc && p.staged == 0) {
-          if (valid) store_split16_256(p.dst, ((size_t)b * p.H + gy) * p.W + gx, p.dst_c_total, p.dst_c_off + cbase, o);
+          if (valid) store_split_direct<CPW>(p.dst, ((size_t)b * p.H + gy) * p.W + gx, p.dst_c_total, p.dst_c_off + cbase, o);
         } else if (p.store_nhwc)  // this quadrant's image row: 30 positions
-          staged_store(p.dst, o, lane >= 1 && lane <= TX, lane - 1, TX, p.dst_c_off + cbase - 16 * h, p.dst_c_total,
+          staged_store(p.dst, o, lane >= 1 && lane <= TX, lane - 1, TX, p.dst_c_off, p.dst_c_total,
                        ((size_t)b * p.H + gy) * p.W + tx * TX, p.W - tx * TX, gy < p.H);
         if (valid && p.dst_mode == 2) {
           // PixelShuffle(2) -> channels-last (B, 2H, 2W, cout/4), split format: channel c -> (c%4/2, c%2, c/4)
@@ -505,11 +561,18 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               uint8_t* px = reinterpret_cast<uint8_t*>(p.dst) +
                             (((size_t)b * H2 + 2 * gy + i) * W2 + 2 * gx + j) * (size_t)p.dst_c_total * 4;
               const int c = p.dst_c_off + cbase / 4;
-              uint32_t hi2[2], lo2[2];
-              split_pair(o[s], o[4 + s], hi2[0], lo2[0]);
-              split_pair(o[8 + s], o[12 + s], hi2[1], lo2[1]);
-              *reinterpret_cast<uint2*>(px + c * 2) = make_uint2(hi2[0], hi2[1]);
-              *reinterpret_cast<uint2*>(px + (p.dst_c_total + c) * 2) = make_uint2(lo2[0], lo2[1]);
+              if (CPW == 16) {
+                uint32_t hi2[2], lo2[2];
+                split_pair(o[s], o[4 + s], hi2[0], lo2[0]);
+                split_pair(o[(8 + s) % CPW], o[(12 + s) % CPW], hi2[1], lo2[1]);
+                *reinterpret_cast<uint2*>(px + c * 2) = make_uint2(hi2[0], hi2[1]);
+                *reinterpret_cast<uint2*>(px + (p.dst_c_total + c) * 2) = make_uint2(lo2[0], lo2[1]);
+              } else {
+                uint32_t hi1, lo1;
+                split_pair(o[s], o[4 + s], hi1, lo1);
+                *reinterpret_cast<uint32_t*>(px + c * 2) = hi1;
+                *reinterpret_cast<uint32_t*>(px + (p.dst_c_total + c) * 2) = lo1;
+              }
             }
         }
       }
@@ -521,22 +584,20 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         aph ^= 1;
       }
     }
-    // an activation beyond the fp16 range would make the next layer's a_hi infinite: report it (sticky flag)
-    if (p.range_flag != nullptr && p.dst_layout == 0 && p.dst_mode != 3) {
-      seen_max = warp_max(seen_max);
-      if (lane == 0 && !(seen_max < 60000.f)) atomicOr(p.range_flag, 1);
-    }
+    // an activation beyond the fp16 range makes the next layer's a_hi infinite: report it (sticky flag)
+    if (p.range_flag != nullptr && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.range_flag, 1);
   } else if (warp == C::WARP_TMA_A) {
     // =========================== activation producer: the hi and the lo box of one chunk per A slot ===============
     if (lane == 0) {
       int as = 0;
       uint32_t aph = 0;
       const uint32_t bytes = p.pair16 ? A_HALF : A_BYTES;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * TX - 1, y0 = ty * TY - 1;
+      TileIter ti((int)blockIdx.x, (int)gridDim.x, p.tiles_x, p.tiles_y);
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ti.next()) {
+        const int b = ti.b;
+        const int x0 = ti.tx * TX - 1, y0 = ti.ty * TY - 1;
         for (int ch = 0; ch < chunks; ++ch) {
-          mbar_wait_relaxed(aempty(as), aph ^ 1u);
+          mbar_wait(aempty(as), aph ^ 1u);  // (spinning: this thread's latency bounds one-chunk tiles)
           const uint32_t dst = base + C::SM_A + as * A_BYTES;
           if (p.knock & 8) {
             mbar_arrive(afull(as));
@@ -728,18 +789,12 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
   const int sms = nvs_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   Params q = p;
-  // three A slots, or two when that is what lets every weight tile of the layer stay resident (64 -> 64 channels)
+  // weights resident when all 3 x chunks tiles fit next to >= 2 A slots (up to 64 -> 64 channels), else a 4-stage ring;
+  // then as many A slots as fit (<= NA_MAX): the activation loads are what one- and two-chunk tiles wait for
   const int w_tiles = 3 * (p.c0_chunks + p.c1_chunks);
-  if (w_tiles <= C::max_w_stages(3)) {
-    q.na = 3;
-    q.w_stages = w_tiles;
-  } else if (w_tiles <= C::max_w_stages(2)) {
-    q.na = 2;
-    q.w_stages = w_tiles;
-  } else {
-    q.na = 3;
-    q.w_stages = C::max_w_stages(3);
-  }
+  q.w_stages = w_tiles <= C::max_w_stages(2) ? w_tiles : (C::max_w_stages(3) < 4 ? C::max_w_stages(3) : 4);
+  q.na = (C::SMEM_MAX - C::SM_A - q.w_stages * C::W_STAGE) / A_BYTES;
+  q.na = q.na > NA_MAX ? NA_MAX : q.na;
   {
     // staged stores pay off when a tile has enough MMA work to hide the quadrant barriers (measured: 96 -> 64 channels
     // 1.62 -> 1.46 ms, but 32 -> 32 0.50 -> 0.60 ms); NVS_RS_STORE = 1 / 2 forces staged / direct

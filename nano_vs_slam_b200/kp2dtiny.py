@@ -410,6 +410,9 @@ class _KP2DTinyBase(nn.Module):
         # those letters use 64-wide slices: 4.4x the FFMA backend's frame rate, inside the 1e-4 tolerance.
         self.tc_slice = int(os.environ.get("NVS_TC_SLICE", "64" if max(c4, c5) > 128 else "128"))
         self.conv_backend = os.environ.get("NVS_CONV_BACKEND", "tc" if tc_ok else "ffma")
+        # arithmetic of the tensor-core convs: "f16" (3xFP16, csrc/conv_rs.cu; needs |activation| < 65504: checked on the
+        # first batch of every launch plan, with an automatic switch to "tf32") or "tf32" (3xTF32, csrc/conv_tc.cu)
+        self.conv_math = ops.conv_math()
         # batches up to this size replay a captured CUDA graph (0 disables)
         self.cuda_graph_max_batch = int(os.environ.get("NVS_CUDA_GRAPH_MAX_BATCH", "16"))
         if self.conv_backend == "tc" and not tc_ok:
@@ -484,7 +487,8 @@ class _KP2DTinyBase(nn.Module):
         bn = {"weight": m.bn.weight, "bias": m.bn.bias, "running_mean": m.bn.running_mean,
               "running_var": m.bn.running_var}
         if tc:
-            return ops.pack_conv_tc(m.conv.weight, bn=bn, eps=m.bn.eps, cin_segments=self._segs(m.conv, seg))
+            return ops.pack_conv_tc(m.conv.weight, bn=bn, eps=m.bn.eps, cin_segments=self._segs(m.conv, seg),
+                                    math=self.conv_math)
         return ops.pack_conv(m.conv.weight, bn=bn, eps=m.bn.eps)
 
     def _pk_block_pair(self, ma: _ConvBnAct, mb: _ConvBnAct):
@@ -499,7 +503,8 @@ class _KP2DTinyBase(nn.Module):
             cp = _p32(w.shape[0])
             ws.append(torch.cat([w, w.new_zeros(cp - w.shape[0], *w.shape[1:])], 0))
             bs.append(torch.cat([b, b.new_zeros(cp - b.shape[0])], 0))
-        return ops.pack_conv_tc(torch.cat(ws, 0), bias=torch.cat(bs, 0), cin_segments=self._segs(ma.conv, None))
+        return ops.pack_conv_tc(torch.cat(ws, 0), bias=torch.cat(bs, 0), cin_segments=self._segs(ma.conv, None),
+                                math=self.conv_math)
 
     def _merge_head_convs(self) -> bool:
         """The first convs of the heads all read the backbone output: pair them up when two fit one 128-wide conv."""
@@ -508,7 +513,7 @@ class _KP2DTinyBase(nn.Module):
 
     def _pk_conv(self, m: nn.Conv2d, s2d=False, tc: bool = False, seg=None):
         if tc:
-            return ops.pack_conv_tc(m.weight, bias=m.bias, cin_segments=self._segs(m, seg))
+            return ops.pack_conv_tc(m.weight, bias=m.bias, cin_segments=self._segs(m, seg), math=self.conv_math)
         return ops.pack_conv(m.weight, bias=m.bias, s2d=s2d)
 
     @staticmethod
@@ -535,7 +540,7 @@ class _KP2DTinyBase(nn.Module):
         """to_mcu upsampling layer as its equivalent 3x3 conv (+ PixelShuffle epilogue), BatchNorm folded."""
         w3, b3 = m.equivalent_conv()
         if tc:
-            return ops.pack_conv_tc(w3, bias=b3, cin_segments=[(w3.shape[1], _p32(w3.shape[1]))])
+            return ops.pack_conv_tc(w3, bias=b3, cin_segments=[(w3.shape[1], _p32(w3.shape[1]))], math=self.conv_math)
         return ops.pack_conv(w3, bias=b3)
 
     def _pack_seg(self, P: dict, sh: "_SegHead", pre: str, tc: bool):
@@ -559,7 +564,7 @@ class _KP2DTinyBase(nn.Module):
         tc = self.conv_backend == "tc"
         # channels-last store mode of the kernels that feed tensor-core convs: 2 = split fp16 hi / lo format of the
         # 3xFP16 kernels (NVS_CONV_MATH=f16, the default), 1 = fp32 (3xTF32 kernels)
-        self._nhwc_mode = 2 if ops.conv_math() == "f16" else 1
+        self._nhwc_mode = 2 if self.conv_math == "f16" else 1
         bb = self.backbone
         for n in ("conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"):
             # the 3-channel stem layer stays on the FFMA kernel (K = 27 is too thin for a TMA row); conv1b
@@ -667,7 +672,20 @@ class _KP2DTinyBase(nn.Module):
                 self._plans.clear()
             plan = self._plans[key] = _Plan(self, B, H, W, x.device)
             plan.in_mode = in_mode
-        return self._run(plan, x)
+        first = plan.runs == 0 and self.conv_backend == "tc" and self.conv_math == "f16"
+        if first:
+            ops.conv_rs_range_flag(reset=True)
+        out = self._run(plan, x)
+        if first and ops.conv_rs_range_flag(reset=True):  # (synchronises: once per launch plan)
+            # an activation left fp16's range: the 3xFP16 operands of the following layer were not finite.  Switch
+            # this model to the 3xTF32 kernels (fp32's exponent range) and run the batch again.
+            import warnings
+            warnings.warn("nano_vs_slam_b200: activations beyond the fp16 range (|x| >= 60000); this model now uses the "
+                          "3xTF32 tensor-core convs (NVS_CONV_MATH=tf32)")
+            self.conv_math = "tf32"
+            self._invalidate()
+            return self._forward_impl(x, unit_input=(in_mode == ops.IN_UNIT))
+        return out
 
     def _launch_all(self, plan: _Plan, x: torch.Tensor, outs: Dict[str, torch.Tensor]) -> None:
         """Enqueue every kernel of the plan on the current stream (pure launches: nothing allocates or syncs)."""
@@ -1091,7 +1109,7 @@ class KP2DTinyV2(_KP2DTinyBase):
         if tc:
             P["kp.b"] = ops.pack_head_pair_tc(self.score_head.convDb.weight, self.score_head.convDb.bias,
                                               self.loc_head.convDb.weight, self.loc_head.convDb.bias,
-                                              cpad=_p32(self.channel_dims[3]))
+                                              cpad=_p32(self.channel_dims[3]), math=self.conv_math)
         else:
             P["score.b"] = self._pk_conv(self.score_head.convDb)
             P["loc.b"] = self._pk_conv(self.loc_head.convDb)
@@ -1226,7 +1244,8 @@ class KP2DTinyV3(_KP2DTinyBase):
         # convDb (c4 -> 3) is launched as two tiny convs so that score (ch 0, sigmoid) and shift (ch 1:3, tanh)
         # land directly in their own output tensors (kp2dtiny.py:927-935) without a slicing copy.
         if tc:
-            P["kp.b"] = ops.pack_head_pair_tc(h.convDb.weight, h.convDb.bias, cpad=_p32(self.channel_dims[3]))
+            P["kp.b"] = ops.pack_head_pair_tc(h.convDb.weight, h.convDb.bias, cpad=_p32(self.channel_dims[3]),
+                                              math=self.conv_math)
         else:
             P["sl.score"] = ops.pack_conv(h.convDb.weight[0:1], bias=h.convDb.bias[0:1])
             P["sl.shift"] = ops.pack_conv(h.convDb.weight[1:3], bias=h.convDb.bias[1:3])
