@@ -616,8 +616,10 @@ def main():
         rf["frac"] = rf["achieved"] / bf16_peak
         rf["peak_source"] = which + " bf16 cuBLAS sustained (MEASURED_PEAKS.json); fp16 operands run at the bf16 rate"
         tr = _traffic("flat_l2_topk")
-        rf["traffic"] = tr["dram_bytes_per_launch"] if tr else None
+        rf["traffic"] = None
         if tr:
+            n_local = retrieval_bench.shard_rows(world, rank)
+            rf["traffic"] = tr["dram_bytes_per_launch"] * (n_local / tr["rows"] if "rows" in tr else 1.0)
             rf["traffic_note"] = tr["note"]
         if rank == 0 and not args.no_cpu_baseline:
             r["cpu_baseline"] = retrieval_cpu_baseline(os.cpu_count() or 1)

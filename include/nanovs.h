@@ -319,6 +319,10 @@ int nvs_pose_batch_adaptive(const float* pts, int32_t n_frames, int32_t kmax, co
  *         allgather per search. */
 int32_t nvs_flat_padded_dim(int32_t d);
 int32_t nvs_flat_max_k(void);
+/* debugging aid (tools/retr_waits.py): every following GEMM launch writes 16 int64 per CTA into dev_buf (device memory,
+ * 16 x 148 entries) -- cycles of the MMA role, producer wait, MMA wait for operands, MMA wait for a drained accumulator,
+ * epilogue wait, epilogue cycles, k-blocks issued, unused; NULL switches it off */
+void nvs_flat_debug_buffer(long long* dev_buf);
 int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_f16, float* norms, float* stats, void* stream);
 size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int32_t d, int32_t k);
 int nvs_flat_search(const float* db, const void* db_f16, const float* db_norms, const float* db_stats, int64_t n_db,

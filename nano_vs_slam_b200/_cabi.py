@@ -62,6 +62,7 @@ SIGNATURES = {
     "nvs_conv_tc_run": (_i32, [_vp, _vp, _vp, _vp]),
     "nvs_conv_rs_range_flag": (_i32, [_i32]),
     "nvs_conv_rs_debug_buffer": (None, [_vp]),
+    "nvs_flat_debug_buffer": (None, [_vp]),
     "nvs_split16": (_i32, [_vp, _vp, C.c_int64, _i32, _vp]),
     "nvs_unsplit16": (_i32, [_vp, _vp, C.c_int64, _i32, _vp]),
     "nvs_conv_small": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -40,8 +40,6 @@ namespace rt {
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;       // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;       // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int THREADS = 256;                // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
@@ -50,10 +48,15 @@ constexpr int CAP = 256;                    // candidates re-ranked exactly per 
 constexpr int MAX_CAND = 12288;             // n_strips * L the selection kernel holds in shared memory (96 KiB)
 
 // shared memory map (dynamic, 1024-byte aligned base): STAGES operand stages, then the per-row lists.
-// 4 stages leave room for lists of 31 entries, 3 stages for 79, 2 for 127 (odd pitch: conflict-free row-per-thread access).
-template <int STAGES>
+// PAIR = false: a CTA holds the whole 256-row database tile (48 KiB stages): 4 stages leave room for lists of 31 entries,
+// 3 stages for 79, 2 for 127 (odd pitch: conflict-free row-per-thread access).  PAIR = true (tcgen05 cta_group::2): a CTA
+// holds its half of the tile (32 KiB stages): 6 stages -> 31, 5 -> 63, 4 -> 95, 3 -> 127.
+template <int STAGES, bool PAIR>
 struct Smem {
-  static constexpr int LMAX = STAGES == 4 ? 31 : (STAGES == 3 ? 79 : 127);
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                 // database rows of a tile in this CTA's stages
+  static constexpr int STAGE_BYTES = A_BYTES + B_ROWS * BK * 2;
+  static constexpr int LROOM = (227 * 1024 - 1024 - 256 - ACC_STAGES * BN * 4 - STAGES * STAGE_BYTES) / (BM * 8);
+  static constexpr int LMAX = LROOM >= 127 ? 127 : ((LROOM - 1) | 1);
   static constexpr int LIST_D = STAGES * STAGE_BYTES;               // float [128][LMAX]
   static constexpr int LIST_I = LIST_D + BM * LMAX * 4;             // int   [128][LMAX]
   static constexpr int XN = LIST_I + BM * LMAX * 4;                 // float [2][256]
@@ -92,6 +95,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 8000000000LL) __trap();
   }
 }
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// the same, adding the cycles spent waiting to `acc` when the wait profile is on (nvs_flat_debug_buffer)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1) {
   asm volatile(
@@ -106,6 +124,62 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensor
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
+}
+// ---- cta_group::2 (CTA pair = the two SMs of a TPC work on one 256-row MMA; operands come from both shared memories)
+// TMA load whose completion is counted on the barrier `bar_cluster` (a shared::cluster address: the pair LEADER's barrier)
+// L2 eviction policies of the TMA loads (the encodings createpolicy.fractional produces for fraction 1.0)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull,
+                   L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// the same, delivered to every CTA of cta_mask; each destination counts it on the barrier of ITS pair leader
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster,
+                                                   int c0, int c1, uint16_t cta_mask, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_rank) {  // -> shared::cluster address
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// wait on a barrier that CTAs of the cluster arrive on with ordinary (generic-proxy) arrives
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster_t(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+  if (on) acc += clock64() - t0;
 }
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
@@ -125,6 +199,28 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one lane of the (converged) warp.  Code guarded by it is single-threaded AND the compiler knows that warp-uniform
+// values stay uniform: tcgen05 operands go to uniform registers directly.  Issued from a plain `if (lane == 0)` region
+// every tcgen05.mma was wrapped in a per-lane ELECT / R2UR.BROADCAST loop (~15 SASS instructions, ~100 cycles of a
+// lone thread's issue latency per MMA -- as long as the 128-cycle MMA itself).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_f16_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -166,6 +262,8 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 }
 // instruction descriptor: D = f32 (bit 4), A = B = fp16 (format 0), both K-major, N = 256, M = 128
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// cta_group::2: M = 256 (128 rows in each CTA of the pair), N = 256 (128 database rows from each CTA's shared memory)
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 struct Params {
   const float* xnorm;   // [N]    |x|^2 (fp32, from the fp32 rows)
@@ -175,16 +273,21 @@ struct Params {
   float* cand_d;        // [Qpad][n_strips][L]  s~ = |x|^2 - 2 q~.x~
   int32_t* cand_i;      // [Qpad][n_strips][L]  row index inside this shard (-1 = empty)
   int Q, N, kblocks;    // kblocks = Dpad / 64
-  int k, L, lp;         // neighbours wanted, list length (>= k), its (odd) pitch
+  int k, L;             // neighbours wanted, list length (>= k; the buffers hold L + 32 or more)
   int n_mblk, n_strips, tiles_per_strip, n_tiles;
-  int n_mpair;          // ceil(n_mblk / 2): a cluster of two CTAs owns query blocks (2*pair, 2*pair + 1)
+  int n_mgrp;           // ceil(n_mblk / cs): a cluster of cs CTAs owns query blocks cs*grp .. cs*grp + cs - 1
+  int cs;               // cluster size (2, 4 or 8): CTAs sharing every database tile by multicast
+  int hint;             // L2 eviction hints of the operand loads (NVS_RETR_HINT)
+  int knock;            // NVS_RETR_KNOCK (timing experiments, results are WRONG): 1 no list work, 2 no TMEM loads, 4 no TMA
+  long long* dbg;       // nvs_flat_debug_buffer: 8 counters per CTA (wait profile), or NULL
 };
 
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+template <int STAGES, bool PAIR>
+__global__ void __launch_bounds__(THREADS, 1)
 flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                     const Params p) {
-  using S = Smem<STAGES>;
+  using S = Smem<STAGES, PAIR>;
+  constexpr int STAGE_BYTES = S::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -199,8 +302,17 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S::BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();          // 0 / 1 inside the CTA pair
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // cluster of cs CTAs (launch attribute): each owns one query block and TMA-loads 1/cs of every database tile for all
+  const uint32_t crank = cluster_ctarank();
+  // PAIR: CTAs (2i, 2i+1) of the cluster form a cta_group::2 pair -- one M = 256 MMA over both query blocks, issued by the
+  // even CTA (the leader); a CTA holds HALF of the database tile (rows [128 h, 128 h + 128), h = rank & 1), loaded in
+  // cs / 2 slices by the CTAs of its parity.  Every operand byte is written to and read from shared memory once per
+  // pair instead of once per CTA (64 instead of 96 KB of shared-memory traffic per SM and k-block).
+  const int cs = p.cs, b_rows = BN / cs;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const uint32_t leader_rank = PAIR ? (crank & ~1u) : crank;
+  const bool leader = crank == leader_rank;
+  const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
@@ -209,19 +321,27 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 2);  // the peer multicasts into this stage too: both CTAs' MMAs must have retired
+      // the peers multicast into this stage too: every CTA's (PAIR: every pair's) MMAs must have retired
+      mbar_init(empty_bar(s), PAIR ? cs / 2 : cs);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), PAIR ? 8 : 4);  // one arrive per epilogue warp (PAIR: of both CTAs, on the leader's)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {  // both CTAs of the pair issue it, same warp, same slot address
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -229,26 +349,46 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_units = p.n_mpair * p.n_strips;  // (strip, query-block pair) units, round-robin over clusters
+  const int n_units = p.n_mgrp * p.n_strips;  // (strip, query-block group) units, round-robin over clusters
+  const bool prof = p.dbg != nullptr;
+  long long w0 = 0, w1 = 0, nkb = 0;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // NVS_RETR_HINT (PAIR): 1 = queries evict-last (they are re-read for every strip), 2 = database rows evict-first
+      const uint64_t hint_q = (p.hint & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+      const uint64_t hint_x = (p.hint & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
       for (int u = cluster_id; u < n_units; u += n_clusters) {
-        const int strip = u / p.n_mpair, mblk = 2 * (u - strip * p.n_mpair) + (int)crank;
+        const int strip = u / p.n_mgrp, mblk = cs * (u - strip * p.n_mgrp) + (int)crank;
         const int t_begin = strip * p.tiles_per_strip;
         const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
         for (int t = t_begin; t < t_end; ++t) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_wait_t(empty_bar(stage), phase ^ 1, prof, w0);
             const uint32_t a_dst = base + stage * STAGE_BYTES;
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);  // own A + own half of B + the peer's half of B
-            tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BK, mblk * BM);  // (rows past Q: zero filled)
-            // my half (128 rows) of the 256-row database tile, delivered to BOTH CTAs of the pair
-            tma_load_2d_mc(a_dst + A_BYTES + crank * (B_BYTES / 2), &tmap_x, full_bar(stage), kb * BK,
-                           t * BN + (int)crank * (BN / 2), (uint16_t)0x3);
+            if (p.knock & 4) {
+              if (leader) mbar_arrive(full_bar(stage));
+            } else if constexpr (PAIR) {
+              // all bytes of the pair (2 x (A + half of B)) are counted on the LEADER's barrier
+              const uint32_t fb = map_to_cta(full_bar(stage), leader_rank);
+              if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+              tma_load_2d_2sm(a_dst, &tmap_q, fb, kb * BK, mblk * BM, hint_q);  // (rows past Q: zero filled)
+              const uint32_t h = crank & 1u, pi = crank >> 1;  // my half of the tile; my slice (256 / cs rows) of it
+              const uint32_t b_dst = a_dst + A_BYTES + pi * (uint32_t)(b_rows * BK * 2);
+              const int row0 = t * BN + (int)h * (BN / 2) + (int)pi * b_rows;
+              if (cs == 2) tma_load_2d_2sm(b_dst, &tmap_x, fb, kb * BK, row0, hint_x);
+              else tma_load_2d_2sm_mc(b_dst, &tmap_x, fb, kb * BK, row0, (uint16_t)((0x5555u << h) & cmask), hint_x);
+            } else {
+              mbar_expect_tx(full_bar(stage), STAGE_BYTES);  // own A + own slice of B + the peers' slices of B
+              tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BK, mblk * BM);  // (rows past Q: zero filled)
+              // my slice (256 / cs rows) of the 256-row database tile, delivered to EVERY CTA of the cluster
+              tma_load_2d_mc(a_dst + A_BYTES + crank * (uint32_t)(b_rows * BK * 2), &tmap_x, full_bar(stage), kb * BK,
+                             t * BN + (int)crank * b_rows, cmask);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -256,73 +396,133 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
       }
+      if (prof) p.dbg[blockIdx.x * 16 + 1] = w0;  // producer: waiting for a free stage
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+    if (leader) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int u = cluster_id; u < n_units; u += n_clusters) {
-        const int strip = u / p.n_mpair;
+        const int strip = u / p.n_mgrp;
         const int t_begin = strip * p.tiles_per_strip;
         const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
         for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+          // epilogue (PAIR: of both CTAs) has drained this accumulator
+          if constexpr (PAIR) mbar_wait_cluster_t(tempty_bar(acc), acc_phase ^ 1, prof, w1);
+          else mbar_wait_t(tempty_bar(acc), acc_phase ^ 1, prof, w1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait_t(full_bar(stage), phase, prof, w0);
+            ++nkb;
             tc_fence_after();
             const uint32_t a_addr = base + stage * STAGE_BYTES;
             const uint64_t adesc = make_sdesc(a_addr);
             const uint64_t bdesc = make_sdesc(a_addr + A_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 halves = 32 bytes along K inside the 128-byte swizzle span: +2 in (addr >> 4)
-              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
-                         (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 16 halves = 32 bytes along K inside the 128-byte swizzle span: +2 in (addr >> 4)
+                if constexpr (PAIR)
+                  tc_mma_f16_2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC2,
+                               (kb | k) != 0 ? 1u : 0u);
+                else
+                  tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                             (kb | k) != 0 ? 1u : 0u);
+              }
+              // frees this stage in EVERY CTA when these MMAs retire
+              if constexpr (PAIR) tc_commit_mc2(empty_bar(stage), cmask);
+              else tc_commit_mc(empty_bar(stage), cmask);
             }
-            tc_commit_mc(empty_bar(stage), (uint16_t)0x3);  // frees this stage in BOTH CTAs when these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          if (elect_one()) {  // accumulator complete -> epilogue (PAIR: of both CTAs)
+            if constexpr (PAIR) tc_commit_mc2(tfull_bar(acc), (uint16_t)(0x3u << leader_rank));
+            else tc_commit(tfull_bar(acc));
+          }
           if (++acc == ACC_STAGES) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
       }
+      if (prof && lane == 0) {
+        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_start;  // MMA role: total cycles,
+        p.dbg[blockIdx.x * 16 + 2] = w0;                   // waiting for operand stages,
+        p.dbg[blockIdx.x * 16 + 3] = w1;                   // waiting for a drained accumulator,
+        p.dbg[blockIdx.x * 16 + 6] = nkb;                  // k-blocks issued
+      }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: running per-row list of the L smallest s~ =================
+    // ================= epilogue: per-row list of the L smallest s~ (append + lazy warp-cooperative compaction) =========
+    // A thread owns one query row.  Rows that pass  d < thr && d <= bound  are APPENDED to the row's buffer (two stores);
+    // when a buffer could overflow in the next 32 columns the whole warp compacts it to its L smallest entries (sorted)
+    // and thr becomes the L-th smallest.  (Keeping a running maximum instead cost a serial O(L) scan per insertion in
+    // ONE lane with 31 lanes idle: 30 % of the kernel's cycles, knock-out measurement in profiles/.)
+    constexpr int CAPL = S::LMAX;       // buffer capacity = pitch (odd: conflict-free row-per-thread access)
+    constexpr int EPL = (CAPL + 31) / 32;
     const int ew = warp - 4;            // == warp % 4: TMEM lane quadrant this warp may read
     const int row = ew * 32 + lane;     // accumulator row (query inside the block)
     const int et = threadIdx.x - 128;   // 0..127
-    float* my_d = list_d + row * p.lp;
-    int32_t* my_i = list_i + row * p.lp;
+    float* my_d = list_d + row * CAPL;
+    int32_t* my_i = list_i + row * CAPL;
+    float* warp_d = list_d + ew * 32 * CAPL;
+    int32_t* warp_i = list_i + ew * 32 * CAPL;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_bar = 0, w_ld = 0, n_ins = 0, n_cmp = 0;
+    // keep the L smallest of row r's n entries, ascending, the earlier entry first among equals (all lanes take part)
+    auto compact_row = [&](int r, int n) {
+      float* rd = warp_d + r * CAPL;
+      int32_t* ri = warp_i + r * CAPL;
+      float d[EPL];
+      int32_t id[EPL];
+      int rank[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = lane + 32 * e;
+        d[e] = i < n ? rd[i] : INFINITY;
+        id[e] = i < n ? ri[i] : -1;
+        rank[e] = 0;
+      }
+      for (int j = 0; j < n; ++j) {
+        const float w = rd[j];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) rank[e] += (w < d[e] || (w == d[e] && j < lane + 32 * e)) ? 1 : 0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        if (lane + 32 * e < n && rank[e] < p.L) {
+          rd[rank[e]] = d[e];
+          ri[rank[e]] = id[e];
+        }
+      }
+      __syncwarp();
+    };
+    auto publish = [&](int qrow, float kth) {  // tighten the query's published bound of its k-th smallest s~
+      if (kth >= 0.f) atomicMin(reinterpret_cast<int*>(p.gbound + qrow), __float_as_int(kth));
+      else atomicMax(reinterpret_cast<unsigned int*>(p.gbound + qrow), __float_as_uint(kth));
+    };
     for (int u = cluster_id; u < n_units; u += n_clusters) {
-      const int strip = u / p.n_mpair, mblk = 2 * (u - strip * p.n_mpair) + (int)crank;
+      const int strip = u / p.n_mgrp, mblk = cs * (u - strip * p.n_mgrp) + (int)crank;
       const int t_begin = strip * p.tiles_per_strip;
       const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
-      for (int j = 0; j < p.L; ++j) {
-        my_d[j] = INFINITY;
-        my_i[j] = -1;
-      }
-      float thr = INFINITY;  // largest list entry: +inf until the list is full
-      int pmax = 0;
+      int cnt = 0;           // entries in my buffer
+      float thr = INFINITY;  // L-th smallest at the last compaction: +inf before the first
       const int qrow = mblk * BM + row;
       const bool live = qrow < p.Q;
       const float coef = live ? __ldg(p.qcoef + qrow) : 0.f;
-      // upper bound of the query's k-th smallest s~ published by strips that finished earlier, plus the slack: a row
-      // above it cannot be one of the k nearest (see the header); +inf while nothing is published
-      const float gb2 = live ? __ldcg(p.gbound + qrow) + __ldg(p.qslack + qrow) : -INFINITY;
+      const float slack = live ? __ldg(p.qslack + qrow) : 0.f;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = t * BN;
+        // upper bound of the query's k-th smallest s~ published so far (by any strip, any CTA), plus the slack: a row
+        // above it cannot be one of the k nearest (see the header); +inf while nothing is published
+        float gb2 = live ? __ldcg(p.gbound + qrow) + slack : -INFINITY;
         // stage |x|^2 of this tile (+inf past the end of the shard so padded columns never enter a list)
         float* xs = xn_s + acc * BN;
 #pragma unroll
@@ -330,67 +530,98 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           const int n = n0 + et + i * 128;
           xs[et + i * 128] = n < p.N ? __ldg(p.xnorm + n) : INFINITY;
         }
+        const long long tb0 = prof ? clock64() : 0;
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(tfull_bar(acc), acc_phase);
+        if (prof) w_bar += clock64() - tb0;
+        mbar_wait_t(tfull_bar(acc), acc_phase, prof, w0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < ((p.knock & 2) ? 0 : BN / 32); ++c) {
+          // room for 32 more entries in every buffer of the warp
+          unsigned need = __ballot_sync(0xffffffffu, cnt > CAPL - 32);
+          while (need) {
+            const int r = __ffs(need) - 1;
+            need &= need - 1;
+            compact_row(r, __shfl_sync(0xffffffffu, cnt, r));
+            if (lane == r) {
+              cnt = p.L;
+              thr = my_d[p.L - 1];
+              const float kth = my_d[p.k - 1];  // k-th smallest of the strip so far: a valid bound already
+              if (live) publish(qrow, kth);
+              gb2 = fminf(gb2, kth + slack);
+              ++n_cmp;
+            }
+          }
           float v[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after divergent list insertions
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after divergent appends
+          const long long tl0 = prof ? clock64() : 0;
           tmem_ld32(taddr + (uint32_t)(c * 32), v);
+          if (prof) w_ld += clock64() - tl0;
+          const float4* xs4 = reinterpret_cast<const float4*>(xs + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = fmaf(coef, v[j], xs[c * 32 + j]);
-            // keep the L smallest (strict: the first row seen wins a tie) among the rows the published bound allows
-            if (d < thr && d <= gb2) {
-              my_d[pmax] = d;
-              my_i[pmax] = n0 + c * 32 + j;
-              thr = my_d[0];
-              pmax = 0;
-              for (int q = 1; q < p.L; ++q) {
-                const float w = my_d[q];
-                if (w > thr) {
-                  thr = w;
-                  pmax = q;
-                }
+          for (int j = 0; j < 8; ++j) {
+            const float4 x4 = xs4[j];
+            v[4 * j + 0] = fmaf(coef, v[4 * j + 0], x4.x);
+            v[4 * j + 1] = fmaf(coef, v[4 * j + 1], x4.y);
+            v[4 * j + 2] = fmaf(coef, v[4 * j + 2], x4.z);
+            v[4 * j + 3] = fmaf(coef, v[4 * j + 3], x4.w);
+          }
+          float m[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = fminf(fminf(v[4 * j], v[4 * j + 1]), fminf(v[4 * j + 2], v[4 * j + 3]));
+          const float mn = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+          if (mn < thr && mn <= gb2 && !(p.knock & 1)) {  // rare per lane: some column of this chunk belongs in the list
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] < thr && v[j] <= gb2) {
+                my_d[cnt] = v[j];
+                my_i[cnt] = n0 + c * 32 + j;
+                ++cnt;
               }
             }
+            ++n_ins;
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(tempty_bar(acc), leader_rank));
+          else mbar_arrive(tempty_bar(acc));
+        }
         if (++acc == ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
-      // flush this (query block, strip) list; its k-th smallest entry tightens the published bound
+      // flush this (query block, strip) list: sort every row's buffer (its L smallest, ascending); the k-th smallest
+      // entry tightens the published bound
+      __syncwarp();
+      for (int r = 0; r < 32; ++r) {
+        const int n = __shfl_sync(0xffffffffu, cnt, r);
+        if (n > 1) compact_row(r, n);
+      }
+      cnt = cnt < p.L ? cnt : p.L;
       if (live) {
-        float kth = INFINITY;
-        if (p.L == p.k) {
-          kth = thr;
-        } else {
-          for (int a = 0; a < p.L; ++a) {  // entry of rank k-1 (ties ordered by slot)
-            const float da = my_d[a];
-            int rank = 0;
-            for (int b = 0; b < p.L; ++b) {
-              const float db = my_d[b];
-              rank += (db < da || (db == da && b < a)) ? 1 : 0;
-            }
-            if (rank == p.k - 1) kth = da;
-          }
-        }
-        if (kth < INFINITY) {
-          if (kth >= 0.f) atomicMin(reinterpret_cast<int*>(p.gbound + qrow), __float_as_int(kth));
-          else atomicMax(reinterpret_cast<unsigned int*>(p.gbound + qrow), __float_as_uint(kth));
-        }
+        if (cnt >= p.k) publish(qrow, my_d[p.k - 1]);
         const size_t o = ((size_t)qrow * p.n_strips + strip) * p.L;
         for (int j = 0; j < p.L; ++j) {
-          p.cand_d[o + j] = my_d[j];
-          p.cand_i[o + j] = my_i[j];
+          p.cand_d[o + j] = j < cnt ? my_d[j] : INFINITY;
+          p.cand_i[o + j] = j < cnt ? my_i[j] : -1;
         }
+      }
+      __syncwarp();
+    }
+    if (prof && ew == 0) {
+      const long long ins_sum = warp_sum_ll(n_ins);
+      if (lane == 0) {
+        p.dbg[blockIdx.x * 16 + 4] = w0;                   // epilogue warp 0: waiting for a finished accumulator,
+        p.dbg[blockIdx.x * 16 + 5] = clock64() - t_start;  // its total,
+        p.dbg[blockIdx.x * 16 + 7] = w_ld;                 // inside tcgen05.ld + wait::ld,
+        p.dbg[blockIdx.x * 16 + 8] = w_bar;                // at the named barrier of the four epilogue warps,
+        p.dbg[blockIdx.x * 16 + 9] = n_ins;                // 32-column chunks with an append, one row
+        p.dbg[blockIdx.x * 16 + 10] = ins_sum;             // and the warp's 32 rows
+        p.dbg[blockIdx.x * 16 + 11] = n_cmp;               // compactions of one row
       }
     }
   }
@@ -400,8 +631,12 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   cluster_sync();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -898,7 +1133,7 @@ static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 static inline int dpad_of(int d) { return (d + BK - 1) / BK * BK; }
 
 struct Layout {
-  int dpad, n_mblk, n_tiles, tiles_per_strip, n_strips, qpad, L, stages;
+  int dpad, n_mblk, n_tiles, tiles_per_strip, n_strips, qpad, L, stages, cs, pair;
   size_t off_qb, off_qn, off_qc, off_qs, off_gb, off_cd, off_ci, off_si, off_sn, off_fl, off_lk, total;
 };
 
@@ -907,9 +1142,36 @@ static int forced_stages() {
   if (v < 0) {
     const char* e = getenv("NVS_RETR_STAGES");
     v = e ? atoi(e) : 0;
-    if (v != 2 && v != 3 && v != 4) v = 0;
+    if (v < 2 || v > 6) v = 0;
   }
   return v;
+}
+
+// cta_group::2 pairs (default) or one MMA per CTA (NVS_RETR_PAIR=0, the kernel of the earlier rounds, kept for A/B runs)
+static int pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVS_RETR_PAIR");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
+// CTAs per cluster.  Every CTA of a cluster works on its own 128-query block against the SAME database tile and loads
+// 1/cs of it for all (TMA multicast), so a k-block costs 16 KB (A) + 32/cs KB (B slice) of L2 -> SM traffic per CTA:
+// 32 KB at cs = 2, 24 KB at 4, 20 KB at 8 against 512 cycles of MMA time.  The kernel runs against the board's power
+// limit (SM clock 1.0-1.5 GHz under load), so bytes moved per FLOP decide the speed: measured at 10k x 1M x 4096 on
+// cta_group::2 pairs 977 / 1037 / 1070 TFLOP/s with cs = 2 / 4 / 8 (SM clock 1.03 / 1.40 / 1.43 GHz) although only
+// 132 / 120 of the 148 SMs can hold clusters of 4 / 8.  NVS_RETR_CLUSTER = 2 / 4 / 8 for A/B runs.
+static int cluster_size_for(int n_mblk) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("NVS_RETR_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    forced = (v == 2 || v == 4 || v == 8) ? v : 0;
+  }
+  if (forced) return forced;
+  return n_mblk >= 24 ? 8 : (n_mblk >= 8 ? 4 : 2);  // few query blocks: small clusters waste fewer CTAs on padding
 }
 
 static Layout make_layout(long long n_db, int nq, int d, int k) {
@@ -919,21 +1181,34 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   L.qpad = L.n_mblk * BM;
   L.n_tiles = (int)((n_db + BN - 1) / BN);
   // per-row list length: k plus room for rows inside the slack (a list that fills up with them flags the query for
-  // the exact scan); the 4-stage kernel holds 31 entries per row, the 3-stage one 79
+  // the exact scan).  NVS_RETR_STAGES forces the ring depth for A/B runs.
   int want_l = k + (k / 4 > 6 ? k / 4 : 6);
-  // three operand stages: measured 10 % faster than four at 10k x 1M x 4096 (98.2 vs 109.0 ms, same lists) and room
-  // for lists of 79; NVS_RETR_STAGES = 2 / 3 / 4 for A/B runs
-  auto lmax_of = [](int st) { return st == 4 ? Smem<4>::LMAX : (st == 3 ? Smem<3>::LMAX : Smem<2>::LMAX); };
+  L.pair = pair_mode();
   const int fs = forced_stages();
-  L.stages = fs ? fs : 3;
-  if (k > lmax_of(L.stages)) L.stages = 3;
-  L.L = want_l < lmax_of(L.stages) ? want_l : lmax_of(L.stages);
-  // Strips (each (strip, query-block pair) is one work unit of a CTA pair and yields L listed rows per query):
-  // enough units for ~32 rounds over the 74 clusters of a B200 (load balance to ~2 %), no more -- every strip
+  // The epilogue appends to per-row buffers of LMAX entries and compacts them to L when fewer than 32 slots are left:
+  // LMAX >= L + 32 is required, L + 64 keeps compactions rare.  PAIR (32 KiB stages): 5 stages -> 63, 4 -> 95, 3 -> 127;
+  // one MMA per CTA (48 KiB stages): 3 -> 79, 2 -> 127.
+  int lmax;
+  if (L.pair) {
+    auto lmax_of = [](int st) { return st == 5 ? Smem<5, true>::LMAX : (st == 4 ? Smem<4, true>::LMAX : Smem<3, true>::LMAX); };
+    L.stages = want_l + 64 <= lmax_of(4) ? 4 : 3;
+    if (fs >= 3 && fs <= 5 && lmax_of(fs) >= k + 32) L.stages = fs;
+    lmax = lmax_of(L.stages);
+  } else {
+    auto lmax_of = [](int st) { return st == 3 ? Smem<3, false>::LMAX : Smem<2, false>::LMAX; };
+    L.stages = want_l + 32 <= lmax_of(3) ? 3 : 2;
+    if (fs >= 2 && fs <= 3 && lmax_of(fs) >= k + 32) L.stages = fs;
+    lmax = lmax_of(L.stages);
+  }
+  lmax -= 32;
+  L.L = want_l < lmax ? want_l : lmax;
+  // Strips (each (strip, query-block group) is one work unit of a cluster and yields L listed rows per query):
+  // enough units for ~32 rounds over the 148 / cs clusters of a B200 (load balance to ~2 %), no more -- every strip
   // restarts its per-row lists -- at most 256 (and what the selection kernel can hold), at least 16 tiles
   // (4096 rows) each.
-  const int n_mpair = (L.n_mblk + 1) / 2;
-  int want = (32 * 74 + n_mpair - 1) / n_mpair;
+  L.cs = cluster_size_for(L.n_mblk);
+  const int n_mgrp = (L.n_mblk + L.cs - 1) / L.cs;
+  int want = (32 * (148 / L.cs) + n_mgrp - 1) / n_mgrp;
   if (want > 256) want = 256;
   if (want > MAX_CAND / L.L) want = MAX_CAND / L.L;
   int tps = (L.n_tiles + want - 1) / want;
@@ -956,14 +1231,40 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   return L;
 }
 
-template <int STAGES>
+static long long* g_dbg = nullptr;
+
+template <int STAGES, bool PAIR>
 static int launch_gemm(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, int n_units, cudaStream_t st) {
-  auto kern = flat_l2_topk_kernel<STAGES>;
-  NVS_OPT_IN_SMEM(kern, Smem<STAGES>::BYTES);
+  auto kern = flat_l2_topk_kernel<STAGES, PAIR>;
+  NVS_OPT_IN_SMEM(kern, (Smem<STAGES, PAIR>::BYTES));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Smem<STAGES, PAIR>::BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // clusters that can be resident at once (one CTA per SM; a cluster lives inside one GPC): per device and size
+  static int resident[64][9] = {{0}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n_res = __atomic_load_n(&resident[dev & 63][p.cs], __ATOMIC_ACQUIRE);
+  if (n_res == 0) {
+    cfg.gridDim = dim3((unsigned)(nvs_sm_count() / p.cs * p.cs));
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n_res, kern, &cfg);
+    if (e != cudaSuccess) return nvs_set_cuda_error(e);
+    if (n_res <= 0) return NVS_ERR_CUDA;
+    __atomic_store_n(&resident[dev & 63][p.cs], n_res, __ATOMIC_RELEASE);
+  }
   const int sms = nvs_sm_count();
-  const int grid = 2 * (n_units < sms / 2 ? n_units : sms / 2);  // clusters of two CTAs
-  kern<<<grid, THREADS, Smem<STAGES>::BYTES, st>>>(mq, mx, p);
-  NVS_CHECK_LAUNCH();
+  if (n_res > sms / p.cs) n_res = sms / p.cs;
+  cfg.gridDim = dim3((unsigned)(p.cs * (n_units < n_res ? n_units : n_res)));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mx, p);
+  if (e != cudaSuccess) return nvs_set_cuda_error(e);
   return NVS_OK;
 }
 
@@ -993,6 +1294,10 @@ extern "C" int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_f1
 }
 
 extern "C" int32_t nvs_flat_max_k(void) { return KMAX; }
+
+// debugging aid (tools/retr_waits.py): 16 int64 per CTA written by every following GEMM launch -- MMA-role cycles, producer
+// wait, MMA wait for operands, MMA wait for an accumulator, epilogue wait, epilogue cycles, k-blocks, unused
+extern "C" void nvs_flat_debug_buffer(long long* dev_buf) { nvs::rt::g_dbg = dev_buf; }
 
 extern "C" size_t nvs_flat_search_workspace_bytes(int64_t n_db, int32_t nq, int32_t d, int32_t k) {
   if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > KMAX) return 0;
@@ -1046,19 +1351,32 @@ static int flat_search_impl(const float* db, const void* db_f16, const float* db
 
     CUtensorMap mq, mx;
     if (make_map(&mq, qb, (uint64_t)L.qpad, (uint64_t)L.dpad, BM) != NVS_OK) return NVS_ERR_CUDA;
-    if (make_map(&mx, db_f16, (uint64_t)n_db, (uint64_t)L.dpad, BN / 2) != NVS_OK) return NVS_ERR_CUDA;  // half tiles
+    if (make_map(&mx, db_f16, (uint64_t)n_db, (uint64_t)L.dpad, BN / L.cs) != NVS_OK) return NVS_ERR_CUDA;  // tile slices
 
     Params p;
     p.xnorm = db_norms; p.qcoef = qc; p.qslack = qs; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
     p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
-    p.k = k; p.L = L.L; p.lp = L.L | 1;
+    p.k = k; p.L = L.L;
     p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;
-    p.n_mpair = (L.n_mblk + 1) / 2;
-    const int n_units = p.n_mpair * L.n_strips;  // work units of CTA pairs
+    p.cs = L.cs;
+    p.dbg = g_dbg;
+    {
+      const char* e = getenv("NVS_RETR_KNOCK");
+      p.knock = e ? atoi(e) : 0;
+      const char* h = getenv("NVS_RETR_HINT");
+      p.hint = h ? atoi(h) : 2;  // measured at 10k x 1M x 4096: 1061 / 1102 / 1111 / 1103 TFLOP/s with hints 0 / 1 / 2 / 3
+    }
+    p.n_mgrp = (L.n_mblk + L.cs - 1) / L.cs;
+    const int n_units = p.n_mgrp * L.n_strips;  // work units of clusters
 
     if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
-    int rc = L.stages == 4 ? launch_gemm<4>(mq, mx, p, n_units, st)
-                           : (L.stages == 3 ? launch_gemm<3>(mq, mx, p, n_units, st) : launch_gemm<2>(mq, mx, p, n_units, st));
+    int rc;
+    if (L.pair)
+      rc = L.stages == 5 ? launch_gemm<5, true>(mq, mx, p, n_units, st)
+                         : (L.stages == 4 ? launch_gemm<4, true>(mq, mx, p, n_units, st)
+                                          : launch_gemm<3, true>(mq, mx, p, n_units, st));
+    else
+      rc = L.stages == 3 ? launch_gemm<3, false>(mq, mx, p, n_units, st) : launch_gemm<2, false>(mq, mx, p, n_units, st);
     if (rc != NVS_OK) return rc;
     if (ev_gemm_stop) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_stop), st);
     if (phase == 1) {

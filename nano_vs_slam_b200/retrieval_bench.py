@@ -14,6 +14,15 @@ import statistics
 import torch
 
 
+def shard_rows(world: int, rank: int, n_db: int = None) -> int:
+    """Database rows of this rank's shard in run()."""
+    from .retrieval import shard_bounds
+
+    n_db = int(os.environ.get("NVS_RETR_NDB", 1_000_000)) if n_db is None else n_db
+    lo, hi = shard_bounds(n_db, world, rank)
+    return hi - lo
+
+
 def run(dev, world: int, rank: int, n_db: int = None, n_q: int = None, dim: int = 4096, k: int = 25,
         steps: int = 5, warmup: int = 2):
     import torch.distributed as dist
@@ -64,7 +73,7 @@ def run(dev, world: int, rank: int, n_db: int = None, n_q: int = None, dim: int 
                                (", global k-th bound exchange + NCCL all_gather merge" if world > 1 else "")},
         "ms_per_search": ms, "gemm_kernel_ms": gemm, "topk_bit_exact_vs_planted": exact, "scaling": "strong",
         "roofline": {"bound": "tensor", "achieved": flops_rank / (gemm / 1e3) / 1e12, "unit": "TFLOP/s",
-                     "kind": "fp16 tcgen05.mma cta_group::1 128x256x16"},
+                     "kind": "fp16 tcgen05.mma cta_group::2 256x256x16, clusters of 8 CTAs"},
     }
 
 
