@@ -45,7 +45,7 @@ constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int THREADS = 256;                // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
 constexpr int KMAX = 64;                    // largest k served
 constexpr int CAP = 256;                    // candidates re-ranked exactly per query (more -> exact scan)
-constexpr int MAX_CAND = 12288;             // n_strips * L the selection kernel holds in shared memory (96 KiB)
+constexpr int MAX_CAND = 12288;             // list slots * L the selection kernel holds in shared memory (96 KiB)
 
 // shared memory map (dynamic, 1024-byte aligned base): STAGES operand stages, then the per-row lists.
 // PAIR = false: a CTA holds the whole 256-row database tile (48 KiB stages): 4 stages leave room for lists of 31 entries,
@@ -270,11 +270,11 @@ struct Params {
   const float* qcoef;   // [Qpad] -2 / (query scale * database scale): accumulator -> -2 q~.x~
   const float* qslack;  // [Qpad] 2 eps of the query
   float* gbound;        // [Qpad] running upper bound of each query's k-th smallest s~, init +inf
-  float* cand_d;        // [Qpad][n_strips][L]  s~ = |x|^2 - 2 q~.x~
-  int32_t* cand_i;      // [Qpad][n_strips][L]  row index inside this shard (-1 = empty)
+  float* cand_d;        // [Qpad][n_slots][L]  s~ = |x|^2 - 2 q~.x~
+  int32_t* cand_i;      // [Qpad][n_slots][L]  row index inside this shard (-1 = empty; preset by the host)
   int Q, N, kblocks;    // kblocks = Dpad / 64
   int k, L;             // neighbours wanted, list length (>= k; the buffers hold L + 32 or more)
-  int n_mblk, n_strips, tiles_per_strip, n_tiles;
+  int n_mblk, n_slots, n_tiles;  // n_slots: lists per query = most clusters that can share one query-block group
   int n_mgrp;           // ceil(n_mblk / cs): a cluster of cs CTAs owns query blocks cs*grp .. cs*grp + cs - 1
   int cs;               // cluster size (2, 4 or 8): CTAs sharing every database tile by multicast
   int hint;             // L2 eviction hints of the operand loads (NVS_RETR_HINT)
@@ -349,7 +349,13 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_units = p.n_mgrp * p.n_strips;  // (strip, query-block group) units, round-robin over clusters
+  // Work = n_mgrp x n_tiles tile steps (one database tile against the cs query blocks of a group), group-major.  Cluster
+  // c owns the contiguous range [W c / nc, W (c + 1) / nc): balanced to one tile step, and a cluster stays with one
+  // query group for as long as possible -- its per-row lists live on across all those tiles (few restarts, tight
+  // thresholds, few lists per query to select from) and its query blocks stay hot in L2.  A SEGMENT = the tiles
+  // [t_begin, t_end) of one group inside the range; its lists go to slot (cluster - first cluster of the group).
+  const long long W = (long long)p.n_mgrp * p.n_tiles;
+  const long long w_begin = W * cluster_id / n_clusters, w_end = W * (cluster_id + 1) / n_clusters;
   const bool prof = p.dbg != nullptr;
   long long w0 = 0, w1 = 0, nkb = 0;
   const long long t_start = prof ? clock64() : 0;
@@ -362,10 +368,11 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // NVS_RETR_HINT (PAIR): 1 = queries evict-last (they are re-read for every strip), 2 = database rows evict-first
       const uint64_t hint_q = (p.hint & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
       const uint64_t hint_x = (p.hint & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-      for (int u = cluster_id; u < n_units; u += n_clusters) {
-        const int strip = u / p.n_mgrp, mblk = cs * (u - strip * p.n_mgrp) + (int)crank;
-        const int t_begin = strip * p.tiles_per_strip;
-        const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
+      for (long long w = w_begin; w < w_end;) {
+        const int grp = (int)(w / p.n_tiles), mblk = cs * grp + (int)crank;
+        const int t_begin = (int)(w - (long long)grp * p.n_tiles);
+        const int t_end = (int)min((long long)p.n_tiles, t_begin + (w_end - w));
+        w += t_end - t_begin;
         for (int t = t_begin; t < t_end; ++t) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait_t(empty_bar(stage), phase ^ 1, prof, w0);
@@ -403,11 +410,8 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (leader) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int u = cluster_id; u < n_units; u += n_clusters) {
-        const int strip = u / p.n_mgrp;
-        const int t_begin = strip * p.tiles_per_strip;
-        const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
-        for (int t = t_begin; t < t_end; ++t) {
+      {
+        for (long long t = w_begin; t < w_end; ++t) {  // tile steps: the MMA role does not care about segments
           // epilogue (PAIR: of both CTAs) has drained this accumulator
           if constexpr (PAIR) mbar_wait_cluster_t(tempty_bar(acc), acc_phase ^ 1, prof, w1);
           else mbar_wait_t(tempty_bar(acc), acc_phase ^ 1, prof, w1);
@@ -508,10 +512,17 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (kth >= 0.f) atomicMin(reinterpret_cast<int*>(p.gbound + qrow), __float_as_int(kth));
       else atomicMax(reinterpret_cast<unsigned int*>(p.gbound + qrow), __float_as_uint(kth));
     };
-    for (int u = cluster_id; u < n_units; u += n_clusters) {
-      const int strip = u / p.n_mgrp, mblk = cs * (u - strip * p.n_mgrp) + (int)crank;
-      const int t_begin = strip * p.tiles_per_strip;
-      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_strip);
+    for (long long w = w_begin; w < w_end;) {
+      const int grp = (int)(w / p.n_tiles), mblk = cs * grp + (int)crank;
+      const int t_begin = (int)(w - (long long)grp * p.n_tiles);
+      const int t_end = (int)min((long long)p.n_tiles, t_begin + (w_end - w));
+      w += t_end - t_begin;
+      // list slot of this segment: clusters sharing the group are consecutive; c0 = the one owning the group's first tile
+      const long long g0 = (long long)grp * p.n_tiles;
+      int c0 = (int)(g0 * n_clusters / W);
+      while (W * (c0 + 1) / n_clusters <= g0) ++c0;
+      while (W * c0 / n_clusters > g0) --c0;
+      const int slot = cluster_id - c0;
       int cnt = 0;           // entries in my buffer
       float thr = INFINITY;  // L-th smallest at the last compaction: +inf before the first
       const int qrow = mblk * BM + row;
@@ -594,7 +605,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           acc_phase ^= 1;
         }
       }
-      // flush this (query block, strip) list: sort every row's buffer (its L smallest, ascending); the k-th smallest
+      // flush this segment's lists: sort every row's buffer (its L smallest, ascending); the k-th smallest
       // entry tightens the published bound
       __syncwarp();
       for (int r = 0; r < 32; ++r) {
@@ -604,7 +615,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       cnt = cnt < p.L ? cnt : p.L;
       if (live) {
         if (cnt >= p.k) publish(qrow, my_d[p.k - 1]);
-        const size_t o = ((size_t)qrow * p.n_strips + strip) * p.L;
+        const size_t o = ((size_t)qrow * p.n_slots + slot) * p.L;
         for (int j = 0; j < p.L; ++j) {
           p.cand_d[o + j] = j < cnt ? my_d[j] : INFINITY;
           p.cand_i[o + j] = j < cnt ? my_i[j] : -1;
@@ -1133,7 +1144,7 @@ static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 static inline int dpad_of(int d) { return (d + BK - 1) / BK * BK; }
 
 struct Layout {
-  int dpad, n_mblk, n_tiles, tiles_per_strip, n_strips, qpad, L, stages, cs, pair;
+  int dpad, n_mblk, n_tiles, n_strips /* list slots per query */, qpad, L, stages, cs, pair;
   size_t off_qb, off_qn, off_qc, off_qs, off_gb, off_cd, off_ci, off_si, off_sn, off_fl, off_lk, total;
 };
 
@@ -1202,19 +1213,20 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
   }
   lmax -= 32;
   L.L = want_l < lmax ? want_l : lmax;
-  // Strips (each (strip, query-block group) is one work unit of a cluster and yields L listed rows per query):
-  // enough units for ~32 rounds over the 148 / cs clusters of a B200 (load balance to ~2 %), no more -- every strip
-  // restarts its per-row lists -- at most 256 (and what the selection kernel can hold), at least 16 tiles
-  // (4096 rows) each.
+  // List slots per query: the clusters that can share one query-block group.  The n_mgrp x n_tiles tile steps are cut
+  // into one contiguous range per cluster (group-major); a group of n_tiles steps meets at most
+  // ceil(n_tiles / shortest range) + 1 ranges.  (10k queries, clusters of 8 on 148 SMs: 18 clusters, 10 groups -> 3.)
   L.cs = cluster_size_for(L.n_mblk);
   const int n_mgrp = (L.n_mblk + L.cs - 1) / L.cs;
-  int want = (32 * (148 / L.cs) + n_mgrp - 1) / n_mgrp;
-  if (want > 256) want = 256;
-  if (want > MAX_CAND / L.L) want = MAX_CAND / L.L;
-  int tps = (L.n_tiles + want - 1) / want;
-  if (tps < 16) tps = 16;
-  L.tiles_per_strip = tps;
-  L.n_strips = (L.n_tiles + tps - 1) / tps;
+  {
+    const long long W = (long long)n_mgrp * L.n_tiles;
+    const int sms = nvs_sm_count();
+    long long nc = (sms > 0 ? sms : 148) / L.cs;  // (no device: size the workspace for a B200)
+    if (nc < 1) nc = 1;
+    if (nc > W) nc = W;
+    const long long per = W / nc;  // >= 1
+    L.n_strips = (int)((L.n_tiles + per - 1) / per) + 1;
+  }
   size_t o = 0;
   L.off_qb = o; o += al256((size_t)L.qpad * L.dpad * 2);
   L.off_qn = o; o += al256((size_t)L.qpad * 4);
@@ -1234,7 +1246,7 @@ static Layout make_layout(long long n_db, int nq, int d, int k) {
 static long long* g_dbg = nullptr;
 
 template <int STAGES, bool PAIR>
-static int launch_gemm(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, int n_units, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, long long n_steps, cudaStream_t st) {
   auto kern = flat_l2_topk_kernel<STAGES, PAIR>;
   NVS_OPT_IN_SMEM(kern, (Smem<STAGES, PAIR>::BYTES));
   cudaLaunchConfig_t cfg = {};
@@ -1262,7 +1274,7 @@ static int launch_gemm(const CUtensorMap& mq, const CUtensorMap& mx, const Param
   }
   const int sms = nvs_sm_count();
   if (n_res > sms / p.cs) n_res = sms / p.cs;
-  cfg.gridDim = dim3((unsigned)(p.cs * (n_units < n_res ? n_units : n_res)));
+  cfg.gridDim = dim3((unsigned)(p.cs * (n_steps < n_res ? (int)n_steps : n_res)));  // never more clusters than tile steps
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mx, p);
   if (e != cudaSuccess) return nvs_set_cuda_error(e);
   return NVS_OK;
@@ -1335,6 +1347,7 @@ static int flat_search_impl(const float* db, const void* db_f16, const float* db
   int32_t* fl = reinterpret_cast<int32_t*>(ws + L.off_fl);
   int* lk = reinterpret_cast<int*>(ws + L.off_lk);
   const int n_cand = L.n_strips * L.L;
+  if (n_cand > MAX_CAND) return NVS_ERR_UNSUPPORTED;  // the selection kernel holds a query's lists in shared memory
   NVS_OPT_IN_SMEM(select_candidates_kernel, 96 * 1024);
 
   if (phase != 2) {
@@ -1357,7 +1370,7 @@ static int flat_search_impl(const float* db, const void* db_f16, const float* db
     p.xnorm = db_norms; p.qcoef = qc; p.qslack = qs; p.gbound = gb; p.cand_d = cd; p.cand_i = ci;
     p.Q = nq; p.N = (int)n_db; p.kblocks = L.dpad / BK;
     p.k = k; p.L = L.L;
-    p.n_mblk = L.n_mblk; p.n_strips = L.n_strips; p.tiles_per_strip = L.tiles_per_strip; p.n_tiles = L.n_tiles;
+    p.n_mblk = L.n_mblk; p.n_slots = L.n_strips; p.n_tiles = L.n_tiles;
     p.cs = L.cs;
     p.dbg = g_dbg;
     {
@@ -1367,7 +1380,9 @@ static int flat_search_impl(const float* db, const void* db_f16, const float* db
       p.hint = h ? atoi(h) : 2;  // measured at 10k x 1M x 4096: 1061 / 1102 / 1111 / 1103 TFLOP/s with hints 0 / 1 / 2 / 3
     }
     p.n_mgrp = (L.n_mblk + L.cs - 1) / L.cs;
-    const int n_units = p.n_mgrp * L.n_strips;  // work units of clusters
+    const long long n_units = (long long)p.n_mgrp * L.n_tiles;  // tile steps, cut into one range per cluster
+    // empty list slots (a group met by fewer clusters than slots) must read as empty: labels -1
+    if (cudaMemsetAsync(ci, 0xFF, (size_t)L.qpad * L.n_strips * L.L * 4, st) != cudaSuccess) return NVS_ERR_CUDA;
 
     if (ev_gemm_start) cudaEventRecord(static_cast<cudaEvent_t>(ev_gemm_start), st);
     int rc;

@@ -99,10 +99,18 @@ class IndexFlatL2(object):
 
     # --- two-phase search of one shard of a sharded database (nanovs.h: nvs_flat_search_begin / _end) -------------
     def _workspace(self, nq: int, k: int) -> torch.Tensor:
+        """Workspace of slot ``self._slot`` (the lists travel in it from search_begin to search_end; a caller that
+        pipelines query chunks over two streams alternates the slot)."""
         nbytes = int(lib().nvs_flat_search_workspace_bytes(self.ntotal, nq, self.d, k))
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        return self._ws
+        slot = getattr(self, "_slot", 0)
+        if slot == 0:
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            return self._ws
+        extra = self.__dict__.setdefault("_ws_extra", {})
+        if slot not in extra or extra[slot].numel() < nbytes:
+            extra[slot] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return extra[slot]
 
     def _begin_impl(self, q: torch.Tensor, k: int) -> torch.Tensor:
         gemm_events = getattr(self, "_gemm_events", None)
@@ -254,24 +262,91 @@ class ShardedIndexFlatL2(object):
                 return self._index.search_device(q.to(self.device, torch.float32).contiguous(), k, id_offset=self.lo,
                                                  gemm_events=gemm_events)
             return self._local_search(self._shard, q, k, self.lo)
-        # ONE packed buffer per rank (labels, then distances) -> ONE all_gather; the shard search writes straight
-        # into this rank's send buffer and the merge kernel reads the gathered parts in place
+        if self._index is not None:
+            return self._search_pipelined(q, k, gemm_events)
+        # ONE packed buffer per rank (labels, then distances) -> ONE all_gather; the merge reads the gathered parts in place
         words = nq * k + (nq * k + 1) // 2
-        dev = self.device if self._index is not None else q.device
+        dev = q.device
         mine = torch.empty(1, words, dtype=torch.int64, device=dev)
         Dm, Im = self._packed_views(mine, 1, nq, k)
-        if self._index is not None:
-            # two phases around one tiny allreduce: every shard re-ranks only the rows inside the GLOBAL k-th bound
-            qd = q.to(self.device, torch.float32).contiguous()
-            mine_b = self._index.search_begin(qd, k, gemm_events=gemm_events)
-            all_b = torch.empty(self.world, nq, k, dtype=torch.float32, device=self.device)
-            self.dist.all_gather_into_tensor(all_b, mine_b, group=self.group)
-            self._index.search_end(qd, k, merge_bounds(all_b), id_offset=self.lo, out=(Dm[0], Im[0]))
-        else:
-            D, I = self._local_search(self._shard, q, k, self.lo)
-            Dm[0].copy_(D)
-            Im[0].copy_(I)
+        D, I = self._local_search(self._shard, q, k, self.lo)
+        Dm[0].copy_(D)
+        Im[0].copy_(I)
         gathered = torch.empty(self.world, words, dtype=torch.int64, device=dev)
         self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
         Dg, Ig = self._packed_views(gathered, self.world, nq, k)
         return self._merge(Dg, Ig)
+
+    @staticmethod
+    def query_chunks(nq: int, chunk: Optional[int] = None):
+        """[a, b) query ranges of the pipelined sharded search: chunks of NVS_RETR_CHUNK queries, a last chunk below 512
+        queries joins its predecessor.  Default: ONE chunk -- measured at 10k x 1M x 4096 (profiles/r2_retrieval_chunking.txt)
+        the GEMM loses more on shorter launches (N = 8: 10.6 -> 13.1 ms, N = 4: 20.1 -> 22.3 ms) than the hidden
+        exchange tail (1.1 - 2 ms) is worth."""
+        import os
+
+        chunk = int(os.environ.get("NVS_RETR_CHUNK", 1 << 30)) if chunk is None else chunk
+        chunk = max(128, chunk)
+        edges = list(range(0, nq, chunk)) + [nq]
+        if len(edges) > 2 and edges[-1] - edges[-2] < 512:
+            del edges[-2]
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+
+    def _search_pipelined(self, q: torch.Tensor, k: int, gemm_events=None):
+        """Sharded search on the CUDA kernels, pipelined over query chunks: the GEMM of chunk j + 1 (main stream) runs
+        while chunk j's exchange tail -- all_gather of the per-shard k-th bounds, re-rank inside the GLOBAL bound,
+        all_gather of the packed (labels, distances) parts, merge -- runs on a side stream.  Only the last chunk's tail
+        is exposed.  ``gemm_events``: a list that receives one (start, stop) event pair per chunk, or one pair
+        (recorded around the first chunk only)."""
+        dev = self.device
+        qd = q.to(dev, torch.float32).contiguous()
+        nq = qd.shape[0]
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        chunks = self.query_chunks(nq)
+        keep, outs, done = [], [], []
+        for j, (a, b) in enumerate(chunks):
+            n = b - a
+            qj = qd[a:b]
+            ge = None
+            if isinstance(gemm_events, list):
+                ge = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                gemm_events.append(ge)
+            elif gemm_events is not None and j == 0:
+                ge = gemm_events
+            self._index._slot = j % 2
+            if j >= 2:
+                main.wait_event(done[j - 2])  # the workspace slot is free again
+            mine_b = self._index.search_begin(qj, k, gemm_events=ge)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                all_b = torch.empty(self.world, n, k, dtype=torch.float32, device=dev)
+                self.dist.all_gather_into_tensor(all_b, mine_b, group=self.group)
+                words = n * k + (n * k + 1) // 2
+                mine = torch.empty(1, words, dtype=torch.int64, device=dev)
+                Dm, Im = self._packed_views(mine, 1, n, k)
+                self._index._slot = j % 2
+                self._index.search_end(qj, k, merge_bounds(all_b), id_offset=self.lo, out=(Dm[0], Im[0]))
+                gathered = torch.empty(self.world, words, dtype=torch.int64, device=dev)
+                self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
+                Dg, Ig = self._packed_views(gathered, self.world, n, k)
+                outs.append(self._merge(Dg, Ig))
+                d = torch.cuda.Event()
+                d.record(side)
+                done.append(d)
+            keep.append((qj, mine_b, all_b, mine, gathered))  # alive until the main stream has waited for the side stream
+        self._index._slot = 0
+        main.wait_stream(side)
+        for D, I in outs:
+            D.record_stream(main)
+            I.record_stream(main)
+        if len(outs) == 1:
+            return outs[0]
+        D = torch.cat([o[0] for o in outs], 0)
+        I = torch.cat([o[1] for o in outs], 0)
+        del keep
+        return D, I

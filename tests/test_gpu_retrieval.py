@@ -244,3 +244,52 @@ def test_flat_l2_two_phase_sharded_search_is_exact(shards):
         # query, not k each (clustered data: ~100 rows per query are inside the error bound wherever they live)
         kept = sum(int((I >= 0).sum()) for I in Is) / (q.shape[0] * k)
         assert kind == "cluster" or kept < 1.3, kept
+
+
+def test_query_chunks_cover_the_queries():
+    """Host logic of the pipelined sharded search: contiguous chunks, a short last chunk joins its predecessor."""
+    from nano_vs_slam_b200.retrieval import ShardedIndexFlatL2
+
+    for nq, chunk in ((10000, 4096), (4096, 4096), (4097, 4096), (4700, 4096), (1, 4096), (9000, 1024), (300, 128)):
+        ch = ShardedIndexFlatL2.query_chunks(nq, chunk)
+        assert ch[0][0] == 0 and ch[-1][1] == nq
+        assert all(a < b for a, b in ch) and all(ch[i][1] == ch[i + 1][0] for i in range(len(ch) - 1))
+        assert all(b - a <= chunk + 511 for a, b in ch)
+        assert len(ch) == 1 or ch[-1][1] - ch[-1][0] >= min(512, chunk)
+    assert ShardedIndexFlatL2.query_chunks(10000, 4096) == [(0, 4096), (4096, 8192), (8192, 10000)]
+    assert ShardedIndexFlatL2.query_chunks(10000) == [(0, 10000)]  # default: one chunk
+
+
+@gpu
+def test_pipelined_sharded_search_matches_single_index(tmp_path, monkeypatch):
+    """ShardedIndexFlatL2._search_pipelined (query chunks: GEMM on the main stream, exchange tail on a side stream, two
+    workspace slots) in a one-rank NCCL group, five chunks: identical to the plain single-index search."""
+    import torch.distributed as dist
+
+    from nano_vs_slam_b200.retrieval import IndexFlatL2, ShardedIndexFlatL2
+    from nano_vs_slam_b200.synthetic import planted_retrieval_set
+
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        k = 25
+        db, q, planted = planted_retrieval_set(40000, 1300, 256, k, seed=5, device="cuda")
+        whole = IndexFlatL2(256)
+        whole.add(db)
+        Dw, Iw = whole.search(q, k)
+        monkeypatch.setenv("NVS_RETR_CHUNK", "256")
+        idx = ShardedIndexFlatL2(256, db.shape[0], device="cuda")
+        idx.add_local(db)
+        assert len(idx.query_chunks(q.shape[0])) == 5  # 4 x 256 + 276
+        for _ in range(2):  # second pass: the workspace slots and the side stream are reused
+            ge = []
+            D, I = idx._search_pipelined(q, k, gemm_events=ge)
+            torch.cuda.synchronize()
+            assert len(ge) == 5 and all(a.elapsed_time(b) > 0 for a, b in ge)
+            assert torch.equal(I, Iw) and torch.equal(I.cpu(), planted.cpu())
+            assert torch.equal(D, Dw)
+    finally:
+        if created:
+            dist.destroy_process_group()
