@@ -107,6 +107,7 @@ struct Params {
   int w_stages;            // weight ring depth; >= 3 * chunks means resident (every tile loaded once)
   int na;                  // A slots (2 or 3)
   int store_nhwc, store_pool;  // channels-last output / pooled output (split format)
+  int ps_staged;               // PixelShuffle outputs through the quadrant staging cells (Cout = 64 launches, full width)
   int staged;                  // 1: through the quadrant staging buffers (coalesced lines, two barriers per part); 0:
                                // one 32-byte store per thread and part (no barriers: better for one-chunk tiles)
   int issuers;             // MMA-issuing threads: 3, or 1 (fixed accumulation order)
@@ -550,7 +551,49 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         } else if (p.store_nhwc)  // this quadrant's image row: 30 positions
           staged_store(p.dst, o, lane >= 1 && lane <= TX, lane - 1, TX, p.dst_c_off, p.dst_c_total,
                        ((size_t)b * p.H + gy) * p.W + tx * TX, p.W - tx * TX, gy < p.H);
-        if (valid && p.dst_mode == 2) {
+        if (p.dst_mode == 2 && p.ps_staged && CPW == 16) {
+          // PixelShuffle(2), staged: thread = input pixel holds 4 sub-pixels x 4 shuffled channels of its warp's 16
+          // conv channels -- written directly that is 8 bytes to each of 4 output pixels 256 bytes apart (four warps
+          // per 32-byte sector).  Instead the four warps of the quadrant fill 8-byte cells [h][i * 60 + xo] (xo = output
+          // x inside the tile's 60-pixel output row i; conflict-free 16-byte stores of the (j = 0, j = 1) cell pair) and,
+          // after the quadrant's barrier, lane pairs write each output pixel's 32 bytes (one full sector) per part.
+          const int H2 = 2 * p.H, W2 = 2 * p.W;
+          const bool wr = lane >= 1 && lane <= TX;
+          uint32_t hi4[4][2], lo4[4][2];
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            split_pair(o[s4], o[4 + s4], hi4[s4][0], lo4[s4][0]);
+            split_pair(o[(8 + s4) % CPW], o[(12 + s4) % CPW], hi4[s4][1], lo4[s4][1]);
+          }
+          const size_t opx0 = ((size_t)b * H2 + 2 * gy) * W2 + 2 * tx * TX;  // output pixel of (i = 0, xo = 0)
+          const int xo_lim = W2 - 2 * tx * TX;
+          const bool row_ok = gy < p.H;
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            if (wr) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint32_t(*w4)[2] = part ? lo4 : hi4;
+                *reinterpret_cast<uint4*>(stg_q + (size_t)(h * 120 + i * 60 + 2 * (lane - 1)) * 8) =
+                    make_uint4(w4[2 * i][0], w4[2 * i][1], w4[2 * i + 1][0], w4[2 * i + 1][1]);
+              }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
+            if (row_ok) {
+              uint8_t* gb = reinterpret_cast<uint8_t*>(p.dst) + (size_t)(p.dst_c_off + part * p.dst_c_total) * 2;
+              for (int idx = qtid; idx < 240; idx += QTHREADS) {
+                const int r = idx >> 1, jc = idx & 1, i = r >= 60 ? 1 : 0, xo = r - 60 * i;
+                if (xo < xo_lim) {
+                  const uint2 c0 = *reinterpret_cast<const uint2*>(stg_q + (size_t)((2 * jc) * 120 + r) * 8);
+                  const uint2 c1 = *reinterpret_cast<const uint2*>(stg_q + (size_t)((2 * jc + 1) * 120 + r) * 8);
+                  *reinterpret_cast<uint4*>(gb + (opx0 + (size_t)i * W2 + xo) * (size_t)p.dst_c_total * 4 + jc * 16) =
+                      make_uint4(c0.x, c0.y, c1.x, c1.y);
+                }
+              }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
+          }
+        } else if (valid && p.dst_mode == 2) {
           // PixelShuffle(2) -> channels-last (B, 2H, 2W, cout/4), split format: channel c -> (c%4/2, c%2, c/4)
           const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
@@ -806,6 +849,17 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
     q.staged = mode == 1 ? 1 : (mode == 2 ? 0 : (p.c0_chunks + p.c1_chunks >= 3 ? 1 : 0));
   }
   {
+    // PixelShuffle outputs: staged full-sector stores (NVS_RS_PS=0: the direct 8-byte stores) when the launch writes
+    // all of its 64 channels and the destination channel offsets keep 16-byte alignment
+    static int ps = -1;
+    if (ps < 0) {
+      const char* e = getenv("NVS_RS_PS");
+      ps = e ? atoi(e) : 1;
+    }
+    q.ps_staged = (ps && CO == 64 && p.dst_mode == 2 && p.cout == CO && p.dst_c_off % 8 == 0 && p.dst_c_total % 4 == 0 &&
+                   C::QSTG_BYTES >= 4 * 120 * 8) ? 1 : 0;
+  }
+  {
     const char* e = getenv("NVS_RS_KNOCK");
     q.knock = e ? atoi(e) : 0;
     q.dbg = g_dbg;
@@ -892,6 +946,7 @@ int plan_init(void* plan_mem, const NvsConvTcArgs* a) {
   p.w_stages = 0;
   p.na = NA_MAX;
   p.staged = 0;
+  p.ps_staged = 0;
   p.w_scale = a->w_scale;
   p.knock = 0;
   p.dbg = nullptr;
