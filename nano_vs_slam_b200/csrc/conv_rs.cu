@@ -65,7 +65,14 @@ struct Cfg {
   // epilogue warps: TMEM lane quadrant (image row of the tile) x one of four channel groups.  The epilogue is a chain
   // of long-latency steps (TMEM loads, shuffles, scattered stores): it needs warps, not instructions per warp
   static constexpr int EPI_WARPS = 16;
-  static constexpr int CPW = CO / 4;                // output channels per epilogue warp: 16 (Cout 64) or 8 (Cout 32)
+  // Cout = 32: TWO epilogue warp sets of 8 warps (quadrant x half of the channels), set s owns accumulator stage s =
+  // every other tile.  Such tiles have too little MMA work (<= 2 chunks, ~1500 cycles) to hide one epilogue chain of
+  // ~2300 cycles (TMEM loads -> shuffles -> stores; clock64 timelines in profiles/): with two tiles in flight the chains
+  // overlap, and a thread owns 16 channels = one full 32-byte sector per store instead of half of one.
+  static constexpr bool SETS = CO == 32;
+  static constexpr int SET_WARPS = SETS ? EPI_WARPS / 2 : EPI_WARPS;  // warps that drain one accumulator stage
+  static constexpr int CPW = 16;                    // output channels per epilogue warp
+  static constexpr int LPW = SETS ? 8 : 16;         // channels per batch of TMEM loads (registers: 3 or 6 x LPW)
   static constexpr int WARP_TMA_A = EPI_WARPS, WARP_TMA_W = WARP_TMA_A + 1, WARP_MMA = WARP_TMA_W + 1;
   static constexpr int THREADS = 32 * (WARP_MMA + MAX_ISSUERS);
   // output staging: per TMEM lane quadrant one operand part (a_hi or a_lo, CO fp16 per position) of its 30 outputs
@@ -348,7 +355,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(accfull(i), p.issuers);
-      mbar_init(accempty(i), C::EPI_WARPS);
+      mbar_init(accempty(i), C::SET_WARPS);
       mbar_init(astart(i), 1);          // issuer 0 has queued the tile's first (overwriting) MMA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -369,9 +376,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // quadrant (= image row of the tile) warp % 4, channel group h = warp / 4 (16 channels); lane = position of the 32-wide strip
     // (lane 0 / 31 are halo positions).  Accumulator columns of a stage: [kx 0 | kx 1 | kx 2] x CO channels (CONCAT:
     // then the same three blocks of a_hi w_lo + a_lo w_hi).  out[i] = D_0[i-1] + D_1[i] + D_2[i+1].
-    int acc = 0;
+    const int quad = warp & 3;
+    const int set = C::SETS ? (warp >> 2) & 1 : 0;  // accumulator stage (= tile parity) this warp drains
+    const int h = C::SETS ? warp >> 3 : warp >> 2;  // group of CPW channels
+    int acc = set;
     uint32_t aph = 0;
-    const int quad = warp & 3, h = warp >> 2;
     const float neg_slope = p.act == NVS_ACT_LRELU ? 0.01f : (p.act == NVS_ACT_RELU ? 0.f : 1.f);
     int bad = 0, out_of_range = 0;
     // channels-last outputs feed the next layer's fp16 operands: flag |x| >= 60000; other outputs: flag non-finite values
@@ -422,8 +431,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         asm volatile("bar.sync %0, %1;" ::"r"(10 + quad), "n"(QTHREADS) : "memory");
       }
     };
-    TileIter ti((int)blockIdx.x, (int)gridDim.x, p.tiles_x, p.tiles_y);
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ti.next()) {
+    const int t_step = (C::SETS ? 2 : 1) * (int)gridDim.x;
+    TileIter ti((int)blockIdx.x + set * (int)gridDim.x, t_step, p.tiles_x, p.tiles_y);
+    for (int t = (int)blockIdx.x + set * (int)gridDim.x; t < p.n_tiles; t += t_step, ti.next()) {
       if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && dbg_i < 256) p.dbg[dbg_i++] = clock64();
       const int tx = ti.tx, ty = ti.ty, b = ti.b;
       const int gx = tx * TX - 1 + lane, gy = ty * TY + quad;
@@ -438,32 +448,35 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // (channels beyond cout are zero weights + zero bias: a staged store writes them, as exact zeros, with the rest)
         if (cbase >= p.cout && !(p.store_nhwc | p.store_pool)) continue;
         float o[CPW];
-        {
-          uint32_t u0[CPW], u1[CPW], u2[CPW];
-          tmem_ld_issue<CPW>(taddr + (uint32_t)cbase, u0);
-          tmem_ld_issue<CPW>(taddr + (uint32_t)(CO + cbase), u1);
-          tmem_ld_issue<CPW>(taddr + (uint32_t)(2 * CO + cbase), u2);
-          if (C::CONCAT) {  // ... and the same three blocks of a_hi w_lo + a_lo w_hi
-            uint32_t w0[CPW], w1[CPW], w2[CPW];
-            tmem_ld_issue<CPW>(taddr + (uint32_t)(C::NW + cbase), w0);
-            tmem_ld_issue<CPW>(taddr + (uint32_t)(C::NW + CO + cbase), w1);
-            tmem_ld_issue<CPW>(taddr + (uint32_t)(C::NW + 2 * CO + cbase), w2);
-            tmem_ld_wait();
-            tmem_pin<CPW>(u0); tmem_pin<CPW>(u1); tmem_pin<CPW>(u2); tmem_pin<CPW>(w0); tmem_pin<CPW>(w1); tmem_pin<CPW>(w2);
+        constexpr int LPW = C::LPW;
 #pragma unroll
-            for (int j = 0; j < CPW; ++j) {
+        for (int sb = 0; sb < CPW / LPW; ++sb) {
+          const int cb = cbase + sb * LPW;
+          uint32_t u0[LPW], u1[LPW], u2[LPW];
+          tmem_ld_issue<LPW>(taddr + (uint32_t)cb, u0);
+          tmem_ld_issue<LPW>(taddr + (uint32_t)(CO + cb), u1);
+          tmem_ld_issue<LPW>(taddr + (uint32_t)(2 * CO + cb), u2);
+          if (C::CONCAT) {  // ... and the same three blocks of a_hi w_lo + a_lo w_hi
+            uint32_t w0[LPW], w1[LPW], w2[LPW];
+            tmem_ld_issue<LPW>(taddr + (uint32_t)(C::NW + cb), w0);
+            tmem_ld_issue<LPW>(taddr + (uint32_t)(C::NW + CO + cb), w1);
+            tmem_ld_issue<LPW>(taddr + (uint32_t)(C::NW + 2 * CO + cb), w2);
+            tmem_ld_wait();
+            tmem_pin<LPW>(u0); tmem_pin<LPW>(u1); tmem_pin<LPW>(u2); tmem_pin<LPW>(w0); tmem_pin<LPW>(w1); tmem_pin<LPW>(w2);
+#pragma unroll
+            for (int j = 0; j < LPW; ++j) {
               const float d0 = __uint_as_float(u0[j]) + __uint_as_float(w0[j]);
               const float d1 = __uint_as_float(u1[j]) + __uint_as_float(w1[j]);
               const float d2 = __uint_as_float(u2[j]) + __uint_as_float(w2[j]);
-              o[j] = __shfl_up_sync(0xffffffffu, d0, 1) + d1 + __shfl_down_sync(0xffffffffu, d2, 1);
+              o[sb * LPW + j] = __shfl_up_sync(0xffffffffu, d0, 1) + d1 + __shfl_down_sync(0xffffffffu, d2, 1);
             }
           } else {
             tmem_ld_wait();
-            tmem_pin<CPW>(u0); tmem_pin<CPW>(u1); tmem_pin<CPW>(u2);
+            tmem_pin<LPW>(u0); tmem_pin<LPW>(u1); tmem_pin<LPW>(u2);
 #pragma unroll
-            for (int j = 0; j < CPW; ++j)
-              o[j] = __shfl_up_sync(0xffffffffu, __uint_as_float(u0[j]), 1) + __uint_as_float(u1[j]) +
-                     __shfl_down_sync(0xffffffffu, __uint_as_float(u2[j]), 1);
+            for (int j = 0; j < LPW; ++j)
+              o[sb * LPW + j] = __shfl_up_sync(0xffffffffu, __uint_as_float(u0[j]), 1) + __uint_as_float(u1[j]) +
+                                __shfl_down_sync(0xffffffffu, __uint_as_float(u2[j]), 1);
           }
         }
 #pragma unroll
@@ -500,8 +513,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           // y partner = the row of the next quadrant's warp: odd quadrants hand their x-pooled values to the even
           // quadrant below them through shared memory (one buffer and one named barrier per (h, quadrant pair);
           // the pair's second barrier keeps the next write behind this read)
-          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + (h * 2 + (quad >> 1)) * (15 * CPW);
-          const int bar_id = 2 + h * 2 + (quad >> 1);
+          const int pool_grp = (C::SETS ? set * 2 + h : h) * 2 + (quad >> 1);  // 0 .. 7
+          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + pool_grp * (15 * CPW);
+          const int bar_id = 2 + pool_grp;
           float m[CPW];
 #pragma unroll
           for (int j = 0; j < CPW; ++j) m[j] = fmaxf(o[j], __shfl_down_sync(0xffffffffu, o[j], 1));
@@ -527,8 +541,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           // pooled row (15 positions) of the even quadrants; the odd ones have nothing to store
           if (p.staged == 0) {
             const int qx = gx >> 1, qy = gy >> 1;
-            if (pool_owner && qx < (p.W >> 1) && qy < (p.H >> 1))
-              store_split_direct<CPW>(p.dst_pool, ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx, p.pool_c_total, p.pool_c_off + cbase, m);
+            if (pool_owner && qx < (p.W >> 1) && qy < (p.H >> 1)) {
+              const size_t ppx = ((size_t)b * (p.H >> 1) + qy) * (p.W >> 1) + qx;
+              if (p.pool_c_off & 15) store_split16(p.dst_pool, ppx, p.pool_c_total, p.pool_c_off + cbase, m, CPW);  // 16-byte stores
+              else store_split_direct<CPW>(p.dst_pool, ppx, p.pool_c_total, p.pool_c_off + cbase, m);
+            }
           } else if (!(quad & 1)) {
             const int Hp = p.H >> 1, Wp = p.W >> 1, qy = gy >> 1, qx0 = tx * (TX / 2);
             staged_store(p.dst_pool, m, owner, pc, TX / 2, p.pool_c_off, p.pool_c_total,
@@ -547,7 +564,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
         if (p.store_nhwc && p.staged == 0) {
-          if (valid) store_split_direct<CPW>(p.dst, ((size_t)b * p.H + gy) * p.W + gx, p.dst_c_total, p.dst_c_off + cbase, o);
+          if (valid) {
+            const size_t opx = ((size_t)b * p.H + gy) * p.W + gx;
+            if (p.dst_c_off & 15) store_split16(p.dst, opx, p.dst_c_total, p.dst_c_off + cbase, o, CPW);  // 16-byte stores
+            else store_split_direct<CPW>(p.dst, opx, p.dst_c_total, p.dst_c_off + cbase, o);
+          }
         } else if (p.store_nhwc)  // this quadrant's image row: 30 positions
           staged_store(p.dst, o, lane >= 1 && lane <= TX, lane - 1, TX, p.dst_c_off, p.dst_c_total,
                        ((size_t)b * p.H + gy) * p.W + tx * TX, p.W - tx * TX, gy < p.H);
@@ -622,7 +643,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty(acc));
-      if (++acc == ACC_STAGES) {
+      if (C::SETS) {
+        aph ^= 1;  // my stage again two tiles later
+      } else if (++acc == ACC_STAGES) {
         acc = 0;
         aph ^= 1;
       }
@@ -847,6 +870,7 @@ static int launch(const Plan& pl, const Params& p, cudaStream_t st) {
       mode = e ? atoi(e) : 0;
     }
     q.staged = mode == 1 ? 1 : (mode == 2 ? 0 : (p.c0_chunks + p.c1_chunks >= 3 ? 1 : 0));
+    if (C::SETS) q.staged = 0;  // two epilogue sets: full-sector stores straight from the registers, no quadrant barriers
   }
   {
     // PixelShuffle outputs: staged full-sector stores (NVS_RS_PS=0: the direct 8-byte stores) when the launch writes
