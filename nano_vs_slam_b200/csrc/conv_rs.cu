@@ -725,7 +725,61 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       ws -= p.w_stages;
       wph ^= 1;
     }
-    for (int tl = 0; tl < my_tiles; ++tl) {
+    // Fast path (the default configuration: one issuer, weights resident): the barrier / election skeleton of the general
+    // loop below costs ~920 cycles per one-chunk tile with NO work in it (knock-outs 2 | 4 | 8, clock64 timeline), more
+    // than the tile's MMAs (~400).  Here a chunk is ONE elected region: all three kernel rows' MMAs and the commits
+    // back to back, no per-row election / __syncwarp, no astart hand-off, the weight barriers waited for once.
+    const bool fast = nis == 1 && w_resident && !(p.knock & 4) && !(p.knock & 256);
+    if (fast) {
+      for (int i = 0; i < w_tiles; ++i) mbar_wait(wfull(i), 0u);
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        mbar_wait(accempty(acc), cph ^ 1u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_COLS);
+        for (int ch = 0; ch < chunks; ++ch) {
+          if (p.dbg && blockIdx.x == 0 && lane == 0 && dbg_i < 256) p.dbg[512 + dbg_i] = clock64();
+          ++dbg_i;
+          mbar_wait(afull(as), aph);
+          tc_fence_after();
+          const int nk = p.pair16 ? 1 : (ch == p.c0_chunks - 1 ? p.nk_last0 : (ch == chunks - 1 ? p.nk_last1 : 2));
+          const uint32_t a_slot = a_lo0 + (uint32_t)as * (uint32_t)(A_BYTES >> 4);
+          const uint32_t w_ch = w_lo0 + (uint32_t)(3 * ch) * (uint32_t)(C::W_STAGE >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t a_hi = a_slot + (uint32_t)ky * (uint32_t)((HX * 64) >> 4), a_lo = a_hi + lo_part;
+              const uint32_t w_hi = w_ch + (uint32_t)ky * (uint32_t)(C::W_STAGE >> 4), w_lo = w_hi + (uint32_t)(C::W_HALF >> 4);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (k < nk) {
+                  const uint32_t o = 2u * k;  // 16 fp16 = 32 bytes along K = +2 in the (address >> 4) field
+                  const uint32_t accum = (ch | ky | k) != 0 ? 1u : 0u;
+                  if (C::CONCAT) {
+                    tc_mma_f16(d_tmem, desc(a_hi + o), desc(w_hi + o), C::idesc(2 * C::NW), accum);  // x [W_hi ; W_lo]
+                    tc_mma_f16(d_tmem + (uint32_t)C::NW, desc(a_lo + o), desc(w_hi + o), C::idesc(C::NW), 1u);
+                  } else {
+                    tc_mma_f16(d_tmem, desc(a_hi + o), desc(w_hi + o), C::idesc(C::NW), accum);
+                    tc_mma_f16(d_tmem, desc(a_hi + o), desc(w_lo + o), C::idesc(C::NW), 1u);
+                    tc_mma_f16(d_tmem, desc(a_lo + o), desc(w_hi + o), C::idesc(C::NW), 1u);
+                  }
+                }
+              }
+            }
+            tc_commit(aempty(as));
+            if (ch == chunks - 1) tc_commit(accfull(acc));
+          }
+          __syncwarp();
+          if (++as == NA) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        if (++acc == ACC_STAGES) {
+          acc = 0;
+          cph ^= 1;
+        }
+      }
+    }
+    for (int tl = fast ? my_tiles : 0; tl < my_tiles; ++tl) {
       mbar_wait(accempty(acc), cph ^ 1u);
       if (me != 0) mbar_wait(astart(acc), cph);
       tc_fence_after();
