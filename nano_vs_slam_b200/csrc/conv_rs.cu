@@ -82,7 +82,8 @@ struct Cfg {
   static constexpr int SM_STG = 0;
   static constexpr int SM_BIAS = SM_STG + STG_BYTES;
   static constexpr int SM_POOL = SM_BIAS + CO * 4;
-  static constexpr int POOL_BYTES = (EPI_WARPS / 4) * 2 * 15 * CPW * 4;  // max-pool exchange: (channel group, quadrant pair) x 15 x CPW
+  // max-pool exchange: (set, channel group, quadrant pair) x 15 x CPW; SETS: double buffered (one barrier per tile)
+  static constexpr int POOL_BYTES = (SETS ? 2 : 1) * (EPI_WARPS / 4) * 2 * 15 * CPW * 4;
   static constexpr int SM_BAR = SM_POOL + POOL_BYTES;
   static constexpr int MAX_WS = 16;                  // barrier slots reserved for the weight ring
   static constexpr int N_BARS = 2 * NA_MAX + 2 * MAX_WS + 6 + 1;
@@ -440,6 +441,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool valid = lane >= 1 && lane <= TX && gx < p.W && gy < p.H;
       mbar_wait(accfull(acc), aph);
       tc_fence_after();
+      bool released = false;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int part = 0; part < ((p.knock & 2) ? 0 : 1); ++part) {
@@ -479,6 +481,15 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                                 __shfl_down_sync(0xffffffffu, __uint_as_float(u2[j]), 1);
           }
         }
+        // the accumulator is in registers: hand the stage back to the MMA role before the activation / pooling / stores.
+        // Only for tiles with little MMA work (same-box A/B, call 64: conv1b -7 %, 64 -> 64 -4 %, but the three-chunk
+        // 96 -> 64 layers and the staged PixelShuffle layers +3..5 % -- there the epilogue runs better undisturbed)
+        if (chunks <= 2 && !p.ps_staged) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accempty(acc));
+          released = true;
+        }
 #pragma unroll
         for (int j = 0; j < CPW; ++j) {
           const float a = fmaf(o[j], p.w_scale, bias_s[cbase + j]);
@@ -514,7 +525,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           // quadrant below them through shared memory (one buffer and one named barrier per (h, quadrant pair);
           // the pair's second barrier keeps the next write behind this read)
           const int pool_grp = (C::SETS ? set * 2 + h : h) * 2 + (quad >> 1);  // 0 .. 7
-          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + pool_grp * (15 * CPW);
+          float* ps = reinterpret_cast<float*>(sm + C::SM_POOL) + (pool_grp + (C::SETS ? 8 * (int)(aph & 1u) : 0)) * (15 * CPW);
           const int bar_id = 2 + pool_grp;
           float m[CPW];
 #pragma unroll
@@ -551,7 +562,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             staged_store(p.dst_pool, m, owner, pc, TX / 2, p.pool_c_off, p.pool_c_total,
                          ((size_t)b * Hp + qy) * Wp + qx0, Wp - qx0, qy < Hp);
           }
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          // (SETS: the exchange buffer alternates per tile; the next tile's first barrier orders its reuse)
+          if (!C::SETS) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         }
         if (valid && p.dst_mode == 1) {
           if (p.dst_layout == 0) {  // channels-last, split format: through the staging buffer (below)
@@ -640,9 +652,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(accempty(acc));
+      if (!released) {  // (warps with no channels to load in this launch)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty(acc));
+      }
       if (C::SETS) {
         aph ^= 1;  // my stage again two tiles later
       } else if (++acc == ACC_STAGES) {
