@@ -400,17 +400,52 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(ConvP p) {
   const unsigned char* src8 = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)b * p.H * p.W * 3;
   const bool u8 = p.in_mode == NVS_IN_U8_HWC;
   const bool unit = p.in_mode == NVS_IN_UNIT;  // fp32 frames in [0,1]: x.sub(0.5).mul(2.0) of frontend.py:79 on load
-  for (int i = threadIdx.x; i < 3 * (STEM_TY + 2) * (STEM_TX + 2); i += 128) {
-    const int c = i / ((STEM_TY + 2) * (STEM_TX + 2)), r = i - c * (STEM_TY + 2) * (STEM_TX + 2);
-    const int yy = r / (STEM_TX + 2), xx = r - yy * (STEM_TX + 2);
-    const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-    float v = 0.f;
-    if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-      if (u8) v = __fmul_rn(__fsub_rn(__fdiv_rn((float)src8[((size_t)gy * p.W + gx) * 3 + c], 255.f), 0.5f), 2.f);
-      else v = src[((size_t)c * p.H + gy) * p.W + gx];
-      if (unit) v = __fmul_rn(__fsub_rn(v, 0.5f), 2.f);
+  // Input window: ALL of a thread's global loads are issued before the first one is consumed (two fully unrolled
+  // loops).  As one load-convert-store loop every iteration exposed a full global-load latency: ncu's source counters put
+  // 66 % of the kernel's stall samples in this prologue and 16 % in the FFMA2 loop.
+  {
+    constexpr int WIN = (STEM_TY + 2) * (STEM_TX + 2), TOT = 3 * WIN, NLD = (TOT + 127) / 128;
+    float v[NLD];
+    int so[NLD];  // float2 offset inside `tile`, -1 = nothing to store
+    // branch-free: clamped (always valid) addresses, the padding decision is kept in so[]; the uniform input-mode branch
+    // sits outside the loops, so the sixteen loads of a thread issue back to back
+    size_t ga[NLD];
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+      const int i = threadIdx.x + j * 128;
+      const int c0 = i / WIN, r = i - c0 * WIN;
+      const int c = c0 < 3 ? c0 : 2;
+      const int yy = r / (STEM_TX + 2), xx = r - yy * (STEM_TX + 2);
+      const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+      const bool live = i < TOT;
+      const bool inside = live && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+      const int o = (c * (STEM_TY + 2) + yy) * (STEM_TX + 4) + xx;
+      so[j] = !live ? -1 : (inside ? o : -2 - o);  // -2 - o: zero padding, stored as 0 without the input conversion
+      const int cy = min(max(gy, 0), p.H - 1), cx = min(max(gx, 0), p.W - 1);
+      ga[j] = u8 ? ((size_t)cy * p.W + cx) * 3 + c : ((size_t)c * p.H + cy) * p.W + cx;
     }
-    tile[c][yy][xx] = make_float2(v, v);
+    if (u8) {
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) v[j] = (float)__ldg(src8 + ga[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) v[j] = __ldg(src + ga[j]);
+    }
+    float2* tl = &tile[0][0][0];
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+      if (so[j] == -1) continue;
+      float w = v[j];
+      int o = so[j];
+      if (o >= 0) {
+        if (u8) w = __fmul_rn(__fsub_rn(__fdiv_rn(w, 255.f), 0.5f), 2.f);
+        if (unit) w = __fmul_rn(__fsub_rn(w, 0.5f), 2.f);
+      } else {
+        o = -2 - o;
+        w = 0.f;
+      }
+      tl[o] = make_float2(w, w);
+    }
   }
   for (int i = threadIdx.x; i < 27 * STEM_CO; i += 128) {
     const int k = i / STEM_CO, co = i - k * STEM_CO;  // k = ci * 9 + tap; packed weights are [cin_pad][9][cout_pad]
