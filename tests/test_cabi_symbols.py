@@ -39,7 +39,7 @@ def test_pure_host_entry_points():
     assert lib.nvs_conv_cin_chunk(3) == 4 and lib.nvs_conv_cin_chunk(96) == 8
     assert lib.nvs_flat_padded_dim(4096) == 4096 and lib.nvs_flat_padded_dim(100) == 128
     assert lib.nvs_flat_search_workspace_bytes(125000, 10000, 4096, 25) > 0
-    assert lib.nvs_netvlad_workspace_bytes(256, 64, 64, 4800) == 4 * 256 * 2 * (64 * 64 + 64)
+    assert lib.nvs_netvlad_workspace_bytes(256, 64, 64, 4800) == 4 * 256 * 5 * (64 * 64 + 64)  # 5 slices per frame
     # without a GPU the device probe must say so (and never crash)
     import torch
     if not torch.cuda.is_available():
