@@ -768,6 +768,31 @@ __device__ __forceinline__ uint32_t ord_key(float f) {  // unsigned order == flo
 __device__ __forceinline__ float ord_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
+// One digit of the radix selects below, 256 threads, hist[tid] = occupancy of bin tid: the bin in which the cumulative
+// count reaches *s_remaining (parallel prefix sum; a lone thread scanning the 256 bins cost ~7 000 cycles per digit) goes
+// into *s_prefix at `shift`, the rank inside that bin into *s_remaining.  Ends with a __syncthreads.
+__device__ __forceinline__ void radix_pick_digit(const int* hist, int* s_wsum, uint32_t* s_prefix, int* s_remaining, int shift) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = hist[tid], rem = *s_remaining;
+  const uint32_t prefix = *s_prefix;
+  int inc = h;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_wsum[w];
+  const int cum_incl = base + inc, cum_excl = cum_incl - h;
+  // (tid 255 also takes a rank beyond the total: the serial form stopped at the last bin)
+  if ((cum_excl < rem && rem <= cum_incl) || (tid == 255 && rem > cum_incl)) {
+    *s_remaining = rem - cum_excl;
+    *s_prefix = prefix | ((uint32_t)tid << shift);
+  }
+  __syncthreads();
+}
 
 // Per query: tau~ = exact k-th smallest s~ over the n_strips * L listed rows (radix select on the ordered bit
 // pattern), candidates = every listed row with s~ <= tau~ + 2 eps, flag = the lists may be missing a row that also
@@ -792,6 +817,7 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __r
   float* sd = reinterpret_cast<float*>(sraw);
   int32_t* si = reinterpret_cast<int32_t*>(sraw) + n_cand;
   __shared__ int hist[256];
+  __shared__ int s_wsum[8];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining, s_valid, s_cnt, s_flag;
   const int q = blockIdx.x, tid = threadIdx.x;
@@ -822,13 +848,7 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(const float* __r
         if ((key & mask) == (prefix & mask)) atomicAdd(&hist[(key >> shift) & 255u], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int rem = s_remaining, b = 0;
-        while (b < 255 && hist[b] < rem) rem -= hist[b++];
-        s_remaining = rem;
-        s_prefix = prefix | ((uint32_t)b << shift);
-      }
-      __syncthreads();
+      radix_pick_digit(hist, s_wsum, &s_prefix, &s_remaining, shift);
     }
     T = ord_float(s_prefix) + qslack[q];
   }
@@ -877,6 +897,7 @@ __global__ void __launch_bounds__(256) kth_union_kernel(const float* __restrict_
                                                         float* __restrict__ out_b) {
   extern __shared__ float su[];
   __shared__ int hist[256];
+  __shared__ int s_wsum[8];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining;
   const int q = blockIdx.x, tid = threadIdx.x, n = parts * k;
@@ -893,13 +914,7 @@ __global__ void __launch_bounds__(256) kth_union_kernel(const float* __restrict_
       if ((key & mask) == (prefix & mask)) atomicAdd(&hist[(key >> shift) & 255u], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int rem = s_remaining, b = 0;
-      while (b < 255 && hist[b] < rem) rem -= hist[b++];
-      s_remaining = rem;
-      s_prefix = prefix | ((uint32_t)b << shift);
-    }
-    __syncthreads();
+    radix_pick_digit(hist, s_wsum, &s_prefix, &s_remaining, shift);
   }
   if (tid == 0) out_b[q] = ord_float(s_prefix);
 }
