@@ -13,19 +13,23 @@
 //           which, with the fp32 accumulation of the tensor core and of the re-rank bounded generously, gives a
 //           per-query eps with |s~ - s| <= eps for every row, s = |x|^2 - 2 q.x.  If tau~ is ANY upper bound of the
 //           k-th smallest s~, every row of the true top-k has s~ <= tau~ + 2 eps.  So:
-//   GEMM    warp-specialised tcgen05 kernel (TMA SWIZZLE_128B -> smem ring -> tcgen05.mma kind::f16 128x256x16 ->
-//           2 x 256-column TMEM accumulators; CTA pairs share every database tile by TMA multicast).  The epilogue
-//           keeps, per query row and database strip, the L >= k smallest s~ that are <= (published bound + 2 eps)
-//           in shared memory; a finished strip publishes its k-th smallest (an upper bound of tau~).
-//   select  per query: exact k-th smallest s~ over all strips by radix select = tau~; candidates = everything with
+//   GEMM    warp-specialised tcgen05 kernel (TMA SWIZZLE_128B -> smem ring -> tcgen05.mma kind::f16 -> 2 x 256-column
+//           TMEM accumulators).  Clusters of 8 / 4 / 2 CTAs work on the same 256-row database tile, every CTA on its own
+//           128-query block; each loads a slice of the tile for all (TMA multicast); CTA pairs issue ONE M = 256
+//           cta_group::2 MMA over both query blocks.  A cluster owns one contiguous range of (query group, tile) steps;
+//           the part of it inside one query group is a SEGMENT.  The epilogue keeps, per query row and segment, the
+//           L >= k smallest s~ that are <= (published bound + 2 eps) in shared memory (append + warp-cooperative
+//           compaction); every compaction and every finished segment publish the k-th smallest so far (an upper
+//           bound of tau~).
+//   select  per query: exact k-th smallest s~ over all segment lists by radix select = tau~; candidates = everything with
 //           s~ <= tau~ + 2 eps (as many as the data puts there, not a constant).  A query is FLAGGED when the proof
-//           has a hole: a strip list that is full with all entries inside the slack (it may have dropped a row), or
+//           has a hole: a segment list that is full with all entries inside the slack (it may have dropped a row), or
 //           more candidates than the re-rank buffer holds.
 //   rerank  exact fp32 distances of the candidates, k smallest by (distance, id).
 //   scan    flagged queries only (normally none): exact fp32 distances against EVERY row, merged into the result
 //           under a per-query lock.  Slow, never wrong: dense near-ties or duplicate rows cost time, not exactness.
 //
-// The answer therefore does not depend on how the strips were scheduled, and equals an fp32 IndexFlatL2 wherever the
+// The answer therefore does not depend on how the work was scheduled, and equals an fp32 IndexFlatL2 wherever the
 // fp32 distances themselves are distinct.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -523,6 +527,7 @@ flat_l2_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       while (W * (c0 + 1) / n_clusters <= g0) ++c0;
       while (W * c0 / n_clusters > g0) --c0;
       const int slot = cluster_id - c0;
+      if (slot < 0 || slot >= p.n_slots) __trap();  // (the host sized the slots for the shortest possible range)
       int cnt = 0;           // entries in my buffer
       float thr = INFINITY;  // L-th smallest at the last compaction: +inf before the first
       const int qrow = mblk * BM + row;
