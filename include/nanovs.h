@@ -319,6 +319,9 @@ int nvs_pose_batch_adaptive(const float* pts, int32_t n_frames, int32_t kmax, co
  *         allgather per search. */
 int32_t nvs_flat_padded_dim(int32_t d);
 int32_t nvs_flat_max_k(void);
+/* host-only: number of per-query list slots (= most clusters that can share one group of query blocks) and, through
+ * *cluster_size (may be NULL), the CTAs per cluster a search of this shape uses; 0 for invalid arguments */
+int32_t nvs_flat_list_slots(int64_t n_db, int32_t nq, int32_t d, int32_t k, int32_t* cluster_size);
 /* debugging aid (tools/retr_waits.py): every following GEMM launch writes 16 int64 per CTA into dev_buf (device memory,
  * 16 x 148 entries) -- cycles of the MMA role, producer wait, MMA wait for operands, MMA wait for a drained accumulator,
  * epilogue wait, epilogue cycles, k-blocks issued, unused; NULL switches it off */

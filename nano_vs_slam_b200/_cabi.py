@@ -93,6 +93,7 @@ SIGNATURES = {
                                         _u64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nvs_flat_padded_dim": (_i32, [_i32]),
     "nvs_flat_max_k": (_i32, []),
+    "nvs_flat_list_slots": (_i32, [C.c_int64, _i32, _i32, _i32, _vp]),
     "nvs_flat_prepare": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "nvs_flat_search_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "nvs_flat_search": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _vp, _vp,

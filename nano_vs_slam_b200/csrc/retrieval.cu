@@ -1327,6 +1327,15 @@ extern "C" int nvs_flat_prepare(const float* x, int64_t n, int32_t d, void* x_f1
 
 extern "C" int32_t nvs_flat_max_k(void) { return KMAX; }
 
+// host-only: list slots per query and cluster size the search of this shape will use (tests check the work split
+// against them; without a device the layout is sized for the 148 SMs of a B200)
+extern "C" int32_t nvs_flat_list_slots(int64_t n_db, int32_t nq, int32_t d, int32_t k, int32_t* cluster_size) {
+  if (n_db <= 0 || nq <= 0 || d <= 0 || k <= 0 || k > KMAX) return 0;
+  const Layout L = make_layout(n_db, nq, d, k);
+  if (cluster_size) *cluster_size = L.cs;
+  return L.n_strips;
+}
+
 // debugging aid (tools/retr_waits.py): 16 int64 per CTA written by every following GEMM launch -- MMA-role cycles, producer
 // wait, MMA wait for operands, MMA wait for an accumulator, epilogue wait, epilogue cycles, k-blocks, unused
 extern "C" void nvs_flat_debug_buffer(long long* dev_buf) { nvs::rt::g_dbg = dev_buf; }

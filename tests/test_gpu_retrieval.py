@@ -293,3 +293,49 @@ def test_pipelined_sharded_search_matches_single_index(tmp_path, monkeypatch):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_work_split_fits_the_list_slots():
+    """Host logic of the retrieval GEMM's work split (no GPU): the (query group, tile) steps are cut into one contiguous
+    range per cluster, and the segment of a cluster inside one query group writes its lists to slot
+    (cluster - first cluster of the group).  For every shape and every possible number of resident clusters that slot
+    must stay below the slot count the C layout (nvs_flat_list_slots) sizes the candidate arrays for."""
+    import ctypes
+    import random
+
+    from nano_vs_slam_b200 import _cabi
+
+    lib = _cabi.lib()
+
+    def kernel_slots(n_mgrp, n_tiles, ncl):  # restates the epilogue's segment walk (retrieval.cu)
+        W, mx = n_mgrp * n_tiles, 0
+        for c in range(ncl):
+            w, we = W * c // ncl, W * (c + 1) // ncl
+            while w < we:
+                grp = w // n_tiles
+                tb = w - grp * n_tiles
+                te = min(n_tiles, tb + (we - w))
+                w += te - tb
+                g0 = grp * n_tiles
+                c0 = g0 * ncl // W
+                while W * (c0 + 1) // ncl <= g0:
+                    c0 += 1
+                while W * c0 // ncl > g0:
+                    c0 -= 1
+                assert c >= c0
+                mx = max(mx, c - c0)
+        return mx + 1
+
+    rng = random.Random(3)
+    shapes = [(1_000_000, 10_000), (125_000, 10_000), (300, 1), (256, 128), (257, 129), (70_000, 900), (5_000, 3_000)]
+    shapes += [(rng.randint(1, 400_000), rng.randint(1, 6_000)) for _ in range(40)]
+    for n_db, nq in shapes:
+        cs = ctypes.c_int32(0)
+        slots = lib.nvs_flat_list_slots(n_db, nq, 4096, 25, ctypes.byref(cs))
+        assert slots >= 1 and cs.value in (2, 4, 8), (n_db, nq, slots, cs.value)
+        n_tiles, n_mblk = -(-n_db // 256), -(-nq // 128)
+        n_mgrp = -(-n_mblk // cs.value)
+        most = min(148 // cs.value, n_mgrp * n_tiles)
+        for ncl in sorted({1, 2, most // 2 or 1, max(1, most - 1), most}):
+            assert kernel_slots(n_mgrp, n_tiles, ncl) <= slots, (n_db, nq, cs.value, ncl, slots)
+    assert lib.nvs_flat_list_slots(0, 1, 4096, 25, None) == 0
